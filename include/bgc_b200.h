@@ -40,6 +40,8 @@
 #ifndef BGC_B200_H
 #define BGC_B200_H
 
+#include <stddef.h>
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -327,6 +329,7 @@ int macros_source_sink(bgc_ctx *ctx, const MacrosInput *in, MacrosOutput *out,
 /* Inventory: device vector accumulated by the *_source_sink calls since the
  * last bgc_inventory_reset.  bgc_inventory_get copies this rank's vector to the
  * host; bgc_inventory_device_ptr exposes it for a caller-side collective. */
+int bgc_inventory_enable(bgc_ctx *ctx, int enable);   /* default: disabled (no extra pass) */
 int bgc_inventory_reset(bgc_ctx *ctx);
 int bgc_inventory_get(bgc_ctx *ctx, double out[BGC_INVENTORY_LEN]);
 int bgc_inventory_device_ptr(bgc_ctx *ctx, double **dev_ptr);
@@ -337,6 +340,14 @@ int bgc_inventory_device_ptr(bgc_ctx *ctx, double **dev_ptr);
 int bgc_comm_unique_id(unsigned char id[128]);
 int bgc_comm_init_rank(bgc_ctx *ctx, int nranks, int rank, const unsigned char id[128]);
 int bgc_inventory_allreduce(bgc_ctx *ctx, double out[BGC_INVENTORY_LEN]);
+
+/* Page-locked host memory for the HOST_FORTRAN path: arrays allocated here (or
+ * registered with bgc_host_register) move over PCIe/NVLink-C2C by DMA at full
+ * speed; ordinary pageable arrays work too, through the driver's bounce buffer. */
+int bgc_host_alloc(void **ptr, size_t bytes);
+int bgc_host_free(void *ptr);
+int bgc_host_register(void *ptr, size_t bytes);
+int bgc_host_unregister(void *ptr);
 
 /* Layout helpers (device kernels, stream-ordered): Fortran (k,col,n) <-> SoA. */
 int bgc_layout_to_soa(bgc_ctx *ctx, const double *dev_fortran, double *dev_soa,

@@ -1,0 +1,898 @@
+// bgc_capi.cu — the C ABI of include/bgc_b200.h: context, parameter upload,
+// the two memory spaces (host Fortran layout / device SoA) and the launches.
+//
+// There is NO CPU fallback anywhere in this file: without a CUDA device every
+// compute entry point fails with BGC_ERR_NO_DEVICE / BGC_ERR_CUDA.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "bgc_b200.h"
+#include "bgc_kernels.cuh"
+
+namespace bgc {
+cudaError_t upload_bgc_tables_eco(const BgcTables &t, cudaStream_t s);
+cudaError_t upload_bgc_tables_co3(const BgcTables &t, cudaStream_t s);
+}
+
+// ------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CU(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess)                                                                    \
+      return fail(BGC_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+#define RC(call) do { int rc_ = (call); if (rc_ != BGC_OK) return rc_; } while (0)
+
+extern "C" const char *bgc_last_error(void) { return g_err; }
+extern "C" const char *bgc_version(void) { return "ocean-bgc_b200 0.1 (sm_100a)"; }
+
+// ------------------------------------------------------------------ minimal NCCL binding (dlopen)
+// Only ncclGetUniqueId / ncclCommInitRank / ncclAllReduce / ncclCommDestroy are
+// needed, for one 64-element FP64 sum per step; binding them at run time keeps
+// the library loadable on machines without NCCL.
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId_;
+struct NcclApi {
+  void *h = nullptr;
+  int (*GetUniqueId)(ncclUniqueId_ *) = nullptr;
+  int (*CommInitRank)(ncclComm_t *, int, ncclUniqueId_, int) = nullptr;
+  int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*CommDestroy)(ncclComm_t) = nullptr;
+  const char *(*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+static int nccl_load() {
+  if (g_nccl.h) return BGC_OK;
+  const char *names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char *n : names) {
+    g_nccl.h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (g_nccl.h) break;
+  }
+  if (!g_nccl.h) return fail(BGC_ERR_NCCL, "cannot dlopen libnccl.so.2: %s", dlerror());
+  g_nccl.GetUniqueId = (int (*)(ncclUniqueId_ *))dlsym(g_nccl.h, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (int (*)(ncclComm_t *, int, ncclUniqueId_, int))dlsym(g_nccl.h, "ncclCommInitRank");
+  g_nccl.AllReduce = (int (*)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(g_nccl.h, "ncclAllReduce");
+  g_nccl.CommDestroy = (int (*)(ncclComm_t))dlsym(g_nccl.h, "ncclCommDestroy");
+  g_nccl.GetErrorString = (const char *(*)(int))dlsym(g_nccl.h, "ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy)
+    return fail(BGC_ERR_NCCL, "libnccl is missing required symbols");
+  return BGC_OK;
+}
+#define NC(call)                                                                         \
+  do {                                                                                   \
+    int r_ = (call);                                                                     \
+    if (r_ != 0)                                                                         \
+      return fail(BGC_ERR_NCCL, "%s failed: %s", #call,                                  \
+                  g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "nccl error");     \
+  } while (0)
+enum { kNcclFloat64 = 8, kNcclSum = 0 };
+
+// ------------------------------------------------------------------ context
+struct DevBuf { void *p = nullptr; size_t bytes = 0; };
+
+struct bgc_ctx {
+  int device = 0;
+  int nL = 0, nC = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  bgc::BgcTables bgc_tab;
+  bgc::DmsTables dms_tab;
+  bgc::MacrosTables macros_tab;
+  bool have_bgc = false, have_dms = false, have_macros = false;
+  unsigned long long *d_status = nullptr;   // 4 counters
+  double *d_inventory = nullptr;            // BGC_INVENTORY_LEN
+  double *d_inv_tmp = nullptr;              // 64
+  double *d_partials = nullptr;             // inventory stage-1 partials
+  const double **d_colptrs = nullptr;       // 8 pointers for the Jint sums
+  bool inventory_on = false;
+  std::map<std::string, DevBuf> arena;      // persistent device buffers (host-layout mode, scratch)
+  ncclComm_t comm = nullptr;
+  int nranks = 1;
+};
+
+// Which ctx's tables currently sit in each device's __constant__ memory.
+static std::map<int, std::pair<const bgc_ctx *, unsigned long long>> g_const_owner_bgc, g_const_owner_dms,
+    g_const_owner_macros;
+static unsigned long long g_version_counter = 1;
+static std::mutex g_mu;   // guards the maps below and g_version_counter
+struct CtxVersions { unsigned long long bgc = 0, dms = 0, macros = 0; };
+static std::map<const bgc_ctx *, CtxVersions> g_versions;
+
+static int use_device(bgc_ctx *c) {
+  if (!c) return fail(BGC_ERR_ARG, "null ctx");
+  CU(cudaSetDevice(c->device));
+  return BGC_OK;
+}
+
+static int arena_get(bgc_ctx *c, const std::string &key, size_t bytes, void **out) {
+  DevBuf &b = c->arena[key];
+  if (b.bytes < bytes) {
+    if (b.p) CU(cudaFree(b.p));
+    b.p = nullptr; b.bytes = 0;
+    CU(cudaMalloc(&b.p, bytes ? bytes : 8));
+    b.bytes = bytes;
+  }
+  *out = b.p;
+  return BGC_OK;
+}
+static int arena_d(bgc_ctx *c, const std::string &key, size_t n, double **out) {
+  void *p = nullptr;
+  RC(arena_get(c, key, n * sizeof(double), &p));
+  *out = (double *)p;
+  return BGC_OK;
+}
+
+extern "C" int bgc_ctx_create(int device, int nLevelsMax, int nColumnsMax, bgc_ctx **out) {
+  if (!out || nLevelsMax < 1 || nColumnsMax < 1) return fail(BGC_ERR_ARG, "bgc_ctx_create: bad arguments");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev < 1)
+    return fail(BGC_ERR_NO_DEVICE, "no CUDA device (%s); this library has no CPU fallback",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+  if (device < 0 || device >= ndev) return fail(BGC_ERR_ARG, "device %d out of range [0,%d)", device, ndev);
+  CU(cudaSetDevice(device));
+  bgc_ctx *c = new bgc_ctx();
+  c->device = device;
+  c->nL = nLevelsMax;
+  c->nC = nColumnsMax;
+  CU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+  c->stream = c->own_stream;
+  CU(cudaMalloc(&c->d_status, 4 * sizeof(unsigned long long)));
+  CU(cudaMemset(c->d_status, 0, 4 * sizeof(unsigned long long)));
+  CU(cudaMalloc(&c->d_inventory, BGC_INVENTORY_LEN * sizeof(double)));
+  CU(cudaMemset(c->d_inventory, 0, BGC_INVENTORY_LEN * sizeof(double)));
+  CU(cudaMalloc(&c->d_inv_tmp, 64 * sizeof(double)));
+  CU(cudaMalloc(&c->d_partials, (size_t)bgc::inventory_grid(nColumnsMax) * 40 * sizeof(double)));
+  CU(cudaMalloc(&c->d_colptrs, 8 * sizeof(double *)));
+  { std::lock_guard<std::mutex> lock(g_mu); g_versions[c] = CtxVersions(); }
+  *out = c;
+  return BGC_OK;
+}
+
+extern "C" int bgc_ctx_destroy(bgc_ctx *c) {
+  if (!c) return BGC_OK;
+  cudaSetDevice(c->device);
+  if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+  cudaStreamSynchronize(c->stream);
+  for (auto &kv : c->arena) if (kv.second.p) cudaFree(kv.second.p);
+  cudaFree(c->d_status); cudaFree(c->d_inventory); cudaFree(c->d_inv_tmp); cudaFree(c->d_partials);
+  cudaFree((void *)c->d_colptrs);
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  std::lock_guard<std::mutex> lock(g_mu);
+  g_versions.erase(c);
+  for (auto *m : {&g_const_owner_bgc, &g_const_owner_dms, &g_const_owner_macros}) {
+    auto it = m->find(c->device);
+    if (it != m->end() && it->second.first == c) m->erase(it);
+  }
+  delete c;
+  return BGC_OK;
+}
+
+extern "C" int bgc_ctx_set_stream(bgc_ctx *c, void *cuda_stream) {
+  if (!c) return fail(BGC_ERR_ARG, "null ctx");
+  c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+  return BGC_OK;
+}
+
+extern "C" int bgc_ctx_synchronize(bgc_ctx *c) {
+  RC(use_device(c));
+  CU(cudaStreamSynchronize(c->stream));
+  return BGC_OK;
+}
+
+extern "C" int bgc_get_status(bgc_ctx *c, BgcStatus *out, int reset) {
+  RC(use_device(c));
+  if (!out) return fail(BGC_ERR_ARG, "null out");
+  unsigned long long h[4];
+  CU(cudaMemcpyAsync(h, c->d_status, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+  if (reset) CU(cudaMemsetAsync(c->d_status, 0, sizeof h, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  out->no_bracket = h[0]; out->no_convergence = h[1]; out->poc_error = h[2]; out->nonfinite = h[3];
+  return BGC_OK;
+}
+
+// ------------------------------------------------------------------ parameters
+static bool index_ok(int v, int n) { return v >= 1 && v <= n; }
+
+extern "C" int bgc_set_params(bgc_ctx *c, const BgcParams *p, const BgcAutotroph a[BGC_AUTOTROPH_CNT],
+                              const BgcIndices *ind) {
+  if (!c || !p || !a || !ind) return fail(BGC_ERR_ARG, "bgc_set_params: null argument");
+  // every tracer slot must be written exactly once: the 16 plain tracers plus
+  // the autotroph slots have to form a permutation of 1..30
+  int seen[BGC_TRACER_CNT + 1] = {0};
+  const int plain[16] = {ind->po4_ind, ind->no3_ind, ind->sio3_ind, ind->nh4_ind, ind->fe_ind, ind->o2_ind,
+                         ind->dic_ind, ind->dic_alt_co2_ind, ind->alk_ind, ind->doc_ind, ind->don_ind,
+                         ind->dofe_ind, ind->dop_ind, ind->dopr_ind, ind->donr_ind, ind->zooC_ind};
+  int count = 0;
+  for (int v : plain) {
+    if (!index_ok(v, BGC_TRACER_CNT) || seen[v]++) return fail(BGC_ERR_ARG, "bgc_set_params: bad/duplicate tracer index %d", v);
+    ++count;
+  }
+  for (int g = 0; g < BGC_AUTOTROPH_CNT; ++g) {
+    const int req[3] = {a[g].Chl_ind, a[g].C_ind, a[g].Fe_ind};
+    for (int v : req) {
+      if (!index_ok(v, BGC_TRACER_CNT) || seen[v]++)
+        return fail(BGC_ERR_ARG, "bgc_set_params: autotroph %d has bad/duplicate tracer index %d (call bgc_init first)", g + 1, v);
+      ++count;
+    }
+    const int opt[2] = {a[g].Si_ind, a[g].CaCO3_ind};
+    for (int v : opt) {
+      if (v == 0) continue;
+      if (!index_ok(v, BGC_TRACER_CNT) || seen[v]++)
+        return fail(BGC_ERR_ARG, "bgc_set_params: autotroph %d has bad/duplicate optional tracer index %d", g + 1, v);
+      ++count;
+    }
+    if (!index_ok(a[g].grazee_ind, BGC_AUTOTROPH_CNT)) return fail(BGC_ERR_ARG, "bgc_set_params: bad grazee_ind");
+  }
+  if (count != BGC_TRACER_CNT)
+    return fail(BGC_ERR_ARG, "bgc_set_params: tracer indices cover %d of %d slots", count, BGC_TRACER_CNT);
+  if (!index_ok(ind->diat_ind, BGC_AUTOTROPH_CNT)) return fail(BGC_ERR_ARG, "bgc_set_params: bad diat_ind");
+
+  c->bgc_tab.p = *p;
+  for (int g = 0; g < BGC_AUTOTROPH_CNT; ++g) c->bgc_tab.a[g] = a[g];
+  c->bgc_tab.ind = *ind;
+  for (int i = 0; i < BGC_AUTOTROPH_CNT; ++i)
+    for (int j = 0; j < BGC_AUTOTROPH_CNT; ++j)
+      c->bgc_tab.same_grazee[i][j] = (a[j].grazee_ind == a[i].grazee_ind) ? 1 : 0;
+  c->have_bgc = true;
+  { std::lock_guard<std::mutex> lock(g_mu); g_versions[c].bgc = g_version_counter++; }
+  return BGC_OK;
+}
+
+extern "C" int dms_set_params(bgc_ctx *c, const DmsParams *p, const DmsIndices *ind) {
+  if (!c || !p || !ind) return fail(BGC_ERR_ARG, "dms_set_params: null argument");
+  const int *v = &ind->dms_ind;
+  int seen[DMS_TRACER_CNT + 1] = {0};
+  for (int i = 0; i < DMS_TRACER_CNT; ++i)
+    if (!index_ok(v[i], DMS_TRACER_CNT) || seen[v[i]]++) return fail(BGC_ERR_ARG, "dms_set_params: bad/duplicate tracer index %d", v[i]);
+  c->dms_tab.p = *p;
+  c->dms_tab.ind = *ind;
+  c->have_dms = true;
+  { std::lock_guard<std::mutex> lock(g_mu); g_versions[c].dms = g_version_counter++; }
+  return BGC_OK;
+}
+
+extern "C" int macros_set_params(bgc_ctx *c, const MacrosParams *p, const MacrosIndices *ind) {
+  if (!c || !p || !ind) return fail(BGC_ERR_ARG, "macros_set_params: null argument");
+  const int *v = &ind->prot_ind;
+  int seen[MACROS_TRACER_CNT + 1] = {0};
+  for (int i = 0; i < MACROS_TRACER_CNT; ++i)
+    if (!index_ok(v[i], MACROS_TRACER_CNT) || seen[v[i]]++) return fail(BGC_ERR_ARG, "macros_set_params: bad/duplicate tracer index %d", v[i]);
+  c->macros_tab.p = *p;
+  c->macros_tab.ind = *ind;
+  c->have_macros = true;
+  { std::lock_guard<std::mutex> lock(g_mu); g_versions[c].macros = g_version_counter++; }
+  return BGC_OK;
+}
+
+// __constant__ memory is one copy per device: re-upload only when another ctx
+// (or a newer *_set_params) owns what is there now.
+static int ensure_bgc_tables(bgc_ctx *c) {
+  std::lock_guard<std::mutex> lock(g_mu);
+  if (!c->have_bgc) return fail(BGC_ERR_PARAMS, "bgc_set_params has not been called on this ctx");
+  auto &own = g_const_owner_bgc[c->device];
+  const unsigned long long v = g_versions[c].bgc;
+  if (own.first != c || own.second != v) {
+    CU(bgc::upload_bgc_tables_eco(c->bgc_tab, c->stream));
+    CU(bgc::upload_bgc_tables_co3(c->bgc_tab, c->stream));
+    own = {c, v};
+  }
+  return BGC_OK;
+}
+static int ensure_dms_tables(bgc_ctx *c) {
+  std::lock_guard<std::mutex> lock(g_mu);
+  if (!c->have_dms) return fail(BGC_ERR_PARAMS, "dms_set_params has not been called on this ctx");
+  auto &own = g_const_owner_dms[c->device];
+  const unsigned long long v = g_versions[c].dms;
+  if (own.first != c || own.second != v) {
+    CU(bgc::upload_dms_tables(c->dms_tab, c->stream));
+    own = {c, v};
+  }
+  return BGC_OK;
+}
+static int ensure_macros_tables(bgc_ctx *c) {
+  std::lock_guard<std::mutex> lock(g_mu);
+  if (!c->have_macros) return fail(BGC_ERR_PARAMS, "macros_set_params has not been called on this ctx");
+  auto &own = g_const_owner_macros[c->device];
+  const unsigned long long v = g_versions[c].macros;
+  if (own.first != c || own.second != v) {
+    CU(bgc::upload_macros_tables(c->macros_tab, c->stream));
+    own = {c, v};
+  }
+  return BGC_OK;
+}
+
+// ------------------------------------------------------------------ host-layout transport
+// Fortran A(k,col,n) <-> SoA: each n-slab is an independent 2-D transpose.  The
+// slab travels through one staging buffer; copy and transpose are stream-ordered,
+// so the buffer is safely reused by the next chunk.
+static const int kStageSlabs = 4;
+
+static int stage_buf(bgc_ctx *c, size_t n2, double **out) { return arena_d(c, "stage", n2 * kStageSlabs, out); }
+
+static int up_k(bgc_ctx *c, const char *key, const double *host, int nL, int nC, int nSlabs, double **dev_out) {
+  const size_t n2 = (size_t)nL * nC;
+  double *dev = nullptr, *stage = nullptr;
+  RC(arena_d(c, key, n2 * nSlabs, &dev));
+  *dev_out = dev;
+  if (!host) return fail(BGC_ERR_ARG, "null host array for %s", key);
+  RC(stage_buf(c, n2, &stage));
+  for (int s0 = 0; s0 < nSlabs; s0 += kStageSlabs) {
+    const int ns = (nSlabs - s0 < kStageSlabs) ? nSlabs - s0 : kStageSlabs;
+    CU(cudaMemcpyAsync(stage, host + (size_t)s0 * n2, (size_t)ns * n2 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CU(bgc::launch_transpose(stage, dev + (size_t)s0 * n2, nL, nC, ns, c->stream));
+  }
+  return BGC_OK;
+}
+
+static int down_k(bgc_ctx *c, const double *dev, double *host, int nL, int nC, int nSlabs) {
+  const size_t n2 = (size_t)nL * nC;
+  double *stage = nullptr;
+  RC(stage_buf(c, n2, &stage));
+  for (int s0 = 0; s0 < nSlabs; s0 += kStageSlabs) {
+    const int ns = (nSlabs - s0 < kStageSlabs) ? nSlabs - s0 : kStageSlabs;
+    CU(bgc::launch_transpose(dev + (size_t)s0 * n2, stage, nC, nL, ns, c->stream));
+    CU(cudaMemcpyAsync(host + (size_t)s0 * n2, stage, (size_t)ns * n2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  }
+  return BGC_OK;
+}
+
+// (col[,n]) arrays have the same layout in both spaces
+static int up_c(bgc_ctx *c, const char *key, const void *host, size_t bytes, void **dev_out) {
+  void *dev = nullptr;
+  RC(arena_get(c, key, bytes, &dev));
+  *dev_out = dev;
+  if (!host) return fail(BGC_ERR_ARG, "null host array for %s", key);
+  CU(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, c->stream));
+  return BGC_OK;
+}
+static int down_c(bgc_ctx *c, const void *dev, void *host, size_t bytes) {
+  CU(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, c->stream));
+  return BGC_OK;
+}
+
+static int check_dims(bgc_ctx *c, int nL, int nC, int nCols) {
+  if (nL < 1 || nC < 1 || nCols < 0 || nCols > nC) return fail(BGC_ERR_ARG, "bad dimensions (%d,%d,%d)", nL, nC, nCols);
+  (void)c;
+  return BGC_OK;
+}
+
+// ------------------------------------------------------------------ inventory
+__global__ void inv_accumulate_kernel(double *inv, const double *tmp, int off, int n) {
+  const int i = threadIdx.x;
+  if (i < n) inv[off + i] += tmp[i];
+}
+
+static int inventory_add(bgc_ctx *c, const double *tend, const double *dz, const int *kmax, int nL, int nC, int nCols,
+                         int nTracers, int off, bool count) {
+  if (!c->inventory_on || !dz) return BGC_OK;
+  const size_t need = (size_t)bgc::inventory_grid(nC) * 40;
+  double *partials = nullptr;
+  RC(arena_d(c, "inv_partials", need, &partials));
+  bgc::InventoryArgs ia;
+  ia.nL = nL; ia.nC = nC; ia.nColumns = nCols; ia.nTracers = nTracers;
+  ia.tend = tend; ia.dz = dz; ia.kmax = kmax; ia.partials = partials; ia.out = c->d_inv_tmp; ia.count = count ? 1 : 0;
+  CU(bgc::launch_inventory(ia, c->stream));
+  inv_accumulate_kernel<<<1, 64, 0, c->stream>>>(c->d_inventory, c->d_inv_tmp, off, nTracers);
+  if (count) inv_accumulate_kernel<<<1, 64, 0, c->stream>>>(c->d_inventory, c->d_inv_tmp + nTracers, 60, 2);
+  CU(cudaGetLastError());
+  return BGC_OK;
+}
+
+extern "C" int bgc_inventory_enable(bgc_ctx *c, int enable) {
+  if (!c) return fail(BGC_ERR_ARG, "null ctx");
+  c->inventory_on = enable != 0;
+  return BGC_OK;
+}
+extern "C" int bgc_inventory_reset(bgc_ctx *c) {
+  RC(use_device(c));
+  CU(cudaMemsetAsync(c->d_inventory, 0, BGC_INVENTORY_LEN * sizeof(double), c->stream));
+  return BGC_OK;
+}
+extern "C" int bgc_inventory_get(bgc_ctx *c, double out[BGC_INVENTORY_LEN]) {
+  RC(use_device(c));
+  if (!out) return fail(BGC_ERR_ARG, "null out");
+  CU(cudaMemcpyAsync(out, c->d_inventory, BGC_INVENTORY_LEN * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return BGC_OK;
+}
+extern "C" int bgc_inventory_device_ptr(bgc_ctx *c, double **dev_ptr) {
+  if (!c || !dev_ptr) return fail(BGC_ERR_ARG, "null argument");
+  *dev_ptr = c->d_inventory;
+  return BGC_OK;
+}
+
+// ------------------------------------------------------------------ BGC_SourceSink
+static int source_sink_device(bgc_ctx *c, const BgcInput *in, const BgcForcing *fo, BgcOutput *out,
+                              const BgcDiagnostics *diag, int nL, int nC, int nCols, int alt_co2_use_eco) {
+  RC(ensure_bgc_tables(c));
+  const size_t n2 = (size_t)nL * nC;
+  BgcDiagnostics d;
+  if (diag) d = *diag; else memset(&d, 0, sizeof d);
+  bool any_diag = false;
+  {
+    double *const *pp = (double *const *)&d;
+    for (size_t i = 0; i < sizeof(BgcDiagnostics) / sizeof(double *); ++i) any_diag = any_diag || pp[i] != nullptr;
+  }
+  if (!in->BGC_tracers || !in->PotentialTemperature || !in->Salinity || !in->cell_center_depth ||
+      !in->cell_thickness || !in->cell_bottom_depth || !in->cell_latitude || !in->number_of_active_levels ||
+      !fo->FESEDFLUX || !fo->dust_FLUX_IN || !fo->ShortWaveFlux_surface || !out->BGC_tendencies ||
+      !out->PH_PREV_3D || !out->PH_PREV_ALT_CO2_3D)
+    return fail(BGC_ERR_ARG, "bgc_source_sink: a required array pointer is NULL");
+  const BgcParams &P = c->bgc_tab.p;
+  if ((P.lrest_no3 || P.lrest_po4 || P.lrest_sio3) && !fo->NUTR_RESTORE_RTAU)
+    return fail(BGC_ERR_ARG, "bgc_source_sink: lrest_* set but NUTR_RESTORE_RTAU is NULL");
+  if ((P.lrest_no3 && !fo->NO3_CLIM) || (P.lrest_po4 && !fo->PO4_CLIM) || (P.lrest_sio3 && !fo->SiO3_CLIM))
+    return fail(BGC_ERR_ARG, "bgc_source_sink: lrest_* set but the climatology array is NULL");
+
+  // carbonate chemistry, cell-parallel
+  bgc::Co3Args ca;
+  ca.nL = nL; ca.nC = nC; ca.nColumns = nCols;
+  ca.tracers = in->BGC_tracers; ca.T = in->PotentialTemperature; ca.S = in->Salinity;
+  ca.zmid = in->cell_center_depth; ca.kmax = in->number_of_active_levels;
+  ca.ph_prev = out->PH_PREV_3D; ca.ph_prev_alt = out->PH_PREV_ALT_CO2_3D;
+  ca.co3 = d.diag_CO3; ca.hco3 = d.diag_HCO3; ca.h2co3 = d.diag_H2CO3; ca.ph = d.diag_pH_3D;
+  ca.co3_alt = d.diag_CO3_ALT_CO2; ca.hco3_alt = d.diag_HCO3_ALT_CO2; ca.h2co3_alt = d.diag_H2CO3_ALT_CO2;
+  ca.ph_alt = d.diag_pH_3D_ALT_CO2; ca.sat_calc = d.diag_co3_sat_calc; ca.sat_arag = d.diag_co3_sat_arag;
+  ca.status = c->d_status;
+  if (any_diag) {   // the column sweep's saturation-depth scan consumes these three
+    if (!ca.co3) RC(arena_d(c, "scratch_co3", n2, &ca.co3));
+    if (!ca.sat_calc) RC(arena_d(c, "scratch_satc", n2, &ca.sat_calc));
+    if (!ca.sat_arag) RC(arena_d(c, "scratch_sata", n2, &ca.sat_arag));
+  }
+  CU(bgc::launch_co3_cells(ca, c->stream));
+
+  // ecosystem + particle sweep, column-parallel
+  bgc::EcoArgs ea;
+  ea.nL = nL; ea.nC = nC; ea.nColumns = nCols; ea.alt_co2_use_eco = alt_co2_use_eco;
+  ea.tracers = in->BGC_tracers; ea.T = in->PotentialTemperature; ea.S = in->Salinity;
+  ea.zmid = in->cell_center_depth; ea.dz = in->cell_thickness; ea.zbot = in->cell_bottom_depth;
+  ea.lat = in->cell_latitude; ea.kmax = in->number_of_active_levels;
+  ea.fesedflux = fo->FESEDFLUX; ea.rtau = fo->NUTR_RESTORE_RTAU; ea.no3_clim = fo->NO3_CLIM;
+  ea.po4_clim = fo->PO4_CLIM; ea.sio3_clim = fo->SiO3_CLIM;
+  ea.dust_flux_in = fo->dust_FLUX_IN; ea.sw_flux = fo->ShortWaveFlux_surface;
+  ea.co3 = ca.co3; ea.sat_calc = ca.sat_calc; ea.sat_arag = ca.sat_arag;
+  ea.tend = out->BGC_tendencies;
+  ea.d = d;
+  // written by the carbonate kernel
+  ea.d.diag_CO3 = ea.d.diag_HCO3 = ea.d.diag_H2CO3 = ea.d.diag_pH_3D = nullptr;
+  ea.d.diag_CO3_ALT_CO2 = ea.d.diag_HCO3_ALT_CO2 = ea.d.diag_H2CO3_ALT_CO2 = ea.d.diag_pH_3D_ALT_CO2 = nullptr;
+  ea.d.diag_co3_sat_calc = ea.d.diag_co3_sat_arag = nullptr;
+  // declared in BGC_diagnostics_type but never zeroed nor written by the reference
+  ea.d.diag_POC_ACCUM = ea.d.diag_DONr_remin = ea.d.diag_DOPr_remin = nullptr;
+  ea.status = c->d_status;
+  CU(bgc::launch_eco_columns(ea, any_diag, c->stream));
+
+  RC(inventory_add(c, out->BGC_tendencies, in->cell_thickness, in->number_of_active_levels, nL, nC, nCols,
+                   BGC_TRACER_CNT, 0, true));
+  if (c->inventory_on && any_diag) {
+    const double *cols[8] = {d.diag_Jint_Ctot, d.diag_Jint_100m_Ctot, d.diag_Jint_Ntot, d.diag_Jint_100m_Ntot,
+                             d.diag_Jint_Ptot, d.diag_Jint_100m_Ptot, d.diag_Jint_Sitot, d.diag_Jint_100m_Sitot};
+    double *partials = nullptr;
+    RC(arena_d(c, "inv_partials", (size_t)bgc::inventory_grid(nC) * 40, &partials));
+    CU(cudaMemcpyAsync((void *)c->d_colptrs, cols, sizeof cols, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));   // `cols` lives on this stack frame
+    CU(bgc::launch_column_sums(c->d_colptrs, 8, nCols, partials, c->d_inv_tmp, c->stream));
+    inv_accumulate_kernel<<<1, 64, 0, c->stream>>>(c->d_inventory, c->d_inv_tmp, 52, 8);
+    CU(cudaGetLastError());
+  }
+  return BGC_OK;
+}
+
+extern "C" int bgc_source_sink(bgc_ctx *c, const BgcInput *in, const BgcForcing *fo, BgcOutput *out,
+                               BgcDiagnostics *diag, int nL, int nC, int nCols, int alt_co2_use_eco,
+                               int mem_space) {
+  RC(use_device(c));
+  if (!in || !fo || !out) return fail(BGC_ERR_ARG, "bgc_source_sink: null argument block");
+  RC(check_dims(c, nL, nC, nCols));
+  if (mem_space == BGC_MEM_DEVICE_SOA)
+    return source_sink_device(c, in, fo, out, diag, nL, nC, nCols, alt_co2_use_eco);
+  if (mem_space != BGC_MEM_HOST_FORTRAN) return fail(BGC_ERR_ARG, "unknown mem_space %d", mem_space);
+  if (!c->have_bgc) return fail(BGC_ERR_PARAMS, "bgc_set_params has not been called on this ctx");
+
+  const size_t n2 = (size_t)nL * nC;
+  BgcInput din; BgcForcing dfo; BgcOutput dout; BgcDiagnostics dd;
+  memset(&din, 0, sizeof din); memset(&dfo, 0, sizeof dfo); memset(&dout, 0, sizeof dout); memset(&dd, 0, sizeof dd);
+  double *t = nullptr; void *v = nullptr;
+  RC(up_k(c, "bgc.tracers", in->BGC_tracers, nL, nC, BGC_TRACER_CNT, &t)); din.BGC_tracers = t;
+  RC(up_k(c, "bgc.T", in->PotentialTemperature, nL, nC, 1, &t)); din.PotentialTemperature = t;
+  RC(up_k(c, "bgc.S", in->Salinity, nL, nC, 1, &t)); din.Salinity = t;
+  RC(up_k(c, "bgc.zmid", in->cell_center_depth, nL, nC, 1, &t)); din.cell_center_depth = t;
+  RC(up_k(c, "bgc.dz", in->cell_thickness, nL, nC, 1, &t)); din.cell_thickness = t;
+  RC(up_k(c, "bgc.zbot", in->cell_bottom_depth, nL, nC, 1, &t)); din.cell_bottom_depth = t;
+  RC(up_c(c, "bgc.lat", in->cell_latitude, (size_t)nC * sizeof(double), &v)); din.cell_latitude = (double *)v;
+  RC(up_c(c, "bgc.kmax", in->number_of_active_levels, (size_t)nC * sizeof(int), &v)); din.number_of_active_levels = (int *)v;
+  RC(up_k(c, "bgc.fesed", fo->FESEDFLUX, nL, nC, 1, &t)); dfo.FESEDFLUX = t;
+  const BgcParams &P = c->bgc_tab.p;
+  if (P.lrest_no3 || P.lrest_po4 || P.lrest_sio3) { RC(up_k(c, "bgc.rtau", fo->NUTR_RESTORE_RTAU, nL, nC, 1, &t)); dfo.NUTR_RESTORE_RTAU = t; }
+  if (P.lrest_no3) { RC(up_k(c, "bgc.no3clim", fo->NO3_CLIM, nL, nC, 1, &t)); dfo.NO3_CLIM = t; }
+  if (P.lrest_po4) { RC(up_k(c, "bgc.po4clim", fo->PO4_CLIM, nL, nC, 1, &t)); dfo.PO4_CLIM = t; }
+  if (P.lrest_sio3) { RC(up_k(c, "bgc.sio3clim", fo->SiO3_CLIM, nL, nC, 1, &t)); dfo.SiO3_CLIM = t; }
+  RC(up_c(c, "bgc.dust", fo->dust_FLUX_IN, (size_t)nC * sizeof(double), &v)); dfo.dust_FLUX_IN = (double *)v;
+  RC(up_c(c, "bgc.sw", fo->ShortWaveFlux_surface, (size_t)nC * sizeof(double), &v)); dfo.ShortWaveFlux_surface = (double *)v;
+  RC(up_k(c, "bgc.phprev", out->PH_PREV_3D, nL, nC, 1, &t)); dout.PH_PREV_3D = t;
+  RC(up_k(c, "bgc.phprevalt", out->PH_PREV_ALT_CO2_3D, nL, nC, 1, &t)); dout.PH_PREV_ALT_CO2_3D = t;
+  RC(arena_d(c, "bgc.tend", n2 * BGC_TRACER_CNT, &dout.BGC_tendencies));
+
+  if (diag) {
+#define DEV_K2(name) if (diag->name) RC(arena_d(c, "bgc.d." #name, n2, &dd.name));
+#define DEV_KA(name) if (diag->name) RC(arena_d(c, "bgc.d." #name, n2 * BGC_AUTOTROPH_CNT, &dd.name));
+#define DEV_CA(name) if (diag->name) RC(arena_d(c, "bgc.d." #name, (size_t)nC * BGC_AUTOTROPH_CNT, &dd.name));
+#define DEV_C1(name) if (diag->name) RC(arena_d(c, "bgc.d." #name, (size_t)nC, &dd.name));
+    BGC_DIAG_K2_LIST(DEV_K2) BGC_DIAG_KA_LIST(DEV_KA) BGC_DIAG_CA_LIST(DEV_CA) BGC_DIAG_C1_LIST(DEV_C1)
+#undef DEV_K2
+#undef DEV_KA
+#undef DEV_CA
+#undef DEV_C1
+  }
+
+  RC(source_sink_device(c, &din, &dfo, &dout, diag ? &dd : nullptr, nL, nC, nCols, alt_co2_use_eco));
+
+  RC(down_k(c, dout.BGC_tendencies, out->BGC_tendencies, nL, nC, BGC_TRACER_CNT));
+  RC(down_k(c, dout.PH_PREV_3D, out->PH_PREV_3D, nL, nC, 1));
+  RC(down_k(c, dout.PH_PREV_ALT_CO2_3D, out->PH_PREV_ALT_CO2_3D, nL, nC, 1));
+  if (diag) {
+    // the three never-touched arrays stay exactly as the caller left them
+    dd.diag_POC_ACCUM = dd.diag_DONr_remin = dd.diag_DOPr_remin = nullptr;
+#define DN_K2(name) if (dd.name) RC(down_k(c, dd.name, diag->name, nL, nC, 1));
+#define DN_KA(name) if (dd.name) RC(down_k(c, dd.name, diag->name, nL, nC, BGC_AUTOTROPH_CNT));
+#define DN_CA(name) if (dd.name) RC(down_c(c, dd.name, diag->name, (size_t)nC * BGC_AUTOTROPH_CNT * sizeof(double)));
+#define DN_C1(name) if (dd.name) RC(down_c(c, dd.name, diag->name, (size_t)nC * sizeof(double)));
+    BGC_DIAG_K2_LIST(DN_K2) BGC_DIAG_KA_LIST(DN_KA) BGC_DIAG_CA_LIST(DN_CA) BGC_DIAG_C1_LIST(DN_C1)
+#undef DN_K2
+#undef DN_KA
+#undef DN_CA
+#undef DN_C1
+  }
+  CU(cudaStreamSynchronize(c->stream));   // Fortran semantics: results are in host memory on return
+  return BGC_OK;
+}
+
+// ------------------------------------------------------------------ BGC_SurfaceFluxes
+static int surface_fluxes_device(bgc_ctx *c, const BgcInput *in, BgcForcing *fo, BgcFluxDiagnostics *diag,
+                                 int nL, int nC, int nCols) {
+  RC(ensure_bgc_tables(c));
+  if (!in->BGC_tracers || !fo->depositionFlux || !fo->riverFlux || !fo->gasFlux || !fo->seaIceFlux ||
+      !fo->netFlux || !fo->iceFraction || !fo->windSpeedSquared10m || !fo->SST || !fo->SSS || !fo->surfacePressure)
+    return fail(BGC_ERR_ARG, "bgc_surface_fluxes: a required array pointer is NULL");
+  if (fo->lcalc_CO2_gas_flux && (!fo->surface_pH || !fo->surface_pH_alt_co2 || !fo->atmCO2 || !fo->atmCO2_ALT_CO2))
+    return fail(BGC_ERR_ARG, "bgc_surface_fluxes: CO2 flux requested but pH / atmCO2 arrays are NULL");
+  bgc::SurfArgs sa;
+  sa.nL = nL; sa.nC = nC; sa.nColumns = nCols;
+  sa.tracers = in->BGC_tracers;
+  sa.f = *fo;
+  if (diag) sa.d = *diag; else memset(&sa.d, 0, sizeof sa.d);
+  sa.status = c->d_status;
+  CU(bgc::launch_surface_fluxes(sa, c->stream));
+  return BGC_OK;
+}
+
+extern "C" int bgc_surface_fluxes(bgc_ctx *c, const BgcInput *in, BgcForcing *fo, BgcFluxDiagnostics *diag,
+                                  int nL, int nC, int nCols, int mem_space) {
+  RC(use_device(c));
+  if (!in || !fo) return fail(BGC_ERR_ARG, "bgc_surface_fluxes: null argument block");
+  RC(check_dims(c, nL, nC, nCols));
+  if (mem_space == BGC_MEM_DEVICE_SOA) return surface_fluxes_device(c, in, fo, diag, nL, nC, nCols);
+  if (mem_space != BGC_MEM_HOST_FORTRAN) return fail(BGC_ERR_ARG, "unknown mem_space %d", mem_space);
+  if (!c->have_bgc) return fail(BGC_ERR_PARAMS, "bgc_set_params has not been called on this ctx");
+
+  // Only level 1 of the tracer array is read: upload that single level per tracer.
+  const size_t colb = (size_t)nC * sizeof(double);
+  BgcInput din; BgcForcing dfo; BgcFluxDiagnostics dd;
+  memset(&din, 0, sizeof din); memset(&dd, 0, sizeof dd);
+  dfo = *fo;
+  double *surf = nullptr;
+  RC(arena_d(c, "surf.tracers", (size_t)nC * BGC_TRACER_CNT, &surf));
+  if (!in->BGC_tracers) return fail(BGC_ERR_ARG, "bgc_surface_fluxes: BGC_tracers is NULL");
+  // host A(1,col,n) is strided by nL: a 2-D copy gathers level 1 of every (col,n)
+  CU(cudaMemcpy2DAsync(surf, sizeof(double), in->BGC_tracers, (size_t)nL * sizeof(double), sizeof(double),
+                       (size_t)nC * BGC_TRACER_CNT, cudaMemcpyHostToDevice, c->stream));
+  din.BGC_tracers = surf;
+  void *v = nullptr;
+#define UPC(member, n) do { if (fo->member) { RC(up_c(c, "surf." #member, fo->member, colb * (n), &v)); dfo.member = (double *)v; } } while (0)
+  UPC(surfacePressure, 1); UPC(iceFraction, 1); UPC(windSpeedSquared10m, 1); UPC(atmCO2, 1); UPC(atmCO2_ALT_CO2, 1);
+  UPC(surface_pH, 1); UPC(surface_pH_alt_co2, 1); UPC(surfaceDepth, 1); UPC(SST, 1); UPC(SSS, 1);
+  UPC(depositionFlux, BGC_TRACER_CNT); UPC(riverFlux, BGC_TRACER_CNT); UPC(gasFlux, BGC_TRACER_CNT);
+  UPC(seaIceFlux, BGC_TRACER_CNT); UPC(netFlux, BGC_TRACER_CNT);
+#undef UPC
+  if (diag) {
+#define DEV_F(name) if (diag->name) RC(arena_d(c, "surf.d." #name, (size_t)nC, &dd.name));
+    BGC_FLUX_DIAG_LIST(DEV_F)
+#undef DEV_F
+  }
+  // device tracer "array" holds level 1 only: nL = 1 on the device side
+  RC(surface_fluxes_device(c, &din, &dfo, diag ? &dd : nullptr, 1, nC, nCols));
+#define DNC(member, n) do { if (fo->member) RC(down_c(c, dfo.member, fo->member, colb * (n))); } while (0)
+  DNC(iceFraction, 1); DNC(surface_pH, 1); DNC(surface_pH_alt_co2, 1);
+  DNC(depositionFlux, BGC_TRACER_CNT); DNC(riverFlux, BGC_TRACER_CNT); DNC(gasFlux, BGC_TRACER_CNT);
+  DNC(seaIceFlux, BGC_TRACER_CNT); DNC(netFlux, BGC_TRACER_CNT);
+#undef DNC
+  if (diag) {
+#define DN_F(name) if (dd.name) RC(down_c(c, dd.name, diag->name, colb));
+    BGC_FLUX_DIAG_LIST(DN_F)
+#undef DN_F
+  }
+  CU(cudaStreamSynchronize(c->stream));
+  return BGC_OK;
+}
+
+// ------------------------------------------------------------------ co2calc_1point, batched
+extern "C" int bgc_co2calc_points(bgc_ctx *c, int n, const double *depth, const double *temp, const double *salt,
+                                  const double *dic, const double *ta, const double *pt, const double *sit,
+                                  const double *phlo, const double *phhi, const double *xco2,
+                                  const double *atmpres, double *ph, double *co2star, double *dco2star,
+                                  double *pco2surf, double *dpco2, int mem_space) {
+  RC(use_device(c));
+  if (n < 0) return fail(BGC_ERR_ARG, "negative n");
+  if (n == 0) return BGC_OK;
+  if (!temp || !salt || !dic || !ta || !pt || !sit || !phlo || !phhi || !xco2 || !atmpres || !ph || !co2star ||
+      !dco2star || !pco2surf || !dpco2)
+    return fail(BGC_ERR_ARG, "bgc_co2calc_points: null array");
+  bgc::Co2PointsArgs a;
+  a.n = n; a.status = c->d_status;
+  if (mem_space == BGC_MEM_DEVICE_SOA) {
+    a.depth = depth; a.temp = temp; a.salt = salt; a.dic = dic; a.ta = ta; a.pt = pt; a.sit = sit;
+    a.phlo = phlo; a.phhi = phhi; a.xco2 = xco2; a.atmpres = atmpres;
+    a.ph = ph; a.co2star = co2star; a.dco2star = dco2star; a.pco2surf = pco2surf; a.dpco2 = dpco2;
+    CU(bgc::launch_co2calc_points(a, c->stream));
+    return BGC_OK;
+  }
+  if (mem_space != BGC_MEM_HOST_FORTRAN) return fail(BGC_ERR_ARG, "unknown mem_space %d", mem_space);
+  const size_t b = (size_t)n * sizeof(double);
+  double *in_dev = nullptr, *out_dev = nullptr;
+  RC(arena_d(c, "pts.in", (size_t)n * 10, &in_dev));
+  RC(arena_d(c, "pts.out", (size_t)n * 5, &out_dev));
+  const double *src[10] = {temp, salt, dic, ta, pt, sit, phlo, phhi, xco2, atmpres};
+  for (int i = 0; i < 10; ++i) CU(cudaMemcpyAsync(in_dev + (size_t)i * n, src[i], b, cudaMemcpyHostToDevice, c->stream));
+  a.depth = nullptr;   // level 1: depth does not enter the result (co2calc.F90:149-160)
+  a.temp = in_dev; a.salt = in_dev + (size_t)n; a.dic = in_dev + 2 * (size_t)n; a.ta = in_dev + 3 * (size_t)n;
+  a.pt = in_dev + 4 * (size_t)n; a.sit = in_dev + 5 * (size_t)n; a.phlo = in_dev + 6 * (size_t)n;
+  a.phhi = in_dev + 7 * (size_t)n; a.xco2 = in_dev + 8 * (size_t)n; a.atmpres = in_dev + 9 * (size_t)n;
+  a.ph = out_dev; a.co2star = out_dev + (size_t)n; a.dco2star = out_dev + 2 * (size_t)n;
+  a.pco2surf = out_dev + 3 * (size_t)n; a.dpco2 = out_dev + 4 * (size_t)n;
+  CU(bgc::launch_co2calc_points(a, c->stream));
+  double *dst[5] = {ph, co2star, dco2star, pco2surf, dpco2};
+  for (int i = 0; i < 5; ++i) CU(cudaMemcpyAsync(dst[i], out_dev + (size_t)i * n, b, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return BGC_OK;
+}
+
+// ------------------------------------------------------------------ DMS
+static int dms_source_sink_device(bgc_ctx *c, const DmsInput *in, const DmsForcing *fo, DmsOutput *out,
+                                  const DmsDiagnostics *diag, int nL, int nC, int nCols) {
+  RC(ensure_dms_tables(c));
+  if (!in->DMS_tracers || !in->cell_thickness || !in->number_of_active_levels || !fo->SST ||
+      !fo->ShortWaveFlux_surface || !out->DMS_tendencies)
+    return fail(BGC_ERR_ARG, "dms_source_sink: a required array pointer is NULL");
+  bgc::DmsArgs a;
+  a.nL = nL; a.nC = nC; a.nColumns = nCols;
+  a.tracers = in->DMS_tracers; a.dz = in->cell_thickness; a.kmax = in->number_of_active_levels;
+  a.sst = fo->SST; a.sw_flux = fo->ShortWaveFlux_surface; a.tend = out->DMS_tendencies;
+  if (diag) a.d = *diag; else memset(&a.d, 0, sizeof a.d);
+  CU(bgc::launch_dms_columns(a, c->stream));
+  RC(inventory_add(c, out->DMS_tendencies, in->cell_thickness, in->number_of_active_levels, nL, nC, nCols,
+                   DMS_TRACER_CNT, 30, false));
+  return BGC_OK;
+}
+
+extern "C" int dms_source_sink(bgc_ctx *c, const DmsInput *in, const DmsForcing *fo, DmsOutput *out,
+                               DmsDiagnostics *diag, int nL, int nC, int nCols, int mem_space) {
+  RC(use_device(c));
+  if (!in || !fo || !out) return fail(BGC_ERR_ARG, "dms_source_sink: null argument block");
+  RC(check_dims(c, nL, nC, nCols));
+  if (mem_space == BGC_MEM_DEVICE_SOA) return dms_source_sink_device(c, in, fo, out, diag, nL, nC, nCols);
+  if (mem_space != BGC_MEM_HOST_FORTRAN) return fail(BGC_ERR_ARG, "unknown mem_space %d", mem_space);
+  const size_t n2 = (size_t)nL * nC;
+  DmsInput din; DmsForcing dfo; DmsOutput dout; DmsDiagnostics dd;
+  memset(&din, 0, sizeof din); memset(&dfo, 0, sizeof dfo); memset(&dout, 0, sizeof dout); memset(&dd, 0, sizeof dd);
+  double *t = nullptr; void *v = nullptr;
+  RC(up_k(c, "dms.tracers", in->DMS_tracers, nL, nC, DMS_TRACER_CNT, &t)); din.DMS_tracers = t;
+  RC(up_k(c, "dms.dz", in->cell_thickness, nL, nC, 1, &t)); din.cell_thickness = t;
+  RC(up_c(c, "dms.kmax", in->number_of_active_levels, (size_t)nC * sizeof(int), &v)); din.number_of_active_levels = (int *)v;
+  RC(up_c(c, "dms.sst", fo->SST, (size_t)nC * sizeof(double), &v)); dfo.SST = (double *)v;
+  RC(up_c(c, "dms.sw", fo->ShortWaveFlux_surface, (size_t)nC * sizeof(double), &v)); dfo.ShortWaveFlux_surface = (double *)v;
+  RC(arena_d(c, "dms.tend", n2 * DMS_TRACER_CNT, &dout.DMS_tendencies));
+  if (diag) {
+    // DMS diagnostics are NOT zeroed by the reference: inactive cells keep the
+    // caller's values, so the caller's arrays are uploaded before the kernel runs.
+#define UP_D(name) if (diag->name) { RC(up_k(c, "dms.d." #name, diag->name, nL, nC, 1, &t)); dd.name = t; }
+    DMS_DIAG_LIST(UP_D)
+#undef UP_D
+  }
+  RC(dms_source_sink_device(c, &din, &dfo, &dout, diag ? &dd : nullptr, nL, nC, nCols));
+  RC(down_k(c, dout.DMS_tendencies, out->DMS_tendencies, nL, nC, DMS_TRACER_CNT));
+  if (diag) {
+#define DN_D(name) if (dd.name) RC(down_k(c, dd.name, diag->name, nL, nC, 1));
+    DMS_DIAG_LIST(DN_D)
+#undef DN_D
+  }
+  CU(cudaStreamSynchronize(c->stream));
+  return BGC_OK;
+}
+
+static int dms_surface_device(bgc_ctx *c, const DmsInput *in, DmsForcing *fo, DmsFluxDiagnostics *diag, int nL,
+                              int nC, int nCols) {
+  RC(ensure_dms_tables(c));
+  if (!fo->lcalc_DMS_gas_flux) return BGC_OK;   // DMS_mod.F90:846: nothing at all happens
+  if (!in->DMS_tracers || !fo->SST || !fo->iceFraction || !fo->windSpeedSquared10m || !fo->surfacePressure || !fo->netFlux)
+    return fail(BGC_ERR_ARG, "dms_surface_fluxes: a required array pointer is NULL");
+  bgc::DmsSurfArgs a;
+  a.nL = nL; a.nC = nC; a.nColumns = nCols;
+  a.tracers = in->DMS_tracers; a.f = *fo;
+  if (diag) a.d = *diag; else memset(&a.d, 0, sizeof a.d);
+  CU(bgc::launch_dms_surface(a, c->stream));
+  return BGC_OK;
+}
+
+extern "C" int dms_surface_fluxes(bgc_ctx *c, const DmsInput *in, DmsForcing *fo, DmsFluxDiagnostics *diag,
+                                  int nL, int nC, int nCols, int mem_space) {
+  RC(use_device(c));
+  if (!in || !fo) return fail(BGC_ERR_ARG, "dms_surface_fluxes: null argument block");
+  RC(check_dims(c, nL, nC, nCols));
+  if (mem_space == BGC_MEM_DEVICE_SOA) return dms_surface_device(c, in, fo, diag, nL, nC, nCols);
+  if (mem_space != BGC_MEM_HOST_FORTRAN) return fail(BGC_ERR_ARG, "unknown mem_space %d", mem_space);
+  if (!fo->lcalc_DMS_gas_flux) return BGC_OK;
+  const size_t colb = (size_t)nC * sizeof(double);
+  DmsInput din; DmsForcing dfo = *fo; DmsFluxDiagnostics dd;
+  memset(&din, 0, sizeof din); memset(&dd, 0, sizeof dd);
+  if (!in->DMS_tracers) return fail(BGC_ERR_ARG, "dms_surface_fluxes: DMS_tracers is NULL");
+  double *surf = nullptr;
+  RC(arena_d(c, "dmssurf.tracers", (size_t)nC * DMS_TRACER_CNT, &surf));
+  CU(cudaMemcpy2DAsync(surf, sizeof(double), in->DMS_tracers, (size_t)nL * sizeof(double), sizeof(double),
+                       (size_t)nC * DMS_TRACER_CNT, cudaMemcpyHostToDevice, c->stream));
+  din.DMS_tracers = surf;
+  void *v = nullptr;
+#define UPC(member, n) do { if (fo->member) { RC(up_c(c, "dmssurf." #member, fo->member, colb * (n), &v)); dfo.member = (double *)v; } } while (0)
+  UPC(surfacePressure, 1); UPC(iceFraction, 1); UPC(windSpeedSquared10m, 1); UPC(SST, 1); UPC(SSS, 1);
+  UPC(netFlux, DMS_TRACER_CNT);
+#undef UPC
+  if (diag) {
+    // not zeroed by the reference: columns beyond numColumns keep the caller's values
+#define UP_F(name) if (diag->name) { RC(up_c(c, "dmssurf.d." #name, diag->name, colb, &v)); dd.name = (double *)v; }
+    DMS_FLUX_DIAG_LIST(UP_F)
+#undef UP_F
+  }
+  RC(dms_surface_device(c, &din, &dfo, diag ? &dd : nullptr, 1, nC, nCols));
+  RC(down_c(c, dfo.iceFraction, fo->iceFraction, colb));
+  RC(down_c(c, dfo.netFlux, fo->netFlux, colb * DMS_TRACER_CNT));
+  if (diag) {
+#define DN_F(name) if (dd.name) RC(down_c(c, dd.name, diag->name, colb));
+    DMS_FLUX_DIAG_LIST(DN_F)
+#undef DN_F
+  }
+  CU(cudaStreamSynchronize(c->stream));
+  return BGC_OK;
+}
+
+// ------------------------------------------------------------------ MACROS
+static int macros_device(bgc_ctx *c, const MacrosInput *in, MacrosOutput *out, const MacrosDiagnostics *diag,
+                         int nL, int nC, int nCols) {
+  RC(ensure_macros_tables(c));
+  if (!in->MACROS_tracers || !in->number_of_active_levels || !out->MACROS_tendencies)
+    return fail(BGC_ERR_ARG, "macros_source_sink: a required array pointer is NULL");
+  bgc::MacrosArgs a;
+  a.nL = nL; a.nC = nC; a.nColumns = nCols;
+  a.tracers = in->MACROS_tracers; a.kmax = in->number_of_active_levels; a.tend = out->MACROS_tendencies;
+  if (diag) a.d = *diag; else memset(&a.d, 0, sizeof a.d);
+  CU(bgc::launch_macros_cells(a, c->stream));
+  RC(inventory_add(c, out->MACROS_tendencies, in->cell_thickness, in->number_of_active_levels, nL, nC, nCols,
+                   MACROS_TRACER_CNT, 44, false));
+  return BGC_OK;
+}
+
+extern "C" int macros_source_sink(bgc_ctx *c, const MacrosInput *in, MacrosOutput *out, MacrosDiagnostics *diag,
+                                  int nL, int nC, int nCols, int mem_space) {
+  RC(use_device(c));
+  if (!in || !out) return fail(BGC_ERR_ARG, "macros_source_sink: null argument block");
+  RC(check_dims(c, nL, nC, nCols));
+  if (mem_space == BGC_MEM_DEVICE_SOA) return macros_device(c, in, out, diag, nL, nC, nCols);
+  if (mem_space != BGC_MEM_HOST_FORTRAN) return fail(BGC_ERR_ARG, "unknown mem_space %d", mem_space);
+  const size_t n2 = (size_t)nL * nC;
+  MacrosInput din; MacrosOutput dout; MacrosDiagnostics dd;
+  memset(&din, 0, sizeof din); memset(&dout, 0, sizeof dout); memset(&dd, 0, sizeof dd);
+  double *t = nullptr; void *v = nullptr;
+  RC(up_k(c, "mac.tracers", in->MACROS_tracers, nL, nC, MACROS_TRACER_CNT, &t)); din.MACROS_tracers = t;
+  if (c->inventory_on && in->cell_thickness) { RC(up_k(c, "mac.dz", in->cell_thickness, nL, nC, 1, &t)); din.cell_thickness = t; }
+  RC(up_c(c, "mac.kmax", in->number_of_active_levels, (size_t)nC * sizeof(int), &v)); din.number_of_active_levels = (int *)v;
+  RC(arena_d(c, "mac.tend", n2 * MACROS_TRACER_CNT, &dout.MACROS_tendencies));
+  if (diag) {
+#define UP_D(name) if (diag->name) { RC(up_k(c, "mac.d." #name, diag->name, nL, nC, 1, &t)); dd.name = t; }
+    MACROS_DIAG_LIST(UP_D)
+#undef UP_D
+  }
+  RC(macros_device(c, &din, &dout, diag ? &dd : nullptr, nL, nC, nCols));
+  RC(down_k(c, dout.MACROS_tendencies, out->MACROS_tendencies, nL, nC, MACROS_TRACER_CNT));
+  if (diag) {
+#define DN_D(name) if (dd.name) RC(down_k(c, dd.name, diag->name, nL, nC, 1));
+    MACROS_DIAG_LIST(DN_D)
+#undef DN_D
+  }
+  CU(cudaStreamSynchronize(c->stream));
+  return BGC_OK;
+}
+
+// ------------------------------------------------------------------ multi-GPU
+extern "C" int bgc_comm_unique_id(unsigned char id[128]) {
+  if (!id) return fail(BGC_ERR_ARG, "null id");
+  RC(nccl_load());
+  ncclUniqueId_ u;
+  NC(g_nccl.GetUniqueId(&u));
+  memcpy(id, u.internal, 128);
+  return BGC_OK;
+}
+
+extern "C" int bgc_comm_init_rank(bgc_ctx *c, int nranks, int rank, const unsigned char id[128]) {
+  RC(use_device(c));
+  if (!id || nranks < 1 || rank < 0 || rank >= nranks) return fail(BGC_ERR_ARG, "bgc_comm_init_rank: bad arguments");
+  RC(nccl_load());
+  ncclUniqueId_ u;
+  memcpy(u.internal, id, 128);
+  NC(g_nccl.CommInitRank(&c->comm, nranks, u, rank));
+  c->nranks = nranks;
+  return BGC_OK;
+}
+
+extern "C" int bgc_inventory_allreduce(bgc_ctx *c, double out[BGC_INVENTORY_LEN]) {
+  RC(use_device(c));
+  if (!out) return fail(BGC_ERR_ARG, "null out");
+  double *buf = nullptr;
+  RC(arena_d(c, "inv_reduced", BGC_INVENTORY_LEN, &buf));
+  if (c->comm) {
+    NC(g_nccl.AllReduce(c->d_inventory, buf, BGC_INVENTORY_LEN, kNcclFloat64, kNcclSum, c->comm, c->stream));
+  } else {
+    CU(cudaMemcpyAsync(buf, c->d_inventory, BGC_INVENTORY_LEN * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  }
+  CU(cudaMemcpyAsync(out, buf, BGC_INVENTORY_LEN * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return BGC_OK;
+}
+
+// ------------------------------------------------------------------ host memory, layout helpers
+extern "C" int bgc_host_alloc(void **ptr, size_t bytes) {
+  if (!ptr) return fail(BGC_ERR_ARG, "null ptr");
+  CU(cudaHostAlloc(ptr, bytes ? bytes : 8, cudaHostAllocDefault));
+  return BGC_OK;
+}
+extern "C" int bgc_host_free(void *ptr) {
+  if (ptr) CU(cudaFreeHost(ptr));
+  return BGC_OK;
+}
+extern "C" int bgc_host_register(void *ptr, size_t bytes) {
+  if (!ptr) return fail(BGC_ERR_ARG, "null ptr");
+  CU(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+  return BGC_OK;
+}
+extern "C" int bgc_host_unregister(void *ptr) {
+  if (ptr) CU(cudaHostUnregister(ptr));
+  return BGC_OK;
+}
+
+extern "C" int bgc_layout_to_soa(bgc_ctx *c, const double *dev_fortran, double *dev_soa, int nL, int nC, int nSlabs) {
+  RC(use_device(c));
+  if (!dev_fortran || !dev_soa) return fail(BGC_ERR_ARG, "null array");
+  CU(bgc::launch_transpose(dev_fortran, dev_soa, nL, nC, nSlabs, c->stream));
+  return BGC_OK;
+}
+extern "C" int bgc_layout_to_fortran(bgc_ctx *c, const double *dev_soa, double *dev_fortran, int nL, int nC, int nSlabs) {
+  RC(use_device(c));
+  if (!dev_fortran || !dev_soa) return fail(BGC_ERR_ARG, "null array");
+  CU(bgc::launch_transpose(dev_soa, dev_fortran, nC, nL, nSlabs, c->stream));
+  return BGC_OK;
+}

@@ -1,0 +1,447 @@
+// k_misc.cu — DMS / MACROS source-sink kernels, the DMS surface flux, the
+// Fortran<->SoA layout transposes and the deterministic inventory reductions.
+//
+//   dms_columns_kernel    <- DMS_SourceSink     DMS_mod.F90:156-770   (thread = column; PAR carried down)
+//   dms_surface_kernel    <- DMS_SurfaceFluxes  DMS_mod.F90:778-908   (thread = column)
+//   macros_cells_kernel   <- MACROS_SourceSink  MACROS_mod.F90:137-411 (thread = cell; no vertical coupling)
+//
+// Both source-sink kernels are HBM-bound streaming kernels: each input element
+// is read once and each output element written once, coalesced.
+#include "bgc_kernels.cuh"
+
+namespace bgc {
+
+__constant__ DmsTables c_dms;
+__constant__ MacrosTables c_macros;
+
+cudaError_t upload_dms_tables(const DmsTables &t, cudaStream_t s) {
+  return cudaMemcpyToSymbolAsync(c_dms, &t, sizeof(DmsTables), 0, cudaMemcpyHostToDevice, s);
+}
+cudaError_t upload_macros_tables(const MacrosTables &t, cudaStream_t s) {
+  return cudaMemcpyToSymbolAsync(c_macros, &t, sizeof(MacrosTables), 0, cudaMemcpyHostToDevice, s);
+}
+
+namespace {
+
+constexpr double dms_epsC = 1.00e-8;   // DMS_parms.F90:194-195 (carries the _r8 suffix: exact)
+
+#define DST(name, val) do { if (A.d.name) A.d.name[i2] = (val); } while (0)
+
+__global__ void __launch_bounds__(256)
+dms_columns_kernel(const __grid_constant__ DmsArgs A) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nL = A.nL, nC = A.nC;
+  if (col >= nC) return;
+  const size_t nLnC = (size_t)nL * (size_t)nC;
+  int kmax = (col < A.nColumns) ? A.kmax[col] : 0;
+  if (kmax > nL) kmax = nL;
+  if (kmax < 0) kmax = 0;
+
+  const DmsParams &P = c_dms.p;
+  const DmsIndices &I = c_dms.ind;
+
+  double SST_loc = 0.0, PAR_out = 0.0;
+  if (kmax > 0) {
+    SST_loc = A.sst[col];
+    PAR_out = fmax(0.0, A.sw_flux[col]);
+    PAR_out = PAR_out * P.f_qsw_par_DMS;
+  }
+
+  // column-constant factors (all depend on SST only, DMS_mod.F90:584-592, :637-640)
+  double T_ind = (SST_loc - P.T_lo) / (P.T_hi - P.T_lo);
+  if (T_ind <= 0.0) T_ind = 0.0;
+  if (T_ind >= 1.0) T_ind = 1.0;
+  const double cyano_T = (T_ind * (P.Max_cyano_frac - P.Min_cyano_frac)) + P.Min_cyano_frac;
+  double yield = (T_ind * (P.Max_yld - P.Min_yld)) + P.Min_yld;
+  if (SST_loc < P.T_cryo_hi && SST_loc > P.T_cryo_lo) yield = 0.5;
+  if (SST_loc < -1.0) yield = 0.25;
+
+  const double *trc = A.tracers + col;
+  double *tnd = A.tend + col;
+
+  for (int k = 0; k < nL; ++k) {
+    const size_t i2 = (size_t)col + (size_t)nC * (size_t)k;
+    const size_t o2 = (size_t)nC * (size_t)k;
+    // DMS_output%DMS_tendencies = 0 (:413); the two live slots are overwritten below
+#pragma unroll
+    for (int n = 0; n < DMS_TRACER_CNT; ++n) {
+      if (k >= kmax || (n != I.dms_ind - 1 && n != I.dmsp_ind - 1)) tnd[o2 + (size_t)n * nLnC] = 0.0;
+    }
+    if (k >= kmax) continue;   // diagnostics keep their previous contents outside active cells
+
+#define TR(ind_) fmax(0.0, trc[o2 + (size_t)((ind_) - 1) * nLnC])
+    // NO3 and DOC are copied by the reference (:471-472) but reach no output
+    // (DOC feeds only the unused UV_avg, :531-536): not read here.
+    const double zooC = TR(I.zooC_ind), spC = TR(I.spC_ind), diatC = TR(I.diatC_ind),
+                 diazC = TR(I.diazC_ind), phaeoC = TR(I.phaeoC_ind), spChl = TR(I.spChl_ind),
+                 diatChl = TR(I.diatChl_ind), diazChl = TR(I.diazChl_ind), phaeoChl = TR(I.phaeoChl_ind),
+                 spCaCO3 = TR(I.spCaCO3_ind), DMS_loc = TR(I.dms_ind), DMSP_loc = TR(I.dmsp_ind);
+#undef TR
+    const double dz = A.dz[i2];
+
+    const double k_S_p = P.k_S_p_base * (P.mort + (zooC / 0.3));   // literal 0.3, not zooC_avg (:529)
+
+    const double PAR_in = PAR_out;
+    const double totalChl = spChl + diatChl + diazChl + phaeoChl;
+    const double w = fmax(totalChl, 0.02);
+    double KPARdz;
+    if (w < 0.13224) KPARdz = 0.000919 * pow(w, 0.3536);
+    else             KPARdz = 0.001131 * pow(w, 0.4562);
+    KPARdz = KPARdz * dz;
+    const double eK = exp(-KPARdz);
+    PAR_out = PAR_in * eK;
+    const double PAR_avg = PAR_in * (1.0 - eK) / KPARdz;
+
+    const double j_dms = P.j_dms_perI * PAR_avg;
+
+    double Fcocco = spCaCO3 / (spC + dms_epsC);
+    if (Fcocco > 0.4) Fcocco = 0.4;
+    const double Cocco_frac = Fcocco;
+    const double Cyano_frac = (1.0 - Cocco_frac) * cyano_T;
+    const double Eukar_frac = 1.0 - Cocco_frac - Cyano_frac;
+
+    const double diatN = P.R * diatC;
+    const double phaeoN = P.R * phaeoC;
+    const double coccoN = Cocco_frac * P.R * spC;
+    const double cyanoN = Cyano_frac * P.R * spC;
+    const double eukarN = Eukar_frac * P.R * spC;
+    const double diazN = P.R * diazC;
+    const double zooN = P.R * zooC;
+    const double phytoN = diatN + coccoN + cyanoN + eukarN + diazN + phaeoN;
+
+    double Sp_dec = (P.Sp_ref - spChl) / P.Sp_ref;
+    if (Sp_dec <= 0.0) Sp_dec = 0.0;
+    if (Sp_dec >= 1.0) Sp_dec = 1.0;
+    double Stress_fac = 1.0 + P.Stress_mult * Sp_dec * Sp_dec;
+    if (Stress_fac >= 10.0) Stress_fac = 10.0;
+
+    const double diatS = P.Rs2n_diat * diatN;
+    const double phaeoS = P.Rs2n_phaeo * phaeoN;
+    const double coccoS = P.Rs2n_cocco * coccoN;
+    const double cyanoS = P.Rs2n_cyano * cyanoN;
+    const double eukarS = P.Rs2n_eukar * eukarN * Stress_fac;
+    const double diazS = P.Rs2n_diaz * diazN;
+    const double phytoS = diatS + coccoS + cyanoS + eukarS + diazS + P.G_phaeo_S * phaeoS;
+
+    double Rs2n_zoo;
+    if (phytoN > 0.0) {
+      Rs2n_zoo = (P.Rs2n_diat * diatN +
+                  P.G_phaeo_S * P.Rs2n_phaeo * phaeoN +
+                  P.Rs2n_cocco * coccoN +
+                  P.Rs2n_cyano * cyanoN +
+                  P.Rs2n_eukar * eukarN * Stress_fac +
+                  P.Rs2n_diaz * diazN) / phytoN;
+    } else {
+      Rs2n_zoo = (P.Rs2n_diat + P.Rs2n_cocco + P.Rs2n_cyano + P.Rs2n_eukar + P.Rs2n_diaz + P.Rs2n_phaeo) / 6.0;
+    }
+    const double zooS = Rs2n_zoo * zooN;
+
+    const double B_diagnosed = P.B_preexp * pow(phytoN, P.B_exp);
+
+    const double dms_s_dmsp = yield * P.k_conv * DMSP_loc;
+    const double dms_s = dms_s_dmsp;
+    const double dms_r_B = P.k_S_B * B_diagnosed * DMS_loc;
+    const double dms_r_phot = j_dms * DMS_loc;
+    const double dms_r_bkgnd = P.k_bkgnd * DMS_loc;
+    const double dms_r = dms_r_B + dms_r_phot + dms_r_bkgnd;
+
+    const double dmsp_s_phaeo = P.inject_scale * P.k_S_p_base * phaeoS;
+    const double dmsp_s_nonphaeo = P.inject_scale * k_S_p * phytoS;
+    const double dmsp_s_zoo = P.inject_scale * P.k_S_z * zooS;
+    const double dmsp_s = dmsp_s_phaeo + dmsp_s_nonphaeo + dmsp_s_zoo;
+    const double dmsp_r_B = P.k_conv * DMSP_loc;
+    const double dmsp_r_bkgnd = P.k_bkgnd * DMSP_loc;
+    const double dmsp_r = dmsp_r_B + dmsp_r_bkgnd;
+
+    tnd[o2 + (size_t)(I.dms_ind - 1) * nLnC] = dms_s - dms_r;
+    tnd[o2 + (size_t)(I.dmsp_ind - 1) * nLnC] = dmsp_s - dmsp_r;
+
+    DST(diag_DMS_S_DMSP, dms_s_dmsp);
+    DST(diag_DMS_S_TOTAL, dms_s);
+    DST(diag_DMS_R_B, dms_r_B);
+    DST(diag_DMS_R_PHOT, dms_r_phot);
+    DST(diag_DMS_R_BKGND, dms_r_bkgnd);
+    DST(diag_DMS_R_TOTAL, dms_r);
+    DST(diag_DMSP_S_PHAEO, dmsp_s_phaeo);
+    DST(diag_DMSP_S_NONPHAEO, dmsp_s_nonphaeo);
+    DST(diag_DMSP_S_ZOO, dmsp_s_zoo);
+    DST(diag_DMSP_S_TOTAL, dmsp_s);
+    DST(diag_DMSP_R_B, dmsp_r_B);
+    DST(diag_DMSP_R_BKGND, dmsp_r_bkgnd);
+    DST(diag_DMSP_R_TOTAL, dmsp_r);
+    DST(diag_Cyano_frac, Cyano_frac);
+    DST(diag_Cocco_frac, Cocco_frac);
+    DST(diag_Eukar_frac, Eukar_frac);
+    DST(diag_diatS, diatS);
+    DST(diag_diatN, diatN);
+    DST(diag_phytoN, phytoN);
+    DST(diag_coccoS, coccoS);
+    DST(diag_cyanoS, cyanoS);
+    DST(diag_eukarS, eukarS);
+    DST(diag_diazS, diazS);
+    DST(diag_phaeoS, phaeoS);
+    DST(diag_zooS, zooS);
+    DST(diag_zooCC, zooC);
+    DST(diag_RSNzoo, Rs2n_zoo);
+  }
+}
+#undef DST
+
+__global__ void __launch_bounds__(256)
+dms_surface_kernel(const __grid_constant__ DmsSurfArgs A) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= A.nColumns) return;
+  const size_t nC = (size_t)A.nC;
+  const size_t nLnC = (size_t)A.nL * nC;
+  const DmsIndices &I = c_dms.ind;
+  constexpr double a = 0.31, e2 = 2.85, e3 = 0.612;   // DMS_mod.F90:831-838
+
+  const double seaSurfaceDMS = fmax(0.0, A.tracers[(size_t)col + (size_t)(I.dms_ind - 1) * nLnC]);
+  const double sst = A.f.SST[col];
+  double ice = A.f.iceFraction[col];
+  if (ice < 0.0) ice = 0.0;
+  if (ice > 1.0) ice = 1.0;
+  A.f.iceFraction[col] = ice;   // in-place clamp (:858-859)
+
+  const double sc = 2674.0 + sst * (-147.12 + sst * (3.726 + sst * (-0.038)));   // Kettle & Andreae 2000 (:915-959)
+  const double ws = sqrt(fabs(A.f.windSpeedSquared10m[col])) * 0.01;            // cm/s -> m/s (:866)
+
+  const double XKW_W92 = a * (pow((660.0 / sc), 0.500)) * ws * ws;
+  const double XKW_LM86 = e2 * (pow((600.0 / sc), 0.500)) * (ws - 3.6) + e3 * (pow((600.0 / sc), 0.667));
+  double xkw = 0.0;
+  if (ws < 3.6) xkw = XKW_W92;
+  if ((ws >= 3.6) && (ws < 5.6)) {
+    const double FLM86 = 0.5 * (ws - 3.6);
+    const double FW92 = 1.0 - FLM86;
+    xkw = FW92 * XKW_W92 + FLM86 * XKW_LM86;
+  }
+  if (ws >= 5.6) xkw = XKW_LM86;
+  xkw = xkw / 3600.0;
+  const double xkw_ice = (1.0 - ice) * xkw;
+
+  const double DMSSAT_1atm = 0.0;   // DMSSAT_singleValue is identically zero (:1003)
+  const double pv = xkw_ice * sqrt(660.0 / sc);
+  const double pres = A.f.surfacePressure[col];
+  const double sat = pres * DMSSAT_1atm;
+  A.f.netFlux[(size_t)col + (size_t)(I.dms_ind - 1) * nC] = pv * (sat - seaSurfaceDMS);
+  A.f.netFlux[(size_t)col + (size_t)(I.dmsp_ind - 1) * nC] = 0.0;
+
+#define DG(name, val) do { if (A.d.name) A.d.name[col] = (val); } while (0)
+  DG(diag_DMS_IFRAC, ice);
+  DG(diag_DMS_XKW, xkw_ice);
+  DG(diag_DMS_ATM_PRESS, pres);
+  DG(diag_DMS_PV, pv);
+  DG(diag_DMS_SCHMIDT, sc);
+  DG(diag_DMS_SAT, sat);
+  DG(diag_DMS_SURF, seaSurfaceDMS);
+  DG(diag_DMS_WS, ws);
+#undef DG
+}
+
+__global__ void __launch_bounds__(256)
+macros_cells_kernel(const __grid_constant__ MacrosArgs A) {
+  const size_t nC = (size_t)A.nC;
+  const size_t ncell = (size_t)A.nL * nC;
+  const size_t cell = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (cell >= ncell) return;
+  const int k = (int)(cell / nC);
+  const int col = (int)(cell - (size_t)k * nC);
+  const bool active = col < A.nColumns && k < A.kmax[col];
+  const MacrosParams &P = c_macros.p;
+  const MacrosIndices &I = c_macros.ind;
+
+  double t_prot = 0.0, t_poly = 0.0, t_lip = 0.0;
+  if (active) {
+#define TR(ind_) fmax(0.0, A.tracers[cell + (size_t)((ind_) - 1) * ncell])
+    const double zooC = TR(I.zooC_ind), spC = TR(I.spC_ind), diatC = TR(I.diatC_ind), diazC = TR(I.diazC_ind),
+                 phaeoC = TR(I.phaeoC_ind), prot = TR(I.prot_ind), poly = TR(I.poly_ind), lip = TR(I.lip_ind);
+#undef TR
+    const double k_C_p = P.k_C_p_base * (P.mort + (zooC / P.zooC_avg));
+    const double phytoC = diatC + phaeoC + spC + diazC;
+    const double prot_s = P.inject_scale * P.f_prot * k_C_p * phytoC;
+    const double poly_s = P.inject_scale * P.f_poly * k_C_p * phytoC;
+    const double lip_s = P.inject_scale * P.f_lip * k_C_p * phytoC;
+    const double prot_r = P.k_prot_bac * prot;
+    const double poly_r = P.k_poly_bac * poly;
+    const double lip_r = P.k_lip_bac * lip;
+    t_prot = prot_s - prot_r;
+    t_poly = poly_s - poly_r;
+    t_lip = lip_s - lip_r;
+    if (A.d.diag_PROT_S_TOTAL) A.d.diag_PROT_S_TOTAL[cell] = prot_s;
+    if (A.d.diag_POLY_S_TOTAL) A.d.diag_POLY_S_TOTAL[cell] = poly_s;
+    if (A.d.diag_LIP_S_TOTAL) A.d.diag_LIP_S_TOTAL[cell] = lip_s;
+    if (A.d.diag_PROT_R_TOTAL) A.d.diag_PROT_R_TOTAL[cell] = prot_r;
+    if (A.d.diag_POLY_R_TOTAL) A.d.diag_POLY_R_TOTAL[cell] = poly_r;
+    if (A.d.diag_LIP_R_TOTAL) A.d.diag_LIP_R_TOTAL[cell] = lip_r;
+  }
+  // MACROS_tendencies = 0 everywhere (:267), three live slots on active cells
+#pragma unroll
+  for (int n = 0; n < MACROS_TRACER_CNT; ++n) {
+    double v = 0.0;
+    if (n == I.prot_ind - 1) v = t_prot;
+    if (n == I.poly_ind - 1) v = t_poly;
+    if (n == I.lip_ind - 1) v = t_lip;
+    A.tend[cell + (size_t)n * ncell] = v;
+  }
+}
+
+// ---------------------------------------------------------------- layout
+// dst(c, r) = src(r, c) for each of nSlabs 2-D slabs; src has `R` fastest.
+// 32x32 FP64 tile through padded shared memory: both sides coalesced.
+__global__ void __launch_bounds__(256)
+transpose_kernel(const double *__restrict__ src, double *__restrict__ dst, int R, int C) {
+  __shared__ double tile[32][33];
+  const size_t slab = (size_t)blockIdx.z * (size_t)R * (size_t)C;
+  const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    const int r = r0 + tx, c = c0 + ty + j;
+    if (r < R && c < C) tile[ty + j][tx] = src[slab + (size_t)c * R + r];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    const int c = c0 + tx, r = r0 + ty + j;
+    if (r < R && c < C) dst[slab + (size_t)r * C + c] = tile[tx][ty + j];
+  }
+}
+
+// ---------------------------------------------------------------- inventory
+// Stage 1: block b sums tend(n)*dz over its columns (fixed order inside the
+// block); stage 2: one block folds the partials in index order.  No atomics,
+// so the result is bit-reproducible from run to run and independent of timing.
+constexpr int kInvBlock = 256;
+constexpr int kInvMaxTracers = 32;
+
+__device__ __forceinline__ double block_sum(double v, double *smem) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) smem[wid] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (threadIdx.x == 0) {
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) r += smem[w];
+  }
+  return r;   // valid in thread 0
+}
+
+__global__ void __launch_bounds__(kInvBlock)
+inventory_partial_kernel(const __grid_constant__ InventoryArgs A) {
+  __shared__ double smem[kInvBlock / 32];
+  const size_t nC = (size_t)A.nC, nLnC = (size_t)A.nL * nC;
+  double acc[kInvMaxTracers];
+#pragma unroll
+  for (int n = 0; n < kInvMaxTracers; ++n) acc[n] = 0.0;
+  double cells = 0.0, cols = 0.0;
+  for (int col = blockIdx.x * blockDim.x + threadIdx.x; col < A.nColumns; col += gridDim.x * blockDim.x) {
+    int kmax = A.kmax[col];
+    if (kmax > A.nL) kmax = A.nL;
+    if (kmax > 0) cols += 1.0;
+    for (int k = 0; k < kmax; ++k) {
+      const size_t i2 = (size_t)col + nC * (size_t)k;
+      const double dz = A.dz[i2];
+      cells += 1.0;
+#pragma unroll
+      for (int n = 0; n < kInvMaxTracers; ++n)
+        if (n < A.nTracers) acc[n] += A.tend[i2 + (size_t)n * nLnC] * dz;
+    }
+  }
+  const int stride = A.nTracers + 2;
+#pragma unroll
+  for (int n = 0; n < kInvMaxTracers; ++n) {
+    if (n < A.nTracers) {
+      const double r = block_sum(acc[n], smem);
+      if (threadIdx.x == 0) A.partials[(size_t)blockIdx.x * stride + n] = r;
+    }
+  }
+  double r = block_sum(cells, smem);
+  if (threadIdx.x == 0) A.partials[(size_t)blockIdx.x * stride + A.nTracers] = r;
+  r = block_sum(cols, smem);
+  if (threadIdx.x == 0) A.partials[(size_t)blockIdx.x * stride + A.nTracers + 1] = r;
+}
+
+__global__ void fold_partials_kernel(const double *partials, int nParts, int stride, int nOut, double *out) {
+  const int n = threadIdx.x;
+  if (n >= nOut) return;
+  double s = 0.0;
+  for (int b = 0; b < nParts; ++b) s += partials[(size_t)b * stride + n];
+  out[n] = s;
+}
+
+__global__ void __launch_bounds__(kInvBlock)
+column_sums_partial_kernel(const double *const *cols, int nArrays, int nColumns, double *partials) {
+  __shared__ double smem[kInvBlock / 32];
+  for (int a = 0; a < nArrays; ++a) {
+    const double *p = cols[a];
+    double acc = 0.0;
+    if (p)
+      for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nColumns; c += gridDim.x * blockDim.x) acc += p[c];
+    const double r = block_sum(acc, smem);
+    if (threadIdx.x == 0) partials[(size_t)blockIdx.x * nArrays + a] = r;
+  }
+}
+
+}  // namespace
+
+static inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+cudaError_t launch_dms_columns(const DmsArgs &a, cudaStream_t s) {
+  if (a.nC <= 0 || a.nL <= 0) return cudaSuccess;
+  dms_columns_kernel<<<cdiv((size_t)a.nC, 256), 256, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_dms_surface(const DmsSurfArgs &a, cudaStream_t s) {
+  if (a.nColumns <= 0) return cudaSuccess;
+  dms_surface_kernel<<<cdiv((size_t)a.nColumns, 256), 256, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_macros_cells(const MacrosArgs &a, cudaStream_t s) {
+  const size_t ncell = (size_t)a.nL * (size_t)a.nC;
+  if (ncell == 0) return cudaSuccess;
+  macros_cells_kernel<<<cdiv(ncell, 256), 256, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_transpose(const double *src, double *dst, int R, int C, int nSlabs, cudaStream_t s) {
+  if (R <= 0 || C <= 0 || nSlabs <= 0) return cudaSuccess;
+  // gridDim.y/z are limited to 65535: columns go on x when they are the long axis
+  dim3 grid(cdiv((size_t)R, 32), cdiv((size_t)C, 32), (unsigned)nSlabs);
+  if (grid.y > 65535u || grid.z > 65535u) return cudaErrorInvalidConfiguration;
+  transpose_kernel<<<grid, 256, 0, s>>>(src, dst, R, C);
+  return cudaGetLastError();
+}
+
+int inventory_grid(int nC) {
+  int g = (nC + kInvBlock - 1) / kInvBlock;
+  if (g > 592) g = 592;   // 4 blocks per SM on 148 SMs
+  if (g < 1) g = 1;
+  return g;
+}
+
+cudaError_t launch_inventory(const InventoryArgs &a, cudaStream_t s) {
+  if (a.nTracers > kInvMaxTracers) return cudaErrorInvalidValue;
+  const int grid = inventory_grid(a.nC);
+  inventory_partial_kernel<<<grid, kInvBlock, 0, s>>>(a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  const int nOut = a.nTracers + (a.count ? 2 : 0);
+  fold_partials_kernel<<<1, 64, 0, s>>>(a.partials, grid, a.nTracers + 2, nOut, a.out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_column_sums(const double *const *cols, int nArrays, int nColumns, double *partials,
+                               double *out, cudaStream_t s) {
+  const int grid = inventory_grid(nColumns);
+  column_sums_partial_kernel<<<grid, kInvBlock, 0, s>>>(cols, nArrays, nColumns, partials);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  fold_partials_kernel<<<1, 64, 0, s>>>(partials, grid, nArrays, nArrays, out);
+  return cudaGetLastError();
+}
+
+}  // namespace bgc
