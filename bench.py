@@ -1,0 +1,476 @@
+#!/usr/bin/env python
+"""bench.py — BGC_SourceSink cell-updates/s on B200 (BASELINE.json metric).
+
+Workload (config 4 of BASELINE.json): an EC60to30-sized mesh, 235 160 columns x
+60 levels of synthetic ocean columns, full BGC + DMS + MACROS
+tendency update = BGC_SourceSink + BGC_SurfaceFluxes + DMS_SourceSink +
+DMS_SurfaceFluxes + MACROS_SourceSink with every diagnostic produced, plus the
+tracer-inventory reduction (all-reduced over NCCL when N > 1).  One "step" is
+one such update of the whole mesh.  Columns are independent, so at N GPUs every
+rank owns a contiguous slab of 235 160 columns of an N-times larger mesh (weak
+scaling, no data-path collective; the 64-double inventory all-reduce is the only
+exchange).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Prints ONE JSON line (rank 0).  `value` is device-resident throughput (inputs in
+HBM when the clock starts); `e2e` is the same update through the C ABI's host
+(Fortran-layout) entry points with pinned host arrays, H2D/D2H inside the timed
+region.  `--impl reference` times the CPU oracle (the C restatement of the
+reference Fortran; no Fortran compiler exists in this image) on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+import __graft_entry__ as ge  # noqa: E402
+
+EC_COLUMNS = 235160
+EC_LEVELS = 60
+METRIC = "BGC_SourceSink cell-updates/s (cols x levels), full BGC+DMS+MACROS tendency update"
+UNIT = "cell-updates/s"
+
+# Algorithmic bytes per active cell (DESIGN.md "Roofline"): each
+# array element the algorithm must touch, once, FP64.
+B_BGC = 1592      # BGC_SourceSink: 37 reads + 32 writes + 130 diagnostic writes
+B_DMS = 432       # DMS_SourceSink: 13 reads + 14 writes + 27 diagnostic writes
+B_MACROS = 176    # MACROS_SourceSink: 8 reads + 8 writes + 6 diagnostic writes
+B_API = B_BGC + B_DMS + B_MACROS   # 2200 B per cell for the full step
+# share of B_BGC that belongs to the column-sweep kernel (eco_columns_kernel):
+# everything except the carbonate kernel's private traffic (DIC, ALK reads;
+# PH_PREV x2 read+write; 10 carbonate diagnostics) = 1592 - 16*8
+B_ECO = B_BGC - 128
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def load_peaks():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, pw, reasons = [], [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------ reference arm / cpu baseline
+def cpu_oracle_throughput(pkg, columns, levels, steps, warmup):
+    """The CPU oracle (oracle/libbgc_oracle.so, all host threads) on `columns` columns
+    of the same synthetic workload.  Returns (cell-updates/s, seconds per step, threads)."""
+    sys.path.insert(0, os.path.join(REPO, "oracle"))
+    import oracle as o   # cpu_baseline / --impl reference leg only
+    po = o.Parms()
+    nthreads = o.max_threads()
+    bgc = pkg.BgcColumns(levels, columns)
+    dms = pkg.DmsColumns(levels, columns)
+    mac = pkg.MacrosColumns(levels, columns)
+    pkg.synth_fill(bgc, dms, mac, bgc_ind=po.ind, dms_ind=po.dms_ind, macros_ind=po.macros_ind)
+    cells = int(bgc.active_mask().sum())
+
+    def step():
+        o.BGC_SourceSink(po, bgc, True, nthreads=nthreads)
+        o.BGC_SurfaceFluxes(po, bgc, nthreads=nthreads)
+        o.DMS_SourceSink(po, dms, nthreads=nthreads)
+        o.DMS_SurfaceFluxes(po, dms)
+        o.MACROS_SourceSink(po, mac, nthreads=nthreads)
+    for _ in range(max(1, warmup)):   # the first pass is the cold-bracket one
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return cells / dt, dt, nthreads, cells
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return 0
+    ge.build_oracle_only()
+    pkg = ge.load_package()
+    cols = args.cpu_columns
+    v, dt, nthreads, cells = cpu_oracle_throughput(pkg, cols, args.levels, args.steps, args.warmup)
+    sample = "%d columns x %d levels (%d cells) of the EC60to30 synthetic mesh per step" % (cols, args.levels, cells)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, world),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": nthreads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "CPU oracle = C restatement of the reference Fortran (gcc -O2 -ffp-contract=off, OpenMP over "
+                "columns); gfortran is not available in this image so the Fortran itself cannot be built",
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config(args, world):
+    return {"workload": "EC60to30 full BGC+DMS+MACROS tendency update (BASELINE.json configs[3])",
+            "columns_per_gpu": args.columns, "levels": args.levels, "n_gpus": world,
+            "cells_total": args.columns * args.levels * world,
+            "diagnostics": "all (BGC 130 + DMS 27 + MACROS 6 arrays per cell)",
+            "sharding": "contiguous column slabs, one process per GPU, no halo",
+            "cache": "inputs+outputs per step (%.1f GB per GPU) far exceed the 126 MB L2; no flush needed"
+                     % (args.columns * args.levels * B_API / 1e9),
+            "ph_brackets": "warm (PH_PREV from the untimed cold pass), as in a running model"}
+
+
+# ------------------------------------------------------------------ device-resident arm
+def fill_device_inputs(pkg, parms, bgc, dms, mac, column0, nthreads=0):
+    """Generate this rank's synthetic columns directly in the SoA layout on the host
+    and copy the INPUT members to the device containers."""
+    import ctypes as C
+    import torch
+    abi = pkg.abi
+    nL, nC = bgc.nLevelsMax, bgc.nColumnsMax
+    h = {}
+
+    def arr(shape, dtype=np.float64):
+        return np.zeros(shape, dtype=dtype)
+    # host staging in SoA layout (inputs only)
+    h["tr"] = arr((abi.BGC_TRACER_CNT, nL, nC))
+    for n in bgc.K2_IN:
+        h[n] = arr((nL, nC))
+    h["lat"] = arr((nC,)); h["kmax"] = arr((nC,), np.int32)
+    hf = {n: arr((nL, nC)) for n in ("FESEDFLUX",)}
+    hf.update({n: arr((nC,)) for n in abi.BGC_FORCING_C1})
+    hf.update({n: arr((abi.BGC_TRACER_CNT, nC)) for n in abi.BGC_FORCING_FLUX})
+    h["dtr"] = arr((abi.DMS_TRACER_CNT, nL, nC)); h["ddz"] = arr((nL, nC)); h["dkmax"] = arr((nC,), np.int32)
+    hdf = {n: arr((nC,)) for n in abi.DMS_FORCING_C1}
+    hdf["netFlux"] = arr((abi.DMS_TRACER_CNT, nC))
+    h["mtr"] = arr((abi.MACROS_TRACER_CNT, nL, nC)); h["mdz"] = arr((nL, nC)); h["mkmax"] = arr((nC,), np.int32)
+
+    cin = abi.BgcInput()
+    cin.BGC_tracers = abi.dptr(h["tr"])
+    for n in bgc.K2_IN:
+        setattr(cin, n, abi.dptr(h[n]))
+    cin.cell_latitude = abi.dptr(h["lat"]); cin.number_of_active_levels = abi.iptr(h["kmax"])
+    cfo = abi.BgcForcing()
+    for n, a in hf.items():
+        setattr(cfo, n, abi.dptr(a))
+    din = abi.DmsInput()
+    din.DMS_tracers = abi.dptr(h["dtr"]); din.cell_thickness = abi.dptr(h["ddz"])
+    din.number_of_active_levels = abi.iptr(h["dkmax"])
+    dfo = abi.DmsForcing()
+    for n, a in hdf.items():
+        setattr(dfo, n, abi.dptr(a))
+    min_ = abi.MacrosInput()
+    min_.MACROS_tracers = abi.dptr(h["mtr"]); min_.cell_thickness = abi.dptr(h["mdz"])
+    min_.number_of_active_levels = abi.iptr(h["mkmax"])
+
+    from importlib import import_module
+    colmod = import_module(pkg.__name__ + ".columns")
+    sp = colmod._SynthSpec(colmod.SEED_COLUMNS, nL, nC, bgc.nColumns, column0, nL, 0, 1, 1, nthreads)
+    rc = colmod.synth_lib().bgc_synth_fill(C.byref(sp), C.byref(parms.ind), C.byref(parms.dms_ind),
+                                           C.byref(parms.macros_ind), C.byref(cin), C.byref(cfo), C.byref(din),
+                                           C.byref(dfo), C.byref(min_))
+    if rc != 0:
+        raise RuntimeError("bgc_synth_fill failed: %d" % rc)
+
+    def put(t, a):
+        t.copy_(torch.from_numpy(a))
+    put(bgc.BGC_tracers, h["tr"])
+    for n in bgc.K2_IN:
+        put(getattr(bgc, n), h[n])
+    put(bgc.cell_latitude, h["lat"]); put(bgc.number_of_active_levels, h["kmax"])
+    for n, a in hf.items():
+        put(bgc.forcing[n], a)
+    put(dms.DMS_tracers, h["dtr"]); put(dms.cell_thickness, h["ddz"]); put(dms.number_of_active_levels, h["dkmax"])
+    for n, a in hdf.items():
+        put(dms.forcing[n], a)
+    put(mac.MACROS_tracers, h["mtr"]); put(mac.cell_thickness, h["mdz"]); put(mac.number_of_active_levels, h["mkmax"])
+    return int(h["kmax"].astype(np.int64).sum())
+
+
+def mem_available_gb():
+    try:
+        for ln in open("/proc/meminfo"):
+            if ln.startswith("MemAvailable:"):
+                return int(ln.split()[1]) / 1e6
+    except Exception:
+        pass
+    return 0.0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--columns", type=int, default=EC_COLUMNS, help="columns per GPU")
+    ap.add_argument("--levels", type=int, default=EC_LEVELS)
+    ap.add_argument("--cpu-columns", type=int, default=16384, help="columns of the CPU-oracle sample")
+    ap.add_argument("--e2e-columns", type=int, default=0, help="columns per GPU of the end-to-end leg (0 = auto)")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-inventory", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3   # timing rule: at least 3 warm-up steps
+
+    rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    pkg = ge.load_package()
+    host = pkg.host
+    parms = host.Parms()
+    nL, nC = args.levels, args.columns
+    dev = "cuda:%d" % local_rank
+
+    ctx = host.Context(nL, nC, device=local_rank, parms=parms)
+    stream = torch.cuda.Stream(device=dev)
+    ctx.set_stream(stream.cuda_stream)
+    if world > 1:   # NCCL communicator owned by the ctx; the unique id travels over torch.distributed
+        uid = [ctx.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx.comm_init_rank(world, rank, uid[0])
+    ctx.inventory_enable(not args.no_inventory)
+
+    bgc = host.DeviceBgcColumns(nL, nC, device=dev)
+    dms = host.DeviceDmsColumns(nL, nC, device=dev)
+    mac = host.DeviceMacrosColumns(nL, nC, device=dev)
+    cells = fill_device_inputs(pkg, parms, bgc, dms, mac, column0=rank * nC)
+    torch.cuda.synchronize()
+
+    def step():
+        if not args.no_inventory:
+            ctx.inventory_reset()
+        host.BGC_SourceSink(ctx, bgc, True, True)
+        host.BGC_SurfaceFluxes(ctx, bgc)
+        host.DMS_SourceSink(ctx, dms, True)
+        host.DMS_SurfaceFluxes(ctx, dms)
+        host.MACROS_SourceSink(ctx, mac, True)
+        if not args.no_inventory:
+            return ctx.inventory_allreduce()   # NCCL all-reduce (N > 1) + 512 B to the host
+        return None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    step()                       # cold pass: PH_PREV = 0 -> wide brackets (not timed)
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    ctx.timing_reset()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    inv = None
+    for _ in range(args.steps):
+        inv = step()
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    launches = ctx.launch_count()
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    total_cells = cells
+    if world > 1:
+        c = torch.tensor([cells], dtype=torch.float64, device=dev)
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        total_cells = int(c.item())
+    value = total_cells / (ms_step * 1e-3)
+
+    # ---- per-kernel device times (CUDA events around every launch, separate pass)
+    ctx.timing_reset()
+    ctx.timing_enable(True)
+    for _ in range(args.steps):
+        step()
+    ctx.synchronize()
+    ktimes = ctx.timing()
+    ctx.timing_enable(False)
+    peak, peak_src = load_peaks()
+    eco_ms, eco_n, _ = ktimes["eco_columns_kernel"]
+    eco_ms_per = eco_ms / max(1, eco_n)
+    achieved = cells * B_ECO / (eco_ms_per * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(REPO, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("eco_columns_kernel_bytes_per_cell")
+            traffic = traffic * cells if traffic is not None else None
+        except Exception:
+            traffic = None
+    kernel_ms = {k: (v[0] / max(1, v[1])) for k, v in ktimes.items() if v[1]}
+    roofline = {"bound": "hbm", "kernel": "eco_columns_kernel", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "algorithmic_bytes_per_cell": B_ECO, "cells_per_launch": cells,
+                "kernel_ms": eco_ms_per, "peak_source": peak_src,
+                "step": {"algorithmic_bytes_per_cell": B_API,
+                         "achieved": cells * B_API / (ms_step * 1e-3) / 1e9,
+                         "frac": cells * B_API / (ms_step * 1e-3) / 1e9 / peak},
+                "kernel_ms_per_launch": kernel_ms}
+
+    # ---- end to end: host Fortran-layout arrays (pinned), H2D/D2H inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, pkg, host, ctx, parms, rank, world, local_rank, dev)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        v, dt, nthreads, ccells = cpu_oracle_throughput(pkg, args.cpu_columns, nL, 2, 1)
+        cpu = {"value": v, "unit": UNIT, "cores": nthreads, "kind": "port",
+               "sample": "%d columns x %d levels (%d cells) of the same synthetic mesh, 1 cold + 2 timed warm passes"
+                         % (args.cpu_columns, nL, ccells)}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": workload_config(args, world), "clocks": clocks, "gpu_launches": int(launches),
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+                "inventory_check": None if inv is None else {"active_cells": float(inv[60]), "columns": float(inv[61])}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def run_e2e(args, pkg, host, ctx, parms, rank, world, local_rank, dev):
+    import torch
+    import torch.distributed as dist
+    nL = args.levels
+    ranks_here = max(1, env_int("LOCAL_WORLD_SIZE", world))
+    per_col = nL * (B_API + 8 * 40)   # host bytes per column incl. uploaded DMS/MACROS diagnostics, rough
+    nC = args.e2e_columns
+    if nC <= 0:
+        budget = mem_available_gb() * 1e9 * 0.45 / ranks_here
+        nC = int(min(args.columns, max(4096, budget // (per_col * 1.3))))
+    pinned = []
+
+    def alloc(n, dtype):
+        t = torch.empty(int(n), dtype=torch.float64 if dtype == np.float64 else torch.int32, pin_memory=True)
+        pinned.append(t)
+        return t.numpy()
+    bgc = pkg.BgcColumns(nL, nC, alloc=alloc)
+    dms = pkg.DmsColumns(nL, nC, alloc=alloc)
+    mac = pkg.MacrosColumns(nL, nC, alloc=alloc)
+    pkg.synth_fill(bgc, dms, mac, bgc_ind=parms.ind, dms_ind=parms.dms_ind, macros_ind=parms.macros_ind,
+                   column0=rank * args.columns)
+    cells = int(bgc.active_mask().sum())
+    n2 = nL * nC * 8
+    abi = pkg.abi
+    h2d = n2 * (30 + 5 + 1 + 2) + nC * (8 + 4 + 16) \
+        + n2 * (14 + 1 + len(abi.DMS_DIAG)) + nC * (4 + 16) \
+        + n2 * (8 + 1 + len(abi.MACROS_DIAG)) + nC * 4 \
+        + nC * 8 * (30 + 10 + 5 * 30) + nC * 8 * (14 + 5 + 14 + 8)
+    d2h = n2 * (30 + 2 + 58 + 18 * 4) + nC * 8 * (17 + 12) \
+        + n2 * (14 + len(abi.DMS_DIAG)) + n2 * (8 + len(abi.MACROS_DIAG)) \
+        + nC * 8 * (3 + 5 * 30 + 14) + nC * 8 * (1 + 14 + 8)
+
+    def step():
+        host.BGC_SourceSink(ctx, bgc, True, True)
+        host.BGC_SurfaceFluxes(ctx, bgc)
+        host.DMS_SourceSink(ctx, dms, True)
+        host.DMS_SurfaceFluxes(ctx, dms)
+        host.MACROS_SourceSink(ctx, mac, True)
+    step()   # cold pass + arena allocation
+    step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        step()
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / args.e2e_steps
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    c = torch.tensor([cells], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+    dt = float(t.item())
+    return {"value": float(c.item()) / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+            "ms_per_step": dt * 1e3, "steps": args.e2e_steps, "columns_per_gpu": nC,
+            "api": "bgc_source_sink/bgc_surface_fluxes/dms_source_sink/dms_surface_fluxes/macros_source_sink "
+                   "with BGC_MEM_HOST_FORTRAN, pinned host arrays, synchronous on return"}
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -326,6 +326,21 @@ int macros_source_sink(bgc_ctx *ctx, const MacrosInput *in, MacrosOutput *out,
                        MacrosDiagnostics *diag,
                        int nLevelsMax, int nColumnsMax, int nColumns, int mem_space);
 
+/* Launch accounting and optional per-kernel timing.  The library counts every
+ * kernel it launches (per kernel id below); with timing enabled each launch is
+ * also bracketed by CUDA events on the ctx stream and bgc_timing_get returns the
+ * accumulated device time.  (The reference has no profiling hooks at all.) */
+enum {
+  BGC_K_CO3_CELLS = 0, BGC_K_ECO_COLUMNS = 1, BGC_K_DMS_COLUMNS = 2, BGC_K_MACROS_CELLS = 3,
+  BGC_K_SURFACE_FLUXES = 4, BGC_K_DMS_SURFACE = 5, BGC_K_CO2CALC_POINTS = 6, BGC_K_INVENTORY = 7,
+  BGC_K_TRANSPOSE = 8, BGC_KERNEL_ID_COUNT = 9
+};
+int bgc_timing_enable(bgc_ctx *ctx, int enable);
+int bgc_timing_reset(bgc_ctx *ctx);   /* zeroes times AND launch counters */
+int bgc_timing_get(bgc_ctx *ctx, int kernel_id, double *total_ms,
+                   unsigned long long *timed_launches, unsigned long long *launches);
+const char *bgc_kernel_name(int kernel_id);
+
 /* Inventory: device vector accumulated by the *_source_sink calls since the
  * last bgc_inventory_reset.  bgc_inventory_get copies this rank's vector to the
  * host; bgc_inventory_device_ptr exposes it for a caller-side collective. */

@@ -13,18 +13,29 @@ import numpy as np
 from . import abi
 
 
-def _f(shape):
-    return np.zeros(shape, dtype=np.float64, order="F")
+def _f(shape, alloc=None, dtype=np.float64):
+    """Fortran-layout array.  `alloc(nelem, dtype) -> 1-D ndarray` lets the caller
+    supply the storage (e.g. page-locked memory for the C ABI's host path)."""
+    if alloc is None:
+        return np.zeros(shape, dtype=dtype, order="F")
+    n = int(np.prod(shape))
+    flat = alloc(n, dtype)
+    flat[...] = 0
+    return flat.reshape(shape, order="F")
 
 
 class BgcColumns:
     """BGC_input_type + BGC_forcing_type + BGC_output_type + BGC_diagnostics_type
     + BGC_flux_diagnostics_type for (nLevelsMax, nColumnsMax)."""
 
-    def __init__(self, nLevelsMax, nColumnsMax, nColumns=None):
+    def __init__(self, nLevelsMax, nColumnsMax, nColumns=None, alloc=None, diagnostics=True):
         nL, nC = int(nLevelsMax), int(nColumnsMax)
         self.nLevelsMax, self.nColumnsMax = nL, nC
         self.nColumns = nC if nColumns is None else int(nColumns)
+        _g = globals()["_f"]
+
+        def _f(shape, dtype=np.float64):   # storage from `alloc` when given
+            return _g(shape, alloc, dtype)
         # BGC_input_type
         self.BGC_tracers = _f((nL, nC, abi.BGC_TRACER_CNT))
         self.PotentialTemperature = _f((nL, nC))
@@ -33,7 +44,7 @@ class BgcColumns:
         self.cell_thickness = _f((nL, nC))
         self.cell_bottom_depth = _f((nL, nC))
         self.cell_latitude = _f((nC,))
-        self.number_of_active_levels = np.zeros((nC,), dtype=np.int32)
+        self.number_of_active_levels = _f((nC,), np.int32)
         # BGC_forcing_type
         self.forcing = {}
         for n in abi.BGC_FORCING_K2:
@@ -50,14 +61,15 @@ class BgcColumns:
         self.PH_PREV_ALT_CO2_3D = _f((nL, nC))
         # BGC_diagnostics_type
         self.diag = {}
-        for n in abi.BGC_DIAG_K2:
-            self.diag[n] = _f((nL, nC))
-        for n in abi.BGC_DIAG_KA:
-            self.diag[n] = _f((nL, nC, abi.BGC_AUTOTROPH_CNT))
-        for n in abi.BGC_DIAG_CA:
-            self.diag[n] = _f((nC, abi.BGC_AUTOTROPH_CNT))
-        for n in abi.BGC_DIAG_C1:
-            self.diag[n] = _f((nC,))
+        if diagnostics:
+            for n in abi.BGC_DIAG_K2:
+                self.diag[n] = _f((nL, nC))
+            for n in abi.BGC_DIAG_KA:
+                self.diag[n] = _f((nL, nC, abi.BGC_AUTOTROPH_CNT))
+            for n in abi.BGC_DIAG_CA:
+                self.diag[n] = _f((nC, abi.BGC_AUTOTROPH_CNT))
+            for n in abi.BGC_DIAG_C1:
+                self.diag[n] = _f((nC,))
         # BGC_flux_diagnostics_type
         self.flux_diag = {n: _f((nC,)) for n in abi.BGC_FLUX_DIAG}
 
@@ -99,7 +111,7 @@ class BgcColumns:
         return s
 
     def copy(self):
-        o = BgcColumns(self.nLevelsMax, self.nColumnsMax, self.nColumns)
+        o = BgcColumns(self.nLevelsMax, self.nColumnsMax, self.nColumns, diagnostics=bool(self.diag))
         for n in ("BGC_tracers", "PotentialTemperature", "Salinity", "cell_center_depth",
                   "cell_thickness", "cell_bottom_depth", "cell_latitude",
                   "number_of_active_levels", "BGC_tendencies", "PH_PREV_3D",
@@ -120,18 +132,22 @@ class BgcColumns:
 
 
 class DmsColumns:
-    def __init__(self, nLevelsMax, nColumnsMax, nColumns=None):
+    def __init__(self, nLevelsMax, nColumnsMax, nColumns=None, alloc=None, diagnostics=True):
         nL, nC = int(nLevelsMax), int(nColumnsMax)
         self.nLevelsMax, self.nColumnsMax = nL, nC
         self.nColumns = nC if nColumns is None else int(nColumns)
+        _g = globals()["_f"]
+
+        def _f(shape, dtype=np.float64):
+            return _g(shape, alloc, dtype)
         self.DMS_tracers = _f((nL, nC, abi.DMS_TRACER_CNT))
         self.cell_thickness = _f((nL, nC))
-        self.number_of_active_levels = np.zeros((nC,), dtype=np.int32)
+        self.number_of_active_levels = _f((nC,), np.int32)
         self.forcing = {n: _f((nC,)) for n in abi.DMS_FORCING_C1}
         self.forcing["netFlux"] = _f((nC, abi.DMS_TRACER_CNT))
         self.lcalc_DMS_gas_flux = 1
         self.DMS_tendencies = _f((nL, nC, abi.DMS_TRACER_CNT))
-        self.diag = {n: _f((nL, nC)) for n in abi.DMS_DIAG}
+        self.diag = {n: _f((nL, nC)) for n in abi.DMS_DIAG} if diagnostics else {}
         self.flux_diag = {n: _f((nC,)) for n in abi.DMS_FLUX_DIAG}
 
     def c_input(self):
@@ -167,7 +183,7 @@ class DmsColumns:
         return s
 
     def copy(self):
-        o = DmsColumns(self.nLevelsMax, self.nColumnsMax, self.nColumns)
+        o = DmsColumns(self.nLevelsMax, self.nColumnsMax, self.nColumns, diagnostics=bool(self.diag))
         for n in ("DMS_tracers", "cell_thickness", "number_of_active_levels", "DMS_tendencies"):
             getattr(o, n)[...] = getattr(self, n)
         for d in ("forcing", "diag", "flux_diag"):
@@ -178,15 +194,19 @@ class DmsColumns:
 
 
 class MacrosColumns:
-    def __init__(self, nLevelsMax, nColumnsMax, nColumns=None):
+    def __init__(self, nLevelsMax, nColumnsMax, nColumns=None, alloc=None, diagnostics=True):
         nL, nC = int(nLevelsMax), int(nColumnsMax)
         self.nLevelsMax, self.nColumnsMax = nL, nC
         self.nColumns = nC if nColumns is None else int(nColumns)
+        _g = globals()["_f"]
+
+        def _f(shape, dtype=np.float64):
+            return _g(shape, alloc, dtype)
         self.MACROS_tracers = _f((nL, nC, abi.MACROS_TRACER_CNT))
         self.cell_thickness = _f((nL, nC))
-        self.number_of_active_levels = np.zeros((nC,), dtype=np.int32)
+        self.number_of_active_levels = _f((nC,), np.int32)
         self.MACROS_tendencies = _f((nL, nC, abi.MACROS_TRACER_CNT))
-        self.diag = {n: _f((nL, nC)) for n in abi.MACROS_DIAG}
+        self.diag = {n: _f((nL, nC)) for n in abi.MACROS_DIAG} if diagnostics else {}
 
     def c_input(self):
         s = abi.MacrosInput()
@@ -208,7 +228,7 @@ class MacrosColumns:
         return s
 
     def copy(self):
-        o = MacrosColumns(self.nLevelsMax, self.nColumnsMax, self.nColumns)
+        o = MacrosColumns(self.nLevelsMax, self.nColumnsMax, self.nColumns, diagnostics=bool(self.diag))
         for n in ("MACROS_tracers", "cell_thickness", "number_of_active_levels",
                   "MACROS_tendencies"):
             getattr(o, n)[...] = getattr(self, n)
@@ -248,12 +268,12 @@ SEED_CO2 = 0x0B6C0001
 
 def synth_fill(bgc=None, dms=None, macros=None, *, bgc_ind, dms_ind=None, macros_ind=None,
                seed=SEED_COLUMNS, column0=0, nlev_active=None, ragged=False, jitter=True,
-               nthreads=0):
+               nthreads=0, soa=False):
     """Fill the *input* and *forcing* members of the given containers in place
     (Fortran layout) with the synthetic columns of SURVEY.md 8(d)."""
     ref = bgc or dms or macros
     sp = _SynthSpec(seed, ref.nLevelsMax, ref.nColumnsMax, ref.nColumns, column0,
-                    nlev_active or ref.nLevelsMax, int(ragged), 0, int(jitter), nthreads)
+                    nlev_active or ref.nLevelsMax, int(ragged), int(soa), int(jitter), nthreads)
     keep = []
 
     def byref_or_null(s):

@@ -105,7 +105,43 @@ struct bgc_ctx {
   std::map<std::string, DevBuf> arena;      // persistent device buffers (host-layout mode, scratch)
   ncclComm_t comm = nullptr;
   int nranks = 1;
+  // launch accounting (always on) and optional per-kernel CUDA-event timing
+  unsigned long long launches[BGC_KERNEL_ID_COUNT] = {0};
+  bool timing_on = false;
+  struct Span { int kid; cudaEvent_t a, b; };
+  std::vector<Span> spans;          // recorded, not yet resolved
+  std::vector<cudaEvent_t> ev_pool;
+  double timed_ms[BGC_KERNEL_ID_COUNT] = {0};
+  unsigned long long timed_launches[BGC_KERNEL_ID_COUNT] = {0};
 };
+
+// Every kernel launch of the library goes through LAUNCH: it counts `n` launches
+// under kernel id `kid` and, when timing is enabled, brackets them with CUDA
+// events on the ctx stream (resolved lazily in bgc_timing_get).
+static int span_begin(bgc_ctx *c, int kid, cudaEvent_t *a, cudaEvent_t *b) {
+  auto get = [&](cudaEvent_t *e) -> int {
+    if (!c->ev_pool.empty()) { *e = c->ev_pool.back(); c->ev_pool.pop_back(); return BGC_OK; }
+    cudaError_t r = cudaEventCreate(e);
+    if (r != cudaSuccess) return BGC_ERR_CUDA;
+    return BGC_OK;
+  };
+  if (get(a) != BGC_OK || get(b) != BGC_OK) return BGC_ERR_CUDA;
+  (void)kid;
+  return cudaEventRecord(*a, c->stream) == cudaSuccess ? BGC_OK : BGC_ERR_CUDA;
+}
+#define LAUNCH(kid, n, call)                                                                  \
+  do {                                                                                        \
+    cudaEvent_t ea_ = nullptr, eb_ = nullptr;                                                 \
+    if (c->timing_on && span_begin(c, (kid), &ea_, &eb_) != BGC_OK)                           \
+      return fail(BGC_ERR_CUDA, "cannot create timing events");                               \
+    CU(call);                                                                                 \
+    c->launches[(kid)] += (n);                                                                \
+    if (c->timing_on) {                                                                       \
+      CU(cudaEventRecord(eb_, c->stream));                                                    \
+      c->spans.push_back({(kid), ea_, eb_});                                                  \
+      c->timed_launches[(kid)] += (n);                                                        \
+    }                                                                                         \
+  } while (0)
 
 // Which ctx's tables currently sit in each device's __constant__ memory.
 static std::map<int, std::pair<const bgc_ctx *, unsigned long long>> g_const_owner_bgc, g_const_owner_dms,
@@ -174,6 +210,8 @@ extern "C" int bgc_ctx_destroy(bgc_ctx *c) {
   for (auto &kv : c->arena) if (kv.second.p) cudaFree(kv.second.p);
   cudaFree(c->d_status); cudaFree(c->d_inventory); cudaFree(c->d_inv_tmp); cudaFree(c->d_partials);
   cudaFree((void *)c->d_colptrs);
+  for (auto &sp : c->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+  for (auto e : c->ev_pool) cudaEventDestroy(e);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   std::lock_guard<std::mutex> lock(g_mu);
   g_versions.erase(c);
@@ -206,6 +244,51 @@ extern "C" int bgc_get_status(bgc_ctx *c, BgcStatus *out, int reset) {
   CU(cudaStreamSynchronize(c->stream));
   out->no_bracket = h[0]; out->no_convergence = h[1]; out->poc_error = h[2]; out->nonfinite = h[3];
   return BGC_OK;
+}
+
+// ------------------------------------------------------------------ launch accounting / timing
+static int resolve_spans(bgc_ctx *c) {
+  if (c->spans.empty()) return BGC_OK;
+  CU(cudaStreamSynchronize(c->stream));
+  for (auto &sp : c->spans) {
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, sp.a, sp.b));
+    c->timed_ms[sp.kid] += (double)ms;
+    c->ev_pool.push_back(sp.a);
+    c->ev_pool.push_back(sp.b);
+  }
+  c->spans.clear();
+  return BGC_OK;
+}
+
+extern "C" int bgc_timing_enable(bgc_ctx *c, int enable) {
+  RC(use_device(c));
+  RC(resolve_spans(c));
+  c->timing_on = enable != 0;
+  return BGC_OK;
+}
+extern "C" int bgc_timing_reset(bgc_ctx *c) {
+  RC(use_device(c));
+  RC(resolve_spans(c));
+  for (int i = 0; i < BGC_KERNEL_ID_COUNT; ++i) { c->timed_ms[i] = 0.0; c->timed_launches[i] = 0; c->launches[i] = 0; }
+  return BGC_OK;
+}
+extern "C" int bgc_timing_get(bgc_ctx *c, int kernel_id, double *total_ms, unsigned long long *timed_launches,
+                              unsigned long long *launches) {
+  RC(use_device(c));
+  if (kernel_id < 0 || kernel_id >= BGC_KERNEL_ID_COUNT) return fail(BGC_ERR_ARG, "bad kernel id %d", kernel_id);
+  RC(resolve_spans(c));
+  if (total_ms) *total_ms = c->timed_ms[kernel_id];
+  if (timed_launches) *timed_launches = c->timed_launches[kernel_id];
+  if (launches) *launches = c->launches[kernel_id];
+  return BGC_OK;
+}
+extern "C" const char *bgc_kernel_name(int kernel_id) {
+  static const char *names[BGC_KERNEL_ID_COUNT] = {
+      "co3_cells_kernel", "eco_columns_kernel", "dms_columns_kernel", "macros_cells_kernel",
+      "surface_fluxes_kernel", "dms_surface_kernel", "co2calc_points_kernel", "inventory kernels",
+      "transpose_kernel"};
+  return (kernel_id >= 0 && kernel_id < BGC_KERNEL_ID_COUNT) ? names[kernel_id] : "";
 }
 
 // ------------------------------------------------------------------ parameters
@@ -337,7 +420,7 @@ static int up_k(bgc_ctx *c, const char *key, const double *host, int nL, int nC,
   for (int s0 = 0; s0 < nSlabs; s0 += kStageSlabs) {
     const int ns = (nSlabs - s0 < kStageSlabs) ? nSlabs - s0 : kStageSlabs;
     CU(cudaMemcpyAsync(stage, host + (size_t)s0 * n2, (size_t)ns * n2 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    CU(bgc::launch_transpose(stage, dev + (size_t)s0 * n2, nL, nC, ns, c->stream));
+    LAUNCH(BGC_K_TRANSPOSE, 1, bgc::launch_transpose(stage, dev + (size_t)s0 * n2, nL, nC, ns, c->stream));
   }
   return BGC_OK;
 }
@@ -348,7 +431,7 @@ static int down_k(bgc_ctx *c, const double *dev, double *host, int nL, int nC, i
   RC(stage_buf(c, n2, &stage));
   for (int s0 = 0; s0 < nSlabs; s0 += kStageSlabs) {
     const int ns = (nSlabs - s0 < kStageSlabs) ? nSlabs - s0 : kStageSlabs;
-    CU(bgc::launch_transpose(dev + (size_t)s0 * n2, stage, nC, nL, ns, c->stream));
+    LAUNCH(BGC_K_TRANSPOSE, 1, bgc::launch_transpose(dev + (size_t)s0 * n2, stage, nC, nL, ns, c->stream));
     CU(cudaMemcpyAsync(host + (size_t)s0 * n2, stage, (size_t)ns * n2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   }
   return BGC_OK;
@@ -379,6 +462,10 @@ __global__ void inv_accumulate_kernel(double *inv, const double *tmp, int off, i
   const int i = threadIdx.x;
   if (i < n) inv[off + i] += tmp[i];
 }
+static cudaError_t inv_accumulate(double *inv, const double *tmp, int off, int n, cudaStream_t s) {
+  inv_accumulate_kernel<<<1, 64, 0, s>>>(inv, tmp, off, n);
+  return cudaGetLastError();
+}
 
 static int inventory_add(bgc_ctx *c, const double *tend, const double *dz, const int *kmax, int nL, int nC, int nCols,
                          int nTracers, int off, bool count) {
@@ -389,10 +476,9 @@ static int inventory_add(bgc_ctx *c, const double *tend, const double *dz, const
   bgc::InventoryArgs ia;
   ia.nL = nL; ia.nC = nC; ia.nColumns = nCols; ia.nTracers = nTracers;
   ia.tend = tend; ia.dz = dz; ia.kmax = kmax; ia.partials = partials; ia.out = c->d_inv_tmp; ia.count = count ? 1 : 0;
-  CU(bgc::launch_inventory(ia, c->stream));
-  inv_accumulate_kernel<<<1, 64, 0, c->stream>>>(c->d_inventory, c->d_inv_tmp, off, nTracers);
-  if (count) inv_accumulate_kernel<<<1, 64, 0, c->stream>>>(c->d_inventory, c->d_inv_tmp + nTracers, 60, 2);
-  CU(cudaGetLastError());
+  LAUNCH(BGC_K_INVENTORY, 2, bgc::launch_inventory(ia, c->stream));
+  LAUNCH(BGC_K_INVENTORY, 1, inv_accumulate(c->d_inventory, c->d_inv_tmp, off, nTracers, c->stream));
+  if (count) LAUNCH(BGC_K_INVENTORY, 1, inv_accumulate(c->d_inventory, c->d_inv_tmp + nTracers, 60, 2, c->stream));
   return BGC_OK;
 }
 
@@ -457,7 +543,7 @@ static int source_sink_device(bgc_ctx *c, const BgcInput *in, const BgcForcing *
     if (!ca.sat_calc) RC(arena_d(c, "scratch_satc", n2, &ca.sat_calc));
     if (!ca.sat_arag) RC(arena_d(c, "scratch_sata", n2, &ca.sat_arag));
   }
-  CU(bgc::launch_co3_cells(ca, c->stream));
+  LAUNCH(BGC_K_CO3_CELLS, 1, bgc::launch_co3_cells(ca, c->stream));
 
   // ecosystem + particle sweep, column-parallel
   bgc::EcoArgs ea;
@@ -478,7 +564,7 @@ static int source_sink_device(bgc_ctx *c, const BgcInput *in, const BgcForcing *
   // declared in BGC_diagnostics_type but never zeroed nor written by the reference
   ea.d.diag_POC_ACCUM = ea.d.diag_DONr_remin = ea.d.diag_DOPr_remin = nullptr;
   ea.status = c->d_status;
-  CU(bgc::launch_eco_columns(ea, any_diag, c->stream));
+  LAUNCH(BGC_K_ECO_COLUMNS, 1, bgc::launch_eco_columns(ea, any_diag, c->stream));
 
   RC(inventory_add(c, out->BGC_tendencies, in->cell_thickness, in->number_of_active_levels, nL, nC, nCols,
                    BGC_TRACER_CNT, 0, true));
@@ -489,9 +575,8 @@ static int source_sink_device(bgc_ctx *c, const BgcInput *in, const BgcForcing *
     RC(arena_d(c, "inv_partials", (size_t)bgc::inventory_grid(nC) * 40, &partials));
     CU(cudaMemcpyAsync((void *)c->d_colptrs, cols, sizeof cols, cudaMemcpyHostToDevice, c->stream));
     CU(cudaStreamSynchronize(c->stream));   // `cols` lives on this stack frame
-    CU(bgc::launch_column_sums(c->d_colptrs, 8, nCols, partials, c->d_inv_tmp, c->stream));
-    inv_accumulate_kernel<<<1, 64, 0, c->stream>>>(c->d_inventory, c->d_inv_tmp, 52, 8);
-    CU(cudaGetLastError());
+    LAUNCH(BGC_K_INVENTORY, 2, bgc::launch_column_sums(c->d_colptrs, 8, nCols, partials, c->d_inv_tmp, c->stream));
+    LAUNCH(BGC_K_INVENTORY, 1, inv_accumulate(c->d_inventory, c->d_inv_tmp, 52, 8, c->stream));
   }
   return BGC_OK;
 }
@@ -580,7 +665,7 @@ static int surface_fluxes_device(bgc_ctx *c, const BgcInput *in, BgcForcing *fo,
   sa.f = *fo;
   if (diag) sa.d = *diag; else memset(&sa.d, 0, sizeof sa.d);
   sa.status = c->d_status;
-  CU(bgc::launch_surface_fluxes(sa, c->stream));
+  LAUNCH(BGC_K_SURFACE_FLUXES, 1, bgc::launch_surface_fluxes(sa, c->stream));
   return BGC_OK;
 }
 
@@ -651,7 +736,7 @@ extern "C" int bgc_co2calc_points(bgc_ctx *c, int n, const double *depth, const 
     a.depth = depth; a.temp = temp; a.salt = salt; a.dic = dic; a.ta = ta; a.pt = pt; a.sit = sit;
     a.phlo = phlo; a.phhi = phhi; a.xco2 = xco2; a.atmpres = atmpres;
     a.ph = ph; a.co2star = co2star; a.dco2star = dco2star; a.pco2surf = pco2surf; a.dpco2 = dpco2;
-    CU(bgc::launch_co2calc_points(a, c->stream));
+    LAUNCH(BGC_K_CO2CALC_POINTS, 1, bgc::launch_co2calc_points(a, c->stream));
     return BGC_OK;
   }
   if (mem_space != BGC_MEM_HOST_FORTRAN) return fail(BGC_ERR_ARG, "unknown mem_space %d", mem_space);
@@ -667,7 +752,7 @@ extern "C" int bgc_co2calc_points(bgc_ctx *c, int n, const double *depth, const 
   a.phhi = in_dev + 7 * (size_t)n; a.xco2 = in_dev + 8 * (size_t)n; a.atmpres = in_dev + 9 * (size_t)n;
   a.ph = out_dev; a.co2star = out_dev + (size_t)n; a.dco2star = out_dev + 2 * (size_t)n;
   a.pco2surf = out_dev + 3 * (size_t)n; a.dpco2 = out_dev + 4 * (size_t)n;
-  CU(bgc::launch_co2calc_points(a, c->stream));
+  LAUNCH(BGC_K_CO2CALC_POINTS, 1, bgc::launch_co2calc_points(a, c->stream));
   double *dst[5] = {ph, co2star, dco2star, pco2surf, dpco2};
   for (int i = 0; i < 5; ++i) CU(cudaMemcpyAsync(dst[i], out_dev + (size_t)i * n, b, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
@@ -686,7 +771,7 @@ static int dms_source_sink_device(bgc_ctx *c, const DmsInput *in, const DmsForci
   a.tracers = in->DMS_tracers; a.dz = in->cell_thickness; a.kmax = in->number_of_active_levels;
   a.sst = fo->SST; a.sw_flux = fo->ShortWaveFlux_surface; a.tend = out->DMS_tendencies;
   if (diag) a.d = *diag; else memset(&a.d, 0, sizeof a.d);
-  CU(bgc::launch_dms_columns(a, c->stream));
+  LAUNCH(BGC_K_DMS_COLUMNS, 1, bgc::launch_dms_columns(a, c->stream));
   RC(inventory_add(c, out->DMS_tendencies, in->cell_thickness, in->number_of_active_levels, nL, nC, nCols,
                    DMS_TRACER_CNT, 30, false));
   return BGC_OK;
@@ -737,7 +822,7 @@ static int dms_surface_device(bgc_ctx *c, const DmsInput *in, DmsForcing *fo, Dm
   a.nL = nL; a.nC = nC; a.nColumns = nCols;
   a.tracers = in->DMS_tracers; a.f = *fo;
   if (diag) a.d = *diag; else memset(&a.d, 0, sizeof a.d);
-  CU(bgc::launch_dms_surface(a, c->stream));
+  LAUNCH(BGC_K_DMS_SURFACE, 1, bgc::launch_dms_surface(a, c->stream));
   return BGC_OK;
 }
 
@@ -791,7 +876,7 @@ static int macros_device(bgc_ctx *c, const MacrosInput *in, MacrosOutput *out, c
   a.nL = nL; a.nC = nC; a.nColumns = nCols;
   a.tracers = in->MACROS_tracers; a.kmax = in->number_of_active_levels; a.tend = out->MACROS_tendencies;
   if (diag) a.d = *diag; else memset(&a.d, 0, sizeof a.d);
-  CU(bgc::launch_macros_cells(a, c->stream));
+  LAUNCH(BGC_K_MACROS_CELLS, 1, bgc::launch_macros_cells(a, c->stream));
   RC(inventory_add(c, out->MACROS_tendencies, in->cell_thickness, in->number_of_active_levels, nL, nC, nCols,
                    MACROS_TRACER_CNT, 44, false));
   return BGC_OK;
@@ -887,12 +972,12 @@ extern "C" int bgc_host_unregister(void *ptr) {
 extern "C" int bgc_layout_to_soa(bgc_ctx *c, const double *dev_fortran, double *dev_soa, int nL, int nC, int nSlabs) {
   RC(use_device(c));
   if (!dev_fortran || !dev_soa) return fail(BGC_ERR_ARG, "null array");
-  CU(bgc::launch_transpose(dev_fortran, dev_soa, nL, nC, nSlabs, c->stream));
+  LAUNCH(BGC_K_TRANSPOSE, 1, bgc::launch_transpose(dev_fortran, dev_soa, nL, nC, nSlabs, c->stream));
   return BGC_OK;
 }
 extern "C" int bgc_layout_to_fortran(bgc_ctx *c, const double *dev_soa, double *dev_fortran, int nL, int nC, int nSlabs) {
   RC(use_device(c));
   if (!dev_fortran || !dev_soa) return fail(BGC_ERR_ARG, "null array");
-  CU(bgc::launch_transpose(dev_soa, dev_fortran, nC, nL, nSlabs, c->stream));
+  LAUNCH(BGC_K_TRANSPOSE, 1, bgc::launch_transpose(dev_soa, dev_fortran, nC, nL, nSlabs, c->stream));
   return BGC_OK;
 }

@@ -34,6 +34,7 @@ ABI_SYMBOLS = [
     "bgc_inventory_reset", "bgc_inventory_get", "bgc_inventory_device_ptr", "bgc_comm_unique_id",
     "bgc_comm_init_rank", "bgc_inventory_allreduce", "bgc_host_alloc", "bgc_host_free",
     "bgc_host_register", "bgc_host_unregister", "bgc_layout_to_soa", "bgc_layout_to_fortran",
+    "bgc_timing_enable", "bgc_timing_reset", "bgc_timing_get", "bgc_kernel_name",
 ]
 
 
@@ -56,8 +57,9 @@ def lib(flavour=None):
         L = C.CDLL(path)
         L.bgc_last_error.restype = C.c_char_p
         L.bgc_version.restype = C.c_char_p
+        L.bgc_kernel_name.restype = C.c_char_p
         for s in ABI_SYMBOLS:
-            if s not in ("bgc_last_error", "bgc_version"):
+            if s not in ("bgc_last_error", "bgc_version", "bgc_kernel_name"):
                 getattr(L, s).restype = C.c_int
         _libs[flavour] = L
     return _libs[flavour]
@@ -129,6 +131,24 @@ class Context:
         st = abi.BgcStatus()
         check(self.L, self.L.bgc_get_status(self.ptr, C.byref(st), C.c_int(int(reset))))
         return abi.struct_to_dict(st)
+
+    def timing_enable(self, on=True):
+        check(self.L, self.L.bgc_timing_enable(self.ptr, C.c_int(int(on))))
+
+    def timing_reset(self):
+        check(self.L, self.L.bgc_timing_reset(self.ptr))
+
+    def timing(self):
+        """{kernel name: (device ms under timing, timed launches, all launches)}"""
+        out = {}
+        for kid in range(abi.DEFINES["BGC_KERNEL_ID_COUNT"]):
+            ms, tl, nl = C.c_double(), C.c_ulonglong(), C.c_ulonglong()
+            check(self.L, self.L.bgc_timing_get(self.ptr, C.c_int(kid), C.byref(ms), C.byref(tl), C.byref(nl)))
+            out[self.L.bgc_kernel_name(C.c_int(kid)).decode()] = (ms.value, tl.value, nl.value)
+        return out
+
+    def launch_count(self):
+        return sum(v[2] for v in self.timing().values())
 
     def inventory_enable(self, on=True):
         check(self.L, self.L.bgc_inventory_enable(self.ptr, C.c_int(int(on))))
