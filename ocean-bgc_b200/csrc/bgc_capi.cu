@@ -6,7 +6,9 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <stdarg.h>
+#include <stddef.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <map>
 #include <mutex>
@@ -98,10 +100,8 @@ struct bgc_ctx {
   bool have_bgc = false, have_dms = false, have_macros = false;
   unsigned long long *d_status = nullptr;   // 4 counters
   double *d_inventory = nullptr;            // BGC_INVENTORY_LEN
-  double *d_inv_tmp = nullptr;              // 64
-  double *d_partials = nullptr;             // inventory stage-1 partials
-  const double **d_colptrs = nullptr;       // 8 pointers for the Jint sums
   bool inventory_on = false;
+  int eco_variant = 0;                      // launch shape of the column sweep (BGC_ECO_VARIANT, tuning only)
   std::map<std::string, DevBuf> arena;      // persistent device buffers (host-layout mode, scratch)
   ncclComm_t comm = nullptr;
   int nranks = 1;
@@ -188,15 +188,13 @@ extern "C" int bgc_ctx_create(int device, int nLevelsMax, int nColumnsMax, bgc_c
   c->device = device;
   c->nL = nLevelsMax;
   c->nC = nColumnsMax;
+  if (const char *v = getenv("BGC_ECO_VARIANT")) c->eco_variant = atoi(v);
   CU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
   c->stream = c->own_stream;
   CU(cudaMalloc(&c->d_status, 4 * sizeof(unsigned long long)));
   CU(cudaMemset(c->d_status, 0, 4 * sizeof(unsigned long long)));
   CU(cudaMalloc(&c->d_inventory, BGC_INVENTORY_LEN * sizeof(double)));
   CU(cudaMemset(c->d_inventory, 0, BGC_INVENTORY_LEN * sizeof(double)));
-  CU(cudaMalloc(&c->d_inv_tmp, 64 * sizeof(double)));
-  CU(cudaMalloc(&c->d_partials, (size_t)bgc::inventory_grid(nColumnsMax) * 40 * sizeof(double)));
-  CU(cudaMalloc(&c->d_colptrs, 8 * sizeof(double *)));
   { std::lock_guard<std::mutex> lock(g_mu); g_versions[c] = CtxVersions(); }
   *out = c;
   return BGC_OK;
@@ -208,8 +206,7 @@ extern "C" int bgc_ctx_destroy(bgc_ctx *c) {
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   cudaStreamSynchronize(c->stream);
   for (auto &kv : c->arena) if (kv.second.p) cudaFree(kv.second.p);
-  cudaFree(c->d_status); cudaFree(c->d_inventory); cudaFree(c->d_inv_tmp); cudaFree(c->d_partials);
-  cudaFree((void *)c->d_colptrs);
+  cudaFree(c->d_status); cudaFree(c->d_inventory);
   for (auto &sp : c->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
   for (auto e : c->ev_pool) cudaEventDestroy(e);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -458,27 +455,33 @@ static int check_dims(bgc_ctx *c, int nL, int nC, int nCols) {
 }
 
 // ------------------------------------------------------------------ inventory
-__global__ void inv_accumulate_kernel(double *inv, const double *tmp, int off, int n) {
-  const int i = threadIdx.x;
-  if (i < n) inv[off + i] += tmp[i];
-}
-static cudaError_t inv_accumulate(double *inv, const double *tmp, int off, int n, cudaStream_t s) {
-  inv_accumulate_kernel<<<1, 64, 0, s>>>(inv, tmp, off, n);
-  return cudaGetLastError();
-}
-
+// `slots`: the tracer slots (0-based) whose tendency can be non-zero; `off`: where the
+// module's tracers start in the inventory vector.  Slots not listed are identically
+// zero by construction of the reference (DMS_mod.F90:413, MACROS_mod.F90:267).
 static int inventory_add(bgc_ctx *c, const double *tend, const double *dz, const int *kmax, int nL, int nC, int nCols,
-                         int nTracers, int off, bool count) {
+                         const int *slots, int nSlots, int off, bool count, const double *const *colsum, int nColsum) {
   if (!c->inventory_on || !dz) return BGC_OK;
-  const size_t need = (size_t)bgc::inventory_grid(nC) * 40;
-  double *partials = nullptr;
-  RC(arena_d(c, "inv_partials", need, &partials));
   bgc::InventoryArgs ia;
-  ia.nL = nL; ia.nC = nC; ia.nColumns = nCols; ia.nTracers = nTracers;
-  ia.tend = tend; ia.dz = dz; ia.kmax = kmax; ia.partials = partials; ia.out = c->d_inv_tmp; ia.count = count ? 1 : 0;
+  memset(&ia, 0, sizeof ia);
+  ia.nL = nL; ia.nC = nC; ia.nColumns = nCols;
+  ia.tend = tend; ia.dz = dz; ia.kmax = kmax;
+  for (int g = 0; g < bgc::kInvMaxGroups; ++g)
+    for (int j = 0; j < bgc::kInvGroup; ++j) { ia.slot[g][j] = -1; ia.out_index[g][j] = -1; }
+  ia.count_out = count ? 60 : -1;
+  int g = 0, j = 0;
+  for (int i = 0; i < nSlots; ++i) {
+    const int cap = (g == 0 && count) ? bgc::kInvGroup - 2 : bgc::kInvGroup;
+    if (j == cap) { ++g; j = 0; }
+    if (g >= bgc::kInvMaxGroups) return fail(BGC_ERR_ARG, "inventory: too many tracer slots");
+    ia.slot[g][j] = slots[i]; ia.out_index[g][j] = off + slots[i]; ++j;
+  }
+  ia.nGroups = nSlots ? g + 1 : 0;
+  for (int q = 0; q < nColsum && q < bgc::kInvGroup; ++q) ia.colsum[q] = colsum[q];
+  ia.colsum_out = 52;
+  const size_t need = (size_t)bgc::inventory_grid(nCols) * (bgc::kInvMaxGroups + 1) * bgc::kInvGroup;
+  RC(arena_d(c, "inv_partials", need, &ia.partials));
+  ia.inventory = c->d_inventory;
   LAUNCH(BGC_K_INVENTORY, 2, bgc::launch_inventory(ia, c->stream));
-  LAUNCH(BGC_K_INVENTORY, 1, inv_accumulate(c->d_inventory, c->d_inv_tmp, off, nTracers, c->stream));
-  if (count) LAUNCH(BGC_K_INVENTORY, 1, inv_accumulate(c->d_inventory, c->d_inv_tmp + nTracers, 60, 2, c->stream));
   return BGC_OK;
 }
 
@@ -564,19 +567,34 @@ static int source_sink_device(bgc_ctx *c, const BgcInput *in, const BgcForcing *
   // declared in BGC_diagnostics_type but never zeroed nor written by the reference
   ea.d.diag_POC_ACCUM = ea.d.diag_DONr_remin = ea.d.diag_DOPr_remin = nullptr;
   ea.status = c->d_status;
-  LAUNCH(BGC_K_ECO_COLUMNS, 1, bgc::launch_eco_columns(ea, any_diag, c->stream));
+  // diag_mode 2 = every array the sweep owns is present -> unchecked stores.  The ten
+  // carbonate arrays belong to co3_cells_kernel and the three never-touched members of
+  // the reference type may be NULL without leaving that mode.
+  int diag_mode = 0;
+  if (any_diag) {
+    diag_mode = 2;
+    double *const *pp = (double *const *)&ea.d;
+    const size_t first_carb = offsetof(BgcDiagnostics, diag_CO3) / sizeof(double *);
+    const size_t last_carb = offsetof(BgcDiagnostics, diag_co3_sat_arag) / sizeof(double *);
+    const size_t untouched[3] = {offsetof(BgcDiagnostics, diag_POC_ACCUM) / sizeof(double *),
+                                 offsetof(BgcDiagnostics, diag_DONr_remin) / sizeof(double *),
+                                 offsetof(BgcDiagnostics, diag_DOPr_remin) / sizeof(double *)};
+    for (size_t i = 0; i < sizeof(BgcDiagnostics) / sizeof(double *); ++i) {
+      if (pp[i] || (i >= first_carb && i <= last_carb)) continue;
+      if (i == untouched[0] || i == untouched[1] || i == untouched[2]) continue;
+      diag_mode = 1;
+      break;
+    }
+  }
+  LAUNCH(BGC_K_ECO_COLUMNS, 1, bgc::launch_eco_columns(ea, diag_mode, c->eco_variant, c->stream));
 
-  RC(inventory_add(c, out->BGC_tendencies, in->cell_thickness, in->number_of_active_levels, nL, nC, nCols,
-                   BGC_TRACER_CNT, 0, true));
-  if (c->inventory_on && any_diag) {
+  if (c->inventory_on) {
+    int slots[BGC_TRACER_CNT];
+    for (int n = 0; n < BGC_TRACER_CNT; ++n) slots[n] = n;
     const double *cols[8] = {d.diag_Jint_Ctot, d.diag_Jint_100m_Ctot, d.diag_Jint_Ntot, d.diag_Jint_100m_Ntot,
                              d.diag_Jint_Ptot, d.diag_Jint_100m_Ptot, d.diag_Jint_Sitot, d.diag_Jint_100m_Sitot};
-    double *partials = nullptr;
-    RC(arena_d(c, "inv_partials", (size_t)bgc::inventory_grid(nC) * 40, &partials));
-    CU(cudaMemcpyAsync((void *)c->d_colptrs, cols, sizeof cols, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaStreamSynchronize(c->stream));   // `cols` lives on this stack frame
-    LAUNCH(BGC_K_INVENTORY, 2, bgc::launch_column_sums(c->d_colptrs, 8, nCols, partials, c->d_inv_tmp, c->stream));
-    LAUNCH(BGC_K_INVENTORY, 1, inv_accumulate(c->d_inventory, c->d_inv_tmp, 52, 8, c->stream));
+    RC(inventory_add(c, out->BGC_tendencies, in->cell_thickness, in->number_of_active_levels, nL, nC, nCols,
+                     slots, BGC_TRACER_CNT, 0, true, cols, 8));
   }
   return BGC_OK;
 }
@@ -772,8 +790,11 @@ static int dms_source_sink_device(bgc_ctx *c, const DmsInput *in, const DmsForci
   a.sst = fo->SST; a.sw_flux = fo->ShortWaveFlux_surface; a.tend = out->DMS_tendencies;
   if (diag) a.d = *diag; else memset(&a.d, 0, sizeof a.d);
   LAUNCH(BGC_K_DMS_COLUMNS, 1, bgc::launch_dms_columns(a, c->stream));
-  RC(inventory_add(c, out->DMS_tendencies, in->cell_thickness, in->number_of_active_levels, nL, nC, nCols,
-                   DMS_TRACER_CNT, 30, false));
+  {   // only DMS and DMSP have non-zero tendencies (DMS_mod.F90:413, :741-742)
+    const int slots[2] = {c->dms_tab.ind.dms_ind - 1, c->dms_tab.ind.dmsp_ind - 1};
+    RC(inventory_add(c, out->DMS_tendencies, in->cell_thickness, in->number_of_active_levels, nL, nC, nCols,
+                     slots, 2, 30, false, nullptr, 0));
+  }
   return BGC_OK;
 }
 
@@ -877,8 +898,11 @@ static int macros_device(bgc_ctx *c, const MacrosInput *in, MacrosOutput *out, c
   a.tracers = in->MACROS_tracers; a.kmax = in->number_of_active_levels; a.tend = out->MACROS_tendencies;
   if (diag) a.d = *diag; else memset(&a.d, 0, sizeof a.d);
   LAUNCH(BGC_K_MACROS_CELLS, 1, bgc::launch_macros_cells(a, c->stream));
-  RC(inventory_add(c, out->MACROS_tendencies, in->cell_thickness, in->number_of_active_levels, nL, nC, nCols,
-                   MACROS_TRACER_CNT, 44, false));
+  {   // only PROT, POLY and LIP have non-zero tendencies (MACROS_mod.F90:267, :389-391)
+    const int slots[3] = {c->macros_tab.ind.prot_ind - 1, c->macros_tab.ind.poly_ind - 1, c->macros_tab.ind.lip_ind - 1};
+    RC(inventory_add(c, out->MACROS_tendencies, in->cell_thickness, in->number_of_active_levels, nL, nC, nCols,
+                     slots, 3, 44, false, nullptr, 0));
+  }
   return BGC_OK;
 }
 

@@ -55,7 +55,10 @@ struct EcoArgs {
   BgcDiagnostics d;                      // carbonate + never-touched members nulled by the caller
   unsigned long long *status;
 };
-cudaError_t launch_eco_columns(const EcoArgs &a, bool any_diag, cudaStream_t s);
+// diag_mode: 0 = no diagnostic array, 1 = any subset (NULL-checked stores), 2 = every array
+// the kernel owns is present (unchecked stores).  variant selects the launch shape
+// (k_eco.cu: launch_diag); 0 = default.
+cudaError_t launch_eco_columns(const EcoArgs &a, int diag_mode, int variant, cudaStream_t s);
 
 // ---- surface fluxes, one thread per column
 struct SurfArgs {
@@ -108,19 +111,23 @@ cudaError_t launch_macros_cells(const MacrosArgs &a, cudaStream_t s);
 cudaError_t launch_transpose(const double *src, double *dst, int rows_fast_src, int cols_slow_src,
                              int nSlabs, cudaStream_t s);
 
-// ---- inventory: sum_col sum_k tend(n)*dz over active cells, deterministic
+// ---- inventory: sum_col sum_k tend(n)*dz over active cells (+ sums of per-column
+// diagnostics), deterministic, accumulated into the ctx inventory vector
+constexpr int kInvGroup = 8;        // values per group (tracer slots, or 6 slots + the two counters in group 0)
+constexpr int kInvMaxGroups = 6;
 struct InventoryArgs {
-  int nL, nC, nColumns, nTracers;
+  int nL, nC, nColumns, nGroups;
   const double *tend, *dz;
   const int *kmax;
-  double *partials;      // [gridDim][nTracers + 2]
-  double *out;           // nTracers (+ active cells, active columns when count != 0)
-  int count;
+  int slot[kInvMaxGroups][kInvGroup];        // 0-based tracer slot, -1 = unused
+  int out_index[kInvMaxGroups][kInvGroup];   // destination in the inventory vector
+  int count_out;                             // >= 0: group 0's last two values are (active cells, active columns)
+  const double *colsum[kInvGroup];           // per-column arrays summed as one extra group (NULL = unused)
+  int colsum_out;
+  double *partials;                          // [inventory_grid][groups][kInvGroup]
+  double *inventory;                         // accumulated into (+=)
 };
-int inventory_grid(int nC);
+int inventory_grid(int nColumns);
 cudaError_t launch_inventory(const InventoryArgs &a, cudaStream_t s);
-// sums of per-column diagnostics (Jint_*), deterministic
-cudaError_t launch_column_sums(const double *const *cols, int nArrays, int nColumns, double *partials,
-                               double *out, cudaStream_t s);
 
 }  // namespace bgc

@@ -9,17 +9,77 @@
 // zero fills (:570, :625-727) are folded into the same sweep: a cell is read
 // once and every output element is written exactly once.
 //
+// Code-footprint design.  The reference's per-cell arithmetic is ~9k SASS
+// instructions when the loop over the four functional groups is unrolled and
+// every divide is the IEEE sequence: a 200 KB loop body that streams through the
+// 32 KB L1.5 instruction cache once per level per warp (ncu on the first version:
+// "no instruction" was the top stall, 4.8 cycles per issue).  Here
+//   * the functional-group loop is ROLLED: its body exists once, the group's
+//     parameters come from __constant__ memory by run-time index, the group's
+//     tracers are staged in shared memory, and every SUM(x(:)) of the reference
+//     is a running accumulator (same left-to-right order as Fortran's SUM);
+//   * divides use bgc_math.cuh (reciprocal seed + Newton, shared reciprocals where
+//     the reference divides several numerators by one denominator);
+//   * a block-wide barrier per level keeps the warps of a block on the same
+//     stretch of code so that one I-cache fill serves all of them.
+//
+// Input staging.  With ~8 resident warps per SM (255 registers per thread) nothing
+// hides an HBM round trip, and a level has ~8 dependent batches of loads.  So one
+// elected thread per block fetches the NEXT level's slab of every input array -
+// 27 tracers, T, S, zmid, dz, zbot, FESEDFLUX, CO3 and the two saturation values,
+// BLOCK consecutive columns = one contiguous BLOCK*8-byte run each - with
+// cp.async.bulk (the TMA unit's 1-D bulk copy) into a double-buffered shared-memory
+// stage, completion signalled on an mbarrier; the compute threads only ever read
+// shared memory.  Falls back to per-thread loads when the slabs are not 16-byte
+// aligned (odd nColumnsMax or a misaligned caller pointer).
+//
 // The carbonate solve of each cell has no vertical coupling and runs in the
 // cell-parallel kernel of k_co3.cu; this kernel only consumes CO3 and the two
 // saturation concentrations for the saturation-depth scan (:1003-1032).
 #include "bgc_kernels.cuh"
+#include "bgc_math.cuh"
 
 namespace bgc {
 
+// Quantities derived once per bgc_set_params from the parameter tables.
+struct EcoDerived {
+  double r_kNO3[4], r_kNH4[4], r_kPO4[4], r_kDOP[4];
+  double cks_kFe[4], r_cks_kFe[4], cksi_kFe[4], cksi_kSiO3[4], r_cksi_kSiO3[4];
+  double agg_max_dps[4], agg_min_dps[4];
+  double r_dTN[4], r_dTS[4];
+  double r_o2_min_delta;
+  double r_scalelen_dz[4];
+};
+
 __constant__ BgcTables c_eco;
+__constant__ EcoDerived c_der;
 
 cudaError_t upload_bgc_tables_eco(const BgcTables &t, cudaStream_t s) {
-  return cudaMemcpyToSymbolAsync(c_eco, &t, sizeof(BgcTables), 0, cudaMemcpyHostToDevice, s);
+  constexpr double dps = 1.0 / 86400.0;
+  EcoDerived d;
+  for (int a = 0; a < BGC_AUTOTROPH_CNT; ++a) {
+    const BgcAutotroph &at = t.a[a];
+    d.r_kNO3[a] = 1.0 / at.kNO3;
+    d.r_kNH4[a] = 1.0 / at.kNH4;
+    d.r_kPO4[a] = 1.0 / at.kPO4;
+    d.r_kDOP[a] = 1.0 / at.kDOP;
+    d.cks_kFe[a] = t.p.cks * at.kFe;
+    d.r_cks_kFe[a] = 1.0 / d.cks_kFe[a];
+    d.cksi_kFe[a] = t.p.cksi * at.kFe;
+    d.cksi_kSiO3[a] = t.p.cksi * at.kSiO3;
+    d.r_cksi_kSiO3[a] = 1.0 / d.cksi_kSiO3[a];
+    d.agg_max_dps[a] = at.agg_rate_max * dps;
+    d.agg_min_dps[a] = at.agg_rate_min * dps;
+    d.r_dTN[a] = 1.0 / (at.temp_thresN - at.temp_optN);
+    d.r_dTS[a] = 1.0 / (at.temp_thresS - at.temp_optS);
+  }
+  d.r_o2_min_delta = 1.0 / t.p.parm_o2_min_delta;
+  d.r_scalelen_dz[0] = 0.0;
+  for (int n = 1; n < 4; ++n) d.r_scalelen_dz[n] = 1.0 / (t.p.parm_scalelen_z[n] - t.p.parm_scalelen_z[n - 1]);
+  cudaError_t e = cudaMemcpyToSymbolAsync(c_eco, &t, sizeof(BgcTables), 0, cudaMemcpyHostToDevice, s);
+  if (e != cudaSuccess) return e;
+  // `d` is pageable stack memory: the runtime stages it before returning.
+  return cudaMemcpyToSymbolAsync(c_der, &d, sizeof(EcoDerived), 0, cudaMemcpyHostToDevice, s);
 }
 
 namespace {
@@ -64,6 +124,8 @@ constexpr double CaCO3_sp_thres = 4.0;
 constexpr double f_qsw_par = 0.45;
 constexpr double Tref = 30.0;
 constexpr double Q_10 = 1.5;
+constexpr double kLnQ10 = 0.4054651081081644;      // log(1.5), correctly rounded
+constexpr double kLn099 = -0.01005033585350145;    // log(0.99)
 constexpr double DOC_reminR = (1.0 / 250.0) * dps;
 constexpr double DON_reminR = (1.0 / 160.0) * dps;
 constexpr double DOFe_reminR = (1.0 / 160.0) * dps;
@@ -84,30 +146,96 @@ constexpr double P_iron_gamma = 0.0;
 
 constexpr int NA = BGC_AUTOTROPH_CNT;
 
-#define ST2(name, val) do { if (A.d.name) A.d.name[i2] = (val); } while (0)
-#define STA(name, a, val) do { if (A.d.name) A.d.name[i2 + (size_t)(a) * nLnC] = (val); } while (0)
-#define STC(name, val) do { if (A.d.name) A.d.name[col] = (val); } while (0)
-#define STCA(name, a, val) do { if (A.d.name) A.d.name[col + (size_t)(a) * (size_t)nC] = (val); } while (0)
+// DIAG: 0 = no diagnostic array, 1 = any subset (NULL checks), 2 = every array present
+#define HAS(name) (DIAG == 2 || A.d.name != nullptr)
+#define ST2(name, val) do { if (HAS(name)) A.d.name[i2] = (val); } while (0)
+#define STA(name, val) do { if (HAS(name)) A.d.name[ia] = (val); } while (0)
+#define STA_AT(name, a_, val) do { if (HAS(name)) A.d.name[i2 + (size_t)(a_) * nLnC] = (val); } while (0)
+#define STC(name, val) do { if (HAS(name)) A.d.name[col] = (val); } while (0)
+#define STCA(name, a_, val) do { if (HAS(name)) A.d.name[col + (size_t)(a_) * (size_t)nC] = (val); } while (0)
+
+// The (k,col) diagnostics this kernel owns: BGC_DIAG_K2_LIST minus the ten carbonate
+// arrays (written by co3_cells_kernel) and the three arrays the reference declares but
+// never zeroes nor writes (diag_POC_ACCUM, diag_DONr_remin, diag_DOPr_remin).
+#define ECO_DIAG_K2_LIST(X) \
+  X(diag_tot_Nfix) X(diag_O2_PRODUCTION) X(diag_O2_CONSUMPTION) X(diag_AOU) \
+  X(diag_PO4_RESTORE) X(diag_NO3_RESTORE) X(diag_SiO3_RESTORE) X(diag_PAR_avg) \
+  X(diag_POC_FLUX_IN) X(diag_POC_PROD) X(diag_POC_REMIN) \
+  X(diag_CaCO3_FLUX_IN) X(diag_CaCO3_PROD) X(diag_CaCO3_REMIN) X(diag_SiO2_FLUX_IN) \
+  X(diag_SiO2_PROD) X(diag_SiO2_REMIN) X(diag_dust_FLUX_IN) X(diag_dust_REMIN) \
+  X(diag_P_iron_FLUX_IN) X(diag_P_iron_PROD) X(diag_P_iron_REMIN) X(diag_auto_graze_TOT) \
+  X(diag_zoo_loss) X(diag_photoC_TOT) X(diag_photoC_NO3_TOT) X(diag_DOC_prod) \
+  X(diag_DOC_remin) X(diag_DON_prod) X(diag_DON_remin) X(diag_DOFe_prod) \
+  X(diag_DOFe_remin) X(diag_DOP_prod) X(diag_DOP_remin) X(diag_Fe_scavenge) \
+  X(diag_Fe_scavenge_rate) X(diag_NITRIF) X(diag_DENITRIF) \
+  X(diag_calcToSed) X(diag_pocToSed) X(diag_ponToSed) \
+  X(diag_popToSed) X(diag_bsiToSed) X(diag_dustToSed) X(diag_pfeToSed) \
+  X(diag_SedDenitrif) X(diag_OtherRemin) X(diag_tot_CaCO3_form)
+#define COUNT_ONE(name) +1
+static_assert((0 ECO_DIAG_K2_LIST(COUNT_ONE)) + 13 == (0 BGC_DIAG_K2_LIST(COUNT_ONE)),
+              "ECO_DIAG_K2_LIST is out of step with BGC_DIAG_K2_LIST");
 
 #define ZERO_K2(name) ST2(name, 0.0);
-#define ZERO_KA(name) { STA(name, 0, 0.0); STA(name, 1, 0.0); STA(name, 2, 0.0); STA(name, 3, 0.0); }
+#define ZERO_KA(name) { STA_AT(name, 0, 0.0); STA_AT(name, 1, 0.0); STA_AT(name, 2, 0.0); STA_AT(name, 3, 0.0); }
 #define ZERO_CA(name) { STCA(name, 0, 0.0); STCA(name, 1, 0.0); STCA(name, 2, 0.0); STCA(name, 3, 0.0); }
 #define ZERO_C1(name) STC(name, 0.0);
 
-template <bool DIAG>
-__global__ void __launch_bounds__(128)
-eco_columns_kernel(const __grid_constant__ EcoArgs A) {
-  const int col = blockIdx.x * blockDim.x + threadIdx.x;
-  const int nL = A.nL, nC = A.nC;
-  if (col >= nC) return;
-  const size_t nLnC = (size_t)nL * (size_t)nC;
+// Shared memory of a block, in rows of BLOCK doubles (one slot per thread):
+//   2 stages x R_ROWS   the level's input slab: rows 0..29 = tracer slots, then the rows below
+//   X_ROWS              per-thread scratch: Pprime(4); DIAG: the three per-group column
+//                       integrals (:1838-1846, :1268), 4 each
+//   2 mbarriers
+enum { R_T = BGC_TRACER_CNT, R_ZMID, R_DZ, R_ZBOT, R_FESED, R_S, R_CO3, R_SATC, R_SATA, R_ROWS };
+enum { X_PPRIME = 0, X_ZPHOTO = 4, X_ZNO3 = 8, X_ZCACO3 = 12, X_ROWS = 16 };
 
-  int kmax = (col < A.nColumns) ? A.kmax[col] : 0;
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "LAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra LAB_WAIT;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+// 1-D bulk copy global -> shared through the TMA unit (SASS: UBLKCP); bytes % 16 == 0,
+// both addresses 16-byte aligned; completion is counted on the mbarrier.
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <int DIAG, int BLOCK, int MINB, bool TMA>
+__global__ void __launch_bounds__(BLOCK, MINB)
+eco_columns_kernel(const __grid_constant__ EcoArgs A) {
+  extern __shared__ __align__(128) double smem[];
+  const int tid = threadIdx.x;
+  const int col0 = blockIdx.x * BLOCK;
+  const int col = col0 + tid;
+  const int nL = A.nL, nC = A.nC;
+  const bool in_range = col < nC;
+  const size_t nLnC = (size_t)nL * (size_t)nC;
+  double *const xs = smem + 2 * R_ROWS * BLOCK;                       // per-thread scratch rows
+  unsigned long long *const bars = (unsigned long long *)(xs + X_ROWS * BLOCK);
+#define XS(row) xs[(row) * BLOCK + tid]
+#define IN(row) st[(row) * BLOCK + tid]
+
+  int kmax = (in_range && col < A.nColumns) ? A.kmax[col] : 0;
   if (kmax > nL) kmax = nL;
   if (kmax < 0) kmax = 0;
 
   const BgcParams &P = c_eco.p;
   const BgcIndices &I = c_eco.ind;
+  const EcoDerived &D = c_der;
   const double epsC = P.epsC, epsTinv = P.epsTinv;
   const double T0K = P.T0_Kelvin_BGC;
 
@@ -133,147 +261,136 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
   double zmid_km1 = 0.0, zbot_km1 = 0.0;
   double tot_bSi_form = 0.0, tot_CaCO3_form_zint = 0.0, photoC_TOT_zint = 0.0,
          photoC_NO3_TOT_zint = 0.0, Chl_TOT_zint_100m = 0.0;
-  double CaCO3_form_zint[NA] = {0.0, 0.0, 0.0, 0.0}, photoC_zint[NA] = {0.0, 0.0, 0.0, 0.0},
-         photoC_NO3_zint[NA] = {0.0, 0.0, 0.0, 0.0};
   double JC = 0.0, JC100 = 0.0, JN = 0.0, JN100 = 0.0, JP = 0.0, JP100 = 0.0, JSi = 0.0, JSi100 = 0.0;
   double O2_min = 0.0, O2_min_depth = 0.0;
   unsigned poc_errors = 0;
+  if (DIAG) {
+#pragma unroll
+    for (int a = 0; a < NA; ++a) { XS(X_ZPHOTO + a) = 0.0; XS(X_ZNO3 + a) = 0.0; XS(X_ZCACO3 + a) = 0.0; }
+  }
 
-  const double *trc = A.tracers + col;
   double *tnd = A.tend + col;
+
+  // ---- deepest active level of the block: nothing below it is fetched
+  __shared__ int s_kmax_blk;
+  if (tid == 0) {
+    s_kmax_blk = 0;
+    if (TMA) { mbar_init(smem_u32(&bars[0]), 1); mbar_init(smem_u32(&bars[1]), 1); }
+  }
+  __syncthreads();
+  if (kmax > 0) atomicMax(&s_kmax_blk, kmax);
+  if (TMA && tid == 0) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+  const int kmax_blk = s_kmax_blk;
+  const unsigned slab_bytes = (unsigned)(min(BLOCK, nC - col0) * (int)sizeof(double));
+  // tracer slots the sweep never reads: DIC, ALK (carbonate kernel only) and DIC_ALT_CO2 (dead, :748)
+  const unsigned skip_slots = (1u << (I.dic_ind - 1)) | (1u << (I.alk_ind - 1)) | (1u << (I.dic_alt_co2_ind - 1));
+
+  // Fetch level `kk` of every input array into stage `kk & 1` (one elected thread).
+  auto fetch_level = [&](int kk) {
+    double *dst = smem + (size_t)(kk & 1) * R_ROWS * BLOCK;
+    const unsigned bar = smem_u32(&bars[kk & 1]);
+    const size_t off = (size_t)nC * (size_t)kk + (size_t)col0;
+    const int nrows = (BGC_TRACER_CNT - 3) + 5 + (DIAG ? 4 : 0);
+    mbar_expect_tx(bar, slab_bytes * (unsigned)nrows);
+    const double *src = A.tracers + off;
+#pragma unroll 1
+    for (int n = 0; n < BGC_TRACER_CNT; ++n, src += nLnC)
+      if (!((skip_slots >> n) & 1u)) bulk_g2s(smem_u32(dst + n * BLOCK), src, slab_bytes, bar);
+    bulk_g2s(smem_u32(dst + R_T * BLOCK), A.T + off, slab_bytes, bar);
+    bulk_g2s(smem_u32(dst + R_ZMID * BLOCK), A.zmid + off, slab_bytes, bar);
+    bulk_g2s(smem_u32(dst + R_DZ * BLOCK), A.dz + off, slab_bytes, bar);
+    bulk_g2s(smem_u32(dst + R_ZBOT * BLOCK), A.zbot + off, slab_bytes, bar);
+    bulk_g2s(smem_u32(dst + R_FESED * BLOCK), A.fesedflux + off, slab_bytes, bar);
+    if (DIAG) {
+      bulk_g2s(smem_u32(dst + R_S * BLOCK), A.S + off, slab_bytes, bar);
+      bulk_g2s(smem_u32(dst + R_CO3 * BLOCK), A.co3 + off, slab_bytes, bar);
+      bulk_g2s(smem_u32(dst + R_SATC * BLOCK), A.sat_calc + off, slab_bytes, bar);
+      bulk_g2s(smem_u32(dst + R_SATA * BLOCK), A.sat_arag + off, slab_bytes, bar);
+    }
+  };
+  if (TMA && tid == 0) {
+    if (kmax_blk > 0) fetch_level(0);
+    if (kmax_blk > 1) fetch_level(1);
+  }
 
   for (int k = 0; k < nL; ++k) {
     const size_t i2 = (size_t)col + (size_t)nC * (size_t)k;
     const size_t o2 = (size_t)nC * (size_t)k;   // offset of level k within one tracer slab
+    double *const st = smem + (size_t)(k & 1) * R_ROWS * BLOCK;
+
+    if (TMA) {
+      if (k < kmax_blk) mbar_wait(smem_u32(&bars[k & 1]), (unsigned)((k >> 1) & 1));
+    } else if (k < kmax) {
+      // fallback: every thread loads its own column's slab entries
+      const double *src = A.tracers + i2;
+#pragma unroll 1
+      for (int n = 0; n < BGC_TRACER_CNT; ++n, src += nLnC)
+        if (!((skip_slots >> n) & 1u)) IN(n) = *src;
+      IN(R_T) = A.T[i2]; IN(R_ZMID) = A.zmid[i2]; IN(R_DZ) = A.dz[i2]; IN(R_ZBOT) = A.zbot[i2];
+      IN(R_FESED) = A.fesedflux[i2];
+      if (DIAG) { IN(R_S) = A.S[i2]; IN(R_CO3) = A.co3[i2]; IN(R_SATC) = A.sat_calc[i2]; IN(R_SATA) = A.sat_arag[i2]; }
+    }
 
     if (k >= kmax) {
       // ---- inactive cell: the reference's whole-array zero fills
-#pragma unroll
-      for (int n = 0; n < BGC_TRACER_CNT; ++n) tnd[o2 + (size_t)n * nLnC] = 0.0;
-      if (DIAG) {
-        BGC_DIAG_K2_LIST(ZERO_K2)
-        BGC_DIAG_KA_LIST(ZERO_KA)
+      if (in_range) {
+#pragma unroll 6
+        for (int n = 0; n < BGC_TRACER_CNT; ++n) tnd[o2 + (size_t)n * nLnC] = 0.0;
+        if (DIAG) {
+          ECO_DIAG_K2_LIST(ZERO_K2)
+          BGC_DIAG_KA_LIST(ZERO_KA)
+        }
       }
-      continue;
-    }
+    } else {
 
-#define TR(ind_) fmax(0.0, trc[o2 + (size_t)((ind_) - 1) * nLnC])
+#define TR(ind_) fmax(0.0, IN((ind_) - 1))
 #define TEND(ind_) tnd[o2 + (size_t)((ind_) - 1) * nLnC]
 
     // ---- this level's inputs (setup_loop clamp folded in, :747-783)
-    const double TEMP = A.T[i2];
-    const double zmid = A.zmid[i2];
-    const double dz = A.dz[i2];
-    const double zbot = A.zbot[i2];
+    const double TEMP = IN(R_T);
+    const double zmid = IN(R_ZMID);
+    const double dz = IN(R_DZ);
+    const double zbot = IN(R_ZBOT);
     const double PO4_loc = TR(I.po4_ind), NO3_loc = TR(I.no3_ind), SiO3_loc = TR(I.sio3_ind),
                  NH4_loc = TR(I.nh4_ind), Fe_loc = TR(I.fe_ind), O2_loc = TR(I.o2_ind),
                  DOC_loc = TR(I.doc_ind), DON_loc = TR(I.don_ind), DOFe_loc = TR(I.dofe_ind),
                  DOP_loc = TR(I.dop_ind), DOPr_loc = TR(I.dopr_ind), DONr_loc = TR(I.donr_ind),
                  zooC_loc = TR(I.zooC_ind);
-    double aChl[NA], aC[NA], aFe[NA], aSi[NA], aCaCO3[NA];
-#pragma unroll
-    for (int a = 0; a < NA; ++a) {
-      const BgcAutotroph &at = c_eco.a[a];
-      aChl[a] = TR(at.Chl_ind);
-      aC[a] = TR(at.C_ind);
-      aFe[a] = TR(at.Fe_ind);
-      aSi[a] = (at.Si_ind > 0) ? TR(at.Si_ind) : 0.0;
-      aCaCO3[a] = (at.CaCO3_ind > 0) ? TR(at.CaCO3_ind) : 0.0;
-    }
-
-    // ---- zero mask (:826-844)
-#pragma unroll
-    for (int a = 0; a < NA; ++a) {
-      const BgcAutotroph &at = c_eco.a[a];
-      bool zero_mask = aChl[a] == 0.0 || aC[a] == 0.0 || aFe[a] == 0.0;
-      if (at.Si_ind > 0) zero_mask = zero_mask || aSi[a] == 0.0;
-      if (zero_mask) {
-        aChl[a] = 0.0; aC[a] = 0.0; aFe[a] = 0.0; aSi[a] = 0.0; aCaCO3[a] = 0.0;
-      }
-    }
-
-    // ---- incoming quotas and growth quotas (:850-898)
-    double thetaC[NA], Qfe[NA], Qsi[NA], gQfe[NA], gQsi[NA], QCaCO3[NA];
-#pragma unroll
-    for (int a = 0; a < NA; ++a) {
-      const BgcAutotroph &at = c_eco.a[a];
-      const double Cden = aC[a] + epsC;
-      thetaC[a] = aChl[a] / Cden;
-      Qfe[a] = aFe[a] / Cden;
-      Qsi[a] = 0.0; gQsi[a] = 0.0; QCaCO3[a] = 0.0;
-      if (at.Si_ind > 0) Qsi[a] = fmin(aSi[a] / Cden, gQsi_max);
-
-      gQfe[a] = at.gQfe_0;
-      if (Fe_loc < P.cks * at.kFe) {
-        gQfe[a] = fmax((gQfe[a] * Fe_loc / (P.cks * at.kFe)), at.gQfe_min);
-      }
-      if (at.Si_ind > 0) {
-        double g = gQsi_0;
-        if ((Fe_loc < P.cksi * at.kFe) && (Fe_loc > 0.0) && (SiO3_loc > (P.cksi * at.kSiO3))) {
-          g = fmin((g * P.cksi * at.kFe / Fe_loc), gQsi_max);
-        }
-        if (Fe_loc == 0.0) g = gQsi_max;
-        if (SiO3_loc < (P.cksi * at.kSiO3)) {
-          g = fmax((g * SiO3_loc / (P.cksi * at.kSiO3)), gQsi_min);
-        }
-        gQsi[a] = g;
-      }
-      if (at.CaCO3_ind > 0) {
-        QCaCO3[a] = aCaCO3[a] / Cden;
-        if (QCaCO3[a] > QCaCO3_max) QCaCO3[a] = QCaCO3_max;
-      }
-    }
-
-    // ---- PAR (Morel & Maritorena 2001), :907-924
-    const double PAR_in = PAR_out;
-    double KPARdz;
-    {
-      double s = 0.0;
-#pragma unroll
-      for (int a = 0; a < NA; ++a) s = s + aChl[a];
-      const double w = fmax(s, 0.02);
-      if (w < 0.13224) KPARdz = 0.000919 * pow(w, 0.3536);
-      else             KPARdz = 0.001131 * pow(w, 0.4562);
-    }
-    KPARdz = KPARdz * dz;
-    const double eKPAR = exp(-KPARdz);
-    PAR_out = PAR_in * eKPAR;
-    const double PAR_avg = PAR_in * (1.0 - eKPAR) / KPARdz;
-
-    // ---- saturation-depth scan (:1003-1032); CO3 & saturation values come from k_co3
-    if (DIAG) {
-      const double CO3 = A.co3[i2], sat_c = A.sat_calc[i2], sat_a = A.sat_arag[i2];
-      if (k == 0) {
-        ZSATCALC = (CO3 > sat_c) ? -1.0 : 0.0;
-        ZSATARAG = (CO3 > sat_a) ? -1.0 : 0.0;
-      } else {
-        const double w4 = zmid_km1 + (zmid - zmid_km1);
-        if (ZSATCALC == -1.0 && CO3 <= sat_c)
-          ZSATCALC = w4 * CALC_ANOM_km1 / (CALC_ANOM_km1 - (CO3 - sat_c));
-        if (ZSATARAG == -1.0 && CO3 <= sat_a)
-          ZSATARAG = w4 * ARAG_ANOM_km1 / (ARAG_ANOM_km1 - (CO3 - sat_a));
-        if (ZSATCALC == -1.0 && k == kmax - 1) ZSATCALC = zbot;
-        if (ZSATARAG == -1.0 && k == kmax - 1) ZSATARAG = zbot;
-      }
-      CALC_ANOM_km1 = CO3 - sat_c;
-      ARAG_ANOM_km1 = CO3 - sat_a;
-    }
+    const double fesed = IN(R_FESED);
 
     // ---- temperature function, loss thresholds (:1041-1094)
-    const double Tfunc = pow(Q_10, ((TEMP + T0K) - (Tref + T0K)) / 10.0);
-
+    const double Tfunc = fpow_base(Q_10, kLnQ10, cdiv(((TEMP + T0K) - (Tref + T0K)), 10.0, 0.1));
     double f_loss_thres;
     if (zmid > thres_z1) {
-      if (zmid < thres_z2) f_loss_thres = (thres_z2 - zmid) / (thres_z2 - thres_z1);
+      if (zmid < thres_z2) f_loss_thres = cdiv((thres_z2 - zmid), (thres_z2 - thres_z1), 1.0 / (thres_z2 - thres_z1));
       else                 f_loss_thres = 0.0;
     } else {
       f_loss_thres = 1.0;
     }
 
-    double Pprime[NA];
+    const double ztop = (k > 0) ? zbot_km1 : 0.0;
+    const double pt100 = fmax(fmin(100.0e2 - ztop, dz), 0.0);   // upper-100 m part of this layer (:1880-1885)
+
+    // ---- functional-group tracers: clamp, zero mask (:826-844), Pprime (:1083-1094);
+    //      staged in shared memory for the rolled group loop below
+    double Chl_sum = 0.0;
 #pragma unroll
     for (int a = 0; a < NA; ++a) {
       const BgcAutotroph &at = c_eco.a[a];
+      double vChl = TR(at.Chl_ind), vC = TR(at.C_ind), vFe = TR(at.Fe_ind);
+      double vSi = (at.Si_ind > 0) ? TR(at.Si_ind) : 0.0;
+      double vCa = (at.CaCO3_ind > 0) ? TR(at.CaCO3_ind) : 0.0;
+      bool zero_mask = vChl == 0.0 || vC == 0.0 || vFe == 0.0;
+      if (at.Si_ind > 0) zero_mask = zero_mask || vSi == 0.0;
+      if (zero_mask) { vChl = 0.0; vC = 0.0; vFe = 0.0; vSi = 0.0; vCa = 0.0; }
+      // masked values go back into the stage rows, where the rolled loop picks them up
+      IN(at.Chl_ind - 1) = vChl; IN(at.C_ind - 1) = vC; IN(at.Fe_ind - 1) = vFe;
+      if (at.Si_ind > 0) IN(at.Si_ind - 1) = vSi;
+      if (at.CaCO3_ind > 0) IN(at.CaCO3_ind - 1) = vCa;
+      Chl_sum = Chl_sum + vChl;
+      if (DIAG) Chl_TOT_zint_100m = Chl_TOT_zint_100m + vChl * pt100;
+
       double C_loss_thres = f_loss_thres * at.loss_thres;
       if (at.temp_function == BGC_TFNC_Q10) {
         if (TEMP < at.temp_thres) C_loss_thres = f_loss_thres * at.loss_thres2;
@@ -281,225 +398,399 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
         const double tmpTmax = north ? at.temp_thresN : at.temp_thresS;
         if (TEMP > tmpTmax) C_loss_thres = f_loss_thres * at.loss_thres2;
       }
-      Pprime[a] = fmax(aC[a] - C_loss_thres, 0.0);
+      XS(X_PPRIME + a) = fmax(vC - C_loss_thres, 0.0);
     }
 
-    // ---- per functional group: uptake, photosynthesis, losses, grazing, routing (:1107-1388)
-    double NO3_V[NA], NH4_V[NA], PO4_V[NA], DOP_V[NA], auto_graze[NA], auto_graze_zoo[NA],
-           auto_graze_poc[NA], auto_graze_doc[NA], auto_graze_dic[NA], auto_loss[NA],
-           auto_loss_poc[NA], auto_loss_doc[NA], auto_loss_dic[NA], auto_agg[NA], photoC[NA],
-           photoFe[NA], photoSi[NA], CaCO3_PROD[NA], photoacc[NA], Nfix[NA], Nexcrete[NA],
-           remaining_P_dop[NA], remaining_P_dip[NA], photoC_NO3[NA];
-    double tot_CaCO3_form = 0.0, tot_Nfix = 0.0;
+    // ---- PAR (Morel & Maritorena 2001), :907-924
+    const double PAR_in = PAR_out;
+    double KPARdz;
+    {
+      const double w = fmax(Chl_sum, 0.02);
+      if (w < 0.13224) KPARdz = 0.000919 * fpow(w, 0.3536);
+      else             KPARdz = 0.001131 * fpow(w, 0.4562);
+    }
+    KPARdz = KPARdz * dz;
+    const double eKPAR = exp(-KPARdz);
+    PAR_out = PAR_in * eKPAR;
+    const double PAR_avg = fdiv(PAR_in * (1.0 - eKPAR), KPARdz);
 
-#pragma unroll
+    // ---- saturation-depth scan (:1003-1032); CO3 & saturation values come from k_co3
+    if (DIAG) {
+      const double CO3 = IN(R_CO3), sat_c = IN(R_SATC), sat_a = IN(R_SATA);
+      if (k == 0) {
+        ZSATCALC = (CO3 > sat_c) ? -1.0 : 0.0;
+        ZSATARAG = (CO3 > sat_a) ? -1.0 : 0.0;
+      } else {
+        const double w4 = zmid_km1 + (zmid - zmid_km1);
+        if (ZSATCALC == -1.0 && CO3 <= sat_c)
+          ZSATCALC = fdiv(w4 * CALC_ANOM_km1, (CALC_ANOM_km1 - (CO3 - sat_c)));
+        if (ZSATARAG == -1.0 && CO3 <= sat_a)
+          ZSATARAG = fdiv(w4 * ARAG_ANOM_km1, (ARAG_ANOM_km1 - (CO3 - sat_a)));
+        if (ZSATCALC == -1.0 && k == kmax - 1) ZSATCALC = zbot;
+        if (ZSATARAG == -1.0 && k == kmax - 1) ZSATARAG = zbot;
+      }
+      CALC_ANOM_km1 = CO3 - sat_c;
+      ARAG_ANOM_km1 = CO3 - sat_a;
+    }
+
+    // ---- running sums over the functional groups.  Fortran's SUM(x(:)) adds the
+    //      elements left to right starting from zero: so do these accumulators.
+    double s_auto_loss_doc = 0.0, s_auto_graze_doc = 0.0, s_auto_graze_poc = 0.0, s_auto_agg = 0.0,
+           s_auto_loss_poc = 0.0, s_NO3_V = 0.0, s_NH4_V = 0.0, s_auto_loss_dic = 0.0, s_auto_graze_dic = 0.0,
+           s_photoFe = 0.0, s_PO4_V = 0.0, s_auto_graze_zoo = 0.0, s_DOP_V = 0.0, s_photoC = 0.0,
+           s_auto_graze = 0.0;
+    double zd_num = 0.0, zd_den = 0.0;          // f_zoo_detr (:1395-1401)
+    double acc_DOP_prod = 0.0, acc_DOFe_prod = 0.0, acc_Fe_prod = 0.0;
+    double acc_t_fe = 0.0, acc_t_nh4 = 0.0, acc_t_sio3 = 0.0, acc_t_po4 = 0.0, acc_t_dic = 0.0;
+    double O2_PRODUCTION = 0.0;
+    double Ca_prod = 0.0, Si_prod = 0.0;        // last writer wins among qualifying groups (:1480-1498)
+    double tot_CaCO3_form = 0.0, tot_Nfix = 0.0;
+    double s_tC = 0.0, s_tCaCO3 = 0.0, s_tSi = 0.0, s_QpC = 0.0, s_Nfix_J = 0.0, photoC_NO3_TOT = 0.0;
+
+    // ---- per functional group: quotas (:850-898), uptake, photosynthesis, losses,
+    //      grazing, routing (:1107-1388), tendencies (:1700-1745)
+#pragma unroll 1
     for (int a = 0; a < NA; ++a) {
       const BgcAutotroph &at = c_eco.a[a];
+      const size_t ia = i2 + (size_t)a * nLnC;
+      const double aChl = IN(at.Chl_ind - 1), aC = IN(at.C_ind - 1), aFe = IN(at.Fe_ind - 1), Pprime = XS(X_PPRIME + a);
+      const bool has_Si = at.Si_ind > 0, has_Ca = at.CaCO3_ind > 0;
 
-      const double rNO3 = NO3_loc / at.kNO3, rNH4 = NH4_loc / at.kNH4;
+      const double rCden = frcp(aC + epsC);
+#ifdef BGC_STRICT
+      const double thetaC = aChl / (aC + epsC), Qfe = aFe / (aC + epsC);
+#else
+      const double thetaC = aChl * rCden, Qfe = aFe * rCden;
+#endif
+      double Qsi = 0.0, gQsi = 0.0, QCaCO3 = 0.0;
+      if (has_Si) {
+#ifdef BGC_STRICT
+        Qsi = fmin(IN(at.Si_ind - 1) / (aC + epsC), gQsi_max);
+#else
+        Qsi = fmin(IN(at.Si_ind - 1) * rCden, gQsi_max);
+#endif
+      }
+      double gQfe = at.gQfe_0;
+      if (Fe_loc < D.cks_kFe[a])
+        gQfe = fmax(cdiv(gQfe * Fe_loc, D.cks_kFe[a], D.r_cks_kFe[a]), at.gQfe_min);
+      if (has_Si) {
+        double g = gQsi_0;
+        if ((Fe_loc < D.cksi_kFe[a]) && (Fe_loc > 0.0) && (SiO3_loc > D.cksi_kSiO3[a]))
+          g = fmin(fdiv(g * P.cksi * at.kFe, Fe_loc), gQsi_max);
+        if (Fe_loc == 0.0) g = gQsi_max;
+        if (SiO3_loc < D.cksi_kSiO3[a])
+          g = fmax(cdiv(g * SiO3_loc, D.cksi_kSiO3[a], D.r_cksi_kSiO3[a]), gQsi_min);
+        gQsi = g;
+      }
+      if (has_Ca) {
+#ifdef BGC_STRICT
+        QCaCO3 = IN(at.CaCO3_ind - 1) / (aC + epsC);
+#else
+        QCaCO3 = IN(at.CaCO3_ind - 1) * rCden;
+#endif
+        if (QCaCO3 > QCaCO3_max) QCaCO3 = QCaCO3_max;
+      }
+
+      // nutrient limitation (:1107-1150)
+      const double rNO3 = cdiv(NO3_loc, at.kNO3, D.r_kNO3[a]), rNH4 = cdiv(NH4_loc, at.kNH4, D.r_kNH4[a]);
+#ifdef BGC_STRICT
       const double VNO3 = rNO3 / (1.0 + rNO3 + rNH4);
       const double VNH4 = rNH4 / (1.0 + rNO3 + rNH4);
+#else
+      const double rN = frcp(1.0 + rNO3 + rNH4);
+      const double VNO3 = rNO3 * rN, VNH4 = rNH4 * rN;
+#endif
       double VNtot = VNO3 + VNH4;
       if (at.Nfixer) VNtot = 1.0;
 
-      const double VFe = Fe_loc / (Fe_loc + at.kFe);
+      const double VFe = fdiv(Fe_loc, Fe_loc + at.kFe);
       double f_nut = fmin(VNtot, VFe);
 
-      const double rPO4 = PO4_loc / at.kPO4, rDOP = DOP_loc / at.kDOP;
+      const double rPO4 = cdiv(PO4_loc, at.kPO4, D.r_kPO4[a]), rDOP = cdiv(DOP_loc, at.kDOP, D.r_kDOP[a]);
+#ifdef BGC_STRICT
       const double VPO4 = rPO4 / (1.0 + rPO4 + rDOP);
       const double VDOP = rDOP / (1.0 + rPO4 + rDOP);
+#else
+      const double rPd = frcp(1.0 + rPO4 + rDOP);
+      const double VPO4 = rPO4 * rPd, VDOP = rDOP * rPd;
+#endif
       const double VPtot = VPO4 + VDOP;
       f_nut = fmin(f_nut, VPtot);
 
       double VSiO3 = 0.0;
       if (at.kSiO3 > 0.0) {
-        VSiO3 = SiO3_loc / (SiO3_loc + at.kSiO3);
+        VSiO3 = fdiv(SiO3_loc, SiO3_loc + at.kSiO3);
         f_nut = fmin(f_nut, VSiO3);
       }
       if (DIAG) {
-        STA(diag_N_lim, a, VNtot);
-        STA(diag_Fe_lim, a, VFe);
-        STA(diag_P_lim, a, VPtot);
-        STA(diag_SiO3_lim, a, VSiO3);
+        STA(diag_N_lim, VNtot);
+        STA(diag_Fe_lim, VFe);
+        STA(diag_P_lim, VPtot);
+        STA(diag_SiO3_lim, VSiO3);
       }
 
+      // photosynthesis (:1157-1182)
       double PCmax = at.PCref * f_nut * Tfunc;
       if (TEMP < at.temp_thres) PCmax = 0.0;
       if (at.temp_function == BGC_TFNC_QUASI_MMRT) {
         const double tmpTopt = north ? at.temp_optN : at.temp_optS;
         const double tmpTmax = north ? at.temp_thresN : at.temp_thresS;
-        PCmax = PCmax * fmin(1.0, ((tmpTmax - TEMP) / (tmpTmax - tmpTopt)));
+        PCmax = PCmax * fmin(1.0, cdiv(tmpTmax - TEMP, tmpTmax - tmpTopt, north ? D.r_dTN[a] : D.r_dTS[a]));
         if (TEMP > tmpTmax) PCmax = 0.0;
       }
-
-      const double light_lim =
-          (1.0 - exp((-1.0 * at.alphaPI * thetaC[a] * PAR_avg) / (PCmax + epsTinv)));
+      const double aPI = at.alphaPI * thetaC * PAR_avg;
+      const double light_lim = (1.0 - exp(fdiv(-1.0 * aPI, PCmax + epsTinv)));
       const double PCphoto = PCmax * light_lim;
-      if (DIAG) STA(diag_light_lim, a, light_lim);
+      if (DIAG) STA(diag_light_lim, light_lim);
 
-      photoC[a] = PCphoto * aC[a];
+      const double photoC = PCphoto * aC;
 
-      double VNC;
+      // uptake ratios (:1190-1222)
+      double NO3_V, NH4_V, VNC, photoC_NO3, PO4_V, DOP_V;
       if (VNtot > 0.0) {
-        NO3_V[a] = (VNO3 / VNtot) * photoC[a] * Qn;
-        NH4_V[a] = (VNH4 / VNtot) * photoC[a] * Qn;
+#ifdef BGC_STRICT
+        NO3_V = (VNO3 / VNtot) * photoC * Qn;
+        NH4_V = (VNH4 / VNtot) * photoC * Qn;
+        photoC_NO3 = (VNO3 / VNtot) * photoC;
+#else
+        const double rV = frcp(VNtot);
+        NO3_V = (VNO3 * rV) * photoC * Qn;
+        NH4_V = (VNH4 * rV) * photoC * Qn;
+        photoC_NO3 = (VNO3 * rV) * photoC;
+#endif
         VNC = PCphoto * Qn;
-        photoC_NO3[a] = (VNO3 / VNtot) * photoC[a];
       } else {
-        NO3_V[a] = 0.0; NH4_V[a] = 0.0; VNC = 0.0; photoC_NO3[a] = 0.0;
+        NO3_V = 0.0; NH4_V = 0.0; VNC = 0.0; photoC_NO3 = 0.0;
       }
       if (VPtot > 0.0) {
-        PO4_V[a] = (VPO4 / VPtot) * photoC[a] * at.Qp;
-        DOP_V[a] = (VDOP / VPtot) * photoC[a] * at.Qp;
+#ifdef BGC_STRICT
+        PO4_V = (VPO4 / VPtot) * photoC * at.Qp;
+        DOP_V = (VDOP / VPtot) * photoC * at.Qp;
+#else
+        const double rV = frcp(VPtot);
+        PO4_V = (VPO4 * rV) * photoC * at.Qp;
+        DOP_V = (VDOP * rV) * photoC * at.Qp;
+#endif
       } else {
-        PO4_V[a] = 0.0; DOP_V[a] = 0.0;
+        PO4_V = 0.0; DOP_V = 0.0;
       }
-      photoFe[a] = photoC[a] * gQfe[a];
+      const double photoFe = photoC * gQfe;
 
-      photoSi[a] = 0.0;
-      if (at.Si_ind > 0) {
-        photoSi[a] = photoC[a] * gQsi[a];
-        tot_bSi_form = tot_bSi_form + photoSi[a];   // (:1230-1231, no dz)
+      double photoSi = 0.0;
+      if (has_Si) {
+        photoSi = photoC * gQsi;
+        tot_bSi_form = tot_bSi_form + photoSi;   // (:1230-1231, no dz)
       }
       if (DIAG) {
-        STA(diag_photoNO3, a, NO3_V[a]);
-        STA(diag_photoNH4, a, NH4_V[a]);
-        STA(diag_PO4_uptake, a, PO4_V[a]);
-        STA(diag_DOP_uptake, a, DOP_V[a]);
-        STA(diag_photoFe, a, photoFe[a]);
-        STA(diag_bSi_form, a, photoSi[a]);
+        STA(diag_photoNO3, NO3_V);
+        STA(diag_photoNH4, NH4_V);
+        STA(diag_PO4_uptake, PO4_V);
+        STA(diag_DOP_uptake, DOP_V);
+        STA(diag_photoFe, photoFe);
+        STA(diag_bSi_form, photoSi);
       }
 
       // Chl synthesis, GD98 (:1240-1246)
-      {
-        const double w = at.alphaPI * thetaC[a] * PAR_avg;
-        if (w > 0.0) {
-          const double pChl = at.thetaN_max * PCphoto / w;
-          photoacc[a] = (pChl * VNC / thetaC[a]) * aChl[a];
-        } else {
-          photoacc[a] = 0.0;
-        }
+      double photoacc = 0.0;
+      if (aPI > 0.0) {
+        const double pChl = fdiv(at.thetaN_max * PCphoto, aPI);
+        photoacc = fdiv(pChl * VNC, thetaC) * aChl;
       }
 
       // implicit calcification (:1255-1278)
-      CaCO3_PROD[a] = 0.0;
+      double CaCO3_PROD = 0.0;
       if (at.imp_calcifier) {
-        double cp = P.parm_f_prod_sp_CaCO3 * photoC[a];
+        double cp = P.parm_f_prod_sp_CaCO3 * photoC;
         cp = cp * f_nut;
         if (TEMP < CaCO3_temp_thres1)
           cp = cp * fmax((TEMP - CaCO3_temp_thres2), 0.0) / (CaCO3_temp_thres1 - CaCO3_temp_thres2);
-        if (aC[a] > CaCO3_sp_thres)
-          cp = fmin((cp * aC[a] / CaCO3_sp_thres), (f_photosp_CaCO3 * photoC[a]));
-        CaCO3_PROD[a] = cp;
+        if (aC > CaCO3_sp_thres)
+          cp = fmin((cp * aC / CaCO3_sp_thres), (f_photosp_CaCO3 * photoC));
+        CaCO3_PROD = cp;
         tot_CaCO3_form = tot_CaCO3_form + cp;
         if (DIAG) {
           const double w = dz * cp;
-          CaCO3_form_zint[a] = CaCO3_form_zint[a] + w;
+          XS(X_ZCACO3 + a) = XS(X_ZCACO3 + a) + w;
           tot_CaCO3_form_zint = tot_CaCO3_form_zint + w;
         }
       }
-      if (DIAG) STA(diag_CaCO3_form, a, CaCO3_PROD[a]);
+      if (DIAG) STA(diag_CaCO3_form, CaCO3_PROD);
 
       // losses and aggregation (:1285-1290)
-      auto_loss[a] = at.mort * Pprime[a] * Tfunc;
-      auto_agg[a] = fmin((at.agg_rate_max * dps) * Pprime[a], at.mort2 * Pprime[a] * Pprime[a]);
-      auto_agg[a] = fmax((at.agg_rate_min * dps) * Pprime[a], auto_agg[a]);
+      const double auto_loss = at.mort * Pprime * Tfunc;
+      double auto_agg = fmin(D.agg_max_dps[a] * Pprime, at.mort2 * Pprime * Pprime);
+      auto_agg = fmax(D.agg_min_dps[a] * Pprime, auto_agg);
 
       // grazing (:1297-1324)
       double grazee_C = 0.0;
 #pragma unroll
       for (int b = 0; b < NA; ++b)
-        if (c_eco.same_grazee[a][b]) grazee_C = grazee_C + Pprime[b];
+        if (c_eco.same_grazee[a][b]) grazee_C = grazee_C + XS(X_PPRIME + b);
 
       double z_umax = at.z_umax_0 * Tfunc;
       if (a + 1 == I.diat_ind) {
         if (north && (TEMP > at.temp_optN)) {
-          z_umax = z_umax * fmax((at.temp_thresN - TEMP) / (at.temp_thresN - at.temp_optN), 0.95);
+          z_umax = z_umax * fmax(cdiv(at.temp_thresN - TEMP, at.temp_thresN - at.temp_optN, D.r_dTN[a]), 0.95);
         } else if ((lat <= 0.0) && (TEMP > at.temp_optS)) {
-          z_umax = z_umax * fmax((at.temp_thresS - TEMP) / (at.temp_thresS - at.temp_optS), 0.95);
+          z_umax = z_umax * fmax(cdiv(at.temp_thresS - TEMP, at.temp_thresS - at.temp_optS, D.r_dTS[a]), 0.95);
         }
       }
+      double auto_graze = 0.0;
       if (grazee_C > 0.0) {
-        auto_graze[a] = (Pprime[a] / grazee_C) * z_umax * zooC_loc * (grazee_C / (grazee_C + at.z_grz));
-      } else {
-        auto_graze[a] = 0.0;
+#ifdef BGC_STRICT
+        auto_graze = (Pprime / grazee_C) * z_umax * zooC_loc * (grazee_C / (grazee_C + at.z_grz));
+#else
+        // (P/g) * u * z * (g/(g+zg)) with both quotients formed from reciprocals
+        auto_graze = (Pprime * frcp(grazee_C)) * z_umax * zooC_loc * (grazee_C * frcp(grazee_C + at.z_grz));
+#endif
       }
 
       // N fixation (:1331-1338)
-      Nfix[a] = 0.0; Nexcrete[a] = 0.0;
+      double Nfix = 0.0, Nexcrete = 0.0;
       if (at.Nfixer) {
-        const double w = photoC[a] * Qn;
-        Nfix[a] = (w * r_Nfix_photo) - NO3_V[a] - NH4_V[a];
-        Nexcrete[a] = Nfix[a] + NO3_V[a] + NH4_V[a] - w;
-        tot_Nfix = tot_Nfix + Nfix[a];
+        const double w = photoC * Qn;
+        Nfix = (w * r_Nfix_photo) - NO3_V - NH4_V;
+        Nexcrete = Nfix + NO3_V + NH4_V - w;
+        tot_Nfix = tot_Nfix + Nfix;
+        acc_t_nh4 = acc_t_nh4 + Nexcrete;
+        s_Nfix_J = s_Nfix_J + Nfix;
       }
-      if (DIAG) STA(diag_Nfix, a, Nfix[a]);
+      if (DIAG) STA(diag_Nfix, Nfix);
 
       // routing (:1354-1372)
-      auto_graze_zoo[a] = at.graze_zoo * auto_graze[a];
+      const double auto_graze_zoo = at.graze_zoo * auto_graze;
+      double auto_graze_poc, auto_loss_poc;
       if (at.imp_calcifier) {
-        auto_graze_poc[a] = auto_graze[a] * fmax((caco3_poc_min * QCaCO3[a]),
-                                                 fmin(spc_poc_fac * fmax(1.0, Pprime[a]), f_graze_sp_poc_lim));
+        auto_graze_poc = auto_graze * fmax((caco3_poc_min * QCaCO3),
+                                           fmin(spc_poc_fac * fmax(1.0, Pprime), f_graze_sp_poc_lim));
+        auto_loss_poc = QCaCO3 * auto_loss;
       } else {
-        auto_graze_poc[a] = at.graze_poc * auto_graze[a];
+        auto_graze_poc = at.graze_poc * auto_graze;
+        auto_loss_poc = at.loss_poc * auto_loss;
       }
-      auto_graze_doc[a] = at.graze_doc * auto_graze[a];
-      auto_graze_dic[a] = auto_graze[a] - (auto_graze_zoo[a] + auto_graze_poc[a] + auto_graze_doc[a]);
+      const double auto_graze_doc = at.graze_doc * auto_graze;
+      const double auto_graze_dic = auto_graze - (auto_graze_zoo + auto_graze_poc + auto_graze_doc);
+      const double auto_loss_doc = (1.0 - P.parm_labile_ratio) * (auto_loss - auto_loss_poc);
+      const double auto_loss_dic = P.parm_labile_ratio * (auto_loss - auto_loss_poc);
 
-      if (at.imp_calcifier) auto_loss_poc[a] = QCaCO3[a] * auto_loss[a];
-      else                  auto_loss_poc[a] = at.loss_poc * auto_loss[a];
-      auto_loss_doc[a] = (1.0 - P.parm_labile_ratio) * (auto_loss[a] - auto_loss_poc[a]);
-      auto_loss_dic[a] = P.parm_labile_ratio * (auto_loss[a] - auto_loss_poc[a]);
-
-      // P routing for groups whose Qp differs from Qp_zoo_pom (:1380-1386)
-      remaining_P_dop[a] = 0.0; remaining_P_dip[a] = 0.0;
+      // P routing for groups whose Qp differs from Qp_zoo_pom (:1380-1386, :1434-1440, :1668-1674)
       if (at.Qp != Qp_zoo_pom) {
-        const double remaining_P = ((auto_graze[a] + auto_loss[a] + auto_agg[a]) * at.Qp)
-                                 - ((auto_graze_zoo[a]) * Qp_zoo_pom)
-                                 - ((auto_graze_poc[a] + auto_loss_poc[a] + auto_agg[a]) * Qp_zoo_pom);
-        remaining_P_dop[a] = (1.0 - P.parm_labile_ratio) * remaining_P;
-        remaining_P_dip[a] = P.parm_labile_ratio * remaining_P;
+        const double remaining_P = ((auto_graze + auto_loss + auto_agg) * at.Qp)
+                                 - ((auto_graze_zoo) * Qp_zoo_pom)
+                                 - ((auto_graze_poc + auto_loss_poc + auto_agg) * Qp_zoo_pom);
+        acc_DOP_prod = acc_DOP_prod + (1.0 - P.parm_labile_ratio) * remaining_P;
+        acc_t_po4 = acc_t_po4 + P.parm_labile_ratio * remaining_P;
+      } else {
+        acc_DOP_prod = acc_DOP_prod + at.Qp * (auto_loss_doc + auto_graze_doc);
+        acc_t_po4 = acc_t_po4 + at.Qp * (auto_loss_dic + auto_graze_dic);
       }
-    }
 
-    // sequential sums over the functional groups, in the reference's SUM order
-#define SUM4(x) ((((0.0 + x[0]) + x[1]) + x[2]) + x[3])
-    const double s_auto_loss_doc = SUM4(auto_loss_doc), s_auto_graze_doc = SUM4(auto_graze_doc),
-                 s_auto_graze_poc = SUM4(auto_graze_poc), s_auto_agg = SUM4(auto_agg),
-                 s_auto_loss_poc = SUM4(auto_loss_poc), s_NO3_V = SUM4(NO3_V), s_NH4_V = SUM4(NH4_V),
-                 s_auto_loss_dic = SUM4(auto_loss_dic), s_auto_graze_dic = SUM4(auto_graze_dic),
-                 s_photoFe = SUM4(photoFe), s_PO4_V = SUM4(PO4_V), s_auto_graze_zoo = SUM4(auto_graze_zoo),
-                 s_DOP_V = SUM4(DOP_V), s_photoC = SUM4(photoC);
+      // running sums
+      s_auto_loss_doc = s_auto_loss_doc + auto_loss_doc;
+      s_auto_graze_doc = s_auto_graze_doc + auto_graze_doc;
+      s_auto_graze_poc = s_auto_graze_poc + auto_graze_poc;
+      s_auto_agg = s_auto_agg + auto_agg;
+      s_auto_loss_poc = s_auto_loss_poc + auto_loss_poc;
+      s_NO3_V = s_NO3_V + NO3_V;
+      s_NH4_V = s_NH4_V + NH4_V;
+      s_auto_loss_dic = s_auto_loss_dic + auto_loss_dic;
+      s_auto_graze_dic = s_auto_graze_dic + auto_graze_dic;
+      s_photoFe = s_photoFe + photoFe;
+      s_PO4_V = s_PO4_V + PO4_V;
+      s_auto_graze_zoo = s_auto_graze_zoo + auto_graze_zoo;
+      s_DOP_V = s_DOP_V + DOP_V;
+      s_photoC = s_photoC + photoC;
+      s_auto_graze = s_auto_graze + auto_graze;
+      zd_num = zd_num + at.f_zoo_detr * (auto_graze + epsC * epsTinv);
+      zd_den = zd_den + (auto_graze + epsC * epsTinv);
+      acc_DOFe_prod = acc_DOFe_prod + Qfe * (auto_loss_doc + auto_graze_doc);
+      acc_Fe_prod = acc_Fe_prod + Qfe * (auto_agg + auto_graze_poc + auto_loss_poc);
+      acc_t_fe = acc_t_fe + (Qfe * (auto_loss_dic + auto_graze_dic)) + auto_graze_zoo * (Qfe - Qfe_zoo);
+      if (has_Ca) {
+        Ca_prod = ((1.0 - f_graze_CaCO3_remin) * auto_graze + auto_loss + auto_agg) * QCaCO3;
+        acc_t_dic = acc_t_dic + f_graze_CaCO3_remin * auto_graze * QCaCO3 - CaCO3_PROD;
+      }
+      if (has_Si) {
+        Si_prod = Qsi * ((1.0 - f_graze_si_remin) * auto_graze + auto_agg + at.loss_poc * auto_loss);
+        acc_t_sio3 = acc_t_sio3 - photoSi +
+                     Qsi * (f_graze_si_remin * auto_graze + (1.0 - at.loss_poc) * auto_loss);
+      }
+
+      // O2 production (:1752-1775)
+      if (photoC > 0.0) {
+        if (!at.Nfixer) {
+#ifdef BGC_STRICT
+          const double den = NO3_V + NH4_V;
+          O2_PRODUCTION = O2_PRODUCTION + photoC *
+              ((NO3_V / den) / parm_Red_D_C_O2 + (NH4_V / den) / parm_Remin_D_C_O2);
+#else
+          const double rden = frcp(NO3_V + NH4_V);
+          O2_PRODUCTION = O2_PRODUCTION + photoC *
+              ((NO3_V * rden) * (1.0 / parm_Red_D_C_O2) + (NH4_V * rden) * (1.0 / parm_Remin_D_C_O2));
+#endif
+        } else {
+#ifdef BGC_STRICT
+          const double den = NO3_V + NH4_V + Nfix;
+          O2_PRODUCTION = O2_PRODUCTION + photoC *
+              ((NO3_V / den) / parm_Red_D_C_O2 + (NH4_V / den) / parm_Remin_D_C_O2 +
+               (Nfix / den) / parm_Red_D_C_O2_diaz);
+#else
+          const double rden = frcp(NO3_V + NH4_V + Nfix);
+          O2_PRODUCTION = O2_PRODUCTION + photoC *
+              ((NO3_V * rden) * (1.0 / parm_Red_D_C_O2) + (NH4_V * rden) * (1.0 / parm_Remin_D_C_O2) +
+               (Nfix * rden) * (1.0 / parm_Red_D_C_O2_diaz));
+#endif
+        }
+      }
+
+      // the group's own tendencies (:1700-1745)
+      {
+        const double w = auto_graze + auto_loss + auto_agg;
+        const double t_autoC = photoC - w;
+        TEND(at.C_ind) = t_autoC;
+        TEND(at.Chl_ind) = photoacc - thetaC * w;
+        TEND(at.Fe_ind) = photoFe - Qfe * w;
+        s_tC = s_tC + t_autoC;
+        s_QpC = s_QpC + at.Qp * t_autoC;
+        if (has_Si) {
+          const double t = photoSi - Qsi * w;
+          TEND(at.Si_ind) = t;
+          s_tSi = s_tSi + t;
+        }
+        if (has_Ca) {
+          const double t = CaCO3_PROD - QCaCO3 * w;
+          TEND(at.CaCO3_ind) = t;
+          s_tCaCO3 = s_tCaCO3 + t;
+        }
+      }
+
+      if (DIAG) {   // :1815-1846
+        STA(diag_auto_graze, auto_graze);
+        STA(diag_auto_loss, auto_loss);
+        STA(diag_auto_agg, auto_agg);
+        STA(diag_photoC, photoC);
+        STA(diag_photoC_NO3, photoC_NO3);
+        XS(X_ZPHOTO + a) = XS(X_ZPHOTO + a) + dz * photoC;
+        const double zn = XS(X_ZNO3 + a) + photoC_NO3 * dz;
+        XS(X_ZNO3 + a) = zn;
+        photoC_NO3_TOT = photoC_NO3_TOT + photoC_NO3;
+        // adds the RUNNING per-group integral every level (:1844-1846)
+        photoC_NO3_TOT_zint = photoC_NO3_TOT_zint + zn;
+      }
+    }   // functional groups
 
     // ---- zooplankton routing (:1395-1415)
-    double f_zoo_detr;
-    {
-      double w1 = 0.0, w2 = 0.0;
-#pragma unroll
-      for (int a = 0; a < NA; ++a) {
-        w1 = w1 + c_eco.a[a].f_zoo_detr * (auto_graze[a] + epsC * epsTinv);
-        w2 = w2 + (auto_graze[a] + epsC * epsTinv);
-      }
-      f_zoo_detr = w1 / w2;
-    }
+    const double f_zoo_detr = fdiv(zd_num, zd_den);
     const double Zprime = fmax(zooC_loc - f_loss_thres * loss_thres_zoo, 0.0);
-    const double zoo_loss = (P.parm_z_mort2_0 * pow(Zprime, 1.5) + P.parm_z_mort_0 * Zprime) * Tfunc;
+    const double zoo_loss = (P.parm_z_mort2_0 * fpow15(Zprime) + P.parm_z_mort_0 * Zprime) * Tfunc;
     const double zoo_loss_doc = (1.0 - P.parm_labile_ratio) * (1.0 - f_zoo_detr) * zoo_loss;
     const double zoo_loss_dic = P.parm_labile_ratio * (1.0 - f_zoo_detr) * zoo_loss;
 
     // ---- DOM (:1421-1461)
     const double DOC_prod = zoo_loss_doc + s_auto_loss_doc + s_auto_graze_doc;
     const double DON_prod = Qn * DOC_prod;
-    double DOP_prod = Qp_zoo_pom * zoo_loss_doc;
-#pragma unroll
-    for (int a = 0; a < NA; ++a) {
-      const BgcAutotroph &at = c_eco.a[a];
-      if (at.Qp == Qp_zoo_pom) DOP_prod = DOP_prod + at.Qp * (auto_loss_doc[a] + auto_graze_doc[a]);
-      else                     DOP_prod = DOP_prod + remaining_P_dop[a];
-    }
-    double DOFe_prod = Qfe_zoo * zoo_loss_doc;
-#pragma unroll
-    for (int a = 0; a < NA; ++a) DOFe_prod = DOFe_prod + Qfe[a] * (auto_loss_doc[a] + auto_graze_doc[a]);
+    const double DOP_prod = Qp_zoo_pom * zoo_loss_doc + acc_DOP_prod;
+    const double DOFe_prod = Qfe_zoo * zoo_loss_doc + acc_DOFe_prod;
 
     double DOC_remin = DOC_loc * DOC_reminR;
     double DON_remin = DON_loc * DON_reminR;
@@ -520,18 +811,6 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
 
     // ---- particle production (:1467-1529)
     const double POC_prod = f_zoo_detr * zoo_loss + s_auto_graze_poc + s_auto_agg + s_auto_loss_poc;
-    double Ca_prod = 0.0, Si_prod = 0.0;   // last writer wins among qualifying groups (:1480-1498)
-#pragma unroll
-    for (int a = 0; a < NA; ++a) {
-      if (c_eco.a[a].CaCO3_ind > 0)
-        Ca_prod = ((1.0 - f_graze_CaCO3_remin) * auto_graze[a] + auto_loss[a] + auto_agg[a]) * QCaCO3[a];
-    }
-#pragma unroll
-    for (int a = 0; a < NA; ++a) {
-      if (c_eco.a[a].Si_ind > 0)
-        Si_prod = Qsi[a] * ((1.0 - f_graze_si_remin) * auto_graze[a] + auto_agg[a] +
-                            c_eco.a[a].loss_poc * auto_loss[a]);
-    }
 
     double Fe_scavenge_rate = P.parm_fe_scavenge_rate0;
     Fe_scavenge_rate = Fe_scavenge_rate *
@@ -542,11 +821,7 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
     if (Fe_loc > fe_scavenge_thres1)
       Fe_scavenge_rate = Fe_scavenge_rate + (Fe_loc - fe_scavenge_thres1) * fe_max_scale2;
     const double Fe_scavenge = yps * Fe_loc * Fe_scavenge_rate;
-
-    double Fe_prod = (zoo_loss * f_zoo_detr * Qfe_zoo) + Fe_scavenge;
-#pragma unroll
-    for (int a = 0; a < NA; ++a)
-      Fe_prod = Fe_prod + Qfe[a] * (auto_agg[a] + auto_graze_poc[a] + auto_loss_poc[a]);
+    const double Fe_prod = ((zoo_loss * f_zoo_detr * Qfe_zoo) + Fe_scavenge) + acc_Fe_prod;
 
     // =====================================================================
     // compute_particulate_terms (BGC_mod.F90:2116-2699) for this level
@@ -569,21 +844,21 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
         for (int n = 3; n >= 1; --n) {   // first n (ascending) with zbot < z[n]  <=>  last assignment descending
           if (zbot < P.parm_scalelen_z[n])
             scalelength = P.parm_scalelen_vals[n - 1] +
-                          (P.parm_scalelen_vals[n] - P.parm_scalelen_vals[n - 1]) *
-                              (zbot - P.parm_scalelen_z[n - 1]) /
-                              (P.parm_scalelen_z[n] - P.parm_scalelen_z[n - 1]);
+                          cdiv((P.parm_scalelen_vals[n] - P.parm_scalelen_vals[n - 1]) *
+                                   (zbot - P.parm_scalelen_z[n - 1]),
+                               (P.parm_scalelen_z[n] - P.parm_scalelen_z[n - 1]), D.r_scalelen_dz[n]);
         }
       }
 
-      const double DECAY_Hard = exp(-dz / 4.0e6);
-      const double DECAY_HardDust = exp(-dz / 1.2e7);
+      const double DECAY_Hard = exp(cdiv(-dz, 4.0e6, 1.0 / 4.0e6));
+      const double DECAY_HardDust = exp(cdiv(-dz, 1.2e7, 1.0 / 1.2e7));
       const double TfuncS = Tfunc;   // 1.5**(same exponent) (:2295) is bit-identical to Tfunc (:1041)
 
-      const double dzr = 1.0 / dz;
+      const double dzr = frcp(dz);
 
       double poc_diss = P.parm_POC_diss;
       if ((O2_loc >= 5.0) && (O2_loc < 40.0)) {
-        poc_diss = P.parm_POC_diss * (1.0 + (3.3 - 1.0) * (40.0 - O2_loc) / 35.0);
+        poc_diss = P.parm_POC_diss * (1.0 + cdiv((3.3 - 1.0) * (40.0 - O2_loc), 35.0, 1.0 / 35.0));
       } else if (O2_loc < 5.0) {
         poc_diss = P.parm_POC_diss * 3.3;
       }
@@ -591,12 +866,12 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
       double sio2_diss = scalelength * P.parm_SiO2_diss;
       const double caco3_diss = scalelength * P.parm_CaCO3_diss;
       const double dust_diss = scalelength * dust_diss0;
-      sio2_diss = sio2_diss / TfuncS;
+      sio2_diss = fdiv(sio2_diss, TfuncS);
 
-      const double decay_POC_E = exp(-dz / poc_diss);
-      const double decay_SiO2 = exp(-dz / sio2_diss);
-      const double decay_CaCO3 = exp(-dz / caco3_diss);
-      const double decay_dust = exp(-dz / dust_diss);
+      const double decay_POC_E = exp(fdiv(-dz, poc_diss));
+      const double decay_SiO2 = exp(fdiv(-dz, sio2_diss));
+      const double decay_CaCO3 = exp(fdiv(-dz, caco3_diss));
+      const double decay_dust = exp(fdiv(-dz, dust_diss));
 
       Ca_s = Ca_s_in * decay_CaCO3 + Ca_prod * ((1.0 - CaCO3_gamma) * (1.0 - decay_CaCO3) * caco3_diss);
       Ca_h = Ca_h_in * DECAY_Hard + Ca_prod * (CaCO3_gamma * dz);
@@ -610,7 +885,7 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
 
       double new_QA_dust_def;
       if (QA_dust_def > 0.0) {
-        new_QA_dust_def = QA_dust_def * (du_s + du_h) / (du_s_in + du_h_in);
+        new_QA_dust_def = fdiv(QA_dust_def * (du_s + du_h), (du_s_in + du_h_in));
       } else {
         new_QA_dust_def = 0.0;
       }
@@ -642,7 +917,7 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
       if (POC_s_in + POC_h_in == 0.0) {
         Fe_remin = (POC_remin * parm_Red_Fe_C);
       } else {
-        Fe_remin = (POC_remin * (Fe_s_in + Fe_h_in) / (POC_s_in + POC_h_in));
+        Fe_remin = fdiv(POC_remin * (Fe_s_in + Fe_h_in), (POC_s_in + POC_h_in));
       }
       Fe_remin = Fe_remin + (Fe_s_in * 1.5e-5);
       Fe_s = Fe_s_in + dz * ((1.0 - P_iron_gamma) * Fe_prod - Fe_remin);
@@ -650,7 +925,7 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
         Fe_s = 0.0;
         Fe_remin = Fe_s_in * dzr + (1.0 - P_iron_gamma) * Fe_prod;
       }
-      Fe_remin = Fe_remin + du_remin * dust_to_Fe + (A.fesedflux[i2] * dzr);
+      Fe_remin = Fe_remin + du_remin * dust_to_Fe + (fesed * dzr);
       Fe_h = Fe_h_in;
 
       if (k == kmax - 1) {   // bottom cell: burial, sediment denitrification (:2522-2631)
@@ -658,9 +933,9 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
         if (flux > 0.0) {
           double flux_alt = flux * mpercm * spd;
           POC_sed = flux * fmin(0.8, P.parm_POMbury *
-                                         (0.013 + 0.53 * flux_alt * flux_alt /
-                                                      ((7.0 + flux_alt) * (7.0 + flux_alt))));
-          SED_DENITRIF = dzr * flux * (0.06 + 0.19 * pow(0.99, (O2_loc - NO3_loc)));
+                                         (0.013 + fdiv(0.53 * flux_alt * flux_alt,
+                                                       ((7.0 + flux_alt) * (7.0 + flux_alt)))));
+          SED_DENITRIF = dzr * flux * (0.06 + 0.19 * fpow_base(0.99, kLn099, (O2_loc - NO3_loc)));
           if (NO3_loc < 5.0) SED_DENITRIF = 0.0;
           flux_alt = flux * 1.0e-6 * spd * 365.0;
           OTHER_REMIN = dzr * fmin(fmin(0.1 + flux_alt, 0.5) * (flux - POC_sed),
@@ -728,65 +1003,28 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
     if (PAR_out < P.parm_nitrif_par_lim) {
       NITRIF = P.parm_kappa_nitrif * NH4_loc;
       if (PAR_in > P.parm_nitrif_par_lim)
-        NITRIF = NITRIF * log(PAR_out / P.parm_nitrif_par_lim) / (-KPARdz);
+        NITRIF = fdiv(NITRIF * log(fdiv(PAR_out, P.parm_nitrif_par_lim)), (-KPARdz));
     } else {
       NITRIF = 0.0;
     }
 
     double DENITRIF;
     {
-      double w = ((P.parm_o2_min + P.parm_o2_min_delta) - O2_loc) / P.parm_o2_min_delta;
+      double w = cdiv(((P.parm_o2_min + P.parm_o2_min_delta) - O2_loc), P.parm_o2_min_delta, D.r_o2_min_delta);
       w = fmin(fmax(w, 0.0), 1.0);
       if (NO3_loc == 0.0) w = 0.0;
-      DENITRIF = w * ((DOC_remin + POC_remin - OTHER_REMIN) / denitrif_C_N - SED_DENITRIF);
+      DENITRIF = w * (cdiv((DOC_remin + POC_remin - OTHER_REMIN), denitrif_C_N, 1.0 / denitrif_C_N) - SED_DENITRIF);
     }
 
     // ---- tendencies (:1583-1790)
     const double t_no3 = RESTORE_NO3 + NITRIF - DENITRIF - SED_DENITRIF - s_NO3_V;
-
-    double t_nh4 = -s_NH4_V - NITRIF + DON_remin + DONr_remin +
-                   Qn * (zoo_loss_dic + s_auto_loss_dic + s_auto_graze_dic + POC_remin * (1.0 - DONrefract));
-#pragma unroll
-    for (int a = 0; a < NA; ++a)
-      if (c_eco.a[a].Nfixer) t_nh4 = t_nh4 + Nexcrete[a];
-
-    double t_fe = Fe_remin + (Qfe_zoo * zoo_loss_dic) + DOFe_remin - s_photoFe - Fe_scavenge;
-#pragma unroll
-    for (int a = 0; a < NA; ++a)
-      t_fe = t_fe + (Qfe[a] * (auto_loss_dic[a] + auto_graze_dic[a])) + auto_graze_zoo[a] * (Qfe[a] - Qfe_zoo);
-
-    double t_sio3 = RESTORE_SiO3 + Si_remin;
-#pragma unroll
-    for (int a = 0; a < NA; ++a) {
-      if (c_eco.a[a].Si_ind > 0)
-        t_sio3 = t_sio3 - photoSi[a] +
-                 Qsi[a] * (f_graze_si_remin * auto_graze[a] + (1.0 - c_eco.a[a].loss_poc) * auto_loss[a]);
-    }
-
-    double t_po4 = RESTORE_PO4 + DOP_remin + DOPr_remin - s_PO4_V +
-                   Qp_zoo_pom * ((1.0 - DOPrefract) * POC_remin + zoo_loss_dic);
-#pragma unroll
-    for (int a = 0; a < NA; ++a) {
-      const BgcAutotroph &at = c_eco.a[a];
-      if (at.Qp == Qp_zoo_pom) t_po4 = t_po4 + at.Qp * (auto_loss_dic[a] + auto_graze_dic[a]);
-      else                     t_po4 = t_po4 + remaining_P_dip[a];
-    }
-
-    double t_autoC[NA], t_autoSi[NA], t_autoCaCO3[NA];
-#pragma unroll
-    for (int a = 0; a < NA; ++a) {
-      const BgcAutotroph &at = c_eco.a[a];
-      const double w = auto_graze[a] + auto_loss[a] + auto_agg[a];
-      t_autoC[a] = photoC[a] - w;
-      t_autoSi[a] = photoSi[a] - Qsi[a] * w;
-      t_autoCaCO3[a] = CaCO3_PROD[a] - QCaCO3[a] * w;
-      TEND(at.C_ind) = t_autoC[a];
-      TEND(at.Chl_ind) = photoacc[a] - thetaC[a] * w;
-      TEND(at.Fe_ind) = photoFe[a] - Qfe[a] * w;
-      if (at.Si_ind > 0) TEND(at.Si_ind) = t_autoSi[a];
-      if (at.CaCO3_ind > 0) TEND(at.CaCO3_ind) = t_autoCaCO3[a];
-    }
-
+    const double t_nh4 = (-s_NH4_V - NITRIF + DON_remin + DONr_remin +
+                          Qn * (zoo_loss_dic + s_auto_loss_dic + s_auto_graze_dic + POC_remin * (1.0 - DONrefract))) +
+                         acc_t_nh4;
+    const double t_fe = (Fe_remin + (Qfe_zoo * zoo_loss_dic) + DOFe_remin - s_photoFe - Fe_scavenge) + acc_t_fe;
+    const double t_sio3 = (RESTORE_SiO3 + Si_remin) + acc_t_sio3;
+    const double t_po4 = (RESTORE_PO4 + DOP_remin + DOPr_remin - s_PO4_V +
+                          Qp_zoo_pom * ((1.0 - DOPrefract) * POC_remin + zoo_loss_dic)) + acc_t_po4;
     const double t_zooC = s_auto_graze_zoo - zoo_loss;
     const double t_doc = DOC_prod - DOC_remin;
     const double t_don = (DON_prod * (1.0 - DONrefract)) - DON_remin;
@@ -794,44 +1032,18 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
     const double t_dop = (DOP_prod * (1.0 - DOPrefract)) - DOP_remin - s_DOP_V;
     const double t_dopr = (DOP_prod * DOPrefract) - DOPr_remin + (POC_remin * DOPrefract * Qp_zoo_pom);
     const double t_dofe = DOFe_prod - DOFe_remin;
-
-    double t_dic = s_auto_loss_dic + s_auto_graze_dic - s_photoC + DOC_remin + POC_remin + zoo_loss_dic + Ca_remin;
-#pragma unroll
-    for (int a = 0; a < NA; ++a) {
-      if (c_eco.a[a].CaCO3_ind > 0)
-        t_dic = t_dic + f_graze_CaCO3_remin * auto_graze[a] * QCaCO3[a] - CaCO3_PROD[a];
-    }
+    const double t_dic = (s_auto_loss_dic + s_auto_graze_dic - s_photoC + DOC_remin + POC_remin + zoo_loss_dic +
+                          Ca_remin) + acc_t_dic;
     const double t_dic_alt = A.alt_co2_use_eco ? t_dic : 0.0;
+    const double t_alk = (-t_no3 + t_nh4 + 2.0 * Ca_remin) + 2.0 * acc_t_dic;
 
-    double t_alk = -t_no3 + t_nh4 + 2.0 * Ca_remin;
-#pragma unroll
-    for (int a = 0; a < NA; ++a) {
-      if (c_eco.a[a].CaCO3_ind > 0)
-        t_alk = t_alk + 2.0 * (f_graze_CaCO3_remin * auto_graze[a] * QCaCO3[a] - CaCO3_PROD[a]);
-    }
-
-    double O2_PRODUCTION = 0.0;
-#pragma unroll
-    for (int a = 0; a < NA; ++a) {
-      if (photoC[a] > 0.0) {
-        if (!c_eco.a[a].Nfixer) {
-          const double den = NO3_V[a] + NH4_V[a];
-          O2_PRODUCTION = O2_PRODUCTION + photoC[a] *
-              ((NO3_V[a] / den) / parm_Red_D_C_O2 + (NH4_V[a] / den) / parm_Remin_D_C_O2);
-        } else {
-          const double den = NO3_V[a] + NH4_V[a] + Nfix[a];
-          O2_PRODUCTION = O2_PRODUCTION + photoC[a] *
-              ((NO3_V[a] / den) / parm_Red_D_C_O2 + (NH4_V[a] / den) / parm_Remin_D_C_O2 +
-               (Nfix[a] / den) / parm_Red_D_C_O2_diaz);
-        }
-      }
-    }
     double O2_CONSUMPTION;
     {
-      double w = (O2_loc - P.parm_o2_min) / P.parm_o2_min_delta;
+      double w = cdiv((O2_loc - P.parm_o2_min), P.parm_o2_min_delta, D.r_o2_min_delta);
       w = fmin(fmax(w, 0.0), 1.0);
-      O2_CONSUMPTION = w * ((POC_remin + DOC_remin - (SED_DENITRIF * denitrif_C_N) - OTHER_REMIN +
-                             zoo_loss_dic + s_auto_loss_dic + s_auto_graze_dic) / parm_Remin_D_C_O2 +
+      O2_CONSUMPTION = w * (cdiv((POC_remin + DOC_remin - (SED_DENITRIF * denitrif_C_N) - OTHER_REMIN +
+                                  zoo_loss_dic + s_auto_loss_dic + s_auto_graze_dic),
+                                 parm_Remin_D_C_O2, 1.0 / parm_Remin_D_C_O2) +
                             (2.0 * NITRIF));
     }
     const double t_o2 = O2_PRODUCTION - O2_CONSUMPTION;
@@ -864,38 +1076,20 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
       ST2(diag_DENITRIF, DENITRIF);
       ST2(diag_O2_PRODUCTION, O2_PRODUCTION);
       ST2(diag_O2_CONSUMPTION, O2_CONSUMPTION);
-      if (A.d.diag_AOU) {   // O2SAT_singleValue, Garcia & Gordon 1992 (:3012-3083)
-        const double SALT = A.S[i2];
-        const double TS = log(((T0K + 25.0) - TEMP) / (T0K + TEMP));
+      if (HAS(diag_AOU)) {   // O2SAT_singleValue, Garcia & Gordon 1992 (:3012-3083)
+        const double SALT = IN(R_S);
+        const double TS = log(fdiv(((T0K + 25.0) - TEMP), (T0K + TEMP)));
         double o2sat = exp(2.00907 + TS * (3.22014 + TS * (4.05010 + TS * (4.94457 + TS * (-2.56847E-1 + TS * 3.88767)))) +
                            SALT * ((-6.24523E-3 + TS * (-7.37614E-3 + TS * (-1.03410E-2 + TS * -8.17083E-3))) +
                                    SALT * -4.88682E-7));
-        o2sat = o2sat / 0.0223916;
+        o2sat = cdiv(o2sat, 0.0223916, 1.0 / 0.0223916);
         A.d.diag_AOU[i2] = o2sat - O2_loc;
       }
       ST2(diag_PAR_avg, PAR_avg);
       ST2(diag_zoo_loss, zoo_loss);
-      ST2(diag_auto_graze_TOT, SUM4(auto_graze));
-#pragma unroll
-      for (int a = 0; a < NA; ++a) {
-        STA(diag_auto_graze, a, auto_graze[a]);
-        STA(diag_auto_loss, a, auto_loss[a]);
-        STA(diag_auto_agg, a, auto_agg[a]);
-        STA(diag_photoC, a, photoC[a]);
-        photoC_zint[a] = photoC_zint[a] + dz * photoC[a];
-      }
+      ST2(diag_auto_graze_TOT, s_auto_graze);
       ST2(diag_photoC_TOT, s_photoC);
       photoC_TOT_zint = photoC_TOT_zint + s_photoC * dz;
-
-      double photoC_NO3_TOT = 0.0;
-#pragma unroll
-      for (int a = 0; a < NA; ++a) {
-        STA(diag_photoC_NO3, a, photoC_NO3[a]);
-        photoC_NO3_zint[a] = photoC_NO3_zint[a] + photoC_NO3[a] * dz;
-        photoC_NO3_TOT = photoC_NO3_TOT + photoC_NO3[a];
-        // adds the RUNNING per-group integral every level (:1844-1846)
-        photoC_NO3_TOT_zint = photoC_NO3_TOT_zint + photoC_NO3_zint[a];
-      }
       ST2(diag_photoC_NO3_TOT, photoC_NO3_TOT);
 
       ST2(diag_DOC_prod, DOC_prod);
@@ -909,55 +1103,45 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
       ST2(diag_Fe_scavenge, Fe_scavenge);
       ST2(diag_Fe_scavenge_rate, Fe_scavenge_rate);
 
-      const double ztop = (k > 0) ? zbot_km1 : 0.0;
-      const double w2 = fmin(100.0e2 - ztop, dz);
-      const double pt100 = (w2 > 0.0) ? w2 : 0.0;
       const bool shallow = zbot <= 100.0e2;
 
-      const double s_tC = SUM4(t_autoC);
-      double w1 = t_dic + t_doc + t_zooC + s_tC;
-#pragma unroll
-      for (int a = 0; a < NA; ++a)
-        if (c_eco.a[a].CaCO3_ind > 0) w1 = w1 + t_autoCaCO3[a];
+      double w1 = (t_dic + t_doc + t_zooC + s_tC) + s_tCaCO3;
       JC = JC + w1 * dz + POC_sed + Ca_sed;
       JC100 = JC100 + w1 * pt100 + (shallow ? (POC_sed + Ca_sed) : 0.0);
 
       w1 = t_no3 + t_nh4 + t_don + t_donr + Qn * t_zooC + Qn * s_tC;
-      w1 = w1 + DENITRIF + SED_DENITRIF;
-#pragma unroll
-      for (int a = 0; a < NA; ++a)
-        if (c_eco.a[a].Nfixer) w1 = w1 - Nfix[a];
+      w1 = (w1 + DENITRIF + SED_DENITRIF) - s_Nfix_J;
       JN = JN + w1 * dz + POC_sed * Qn;
       JN100 = JN100 + w1 * pt100 + (shallow ? (POC_sed * Qn) : 0.0);
 
-      w1 = t_po4 + t_dop + t_dopr + Qp_zoo_pom * t_zooC;
-#pragma unroll
-      for (int a = 0; a < NA; ++a) w1 = w1 + c_eco.a[a].Qp * t_autoC[a];
+      w1 = (t_po4 + t_dop + t_dopr + Qp_zoo_pom * t_zooC) + s_QpC;
       JP = JP + w1 * dz + POC_sed * Qp_zoo_pom;
       JP100 = JP100 + w1 * pt100 + (shallow ? (POC_sed * Qp_zoo_pom) : 0.0);
 
-      w1 = t_sio3;
-#pragma unroll
-      for (int a = 0; a < NA; ++a)
-        if (c_eco.a[a].Si_ind > 0) w1 = w1 + t_autoSi[a];
+      w1 = t_sio3 + s_tSi;
       JSi = JSi + w1 * dz + Si_sed;
       JSi100 = JSi100 + w1 * pt100 + (shallow ? Si_sed : 0.0);
-
-#pragma unroll
-      for (int a = 0; a < NA; ++a) Chl_TOT_zint_100m = Chl_TOT_zint_100m + aChl[a] * pt100;
 
       // O2 minimum scan (:1954-1968)
       if (k == 0 || O2_loc < O2_min) { O2_min = O2_loc; O2_min_depth = zmid; }
 
       zmid_km1 = zmid;
-      zbot_km1 = zbot;
     }
+    zbot_km1 = zbot;
 #undef TR
 #undef TEND
+    }   // active cell
+
+    // ---- end of level: every thread is done with stage k&1 (generic-proxy reads and the
+    //      in-place mask writes) before the TMA unit refills it with level k+2.  The same
+    //      barrier keeps the block's warps on one stretch of code (I-cache).
+    if (TMA) fence_proxy_async();
+    __syncthreads();
+    if (TMA && tid == 0 && k + 2 < kmax_blk) fetch_level(k + 2);
   }   // level loop
 
   // ---- per-column diagnostics
-  if (DIAG) {
+  if (DIAG && in_range) {
     if (kmax > 0) {
       STC(diag_photoC_TOT_zint, photoC_TOT_zint);
       STC(diag_photoC_NO3_TOT_zint, photoC_NO3_TOT_zint);
@@ -974,9 +1158,9 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
       STC(diag_O2_ZMIN_DEPTH, O2_min_depth);
 #pragma unroll
       for (int a = 0; a < NA; ++a) {
-        STCA(diag_photoC_zint, a, photoC_zint[a]);
-        STCA(diag_photoC_NO3_zint, a, photoC_NO3_zint[a]);
-        STCA(diag_CaCO3_form_zint, a, CaCO3_form_zint[a]);
+        STCA(diag_photoC_zint, a, XS(X_ZPHOTO + a));
+        STCA(diag_photoC_NO3_zint, a, XS(X_ZNO3 + a));
+        STCA(diag_CaCO3_form_zint, a, XS(X_ZCACO3 + a));
       }
     } else {
       BGC_DIAG_C1_LIST(ZERO_C1)
@@ -984,17 +1168,50 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
     }
   }
   if (poc_errors && A.status) atomicAdd(&A.status[2], (unsigned long long)poc_errors);
+#undef XS
+#undef IN
+}
+
+template <int DIAG, int BLOCK, int MINB, bool TMA>
+cudaError_t launch_variant(const EcoArgs &a, cudaStream_t s) {
+  const size_t smem = (size_t)(2 * R_ROWS + X_ROWS) * BLOCK * sizeof(double) + 2 * sizeof(unsigned long long);
+  auto kern = eco_columns_kernel<DIAG, BLOCK, MINB, TMA>;
+  // > 48 KB of dynamic shared memory is opt-in, per device: cheap enough to set on every launch
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const int grid = (a.nC + BLOCK - 1) / BLOCK;
+  kern<<<grid, BLOCK, smem, s>>>(a);
+  return cudaGetLastError();
+}
+
+// cp.async.bulk needs 16-byte aligned global addresses and sizes: every slab starts at
+// base + 8*(k*nC + 128*j), so nC must be even and every base pointer 16-byte aligned.
+bool slabs_are_bulk_copyable(const EcoArgs &a, bool diag) {
+  if (a.nC & 1) return false;
+  const void *p[] = {a.tracers, a.T, a.zmid, a.dz, a.zbot, a.fesedflux,
+                     diag ? a.S : a.T, diag ? a.co3 : a.T, diag ? a.sat_calc : a.T, diag ? a.sat_arag : a.T};
+  for (const void *q : p) if (((size_t)q) & 15u) return false;
+  return true;
+}
+
+template <int DIAG>
+cudaError_t launch_diag(const EcoArgs &a, int variant, cudaStream_t s) {
+  const bool tma = slabs_are_bulk_copyable(a, DIAG != 0) && variant != 9;
+  if (!tma) return launch_variant<DIAG, 128, 2, false>(a, s);
+  switch (variant) {
+    case 1:  return launch_variant<DIAG, 256, 1, true>(a, s);    // one 8-warp block per SM
+    default: return launch_variant<DIAG, 128, 2, true>(a, s);    // two 4-warp blocks per SM
+  }
 }
 
 }  // namespace
 
-cudaError_t launch_eco_columns(const EcoArgs &a, bool any_diag, cudaStream_t s) {
+// diag_mode: 0 none, 1 some (NULL-checked stores), 2 every array present
+cudaError_t launch_eco_columns(const EcoArgs &a, int diag_mode, int variant, cudaStream_t s) {
   if (a.nC <= 0 || a.nL <= 0) return cudaSuccess;
-  const int block = 128;
-  const int grid = (a.nC + block - 1) / block;
-  if (any_diag) eco_columns_kernel<true><<<grid, block, 0, s>>>(a);
-  else          eco_columns_kernel<false><<<grid, block, 0, s>>>(a);
-  return cudaGetLastError();
+  if (diag_mode == 0) return launch_diag<0>(a, variant, s);
+  if (diag_mode == 2) return launch_diag<2>(a, variant, s);
+  return launch_diag<1>(a, variant, s);
 }
 
 }  // namespace bgc

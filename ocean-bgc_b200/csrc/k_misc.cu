@@ -308,11 +308,15 @@ transpose_kernel(const double *__restrict__ src, double *__restrict__ dst, int R
 }
 
 // ---------------------------------------------------------------- inventory
-// Stage 1: block b sums tend(n)*dz over its columns (fixed order inside the
-// block); stage 2: one block folds the partials in index order.  No atomics,
-// so the result is bit-reproducible from run to run and independent of timing.
+// sum_col sum_k tend(n)*dz over active cells, and the sums of a few per-column
+// diagnostics, for the global conservation vector (include/bgc_b200.h).
+//
+// Stage 1 (inventory_partial_kernel): one thread per column, grid.y = group of up
+// to kInvGroup tracer slots, so a 235k-column mesh offers >1M threads of independent
+// streaming loads; block b writes its partial sums.  Stage 2 (inventory_fold_kernel):
+// one block per group adds the partials in a fixed order into the inventory vector.
+// No atomics: the result is bit-reproducible and independent of timing.
 constexpr int kInvBlock = 256;
-constexpr int kInvMaxTracers = 32;
 
 __device__ __forceinline__ double block_sum(double v, double *smem) {
 #pragma unroll
@@ -331,56 +335,71 @@ __device__ __forceinline__ double block_sum(double v, double *smem) {
 __global__ void __launch_bounds__(kInvBlock)
 inventory_partial_kernel(const __grid_constant__ InventoryArgs A) {
   __shared__ double smem[kInvBlock / 32];
+  const int g = blockIdx.y;
+  const int col = blockIdx.x * kInvBlock + threadIdx.x;
   const size_t nC = (size_t)A.nC, nLnC = (size_t)A.nL * nC;
-  double acc[kInvMaxTracers];
+  double acc[kInvGroup];
 #pragma unroll
-  for (int n = 0; n < kInvMaxTracers; ++n) acc[n] = 0.0;
-  double cells = 0.0, cols = 0.0;
-  for (int col = blockIdx.x * blockDim.x + threadIdx.x; col < A.nColumns; col += gridDim.x * blockDim.x) {
-    int kmax = A.kmax[col];
+  for (int j = 0; j < kInvGroup; ++j) acc[j] = 0.0;
+
+  if (g < A.nGroups) {
+    int kmax = (col < A.nColumns) ? A.kmax[col] : 0;
     if (kmax > A.nL) kmax = A.nL;
-    if (kmax > 0) cols += 1.0;
+    const double *src[kInvGroup];
+#pragma unroll
+    for (int j = 0; j < kInvGroup; ++j) {
+      const int slot = A.slot[g][j];
+      src[j] = (slot >= 0) ? A.tend + (size_t)slot * nLnC + col : nullptr;
+    }
+    const double *dzp = A.dz + col;
+    const bool counts = (g == 0) && A.count_out >= 0;
+    double cells = 0.0;
+#pragma unroll 2
     for (int k = 0; k < kmax; ++k) {
-      const size_t i2 = (size_t)col + nC * (size_t)k;
-      const double dz = A.dz[i2];
+      const size_t o = nC * (size_t)k;
+      const double dz = dzp[o];
+#pragma unroll
+      for (int j = 0; j < kInvGroup; ++j)
+        if (src[j]) acc[j] += src[j][o] * dz;
       cells += 1.0;
+    }
+    if (counts) { acc[kInvGroup - 2] = cells; acc[kInvGroup - 1] = (kmax > 0) ? 1.0 : 0.0; }
+  } else {   // the per-column diagnostic sums
+    if (col < A.nColumns) {
 #pragma unroll
-      for (int n = 0; n < kInvMaxTracers; ++n)
-        if (n < A.nTracers) acc[n] += A.tend[i2 + (size_t)n * nLnC] * dz;
+      for (int j = 0; j < kInvGroup; ++j)
+        if (A.colsum[j]) acc[j] = A.colsum[j][col];
     }
   }
-  const int stride = A.nTracers + 2;
+  double *out = A.partials + ((size_t)blockIdx.x * gridDim.y + g) * kInvGroup;
 #pragma unroll
-  for (int n = 0; n < kInvMaxTracers; ++n) {
-    if (n < A.nTracers) {
-      const double r = block_sum(acc[n], smem);
-      if (threadIdx.x == 0) A.partials[(size_t)blockIdx.x * stride + n] = r;
-    }
+  for (int j = 0; j < kInvGroup; ++j) {
+    const double r = block_sum(acc[j], smem);
+    if (threadIdx.x == 0) out[j] = r;
   }
-  double r = block_sum(cells, smem);
-  if (threadIdx.x == 0) A.partials[(size_t)blockIdx.x * stride + A.nTracers] = r;
-  r = block_sum(cols, smem);
-  if (threadIdx.x == 0) A.partials[(size_t)blockIdx.x * stride + A.nTracers + 1] = r;
 }
 
-__global__ void fold_partials_kernel(const double *partials, int nParts, int stride, int nOut, double *out) {
-  const int n = threadIdx.x;
-  if (n >= nOut) return;
+// grid = number of groups, block = 256: lane j = t % 8 of "row" t / 8 walks the partials
+// of value j with stride 32 blocks; the 32 row sums are then added in row order.
+__global__ void __launch_bounds__(256)
+inventory_fold_kernel(const __grid_constant__ InventoryArgs A, int nParts) {
+  __shared__ double rows[32][kInvGroup];
+  const int g = blockIdx.x, j = threadIdx.x % kInvGroup, r = threadIdx.x / kInvGroup;
   double s = 0.0;
-  for (int b = 0; b < nParts; ++b) s += partials[(size_t)b * stride + n];
-  out[n] = s;
-}
-
-__global__ void __launch_bounds__(kInvBlock)
-column_sums_partial_kernel(const double *const *cols, int nArrays, int nColumns, double *partials) {
-  __shared__ double smem[kInvBlock / 32];
-  for (int a = 0; a < nArrays; ++a) {
-    const double *p = cols[a];
-    double acc = 0.0;
-    if (p)
-      for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nColumns; c += gridDim.x * blockDim.x) acc += p[c];
-    const double r = block_sum(acc, smem);
-    if (threadIdx.x == 0) partials[(size_t)blockIdx.x * nArrays + a] = r;
+  for (int b = r; b < nParts; b += 32) s += A.partials[((size_t)b * gridDim.x + g) * kInvGroup + j];
+  rows[r][j] = s;
+  __syncthreads();
+  if (r == 0) {
+    double t = 0.0;
+    for (int q = 0; q < 32; ++q) t += rows[q][j];
+    int dst = -1;
+    if (g < A.nGroups) {
+      if (A.slot[g][j] >= 0) dst = A.out_index[g][j];
+      if (g == 0 && A.count_out >= 0 && j >= kInvGroup - 2) dst = A.count_out + (j - (kInvGroup - 2));
+    } else if (A.colsum[j]) {
+      dst = A.colsum_out + j;
+    }
+    if (dst >= 0) A.inventory[dst] += t;
   }
 }
 
@@ -418,29 +437,20 @@ cudaError_t launch_transpose(const double *src, double *dst, int R, int C, int n
 
 int inventory_grid(int nC) {
   int g = (nC + kInvBlock - 1) / kInvBlock;
-  if (g > 592) g = 592;   // 4 blocks per SM on 148 SMs
-  if (g < 1) g = 1;
-  return g;
+  return g < 1 ? 1 : g;
 }
 
 cudaError_t launch_inventory(const InventoryArgs &a, cudaStream_t s) {
-  if (a.nTracers > kInvMaxTracers) return cudaErrorInvalidValue;
-  const int grid = inventory_grid(a.nC);
-  inventory_partial_kernel<<<grid, kInvBlock, 0, s>>>(a);
+  if (a.nGroups < 0 || a.nGroups > kInvMaxGroups) return cudaErrorInvalidValue;
+  bool any_colsum = false;
+  for (int j = 0; j < kInvGroup; ++j) any_colsum = any_colsum || a.colsum[j] != nullptr;
+  const int gy = a.nGroups + (any_colsum ? 1 : 0);
+  if (gy == 0 || a.nColumns <= 0) return cudaSuccess;
+  const int gx = inventory_grid(a.nColumns);
+  inventory_partial_kernel<<<dim3(gx, gy), kInvBlock, 0, s>>>(a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  const int nOut = a.nTracers + (a.count ? 2 : 0);
-  fold_partials_kernel<<<1, 64, 0, s>>>(a.partials, grid, a.nTracers + 2, nOut, a.out);
-  return cudaGetLastError();
-}
-
-cudaError_t launch_column_sums(const double *const *cols, int nArrays, int nColumns, double *partials,
-                               double *out, cudaStream_t s) {
-  const int grid = inventory_grid(nColumns);
-  column_sums_partial_kernel<<<grid, kInvBlock, 0, s>>>(cols, nArrays, nColumns, partials);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return e;
-  fold_partials_kernel<<<1, 64, 0, s>>>(partials, grid, nArrays, nArrays, out);
+  inventory_fold_kernel<<<gy, 256, 0, s>>>(a, gx);
   return cudaGetLastError();
 }
 

@@ -1,0 +1,384 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the CPU
+oracle on the same seeded synthetic columns (tolerances: tests/parity.py), plus
+size-independent properties at the full EC60to30 size.
+
+Covers the edge cases the reference's own semantics create: ragged bathymetry, land
+columns (kmax = 0), numColumns < numColumnsMax, odd numColumnsMax (per-thread load
+path instead of the bulk-copy path), cold and warm pH brackets, diagnostics absent /
+partially present, permuted tracer slots, dark columns, negative tracers, the
+zero-mask of a functional group.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import parity
+
+pkg = parity.pkg
+abi = pkg.abi
+host = pkg.host
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def o():
+    return parity.oracle()
+
+
+def _ctx(nL, nC, flavour=None, parms=None):
+    parms = parms or host.Parms(flavour)
+    return host.Context(nL, nC, device=0, flavour=flavour, parms=parms), parms
+
+
+# ------------------------------------------------------------------ BGC_SourceSink
+@pytest.mark.parametrize("nL,nC,nCols,ragged", [
+    (60, 256, 256, False),    # two full blocks, bulk-copy path
+    (60, 258, 250, True),     # partial last block, numColumns < numColumnsMax, land columns
+    (33, 257, 257, True),     # odd numColumnsMax -> per-thread load path
+    (80, 130, 130, True),     # RRS18to6 level count
+    (2, 64, 64, False),       # kmax forced to 1 below: level 1 is surface AND bottom
+])
+@pytest.mark.parametrize("device_mode", [True, False])
+def test_bgc_source_sink_cold_and_warm(o, nL, nC, nCols, ragged, device_mode):
+    ctx, parms = _ctx(nL, nC)
+    po = o.Parms()
+    cols, _, _ = parity.make_bgc(nL, nC, parms, nColumns=nCols, ragged=ragged)
+    if nL == 2:
+        cols.number_of_active_levels[:] = 1
+    parity.poison_outputs(cols)
+    ref = cols.copy()
+    o.BGC_SourceSink(po, ref, True, nthreads=o.max_threads())
+    got = parity.run_gpu_bgc(ctx, cols, device_mode=device_mode)
+    parity.compare_bgc_source_sink(ref, got)
+    # warm brackets: PH_PREV_* from the first pass
+    ref2, got2 = ref.copy(), got.copy()
+    o.BGC_SourceSink(po, ref2, True, nthreads=o.max_threads())
+    got2 = parity.run_gpu_bgc(ctx, got2, device_mode=device_mode)
+    parity.compare_bgc_source_sink(ref2, got2)
+    st = ctx.status()
+    assert st["no_bracket"] == 0 and st["no_convergence"] == 0 and st["nonfinite"] == 0, st
+    ctx.close()
+
+
+def test_bgc_strict_flavour_matches_too(o):
+    ctx, parms = _ctx(40, 192, flavour="strict")
+    po = o.Parms()
+    cols, _, _ = parity.make_bgc(40, 192, parms, ragged=True)
+    ref = cols.copy()
+    o.BGC_SourceSink(po, ref, True, nthreads=o.max_threads())
+    got = parity.run_gpu_bgc(ctx, cols, device_mode=True)
+    errs = parity.compare_bgc_source_sink(ref, got, tol=1e-12)   # no FMA, IEEE divide: much tighter than 1e-10
+    assert max(errs["tend[%d]" % (n + 1)] for n in range(30)) <= 1e-12
+    ctx.close()
+
+
+def test_alt_co2_use_eco_false_zeroes_dic_alt_tendency(o):
+    ctx, parms = _ctx(30, 128)
+    po = o.Parms()
+    cols, _, _ = parity.make_bgc(30, 128, parms)
+    ref = cols.copy()
+    o.BGC_SourceSink(po, ref, False, nthreads=o.max_threads())
+    got = parity.run_gpu_bgc(ctx, cols, device_mode=True, alt_co2_use_eco=False)
+    parity.compare_bgc_source_sink(ref, got)
+    assert np.all(got.BGC_tendencies[:, :, parms.ind.dic_alt_co2_ind - 1] == 0.0)
+    ctx.close()
+
+
+def test_diagnostics_absent_or_partial_do_not_change_tendencies():
+    nL, nC = 40, 256
+    ctx, parms = _ctx(nL, nC)
+    cols, _, _ = parity.make_bgc(nL, nC, parms, ragged=True)
+    full = parity.run_gpu_bgc(ctx, cols, device_mode=False)
+
+    none = cols.copy()
+    host.BGC_SourceSink(ctx, none, True, diagnostics=False)
+    assert np.array_equal(none.BGC_tendencies, full.BGC_tendencies)
+    assert np.array_equal(none.PH_PREV_3D, full.PH_PREV_3D)
+
+    # a handful of diagnostics only (NULL-checked store path of the sweep)
+    part = cols.copy()
+    parity.poison_outputs(part)
+    keep = ("diag_PAR_avg", "diag_photoC", "diag_Jint_Ctot", "diag_zsatcalc", "diag_CaCO3_form_zint", "diag_pH_3D")
+    dg = abi.BgcDiagnostics()
+    for n in keep:
+        setattr(dg, n, abi.dptr(part.diag[n]))
+    cin, cfo, cout = part.c_input(), part.c_forcing(), part.c_output()
+    host.check(ctx.L, ctx.L.bgc_source_sink(ctx.ptr, C.byref(cin), C.byref(cfo), C.byref(cout), C.byref(dg),
+                                            C.c_int(nL), C.c_int(nC), C.c_int(nC), C.c_int(1),
+                                            C.c_int(abi.BGC_MEM_HOST_FORTRAN)))
+    assert np.array_equal(part.BGC_tendencies, full.BGC_tendencies)
+    for n in keep:
+        assert np.array_equal(part.diag[n], full.diag[n]), n
+    for n in part.diag:
+        if n not in keep:
+            assert np.all(part.diag[n] == 7.25), n   # untouched
+    ctx.close()
+
+
+def test_untouched_members_and_inactive_cells(o):
+    """diag_POC_ACCUM / diag_DONr_remin / diag_DOPr_remin are never written (they are never
+    written by the reference either); tendencies and every other BGC diagnostic are zero
+    outside active cells; PH_PREV_* keep their values there (BGC_mod.F90:570, :625-727)."""
+    nL, nC, nCols = 24, 128, 120
+    ctx, parms = _ctx(nL, nC)
+    cols, _, _ = parity.make_bgc(nL, nC, parms, nColumns=nCols, ragged=True)
+    parity.poison_outputs(cols)
+    cols.PH_PREV_3D[...] = 0.0
+    cols.PH_PREV_ALT_CO2_3D[...] = 0.0
+    mask = cols.active_mask()
+    cols.PH_PREV_3D[~mask] = 3.5
+    for dev in (True, False):
+        got = parity.run_gpu_bgc(ctx, cols, device_mode=dev)
+        for n in abi.BGC_DIAG_UNTOUCHED:
+            assert np.all(got.diag[n] == 7.25), n
+        assert np.all(got.BGC_tendencies[~mask] == 0.0)
+        assert np.all(got.PH_PREV_3D[~mask] == 3.5)
+        for n in abi.BGC_DIAG_K2:
+            if n not in abi.BGC_DIAG_UNTOUCHED:
+                assert np.all(got.diag[n][~mask] == 0.0), n
+        for n in abi.BGC_DIAG_KA:
+            assert np.all(got.diag[n][~mask] == 0.0), n
+        land = np.nonzero(~mask.any(axis=0))[0]
+        assert land.size > 0
+        for n in abi.BGC_DIAG_C1:
+            assert np.all(got.diag[n][land] == 0.0), n
+    ctx.close()
+
+
+def test_permuted_tracer_slots(o):
+    """The host chooses the tracer slots (BGC_indices_type): a permutation must only
+    permute the outputs."""
+    nL, nC = 30, 128
+    rng = np.random.default_rng(7)
+    perm = rng.permutation(30)
+    ctx0, parms0 = _ctx(nL, nC)
+    cols0, _, _ = parity.make_bgc(nL, nC, parms0, ragged=True)
+    got0 = parity.run_gpu_bgc(ctx0, cols0, device_mode=True)
+    ctx0.close()
+
+    parms1 = host.Parms()
+    parms1.permute_tracers(perm)
+    ctx1 = host.Context(nL, nC, device=0, parms=parms1)
+    cols1 = cols0.copy()
+    for i in range(30):
+        cols1.BGC_tracers[:, :, perm[i]] = cols0.BGC_tracers[:, :, i]
+    got1 = parity.run_gpu_bgc(ctx1, cols1, device_mode=True)
+    for i in range(30):
+        assert np.array_equal(got1.BGC_tendencies[:, :, perm[i]], got0.BGC_tendencies[:, :, i]), i
+    for n in ("diag_photoC", "diag_POC_REMIN", "diag_Jint_100m_Ntot"):
+        assert np.array_equal(got1.diag[n], got0.diag[n]), n
+    ctx1.close()
+
+
+# ------------------------------------------------------------------ surface fluxes, co2calc
+def test_surface_fluxes_and_side_effects(o):
+    nL, nC = 20, 384
+    ctx, parms = _ctx(nL, nC)
+    po = o.Parms()
+    parms.bgc.parm_Fe_bioavail = 0.5      # makes the in-place Fe scaling visible (BGC_mod.F90:2828-2838)
+    po.bgc.parm_Fe_bioavail = 0.5
+    ctx.set_params(parms)
+    cols, _, _ = parity.make_bgc(nL, nC, parms, nColumns=380)
+    cols.forcing["iceFraction"][:7] = [-0.2, 1.4, 0.3, 0.0, 1.0, 2.0, -1.0]
+    for dev in (True, False):
+        ref, got = cols.copy(), cols.copy()
+        o.BGC_SurfaceFluxes(po, ref, nthreads=o.max_threads())
+        if dev:
+            d = host.DeviceBgcColumns(nL, nC, 380).load(got)
+            host.BGC_SurfaceFluxes(ctx, d)
+            ctx.synchronize()
+            d.store(got)
+        else:
+            host.BGC_SurfaceFluxes(ctx, got)
+        parity.compare_fields(ref.forcing, got.forcing, parity.TOL_TEND, "BGC_forcing",
+                              solver_keys=("gasFlux", "netFlux", "surface_pH", "surface_pH_alt_co2"))
+        parity.compare_fields(ref.flux_diag, got.flux_diag, parity.TOL_TEND, "BGC_flux_diagnostics",
+                              solver_keys=parity.SOLVER_FLUX)
+        assert np.array_equal(got.forcing["iceFraction"][:7], [0.0, 1.0, 0.3, 0.0, 1.0, 1.0, 0.0])
+    ctx.close()
+
+
+@pytest.mark.parametrize("warm", [False, True])
+def test_co2calc_points(o, warm):
+    n = 1 << 16
+    ctx, _ = _ctx(1, 16)
+    pts = pkg.synth_co2_points(n)
+    if warm:
+        cold = o.co2calc_points(pts, nthreads=o.max_threads())
+        pts["phlo"] = cold["ph"] - 0.2
+        pts["phhi"] = cold["ph"] + 0.2
+    r = o.co2calc_points(pts, nthreads=o.max_threads())
+    g = host.co2calc_points(ctx, pts)
+    for k in ("ph", "co2star", "dco2star", "pco2surf", "dpco2"):
+        assert parity.nerr(g[k], r[k]) <= parity.TOL_SOLVER, k
+    # |dH| <= xacc (co2calc.F90:53)
+    assert np.max(np.abs(10.0 ** -g["ph"] - 10.0 ** -r["ph"])) <= 1e-10
+    assert host.co2calc_points(ctx, {k: v[:0] for k, v in pts.items()})["ph"].size == 0   # n = 0
+    ctx.close()
+
+
+# ------------------------------------------------------------------ DMS / MACROS
+def _active(c):
+    k = np.arange(1, c.nLevelsMax + 1)[:, None]
+    kmax = c.number_of_active_levels.copy()
+    kmax[c.nColumns:] = 0
+    return k <= kmax[None, :]
+
+
+@pytest.mark.parametrize("device_mode", [True, False])
+def test_dms_and_macros(o, device_mode):
+    nL, nC, nCols = 45, 258, 255
+    ctx, parms = _ctx(nL, nC)
+    po = o.Parms()
+    _, dms, mac = parity.make_bgc(nL, nC, parms, nColumns=nCols, ragged=True, with_dms=True, with_macros=True)
+    dref, mref = dms.copy(), mac.copy()
+    o.DMS_SourceSink(po, dref, nthreads=o.max_threads())
+    o.DMS_SurfaceFluxes(po, dref)
+    o.MACROS_SourceSink(po, mref, nthreads=o.max_threads())
+    dgot, mgot = dms.copy(), mac.copy()
+    if device_mode:
+        dd = host.DeviceDmsColumns(nL, nC, nCols).load(dgot)
+        md = host.DeviceMacrosColumns(nL, nC, nCols).load(mgot)
+        host.DMS_SourceSink(ctx, dd); host.DMS_SurfaceFluxes(ctx, dd); host.MACROS_SourceSink(ctx, md)
+        ctx.synchronize()
+        dd.store(dgot); md.store(mgot)
+    else:
+        host.DMS_SourceSink(ctx, dgot); host.DMS_SurfaceFluxes(ctx, dgot); host.MACROS_SourceSink(ctx, mgot)
+    for n in range(abi.DMS_TRACER_CNT):
+        assert parity.nerr(dgot.DMS_tendencies[:, :, n], dref.DMS_tendencies[:, :, n]) <= parity.TOL_TEND, n
+    for n in range(abi.MACROS_TRACER_CNT):
+        assert parity.nerr(mgot.MACROS_tendencies[:, :, n], mref.MACROS_tendencies[:, :, n]) <= parity.TOL_TEND, n
+    # DMS / MACROS diagnostics are only defined on active cells (the reference never zeroes them)
+    parity.compare_fields(dref.diag, dgot.diag, parity.TOL_TEND, "DMS diagnostics", mask=_active(dms))
+    parity.compare_fields(mref.diag, mgot.diag, parity.TOL_TEND, "MACROS diagnostics", mask=_active(mac))
+    cm = np.arange(nC) < nCols
+    for nm in dref.flux_diag:
+        assert parity.nerr(dgot.flux_diag[nm][cm], dref.flux_diag[nm][cm]) <= parity.TOL_TEND, nm
+    assert parity.nerr(dgot.forcing["netFlux"][cm], dref.forcing["netFlux"][cm]) <= parity.TOL_TEND
+    ctx.close()
+
+
+# ------------------------------------------------------------------ inventory
+def test_inventory_vector_matches_the_outputs():
+    nL, nC, nCols = 36, 514, 500
+    ctx, parms = _ctx(nL, nC)
+    cols, dms, mac = parity.make_bgc(nL, nC, parms, nColumns=nCols, ragged=True, with_dms=True, with_macros=True)
+    ctx.inventory_enable(True)
+    ctx.inventory_reset()
+    host.BGC_SourceSink(ctx, cols); host.DMS_SourceSink(ctx, dms); host.MACROS_SourceSink(ctx, mac)
+    inv = ctx.inventory_allreduce()     # single rank: a copy
+    mask = cols.active_mask()
+    dz = np.where(mask, cols.cell_thickness, 0.0)
+    want = np.zeros(abi.BGC_INVENTORY_LEN)
+    want[0:30] = np.einsum("kcn,kc->n", cols.BGC_tendencies, dz)
+    want[30:44] = np.einsum("kcn,kc->n", dms.DMS_tendencies, dz)
+    want[44:52] = np.einsum("kcn,kc->n", mac.MACROS_tendencies, dz)
+    for i, nm in enumerate(("Ctot", "100m_Ctot", "Ntot", "100m_Ntot", "Ptot", "100m_Ptot", "Sitot", "100m_Sitot")):
+        want[52 + i] = cols.diag["diag_Jint_" + nm][:nCols].sum()
+    want[60], want[61] = mask.sum(), mask.any(axis=0).sum()
+    scale = np.zeros_like(want)
+    scale[0:30] = np.einsum("kcn,kc->n", np.abs(cols.BGC_tendencies), dz)
+    scale[30:44] = np.einsum("kcn,kc->n", np.abs(dms.DMS_tendencies), dz)
+    scale[44:52] = np.einsum("kcn,kc->n", np.abs(mac.MACROS_tendencies), dz)
+    scale[52:60] = np.abs(cols.diag["diag_Jint_100m_Ctot"][:nCols]).sum() + 1.0
+    scale[60:62] = 1.0
+    assert np.all(np.abs(inv - want)[:62] <= 1e-12 * np.maximum(scale[:62], 1e-300)), (inv - want)[:62]
+    # accumulates across calls until reset; bit-reproducible (no atomics)
+    host.BGC_SourceSink(ctx, cols)
+    inv2 = ctx.inventory_get()
+    ctx.inventory_reset()
+    host.BGC_SourceSink(ctx, cols)
+    inv3 = ctx.inventory_get()
+    assert np.allclose(inv2[:30], inv[:30] + inv3[:30], rtol=1e-13, atol=0)
+    ctx.inventory_reset()
+    host.BGC_SourceSink(ctx, cols)
+    assert np.array_equal(ctx.inventory_get(), inv3)
+    ctx.close()
+
+
+# ------------------------------------------------------------------ full size: properties
+def test_ec60to30_full_size_properties():
+    """235 160 columns x 60 levels, device resident.  The oracle would need minutes here,
+    so check what the algorithm guarantees: element conservation (the code's own Jint
+    integrals vanish to round-off relative to their upper-100 m parts, BGC_mod.F90:1875-1938),
+    slab independence (a sub-slab run alone reproduces the same bits - the sharding
+    property), clean solver status, warm-bracket idempotence of pH."""
+    import torch
+    nL, nC = 60, 235160
+    ctx, parms = _ctx(nL, nC)
+    d = host.DeviceBgcColumns(nL, nC)
+    # fill 8 slabs through a small host container (keeps host memory modest)
+    slab = 29395
+    assert slab * 8 == nC
+    h = pkg.BgcColumns(nL, slab)
+    for s in range(8):
+        pkg.synth_fill(h, bgc_ind=parms.ind, column0=s * slab, ragged=True)
+        sl = slice(s * slab, (s + 1) * slab)
+        d.BGC_tracers[:, :, sl] = torch.from_numpy(np.ascontiguousarray(np.transpose(h.BGC_tracers, (2, 0, 1))))
+        for n in d.K2_IN:
+            getattr(d, n)[:, sl] = torch.from_numpy(np.ascontiguousarray(getattr(h, n)))
+        d.cell_latitude[sl] = torch.from_numpy(h.cell_latitude)
+        d.number_of_active_levels[sl] = torch.from_numpy(h.number_of_active_levels)
+        d.forcing["FESEDFLUX"][:, sl] = torch.from_numpy(np.ascontiguousarray(h.forcing["FESEDFLUX"]))
+        for n in ("dust_FLUX_IN", "ShortWaveFlux_surface"):
+            d.forcing[n][sl] = torch.from_numpy(h.forcing[n])
+    torch.cuda.synchronize()
+    host.BGC_SourceSink(ctx, d)           # cold
+    ctx.synchronize()
+    ph_cold = d.PH_PREV_3D.clone()
+    host.BGC_SourceSink(ctx, d)           # warm
+    ctx.synchronize()
+    st = ctx.status()
+    assert st["no_bracket"] == 0 and st["no_convergence"] == 0, st
+    kmax = d.number_of_active_levels.long()
+    active = torch.arange(nL, device=d.device)[:, None] < kmax[None, :]
+    assert torch.isfinite(d.BGC_tendencies).all()
+    assert (d.BGC_tendencies[:, ~active] == 0).all()
+    # warm-bracket solve lands on the same root (both stop at |dx| < 1e-10 mol/kg)
+    assert (d.PH_PREV_3D - ph_cold)[active].abs().max().item() < 1e-6
+    for el in ("C", "N", "P", "Si"):
+        tot = d.diag["diag_Jint_%stot" % el].abs().max().item()
+        part = d.diag["diag_Jint_100m_%stot" % el].abs().max().item()
+        assert tot <= 1e-10 * part, (el, tot, part)
+    # slab independence: columns [2*slab, 3*slab) alone, bit for bit
+    sl = slice(2 * slab, 3 * slab)
+    sub = host.DeviceBgcColumns(nL, slab)
+    sub.BGC_tracers.copy_(d.BGC_tracers[:, :, sl])
+    for n in d.K2_IN:
+        getattr(sub, n).copy_(getattr(d, n)[:, sl])
+    sub.cell_latitude.copy_(d.cell_latitude[sl])
+    sub.number_of_active_levels.copy_(d.number_of_active_levels[sl])
+    sub.forcing["FESEDFLUX"].copy_(d.forcing["FESEDFLUX"][:, sl])
+    for n in ("dust_FLUX_IN", "ShortWaveFlux_surface"):
+        sub.forcing[n].copy_(d.forcing[n][sl])
+    sub.PH_PREV_3D.copy_(ph_cold[:, sl])
+    sub.PH_PREV_ALT_CO2_3D.copy_(ph_cold[:, sl])   # both solves share inputs (BGC_mod.F90:975): same root
+    ctx2 = host.Context(nL, slab, device=0, parms=parms)
+    host.BGC_SourceSink(ctx2, sub)
+    ctx2.synchronize()
+    assert torch.equal(sub.BGC_tendencies, d.BGC_tendencies[:, :, sl])
+    assert torch.equal(sub.diag["diag_POC_REMIN"], d.diag["diag_POC_REMIN"][:, sl])
+    ctx2.close()
+    ctx.close()
+
+
+# ------------------------------------------------------------------ error behaviour
+def test_error_codes():
+    L = host.lib()
+    ctx = host.Context(8, 32, device=0)          # no parameters yet
+    cols = pkg.BgcColumns(8, 32)
+    with pytest.raises(host.BgcError, match="set_params"):
+        host.BGC_SourceSink(ctx, cols)
+    parms = host.Parms()
+    ctx.set_params(parms)
+    cin, cfo, cout, cdg = cols.c_input(), cols.c_forcing(), cols.c_output(), cols.c_diag()
+    cin.cell_thickness = abi.dptr(None)
+    rc = L.bgc_source_sink(ctx.ptr, C.byref(cin), C.byref(cfo), C.byref(cout), C.byref(cdg), C.c_int(8), C.c_int(32),
+                           C.c_int(32), C.c_int(1), C.c_int(abi.BGC_MEM_HOST_FORTRAN))
+    assert rc == abi.DEFINES["BGC_ERR_ARG"]
+    rc = L.bgc_source_sink(ctx.ptr, C.byref(cols.c_input()), C.byref(cfo), C.byref(cout), C.byref(cdg), C.c_int(8),
+                           C.c_int(32), C.c_int(33), C.c_int(1), C.c_int(abi.BGC_MEM_HOST_FORTRAN))
+    assert rc == abi.DEFINES["BGC_ERR_ARG"]       # numColumns > numColumnsMax
+    ctx.close()
