@@ -455,33 +455,18 @@ static int check_dims(bgc_ctx *c, int nL, int nC, int nCols) {
 }
 
 // ------------------------------------------------------------------ inventory
-// `slots`: the tracer slots (0-based) whose tendency can be non-zero; `off`: where the
-// module's tracers start in the inventory vector.  Slots not listed are identically
-// zero by construction of the reference (DMS_mod.F90:413, MACROS_mod.F90:267).
-static int inventory_add(bgc_ctx *c, const double *tend, const double *dz, const int *kmax, int nL, int nC, int nCols,
-                         const int *slots, int nSlots, int off, bool count, const double *const *colsum, int nColsum) {
-  if (!c->inventory_on || !dz) return BGC_OK;
-  bgc::InventoryArgs ia;
-  memset(&ia, 0, sizeof ia);
-  ia.nL = nL; ia.nC = nC; ia.nColumns = nCols;
-  ia.tend = tend; ia.dz = dz; ia.kmax = kmax;
+// Stage 2 of the inventory reduction (stage 1 is fused into the source-sink kernels, which
+// write one partial per block): add the partials into the ctx inventory vector.
+static int inventory_fold(bgc_ctx *c, const double *partials, int nParts, int nGroups,
+                          const int out_index[][bgc::kInvGroup]) {
+  bgc::InventoryFoldArgs fa;
+  memset(&fa, 0, sizeof fa);
+  fa.nGroups = nGroups;
   for (int g = 0; g < bgc::kInvMaxGroups; ++g)
-    for (int j = 0; j < bgc::kInvGroup; ++j) { ia.slot[g][j] = -1; ia.out_index[g][j] = -1; }
-  ia.count_out = count ? 60 : -1;
-  int g = 0, j = 0;
-  for (int i = 0; i < nSlots; ++i) {
-    const int cap = (g == 0 && count) ? bgc::kInvGroup - 2 : bgc::kInvGroup;
-    if (j == cap) { ++g; j = 0; }
-    if (g >= bgc::kInvMaxGroups) return fail(BGC_ERR_ARG, "inventory: too many tracer slots");
-    ia.slot[g][j] = slots[i]; ia.out_index[g][j] = off + slots[i]; ++j;
-  }
-  ia.nGroups = nSlots ? g + 1 : 0;
-  for (int q = 0; q < nColsum && q < bgc::kInvGroup; ++q) ia.colsum[q] = colsum[q];
-  ia.colsum_out = 52;
-  const size_t need = (size_t)bgc::inventory_grid(nCols) * (bgc::kInvMaxGroups + 1) * bgc::kInvGroup;
-  RC(arena_d(c, "inv_partials", need, &ia.partials));
-  ia.inventory = c->d_inventory;
-  LAUNCH(BGC_K_INVENTORY, 2, bgc::launch_inventory(ia, c->stream));
+    for (int j = 0; j < bgc::kInvGroup; ++j) fa.out_index[g][j] = (g < nGroups) ? out_index[g][j] : -1;
+  fa.partials = partials;
+  fa.inventory = c->d_inventory;
+  LAUNCH(BGC_K_INVENTORY, 1, bgc::launch_inventory_fold(fa, nParts, c->stream));
   return BGC_OK;
 }
 
@@ -586,15 +571,32 @@ static int source_sink_device(bgc_ctx *c, const BgcInput *in, const BgcForcing *
       break;
     }
   }
-  LAUNCH(BGC_K_ECO_COLUMNS, 1, bgc::launch_eco_columns(ea, diag_mode, c->eco_variant, c->stream));
-
+  ea.inv_partials = nullptr;
+  int inv_parts = 0;
   if (c->inventory_on) {
-    int slots[BGC_TRACER_CNT];
-    for (int n = 0; n < BGC_TRACER_CNT; ++n) slots[n] = n;
-    const double *cols[8] = {d.diag_Jint_Ctot, d.diag_Jint_100m_Ctot, d.diag_Jint_Ntot, d.diag_Jint_100m_Ntot,
-                             d.diag_Jint_Ptot, d.diag_Jint_100m_Ptot, d.diag_Jint_Sitot, d.diag_Jint_100m_Sitot};
-    RC(inventory_add(c, out->BGC_tendencies, in->cell_thickness, in->number_of_active_levels, nL, nC, nCols,
-                     slots, BGC_TRACER_CNT, 0, true, cols, 8));
+    inv_parts = bgc::eco_inventory_parts(ea, diag_mode, c->eco_variant);
+    RC(arena_d(c, "inv_partials_bgc", (size_t)inv_parts * bgc::kEcoInvGroups * bgc::kInvGroup, &ea.inv_partials));
+  }
+  LAUNCH(BGC_K_ECO_COLUMNS, 1, bgc::launch_eco_columns(ea, diag_mode, c->eco_variant, c->stream));
+  if (c->inventory_on) {
+    // destination of every value the sweep produced (layout: bgc_kernels.cuh, kEcoInvGroups)
+    const BgcIndices &I = c->bgc_tab.ind;
+    int oi[bgc::kEcoInvGroups][bgc::kInvGroup];
+    const int plain[16] = {I.no3_ind, I.nh4_ind, I.fe_ind, I.sio3_ind, I.po4_ind, I.zooC_ind, I.doc_ind, I.don_ind,
+                           I.donr_ind, I.dop_ind, I.dopr_ind, I.dofe_ind, I.dic_ind, I.dic_alt_co2_ind, I.alk_ind,
+                           I.o2_ind};   // kEcoInvPlainOrder
+    for (int j = 0; j < 16; ++j) oi[j / 8][j % 8] = plain[j] - 1;
+    int row = 0;
+    for (int j = 0; j < 16; ++j) oi[2 + j / 8][j % 8] = -1;
+    for (int g = 0; g < BGC_AUTOTROPH_CNT; ++g) {
+      const BgcAutotroph &at = c->bgc_tab.a[g];
+      const int ind[5] = {at.Chl_ind, at.C_ind, at.Fe_ind, at.Si_ind, at.CaCO3_ind};
+      for (int j = 0; j < 5; ++j)
+        if (ind[j] > 0 && row < 14) { oi[2 + row / 8][row % 8] = ind[j] - 1; ++row; }
+    }
+    oi[3][6] = 60; oi[3][7] = 61;                       // active cells, active columns
+    for (int j = 0; j < 8; ++j) oi[4][j] = any_diag ? 52 + j : -1;   // the Jint_* sums exist only with diagnostics
+    RC(inventory_fold(c, ea.inv_partials, inv_parts, bgc::kEcoInvGroups, oi));
   }
   return BGC_OK;
 }
@@ -789,11 +791,16 @@ static int dms_source_sink_device(bgc_ctx *c, const DmsInput *in, const DmsForci
   a.tracers = in->DMS_tracers; a.dz = in->cell_thickness; a.kmax = in->number_of_active_levels;
   a.sst = fo->SST; a.sw_flux = fo->ShortWaveFlux_surface; a.tend = out->DMS_tendencies;
   if (diag) a.d = *diag; else memset(&a.d, 0, sizeof a.d);
+  const bool inv = c->inventory_on;
+  a.inv_partials = nullptr;
+  if (inv) RC(arena_d(c, "inv_partials_dms", (size_t)bgc::dms_inventory_parts(nC) * bgc::kInvGroup, &a.inv_partials));
   LAUNCH(BGC_K_DMS_COLUMNS, 1, bgc::launch_dms_columns(a, c->stream));
-  {   // only DMS and DMSP have non-zero tendencies (DMS_mod.F90:413, :741-742)
-    const int slots[2] = {c->dms_tab.ind.dms_ind - 1, c->dms_tab.ind.dmsp_ind - 1};
-    RC(inventory_add(c, out->DMS_tendencies, in->cell_thickness, in->number_of_active_levels, nL, nC, nCols,
-                     slots, 2, 30, false, nullptr, 0));
+  if (inv) {   // only DMS and DMSP have non-zero tendencies (DMS_mod.F90:413, :741-742)
+    int oi[1][bgc::kInvGroup];
+    for (int j = 0; j < bgc::kInvGroup; ++j) oi[0][j] = -1;
+    oi[0][0] = 30 + c->dms_tab.ind.dms_ind - 1;
+    oi[0][1] = 30 + c->dms_tab.ind.dmsp_ind - 1;
+    RC(inventory_fold(c, a.inv_partials, bgc::dms_inventory_parts(nC), 1, oi));
   }
   return BGC_OK;
 }
@@ -897,11 +904,18 @@ static int macros_device(bgc_ctx *c, const MacrosInput *in, MacrosOutput *out, c
   a.nL = nL; a.nC = nC; a.nColumns = nCols;
   a.tracers = in->MACROS_tracers; a.kmax = in->number_of_active_levels; a.tend = out->MACROS_tendencies;
   if (diag) a.d = *diag; else memset(&a.d, 0, sizeof a.d);
+  const bool inv = c->inventory_on && in->cell_thickness;
+  a.dz = in->cell_thickness;
+  a.inv_partials = nullptr;
+  if (inv) RC(arena_d(c, "inv_partials_macros", (size_t)bgc::macros_inventory_parts(nL, nC) * bgc::kInvGroup, &a.inv_partials));
   LAUNCH(BGC_K_MACROS_CELLS, 1, bgc::launch_macros_cells(a, c->stream));
-  {   // only PROT, POLY and LIP have non-zero tendencies (MACROS_mod.F90:267, :389-391)
-    const int slots[3] = {c->macros_tab.ind.prot_ind - 1, c->macros_tab.ind.poly_ind - 1, c->macros_tab.ind.lip_ind - 1};
-    RC(inventory_add(c, out->MACROS_tendencies, in->cell_thickness, in->number_of_active_levels, nL, nC, nCols,
-                     slots, 3, 44, false, nullptr, 0));
+  if (inv) {   // only PROT, POLY and LIP have non-zero tendencies (MACROS_mod.F90:267, :389-391)
+    int oi[1][bgc::kInvGroup];
+    for (int j = 0; j < bgc::kInvGroup; ++j) oi[0][j] = -1;
+    oi[0][0] = 44 + c->macros_tab.ind.prot_ind - 1;
+    oi[0][1] = 44 + c->macros_tab.ind.poly_ind - 1;
+    oi[0][2] = 44 + c->macros_tab.ind.lip_ind - 1;
+    RC(inventory_fold(c, a.inv_partials, bgc::macros_inventory_parts(nL, nC), 1, oi));
   }
   return BGC_OK;
 }

@@ -16,6 +16,7 @@
 // slow lane costs its own warp a few extra passes, never the whole block.
 #pragma once
 #include <cuda_runtime.h>
+#include "bgc_math.cuh"
 
 namespace bgc {
 
@@ -72,22 +73,22 @@ __device__ __forceinline__ void co3_coeffs(bool deep, double depth, double temp,
   const double tk = kT0Kelvin + temp;
   const double tk100 = tk * 1e-2;
   const double tk1002 = tk100 * tk100;
-  const double invtk = 1.0 / tk;
+  const double invtk = frcp(tk);
   const double dlogtk = log(tk);
   const double invRtk = (1.0 / 83.1451) * invtk;
 
-  const double is = 19.924 * salt_lim / (1000.0 - 1.005 * salt_lim);
+  const double is = fdiv(19.924 * salt_lim, (1000.0 - 1.005 * salt_lim));
   const double is2 = is * is;
   const double sqrtis = sqrt(is);
   const double sqrts = sqrt(salt_lim);
   const double s2 = salt_lim * salt_lim;
-  const double scl = salt_lim / 1.80655;
+  const double scl = cdiv(salt_lim, 1.80655, 1.0 / 1.80655);
 
   const double log_1_m_1p005em3_s = log(1.0 - 0.001005 * salt_lim);
   double arg;
 
   if (WANT_FF) {   // Weiss & Price 1980, co2calc.F90:423-431
-    arg = -162.8301 + 218.2968 / tk100 + 90.9241 * (dlogtk + kLn1em2) - 1.47696 * tk1002 +
+    arg = -162.8301 + fdiv(218.2968, tk100) + 90.9241 * (dlogtk + kLn1em2) - 1.47696 * tk1002 +
           salt_lim * (.025695 - .025225 * tk100 + 0.0049867 * tk1002);
     c.ff = exp(arg);
   } else {
@@ -152,7 +153,7 @@ __device__ __forceinline__ void co3_coeffs(bool deep, double depth, double temp,
   }
 
   // kf, Dickson & Riley 1979, uses the (corrected) ks (co2calc.F90:740-764)
-  arg = 1.0 + (0.1400 / 96.062) * (scl) / c.ks;
+  arg = 1.0 + fdiv((0.1400 / 96.062) * (scl), c.ks);
   const double log_1_p_tot_sulfate_div_ks = log(arg);
   arg = 1590.2 * invtk - 12.641 + 1.525 * sqrtis + log_1_m_1p005em3_s + log_1_p_tot_sulfate_div_ks;
   c.kf = exp(arg);
@@ -175,8 +176,8 @@ __device__ __forceinline__ TalkInv talk_invariants(const Co3Consts &k) {
   t.k12 = k.k1 * k.k2;
   t.k12p = k.k1p * k.k2p;
   t.k123p = t.k12p * k.k3p;
-  t.c = 1.0 + k.st / k.ks;
-  t.c_r = 1.0 / t.c;
+  t.c = 1.0 + fdiv(k.st, k.ks);
+  t.c_r = frcp(t.c);
   t.cks_ = t.c * k.ks;
   return t;
 }
@@ -185,22 +186,22 @@ __device__ __forceinline__ TalkInv talk_invariants(const Co3Consts &k) {
 __device__ __forceinline__ void talk_residual(const Co3Consts &k, const Co3Totals &t, const TalkInv &v,
                                               double x, double &fn, double &df) {
   const double x1 = x;
-  const double x1_r = 1.0 / x1;
+  const double x1_r = frcp(x1);
   const double x2 = x1 * x1;
   const double x2_r = x1_r * x1_r;
   const double x3 = x2 * x1;
   const double a = x3 + k.k1p * x2 + v.k12p * x1 + v.k123p;
-  const double a_r = 1.0 / a;
+  const double a_r = frcp(a);
   const double a2_r = a_r * a_r;
   const double da = 3.0 * x2 + 2.0 * k.k1p * x1 + v.k12p;
   const double b = x2 + k.k1 * x1 + v.k12;
-  const double b_r = 1.0 / b;
+  const double b_r = frcp(b);
   const double b2_r = b_r * b_r;
   const double db = 2.0 * x1 + k.k1;
-  const double kb_p_x1_r = 1.0 / (k.kb + x1);
-  const double ksi_p_x1_r = 1.0 / (k.ksi + x1);
-  const double c1_p_c_ks_x1_r_r = 1.0 / (1.0 + v.cks_ * x1_r);
-  const double c1_p_kf_x1_r_r = 1.0 / (1.0 + k.kf * x1_r);
+  const double kb_p_x1_r = frcp(k.kb + x1);
+  const double ksi_p_x1_r = frcp(k.ksi + x1);
+  const double c1_p_c_ks_x1_r_r = frcp(1.0 + v.cks_ * x1_r);
+  const double c1_p_kf_x1_r_r = frcp(1.0 + k.kf * x1_r);
 
   fn = k.k1 * t.dic * x1 * b_r
      + 2.0 * t.dic * v.k12 * b_r
@@ -262,9 +263,9 @@ __device__ __forceinline__ double solve_htotal(const Co3Consts &k, const Co3Tota
       break;
     }
     if (same_sign) {
-      const double dxg = sqrt(x2 / x1);
+      const double dxg = sqrt(fdiv(x2, x1));
       x2 = x2 * dxg;
-      x1 = x1 / dxg;
+      x1 = fdiv(x1, dxg);
       talk_residual(k, t, v, x1, flo, df);
       talk_residual(k, t, v, x2, fhi, df);
       same_sign = (flo > 0.0 && fhi > 0.0) || (flo < 0.0 && fhi < 0.0);
@@ -291,7 +292,7 @@ __device__ __forceinline__ double solve_htotal(const Co3Consts &k, const Co3Tota
         soln = xlo + dx;
         if (xlo == soln) live = false;
       } else {
-        dx = -f / df;
+        dx = fdiv(-f, df);
         const double prev = soln;
         soln = soln + dx;
         if (prev == soln) live = false;
@@ -317,8 +318,8 @@ __device__ __forceinline__ void co3_sat_vals(bool deep, double depth, double tem
   const double press_bar = press_bar_of_depth(depth);
   const double salt_lim = fmax(salt, kSaltMin);
   const double tk = kT0Kelvin + temp;
-  const double log10tk = log(tk) / kLn10;   // :1161-1164
-  const double invtk = 1.0 / tk;
+  const double log10tk = cdiv(log(tk), kLn10, 1.0 / kLn10);   // :1161-1164
+  const double invtk = frcp(tk);
   const double invRtk = (1.0 / 83.1451) * invtk;
   const double sqrts = sqrt(salt_lim);
   const double s15 = sqrts * salt_lim;
@@ -340,7 +341,7 @@ __device__ __forceinline__ void co3_sat_vals(bool deep, double depth, double tem
     K_arag *= kfac(deltaV, Kappa, press_bar, invRtk);
   }
 
-  const double inv_Ca = (35.0 / 0.01028) / salt_lim;
+  const double inv_Ca = fdiv((35.0 / 0.01028), salt_lim);
   co3_sat_calc = (K_calc * inv_Ca) * kMassToVol;
   co3_sat_arag = (K_arag * inv_Ca) * kMassToVol;
 }

@@ -26,6 +26,10 @@ cudaError_t upload_bgc_tables(const BgcTables &t, cudaStream_t s);
 cudaError_t upload_dms_tables(const DmsTables &t, cudaStream_t s);
 cudaError_t upload_macros_tables(const MacrosTables &t, cudaStream_t s);
 
+constexpr int kInvGroup = 8;        // inventory: values per group (tracer slots; group 0 may end with the two counters)
+constexpr int kInvMaxGroups = 6;
+constexpr int kEcoInvGroups = 5;   // inventory groups produced by the column sweep (see below)
+
 // ---- carbonate kernel, one thread per CELL (no vertical coupling)
 struct Co3Args {
   int nL, nC, nColumns;
@@ -54,11 +58,13 @@ struct EcoArgs {
   double *tend;                          // (k,col,30)
   BgcDiagnostics d;                      // carbonate + never-touched members nulled by the caller
   unsigned long long *status;
+  double *inv_partials;                  // NULL, or the fused stage 1 of the inventory reduction
 };
 // diag_mode: 0 = no diagnostic array, 1 = any subset (NULL-checked stores), 2 = every array
 // the kernel owns is present (unchecked stores).  variant selects the launch shape
 // (k_eco.cu: launch_diag); 0 = default.
 cudaError_t launch_eco_columns(const EcoArgs &a, int diag_mode, int variant, cudaStream_t s);
+int eco_inventory_parts(const EcoArgs &a, int diag_mode, int variant);   // blocks the launch will use
 
 // ---- surface fluxes, one thread per column
 struct SurfArgs {
@@ -87,6 +93,7 @@ struct DmsArgs {
   const double *sst, *sw_flux;
   double *tend;
   DmsDiagnostics d;
+  double *inv_partials;   // NULL, or [dms_inventory_parts][kInvGroup]: fused stage 1 of the inventory
 };
 cudaError_t launch_dms_columns(const DmsArgs &a, cudaStream_t s);
 
@@ -104,6 +111,8 @@ struct MacrosArgs {
   const int *kmax;
   double *tend;
   MacrosDiagnostics d;
+  const double *dz;       // read only for the inventory
+  double *inv_partials;   // NULL, or [macros_inventory_parts][kInvGroup]
 };
 cudaError_t launch_macros_cells(const MacrosArgs &a, cudaStream_t s);
 
@@ -112,22 +121,19 @@ cudaError_t launch_transpose(const double *src, double *dst, int rows_fast_src, 
                              int nSlabs, cudaStream_t s);
 
 // ---- inventory: sum_col sum_k tend(n)*dz over active cells (+ sums of per-column
-// diagnostics), deterministic, accumulated into the ctx inventory vector
-constexpr int kInvGroup = 8;        // values per group (tracer slots, or 6 slots + the two counters in group 0)
-constexpr int kInvMaxGroups = 6;
-struct InventoryArgs {
-  int nL, nC, nColumns, nGroups;
-  const double *tend, *dz;
-  const int *kmax;
-  int slot[kInvMaxGroups][kInvGroup];        // 0-based tracer slot, -1 = unused
-  int out_index[kInvMaxGroups][kInvGroup];   // destination in the inventory vector
-  int count_out;                             // >= 0: group 0's last two values are (active cells, active columns)
-  const double *colsum[kInvGroup];           // per-column arrays summed as one extra group (NULL = unused)
-  int colsum_out;
-  double *partials;                          // [inventory_grid][groups][kInvGroup]
+// diagnostics).  Stage 1 is fused into the source-sink kernels (block partials); stage 2:
+struct InventoryFoldArgs {
+  int nGroups;                               // partial layout [nParts][nGroups][kInvGroup]
+  int out_index[kInvMaxGroups][kInvGroup];   // destination in the inventory vector, -1 = ignore
+  const double *partials;
   double *inventory;                         // accumulated into (+=)
 };
-int inventory_grid(int nColumns);
-cudaError_t launch_inventory(const InventoryArgs &a, cudaStream_t s);
+cudaError_t launch_inventory_fold(const InventoryFoldArgs &a, int nParts, cudaStream_t s);
+int dms_inventory_parts(int nC);
+int macros_inventory_parts(int nL, int nC);
+// column sweep: [eco_inventory_parts][kEcoInvGroups][kInvGroup]
+//   groups 0,1: the 16 plain tracers in the order of kEcoInvPlainOrder (k_eco.cu / bgc_capi.cu)
+//   groups 2,3: the 14 functional-group tracers (row = order of appearance: group 1..4, Chl C Fe Si CaCO3),
+//               then active cells, active columns;   group 4: the eight Jint_* column sums
 
 }  // namespace bgc

@@ -38,6 +38,7 @@
 // saturation concentrations for the saturation-depth scan (:1003-1032).
 #include "bgc_kernels.cuh"
 #include "bgc_math.cuh"
+#include "bgc_reduce.cuh"
 
 namespace bgc {
 
@@ -49,6 +50,7 @@ struct EcoDerived {
   double r_dTN[4], r_dTS[4];
   double r_o2_min_delta;
   double r_scalelen_dz[4];
+  int inv_row[4][5];   // inventory: row (0..13) of the group's Chl, C, Fe, Si, CaCO3 tracer; -1 = none
 };
 
 __constant__ BgcTables c_eco;
@@ -72,6 +74,12 @@ cudaError_t upload_bgc_tables_eco(const BgcTables &t, cudaStream_t s) {
     d.agg_min_dps[a] = at.agg_rate_min * dps;
     d.r_dTN[a] = 1.0 / (at.temp_thresN - at.temp_optN);
     d.r_dTS[a] = 1.0 / (at.temp_thresS - at.temp_optS);
+  }
+  int row = 0;
+  for (int a = 0; a < BGC_AUTOTROPH_CNT; ++a) {
+    const BgcAutotroph &at = t.a[a];
+    const int ind[5] = {at.Chl_ind, at.C_ind, at.Fe_ind, at.Si_ind, at.CaCO3_ind};
+    for (int j = 0; j < 5; ++j) d.inv_row[a][j] = (ind[j] > 0 && row < 14) ? row++ : -1;
   }
   d.r_o2_min_delta = 1.0 / t.p.parm_o2_min_delta;
   d.r_scalelen_dz[0] = 0.0;
@@ -183,10 +191,11 @@ static_assert((0 ECO_DIAG_K2_LIST(COUNT_ONE)) + 13 == (0 BGC_DIAG_K2_LIST(COUNT_
 // Shared memory of a block, in rows of BLOCK doubles (one slot per thread):
 //   2 stages x R_ROWS   the level's input slab: rows 0..29 = tracer slots, then the rows below
 //   X_ROWS              per-thread scratch: Pprime(4); DIAG: the three per-group column
-//                       integrals (:1838-1846, :1268), 4 each
+//                       integrals (:1838-1846, :1268), 4 each; inventory: sum_k tendency*dz of
+//                       the 14 functional-group tracers
 //   2 mbarriers
 enum { R_T = BGC_TRACER_CNT, R_ZMID, R_DZ, R_ZBOT, R_FESED, R_S, R_CO3, R_SATC, R_SATA, R_ROWS };
-enum { X_PPRIME = 0, X_ZPHOTO = 4, X_ZNO3 = 8, X_ZCACO3 = 12, X_ROWS = 16 };
+enum { X_PPRIME = 0, X_ZPHOTO = 4, X_ZNO3 = 8, X_ZCACO3 = 12, X_INV = 16, X_ROWS = 30 };
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
@@ -271,6 +280,16 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
 
   double *tnd = A.tend + col;
 
+  // ---- inventory (fused stage 1): sum_k tendency*dz.  The 14 functional-group tracers are
+  //      accumulated per thread in shared memory (run-time slot); the 16 plain tracers go through
+  //      a warp-level transpose every level and live as ONE register per lane.
+  const bool inv = A.inv_partials != nullptr;
+  double inv_plain = 0.0;
+  if (inv) {
+#pragma unroll
+    for (int r = 0; r < 14; ++r) XS(X_INV + r) = 0.0;
+  }
+
   // ---- deepest active level of the block: nothing below it is fetched
   __shared__ int s_kmax_blk;
   if (tid == 0) {
@@ -286,30 +305,41 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
   // tracer slots the sweep never reads: DIC, ALK (carbonate kernel only) and DIC_ALT_CO2 (dead, :748)
   const unsigned skip_slots = (1u << (I.dic_ind - 1)) | (1u << (I.alk_ind - 1)) | (1u << (I.dic_alt_co2_ind - 1));
 
-  // Fetch level `kk` of every input array into stage `kk & 1` (one elected thread).
+  // Fetch level `kk` of every input array into stage `kk & 1`.  Lane 0 of every warp issues a
+  // share of the bulk copies (rows w, w + NW, ...) so that no single warp carries the whole
+  // issue cost; thread 0 also arms the mbarrier with the byte count of the whole level.  (A
+  // copy that lands before the arm only drives the transaction count negative for a moment:
+  // the phase cannot complete before thread 0's arrival.)
+  constexpr int NW = BLOCK / 32;
   auto fetch_level = [&](int kk) {
+    if (tid & 31) return;
     double *dst = smem + (size_t)(kk & 1) * R_ROWS * BLOCK;
     const unsigned bar = smem_u32(&bars[kk & 1]);
     const size_t off = (size_t)nC * (size_t)kk + (size_t)col0;
-    const int nrows = (BGC_TRACER_CNT - 3) + 5 + (DIAG ? 4 : 0);
-    mbar_expect_tx(bar, slab_bytes * (unsigned)nrows);
-    const double *src = A.tracers + off;
+    if (tid == 0) mbar_expect_tx(bar, slab_bytes * (unsigned)((BGC_TRACER_CNT - 3) + 5 + (DIAG ? 4 : 0)));
 #pragma unroll 1
-    for (int n = 0; n < BGC_TRACER_CNT; ++n, src += nLnC)
-      if (!((skip_slots >> n) & 1u)) bulk_g2s(smem_u32(dst + n * BLOCK), src, slab_bytes, bar);
-    bulk_g2s(smem_u32(dst + R_T * BLOCK), A.T + off, slab_bytes, bar);
-    bulk_g2s(smem_u32(dst + R_ZMID * BLOCK), A.zmid + off, slab_bytes, bar);
-    bulk_g2s(smem_u32(dst + R_DZ * BLOCK), A.dz + off, slab_bytes, bar);
-    bulk_g2s(smem_u32(dst + R_ZBOT * BLOCK), A.zbot + off, slab_bytes, bar);
-    bulk_g2s(smem_u32(dst + R_FESED * BLOCK), A.fesedflux + off, slab_bytes, bar);
-    if (DIAG) {
-      bulk_g2s(smem_u32(dst + R_S * BLOCK), A.S + off, slab_bytes, bar);
-      bulk_g2s(smem_u32(dst + R_CO3 * BLOCK), A.co3 + off, slab_bytes, bar);
-      bulk_g2s(smem_u32(dst + R_SATC * BLOCK), A.sat_calc + off, slab_bytes, bar);
-      bulk_g2s(smem_u32(dst + R_SATA * BLOCK), A.sat_arag + off, slab_bytes, bar);
+    for (int r = tid >> 5; r < (DIAG ? R_ROWS : R_S); r += NW) {
+      const double *src;
+      if (r < BGC_TRACER_CNT) {
+        if ((skip_slots >> r) & 1u) continue;
+        src = A.tracers + (size_t)r * nLnC;
+      } else {
+        switch (r) {
+          case R_T:     src = A.T; break;
+          case R_ZMID:  src = A.zmid; break;
+          case R_DZ:    src = A.dz; break;
+          case R_ZBOT:  src = A.zbot; break;
+          case R_FESED: src = A.fesedflux; break;
+          case R_S:     src = A.S; break;
+          case R_CO3:   src = A.co3; break;
+          case R_SATC:  src = A.sat_calc; break;
+          default:      src = A.sat_arag; break;
+        }
+      }
+      bulk_g2s(smem_u32(dst + r * BLOCK), src + off, slab_bytes, bar);
     }
   };
-  if (TMA && tid == 0) {
+  if (TMA) {
     if (kmax_blk > 0) fetch_level(0);
     if (kmax_blk > 1) fetch_level(1);
   }
@@ -334,6 +364,10 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
 
     if (k >= kmax) {
       // ---- inactive cell: the reference's whole-array zero fills
+      if (inv && k < kmax_blk) {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) IN(q) = 0.0;   // this column's share of the level's inventory sums
+      }
       if (in_range) {
 #pragma unroll 6
         for (int n = 0; n < BGC_TRACER_CNT; ++n) tnd[o2 + (size_t)n * nLnC] = 0.0;
@@ -747,20 +781,28 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
       {
         const double w = auto_graze + auto_loss + auto_agg;
         const double t_autoC = photoC - w;
+        const double t_autoChl = photoacc - thetaC * w, t_autoFe = photoFe - Qfe * w;
         TEND(at.C_ind) = t_autoC;
-        TEND(at.Chl_ind) = photoacc - thetaC * w;
-        TEND(at.Fe_ind) = photoFe - Qfe * w;
+        TEND(at.Chl_ind) = t_autoChl;
+        TEND(at.Fe_ind) = t_autoFe;
         s_tC = s_tC + t_autoC;
         s_QpC = s_QpC + at.Qp * t_autoC;
+        if (inv) {
+          XS(X_INV + D.inv_row[a][0]) += t_autoChl * dz;
+          XS(X_INV + D.inv_row[a][1]) += t_autoC * dz;
+          XS(X_INV + D.inv_row[a][2]) += t_autoFe * dz;
+        }
         if (has_Si) {
           const double t = photoSi - Qsi * w;
           TEND(at.Si_ind) = t;
           s_tSi = s_tSi + t;
+          if (inv) XS(X_INV + D.inv_row[a][3]) += t * dz;
         }
         if (has_Ca) {
           const double t = CaCO3_PROD - QCaCO3 * w;
           TEND(at.CaCO3_ind) = t;
           s_tCaCO3 = s_tCaCO3 + t;
+          if (inv) XS(X_INV + D.inv_row[a][4]) += t * dz;
         }
       }
 
@@ -1064,6 +1106,14 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
     TEND(I.dic_alt_co2_ind) = t_dic_alt;
     TEND(I.alk_ind) = t_alk;
     TEND(I.o2_ind) = t_o2;
+    if (inv) {
+      // Every tracer input of this level has been consumed: rows 0..15 of the stage become the
+      // scratch of the inventory transpose below.  Order = kEcoInvPlainOrder.
+      IN(0) = t_no3 * dz; IN(1) = t_nh4 * dz; IN(2) = t_fe * dz; IN(3) = t_sio3 * dz;
+      IN(4) = t_po4 * dz; IN(5) = t_zooC * dz; IN(6) = t_doc * dz; IN(7) = t_don * dz;
+      IN(8) = t_donr * dz; IN(9) = t_dop * dz; IN(10) = t_dopr * dz; IN(11) = t_dofe * dz;
+      IN(12) = t_dic * dz; IN(13) = t_dic_alt * dz; IN(14) = t_alk * dz; IN(15) = t_o2 * dz;
+    }
 
     // ---- diagnostics and column integrals (:1796-1945)
     if (DIAG) {
@@ -1131,13 +1181,26 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
 #undef TR
 #undef TEND
     }   // active cell
+    if (inv && k < kmax_blk) {   // block-uniform condition
+      // Transpose through shared memory: lane l adds row (l & 15) over 16 of the warp's 32
+      // columns (skewed start: conflict-free), then the two halves meet.  Lanes l and l ^ 16
+      // both end up with the warp's sum of plain tracer (l & 15); fixed order, no atomics.
+      __syncwarp();
+      const int lane = tid & 31, row = lane & 15;
+      const double *src = st + row * BLOCK + (tid & ~31) + (lane & 16);
+      double d = 0.0;
+#pragma unroll
+      for (int c = 0; c < 16; ++c) d += src[(c + row) & 15];
+      d += __shfl_xor_sync(0xffffffffu, d, 16);
+      inv_plain += d;
+    }
 
     // ---- end of level: every thread is done with stage k&1 (generic-proxy reads and the
     //      in-place mask writes) before the TMA unit refills it with level k+2.  The same
     //      barrier keeps the block's warps on one stretch of code (I-cache).
     if (TMA) fence_proxy_async();
     __syncthreads();
-    if (TMA && tid == 0 && k + 2 < kmax_blk) fetch_level(k + 2);
+    if (TMA && k + 2 < kmax_blk) fetch_level(k + 2);
   }   // level loop
 
   // ---- per-column diagnostics
@@ -1168,6 +1231,36 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
     }
   }
   if (poc_errors && A.status) atomicAdd(&A.status[2], (unsigned long long)poc_errors);
+
+  // ---- inventory partials of this block: [kEcoInvGroups][kInvGroup]
+  if (inv) {
+    __shared__ double s_red[BLOCK / 32];
+    __shared__ double s_plain[BLOCK / 32][16];
+    double *out = A.inv_partials + (size_t)blockIdx.x * (kEcoInvGroups * kInvGroup);
+    if ((tid & 31) < 16) s_plain[tid >> 5][tid & 15] = inv_plain;
+    __syncthreads();
+    if (tid < 16) {
+      double t = 0.0;
+#pragma unroll
+      for (int w = 0; w < BLOCK / 32; ++w) t += s_plain[w][tid];
+      out[tid] = t;                                   // groups 0 and 1
+    }
+#pragma unroll 1
+    for (int r = 0; r < 14; ++r) {
+      const double t = block_sum(XS(X_INV + r), s_red);
+      if (tid == 0) out[16 + r] = t;                  // groups 2 and 3
+    }
+    {
+      const double cells = block_sum((double)kmax, s_red), cols = block_sum(kmax > 0 ? 1.0 : 0.0, s_red);
+      if (tid == 0) { out[30] = cells; out[31] = cols; }
+    }
+    const double jv[8] = {JC, JC100, JN, JN100, JP, JP100, JSi, JSi100};   // zero without diagnostics
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const double t = block_sum(DIAG ? jv[q] : 0.0, s_red);
+      if (tid == 0) out[32 + q] = t;                  // group 4
+    }
+  }
 #undef XS
 #undef IN
 }
@@ -1194,17 +1287,29 @@ bool slabs_are_bulk_copyable(const EcoArgs &a, bool diag) {
   return true;
 }
 
+// 0 (default): one 8-warp block per SM; 1: two 4-warp blocks per SM; 9: force the per-thread
+// load path (also taken whenever the slabs are not bulk-copyable)
+int block_of(const EcoArgs &a, bool diag, int variant, bool *tma_out) {
+  const bool tma = slabs_are_bulk_copyable(a, diag) && variant != 9;
+  if (tma_out) *tma_out = tma;
+  return (tma && variant != 1) ? 256 : 128;
+}
+
 template <int DIAG>
 cudaError_t launch_diag(const EcoArgs &a, int variant, cudaStream_t s) {
-  const bool tma = slabs_are_bulk_copyable(a, DIAG != 0) && variant != 9;
+  bool tma;
+  const int block = block_of(a, DIAG != 0, variant, &tma);
   if (!tma) return launch_variant<DIAG, 128, 2, false>(a, s);
-  switch (variant) {
-    case 1:  return launch_variant<DIAG, 256, 1, true>(a, s);    // one 8-warp block per SM
-    default: return launch_variant<DIAG, 128, 2, true>(a, s);    // two 4-warp blocks per SM
-  }
+  if (block == 256) return launch_variant<DIAG, 256, 1, true>(a, s);
+  return launch_variant<DIAG, 128, 2, true>(a, s);
 }
 
 }  // namespace
+
+int eco_inventory_parts(const EcoArgs &a, int diag_mode, int variant) {
+  const int block = block_of(a, diag_mode != 0, variant, nullptr);
+  return (a.nC + block - 1) / block;
+}
 
 // diag_mode: 0 none, 1 some (NULL-checked stores), 2 every array present
 cudaError_t launch_eco_columns(const EcoArgs &a, int diag_mode, int variant, cudaStream_t s) {

@@ -8,6 +8,8 @@
 // Both source-sink kernels are HBM-bound streaming kernels: each input element
 // is read once and each output element written once, coalesced.
 #include "bgc_kernels.cuh"
+#include "bgc_math.cuh"
+#include "bgc_reduce.cuh"
 
 namespace bgc {
 
@@ -27,15 +29,17 @@ constexpr double dms_epsC = 1.00e-8;   // DMS_parms.F90:194-195 (carries the _r8
 
 #define DST(name, val) do { if (A.d.name) A.d.name[i2] = (val); } while (0)
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 dms_columns_kernel(const __grid_constant__ DmsArgs A) {
+  __shared__ double red[256 / 32];
   const int col = blockIdx.x * blockDim.x + threadIdx.x;
   const int nL = A.nL, nC = A.nC;
-  if (col >= nC) return;
+  const bool in_range = col < nC;
   const size_t nLnC = (size_t)nL * (size_t)nC;
-  int kmax = (col < A.nColumns) ? A.kmax[col] : 0;
+  int kmax = (in_range && col < A.nColumns) ? A.kmax[col] : 0;
   if (kmax > nL) kmax = nL;
   if (kmax < 0) kmax = 0;
+  double inv_dms = 0.0, inv_dmsp = 0.0;   // sum_k tendency * dz of this column (inventory)
 
   const DmsParams &P = c_dms.p;
   const DmsIndices &I = c_dms.ind;
@@ -59,7 +63,7 @@ dms_columns_kernel(const __grid_constant__ DmsArgs A) {
   const double *trc = A.tracers + col;
   double *tnd = A.tend + col;
 
-  for (int k = 0; k < nL; ++k) {
+  for (int k = 0; in_range && k < nL; ++k) {
     const size_t i2 = (size_t)col + (size_t)nC * (size_t)k;
     const size_t o2 = (size_t)nC * (size_t)k;
     // DMS_output%DMS_tendencies = 0 (:413); the two live slots are overwritten below
@@ -79,22 +83,22 @@ dms_columns_kernel(const __grid_constant__ DmsArgs A) {
 #undef TR
     const double dz = A.dz[i2];
 
-    const double k_S_p = P.k_S_p_base * (P.mort + (zooC / 0.3));   // literal 0.3, not zooC_avg (:529)
+    const double k_S_p = P.k_S_p_base * (P.mort + cdiv(zooC, 0.3, 1.0 / 0.3));   // literal 0.3, not zooC_avg (:529)
 
     const double PAR_in = PAR_out;
     const double totalChl = spChl + diatChl + diazChl + phaeoChl;
     const double w = fmax(totalChl, 0.02);
     double KPARdz;
-    if (w < 0.13224) KPARdz = 0.000919 * pow(w, 0.3536);
-    else             KPARdz = 0.001131 * pow(w, 0.4562);
+    if (w < 0.13224) KPARdz = 0.000919 * fpow(w, 0.3536);
+    else             KPARdz = 0.001131 * fpow(w, 0.4562);
     KPARdz = KPARdz * dz;
     const double eK = exp(-KPARdz);
     PAR_out = PAR_in * eK;
-    const double PAR_avg = PAR_in * (1.0 - eK) / KPARdz;
+    const double PAR_avg = fdiv(PAR_in * (1.0 - eK), KPARdz);
 
     const double j_dms = P.j_dms_perI * PAR_avg;
 
-    double Fcocco = spCaCO3 / (spC + dms_epsC);
+    double Fcocco = fdiv(spCaCO3, (spC + dms_epsC));
     if (Fcocco > 0.4) Fcocco = 0.4;
     const double Cocco_frac = Fcocco;
     const double Cyano_frac = (1.0 - Cocco_frac) * cyano_T;
@@ -109,7 +113,7 @@ dms_columns_kernel(const __grid_constant__ DmsArgs A) {
     const double zooN = P.R * zooC;
     const double phytoN = diatN + coccoN + cyanoN + eukarN + diazN + phaeoN;
 
-    double Sp_dec = (P.Sp_ref - spChl) / P.Sp_ref;
+    double Sp_dec = fdiv((P.Sp_ref - spChl), P.Sp_ref);
     if (Sp_dec <= 0.0) Sp_dec = 0.0;
     if (Sp_dec >= 1.0) Sp_dec = 1.0;
     double Stress_fac = 1.0 + P.Stress_mult * Sp_dec * Sp_dec;
@@ -130,13 +134,14 @@ dms_columns_kernel(const __grid_constant__ DmsArgs A) {
                   P.Rs2n_cocco * coccoN +
                   P.Rs2n_cyano * cyanoN +
                   P.Rs2n_eukar * eukarN * Stress_fac +
-                  P.Rs2n_diaz * diazN) / phytoN;
+                  P.Rs2n_diaz * diazN);
+      Rs2n_zoo = fdiv(Rs2n_zoo, phytoN);
     } else {
       Rs2n_zoo = (P.Rs2n_diat + P.Rs2n_cocco + P.Rs2n_cyano + P.Rs2n_eukar + P.Rs2n_diaz + P.Rs2n_phaeo) / 6.0;
     }
     const double zooS = Rs2n_zoo * zooN;
 
-    const double B_diagnosed = P.B_preexp * pow(phytoN, P.B_exp);
+    const double B_diagnosed = P.B_preexp * ((phytoN > 0.0) ? fpow(phytoN, P.B_exp) : pow(phytoN, P.B_exp));
 
     const double dms_s_dmsp = yield * P.k_conv * DMSP_loc;
     const double dms_s = dms_s_dmsp;
@@ -153,8 +158,11 @@ dms_columns_kernel(const __grid_constant__ DmsArgs A) {
     const double dmsp_r_bkgnd = P.k_bkgnd * DMSP_loc;
     const double dmsp_r = dmsp_r_B + dmsp_r_bkgnd;
 
-    tnd[o2 + (size_t)(I.dms_ind - 1) * nLnC] = dms_s - dms_r;
-    tnd[o2 + (size_t)(I.dmsp_ind - 1) * nLnC] = dmsp_s - dmsp_r;
+    const double t_dms = dms_s - dms_r, t_dmsp = dmsp_s - dmsp_r;
+    tnd[o2 + (size_t)(I.dms_ind - 1) * nLnC] = t_dms;
+    tnd[o2 + (size_t)(I.dmsp_ind - 1) * nLnC] = t_dmsp;
+    inv_dms += t_dms * dz;
+    inv_dmsp += t_dmsp * dz;
 
     DST(diag_DMS_S_DMSP, dms_s_dmsp);
     DST(diag_DMS_S_TOTAL, dms_s);
@@ -183,6 +191,15 @@ dms_columns_kernel(const __grid_constant__ DmsArgs A) {
     DST(diag_zooS, zooS);
     DST(diag_zooCC, zooC);
     DST(diag_RSNzoo, Rs2n_zoo);
+  }
+  if (A.inv_partials) {   // stage 1 of the inventory reduction, fused: one partial per block
+    const double a = block_sum(inv_dms, red), b = block_sum(inv_dmsp, red);
+    if (threadIdx.x == 0) {
+      double *out = A.inv_partials + (size_t)blockIdx.x * kInvGroup;
+      out[0] = a; out[1] = b;
+#pragma unroll
+      for (int j = 2; j < kInvGroup; ++j) out[j] = 0.0;
+    }
   }
 }
 #undef DST
@@ -238,15 +255,18 @@ dms_surface_kernel(const __grid_constant__ DmsSurfArgs A) {
 #undef DG
 }
 
-__global__ void __launch_bounds__(256)
+constexpr int kMacrosBlock = 1024;   // few, large blocks: one inventory partial per block
+
+__global__ void __launch_bounds__(kMacrosBlock)
 macros_cells_kernel(const __grid_constant__ MacrosArgs A) {
   const size_t nC = (size_t)A.nC;
   const size_t ncell = (size_t)A.nL * nC;
+  __shared__ double red[kMacrosBlock / 32];
   const size_t cell = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (cell >= ncell) return;
-  const int k = (int)(cell / nC);
-  const int col = (int)(cell - (size_t)k * nC);
-  const bool active = col < A.nColumns && k < A.kmax[col];
+  const bool in_range = cell < ncell;
+  const int k = in_range ? (int)(cell / nC) : 0;
+  const int col = in_range ? (int)(cell - (size_t)k * nC) : 0;
+  const bool active = in_range && col < A.nColumns && k < A.kmax[col];
   const MacrosParams &P = c_macros.p;
   const MacrosIndices &I = c_macros.ind;
 
@@ -256,7 +276,7 @@ macros_cells_kernel(const __grid_constant__ MacrosArgs A) {
     const double zooC = TR(I.zooC_ind), spC = TR(I.spC_ind), diatC = TR(I.diatC_ind), diazC = TR(I.diazC_ind),
                  phaeoC = TR(I.phaeoC_ind), prot = TR(I.prot_ind), poly = TR(I.poly_ind), lip = TR(I.lip_ind);
 #undef TR
-    const double k_C_p = P.k_C_p_base * (P.mort + (zooC / P.zooC_avg));
+    const double k_C_p = P.k_C_p_base * (P.mort + fdiv(zooC, P.zooC_avg));
     const double phytoC = diatC + phaeoC + spC + diazC;
     const double prot_s = P.inject_scale * P.f_prot * k_C_p * phytoC;
     const double poly_s = P.inject_scale * P.f_poly * k_C_p * phytoC;
@@ -281,7 +301,17 @@ macros_cells_kernel(const __grid_constant__ MacrosArgs A) {
     if (n == I.prot_ind - 1) v = t_prot;
     if (n == I.poly_ind - 1) v = t_poly;
     if (n == I.lip_ind - 1) v = t_lip;
-    A.tend[cell + (size_t)n * ncell] = v;
+    if (in_range) A.tend[cell + (size_t)n * ncell] = v;
+  }
+  if (A.inv_partials) {   // stage 1 of the inventory reduction, fused (tendencies are 0 off active cells)
+    const double dz = active ? A.dz[cell] : 0.0;
+    const double a = block_sum(t_prot * dz, red), b = block_sum(t_poly * dz, red), c = block_sum(t_lip * dz, red);
+    if (threadIdx.x == 0) {
+      double *out = A.inv_partials + (size_t)blockIdx.x * kInvGroup;
+      out[0] = a; out[1] = b; out[2] = c;
+#pragma unroll
+      for (int j = 3; j < kInvGroup; ++j) out[j] = 0.0;
+    }
   }
 }
 
@@ -308,97 +338,33 @@ transpose_kernel(const double *__restrict__ src, double *__restrict__ dst, int R
 }
 
 // ---------------------------------------------------------------- inventory
-// sum_col sum_k tend(n)*dz over active cells, and the sums of a few per-column
-// diagnostics, for the global conservation vector (include/bgc_b200.h).
-//
-// Stage 1 (inventory_partial_kernel): one thread per column, grid.y = group of up
-// to kInvGroup tracer slots, so a 235k-column mesh offers >1M threads of independent
-// streaming loads; block b writes its partial sums.  Stage 2 (inventory_fold_kernel):
-// one block per group adds the partials in a fixed order into the inventory vector.
-// No atomics: the result is bit-reproducible and independent of timing.
-constexpr int kInvBlock = 256;
+// Stage 1 of the inventory reduction is fused into the source-sink kernels: every block
+// writes its partial sums, [nParts][nGroups][kInvGroup].  Stage 2 below adds the partials
+// of each value in a fixed order into the inventory vector: block = group, 128 rows of
+// kInvGroup threads, row r walks partials r, r + 128, ... with four loads in flight.
+constexpr int kFoldRows = 128;
 
-__device__ __forceinline__ double block_sum(double v, double *smem) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  __syncthreads();
-  if (lane == 0) smem[wid] = v;
-  __syncthreads();
-  double r = 0.0;
-  if (threadIdx.x == 0) {
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) r += smem[w];
-  }
-  return r;   // valid in thread 0
-}
-
-__global__ void __launch_bounds__(kInvBlock)
-inventory_partial_kernel(const __grid_constant__ InventoryArgs A) {
-  __shared__ double smem[kInvBlock / 32];
-  const int g = blockIdx.y;
-  const int col = blockIdx.x * kInvBlock + threadIdx.x;
-  const size_t nC = (size_t)A.nC, nLnC = (size_t)A.nL * nC;
-  double acc[kInvGroup];
-#pragma unroll
-  for (int j = 0; j < kInvGroup; ++j) acc[j] = 0.0;
-
-  if (g < A.nGroups) {
-    int kmax = (col < A.nColumns) ? A.kmax[col] : 0;
-    if (kmax > A.nL) kmax = A.nL;
-    const double *src[kInvGroup];
-#pragma unroll
-    for (int j = 0; j < kInvGroup; ++j) {
-      const int slot = A.slot[g][j];
-      src[j] = (slot >= 0) ? A.tend + (size_t)slot * nLnC + col : nullptr;
-    }
-    const double *dzp = A.dz + col;
-    const bool counts = (g == 0) && A.count_out >= 0;
-    double cells = 0.0;
-#pragma unroll 2
-    for (int k = 0; k < kmax; ++k) {
-      const size_t o = nC * (size_t)k;
-      const double dz = dzp[o];
-#pragma unroll
-      for (int j = 0; j < kInvGroup; ++j)
-        if (src[j]) acc[j] += src[j][o] * dz;
-      cells += 1.0;
-    }
-    if (counts) { acc[kInvGroup - 2] = cells; acc[kInvGroup - 1] = (kmax > 0) ? 1.0 : 0.0; }
-  } else {   // the per-column diagnostic sums
-    if (col < A.nColumns) {
-#pragma unroll
-      for (int j = 0; j < kInvGroup; ++j)
-        if (A.colsum[j]) acc[j] = A.colsum[j][col];
-    }
-  }
-  double *out = A.partials + ((size_t)blockIdx.x * gridDim.y + g) * kInvGroup;
-#pragma unroll
-  for (int j = 0; j < kInvGroup; ++j) {
-    const double r = block_sum(acc[j], smem);
-    if (threadIdx.x == 0) out[j] = r;
-  }
-}
-
-// grid = number of groups, block = 256: lane j = t % 8 of "row" t / 8 walks the partials
-// of value j with stride 32 blocks; the 32 row sums are then added in row order.
-__global__ void __launch_bounds__(256)
-inventory_fold_kernel(const __grid_constant__ InventoryArgs A, int nParts) {
-  __shared__ double rows[32][kInvGroup];
+__global__ void __launch_bounds__(kFoldRows * kInvGroup)
+inventory_fold_kernel(const __grid_constant__ InventoryFoldArgs A, int nParts) {
+  __shared__ double rows[kFoldRows][kInvGroup];
   const int g = blockIdx.x, j = threadIdx.x % kInvGroup, r = threadIdx.x / kInvGroup;
-  double s = 0.0;
-  for (int b = r; b < nParts; b += 32) s += A.partials[((size_t)b * gridDim.x + g) * kInvGroup + j];
-  rows[r][j] = s;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  const size_t stride = (size_t)gridDim.x * kInvGroup;
+  const double *p = A.partials + (size_t)g * kInvGroup + j;
+  int b = r;
+  for (; b + 3 * kFoldRows < nParts; b += 4 * kFoldRows) {
+    s0 += p[(size_t)b * stride];
+    s1 += p[(size_t)(b + kFoldRows) * stride];
+    s2 += p[(size_t)(b + 2 * kFoldRows) * stride];
+    s3 += p[(size_t)(b + 3 * kFoldRows) * stride];
+  }
+  for (; b < nParts; b += kFoldRows) s0 += p[(size_t)b * stride];
+  rows[r][j] = (s0 + s1) + (s2 + s3);
   __syncthreads();
   if (r == 0) {
     double t = 0.0;
-    for (int q = 0; q < 32; ++q) t += rows[q][j];
-    int dst = -1;
-    if (g < A.nGroups) {
-      if (A.slot[g][j] >= 0) dst = A.out_index[g][j];
-      if (g == 0 && A.count_out >= 0 && j >= kInvGroup - 2) dst = A.count_out + (j - (kInvGroup - 2));
-    } else if (A.colsum[j]) {
-      dst = A.colsum_out + j;
-    }
+    for (int q = 0; q < kFoldRows; ++q) t += rows[q][j];
+    const int dst = A.out_index[g][j];
     if (dst >= 0) A.inventory[dst] += t;
   }
 }
@@ -422,7 +388,7 @@ cudaError_t launch_dms_surface(const DmsSurfArgs &a, cudaStream_t s) {
 cudaError_t launch_macros_cells(const MacrosArgs &a, cudaStream_t s) {
   const size_t ncell = (size_t)a.nL * (size_t)a.nC;
   if (ncell == 0) return cudaSuccess;
-  macros_cells_kernel<<<cdiv(ncell, 256), 256, 0, s>>>(a);
+  macros_cells_kernel<<<cdiv(ncell, kMacrosBlock), kMacrosBlock, 0, s>>>(a);
   return cudaGetLastError();
 }
 
@@ -435,23 +401,13 @@ cudaError_t launch_transpose(const double *src, double *dst, int R, int C, int n
   return cudaGetLastError();
 }
 
-int inventory_grid(int nC) {
-  int g = (nC + kInvBlock - 1) / kInvBlock;
-  return g < 1 ? 1 : g;
-}
-
-cudaError_t launch_inventory(const InventoryArgs &a, cudaStream_t s) {
-  if (a.nGroups < 0 || a.nGroups > kInvMaxGroups) return cudaErrorInvalidValue;
-  bool any_colsum = false;
-  for (int j = 0; j < kInvGroup; ++j) any_colsum = any_colsum || a.colsum[j] != nullptr;
-  const int gy = a.nGroups + (any_colsum ? 1 : 0);
-  if (gy == 0 || a.nColumns <= 0) return cudaSuccess;
-  const int gx = inventory_grid(a.nColumns);
-  inventory_partial_kernel<<<dim3(gx, gy), kInvBlock, 0, s>>>(a);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return e;
-  inventory_fold_kernel<<<gy, 256, 0, s>>>(a, gx);
+cudaError_t launch_inventory_fold(const InventoryFoldArgs &a, int nParts, cudaStream_t s) {
+  if (nParts <= 0 || a.nGroups <= 0) return cudaSuccess;
+  if (a.nGroups > kInvMaxGroups) return cudaErrorInvalidValue;
+  inventory_fold_kernel<<<a.nGroups, kFoldRows * kInvGroup, 0, s>>>(a, nParts);
   return cudaGetLastError();
 }
+int dms_inventory_parts(int nC) { return (nC + 255) / 256; }
+int macros_inventory_parts(int nL, int nC) { return (int)(((size_t)nL * (size_t)nC + kMacrosBlock - 1) / kMacrosBlock); }
 
 }  // namespace bgc
