@@ -325,6 +325,11 @@ extern "C" int bgc_set_params(bgc_ctx *c, const BgcParams *p, const BgcAutotroph
     return fail(BGC_ERR_ARG, "bgc_set_params: tracer indices cover %d of %d slots", count, BGC_TRACER_CNT);
   if (!index_ok(ind->diat_ind, BGC_AUTOTROPH_CNT)) return fail(BGC_ERR_ARG, "bgc_set_params: bad diat_ind");
 
+  // The Fortran shim calls this before every BGC_SourceSink: identical tables keep their
+  // version, so the __constant__ copy is not uploaded again.
+  if (c->have_bgc && memcmp(&c->bgc_tab.p, p, sizeof *p) == 0 && memcmp(c->bgc_tab.a, a, sizeof(BgcAutotroph) * BGC_AUTOTROPH_CNT) == 0 &&
+      memcmp(&c->bgc_tab.ind, ind, sizeof *ind) == 0)
+    return BGC_OK;
   c->bgc_tab.p = *p;
   for (int g = 0; g < BGC_AUTOTROPH_CNT; ++g) c->bgc_tab.a[g] = a[g];
   c->bgc_tab.ind = *ind;
@@ -342,6 +347,7 @@ extern "C" int dms_set_params(bgc_ctx *c, const DmsParams *p, const DmsIndices *
   int seen[DMS_TRACER_CNT + 1] = {0};
   for (int i = 0; i < DMS_TRACER_CNT; ++i)
     if (!index_ok(v[i], DMS_TRACER_CNT) || seen[v[i]]++) return fail(BGC_ERR_ARG, "dms_set_params: bad/duplicate tracer index %d", v[i]);
+  if (c->have_dms && memcmp(&c->dms_tab.p, p, sizeof *p) == 0 && memcmp(&c->dms_tab.ind, ind, sizeof *ind) == 0) return BGC_OK;
   c->dms_tab.p = *p;
   c->dms_tab.ind = *ind;
   c->have_dms = true;
@@ -355,6 +361,8 @@ extern "C" int macros_set_params(bgc_ctx *c, const MacrosParams *p, const Macros
   int seen[MACROS_TRACER_CNT + 1] = {0};
   for (int i = 0; i < MACROS_TRACER_CNT; ++i)
     if (!index_ok(v[i], MACROS_TRACER_CNT) || seen[v[i]]++) return fail(BGC_ERR_ARG, "macros_set_params: bad/duplicate tracer index %d", v[i]);
+  if (c->have_macros && memcmp(&c->macros_tab.p, p, sizeof *p) == 0 && memcmp(&c->macros_tab.ind, ind, sizeof *ind) == 0)
+    return BGC_OK;
   c->macros_tab.p = *p;
   c->macros_tab.ind = *ind;
   c->have_macros = true;
