@@ -1,0 +1,38 @@
+#!/bin/bash
+# One GPU-box visit: parity tests, the default bench line, the reference arm, the per-launch
+# device-time list of one step and one `ncu --set full` capture per hot kernel (full EC60to30
+# mesh).  Every ncu pass runs only after the same command exited 0 without ncu.
+# Usage: TAG=r01_v4 scripts/gpu_round.sh   (outputs under gpurun_out/)
+set -u
+TAG=${TAG:-r01}
+mkdir -p gpurun_out
+if [ "${SKIP_TESTS:-0}" != "1" ]; then
+  python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_$TAG.log 2>&1; echo "pytest exit $?" | tee -a gpurun_out/pytest_gpu_$TAG.log
+  tail -3 gpurun_out/pytest_gpu_$TAG.log
+fi
+python __graft_entry__.py smoke > gpurun_out/smoke_$TAG.log 2>&1; echo "smoke exit $?"
+python bench.py > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; echo "bench exit $?"
+python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref_$TAG.json 2> gpurun_out/bench_ref_$TAG.err; echo "ref exit $?"
+CMD="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu"
+$CMD > gpurun_out/plain.log 2>&1 || { echo "plain run failed"; tail -20 gpurun_out/plain.log; exit 1; }
+ncu --metrics gpu__time_duration.sum --clock-control none -s ${SKIP:-48} -c ${COUNT:-24} --csv \
+    --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_launches.log 2>&1
+echo "ncu launches exit $?"
+if [ "${SKIP_FULL:-0}" != "1" ]; then
+  ncu --set full --clock-control none --import-source on \
+      -k "regex:${KERNELS:-eco_columns|co3_cells|dms_columns|macros_cells}" -s ${FSKIP:-16} -c ${FCOUNT:-4} -f \
+      -o gpurun_out/ncu_full_$TAG $CMD > gpurun_out/ncu_full.log 2>&1
+  echo "ncu full exit $?"; grep -c "==PROF== Profiling" gpurun_out/ncu_full.log
+fi
+python - <<PY
+import json
+for f in ("gpurun_out/bench_$TAG.json", "gpurun_out/bench_ref_$TAG.json"):
+    try:
+        d = json.loads(open(f).read().strip().splitlines()[-1])
+        print(f, "value %.4g" % d["value"], "ms/step %.3f" % d["ms_per_step"],
+              "e2e", (d.get("e2e") or {}).get("value"), "cpu", (d.get("cpu_baseline") or {}).get("value"))
+        if "roofline" in d:
+            print("  kernels", {k: round(v, 3) for k, v in d["roofline"]["kernel_ms_per_launch"].items()})
+    except Exception as e:
+        print(f, "no result:", e)
+PY
