@@ -107,32 +107,40 @@ __device__ __forceinline__ void co3_coeffs(bool deep, double depth, double temp,
         (148.0248 + 137.1942 * sqrts + 1.62142 * salt_lim) +
         (-24.4344 - 25.085 * sqrts - 0.2474 * salt_lim) * dlogtk +
         0.053105 * sqrts * tk;
-  c.kb = exp(arg);
+  // Pressure correction (Millero 1995).  Strict build: K = exp(arg) * exp(pressure term), the
+  // reference's two factors.  Production build: one exponential of the summed argument
+  // (identical up to the rounding of one addition, ~1e-16 relative * |arg|).
+#ifdef BGC_STRICT
+#define K_OF(arg_, dV_, Kap_) (exp(arg_) * (deep ? kfac((dV_), (Kap_), press_bar, invRtk) : 1.0))
+#else
+#define K_OF(arg_, dV_, Kap_) exp((arg_) + (deep ? (-(dV_) + 0.5 * (Kap_) * press_bar) * press_bar * invRtk : 0.0))
+#endif
+  c.kb = K_OF(arg, -29.48 + (0.1622 - 0.002608 * temp) * temp, -2.84 * 0.001);
   // k1p, k2p, k3p: DOE 1994 (co2calc.F90:560-637)
   arg = -4576.752 * invtk + 115.525 - 18.453 * dlogtk +
         (-106.736 * invtk + 0.69171) * sqrts +
         (-0.65643 * invtk - 0.01844) * salt_lim;
-  c.k1p = exp(arg);
+  c.k1p = K_OF(arg, -14.51 + (0.1211 - 0.000321 * temp) * temp, (-2.67 + 0.0427 * temp) * 0.001);
   arg = -8814.715 * invtk + 172.0883 - 27.927 * dlogtk +
         (-160.340 * invtk + 1.3566) * sqrts +
         (0.37335 * invtk - 0.05778) * salt_lim;
-  c.k2p = exp(arg);
+  c.k2p = K_OF(arg, -23.12 + (0.1758 - 0.002647 * temp) * temp, (-5.15 + 0.09 * temp) * 0.001);
   arg = -3070.75 * invtk - 18.141 +
         (17.27039 * invtk + 2.81197) * sqrts +
         (-44.99486 * invtk - 0.09984) * salt_lim;
-  c.k3p = exp(arg);
+  c.k3p = K_OF(arg, -26.57 + (0.202 - 0.003042 * temp) * temp, (-4.08 + 0.0714 * temp) * 0.001);
   // ksi, Yao & Millero 1995 (co2calc.F90:647-669)
   arg = -8904.2 * invtk + 117.385 - 19.334 * dlogtk +
         (-458.79 * invtk + 3.5913) * sqrtis +
         (188.74 * invtk - 1.5998) * is +
         (-12.1652 * invtk + 0.07871) * is2 +
         log_1_m_1p005em3_s;
-  c.ksi = exp(arg);
+  c.ksi = K_OF(arg, -29.48 + (0.1622 - 0.002608 * temp) * temp, -2.84 * 0.001);
   // kw, Millero 1995 (co2calc.F90:681-700)
   arg = -13847.26 * invtk + 148.9652 - 23.6521 * dlogtk +
         (118.67 * invtk - 5.977 + 1.0495 * dlogtk) * sqrts -
         0.01615 * salt_lim;
-  c.kw = exp(arg);
+  c.kw = K_OF(arg, -20.02 + (0.1119 - 0.001409 * temp) * temp, (-5.13 + 0.0794 * temp) * 0.001);
   // ks, Dickson 1990 (co2calc.F90:709-731)
   arg = -4276.1 * invtk + 141.328 - 23.093 * dlogtk +
         (-13856.0 * invtk + 324.57 - 47.986 * dlogtk) * sqrtis +
@@ -140,26 +148,14 @@ __device__ __forceinline__ void co3_coeffs(bool deep, double depth, double temp,
         2698.0 * invtk * is * sqrtis +
         1776.0 * invtk * is2 +
         log_1_m_1p005em3_s;
-  c.ks = exp(arg);
-
-  if (deep) {
-    c.kb *= kfac(-29.48 + (0.1622 - 0.002608 * temp) * temp, -2.84 * 0.001, press_bar, invRtk);
-    c.k1p *= kfac(-14.51 + (0.1211 - 0.000321 * temp) * temp, (-2.67 + 0.0427 * temp) * 0.001, press_bar, invRtk);
-    c.k2p *= kfac(-23.12 + (0.1758 - 0.002647 * temp) * temp, (-5.15 + 0.09 * temp) * 0.001, press_bar, invRtk);
-    c.k3p *= kfac(-26.57 + (0.202 - 0.003042 * temp) * temp, (-4.08 + 0.0714 * temp) * 0.001, press_bar, invRtk);
-    c.ksi *= kfac(-29.48 + (0.1622 - 0.002608 * temp) * temp, -2.84 * 0.001, press_bar, invRtk);
-    c.kw *= kfac(-20.02 + (0.1119 - 0.001409 * temp) * temp, (-5.13 + 0.0794 * temp) * 0.001, press_bar, invRtk);
-    c.ks *= kfac(-18.03 + (0.0466 + 0.000316 * temp) * temp, (-4.53 + 0.09 * temp) * 0.001, press_bar, invRtk);
-  }
+  c.ks = K_OF(arg, -18.03 + (0.0466 + 0.000316 * temp) * temp, (-4.53 + 0.09 * temp) * 0.001);
 
   // kf, Dickson & Riley 1979, uses the (corrected) ks (co2calc.F90:740-764)
   arg = 1.0 + fdiv((0.1400 / 96.062) * (scl), c.ks);
   const double log_1_p_tot_sulfate_div_ks = log(arg);
   arg = 1590.2 * invtk - 12.641 + 1.525 * sqrtis + log_1_m_1p005em3_s + log_1_p_tot_sulfate_div_ks;
-  c.kf = exp(arg);
-  if (deep) {
-    c.kf *= kfac(-9.78 - (0.009 + 0.000942 * temp) * temp, (-3.91 + 0.054 * temp) * 0.001, press_bar, invRtk);
-  }
+  c.kf = K_OF(arg, -9.78 - (0.009 + 0.000942 * temp) * temp, (-3.91 + 0.054 * temp) * 0.001);
+#undef K_OF
 
   c.bt = 0.000232 / 10.811 * scl;   // co2calc.F90:773-775
   c.st = 0.14 / 96.062 * scl;
@@ -186,22 +182,41 @@ __device__ __forceinline__ TalkInv talk_invariants(const Co3Consts &k) {
 __device__ __forceinline__ void talk_residual(const Co3Consts &k, const Co3Totals &t, const TalkInv &v,
                                               double x, double &fn, double &df) {
   const double x1 = x;
-  const double x1_r = frcp(x1);
   const double x2 = x1 * x1;
-  const double x2_r = x1_r * x1_r;
   const double x3 = x2 * x1;
   const double a = x3 + k.k1p * x2 + v.k12p * x1 + v.k123p;
-  const double a_r = frcp(a);
-  const double a2_r = a_r * a_r;
   const double da = 3.0 * x2 + 2.0 * k.k1p * x1 + v.k12p;
   const double b = x2 + k.k1 * x1 + v.k12;
-  const double b_r = frcp(b);
-  const double b2_r = b_r * b_r;
   const double db = 2.0 * x1 + k.k1;
+#ifdef BGC_STRICT
+  const double x1_r = frcp(x1);
+  const double a_r = frcp(a);
+  const double b_r = frcp(b);
   const double kb_p_x1_r = frcp(k.kb + x1);
   const double ksi_p_x1_r = frcp(k.ksi + x1);
   const double c1_p_c_ks_x1_r_r = frcp(1.0 + v.cks_ * x1_r);
   const double c1_p_kf_x1_r_r = frcp(1.0 + k.kf * x1_r);
+#else
+  // The seven reciprocals of one evaluation from ONE division (batch inversion: prefix
+  // products, one reciprocal, back-substitution).  1/(1 + c/x) is taken as x/(x + c).  The
+  // product of the seven denominators stays within 1e-120..1e+120 for any bracket the
+  // growth loop can produce, far from FP64 under/overflow.
+  const double d3 = k.kb + x1, d4 = k.ksi + x1, d5 = x1 + v.cks_, d6 = x1 + k.kf;
+  const double p1 = x1 * a, p2 = p1 * b, p3 = p2 * d3, p4 = p3 * d4, p5 = p4 * d5, p6 = p5 * d6;
+  double r = frcp(p6);
+  const double d6_r = r * p5; r = r * d6;
+  const double d5_r = r * p4; r = r * d5;
+  const double ksi_p_x1_r = r * p3; r = r * d4;
+  const double kb_p_x1_r = r * p2; r = r * d3;
+  const double b_r = r * p1; r = r * b;
+  const double a_r = r * x1;
+  const double x1_r = r * a;
+  const double c1_p_c_ks_x1_r_r = x1 * d5_r;
+  const double c1_p_kf_x1_r_r = x1 * d6_r;
+#endif
+  const double x2_r = x1_r * x1_r;
+  const double a2_r = a_r * a_r;
+  const double b2_r = b_r * b_r;
 
   fn = k.k1 * t.dic * x1 * b_r
      + 2.0 * t.dic * v.k12 * b_r
@@ -327,19 +342,23 @@ __device__ __forceinline__ void co3_sat_vals(bool deep, double depth, double tem
   double arg = -171.9065 - 0.077993 * tk + 2839.319 * invtk + 71.595 * log10tk +
                (-0.77712 + 0.0028426 * tk + 178.34 * invtk) * sqrts -
                0.07711 * salt_lim + 0.0041249 * s15;
-  double K_calc = exp(kLn10 * arg);
+  const double arg_calc = kLn10 * arg;
   arg = -171.945 - 0.077993 * tk + 2903.293 * invtk + 71.595 * log10tk +
         (-0.068393 + 0.0017276 * tk + 88.135 * invtk) * sqrts -
         0.10018 * salt_lim + 0.0059415 * s15;
-  double K_arag = exp(kLn10 * arg);
-
+  const double arg_arag = kLn10 * arg;
+  const double deltaV = -48.76 + 0.5304 * temp;
+  const double Kappa = (-11.76 + 0.3692 * temp) * 0.001;
+#ifdef BGC_STRICT
+  double K_calc = exp(arg_calc), K_arag = exp(arg_arag);
   if (deep) {
-    double deltaV = -48.76 + 0.5304 * temp;
-    const double Kappa = (-11.76 + 0.3692 * temp) * 0.001;
     K_calc *= kfac(deltaV, Kappa, press_bar, invRtk);
-    deltaV = deltaV + 2.8;
-    K_arag *= kfac(deltaV, Kappa, press_bar, invRtk);
+    K_arag *= kfac(deltaV + 2.8, Kappa, press_bar, invRtk);
   }
+#else   // one exponential of the summed argument, as in co3_coeffs
+  const double K_calc = exp(arg_calc + (deep ? (-deltaV + 0.5 * Kappa * press_bar) * press_bar * invRtk : 0.0));
+  const double K_arag = exp(arg_arag + (deep ? (-(deltaV + 2.8) + 0.5 * Kappa * press_bar) * press_bar * invRtk : 0.0));
+#endif
 
   const double inv_Ca = fdiv((35.0 / 0.01028), salt_lim);
   co3_sat_calc = (K_calc * inv_Ca) * kMassToVol;

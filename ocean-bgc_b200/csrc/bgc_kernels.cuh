@@ -129,7 +129,7 @@ struct InventoryFoldArgs {
   double *inventory;                         // accumulated into (+=)
 };
 cudaError_t launch_inventory_fold(const InventoryFoldArgs &a, int nParts, cudaStream_t s);
-int dms_inventory_parts(int nC);
+int dms_inventory_parts(int nL, int nC);
 int macros_inventory_parts(int nL, int nC);
 // column sweep: [eco_inventory_parts][kEcoInvGroups][kInvGroup]
 //   groups 0,1: the 16 plain tracers in the order of kEcoInvPlainOrder (k_eco.cu / bgc_capi.cu)

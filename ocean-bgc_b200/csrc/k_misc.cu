@@ -1,7 +1,7 @@
 // k_misc.cu — DMS / MACROS source-sink kernels, the DMS surface flux, the
 // Fortran<->SoA layout transposes and the deterministic inventory reductions.
 //
-//   dms_columns_kernel    <- DMS_SourceSink     DMS_mod.F90:156-770   (thread = column; PAR carried down)
+//   dms_cells_kernel      <- DMS_SourceSink     DMS_mod.F90:156-770   (block = 32 columns x all levels, thread = cell)
 //   dms_surface_kernel    <- DMS_SurfaceFluxes  DMS_mod.F90:778-908   (thread = column)
 //   macros_cells_kernel   <- MACROS_SourceSink  MACROS_mod.F90:137-411 (thread = cell; no vertical coupling)
 //
@@ -29,168 +29,228 @@ constexpr double dms_epsC = 1.00e-8;   // DMS_parms.F90:194-195 (carries the _r8
 
 #define DST(name, val) do { if (A.d.name) A.d.name[i2] = (val); } while (0)
 
-__global__ void __launch_bounds__(256, 4)
-dms_columns_kernel(const __grid_constant__ DmsArgs A) {
-  __shared__ double red[256 / 32];
-  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+// Column-constant factors of DMS_SourceSink: all depend on SST only (DMS_mod.F90:584-592, :637-640).
+struct DmsColumnConsts { double cyano_T, yield; };
+
+__device__ __forceinline__ DmsColumnConsts dms_column_consts(double SST_loc) {
+  const DmsParams &P = c_dms.p;
+  double T_ind = (SST_loc - P.T_lo) / (P.T_hi - P.T_lo);
+  if (T_ind <= 0.0) T_ind = 0.0;
+  if (T_ind >= 1.0) T_ind = 1.0;
+  DmsColumnConsts r;
+  r.cyano_T = (T_ind * (P.Max_cyano_frac - P.Min_cyano_frac)) + P.Min_cyano_frac;
+  r.yield = (T_ind * (P.Max_yld - P.Min_yld)) + P.Min_yld;
+  if (SST_loc < P.T_cryo_hi && SST_loc > P.T_cryo_lo) r.yield = 0.5;
+  if (SST_loc < -1.0) r.yield = 0.25;
+  return r;
+}
+
+// Light attenuation over one cell (DMS_mod.F90:510-527): KPARdz and exp(-KPARdz).
+__device__ __forceinline__ void dms_attenuation(double totalChl, double dz, double &KPARdz, double &eK) {
+  const double w = fmax(totalChl, 0.02);
+  double kp;
+  if (w < 0.13224) kp = 0.000919 * fpow(w, 0.3536);
+  else             kp = 0.001131 * fpow(w, 0.4562);
+  KPARdz = kp * dz;
+  eK = exp(-KPARdz);
+}
+
+// Everything of one active cell once PAR_avg is known (DMS_mod.F90:529-765): loads the cell's
+// tracers, stores the two live tendencies and the 27 diagnostics.
+__device__ __forceinline__ void dms_cell(const DmsArgs &A, size_t i2, size_t nLnC, double PAR_avg,
+                                         const DmsColumnConsts cc, double &t_dms, double &t_dmsp) {
+  const DmsParams &P = c_dms.p;
+  const DmsIndices &I = c_dms.ind;
+  const double *trc = A.tracers + i2;
+#define TR(ind_) fmax(0.0, trc[(size_t)((ind_) - 1) * nLnC])
+  // NO3 and DOC are copied by the reference (:471-472) but reach no output
+  // (DOC feeds only the unused UV_avg, :531-536): not read here.
+  const double zooC = TR(I.zooC_ind), spC = TR(I.spC_ind), diatC = TR(I.diatC_ind),
+               diazC = TR(I.diazC_ind), phaeoC = TR(I.phaeoC_ind), spChl = TR(I.spChl_ind),
+               spCaCO3 = TR(I.spCaCO3_ind), DMS_loc = TR(I.dms_ind), DMSP_loc = TR(I.dmsp_ind);
+#undef TR
+  const double k_S_p = P.k_S_p_base * (P.mort + cdiv(zooC, 0.3, 1.0 / 0.3));   // literal 0.3, not zooC_avg (:529)
+  const double j_dms = P.j_dms_perI * PAR_avg;
+
+  double Fcocco = fdiv(spCaCO3, (spC + dms_epsC));
+  if (Fcocco > 0.4) Fcocco = 0.4;
+  const double Cocco_frac = Fcocco;
+  const double Cyano_frac = (1.0 - Cocco_frac) * cc.cyano_T;
+  const double Eukar_frac = 1.0 - Cocco_frac - Cyano_frac;
+
+  const double diatN = P.R * diatC;
+  const double phaeoN = P.R * phaeoC;
+  const double coccoN = Cocco_frac * P.R * spC;
+  const double cyanoN = Cyano_frac * P.R * spC;
+  const double eukarN = Eukar_frac * P.R * spC;
+  const double diazN = P.R * diazC;
+  const double zooN = P.R * zooC;
+  const double phytoN = diatN + coccoN + cyanoN + eukarN + diazN + phaeoN;
+
+  double Sp_dec = fdiv((P.Sp_ref - spChl), P.Sp_ref);
+  if (Sp_dec <= 0.0) Sp_dec = 0.0;
+  if (Sp_dec >= 1.0) Sp_dec = 1.0;
+  double Stress_fac = 1.0 + P.Stress_mult * Sp_dec * Sp_dec;
+  if (Stress_fac >= 10.0) Stress_fac = 10.0;
+
+  const double diatS = P.Rs2n_diat * diatN;
+  const double phaeoS = P.Rs2n_phaeo * phaeoN;
+  const double coccoS = P.Rs2n_cocco * coccoN;
+  const double cyanoS = P.Rs2n_cyano * cyanoN;
+  const double eukarS = P.Rs2n_eukar * eukarN * Stress_fac;
+  const double diazS = P.Rs2n_diaz * diazN;
+  const double phytoS = diatS + coccoS + cyanoS + eukarS + diazS + P.G_phaeo_S * phaeoS;
+
+  double Rs2n_zoo;
+  if (phytoN > 0.0) {
+    Rs2n_zoo = (P.Rs2n_diat * diatN +
+                P.G_phaeo_S * P.Rs2n_phaeo * phaeoN +
+                P.Rs2n_cocco * coccoN +
+                P.Rs2n_cyano * cyanoN +
+                P.Rs2n_eukar * eukarN * Stress_fac +
+                P.Rs2n_diaz * diazN);
+    Rs2n_zoo = fdiv(Rs2n_zoo, phytoN);
+  } else {
+    Rs2n_zoo = (P.Rs2n_diat + P.Rs2n_cocco + P.Rs2n_cyano + P.Rs2n_eukar + P.Rs2n_diaz + P.Rs2n_phaeo) / 6.0;
+  }
+  const double zooS = Rs2n_zoo * zooN;
+
+  const double B_diagnosed = P.B_preexp * ((phytoN > 0.0) ? fpow(phytoN, P.B_exp) : pow(phytoN, P.B_exp));
+
+  const double dms_s_dmsp = cc.yield * P.k_conv * DMSP_loc;
+  const double dms_s = dms_s_dmsp;
+  const double dms_r_B = P.k_S_B * B_diagnosed * DMS_loc;
+  const double dms_r_phot = j_dms * DMS_loc;
+  const double dms_r_bkgnd = P.k_bkgnd * DMS_loc;
+  const double dms_r = dms_r_B + dms_r_phot + dms_r_bkgnd;
+
+  const double dmsp_s_phaeo = P.inject_scale * P.k_S_p_base * phaeoS;
+  const double dmsp_s_nonphaeo = P.inject_scale * k_S_p * phytoS;
+  const double dmsp_s_zoo = P.inject_scale * P.k_S_z * zooS;
+  const double dmsp_s = dmsp_s_phaeo + dmsp_s_nonphaeo + dmsp_s_zoo;
+  const double dmsp_r_B = P.k_conv * DMSP_loc;
+  const double dmsp_r_bkgnd = P.k_bkgnd * DMSP_loc;
+  const double dmsp_r = dmsp_r_B + dmsp_r_bkgnd;
+
+  t_dms = dms_s - dms_r;
+  t_dmsp = dmsp_s - dmsp_r;
+
+  DST(diag_DMS_S_DMSP, dms_s_dmsp);
+  DST(diag_DMS_S_TOTAL, dms_s);
+  DST(diag_DMS_R_B, dms_r_B);
+  DST(diag_DMS_R_PHOT, dms_r_phot);
+  DST(diag_DMS_R_BKGND, dms_r_bkgnd);
+  DST(diag_DMS_R_TOTAL, dms_r);
+  DST(diag_DMSP_S_PHAEO, dmsp_s_phaeo);
+  DST(diag_DMSP_S_NONPHAEO, dmsp_s_nonphaeo);
+  DST(diag_DMSP_S_ZOO, dmsp_s_zoo);
+  DST(diag_DMSP_S_TOTAL, dmsp_s);
+  DST(diag_DMSP_R_B, dmsp_r_B);
+  DST(diag_DMSP_R_BKGND, dmsp_r_bkgnd);
+  DST(diag_DMSP_R_TOTAL, dmsp_r);
+  DST(diag_Cyano_frac, Cyano_frac);
+  DST(diag_Cocco_frac, Cocco_frac);
+  DST(diag_Eukar_frac, Eukar_frac);
+  DST(diag_diatS, diatS);
+  DST(diag_diatN, diatN);
+  DST(diag_phytoN, phytoN);
+  DST(diag_coccoS, coccoS);
+  DST(diag_cyanoS, cyanoS);
+  DST(diag_eukarS, eukarS);
+  DST(diag_diazS, diazS);
+  DST(diag_phaeoS, phaeoS);
+  DST(diag_zooS, zooS);
+  DST(diag_zooCC, zooC);
+  DST(diag_RSNzoo, Rs2n_zoo);
+}
+#undef DST
+
+// DMS_output%DMS_tendencies = 0 (DMS_mod.F90:413) and the two live slots of an active cell.
+__device__ __forceinline__ void dms_store_tendencies(const DmsArgs &A, size_t i2, size_t nLnC, bool active,
+                                                     double t_dms, double t_dmsp) {
+  const DmsIndices &I = c_dms.ind;
+  double *tnd = A.tend + i2;
+#pragma unroll
+  for (int n = 0; n < DMS_TRACER_CNT; ++n) {
+    double v = 0.0;
+    if (active && n == I.dms_ind - 1) v = t_dms;
+    if (active && n == I.dmsp_ind - 1) v = t_dmsp;
+    tnd[(size_t)n * nLnC] = v;
+  }
+}
+
+// Tile kernel: a block owns kDmsTileCols consecutive columns over ALL levels; warp w takes the
+// levels w, w + W, ...  The only vertical coupling of DMS_SourceSink is the PAR attenuation
+// product (:510-527), so
+//   phase 1  every cell's KPARdz and exp(-KPARdz) -> shared memory (cell-parallel),
+//   phase 2  warp 0 walks its 32 columns top to bottom, PAR_out = PAR_in * exp(-KPARdz) in the
+//            reference's order (bit-identical to the sequential sweep), PAR_in -> shared memory,
+//   phase 3  every cell is independent: 9 tracer loads, 14 + 27 stores.
+// The mesh offers nL times more parallelism this way than one thread per column, which is
+// what an HBM-bound streaming kernel needs to keep enough bytes in flight.
+constexpr int kDmsTileCols = 32;
+constexpr int kDmsTileWarps = 8;
+
+__global__ void __launch_bounds__(kDmsTileCols * kDmsTileWarps, 3)
+dms_cells_kernel(const __grid_constant__ DmsArgs A) {
+  extern __shared__ double dsm[];
+  __shared__ double red[kDmsTileWarps];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int col = blockIdx.x * kDmsTileCols + lane;
   const int nL = A.nL, nC = A.nC;
   const bool in_range = col < nC;
   const size_t nLnC = (size_t)nL * (size_t)nC;
   int kmax = (in_range && col < A.nColumns) ? A.kmax[col] : 0;
   if (kmax > nL) kmax = nL;
   if (kmax < 0) kmax = 0;
-  double inv_dms = 0.0, inv_dmsp = 0.0;   // sum_k tendency * dz of this column (inventory)
-
-  const DmsParams &P = c_dms.p;
+  double *const s_kp = dsm;                       // [nL][32] KPARdz
+  double *const s_ek = dsm + (size_t)nL * 32;     // [nL][32] exp(-KPARdz)
+  double *const s_pin = dsm + (size_t)nL * 64;    // [nL][32] PAR_in
   const DmsIndices &I = c_dms.ind;
 
-  double SST_loc = 0.0, PAR_out = 0.0;
-  if (kmax > 0) {
-    SST_loc = A.sst[col];
-    PAR_out = fmax(0.0, A.sw_flux[col]);
-    PAR_out = PAR_out * P.f_qsw_par_DMS;
-  }
+  double SST_loc = 0.0;
+  if (kmax > 0) SST_loc = A.sst[col];
+  const DmsColumnConsts cc = dms_column_consts(SST_loc);
 
-  // column-constant factors (all depend on SST only, DMS_mod.F90:584-592, :637-640)
-  double T_ind = (SST_loc - P.T_lo) / (P.T_hi - P.T_lo);
-  if (T_ind <= 0.0) T_ind = 0.0;
-  if (T_ind >= 1.0) T_ind = 1.0;
-  const double cyano_T = (T_ind * (P.Max_cyano_frac - P.Min_cyano_frac)) + P.Min_cyano_frac;
-  double yield = (T_ind * (P.Max_yld - P.Min_yld)) + P.Min_yld;
-  if (SST_loc < P.T_cryo_hi && SST_loc > P.T_cryo_lo) yield = 0.5;
-  if (SST_loc < -1.0) yield = 0.25;
-
-  const double *trc = A.tracers + col;
-  double *tnd = A.tend + col;
-
-  for (int k = 0; in_range && k < nL; ++k) {
+  for (int k = w; k < kmax; k += kDmsTileWarps) {
     const size_t i2 = (size_t)col + (size_t)nC * (size_t)k;
-    const size_t o2 = (size_t)nC * (size_t)k;
-    // DMS_output%DMS_tendencies = 0 (:413); the two live slots are overwritten below
-#pragma unroll
-    for (int n = 0; n < DMS_TRACER_CNT; ++n) {
-      if (k >= kmax || (n != I.dms_ind - 1 && n != I.dmsp_ind - 1)) tnd[o2 + (size_t)n * nLnC] = 0.0;
-    }
-    if (k >= kmax) continue;   // diagnostics keep their previous contents outside active cells
-
-#define TR(ind_) fmax(0.0, trc[o2 + (size_t)((ind_) - 1) * nLnC])
-    // NO3 and DOC are copied by the reference (:471-472) but reach no output
-    // (DOC feeds only the unused UV_avg, :531-536): not read here.
-    const double zooC = TR(I.zooC_ind), spC = TR(I.spC_ind), diatC = TR(I.diatC_ind),
-                 diazC = TR(I.diazC_ind), phaeoC = TR(I.phaeoC_ind), spChl = TR(I.spChl_ind),
-                 diatChl = TR(I.diatChl_ind), diazChl = TR(I.diazChl_ind), phaeoChl = TR(I.phaeoChl_ind),
-                 spCaCO3 = TR(I.spCaCO3_ind), DMS_loc = TR(I.dms_ind), DMSP_loc = TR(I.dmsp_ind);
+    const double *trc = A.tracers + i2;
+#define TR(ind_) fmax(0.0, trc[(size_t)((ind_) - 1) * nLnC])
+    const double totalChl = TR(I.spChl_ind) + TR(I.diatChl_ind) + TR(I.diazChl_ind) + TR(I.phaeoChl_ind);
 #undef TR
-    const double dz = A.dz[i2];
-
-    const double k_S_p = P.k_S_p_base * (P.mort + cdiv(zooC, 0.3, 1.0 / 0.3));   // literal 0.3, not zooC_avg (:529)
-
-    const double PAR_in = PAR_out;
-    const double totalChl = spChl + diatChl + diazChl + phaeoChl;
-    const double w = fmax(totalChl, 0.02);
-    double KPARdz;
-    if (w < 0.13224) KPARdz = 0.000919 * fpow(w, 0.3536);
-    else             KPARdz = 0.001131 * fpow(w, 0.4562);
-    KPARdz = KPARdz * dz;
-    const double eK = exp(-KPARdz);
-    PAR_out = PAR_in * eK;
-    const double PAR_avg = fdiv(PAR_in * (1.0 - eK), KPARdz);
-
-    const double j_dms = P.j_dms_perI * PAR_avg;
-
-    double Fcocco = fdiv(spCaCO3, (spC + dms_epsC));
-    if (Fcocco > 0.4) Fcocco = 0.4;
-    const double Cocco_frac = Fcocco;
-    const double Cyano_frac = (1.0 - Cocco_frac) * cyano_T;
-    const double Eukar_frac = 1.0 - Cocco_frac - Cyano_frac;
-
-    const double diatN = P.R * diatC;
-    const double phaeoN = P.R * phaeoC;
-    const double coccoN = Cocco_frac * P.R * spC;
-    const double cyanoN = Cyano_frac * P.R * spC;
-    const double eukarN = Eukar_frac * P.R * spC;
-    const double diazN = P.R * diazC;
-    const double zooN = P.R * zooC;
-    const double phytoN = diatN + coccoN + cyanoN + eukarN + diazN + phaeoN;
-
-    double Sp_dec = fdiv((P.Sp_ref - spChl), P.Sp_ref);
-    if (Sp_dec <= 0.0) Sp_dec = 0.0;
-    if (Sp_dec >= 1.0) Sp_dec = 1.0;
-    double Stress_fac = 1.0 + P.Stress_mult * Sp_dec * Sp_dec;
-    if (Stress_fac >= 10.0) Stress_fac = 10.0;
-
-    const double diatS = P.Rs2n_diat * diatN;
-    const double phaeoS = P.Rs2n_phaeo * phaeoN;
-    const double coccoS = P.Rs2n_cocco * coccoN;
-    const double cyanoS = P.Rs2n_cyano * cyanoN;
-    const double eukarS = P.Rs2n_eukar * eukarN * Stress_fac;
-    const double diazS = P.Rs2n_diaz * diazN;
-    const double phytoS = diatS + coccoS + cyanoS + eukarS + diazS + P.G_phaeo_S * phaeoS;
-
-    double Rs2n_zoo;
-    if (phytoN > 0.0) {
-      Rs2n_zoo = (P.Rs2n_diat * diatN +
-                  P.G_phaeo_S * P.Rs2n_phaeo * phaeoN +
-                  P.Rs2n_cocco * coccoN +
-                  P.Rs2n_cyano * cyanoN +
-                  P.Rs2n_eukar * eukarN * Stress_fac +
-                  P.Rs2n_diaz * diazN);
-      Rs2n_zoo = fdiv(Rs2n_zoo, phytoN);
-    } else {
-      Rs2n_zoo = (P.Rs2n_diat + P.Rs2n_cocco + P.Rs2n_cyano + P.Rs2n_eukar + P.Rs2n_diaz + P.Rs2n_phaeo) / 6.0;
+    double kp, ek;
+    dms_attenuation(totalChl, A.dz[i2], kp, ek);
+    s_kp[k * 32 + lane] = kp;
+    s_ek[k * 32 + lane] = ek;
+  }
+  __syncthreads();
+  if (w == 0 && kmax > 0) {
+    double PAR = fmax(0.0, A.sw_flux[col]);
+    PAR = PAR * c_dms.p.f_qsw_par_DMS;
+    for (int k = 0; k < kmax; ++k) {
+      s_pin[k * 32 + lane] = PAR;
+      PAR = PAR * s_ek[k * 32 + lane];
     }
-    const double zooS = Rs2n_zoo * zooN;
+  }
+  __syncthreads();
 
-    const double B_diagnosed = P.B_preexp * ((phytoN > 0.0) ? fpow(phytoN, P.B_exp) : pow(phytoN, P.B_exp));
-
-    const double dms_s_dmsp = yield * P.k_conv * DMSP_loc;
-    const double dms_s = dms_s_dmsp;
-    const double dms_r_B = P.k_S_B * B_diagnosed * DMS_loc;
-    const double dms_r_phot = j_dms * DMS_loc;
-    const double dms_r_bkgnd = P.k_bkgnd * DMS_loc;
-    const double dms_r = dms_r_B + dms_r_phot + dms_r_bkgnd;
-
-    const double dmsp_s_phaeo = P.inject_scale * P.k_S_p_base * phaeoS;
-    const double dmsp_s_nonphaeo = P.inject_scale * k_S_p * phytoS;
-    const double dmsp_s_zoo = P.inject_scale * P.k_S_z * zooS;
-    const double dmsp_s = dmsp_s_phaeo + dmsp_s_nonphaeo + dmsp_s_zoo;
-    const double dmsp_r_B = P.k_conv * DMSP_loc;
-    const double dmsp_r_bkgnd = P.k_bkgnd * DMSP_loc;
-    const double dmsp_r = dmsp_r_B + dmsp_r_bkgnd;
-
-    const double t_dms = dms_s - dms_r, t_dmsp = dmsp_s - dmsp_r;
-    tnd[o2 + (size_t)(I.dms_ind - 1) * nLnC] = t_dms;
-    tnd[o2 + (size_t)(I.dmsp_ind - 1) * nLnC] = t_dmsp;
-    inv_dms += t_dms * dz;
-    inv_dmsp += t_dmsp * dz;
-
-    DST(diag_DMS_S_DMSP, dms_s_dmsp);
-    DST(diag_DMS_S_TOTAL, dms_s);
-    DST(diag_DMS_R_B, dms_r_B);
-    DST(diag_DMS_R_PHOT, dms_r_phot);
-    DST(diag_DMS_R_BKGND, dms_r_bkgnd);
-    DST(diag_DMS_R_TOTAL, dms_r);
-    DST(diag_DMSP_S_PHAEO, dmsp_s_phaeo);
-    DST(diag_DMSP_S_NONPHAEO, dmsp_s_nonphaeo);
-    DST(diag_DMSP_S_ZOO, dmsp_s_zoo);
-    DST(diag_DMSP_S_TOTAL, dmsp_s);
-    DST(diag_DMSP_R_B, dmsp_r_B);
-    DST(diag_DMSP_R_BKGND, dmsp_r_bkgnd);
-    DST(diag_DMSP_R_TOTAL, dmsp_r);
-    DST(diag_Cyano_frac, Cyano_frac);
-    DST(diag_Cocco_frac, Cocco_frac);
-    DST(diag_Eukar_frac, Eukar_frac);
-    DST(diag_diatS, diatS);
-    DST(diag_diatN, diatN);
-    DST(diag_phytoN, phytoN);
-    DST(diag_coccoS, coccoS);
-    DST(diag_cyanoS, cyanoS);
-    DST(diag_eukarS, eukarS);
-    DST(diag_diazS, diazS);
-    DST(diag_phaeoS, phaeoS);
-    DST(diag_zooS, zooS);
-    DST(diag_zooCC, zooC);
-    DST(diag_RSNzoo, Rs2n_zoo);
+  double inv_dms = 0.0, inv_dmsp = 0.0;   // sum over this thread's cells of tendency * dz (inventory)
+  if (in_range) {
+    for (int k = w; k < nL; k += kDmsTileWarps) {
+      const size_t i2 = (size_t)col + (size_t)nC * (size_t)k;
+      const bool active = k < kmax;
+      double t_dms = 0.0, t_dmsp = 0.0;
+      if (active) {   // diagnostics keep their previous contents outside active cells
+        const double PAR_avg = fdiv(s_pin[k * 32 + lane] * (1.0 - s_ek[k * 32 + lane]), s_kp[k * 32 + lane]);
+        dms_cell(A, i2, nLnC, PAR_avg, cc, t_dms, t_dmsp);
+        if (A.inv_partials) {
+          const double dz = A.dz[i2];
+          inv_dms += t_dms * dz;
+          inv_dmsp += t_dmsp * dz;
+        }
+      }
+      dms_store_tendencies(A, i2, nLnC, active, t_dms, t_dmsp);
+    }
   }
   if (A.inv_partials) {   // stage 1 of the inventory reduction, fused: one partial per block
     const double a = block_sum(inv_dms, red), b = block_sum(inv_dmsp, red);
@@ -202,7 +262,61 @@ dms_columns_kernel(const __grid_constant__ DmsArgs A) {
     }
   }
 }
-#undef DST
+
+// Fallback for level counts whose tile does not fit shared memory: one thread per column,
+// PAR carried down the column in a register.
+__global__ void __launch_bounds__(256)
+dms_columns_kernel(const __grid_constant__ DmsArgs A) {
+  __shared__ double red[256 / 32];
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nL = A.nL, nC = A.nC;
+  const bool in_range = col < nC;
+  const size_t nLnC = (size_t)nL * (size_t)nC;
+  int kmax = (in_range && col < A.nColumns) ? A.kmax[col] : 0;
+  if (kmax > nL) kmax = nL;
+  if (kmax < 0) kmax = 0;
+  double inv_dms = 0.0, inv_dmsp = 0.0;
+  const DmsIndices &I = c_dms.ind;
+
+  double SST_loc = 0.0, PAR_out = 0.0;
+  if (kmax > 0) {
+    SST_loc = A.sst[col];
+    PAR_out = fmax(0.0, A.sw_flux[col]);
+    PAR_out = PAR_out * c_dms.p.f_qsw_par_DMS;
+  }
+  const DmsColumnConsts cc = dms_column_consts(SST_loc);
+
+  for (int k = 0; in_range && k < nL; ++k) {
+    const size_t i2 = (size_t)col + (size_t)nC * (size_t)k;
+    const bool active = k < kmax;
+    double t_dms = 0.0, t_dmsp = 0.0;
+    if (active) {
+      const double *trc = A.tracers + i2;
+#define TR(ind_) fmax(0.0, trc[(size_t)((ind_) - 1) * nLnC])
+      const double totalChl = TR(I.spChl_ind) + TR(I.diatChl_ind) + TR(I.diazChl_ind) + TR(I.phaeoChl_ind);
+#undef TR
+      const double dz = A.dz[i2];
+      double KPARdz, eK;
+      dms_attenuation(totalChl, dz, KPARdz, eK);
+      const double PAR_in = PAR_out;
+      PAR_out = PAR_in * eK;
+      const double PAR_avg = fdiv(PAR_in * (1.0 - eK), KPARdz);
+      dms_cell(A, i2, nLnC, PAR_avg, cc, t_dms, t_dmsp);
+      inv_dms += t_dms * dz;
+      inv_dmsp += t_dmsp * dz;
+    }
+    dms_store_tendencies(A, i2, nLnC, active, t_dms, t_dmsp);
+  }
+  if (A.inv_partials) {
+    const double a = block_sum(inv_dms, red), b = block_sum(inv_dmsp, red);
+    if (threadIdx.x == 0) {
+      double *out = A.inv_partials + (size_t)blockIdx.x * kInvGroup;
+      out[0] = a; out[1] = b;
+#pragma unroll
+      for (int j = 2; j < kInvGroup; ++j) out[j] = 0.0;
+    }
+  }
+}
 
 __global__ void __launch_bounds__(256)
 dms_surface_kernel(const __grid_constant__ DmsSurfArgs A) {
@@ -373,9 +487,20 @@ inventory_fold_kernel(const __grid_constant__ InventoryFoldArgs A, int nParts) {
 
 static inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
 
+// shared memory of the tile kernel: three [nL][32] FP64 planes
+static size_t dms_tile_smem(int nL) { return (size_t)nL * 32 * 3 * sizeof(double); }
+static bool dms_use_tiles(int nL) { return dms_tile_smem(nL) <= 160 * 1024; }
+
 cudaError_t launch_dms_columns(const DmsArgs &a, cudaStream_t s) {
   if (a.nC <= 0 || a.nL <= 0) return cudaSuccess;
-  dms_columns_kernel<<<cdiv((size_t)a.nC, 256), 256, 0, s>>>(a);
+  if (dms_use_tiles(a.nL)) {
+    const size_t smem = dms_tile_smem(a.nL);
+    cudaError_t e = cudaFuncSetAttribute(dms_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    dms_cells_kernel<<<cdiv((size_t)a.nC, kDmsTileCols), kDmsTileCols * kDmsTileWarps, smem, s>>>(a);
+  } else {
+    dms_columns_kernel<<<cdiv((size_t)a.nC, 256), 256, 0, s>>>(a);
+  }
   return cudaGetLastError();
 }
 
@@ -407,7 +532,7 @@ cudaError_t launch_inventory_fold(const InventoryFoldArgs &a, int nParts, cudaSt
   inventory_fold_kernel<<<a.nGroups, kFoldRows * kInvGroup, 0, s>>>(a, nParts);
   return cudaGetLastError();
 }
-int dms_inventory_parts(int nC) { return (nC + 255) / 256; }
+int dms_inventory_parts(int nL, int nC) { return dms_use_tiles(nL) ? (nC + kDmsTileCols - 1) / kDmsTileCols : (nC + 255) / 256; }
 int macros_inventory_parts(int nL, int nC) { return (int)(((size_t)nL * (size_t)nC + kMacrosBlock - 1) / kMacrosBlock); }
 
 }  // namespace bgc
