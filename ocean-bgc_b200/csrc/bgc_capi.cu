@@ -588,22 +588,14 @@ static int source_sink_device(bgc_ctx *c, const BgcInput *in, const BgcForcing *
   LAUNCH(BGC_K_ECO_COLUMNS, 1, bgc::launch_eco_columns(ea, diag_mode, c->eco_variant, c->stream));
   if (c->inventory_on) {
     // destination of every value the sweep produced (layout: bgc_kernels.cuh, kEcoInvGroups)
-    const BgcIndices &I = c->bgc_tab.ind;
     int oi[bgc::kEcoInvGroups][bgc::kInvGroup];
-    const int plain[16] = {I.no3_ind, I.nh4_ind, I.fe_ind, I.sio3_ind, I.po4_ind, I.zooC_ind, I.doc_ind, I.don_ind,
-                           I.donr_ind, I.dop_ind, I.dopr_ind, I.dofe_ind, I.dic_ind, I.dic_alt_co2_ind, I.alk_ind,
-                           I.o2_ind};   // kEcoInvPlainOrder
-    for (int j = 0; j < 16; ++j) oi[j / 8][j % 8] = plain[j] - 1;
-    int row = 0;
-    for (int j = 0; j < 16; ++j) oi[2 + j / 8][j % 8] = -1;
-    for (int g = 0; g < BGC_AUTOTROPH_CNT; ++g) {
-      const BgcAutotroph &at = c->bgc_tab.a[g];
-      const int ind[5] = {at.Chl_ind, at.C_ind, at.Fe_ind, at.Si_ind, at.CaCO3_ind};
-      for (int j = 0; j < 5; ++j)
-        if (ind[j] > 0 && row < 14) { oi[2 + row / 8][row % 8] = ind[j] - 1; ++row; }
+    for (int v = 0; v < bgc::kEcoInvGroups * bgc::kInvGroup; ++v) {
+      int dst;
+      if (v < BGC_TRACER_CNT) dst = v;                    // tracer slot
+      else if (v < 32) dst = 60 + (v - 30);               // active cells, active columns
+      else dst = any_diag ? 52 + (v - 32) : -1;           // the Jint_* sums exist only with diagnostics
+      oi[v / bgc::kInvGroup][v % bgc::kInvGroup] = dst;
     }
-    oi[3][6] = 60; oi[3][7] = 61;                       // active cells, active columns
-    for (int j = 0; j < 8; ++j) oi[4][j] = any_diag ? 52 + j : -1;   // the Jint_* sums exist only with diagnostics
     RC(inventory_fold(c, ea.inv_partials, inv_parts, bgc::kEcoInvGroups, oi));
   }
   return BGC_OK;

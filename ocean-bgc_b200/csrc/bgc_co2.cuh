@@ -52,12 +52,12 @@ struct Co3Totals { double dic, ta, pt, sit; };   // mol/kg, after the floors of 
 
 // POP ref_pressure fit, co2calc.F90:371-372 (depth in m -> bar)
 __device__ __forceinline__ double press_bar_of_depth(double depth) {
-  return 0.059808 * (exp(-0.025 * depth) - 1.0) + 0.100766 * depth + 2.28405e-7 * (depth * depth);
+  return 0.059808 * (bexp(-0.025 * depth) - 1.0) + 0.100766 * depth + 2.28405e-7 * (depth * depth);
 }
 
-// Pressure factor exp((-deltaV + 0.5*Kappa*P)*P/(R*T)), Millero 1995.
+// Pressure factor bexp((-deltaV + 0.5*Kappa*P)*P/(R*T)), Millero 1995.
 __device__ __forceinline__ double kfac(double deltaV, double Kappa, double press_bar, double invRtk) {
-  return exp((-deltaV + 0.5 * Kappa * press_bar) * press_bar * invRtk);
+  return bexp((-deltaV + 0.5 * Kappa * press_bar) * press_bar * invRtk);
 }
 
 // `deep` is the reference's (k > 1): the pressure correction is keyed on the
@@ -90,7 +90,7 @@ __device__ __forceinline__ void co3_coeffs(bool deep, double depth, double temp,
   if (WANT_FF) {   // Weiss & Price 1980, co2calc.F90:423-431
     arg = -162.8301 + fdiv(218.2968, tk100) + 90.9241 * (dlogtk + kLn1em2) - 1.47696 * tk1002 +
           salt_lim * (.025695 - .025225 * tk100 + 0.0049867 * tk1002);
-    c.ff = exp(arg);
+    c.ff = bexp(arg);
   } else {
     c.ff = 0.0;
   }
@@ -98,22 +98,22 @@ __device__ __forceinline__ void co3_coeffs(bool deep, double depth, double temp,
   // k1, k2: Lueker et al. 2000, total pH scale (k1_k2_pH_tot = .true. at every
   // call site on this path: co2calc.F90:285, BGC_mod.F90:2764)
   arg = 3633.86 * invtk - 61.2172 + 9.67770 * dlogtk - 0.011555 * salt_lim + 0.0001152 * s2;
-  c.k1 = exp(-kLn10 * arg);
+  c.k1 = bexp(-kLn10 * arg);
   arg = 471.78 * invtk + 25.9290 - 3.16967 * dlogtk - 0.01781 * salt_lim + 0.0001122 * s2;
-  c.k2 = exp(-kLn10 * arg);
+  c.k2 = bexp(-kLn10 * arg);
 
   // kb, Dickson 1990 (co2calc.F90:529-551)
   arg = (-8966.90 - 2890.53 * sqrts - 77.942 * salt_lim + 1.728 * salt_lim * sqrts - 0.0996 * s2) * invtk +
         (148.0248 + 137.1942 * sqrts + 1.62142 * salt_lim) +
         (-24.4344 - 25.085 * sqrts - 0.2474 * salt_lim) * dlogtk +
         0.053105 * sqrts * tk;
-  // Pressure correction (Millero 1995).  Strict build: K = exp(arg) * exp(pressure term), the
+  // Pressure correction (Millero 1995).  Strict build: K = bexp(arg) * bexp(pressure term), the
   // reference's two factors.  Production build: one exponential of the summed argument
   // (identical up to the rounding of one addition, ~1e-16 relative * |arg|).
 #ifdef BGC_STRICT
-#define K_OF(arg_, dV_, Kap_) (exp(arg_) * (deep ? kfac((dV_), (Kap_), press_bar, invRtk) : 1.0))
+#define K_OF(arg_, dV_, Kap_) (bexp(arg_) * (deep ? kfac((dV_), (Kap_), press_bar, invRtk) : 1.0))
 #else
-#define K_OF(arg_, dV_, Kap_) exp((arg_) + (deep ? (-(dV_) + 0.5 * (Kap_) * press_bar) * press_bar * invRtk : 0.0))
+#define K_OF(arg_, dV_, Kap_) bexp((arg_) + (deep ? (-(dV_) + 0.5 * (Kap_) * press_bar) * press_bar * invRtk : 0.0))
 #endif
   c.kb = K_OF(arg, -29.48 + (0.1622 - 0.002608 * temp) * temp, -2.84 * 0.001);
   // k1p, k2p, k3p: DOE 1994 (co2calc.F90:560-637)
@@ -262,8 +262,13 @@ constexpr unsigned kSolveNoConvergence = 2u;
 __device__ __forceinline__ double solve_htotal(const Co3Consts &k, const Co3Totals &t,
                                                double phlo, double phhi, unsigned &status) {
   const TalkInv v = talk_invariants(k);
+#ifdef BGC_STRICT
   double x1 = exp10(-phhi);   // c10 ** (-phhi), co2calc.F90:848-849
   double x2 = exp10(-phlo);
+#else
+  double x1 = bexp(-phhi * kLn10);
+  double x2 = bexp(-phlo * kLn10);
+#endif
 
   double flo, fhi, f, df;
   talk_residual(k, t, v, x1, flo, df);
@@ -350,14 +355,14 @@ __device__ __forceinline__ void co3_sat_vals(bool deep, double depth, double tem
   const double deltaV = -48.76 + 0.5304 * temp;
   const double Kappa = (-11.76 + 0.3692 * temp) * 0.001;
 #ifdef BGC_STRICT
-  double K_calc = exp(arg_calc), K_arag = exp(arg_arag);
+  double K_calc = bexp(arg_calc), K_arag = bexp(arg_arag);
   if (deep) {
     K_calc *= kfac(deltaV, Kappa, press_bar, invRtk);
     K_arag *= kfac(deltaV + 2.8, Kappa, press_bar, invRtk);
   }
 #else   // one exponential of the summed argument, as in co3_coeffs
-  const double K_calc = exp(arg_calc + (deep ? (-deltaV + 0.5 * Kappa * press_bar) * press_bar * invRtk : 0.0));
-  const double K_arag = exp(arg_arag + (deep ? (-(deltaV + 2.8) + 0.5 * Kappa * press_bar) * press_bar * invRtk : 0.0));
+  const double K_calc = bexp(arg_calc + (deep ? (-deltaV + 0.5 * Kappa * press_bar) * press_bar * invRtk : 0.0));
+  const double K_arag = bexp(arg_arag + (deep ? (-(deltaV + 2.8) + 0.5 * Kappa * press_bar) * press_bar * invRtk : 0.0));
 #endif
 
   const double inv_Ca = fdiv((35.0 / 0.01028), salt_lim);

@@ -131,9 +131,8 @@ struct InventoryFoldArgs {
 cudaError_t launch_inventory_fold(const InventoryFoldArgs &a, int nParts, cudaStream_t s);
 int dms_inventory_parts(int nL, int nC);
 int macros_inventory_parts(int nL, int nC);
-// column sweep: [eco_inventory_parts][kEcoInvGroups][kInvGroup]
-//   groups 0,1: the 16 plain tracers in the order of kEcoInvPlainOrder (k_eco.cu / bgc_capi.cu)
-//   groups 2,3: the 14 functional-group tracers (row = order of appearance: group 1..4, Chl C Fe Si CaCO3),
-//               then active cells, active columns;   group 4: the eight Jint_* column sums
+// column sweep: [eco_inventory_parts][kEcoInvGroups][kInvGroup] = 40 values per block:
+//   [0..29] the 30 tracer slots (0-based slot = value index), [30] active cells, [31] active columns,
+//   [32..39] the eight Jint_* column sums
 
 }  // namespace bgc

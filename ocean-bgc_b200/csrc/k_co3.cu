@@ -196,7 +196,7 @@ __device__ __forceinline__ double schmidt_co2(double SST) {  // Wanninkhof 1992 
 }
 __device__ __forceinline__ double o2sat(double SST, double SSS, double T0K) {   // Garcia & Gordon 1992 (:3012-3083)
   const double TS = log(((T0K + 25.0) - SST) / (T0K + SST));
-  const double r = exp(2.00907 + TS * (3.22014 + TS * (4.05010 + TS * (4.94457 + TS * (-2.56847E-1 + TS * 3.88767)))) +
+  const double r = bexp(2.00907 + TS * (3.22014 + TS * (4.05010 + TS * (4.94457 + TS * (-2.56847E-1 + TS * 3.88767)))) +
                        SSS * ((-6.24523E-3 + TS * (-7.37614E-3 + TS * (-1.03410E-2 + TS * -8.17083E-3))) +
                               SSS * -4.88682E-7));
   return r / 0.0223916;

@@ -50,7 +50,6 @@ struct EcoDerived {
   double r_dTN[4], r_dTS[4];
   double r_o2_min_delta;
   double r_scalelen_dz[4];
-  int inv_row[4][5];   // inventory: row (0..13) of the group's Chl, C, Fe, Si, CaCO3 tracer; -1 = none
 };
 
 __constant__ BgcTables c_eco;
@@ -74,12 +73,6 @@ cudaError_t upload_bgc_tables_eco(const BgcTables &t, cudaStream_t s) {
     d.agg_min_dps[a] = at.agg_rate_min * dps;
     d.r_dTN[a] = 1.0 / (at.temp_thresN - at.temp_optN);
     d.r_dTS[a] = 1.0 / (at.temp_thresS - at.temp_optS);
-  }
-  int row = 0;
-  for (int a = 0; a < BGC_AUTOTROPH_CNT; ++a) {
-    const BgcAutotroph &at = t.a[a];
-    const int ind[5] = {at.Chl_ind, at.C_ind, at.Fe_ind, at.Si_ind, at.CaCO3_ind};
-    for (int j = 0; j < 5; ++j) d.inv_row[a][j] = (ind[j] > 0 && row < 14) ? row++ : -1;
   }
   d.r_o2_min_delta = 1.0 / t.p.parm_o2_min_delta;
   d.r_scalelen_dz[0] = 0.0;
@@ -191,11 +184,17 @@ static_assert((0 ECO_DIAG_K2_LIST(COUNT_ONE)) + 13 == (0 BGC_DIAG_K2_LIST(COUNT_
 // Shared memory of a block, in rows of BLOCK doubles (one slot per thread):
 //   2 stages x R_ROWS   the level's input slab: rows 0..29 = tracer slots, then the rows below
 //   X_ROWS              per-thread scratch: Pprime(4); DIAG: the three per-group column
-//                       integrals (:1838-1846, :1268), 4 each; inventory: sum_k tendency*dz of
-//                       the 14 functional-group tracers
+//                       integrals (:1838-1846, :1268), 4 each, and the fourteen column integrals
+//                       that are touched once per level (Jint_*, the z-integrals, the O2 minimum):
+//                       one shared-memory read-modify-write per level each instead of 28 registers
+//                       held across the whole level body (they used to spill to local memory,
+//                       which misses the few KB of L1 left beside a 221 KB carve-out)
 //   2 mbarriers
 enum { R_T = BGC_TRACER_CNT, R_ZMID, R_DZ, R_ZBOT, R_FESED, R_S, R_CO3, R_SATC, R_SATA, R_ROWS };
-enum { X_PPRIME = 0, X_ZPHOTO = 4, X_ZNO3 = 8, X_ZCACO3 = 12, X_INV = 16, X_ROWS = 30 };
+enum { X_PPRIME = 0, X_ZPHOTO = 4, X_ZNO3 = 8, X_ZCACO3 = 12,
+       X_JC = 16, X_JC100, X_JN, X_JN100, X_JP, X_JP100, X_JSI, X_JSI100,
+       X_CHL100, X_BSI, X_CACO3ZINT, X_PHOTOCZINT, X_PHOTOCNO3ZINT, X_O2MIN, X_ROWS };
+static_assert(X_ROWS == 30, "shared-memory budget of the column sweep: 2*R_ROWS + X_ROWS rows of BLOCK doubles");
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
@@ -268,27 +267,18 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
   // ---- column integrals / scan state (diagnostics only)
   double ZSATCALC = 0.0, ZSATARAG = 0.0, CALC_ANOM_km1 = 0.0, ARAG_ANOM_km1 = 0.0;
   double zmid_km1 = 0.0, zbot_km1 = 0.0;
-  double tot_bSi_form = 0.0, tot_CaCO3_form_zint = 0.0, photoC_TOT_zint = 0.0,
-         photoC_NO3_TOT_zint = 0.0, Chl_TOT_zint_100m = 0.0;
-  double JC = 0.0, JC100 = 0.0, JN = 0.0, JN100 = 0.0, JP = 0.0, JP100 = 0.0, JSi = 0.0, JSi100 = 0.0;
-  double O2_min = 0.0, O2_min_depth = 0.0;
-  unsigned poc_errors = 0;
-  if (DIAG) {
+  double O2_min_depth = 0.0;
 #pragma unroll
-    for (int a = 0; a < NA; ++a) { XS(X_ZPHOTO + a) = 0.0; XS(X_ZNO3 + a) = 0.0; XS(X_ZCACO3 + a) = 0.0; }
-  }
+  for (int r = X_ZPHOTO; r < X_ROWS; ++r) XS(r) = 0.0;
 
   double *tnd = A.tend + col;
 
-  // ---- inventory (fused stage 1): sum_k tendency*dz.  The 14 functional-group tracers are
-  //      accumulated per thread in shared memory (run-time slot); the 16 plain tracers go through
-  //      a warp-level transpose every level and live as ONE register per lane.
+  // ---- inventory (fused stage 1): sum_k tendency*dz.  Every tendency*dz of a level is written
+  //      back into the stage row of its own tracer slot (the input has been consumed by then); a
+  //      warp-level transpose at the end of the level leaves lane l with the warp's sum of slot l,
+  //      so the running inventory of all 30 tracers is ONE register per lane.
   const bool inv = A.inv_partials != nullptr;
-  double inv_plain = 0.0;
-  if (inv) {
-#pragma unroll
-    for (int r = 0; r < 14; ++r) XS(X_INV + r) = 0.0;
-  }
+  double inv_acc = 0.0;
 
   // ---- deepest active level of the block: nothing below it is fetched
   __shared__ int s_kmax_blk;
@@ -366,7 +356,7 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
       // ---- inactive cell: the reference's whole-array zero fills
       if (inv && k < kmax_blk) {
 #pragma unroll
-        for (int q = 0; q < 16; ++q) IN(q) = 0.0;   // this column's share of the level's inventory sums
+        for (int q = 0; q < BGC_TRACER_CNT; ++q) IN(q) = 0.0;   // this column's share of the level's inventory sums
       }
       if (in_range) {
 #pragma unroll 6
@@ -408,7 +398,7 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
 
     // ---- functional-group tracers: clamp, zero mask (:826-844), Pprime (:1083-1094);
     //      staged in shared memory for the rolled group loop below
-    double Chl_sum = 0.0;
+    double Chl_sum = 0.0, Chl_100 = 0.0;
 #pragma unroll
     for (int a = 0; a < NA; ++a) {
       const BgcAutotroph &at = c_eco.a[a];
@@ -423,7 +413,7 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
       if (at.Si_ind > 0) IN(at.Si_ind - 1) = vSi;
       if (at.CaCO3_ind > 0) IN(at.CaCO3_ind - 1) = vCa;
       Chl_sum = Chl_sum + vChl;
-      if (DIAG) Chl_TOT_zint_100m = Chl_TOT_zint_100m + vChl * pt100;
+      if (DIAG) Chl_100 = Chl_100 + vChl * pt100;
 
       double C_loss_thres = f_loss_thres * at.loss_thres;
       if (at.temp_function == BGC_TFNC_Q10) {
@@ -434,6 +424,7 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
       }
       XS(X_PPRIME + a) = fmax(vC - C_loss_thres, 0.0);
     }
+    if (DIAG) XS(X_CHL100) = XS(X_CHL100) + Chl_100;
 
     // ---- PAR (Morel & Maritorena 2001), :907-924
     const double PAR_in = PAR_out;
@@ -444,7 +435,7 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
       else             KPARdz = 0.001131 * fpow(w, 0.4562);
     }
     KPARdz = KPARdz * dz;
-    const double eKPAR = exp(-KPARdz);
+    const double eKPAR = bexp(-KPARdz);
     PAR_out = PAR_in * eKPAR;
     const double PAR_avg = fdiv(PAR_in * (1.0 - eKPAR), KPARdz);
 
@@ -480,6 +471,7 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
     double Ca_prod = 0.0, Si_prod = 0.0;        // last writer wins among qualifying groups (:1480-1498)
     double tot_CaCO3_form = 0.0, tot_Nfix = 0.0;
     double s_tC = 0.0, s_tCaCO3 = 0.0, s_tSi = 0.0, s_QpC = 0.0, s_Nfix_J = 0.0, photoC_NO3_TOT = 0.0;
+    double bSi_form_k = 0.0, CaCO3_zint_k = 0.0, NO3_zint_k = 0.0;   // this level's additions to column integrals
 
     // ---- per functional group: quotas (:850-898), uptake, photosynthesis, losses,
     //      grazing, routing (:1107-1388), tendencies (:1700-1745)
@@ -573,7 +565,7 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
         if (TEMP > tmpTmax) PCmax = 0.0;
       }
       const double aPI = at.alphaPI * thetaC * PAR_avg;
-      const double light_lim = (1.0 - exp(fdiv(-1.0 * aPI, PCmax + epsTinv)));
+      const double light_lim = (1.0 - bexp(fdiv(-1.0 * aPI, PCmax + epsTinv)));
       const double PCphoto = PCmax * light_lim;
       if (DIAG) STA(diag_light_lim, light_lim);
 
@@ -613,7 +605,7 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
       double photoSi = 0.0;
       if (has_Si) {
         photoSi = photoC * gQsi;
-        tot_bSi_form = tot_bSi_form + photoSi;   // (:1230-1231, no dz)
+        bSi_form_k = bSi_form_k + photoSi;   // (:1230-1231, no dz)
       }
       if (DIAG) {
         STA(diag_photoNO3, NO3_V);
@@ -645,7 +637,7 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
         if (DIAG) {
           const double w = dz * cp;
           XS(X_ZCACO3 + a) = XS(X_ZCACO3 + a) + w;
-          tot_CaCO3_form_zint = tot_CaCO3_form_zint + w;
+          CaCO3_zint_k = CaCO3_zint_k + w;
         }
       }
       if (DIAG) STA(diag_CaCO3_form, CaCO3_PROD);
@@ -787,22 +779,22 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
         TEND(at.Fe_ind) = t_autoFe;
         s_tC = s_tC + t_autoC;
         s_QpC = s_QpC + at.Qp * t_autoC;
-        if (inv) {
-          XS(X_INV + D.inv_row[a][0]) += t_autoChl * dz;
-          XS(X_INV + D.inv_row[a][1]) += t_autoC * dz;
-          XS(X_INV + D.inv_row[a][2]) += t_autoFe * dz;
+        if (inv) {   // the group's inputs have been read: their rows carry tendency*dz from here on
+          IN(at.Chl_ind - 1) = t_autoChl * dz;
+          IN(at.C_ind - 1) = t_autoC * dz;
+          IN(at.Fe_ind - 1) = t_autoFe * dz;
         }
         if (has_Si) {
           const double t = photoSi - Qsi * w;
           TEND(at.Si_ind) = t;
           s_tSi = s_tSi + t;
-          if (inv) XS(X_INV + D.inv_row[a][3]) += t * dz;
+          if (inv) IN(at.Si_ind - 1) = t * dz;
         }
         if (has_Ca) {
           const double t = CaCO3_PROD - QCaCO3 * w;
           TEND(at.CaCO3_ind) = t;
           s_tCaCO3 = s_tCaCO3 + t;
-          if (inv) XS(X_INV + D.inv_row[a][4]) += t * dz;
+          if (inv) IN(at.CaCO3_ind - 1) = t * dz;
         }
       }
 
@@ -817,7 +809,7 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
         XS(X_ZNO3 + a) = zn;
         photoC_NO3_TOT = photoC_NO3_TOT + photoC_NO3;
         // adds the RUNNING per-group integral every level (:1844-1846)
-        photoC_NO3_TOT_zint = photoC_NO3_TOT_zint + zn;
+        NO3_zint_k = NO3_zint_k + zn;
       }
     }   // functional groups
 
@@ -892,8 +884,8 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
         }
       }
 
-      const double DECAY_Hard = exp(cdiv(-dz, 4.0e6, 1.0 / 4.0e6));
-      const double DECAY_HardDust = exp(cdiv(-dz, 1.2e7, 1.0 / 1.2e7));
+      const double DECAY_Hard = bexp(cdiv(-dz, 4.0e6, 1.0 / 4.0e6));
+      const double DECAY_HardDust = bexp(cdiv(-dz, 1.2e7, 1.0 / 1.2e7));
       const double TfuncS = Tfunc;   // 1.5**(same exponent) (:2295) is bit-identical to Tfunc (:1041)
 
       const double dzr = frcp(dz);
@@ -910,10 +902,10 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
       const double dust_diss = scalelength * dust_diss0;
       sio2_diss = fdiv(sio2_diss, TfuncS);
 
-      const double decay_POC_E = exp(fdiv(-dz, poc_diss));
-      const double decay_SiO2 = exp(fdiv(-dz, sio2_diss));
-      const double decay_CaCO3 = exp(fdiv(-dz, caco3_diss));
-      const double decay_dust = exp(fdiv(-dz, dust_diss));
+      const double decay_POC_E = bexp(fdiv(-dz, poc_diss));
+      const double decay_SiO2 = bexp(fdiv(-dz, sio2_diss));
+      const double decay_CaCO3 = bexp(fdiv(-dz, caco3_diss));
+      const double decay_dust = bexp(fdiv(-dz, dust_diss));
 
       Ca_s = Ca_s_in * decay_CaCO3 + Ca_prod * ((1.0 - CaCO3_gamma) * (1.0 - decay_CaCO3) * caco3_diss);
       Ca_h = Ca_h_in * DECAY_Hard + Ca_prod * (CaCO3_gamma * dz);
@@ -923,7 +915,7 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
       du_h = du_h_in * DECAY_HardDust;
 
       double POC_PROD_avail = POC_prod - CaCO3_rho * Ca_prod - SiO2_rho * Si_prod;
-      if (POC_PROD_avail < 0.0) poc_errors++;   // computed and never reported by the reference (:2381-2383)
+      if (POC_PROD_avail < 0.0 && A.status) atomicAdd(&A.status[2], 1ull);   // computed and never reported by the reference (:2381-2383)
 
       double new_QA_dust_def;
       if (QA_dust_def > 0.0) {
@@ -1106,13 +1098,13 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
     TEND(I.dic_alt_co2_ind) = t_dic_alt;
     TEND(I.alk_ind) = t_alk;
     TEND(I.o2_ind) = t_o2;
-    if (inv) {
-      // Every tracer input of this level has been consumed: rows 0..15 of the stage become the
-      // scratch of the inventory transpose below.  Order = kEcoInvPlainOrder.
-      IN(0) = t_no3 * dz; IN(1) = t_nh4 * dz; IN(2) = t_fe * dz; IN(3) = t_sio3 * dz;
-      IN(4) = t_po4 * dz; IN(5) = t_zooC * dz; IN(6) = t_doc * dz; IN(7) = t_don * dz;
-      IN(8) = t_donr * dz; IN(9) = t_dop * dz; IN(10) = t_dopr * dz; IN(11) = t_dofe * dz;
-      IN(12) = t_dic * dz; IN(13) = t_dic_alt * dz; IN(14) = t_alk * dz; IN(15) = t_o2 * dz;
+    if (inv) {   // every tracer input of this level has been consumed (see the group loop)
+      IN(I.no3_ind - 1) = t_no3 * dz; IN(I.nh4_ind - 1) = t_nh4 * dz; IN(I.fe_ind - 1) = t_fe * dz;
+      IN(I.sio3_ind - 1) = t_sio3 * dz; IN(I.po4_ind - 1) = t_po4 * dz; IN(I.zooC_ind - 1) = t_zooC * dz;
+      IN(I.doc_ind - 1) = t_doc * dz; IN(I.don_ind - 1) = t_don * dz; IN(I.donr_ind - 1) = t_donr * dz;
+      IN(I.dop_ind - 1) = t_dop * dz; IN(I.dopr_ind - 1) = t_dopr * dz; IN(I.dofe_ind - 1) = t_dofe * dz;
+      IN(I.dic_ind - 1) = t_dic * dz; IN(I.dic_alt_co2_ind - 1) = t_dic_alt * dz;
+      IN(I.alk_ind - 1) = t_alk * dz; IN(I.o2_ind - 1) = t_o2 * dz;
     }
 
     // ---- diagnostics and column integrals (:1796-1945)
@@ -1129,7 +1121,7 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
       if (HAS(diag_AOU)) {   // O2SAT_singleValue, Garcia & Gordon 1992 (:3012-3083)
         const double SALT = IN(R_S);
         const double TS = log(fdiv(((T0K + 25.0) - TEMP), (T0K + TEMP)));
-        double o2sat = exp(2.00907 + TS * (3.22014 + TS * (4.05010 + TS * (4.94457 + TS * (-2.56847E-1 + TS * 3.88767)))) +
+        double o2sat = bexp(2.00907 + TS * (3.22014 + TS * (4.05010 + TS * (4.94457 + TS * (-2.56847E-1 + TS * 3.88767)))) +
                            SALT * ((-6.24523E-3 + TS * (-7.37614E-3 + TS * (-1.03410E-2 + TS * -8.17083E-3))) +
                                    SALT * -4.88682E-7));
         o2sat = cdiv(o2sat, 0.0223916, 1.0 / 0.0223916);
@@ -1139,7 +1131,10 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
       ST2(diag_zoo_loss, zoo_loss);
       ST2(diag_auto_graze_TOT, s_auto_graze);
       ST2(diag_photoC_TOT, s_photoC);
-      photoC_TOT_zint = photoC_TOT_zint + s_photoC * dz;
+      XS(X_PHOTOCZINT) = XS(X_PHOTOCZINT) + s_photoC * dz;
+      XS(X_PHOTOCNO3ZINT) = XS(X_PHOTOCNO3ZINT) + NO3_zint_k;
+      XS(X_BSI) = XS(X_BSI) + bSi_form_k;
+      XS(X_CACO3ZINT) = XS(X_CACO3ZINT) + CaCO3_zint_k;
       ST2(diag_photoC_NO3_TOT, photoC_NO3_TOT);
 
       ST2(diag_DOC_prod, DOC_prod);
@@ -1156,24 +1151,24 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
       const bool shallow = zbot <= 100.0e2;
 
       double w1 = (t_dic + t_doc + t_zooC + s_tC) + s_tCaCO3;
-      JC = JC + w1 * dz + POC_sed + Ca_sed;
-      JC100 = JC100 + w1 * pt100 + (shallow ? (POC_sed + Ca_sed) : 0.0);
+      XS(X_JC) = XS(X_JC) + w1 * dz + POC_sed + Ca_sed;
+      XS(X_JC100) = XS(X_JC100) + w1 * pt100 + (shallow ? (POC_sed + Ca_sed) : 0.0);
 
       w1 = t_no3 + t_nh4 + t_don + t_donr + Qn * t_zooC + Qn * s_tC;
       w1 = (w1 + DENITRIF + SED_DENITRIF) - s_Nfix_J;
-      JN = JN + w1 * dz + POC_sed * Qn;
-      JN100 = JN100 + w1 * pt100 + (shallow ? (POC_sed * Qn) : 0.0);
+      XS(X_JN) = XS(X_JN) + w1 * dz + POC_sed * Qn;
+      XS(X_JN100) = XS(X_JN100) + w1 * pt100 + (shallow ? (POC_sed * Qn) : 0.0);
 
       w1 = (t_po4 + t_dop + t_dopr + Qp_zoo_pom * t_zooC) + s_QpC;
-      JP = JP + w1 * dz + POC_sed * Qp_zoo_pom;
-      JP100 = JP100 + w1 * pt100 + (shallow ? (POC_sed * Qp_zoo_pom) : 0.0);
+      XS(X_JP) = XS(X_JP) + w1 * dz + POC_sed * Qp_zoo_pom;
+      XS(X_JP100) = XS(X_JP100) + w1 * pt100 + (shallow ? (POC_sed * Qp_zoo_pom) : 0.0);
 
       w1 = t_sio3 + s_tSi;
-      JSi = JSi + w1 * dz + Si_sed;
-      JSi100 = JSi100 + w1 * pt100 + (shallow ? Si_sed : 0.0);
+      XS(X_JSI) = XS(X_JSI) + w1 * dz + Si_sed;
+      XS(X_JSI100) = XS(X_JSI100) + w1 * pt100 + (shallow ? Si_sed : 0.0);
 
       // O2 minimum scan (:1954-1968)
-      if (k == 0 || O2_loc < O2_min) { O2_min = O2_loc; O2_min_depth = zmid; }
+      if (k == 0 || O2_loc < XS(X_O2MIN)) { XS(X_O2MIN) = O2_loc; O2_min_depth = zmid; }
 
       zmid_km1 = zmid;
     }
@@ -1182,17 +1177,17 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
 #undef TEND
     }   // active cell
     if (inv && k < kmax_blk) {   // block-uniform condition
-      // Transpose through shared memory: lane l adds row (l & 15) over 16 of the warp's 32
-      // columns (skewed start: conflict-free), then the two halves meet.  Lanes l and l ^ 16
-      // both end up with the warp's sum of plain tracer (l & 15); fixed order, no atomics.
+      // Transpose through shared memory: lane l adds row l (= tracer slot l) over the warp's 32
+      // columns, starting at column l (skewed: conflict-free); fixed order, no atomics.
       __syncwarp();
-      const int lane = tid & 31, row = lane & 15;
-      const double *src = st + row * BLOCK + (tid & ~31) + (lane & 16);
-      double d = 0.0;
+      const int lane = tid & 31;
+      if (lane < BGC_TRACER_CNT) {
+        const double *src = st + lane * BLOCK + (tid & ~31);
+        double d = 0.0;
 #pragma unroll
-      for (int c = 0; c < 16; ++c) d += src[(c + row) & 15];
-      d += __shfl_xor_sync(0xffffffffu, d, 16);
-      inv_plain += d;
+        for (int c = 0; c < 32; ++c) d += src[(c + lane) & 31];
+        inv_acc += d;
+      }
     }
 
     // ---- end of level: every thread is done with stage k&1 (generic-proxy reads and the
@@ -1206,18 +1201,18 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
   // ---- per-column diagnostics
   if (DIAG && in_range) {
     if (kmax > 0) {
-      STC(diag_photoC_TOT_zint, photoC_TOT_zint);
-      STC(diag_photoC_NO3_TOT_zint, photoC_NO3_TOT_zint);
-      STC(diag_Jint_Ctot, JC);       STC(diag_Jint_100m_Ctot, JC100);
-      STC(diag_Jint_Ntot, JN);       STC(diag_Jint_100m_Ntot, JN100);
-      STC(diag_Jint_Ptot, JP);       STC(diag_Jint_100m_Ptot, JP100);
-      STC(diag_Jint_Sitot, JSi);     STC(diag_Jint_100m_Sitot, JSi100);
-      STC(diag_Chl_TOT_zint_100m, Chl_TOT_zint_100m);
-      STC(diag_tot_CaCO3_form_zint, tot_CaCO3_form_zint);
-      STC(diag_tot_bSi_form, tot_bSi_form);
+      STC(diag_photoC_TOT_zint, XS(X_PHOTOCZINT));
+      STC(diag_photoC_NO3_TOT_zint, XS(X_PHOTOCNO3ZINT));
+      STC(diag_Jint_Ctot, XS(X_JC));       STC(diag_Jint_100m_Ctot, XS(X_JC100));
+      STC(diag_Jint_Ntot, XS(X_JN));       STC(diag_Jint_100m_Ntot, XS(X_JN100));
+      STC(diag_Jint_Ptot, XS(X_JP));       STC(diag_Jint_100m_Ptot, XS(X_JP100));
+      STC(diag_Jint_Sitot, XS(X_JSI));     STC(diag_Jint_100m_Sitot, XS(X_JSI100));
+      STC(diag_Chl_TOT_zint_100m, XS(X_CHL100));
+      STC(diag_tot_CaCO3_form_zint, XS(X_CACO3ZINT));
+      STC(diag_tot_bSi_form, XS(X_BSI));
       STC(diag_zsatcalc, ZSATCALC);
       STC(diag_zsatarag, ZSATARAG);
-      STC(diag_O2_ZMIN, O2_min);
+      STC(diag_O2_ZMIN, XS(X_O2MIN));
       STC(diag_O2_ZMIN_DEPTH, O2_min_depth);
 #pragma unroll
       for (int a = 0; a < NA; ++a) {
@@ -1230,35 +1225,28 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
       BGC_DIAG_CA_LIST(ZERO_CA)
     }
   }
-  if (poc_errors && A.status) atomicAdd(&A.status[2], (unsigned long long)poc_errors);
-
-  // ---- inventory partials of this block: [kEcoInvGroups][kInvGroup]
+  // ---- inventory partials of this block: [kEcoInvGroups][kInvGroup] =
+  //      30 tracer slots, active cells, active columns, the eight Jint_* column sums
   if (inv) {
     __shared__ double s_red[BLOCK / 32];
-    __shared__ double s_plain[BLOCK / 32][16];
+    __shared__ double s_slot[BLOCK / 32][32];
     double *out = A.inv_partials + (size_t)blockIdx.x * (kEcoInvGroups * kInvGroup);
-    if ((tid & 31) < 16) s_plain[tid >> 5][tid & 15] = inv_plain;
+    s_slot[tid >> 5][tid & 31] = inv_acc;
     __syncthreads();
-    if (tid < 16) {
+    if (tid < BGC_TRACER_CNT) {
       double t = 0.0;
 #pragma unroll
-      for (int w = 0; w < BLOCK / 32; ++w) t += s_plain[w][tid];
-      out[tid] = t;                                   // groups 0 and 1
-    }
-#pragma unroll 1
-    for (int r = 0; r < 14; ++r) {
-      const double t = block_sum(XS(X_INV + r), s_red);
-      if (tid == 0) out[16 + r] = t;                  // groups 2 and 3
+      for (int w = 0; w < BLOCK / 32; ++w) t += s_slot[w][tid];
+      out[tid] = t;
     }
     {
       const double cells = block_sum((double)kmax, s_red), cols = block_sum(kmax > 0 ? 1.0 : 0.0, s_red);
       if (tid == 0) { out[30] = cells; out[31] = cols; }
     }
-    const double jv[8] = {JC, JC100, JN, JN100, JP, JP100, JSi, JSi100};   // zero without diagnostics
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const double t = block_sum(DIAG ? jv[q] : 0.0, s_red);
-      if (tid == 0) out[32 + q] = t;                  // group 4
+#pragma unroll 1
+    for (int q = 0; q < 8; ++q) {   // zero without diagnostics (the rows are never added to)
+      const double t = block_sum(XS(X_JC + q), s_red);
+      if (tid == 0) out[32 + q] = t;
     }
   }
 #undef XS

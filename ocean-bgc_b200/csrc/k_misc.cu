@@ -45,14 +45,14 @@ __device__ __forceinline__ DmsColumnConsts dms_column_consts(double SST_loc) {
   return r;
 }
 
-// Light attenuation over one cell (DMS_mod.F90:510-527): KPARdz and exp(-KPARdz).
+// Light attenuation over one cell (DMS_mod.F90:510-527): KPARdz and bexp(-KPARdz).
 __device__ __forceinline__ void dms_attenuation(double totalChl, double dz, double &KPARdz, double &eK) {
   const double w = fmax(totalChl, 0.02);
   double kp;
   if (w < 0.13224) kp = 0.000919 * fpow(w, 0.3536);
   else             kp = 0.001131 * fpow(w, 0.4562);
   KPARdz = kp * dz;
-  eK = exp(-KPARdz);
+  eK = bexp(-KPARdz);
 }
 
 // Everything of one active cell once PAR_avg is known (DMS_mod.F90:529-765): loads the cell's
@@ -182,8 +182,8 @@ __device__ __forceinline__ void dms_store_tendencies(const DmsArgs &A, size_t i2
 // Tile kernel: a block owns kDmsTileCols consecutive columns over ALL levels; warp w takes the
 // levels w, w + W, ...  The only vertical coupling of DMS_SourceSink is the PAR attenuation
 // product (:510-527), so
-//   phase 1  every cell's KPARdz and exp(-KPARdz) -> shared memory (cell-parallel),
-//   phase 2  warp 0 walks its 32 columns top to bottom, PAR_out = PAR_in * exp(-KPARdz) in the
+//   phase 1  every cell's KPARdz and bexp(-KPARdz) -> shared memory (cell-parallel),
+//   phase 2  warp 0 walks its 32 columns top to bottom, PAR_out = PAR_in * bexp(-KPARdz) in the
 //            reference's order (bit-identical to the sequential sweep), PAR_in -> shared memory,
 //   phase 3  every cell is independent: 9 tracer loads, 14 + 27 stores.
 // The mesh offers nL times more parallelism this way than one thread per column, which is
@@ -204,7 +204,7 @@ dms_cells_kernel(const __grid_constant__ DmsArgs A) {
   if (kmax > nL) kmax = nL;
   if (kmax < 0) kmax = 0;
   double *const s_kp = dsm;                       // [nL][32] KPARdz
-  double *const s_ek = dsm + (size_t)nL * 32;     // [nL][32] exp(-KPARdz)
+  double *const s_ek = dsm + (size_t)nL * 32;     // [nL][32] bexp(-KPARdz)
   double *const s_pin = dsm + (size_t)nL * 64;    // [nL][32] PAR_in
   const DmsIndices &I = c_dms.ind;
 
