@@ -102,6 +102,7 @@ struct bgc_ctx {
   double *d_inventory = nullptr;            // BGC_INVENTORY_LEN
   bool inventory_on = false;
   int eco_variant = 0;                      // launch shape of the column sweep (BGC_ECO_VARIANT, tuning only)
+  int dms_variant = 0;                      // launch shape of the DMS tile kernel (BGC_DMS_VARIANT, tuning only)
   std::map<std::string, DevBuf> arena;      // persistent device buffers (host-layout mode, scratch)
   ncclComm_t comm = nullptr;
   int nranks = 1;
@@ -189,6 +190,7 @@ extern "C" int bgc_ctx_create(int device, int nLevelsMax, int nColumnsMax, bgc_c
   c->nL = nLevelsMax;
   c->nC = nColumnsMax;
   if (const char *v = getenv("BGC_ECO_VARIANT")) c->eco_variant = atoi(v);
+  if (const char *v = getenv("BGC_DMS_VARIANT")) c->dms_variant = atoi(v);
   CU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
   c->stream = c->own_stream;
   CU(cudaMalloc(&c->d_status, 4 * sizeof(unsigned long long)));
@@ -458,6 +460,9 @@ static int down_c(bgc_ctx *c, const void *dev, void *host, size_t bytes) {
 
 static int check_dims(bgc_ctx *c, int nL, int nC, int nCols) {
   if (nL < 1 || nC < 1 || nCols < 0 || nCols > nC) return fail(BGC_ERR_ARG, "bad dimensions (%d,%d,%d)", nL, nC, nCols);
+  // the kernels index elements with 32 bits (k_eco.cu); 30 * nL * nC must stay below 2^32
+  if ((unsigned long long)nL * (unsigned long long)nC * BGC_TRACER_CNT >= (1ull << 32))
+    return fail(BGC_ERR_ARG, "block of %d x %d cells is too large for one call (30*nL*nC >= 2^32): split the columns", nL, nC);
   (void)c;
   return BGC_OK;
 }
@@ -794,7 +799,7 @@ static int dms_source_sink_device(bgc_ctx *c, const DmsInput *in, const DmsForci
   const bool inv = c->inventory_on;
   a.inv_partials = nullptr;
   if (inv) RC(arena_d(c, "inv_partials_dms", (size_t)bgc::dms_inventory_parts(nL, nC) * bgc::kInvGroup, &a.inv_partials));
-  LAUNCH(BGC_K_DMS_COLUMNS, 1, bgc::launch_dms_columns(a, c->stream));
+  LAUNCH(BGC_K_DMS_COLUMNS, 1, bgc::launch_dms_columns(a, c->dms_variant, c->stream));
   if (inv) {   // only DMS and DMSP have non-zero tendencies (DMS_mod.F90:413, :741-742)
     int oi[1][bgc::kInvGroup];
     for (int j = 0; j < bgc::kInvGroup; ++j) oi[0][j] = -1;

@@ -36,6 +36,15 @@ constexpr double kVolToMass = 1.0 / kMassToVol;
 // pin the correctly rounded doubles instead of calling log() on the device.
 constexpr double kLn10 = 2.302585092994046;
 constexpr double kLn1em2 = -4.605170185988091;
+
+// -log10(h): pH from the hydrogen-ion concentration (h is a normal, positive double)
+__device__ __forceinline__ double ph_of_h(double h) {
+#ifdef BGC_STRICT
+  return -log10(h);
+#else
+  return -blog(h) * (1.0 / kLn10);
+#endif
+}
 // The reference's bracket-growth loop has no exit (co2calc.F90:920-938; the
 // abort at :931-933 is commented out).  The ratio x2/x1 squares on every pass,
 // so 64 passes overflow any finite bracket: cap there and raise a status flag.
@@ -74,7 +83,7 @@ __device__ __forceinline__ void co3_coeffs(bool deep, double depth, double temp,
   const double tk100 = tk * 1e-2;
   const double tk1002 = tk100 * tk100;
   const double invtk = frcp(tk);
-  const double dlogtk = log(tk);
+  const double dlogtk = blog(tk);
   const double invRtk = (1.0 / 83.1451) * invtk;
 
   const double is = fdiv(19.924 * salt_lim, (1000.0 - 1.005 * salt_lim));
@@ -84,7 +93,7 @@ __device__ __forceinline__ void co3_coeffs(bool deep, double depth, double temp,
   const double s2 = salt_lim * salt_lim;
   const double scl = cdiv(salt_lim, 1.80655, 1.0 / 1.80655);
 
-  const double log_1_m_1p005em3_s = log(1.0 - 0.001005 * salt_lim);
+  const double log_1_m_1p005em3_s = blog(1.0 - 0.001005 * salt_lim);
   double arg;
 
   if (WANT_FF) {   // Weiss & Price 1980, co2calc.F90:423-431
@@ -152,7 +161,7 @@ __device__ __forceinline__ void co3_coeffs(bool deep, double depth, double temp,
 
   // kf, Dickson & Riley 1979, uses the (corrected) ks (co2calc.F90:740-764)
   arg = 1.0 + fdiv((0.1400 / 96.062) * (scl), c.ks);
-  const double log_1_p_tot_sulfate_div_ks = log(arg);
+  const double log_1_p_tot_sulfate_div_ks = blog(arg);
   arg = 1590.2 * invtk - 12.641 + 1.525 * sqrtis + log_1_m_1p005em3_s + log_1_p_tot_sulfate_div_ks;
   c.kf = K_OF(arg, -9.78 - (0.009 + 0.000942 * temp) * temp, (-3.91 + 0.054 * temp) * 0.001);
 #undef K_OF
@@ -338,7 +347,7 @@ __device__ __forceinline__ void co3_sat_vals(bool deep, double depth, double tem
   const double press_bar = press_bar_of_depth(depth);
   const double salt_lim = fmax(salt, kSaltMin);
   const double tk = kT0Kelvin + temp;
-  const double log10tk = cdiv(log(tk), kLn10, 1.0 / kLn10);   // :1161-1164
+  const double log10tk = cdiv(blog(tk), kLn10, 1.0 / kLn10);   // :1161-1164
   const double invtk = frcp(tk);
   const double invRtk = (1.0 / 83.1451) * invtk;
   const double sqrts = sqrt(salt_lim);

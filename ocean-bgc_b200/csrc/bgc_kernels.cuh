@@ -95,7 +95,7 @@ struct DmsArgs {
   DmsDiagnostics d;
   double *inv_partials;   // NULL, or [dms_inventory_parts][kInvGroup]: fused stage 1 of the inventory
 };
-cudaError_t launch_dms_columns(const DmsArgs &a, cudaStream_t s);
+cudaError_t launch_dms_columns(const DmsArgs &a, int variant, cudaStream_t s);
 
 struct DmsSurfArgs {
   int nL, nC, nColumns;

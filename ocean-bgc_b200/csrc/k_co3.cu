@@ -101,7 +101,7 @@ co3_cells_kernel(const __grid_constant__ Co3Args A) {
     {
       const double h2 = h * h;
       const double denom = frcp(h2 + k1 * h + k1 * k2);
-      const double ph = -log10(h);
+      const double ph = ph_of_h(h);
       if (A.h2co3) A.h2co3[cell] = (tot.dic * h2 * denom) * kMassToVol;
       if (A.hco3) A.hco3[cell] = (tot.dic * k1 * h * denom) * kMassToVol;
       if (A.co3) A.co3[cell] = (tot.dic * k1 * k2 * denom) * kMassToVol;
@@ -111,7 +111,7 @@ co3_cells_kernel(const __grid_constant__ Co3Args A) {
     {
       const double h2 = h_alt * h_alt;
       const double denom = frcp(h2 + k1 * h_alt + k1 * k2);
-      const double ph = -log10(h_alt);
+      const double ph = ph_of_h(h_alt);
       if (A.h2co3_alt) A.h2co3_alt[cell] = (tot.dic * h2 * denom) * kMassToVol;
       if (A.hco3_alt) A.hco3_alt[cell] = (tot.dic * k1 * h_alt * denom) * kMassToVol;
       if (A.co3_alt) A.co3_alt[cell] = (tot.dic * k1 * k2 * denom) * kMassToVol;
@@ -156,7 +156,7 @@ __device__ __forceinline__ SurfaceCo2 co2calc_1point(double temp, double salt, d
   double co2star = fdiv(tot.dic * htotal2, (htotal2 + K.k1 * htotal + K.k1 * K.k2));
   const double co2starair = xco2 * K.ff * atmpres;
   double dco2star = co2starair - co2star;
-  r.ph = -log10(htotal);
+  r.ph = ph_of_h(htotal);
   double pco2surf = fdiv(co2star, K.ff);
   double dpco2 = pco2surf - xco2 * atmpres;
   r.co2star = co2star * kMassToVol;

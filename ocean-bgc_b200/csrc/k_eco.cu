@@ -151,9 +151,9 @@ constexpr int NA = BGC_AUTOTROPH_CNT;
 #define HAS(name) (DIAG == 2 || A.d.name != nullptr)
 #define ST2(name, val) do { if (HAS(name)) A.d.name[i2] = (val); } while (0)
 #define STA(name, val) do { if (HAS(name)) A.d.name[ia] = (val); } while (0)
-#define STA_AT(name, a_, val) do { if (HAS(name)) A.d.name[i2 + (size_t)(a_) * nLnC] = (val); } while (0)
+#define STA_AT(name, a_, val) do { if (HAS(name)) A.d.name[i2 + (unsigned)(a_) * nLnC] = (val); } while (0)
 #define STC(name, val) do { if (HAS(name)) A.d.name[col] = (val); } while (0)
-#define STCA(name, a_, val) do { if (HAS(name)) A.d.name[col + (size_t)(a_) * (size_t)nC] = (val); } while (0)
+#define STCA(name, a_, val) do { if (HAS(name)) A.d.name[(unsigned)col + (unsigned)(a_) * (unsigned)nC] = (val); } while (0)
 
 // The (k,col) diagnostics this kernel owns: BGC_DIAG_K2_LIST minus the ten carbonate
 // arrays (written by co3_cells_kernel) and the three arrays the reference declares but
@@ -231,7 +231,10 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
   const int col = col0 + tid;
   const int nL = A.nL, nC = A.nC;
   const bool in_range = col < nC;
-  const size_t nLnC = (size_t)nL * (size_t)nC;
+  // Element indices are 32-bit: one IMAD.WIDE.U32 forms an address from (index, base pointer).
+  // The largest index, 30 * nL * nC, stays below 2^32 for any block that fits one GPU's memory
+  // (180 GB / 2200 B per cell = 82 M cells); bgc_capi.cu rejects larger blocks.
+  const unsigned nLnC = (unsigned)nL * (unsigned)nC;
   double *const xs = smem + 2 * R_ROWS * BLOCK;                       // per-thread scratch rows
   unsigned long long *const bars = (unsigned long long *)(xs + X_ROWS * BLOCK);
 #define XS(row) xs[(row) * BLOCK + tid]
@@ -271,7 +274,6 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
 #pragma unroll
   for (int r = X_ZPHOTO; r < X_ROWS; ++r) XS(r) = 0.0;
 
-  double *tnd = A.tend + col;
 
   // ---- inventory (fused stage 1): sum_k tendency*dz.  Every tendency*dz of a level is written
   //      back into the stage row of its own tracer slot (the input has been consumed by then); a
@@ -312,7 +314,7 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
       const double *src;
       if (r < BGC_TRACER_CNT) {
         if ((skip_slots >> r) & 1u) continue;
-        src = A.tracers + (size_t)r * nLnC;
+        src = A.tracers + (size_t)r * (size_t)nLnC;
       } else {
         switch (r) {
           case R_T:     src = A.T; break;
@@ -335,8 +337,7 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
   }
 
   for (int k = 0; k < nL; ++k) {
-    const size_t i2 = (size_t)col + (size_t)nC * (size_t)k;
-    const size_t o2 = (size_t)nC * (size_t)k;   // offset of level k within one tracer slab
+    const unsigned i2 = (unsigned)col + (unsigned)nC * (unsigned)k;
     double *const st = smem + (size_t)(k & 1) * R_ROWS * BLOCK;
 
     if (TMA) {
@@ -360,7 +361,7 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
       }
       if (in_range) {
 #pragma unroll 6
-        for (int n = 0; n < BGC_TRACER_CNT; ++n) tnd[o2 + (size_t)n * nLnC] = 0.0;
+        for (int n = 0; n < BGC_TRACER_CNT; ++n) A.tend[i2 + (unsigned)n * nLnC] = 0.0;
         if (DIAG) {
           ECO_DIAG_K2_LIST(ZERO_K2)
           BGC_DIAG_KA_LIST(ZERO_KA)
@@ -369,19 +370,18 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
     } else {
 
 #define TR(ind_) fmax(0.0, IN((ind_) - 1))
-#define TEND(ind_) tnd[o2 + (size_t)((ind_) - 1) * nLnC]
+#define TEND(ind_) A.tend[i2 + (unsigned)((ind_) - 1) * nLnC]
 
     // ---- this level's inputs (setup_loop clamp folded in, :747-783)
     const double TEMP = IN(R_T);
     const double zmid = IN(R_ZMID);
     const double dz = IN(R_DZ);
     const double zbot = IN(R_ZBOT);
+    // (the tracers that only the code after the functional-group loop needs are read from the
+    //  stage there: they would otherwise sit in registers across the whole loop)
     const double PO4_loc = TR(I.po4_ind), NO3_loc = TR(I.no3_ind), SiO3_loc = TR(I.sio3_ind),
-                 NH4_loc = TR(I.nh4_ind), Fe_loc = TR(I.fe_ind), O2_loc = TR(I.o2_ind),
-                 DOC_loc = TR(I.doc_ind), DON_loc = TR(I.don_ind), DOFe_loc = TR(I.dofe_ind),
-                 DOP_loc = TR(I.dop_ind), DOPr_loc = TR(I.dopr_ind), DONr_loc = TR(I.donr_ind),
+                 NH4_loc = TR(I.nh4_ind), Fe_loc = TR(I.fe_ind), DOP_loc = TR(I.dop_ind),
                  zooC_loc = TR(I.zooC_ind);
-    const double fesed = IN(R_FESED);
 
     // ---- temperature function, loss thresholds (:1041-1094)
     const double Tfunc = fpow_base(Q_10, kLnQ10, cdiv(((TEMP + T0K) - (Tref + T0K)), 10.0, 0.1));
@@ -478,7 +478,7 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
 #pragma unroll 1
     for (int a = 0; a < NA; ++a) {
       const BgcAutotroph &at = c_eco.a[a];
-      const size_t ia = i2 + (size_t)a * nLnC;
+      const unsigned ia = i2 + (unsigned)a * nLnC;
       const double aChl = IN(at.Chl_ind - 1), aC = IN(at.C_ind - 1), aFe = IN(at.Fe_ind - 1), Pprime = XS(X_PPRIME + a);
       const bool has_Si = at.Si_ind > 0, has_Ca = at.CaCO3_ind > 0;
 
@@ -813,6 +813,10 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
       }
     }   // functional groups
 
+    const double O2_loc = TR(I.o2_ind), DOC_loc = TR(I.doc_ind), DON_loc = TR(I.don_ind),
+                 DOFe_loc = TR(I.dofe_ind), DOPr_loc = TR(I.dopr_ind), DONr_loc = TR(I.donr_ind);
+    const double fesed = IN(R_FESED);
+
     // ---- zooplankton routing (:1395-1415)
     const double f_zoo_detr = fdiv(zd_num, zd_den);
     const double Zprime = fmax(zooC_loc - f_loss_thres * loss_thres_zoo, 0.0);
@@ -1120,7 +1124,7 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
       ST2(diag_O2_CONSUMPTION, O2_CONSUMPTION);
       if (HAS(diag_AOU)) {   // O2SAT_singleValue, Garcia & Gordon 1992 (:3012-3083)
         const double SALT = IN(R_S);
-        const double TS = log(fdiv(((T0K + 25.0) - TEMP), (T0K + TEMP)));
+        const double TS = blog(fdiv(((T0K + 25.0) - TEMP), (T0K + TEMP)));
         double o2sat = bexp(2.00907 + TS * (3.22014 + TS * (4.05010 + TS * (4.94457 + TS * (-2.56847E-1 + TS * 3.88767)))) +
                            SALT * ((-6.24523E-3 + TS * (-7.37614E-3 + TS * (-1.03410E-2 + TS * -8.17083E-3))) +
                                    SALT * -4.88682E-7));
@@ -1168,9 +1172,9 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
       XS(X_JSI100) = XS(X_JSI100) + w1 * pt100 + (shallow ? Si_sed : 0.0);
 
       // O2 minimum scan (:1954-1968)
-      if (k == 0 || O2_loc < XS(X_O2MIN)) { XS(X_O2MIN) = O2_loc; O2_min_depth = zmid; }
+      if (k == 0 || O2_loc < XS(X_O2MIN)) { XS(X_O2MIN) = O2_loc; O2_min_depth = IN(R_ZMID); }
 
-      zmid_km1 = zmid;
+      zmid_km1 = IN(R_ZMID);
     }
     zbot_km1 = zbot;
 #undef TR

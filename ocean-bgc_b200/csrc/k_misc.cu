@@ -27,7 +27,8 @@ namespace {
 
 constexpr double dms_epsC = 1.00e-8;   // DMS_parms.F90:194-195 (carries the _r8 suffix: exact)
 
-#define DST(name, val) do { if (A.d.name) A.d.name[i2] = (val); } while (0)
+// ALLDIAG: every diagnostic array is present (unchecked stores)
+#define DST(name, val) do { if (ALLDIAG || A.d.name) A.d.name[i2] = (val); } while (0)
 
 // Column-constant factors of DMS_SourceSink: all depend on SST only (DMS_mod.F90:584-592, :637-640).
 struct DmsColumnConsts { double cyano_T, yield; };
@@ -55,20 +56,32 @@ __device__ __forceinline__ void dms_attenuation(double totalChl, double dz, doub
   eK = bexp(-KPARdz);
 }
 
-// Everything of one active cell once PAR_avg is known (DMS_mod.F90:529-765): loads the cell's
-// tracers, stores the two live tendencies and the 27 diagnostics.
-__device__ __forceinline__ void dms_cell(const DmsArgs &A, size_t i2, size_t nLnC, double PAR_avg,
+// The nine tracers one cell consumes (raw; the clamp is applied in dms_cell).  NO3 and DOC are
+// copied by the reference (:471-472) but reach no output (DOC feeds only the unused UV_avg,
+// :531-536): not read here.
+struct DmsCellIn { double zooC, spC, diatC, diazC, phaeoC, spChl, spCaCO3, dms, dmsp; };
+
+__device__ __forceinline__ DmsCellIn dms_load_cell(const DmsArgs &A, unsigned i2, unsigned nLnC) {
+  const DmsIndices &I = c_dms.ind;
+  const double *trc = A.tracers;
+#define TR(ind_) trc[i2 + (unsigned)((ind_) - 1) * nLnC]
+  DmsCellIn c;
+  c.zooC = TR(I.zooC_ind); c.spC = TR(I.spC_ind); c.diatC = TR(I.diatC_ind); c.diazC = TR(I.diazC_ind);
+  c.phaeoC = TR(I.phaeoC_ind); c.spChl = TR(I.spChl_ind); c.spCaCO3 = TR(I.spCaCO3_ind);
+  c.dms = TR(I.dms_ind); c.dmsp = TR(I.dmsp_ind);
+#undef TR
+  return c;
+}
+
+// Everything of one active cell once PAR_avg is known (DMS_mod.F90:529-765): stores the 27
+// diagnostics and returns the two live tendencies.
+template <bool ALLDIAG>
+__device__ __forceinline__ void dms_cell(const DmsArgs &A, unsigned i2, const DmsCellIn &in, double PAR_avg,
                                          const DmsColumnConsts cc, double &t_dms, double &t_dmsp) {
   const DmsParams &P = c_dms.p;
-  const DmsIndices &I = c_dms.ind;
-  const double *trc = A.tracers + i2;
-#define TR(ind_) fmax(0.0, trc[(size_t)((ind_) - 1) * nLnC])
-  // NO3 and DOC are copied by the reference (:471-472) but reach no output
-  // (DOC feeds only the unused UV_avg, :531-536): not read here.
-  const double zooC = TR(I.zooC_ind), spC = TR(I.spC_ind), diatC = TR(I.diatC_ind),
-               diazC = TR(I.diazC_ind), phaeoC = TR(I.phaeoC_ind), spChl = TR(I.spChl_ind),
-               spCaCO3 = TR(I.spCaCO3_ind), DMS_loc = TR(I.dms_ind), DMSP_loc = TR(I.dmsp_ind);
-#undef TR
+  const double zooC = fmax(0.0, in.zooC), spC = fmax(0.0, in.spC), diatC = fmax(0.0, in.diatC),
+               diazC = fmax(0.0, in.diazC), phaeoC = fmax(0.0, in.phaeoC), spChl = fmax(0.0, in.spChl),
+               spCaCO3 = fmax(0.0, in.spCaCO3), DMS_loc = fmax(0.0, in.dms), DMSP_loc = fmax(0.0, in.dmsp);
   const double k_S_p = P.k_S_p_base * (P.mort + cdiv(zooC, 0.3, 1.0 / 0.3));   // literal 0.3, not zooC_avg (:529)
   const double j_dms = P.j_dms_perI * PAR_avg;
 
@@ -166,16 +179,15 @@ __device__ __forceinline__ void dms_cell(const DmsArgs &A, size_t i2, size_t nLn
 #undef DST
 
 // DMS_output%DMS_tendencies = 0 (DMS_mod.F90:413) and the two live slots of an active cell.
-__device__ __forceinline__ void dms_store_tendencies(const DmsArgs &A, size_t i2, size_t nLnC, bool active,
+__device__ __forceinline__ void dms_store_tendencies(const DmsArgs &A, unsigned i2, unsigned nLnC, bool active,
                                                      double t_dms, double t_dmsp) {
   const DmsIndices &I = c_dms.ind;
-  double *tnd = A.tend + i2;
 #pragma unroll
   for (int n = 0; n < DMS_TRACER_CNT; ++n) {
     double v = 0.0;
     if (active && n == I.dms_ind - 1) v = t_dms;
     if (active && n == I.dmsp_ind - 1) v = t_dmsp;
-    tnd[(size_t)n * nLnC] = v;
+    A.tend[i2 + (unsigned)n * nLnC] = v;
   }
 }
 
@@ -191,7 +203,8 @@ __device__ __forceinline__ void dms_store_tendencies(const DmsArgs &A, size_t i2
 constexpr int kDmsTileCols = 32;
 constexpr int kDmsTileWarps = 8;
 
-__global__ void __launch_bounds__(kDmsTileCols * kDmsTileWarps, 3)
+template <bool ALLDIAG, int MINB>
+__global__ void __launch_bounds__(kDmsTileCols * kDmsTileWarps, MINB)
 dms_cells_kernel(const __grid_constant__ DmsArgs A) {
   extern __shared__ double dsm[];
   __shared__ double red[kDmsTileWarps];
@@ -199,12 +212,12 @@ dms_cells_kernel(const __grid_constant__ DmsArgs A) {
   const int col = blockIdx.x * kDmsTileCols + lane;
   const int nL = A.nL, nC = A.nC;
   const bool in_range = col < nC;
-  const size_t nLnC = (size_t)nL * (size_t)nC;
+  const unsigned nLnC = (unsigned)nL * (unsigned)nC;   // 32-bit element indices: see k_eco.cu
   int kmax = (in_range && col < A.nColumns) ? A.kmax[col] : 0;
   if (kmax > nL) kmax = nL;
   if (kmax < 0) kmax = 0;
   double *const s_kp = dsm;                       // [nL][32] KPARdz
-  double *const s_ek = dsm + (size_t)nL * 32;     // [nL][32] bexp(-KPARdz)
+  double *const s_ek = dsm + (size_t)nL * 32;     // [nL][32] exp(-KPARdz)
   double *const s_pin = dsm + (size_t)nL * 64;    // [nL][32] PAR_in
   const DmsIndices &I = c_dms.ind;
 
@@ -213,9 +226,8 @@ dms_cells_kernel(const __grid_constant__ DmsArgs A) {
   const DmsColumnConsts cc = dms_column_consts(SST_loc);
 
   for (int k = w; k < kmax; k += kDmsTileWarps) {
-    const size_t i2 = (size_t)col + (size_t)nC * (size_t)k;
-    const double *trc = A.tracers + i2;
-#define TR(ind_) fmax(0.0, trc[(size_t)((ind_) - 1) * nLnC])
+    const unsigned i2 = (unsigned)col + (unsigned)nC * (unsigned)k;
+#define TR(ind_) fmax(0.0, A.tracers[i2 + (unsigned)((ind_) - 1) * nLnC])
     const double totalChl = TR(I.spChl_ind) + TR(I.diatChl_ind) + TR(I.diazChl_ind) + TR(I.phaeoChl_ind);
 #undef TR
     double kp, ek;
@@ -236,13 +248,18 @@ dms_cells_kernel(const __grid_constant__ DmsArgs A) {
 
   double inv_dms = 0.0, inv_dmsp = 0.0;   // sum over this thread's cells of tendency * dz (inventory)
   if (in_range) {
+    // software pipeline: the next cell's nine loads are in flight while this one is computed
+    DmsCellIn cur = {}, nxt = {};
+    if (w < kmax) cur = dms_load_cell(A, (unsigned)col + (unsigned)nC * (unsigned)w, nLnC);
     for (int k = w; k < nL; k += kDmsTileWarps) {
-      const size_t i2 = (size_t)col + (size_t)nC * (size_t)k;
+      const unsigned i2 = (unsigned)col + (unsigned)nC * (unsigned)k;
+      const int kn = k + kDmsTileWarps;
+      if (kn < kmax) nxt = dms_load_cell(A, i2 + (unsigned)nC * (unsigned)kDmsTileWarps, nLnC);
       const bool active = k < kmax;
       double t_dms = 0.0, t_dmsp = 0.0;
       if (active) {   // diagnostics keep their previous contents outside active cells
         const double PAR_avg = fdiv(s_pin[k * 32 + lane] * (1.0 - s_ek[k * 32 + lane]), s_kp[k * 32 + lane]);
-        dms_cell(A, i2, nLnC, PAR_avg, cc, t_dms, t_dmsp);
+        dms_cell<ALLDIAG>(A, i2, cur, PAR_avg, cc, t_dms, t_dmsp);
         if (A.inv_partials) {
           const double dz = A.dz[i2];
           inv_dms += t_dms * dz;
@@ -250,6 +267,7 @@ dms_cells_kernel(const __grid_constant__ DmsArgs A) {
         }
       }
       dms_store_tendencies(A, i2, nLnC, active, t_dms, t_dmsp);
+      cur = nxt;
     }
   }
   if (A.inv_partials) {   // stage 1 of the inventory reduction, fused: one partial per block
@@ -271,7 +289,7 @@ dms_columns_kernel(const __grid_constant__ DmsArgs A) {
   const int col = blockIdx.x * blockDim.x + threadIdx.x;
   const int nL = A.nL, nC = A.nC;
   const bool in_range = col < nC;
-  const size_t nLnC = (size_t)nL * (size_t)nC;
+  const unsigned nLnC = (unsigned)nL * (unsigned)nC;
   int kmax = (in_range && col < A.nColumns) ? A.kmax[col] : 0;
   if (kmax > nL) kmax = nL;
   if (kmax < 0) kmax = 0;
@@ -287,12 +305,11 @@ dms_columns_kernel(const __grid_constant__ DmsArgs A) {
   const DmsColumnConsts cc = dms_column_consts(SST_loc);
 
   for (int k = 0; in_range && k < nL; ++k) {
-    const size_t i2 = (size_t)col + (size_t)nC * (size_t)k;
+    const unsigned i2 = (unsigned)col + (unsigned)nC * (unsigned)k;
     const bool active = k < kmax;
     double t_dms = 0.0, t_dmsp = 0.0;
     if (active) {
-      const double *trc = A.tracers + i2;
-#define TR(ind_) fmax(0.0, trc[(size_t)((ind_) - 1) * nLnC])
+#define TR(ind_) fmax(0.0, A.tracers[i2 + (unsigned)((ind_) - 1) * nLnC])
       const double totalChl = TR(I.spChl_ind) + TR(I.diatChl_ind) + TR(I.diazChl_ind) + TR(I.phaeoChl_ind);
 #undef TR
       const double dz = A.dz[i2];
@@ -301,7 +318,7 @@ dms_columns_kernel(const __grid_constant__ DmsArgs A) {
       const double PAR_in = PAR_out;
       PAR_out = PAR_in * eK;
       const double PAR_avg = fdiv(PAR_in * (1.0 - eK), KPARdz);
-      dms_cell(A, i2, nLnC, PAR_avg, cc, t_dms, t_dmsp);
+      dms_cell<false>(A, i2, dms_load_cell(A, i2, nLnC), PAR_avg, cc, t_dms, t_dmsp);
       inv_dms += t_dms * dz;
       inv_dmsp += t_dmsp * dz;
     }
@@ -491,17 +508,28 @@ static inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) 
 static size_t dms_tile_smem(int nL) { return (size_t)nL * 32 * 3 * sizeof(double); }
 static bool dms_use_tiles(int nL) { return dms_tile_smem(nL) <= 160 * 1024; }
 
-cudaError_t launch_dms_columns(const DmsArgs &a, cudaStream_t s) {
-  if (a.nC <= 0 || a.nL <= 0) return cudaSuccess;
-  if (dms_use_tiles(a.nL)) {
-    const size_t smem = dms_tile_smem(a.nL);
-    cudaError_t e = cudaFuncSetAttribute(dms_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    dms_cells_kernel<<<cdiv((size_t)a.nC, kDmsTileCols), kDmsTileCols * kDmsTileWarps, smem, s>>>(a);
-  } else {
-    dms_columns_kernel<<<cdiv((size_t)a.nC, 256), 256, 0, s>>>(a);
-  }
+template <bool ALLDIAG, int MINB>
+static cudaError_t launch_dms_tiles(const DmsArgs &a, cudaStream_t s) {
+  const size_t smem = dms_tile_smem(a.nL);
+  auto kern = dms_cells_kernel<ALLDIAG, MINB>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  kern<<<cdiv((size_t)a.nC, kDmsTileCols), kDmsTileCols * kDmsTileWarps, smem, s>>>(a);
   return cudaGetLastError();
+}
+
+cudaError_t launch_dms_columns(const DmsArgs &a, int variant, cudaStream_t s) {
+  if (a.nC <= 0 || a.nL <= 0) return cudaSuccess;
+  if (!dms_use_tiles(a.nL)) {
+    dms_columns_kernel<<<cdiv((size_t)a.nC, 256), 256, 0, s>>>(a);
+    return cudaGetLastError();
+  }
+  bool all = true;
+  double *const *pp = (double *const *)&a.d;
+  for (size_t i = 0; i < sizeof(DmsDiagnostics) / sizeof(double *); ++i) all = all && pp[i] != nullptr;
+  // variant 1: three blocks per SM (80 registers); default: two (128 registers, deeper prefetch)
+  if (variant == 1) return all ? launch_dms_tiles<true, 3>(a, s) : launch_dms_tiles<false, 3>(a, s);
+  return all ? launch_dms_tiles<true, 2>(a, s) : launch_dms_tiles<false, 2>(a, s);
 }
 
 cudaError_t launch_dms_surface(const DmsSurfArgs &a, cudaStream_t s) {
