@@ -436,22 +436,33 @@ def run_e2e(args, pkg, host, ctx, parms, rank, world, local_rank, dev):
     cells = int(bgc.active_mask().sum())
     n2 = nL * nC * 8
     abi = pkg.abi
-    h2d = n2 * (30 + 5 + 1 + 2) + nC * (8 + 4 + 16) \
-        + n2 * (14 + 1 + len(abi.DMS_DIAG)) + nC * (4 + 16) \
-        + n2 * (8 + 1 + len(abi.MACROS_DIAG)) + nC * 4 \
+    # bytes the library moves per step (bgc_capi.cu host_pipeline): inputs no kernel reads are not
+    # uploaded (BGC DIC_ALT_CO2; DMS NO3, DOC; MACROS cell_thickness), and the DMS / MACROS
+    # diagnostics are not uploaded when every cell of a chunk is active (as here).
+    h2d = n2 * (29 + 5 + 1 + 2) + nC * (8 + 4 + 16) \
+        + n2 * (12 + 1) + nC * (4 + 16) \
+        + n2 * 8 + nC * 4 \
         + nC * 8 * (30 + 10 + 5 * 30) + nC * 8 * (14 + 5 + 14 + 8)
     d2h = n2 * (30 + 2 + 58 + 18 * 4) + nC * 8 * (17 + 12) \
         + n2 * (14 + len(abi.DMS_DIAG)) + n2 * (8 + len(abi.MACROS_DIAG)) \
         + nC * 8 * (3 + 5 * 30 + 14) + nC * 8 * (1 + 14 + 8)
+    ctx.inventory_enable(False)   # the Fortran-facing calls do not use the inventory (default: off)
+
+    calls = [("BGC_SourceSink", lambda: host.BGC_SourceSink(ctx, bgc, True, True)),
+             ("BGC_SurfaceFluxes", lambda: host.BGC_SurfaceFluxes(ctx, bgc)),
+             ("DMS_SourceSink", lambda: host.DMS_SourceSink(ctx, dms, True)),
+             ("DMS_SurfaceFluxes", lambda: host.DMS_SurfaceFluxes(ctx, dms)),
+             ("MACROS_SourceSink", lambda: host.MACROS_SourceSink(ctx, mac, True))]
+    call_s = {k: 0.0 for k, _ in calls}
 
     def step():
-        host.BGC_SourceSink(ctx, bgc, True, True)
-        host.BGC_SurfaceFluxes(ctx, bgc)
-        host.DMS_SourceSink(ctx, dms, True)
-        host.DMS_SurfaceFluxes(ctx, dms)
-        host.MACROS_SourceSink(ctx, mac, True)
+        for name, fn in calls:   # every call is synchronous on return (Fortran semantics)
+            t = time.perf_counter()
+            fn()
+            call_s[name] += time.perf_counter() - t
     step()   # cold pass + arena allocation
     step()
+    call_s = {k: 0.0 for k in call_s}
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -468,8 +479,10 @@ def run_e2e(args, pkg, host, ctx, parms, rank, world, local_rank, dev):
     dt = float(t.item())
     return {"value": float(c.item()) / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
             "ms_per_step": dt * 1e3, "steps": args.e2e_steps, "columns_per_gpu": nC,
+            "ms_per_call": {k: v * 1e3 / args.e2e_steps for k, v in call_s.items()},
             "api": "bgc_source_sink/bgc_surface_fluxes/dms_source_sink/dms_surface_fluxes/macros_source_sink "
-                   "with BGC_MEM_HOST_FORTRAN, pinned host arrays, synchronous on return"}
+                   "with BGC_MEM_HOST_FORTRAN, pinned host arrays, synchronous on return; each call is a "
+                   "two-stream pipeline over 32768-column chunks (upload, transpose, kernels, transpose, download)"}
 
 
 if __name__ == "__main__":

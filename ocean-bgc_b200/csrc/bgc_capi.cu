@@ -94,6 +94,9 @@ struct bgc_ctx {
   int nL = 0, nC = 0;
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
+  cudaStream_t pipe_stream = nullptr;       // second slot of the host-layout pipeline
+  cudaEvent_t pipe_event = nullptr;
+  int host_chunk_columns = 0;               // columns per pipeline chunk (0 = automatic; BGC_HOST_CHUNK_COLUMNS)
   bgc::BgcTables bgc_tab;
   bgc::DmsTables dms_tab;
   bgc::MacrosTables macros_tab;
@@ -191,7 +194,10 @@ extern "C" int bgc_ctx_create(int device, int nLevelsMax, int nColumnsMax, bgc_c
   c->nC = nColumnsMax;
   if (const char *v = getenv("BGC_ECO_VARIANT")) c->eco_variant = atoi(v);
   if (const char *v = getenv("BGC_DMS_VARIANT")) c->dms_variant = atoi(v);
+  if (const char *v = getenv("BGC_HOST_CHUNK_COLUMNS")) c->host_chunk_columns = atoi(v);
   CU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&c->pipe_stream, cudaStreamNonBlocking));
+  CU(cudaEventCreateWithFlags(&c->pipe_event, cudaEventDisableTiming));
   c->stream = c->own_stream;
   CU(cudaMalloc(&c->d_status, 4 * sizeof(unsigned long long)));
   CU(cudaMemset(c->d_status, 0, 4 * sizeof(unsigned long long)));
@@ -212,6 +218,8 @@ extern "C" int bgc_ctx_destroy(bgc_ctx *c) {
   for (auto &sp : c->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
   for (auto e : c->ev_pool) cudaEventDestroy(e);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  if (c->pipe_stream) cudaStreamDestroy(c->pipe_stream);
+  if (c->pipe_event) cudaEventDestroy(c->pipe_event);
   std::lock_guard<std::mutex> lock(g_mu);
   g_versions.erase(c);
   for (auto *m : {&g_const_owner_bgc, &g_const_owner_dms, &g_const_owner_macros}) {
@@ -410,52 +418,125 @@ static int ensure_macros_tables(bgc_ctx *c) {
 }
 
 // ------------------------------------------------------------------ host-layout transport
-// Fortran A(k,col,n) <-> SoA: each n-slab is an independent 2-D transpose.  The
-// slab travels through one staging buffer; copy and transpose are stream-ordered,
-// so the buffer is safely reused by the next chunk.
+// BGC_MEM_HOST_FORTRAN calls are PCIe-bound (EC60to30: 11 GB up, 25 GB down per step against
+// 9 ms of kernels), so the transport is a two-slot pipeline over COLUMN CHUNKS: chunk i is
+// uploaded, transposed, computed, transposed back and downloaded on stream (i & 1) with its
+// own set of arena buffers, so the download of one chunk overlaps the upload and the kernels
+// of the next (PCIe is full duplex).  In the reference layout A(k,col,n) the columns
+// [c0, c0+cc) of slab n are one contiguous run of nL*cc doubles: a chunk of an array is one
+// 2-D copy (one row per slab), and on the device the chunk is simply a mesh of cc columns.
+struct HostChunk {
+  int nL, nC;      // the caller's extents (host pitch)
+  int c0, cc;      // first column and number of columns of this chunk
+  int slot;        // pipeline slot: selects the stream and the arena buffer set
+};
+
 static const int kStageSlabs = 4;
 
-static int stage_buf(bgc_ctx *c, size_t n2, double **out) { return arena_d(c, "stage", n2 * kStageSlabs, out); }
+static std::string slot_key(const HostChunk &h, const char *key) { return std::string(key) + (h.slot ? "#1" : "#0"); }
 
-static int up_k(bgc_ctx *c, const char *key, const double *host, int nL, int nC, int nSlabs, double **dev_out) {
-  const size_t n2 = (size_t)nL * nC;
+static int stage_buf(bgc_ctx *c, const HostChunk &h, double **out) {
+  return arena_d(c, slot_key(h, "stage"), (size_t)h.nL * h.cc * kStageSlabs, out);
+}
+
+// Upload the chunk of a (k,col,n) array and transpose it to SoA.  Slabs whose bit is set in
+// skip_mask are not transferred (inputs no kernel reads); their device slab keeps stale data.
+static int up_k(bgc_ctx *c, const HostChunk &h, const char *key, const double *host, int nSlabs, double **dev_out,
+                unsigned skip_mask = 0u) {
+  const size_t n2c = (size_t)h.nL * h.cc, n2 = (size_t)h.nL * h.nC;
   double *dev = nullptr, *stage = nullptr;
-  RC(arena_d(c, key, n2 * nSlabs, &dev));
+  RC(arena_d(c, slot_key(h, key), n2c * nSlabs, &dev));
   *dev_out = dev;
   if (!host) return fail(BGC_ERR_ARG, "null host array for %s", key);
-  RC(stage_buf(c, n2, &stage));
-  for (int s0 = 0; s0 < nSlabs; s0 += kStageSlabs) {
-    const int ns = (nSlabs - s0 < kStageSlabs) ? nSlabs - s0 : kStageSlabs;
-    CU(cudaMemcpyAsync(stage, host + (size_t)s0 * n2, (size_t)ns * n2 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    LAUNCH(BGC_K_TRANSPOSE, 1, bgc::launch_transpose(stage, dev + (size_t)s0 * n2, nL, nC, ns, c->stream));
+  RC(stage_buf(c, h, &stage));
+  for (int s0 = 0; s0 < nSlabs;) {
+    if (s0 < 32 && ((skip_mask >> s0) & 1u)) { ++s0; continue; }
+    int ns = 1;
+    while (ns < kStageSlabs && s0 + ns < nSlabs && !((s0 + ns) < 32 && ((skip_mask >> (s0 + ns)) & 1u))) ++ns;
+    CU(cudaMemcpy2DAsync(stage, n2c * sizeof(double), host + (size_t)s0 * n2 + (size_t)h.c0 * h.nL, n2 * sizeof(double),
+                         n2c * sizeof(double), (size_t)ns, cudaMemcpyHostToDevice, c->stream));
+    LAUNCH(BGC_K_TRANSPOSE, 1, bgc::launch_transpose(stage, dev + (size_t)s0 * n2c, h.nL, h.cc, ns, c->stream));
+    s0 += ns;
   }
   return BGC_OK;
 }
 
-static int down_k(bgc_ctx *c, const double *dev, double *host, int nL, int nC, int nSlabs) {
-  const size_t n2 = (size_t)nL * nC;
+static int down_k(bgc_ctx *c, const HostChunk &h, const double *dev, double *host, int nSlabs) {
+  const size_t n2c = (size_t)h.nL * h.cc, n2 = (size_t)h.nL * h.nC;
   double *stage = nullptr;
-  RC(stage_buf(c, n2, &stage));
+  RC(stage_buf(c, h, &stage));
   for (int s0 = 0; s0 < nSlabs; s0 += kStageSlabs) {
     const int ns = (nSlabs - s0 < kStageSlabs) ? nSlabs - s0 : kStageSlabs;
-    LAUNCH(BGC_K_TRANSPOSE, 1, bgc::launch_transpose(dev + (size_t)s0 * n2, stage, nC, nL, ns, c->stream));
-    CU(cudaMemcpyAsync(host + (size_t)s0 * n2, stage, (size_t)ns * n2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    LAUNCH(BGC_K_TRANSPOSE, 1, bgc::launch_transpose(dev + (size_t)s0 * n2c, stage, h.cc, h.nL, ns, c->stream));
+    CU(cudaMemcpy2DAsync(host + (size_t)s0 * n2 + (size_t)h.c0 * h.nL, n2 * sizeof(double), stage, n2c * sizeof(double),
+                         n2c * sizeof(double), (size_t)ns, cudaMemcpyDeviceToHost, c->stream));
   }
   return BGC_OK;
 }
 
-// (col[,n]) arrays have the same layout in both spaces
-static int up_c(bgc_ctx *c, const char *key, const void *host, size_t bytes, void **dev_out) {
+// (col[,n]) arrays have the same layout in both spaces; elem = bytes per element
+static int up_c(bgc_ctx *c, const HostChunk &h, const char *key, const void *host, size_t elem, int nSlabs, void **dev_out) {
   void *dev = nullptr;
-  RC(arena_get(c, key, bytes, &dev));
+  RC(arena_get(c, slot_key(h, key), (size_t)h.cc * elem * nSlabs, &dev));
   *dev_out = dev;
   if (!host) return fail(BGC_ERR_ARG, "null host array for %s", key);
-  CU(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpy2DAsync(dev, (size_t)h.cc * elem, (const char *)host + (size_t)h.c0 * elem, (size_t)h.nC * elem,
+                       (size_t)h.cc * elem, (size_t)nSlabs, cudaMemcpyHostToDevice, c->stream));
   return BGC_OK;
 }
-static int down_c(bgc_ctx *c, const void *dev, void *host, size_t bytes) {
-  CU(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, c->stream));
+static int down_c(bgc_ctx *c, const HostChunk &h, const void *dev, void *host, size_t elem, int nSlabs) {
+  CU(cudaMemcpy2DAsync((char *)host + (size_t)h.c0 * elem, (size_t)h.nC * elem, dev, (size_t)h.cc * elem,
+                       (size_t)h.cc * elem, (size_t)nSlabs, cudaMemcpyDeviceToHost, c->stream));
   return BGC_OK;
+}
+
+// Chunk plan: about 32 k columns per chunk (large enough for full-speed DMA and kernels, small
+// enough that several chunks overlap), a multiple of 32 columns so every device slab stays
+// 256-byte aligned; BGC_HOST_CHUNK_COLUMNS overrides it (tests use tiny chunks).
+static int chunk_columns(const bgc_ctx *c, int nC) {
+  int cc = c->host_chunk_columns > 0 ? c->host_chunk_columns : 32768;
+  if (c->host_chunk_columns <= 0 && nC <= 49152) return nC;   // small blocks: one chunk
+  cc = (cc + 31) / 32 * 32;
+  return cc < nC ? cc : nC;
+}
+
+// Run `body(chunk)` over all column chunks, alternating between the two pipeline slots.  The
+// second slot's stream first waits for whatever was queued on the ctx stream before the call.
+// The inventory fold accumulates into one device vector, so with the inventory on every chunk
+// goes through slot 0 (sequential, still chunked).
+template <class Body>
+static int host_pipeline(bgc_ctx *c, int nL, int nC, Body body) {
+  const int cc = chunk_columns(c, nC);
+  const int nchunks = (nC + cc - 1) / cc;
+  cudaStream_t user = c->stream;
+  const bool two = nchunks > 1 && !c->inventory_on;
+  if (two) {
+    CU(cudaEventRecord(c->pipe_event, user));
+    CU(cudaStreamWaitEvent(c->pipe_stream, c->pipe_event, 0));
+  }
+  int rc = BGC_OK;
+  for (int i = 0; i < nchunks && rc == BGC_OK; ++i) {
+    HostChunk h;
+    h.nL = nL; h.nC = nC; h.c0 = i * cc; h.cc = (nC - h.c0 < cc) ? nC - h.c0 : cc;
+    h.slot = two ? (i & 1) : 0;
+    c->stream = h.slot ? c->pipe_stream : user;
+    rc = body(h);
+  }
+  c->stream = user;
+  // Fortran semantics: results are in host memory on return
+  cudaError_t e1 = cudaStreamSynchronize(user), e2 = two ? cudaStreamSynchronize(c->pipe_stream) : cudaSuccess;
+  if (rc != BGC_OK) return rc;
+  if (e1 != cudaSuccess) return fail(BGC_ERR_CUDA, "%s", cudaGetErrorString(e1));
+  if (e2 != cudaSuccess) return fail(BGC_ERR_CUDA, "%s", cudaGetErrorString(e2));
+  return BGC_OK;
+}
+
+// true when every column of the chunk is active over all levels: then every element of a
+// (k,col) output is overwritten and the caller's previous contents need not be uploaded
+static bool chunk_fully_active(const HostChunk &h, const int *kmax, int nCols) {
+  if (h.c0 + h.cc > nCols) return false;
+  for (int i = 0; i < h.cc; ++i) if (kmax[h.c0 + i] < h.nL) return false;
+  return true;
 }
 
 static int check_dims(bgc_ctx *c, int nL, int nC, int nCols) {
@@ -617,62 +698,69 @@ extern "C" int bgc_source_sink(bgc_ctx *c, const BgcInput *in, const BgcForcing 
   if (mem_space != BGC_MEM_HOST_FORTRAN) return fail(BGC_ERR_ARG, "unknown mem_space %d", mem_space);
   if (!c->have_bgc) return fail(BGC_ERR_PARAMS, "bgc_set_params has not been called on this ctx");
 
-  const size_t n2 = (size_t)nL * nC;
-  BgcInput din; BgcForcing dfo; BgcOutput dout; BgcDiagnostics dd;
-  memset(&din, 0, sizeof din); memset(&dfo, 0, sizeof dfo); memset(&dout, 0, sizeof dout); memset(&dd, 0, sizeof dd);
-  double *t = nullptr; void *v = nullptr;
-  RC(up_k(c, "bgc.tracers", in->BGC_tracers, nL, nC, BGC_TRACER_CNT, &t)); din.BGC_tracers = t;
-  RC(up_k(c, "bgc.T", in->PotentialTemperature, nL, nC, 1, &t)); din.PotentialTemperature = t;
-  RC(up_k(c, "bgc.S", in->Salinity, nL, nC, 1, &t)); din.Salinity = t;
-  RC(up_k(c, "bgc.zmid", in->cell_center_depth, nL, nC, 1, &t)); din.cell_center_depth = t;
-  RC(up_k(c, "bgc.dz", in->cell_thickness, nL, nC, 1, &t)); din.cell_thickness = t;
-  RC(up_k(c, "bgc.zbot", in->cell_bottom_depth, nL, nC, 1, &t)); din.cell_bottom_depth = t;
-  RC(up_c(c, "bgc.lat", in->cell_latitude, (size_t)nC * sizeof(double), &v)); din.cell_latitude = (double *)v;
-  RC(up_c(c, "bgc.kmax", in->number_of_active_levels, (size_t)nC * sizeof(int), &v)); din.number_of_active_levels = (int *)v;
-  RC(up_k(c, "bgc.fesed", fo->FESEDFLUX, nL, nC, 1, &t)); dfo.FESEDFLUX = t;
+  RC(ensure_bgc_tables(c));
   const BgcParams &P = c->bgc_tab.p;
-  if (P.lrest_no3 || P.lrest_po4 || P.lrest_sio3) { RC(up_k(c, "bgc.rtau", fo->NUTR_RESTORE_RTAU, nL, nC, 1, &t)); dfo.NUTR_RESTORE_RTAU = t; }
-  if (P.lrest_no3) { RC(up_k(c, "bgc.no3clim", fo->NO3_CLIM, nL, nC, 1, &t)); dfo.NO3_CLIM = t; }
-  if (P.lrest_po4) { RC(up_k(c, "bgc.po4clim", fo->PO4_CLIM, nL, nC, 1, &t)); dfo.PO4_CLIM = t; }
-  if (P.lrest_sio3) { RC(up_k(c, "bgc.sio3clim", fo->SiO3_CLIM, nL, nC, 1, &t)); dfo.SiO3_CLIM = t; }
-  RC(up_c(c, "bgc.dust", fo->dust_FLUX_IN, (size_t)nC * sizeof(double), &v)); dfo.dust_FLUX_IN = (double *)v;
-  RC(up_c(c, "bgc.sw", fo->ShortWaveFlux_surface, (size_t)nC * sizeof(double), &v)); dfo.ShortWaveFlux_surface = (double *)v;
-  RC(up_k(c, "bgc.phprev", out->PH_PREV_3D, nL, nC, 1, &t)); dout.PH_PREV_3D = t;
-  RC(up_k(c, "bgc.phprevalt", out->PH_PREV_ALT_CO2_3D, nL, nC, 1, &t)); dout.PH_PREV_ALT_CO2_3D = t;
-  RC(arena_d(c, "bgc.tend", n2 * BGC_TRACER_CNT, &dout.BGC_tendencies));
+  // DIC_ALT_CO2 is clamped and then never read by BGC_SourceSink (BGC_mod.F90:748): not uploaded
+  const unsigned dead_slabs = 1u << (c->bgc_tab.ind.dic_alt_co2_ind - 1);
+  return host_pipeline(c, nL, nC, [&](const HostChunk &h) -> int {
+    const size_t n2 = (size_t)h.nL * h.cc;
+    int cols = nCols - h.c0;
+    if (cols < 0) cols = 0;
+    if (cols > h.cc) cols = h.cc;
+    BgcInput din; BgcForcing dfo; BgcOutput dout; BgcDiagnostics dd;
+    memset(&din, 0, sizeof din); memset(&dfo, 0, sizeof dfo); memset(&dout, 0, sizeof dout); memset(&dd, 0, sizeof dd);
+    double *t = nullptr; void *v = nullptr;
+    RC(up_k(c, h, "bgc.tracers", in->BGC_tracers, BGC_TRACER_CNT, &t, dead_slabs)); din.BGC_tracers = t;
+    RC(up_k(c, h, "bgc.T", in->PotentialTemperature, 1, &t)); din.PotentialTemperature = t;
+    RC(up_k(c, h, "bgc.S", in->Salinity, 1, &t)); din.Salinity = t;
+    RC(up_k(c, h, "bgc.zmid", in->cell_center_depth, 1, &t)); din.cell_center_depth = t;
+    RC(up_k(c, h, "bgc.dz", in->cell_thickness, 1, &t)); din.cell_thickness = t;
+    RC(up_k(c, h, "bgc.zbot", in->cell_bottom_depth, 1, &t)); din.cell_bottom_depth = t;
+    RC(up_c(c, h, "bgc.lat", in->cell_latitude, sizeof(double), 1, &v)); din.cell_latitude = (double *)v;
+    RC(up_c(c, h, "bgc.kmax", in->number_of_active_levels, sizeof(int), 1, &v)); din.number_of_active_levels = (int *)v;
+    RC(up_k(c, h, "bgc.fesed", fo->FESEDFLUX, 1, &t)); dfo.FESEDFLUX = t;
+    if (P.lrest_no3 || P.lrest_po4 || P.lrest_sio3) { RC(up_k(c, h, "bgc.rtau", fo->NUTR_RESTORE_RTAU, 1, &t)); dfo.NUTR_RESTORE_RTAU = t; }
+    if (P.lrest_no3) { RC(up_k(c, h, "bgc.no3clim", fo->NO3_CLIM, 1, &t)); dfo.NO3_CLIM = t; }
+    if (P.lrest_po4) { RC(up_k(c, h, "bgc.po4clim", fo->PO4_CLIM, 1, &t)); dfo.PO4_CLIM = t; }
+    if (P.lrest_sio3) { RC(up_k(c, h, "bgc.sio3clim", fo->SiO3_CLIM, 1, &t)); dfo.SiO3_CLIM = t; }
+    RC(up_c(c, h, "bgc.dust", fo->dust_FLUX_IN, sizeof(double), 1, &v)); dfo.dust_FLUX_IN = (double *)v;
+    RC(up_c(c, h, "bgc.sw", fo->ShortWaveFlux_surface, sizeof(double), 1, &v)); dfo.ShortWaveFlux_surface = (double *)v;
+    RC(up_k(c, h, "bgc.phprev", out->PH_PREV_3D, 1, &t)); dout.PH_PREV_3D = t;
+    RC(up_k(c, h, "bgc.phprevalt", out->PH_PREV_ALT_CO2_3D, 1, &t)); dout.PH_PREV_ALT_CO2_3D = t;
+    RC(arena_d(c, slot_key(h, "bgc.tend"), n2 * BGC_TRACER_CNT, &dout.BGC_tendencies));
 
-  if (diag) {
-#define DEV_K2(name) if (diag->name) RC(arena_d(c, "bgc.d." #name, n2, &dd.name));
-#define DEV_KA(name) if (diag->name) RC(arena_d(c, "bgc.d." #name, n2 * BGC_AUTOTROPH_CNT, &dd.name));
-#define DEV_CA(name) if (diag->name) RC(arena_d(c, "bgc.d." #name, (size_t)nC * BGC_AUTOTROPH_CNT, &dd.name));
-#define DEV_C1(name) if (diag->name) RC(arena_d(c, "bgc.d." #name, (size_t)nC, &dd.name));
-    BGC_DIAG_K2_LIST(DEV_K2) BGC_DIAG_KA_LIST(DEV_KA) BGC_DIAG_CA_LIST(DEV_CA) BGC_DIAG_C1_LIST(DEV_C1)
+    if (diag) {
+#define DEV_K2(name) if (diag->name) RC(arena_d(c, slot_key(h, "bgc.d." #name), n2, &dd.name));
+#define DEV_KA(name) if (diag->name) RC(arena_d(c, slot_key(h, "bgc.d." #name), n2 * BGC_AUTOTROPH_CNT, &dd.name));
+#define DEV_CA(name) if (diag->name) RC(arena_d(c, slot_key(h, "bgc.d." #name), (size_t)h.cc * BGC_AUTOTROPH_CNT, &dd.name));
+#define DEV_C1(name) if (diag->name) RC(arena_d(c, slot_key(h, "bgc.d." #name), (size_t)h.cc, &dd.name));
+      BGC_DIAG_K2_LIST(DEV_K2) BGC_DIAG_KA_LIST(DEV_KA) BGC_DIAG_CA_LIST(DEV_CA) BGC_DIAG_C1_LIST(DEV_C1)
 #undef DEV_K2
 #undef DEV_KA
 #undef DEV_CA
 #undef DEV_C1
-  }
+    }
 
-  RC(source_sink_device(c, &din, &dfo, &dout, diag ? &dd : nullptr, nL, nC, nCols, alt_co2_use_eco));
+    RC(source_sink_device(c, &din, &dfo, &dout, diag ? &dd : nullptr, h.nL, h.cc, cols, alt_co2_use_eco));
 
-  RC(down_k(c, dout.BGC_tendencies, out->BGC_tendencies, nL, nC, BGC_TRACER_CNT));
-  RC(down_k(c, dout.PH_PREV_3D, out->PH_PREV_3D, nL, nC, 1));
-  RC(down_k(c, dout.PH_PREV_ALT_CO2_3D, out->PH_PREV_ALT_CO2_3D, nL, nC, 1));
-  if (diag) {
-    // the three never-touched arrays stay exactly as the caller left them
-    dd.diag_POC_ACCUM = dd.diag_DONr_remin = dd.diag_DOPr_remin = nullptr;
-#define DN_K2(name) if (dd.name) RC(down_k(c, dd.name, diag->name, nL, nC, 1));
-#define DN_KA(name) if (dd.name) RC(down_k(c, dd.name, diag->name, nL, nC, BGC_AUTOTROPH_CNT));
-#define DN_CA(name) if (dd.name) RC(down_c(c, dd.name, diag->name, (size_t)nC * BGC_AUTOTROPH_CNT * sizeof(double)));
-#define DN_C1(name) if (dd.name) RC(down_c(c, dd.name, diag->name, (size_t)nC * sizeof(double)));
-    BGC_DIAG_K2_LIST(DN_K2) BGC_DIAG_KA_LIST(DN_KA) BGC_DIAG_CA_LIST(DN_CA) BGC_DIAG_C1_LIST(DN_C1)
+    RC(down_k(c, h, dout.BGC_tendencies, out->BGC_tendencies, BGC_TRACER_CNT));
+    RC(down_k(c, h, dout.PH_PREV_3D, out->PH_PREV_3D, 1));
+    RC(down_k(c, h, dout.PH_PREV_ALT_CO2_3D, out->PH_PREV_ALT_CO2_3D, 1));
+    if (diag) {
+      // the three never-touched arrays stay exactly as the caller left them
+      dd.diag_POC_ACCUM = dd.diag_DONr_remin = dd.diag_DOPr_remin = nullptr;
+#define DN_K2(name) if (dd.name) RC(down_k(c, h, dd.name, diag->name, 1));
+#define DN_KA(name) if (dd.name) RC(down_k(c, h, dd.name, diag->name, BGC_AUTOTROPH_CNT));
+#define DN_CA(name) if (dd.name) RC(down_c(c, h, dd.name, diag->name, sizeof(double), BGC_AUTOTROPH_CNT));
+#define DN_C1(name) if (dd.name) RC(down_c(c, h, dd.name, diag->name, sizeof(double), 1));
+      BGC_DIAG_K2_LIST(DN_K2) BGC_DIAG_KA_LIST(DN_KA) BGC_DIAG_CA_LIST(DN_CA) BGC_DIAG_C1_LIST(DN_C1)
 #undef DN_K2
 #undef DN_KA
 #undef DN_CA
 #undef DN_C1
-  }
-  CU(cudaStreamSynchronize(c->stream));   // Fortran semantics: results are in host memory on return
-  return BGC_OK;
+    }
+    return BGC_OK;
+  });
 }
 
 // ------------------------------------------------------------------ BGC_SurfaceFluxes
@@ -703,8 +791,9 @@ extern "C" int bgc_surface_fluxes(bgc_ctx *c, const BgcInput *in, BgcForcing *fo
   if (mem_space != BGC_MEM_HOST_FORTRAN) return fail(BGC_ERR_ARG, "unknown mem_space %d", mem_space);
   if (!c->have_bgc) return fail(BGC_ERR_PARAMS, "bgc_set_params has not been called on this ctx");
 
-  // Only level 1 of the tracer array is read: upload that single level per tracer.
-  const size_t colb = (size_t)nC * sizeof(double);
+  // Only level 1 of the tracer array is read: upload that single level per tracer.  Per-column
+  // data only (a few hundred MB at most): one chunk.
+  HostChunk h; h.nL = nL; h.nC = nC; h.c0 = 0; h.cc = nC; h.slot = 0;
   BgcInput din; BgcForcing dfo; BgcFluxDiagnostics dd;
   memset(&din, 0, sizeof din); memset(&dd, 0, sizeof dd);
   dfo = *fo;
@@ -716,7 +805,7 @@ extern "C" int bgc_surface_fluxes(bgc_ctx *c, const BgcInput *in, BgcForcing *fo
                        (size_t)nC * BGC_TRACER_CNT, cudaMemcpyHostToDevice, c->stream));
   din.BGC_tracers = surf;
   void *v = nullptr;
-#define UPC(member, n) do { if (fo->member) { RC(up_c(c, "surf." #member, fo->member, colb * (n), &v)); dfo.member = (double *)v; } } while (0)
+#define UPC(member, n) do { if (fo->member) { RC(up_c(c, h, "surf." #member, fo->member, sizeof(double), (n), &v)); dfo.member = (double *)v; } } while (0)
   UPC(surfacePressure, 1); UPC(iceFraction, 1); UPC(windSpeedSquared10m, 1); UPC(atmCO2, 1); UPC(atmCO2_ALT_CO2, 1);
   UPC(surface_pH, 1); UPC(surface_pH_alt_co2, 1); UPC(surfaceDepth, 1); UPC(SST, 1); UPC(SSS, 1);
   UPC(depositionFlux, BGC_TRACER_CNT); UPC(riverFlux, BGC_TRACER_CNT); UPC(gasFlux, BGC_TRACER_CNT);
@@ -729,13 +818,13 @@ extern "C" int bgc_surface_fluxes(bgc_ctx *c, const BgcInput *in, BgcForcing *fo
   }
   // device tracer "array" holds level 1 only: nL = 1 on the device side
   RC(surface_fluxes_device(c, &din, &dfo, diag ? &dd : nullptr, 1, nC, nCols));
-#define DNC(member, n) do { if (fo->member) RC(down_c(c, dfo.member, fo->member, colb * (n))); } while (0)
+#define DNC(member, n) do { if (fo->member) RC(down_c(c, h, dfo.member, fo->member, sizeof(double), (n))); } while (0)
   DNC(iceFraction, 1); DNC(surface_pH, 1); DNC(surface_pH_alt_co2, 1);
   DNC(depositionFlux, BGC_TRACER_CNT); DNC(riverFlux, BGC_TRACER_CNT); DNC(gasFlux, BGC_TRACER_CNT);
   DNC(seaIceFlux, BGC_TRACER_CNT); DNC(netFlux, BGC_TRACER_CNT);
 #undef DNC
   if (diag) {
-#define DN_F(name) if (dd.name) RC(down_c(c, dd.name, diag->name, colb));
+#define DN_F(name) if (dd.name) RC(down_c(c, h, dd.name, diag->name, sizeof(double), 1));
     BGC_FLUX_DIAG_LIST(DN_F)
 #undef DN_F
   }
@@ -817,32 +906,43 @@ extern "C" int dms_source_sink(bgc_ctx *c, const DmsInput *in, const DmsForcing 
   RC(check_dims(c, nL, nC, nCols));
   if (mem_space == BGC_MEM_DEVICE_SOA) return dms_source_sink_device(c, in, fo, out, diag, nL, nC, nCols);
   if (mem_space != BGC_MEM_HOST_FORTRAN) return fail(BGC_ERR_ARG, "unknown mem_space %d", mem_space);
-  const size_t n2 = (size_t)nL * nC;
-  DmsInput din; DmsForcing dfo; DmsOutput dout; DmsDiagnostics dd;
-  memset(&din, 0, sizeof din); memset(&dfo, 0, sizeof dfo); memset(&dout, 0, sizeof dout); memset(&dd, 0, sizeof dd);
-  double *t = nullptr; void *v = nullptr;
-  RC(up_k(c, "dms.tracers", in->DMS_tracers, nL, nC, DMS_TRACER_CNT, &t)); din.DMS_tracers = t;
-  RC(up_k(c, "dms.dz", in->cell_thickness, nL, nC, 1, &t)); din.cell_thickness = t;
-  RC(up_c(c, "dms.kmax", in->number_of_active_levels, (size_t)nC * sizeof(int), &v)); din.number_of_active_levels = (int *)v;
-  RC(up_c(c, "dms.sst", fo->SST, (size_t)nC * sizeof(double), &v)); dfo.SST = (double *)v;
-  RC(up_c(c, "dms.sw", fo->ShortWaveFlux_surface, (size_t)nC * sizeof(double), &v)); dfo.ShortWaveFlux_surface = (double *)v;
-  RC(arena_d(c, "dms.tend", n2 * DMS_TRACER_CNT, &dout.DMS_tendencies));
-  if (diag) {
-    // DMS diagnostics are NOT zeroed by the reference: inactive cells keep the
-    // caller's values, so the caller's arrays are uploaded before the kernel runs.
-#define UP_D(name) if (diag->name) { RC(up_k(c, "dms.d." #name, diag->name, nL, nC, 1, &t)); dd.name = t; }
-    DMS_DIAG_LIST(UP_D)
+  if (!in->number_of_active_levels) return fail(BGC_ERR_ARG, "dms_source_sink: number_of_active_levels is NULL");
+  RC(ensure_dms_tables(c));
+  // NO3 and DOC are copied by the reference and never reach an output (DMS_mod.F90:471-472): not uploaded
+  const unsigned dead_slabs = (1u << (c->dms_tab.ind.no3_ind - 1)) | (1u << (c->dms_tab.ind.doc_ind - 1));
+  return host_pipeline(c, nL, nC, [&](const HostChunk &h) -> int {
+    const size_t n2 = (size_t)h.nL * h.cc;
+    int cols = nCols - h.c0;
+    if (cols < 0) cols = 0;
+    if (cols > h.cc) cols = h.cc;
+    DmsInput din; DmsForcing dfo; DmsOutput dout; DmsDiagnostics dd;
+    memset(&din, 0, sizeof din); memset(&dfo, 0, sizeof dfo); memset(&dout, 0, sizeof dout); memset(&dd, 0, sizeof dd);
+    double *t = nullptr; void *v = nullptr;
+    RC(up_k(c, h, "dms.tracers", in->DMS_tracers, DMS_TRACER_CNT, &t, dead_slabs)); din.DMS_tracers = t;
+    RC(up_k(c, h, "dms.dz", in->cell_thickness, 1, &t)); din.cell_thickness = t;
+    RC(up_c(c, h, "dms.kmax", in->number_of_active_levels, sizeof(int), 1, &v)); din.number_of_active_levels = (int *)v;
+    RC(up_c(c, h, "dms.sst", fo->SST, sizeof(double), 1, &v)); dfo.SST = (double *)v;
+    RC(up_c(c, h, "dms.sw", fo->ShortWaveFlux_surface, sizeof(double), 1, &v)); dfo.ShortWaveFlux_surface = (double *)v;
+    RC(arena_d(c, slot_key(h, "dms.tend"), n2 * DMS_TRACER_CNT, &dout.DMS_tendencies));
+    if (diag) {
+      // DMS diagnostics are NOT zeroed by the reference: inactive cells keep the caller's
+      // values, so the caller's arrays are uploaded first - unless every cell of the chunk is
+      // active, in which case every element is overwritten anyway.
+      const bool keep = !chunk_fully_active(h, in->number_of_active_levels, nCols);
+#define UP_D(name) if (diag->name) { if (keep) { RC(up_k(c, h, "dms.d." #name, diag->name, 1, &t)); } \
+                                     else { RC(arena_d(c, slot_key(h, "dms.d." #name), n2, &t)); } dd.name = t; }
+      DMS_DIAG_LIST(UP_D)
 #undef UP_D
-  }
-  RC(dms_source_sink_device(c, &din, &dfo, &dout, diag ? &dd : nullptr, nL, nC, nCols));
-  RC(down_k(c, dout.DMS_tendencies, out->DMS_tendencies, nL, nC, DMS_TRACER_CNT));
-  if (diag) {
-#define DN_D(name) if (dd.name) RC(down_k(c, dd.name, diag->name, nL, nC, 1));
-    DMS_DIAG_LIST(DN_D)
+    }
+    RC(dms_source_sink_device(c, &din, &dfo, &dout, diag ? &dd : nullptr, h.nL, h.cc, cols));
+    RC(down_k(c, h, dout.DMS_tendencies, out->DMS_tendencies, DMS_TRACER_CNT));
+    if (diag) {
+#define DN_D(name) if (dd.name) RC(down_k(c, h, dd.name, diag->name, 1));
+      DMS_DIAG_LIST(DN_D)
 #undef DN_D
-  }
-  CU(cudaStreamSynchronize(c->stream));
-  return BGC_OK;
+    }
+    return BGC_OK;
+  });
 }
 
 static int dms_surface_device(bgc_ctx *c, const DmsInput *in, DmsForcing *fo, DmsFluxDiagnostics *diag, int nL,
@@ -867,7 +967,7 @@ extern "C" int dms_surface_fluxes(bgc_ctx *c, const DmsInput *in, DmsForcing *fo
   if (mem_space == BGC_MEM_DEVICE_SOA) return dms_surface_device(c, in, fo, diag, nL, nC, nCols);
   if (mem_space != BGC_MEM_HOST_FORTRAN) return fail(BGC_ERR_ARG, "unknown mem_space %d", mem_space);
   if (!fo->lcalc_DMS_gas_flux) return BGC_OK;
-  const size_t colb = (size_t)nC * sizeof(double);
+  HostChunk h; h.nL = nL; h.nC = nC; h.c0 = 0; h.cc = nC; h.slot = 0;   // per-column data only: one chunk
   DmsInput din; DmsForcing dfo = *fo; DmsFluxDiagnostics dd;
   memset(&din, 0, sizeof din); memset(&dd, 0, sizeof dd);
   if (!in->DMS_tracers) return fail(BGC_ERR_ARG, "dms_surface_fluxes: DMS_tracers is NULL");
@@ -877,21 +977,21 @@ extern "C" int dms_surface_fluxes(bgc_ctx *c, const DmsInput *in, DmsForcing *fo
                        (size_t)nC * DMS_TRACER_CNT, cudaMemcpyHostToDevice, c->stream));
   din.DMS_tracers = surf;
   void *v = nullptr;
-#define UPC(member, n) do { if (fo->member) { RC(up_c(c, "dmssurf." #member, fo->member, colb * (n), &v)); dfo.member = (double *)v; } } while (0)
+#define UPC(member, n) do { if (fo->member) { RC(up_c(c, h, "dmssurf." #member, fo->member, sizeof(double), (n), &v)); dfo.member = (double *)v; } } while (0)
   UPC(surfacePressure, 1); UPC(iceFraction, 1); UPC(windSpeedSquared10m, 1); UPC(SST, 1); UPC(SSS, 1);
   UPC(netFlux, DMS_TRACER_CNT);
 #undef UPC
   if (diag) {
     // not zeroed by the reference: columns beyond numColumns keep the caller's values
-#define UP_F(name) if (diag->name) { RC(up_c(c, "dmssurf.d." #name, diag->name, colb, &v)); dd.name = (double *)v; }
+#define UP_F(name) if (diag->name) { RC(up_c(c, h, "dmssurf.d." #name, diag->name, sizeof(double), 1, &v)); dd.name = (double *)v; }
     DMS_FLUX_DIAG_LIST(UP_F)
 #undef UP_F
   }
   RC(dms_surface_device(c, &din, &dfo, diag ? &dd : nullptr, 1, nC, nCols));
-  RC(down_c(c, dfo.iceFraction, fo->iceFraction, colb));
-  RC(down_c(c, dfo.netFlux, fo->netFlux, colb * DMS_TRACER_CNT));
+  RC(down_c(c, h, dfo.iceFraction, fo->iceFraction, sizeof(double), 1));
+  RC(down_c(c, h, dfo.netFlux, fo->netFlux, sizeof(double), DMS_TRACER_CNT));
   if (diag) {
-#define DN_F(name) if (dd.name) RC(down_c(c, dd.name, diag->name, colb));
+#define DN_F(name) if (dd.name) RC(down_c(c, h, dd.name, diag->name, sizeof(double), 1));
     DMS_FLUX_DIAG_LIST(DN_F)
 #undef DN_F
   }
@@ -932,28 +1032,36 @@ extern "C" int macros_source_sink(bgc_ctx *c, const MacrosInput *in, MacrosOutpu
   RC(check_dims(c, nL, nC, nCols));
   if (mem_space == BGC_MEM_DEVICE_SOA) return macros_device(c, in, out, diag, nL, nC, nCols);
   if (mem_space != BGC_MEM_HOST_FORTRAN) return fail(BGC_ERR_ARG, "unknown mem_space %d", mem_space);
-  const size_t n2 = (size_t)nL * nC;
-  MacrosInput din; MacrosOutput dout; MacrosDiagnostics dd;
-  memset(&din, 0, sizeof din); memset(&dout, 0, sizeof dout); memset(&dd, 0, sizeof dd);
-  double *t = nullptr; void *v = nullptr;
-  RC(up_k(c, "mac.tracers", in->MACROS_tracers, nL, nC, MACROS_TRACER_CNT, &t)); din.MACROS_tracers = t;
-  if (c->inventory_on && in->cell_thickness) { RC(up_k(c, "mac.dz", in->cell_thickness, nL, nC, 1, &t)); din.cell_thickness = t; }
-  RC(up_c(c, "mac.kmax", in->number_of_active_levels, (size_t)nC * sizeof(int), &v)); din.number_of_active_levels = (int *)v;
-  RC(arena_d(c, "mac.tend", n2 * MACROS_TRACER_CNT, &dout.MACROS_tendencies));
-  if (diag) {
-#define UP_D(name) if (diag->name) { RC(up_k(c, "mac.d." #name, diag->name, nL, nC, 1, &t)); dd.name = t; }
-    MACROS_DIAG_LIST(UP_D)
+  if (!in->number_of_active_levels) return fail(BGC_ERR_ARG, "macros_source_sink: number_of_active_levels is NULL");
+  RC(ensure_macros_tables(c));
+  return host_pipeline(c, nL, nC, [&](const HostChunk &h) -> int {
+    const size_t n2 = (size_t)h.nL * h.cc;
+    int cols = nCols - h.c0;
+    if (cols < 0) cols = 0;
+    if (cols > h.cc) cols = h.cc;
+    MacrosInput din; MacrosOutput dout; MacrosDiagnostics dd;
+    memset(&din, 0, sizeof din); memset(&dout, 0, sizeof dout); memset(&dd, 0, sizeof dd);
+    double *t = nullptr; void *v = nullptr;
+    RC(up_k(c, h, "mac.tracers", in->MACROS_tracers, MACROS_TRACER_CNT, &t)); din.MACROS_tracers = t;
+    if (c->inventory_on && in->cell_thickness) { RC(up_k(c, h, "mac.dz", in->cell_thickness, 1, &t)); din.cell_thickness = t; }
+    RC(up_c(c, h, "mac.kmax", in->number_of_active_levels, sizeof(int), 1, &v)); din.number_of_active_levels = (int *)v;
+    RC(arena_d(c, slot_key(h, "mac.tend"), n2 * MACROS_TRACER_CNT, &dout.MACROS_tendencies));
+    if (diag) {   // not zeroed by the reference either: see dms_source_sink
+      const bool keep = !chunk_fully_active(h, in->number_of_active_levels, nCols);
+#define UP_D(name) if (diag->name) { if (keep) { RC(up_k(c, h, "mac.d." #name, diag->name, 1, &t)); } \
+                                     else { RC(arena_d(c, slot_key(h, "mac.d." #name), n2, &t)); } dd.name = t; }
+      MACROS_DIAG_LIST(UP_D)
 #undef UP_D
-  }
-  RC(macros_device(c, &din, &dout, diag ? &dd : nullptr, nL, nC, nCols));
-  RC(down_k(c, dout.MACROS_tendencies, out->MACROS_tendencies, nL, nC, MACROS_TRACER_CNT));
-  if (diag) {
-#define DN_D(name) if (dd.name) RC(down_k(c, dd.name, diag->name, nL, nC, 1));
-    MACROS_DIAG_LIST(DN_D)
+    }
+    RC(macros_device(c, &din, &dout, diag ? &dd : nullptr, h.nL, h.cc, cols));
+    RC(down_k(c, h, dout.MACROS_tendencies, out->MACROS_tendencies, MACROS_TRACER_CNT));
+    if (diag) {
+#define DN_D(name) if (dd.name) RC(down_k(c, h, dd.name, diag->name, 1));
+      MACROS_DIAG_LIST(DN_D)
 #undef DN_D
-  }
-  CU(cudaStreamSynchronize(c->stream));
-  return BGC_OK;
+    }
+    return BGC_OK;
+  });
 }
 
 // ------------------------------------------------------------------ multi-GPU

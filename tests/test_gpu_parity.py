@@ -268,6 +268,42 @@ def test_dms_and_macros(o, device_mode):
     ctx.close()
 
 
+@pytest.mark.parametrize("ragged", [True, False])
+def test_host_layout_pipeline_in_column_chunks(o, ragged, monkeypatch):
+    """BGC_MEM_HOST_FORTRAN calls run as a two-slot pipeline over column chunks (bgc_capi.cu:
+    host_pipeline).  Force tiny chunks so that several chunks, a partial last chunk, both
+    slots and both diagnostic-upload modes (chunk fully active or not) are exercised."""
+    monkeypatch.setenv("BGC_HOST_CHUNK_COLUMNS", "64")
+    nL, nC = 40, 232
+    nCols = 227 if ragged else nC
+    ctx, parms = _ctx(nL, nC)
+    po = o.Parms()
+    cols, dms, mac = parity.make_bgc(nL, nC, parms, nColumns=nCols, ragged=ragged, with_dms=True, with_macros=True)
+    parity.poison_outputs(cols)
+    for d in (dms.diag, mac.diag):
+        for a in d.values():
+            a[...] = -777.0          # DMS / MACROS diagnostics keep the caller's values off active cells
+    ref, dref, mref = cols.copy(), dms.copy(), mac.copy()
+    o.BGC_SourceSink(po, ref, True, nthreads=o.max_threads())
+    o.DMS_SourceSink(po, dref, nthreads=o.max_threads())
+    o.MACROS_SourceSink(po, mref, nthreads=o.max_threads())
+    got = parity.run_gpu_bgc(ctx, cols, device_mode=False)
+    parity.compare_bgc_source_sink(ref, got)
+    dgot, mgot = dms.copy(), mac.copy()
+    host.DMS_SourceSink(ctx, dgot)
+    host.MACROS_SourceSink(ctx, mgot)
+    for n in range(abi.DMS_TRACER_CNT):
+        assert parity.nerr(dgot.DMS_tendencies[:, :, n], dref.DMS_tendencies[:, :, n]) <= parity.TOL_TEND, n
+    for n in range(abi.MACROS_TRACER_CNT):
+        assert parity.nerr(mgot.MACROS_tendencies[:, :, n], mref.MACROS_tendencies[:, :, n]) <= parity.TOL_TEND, n
+    act = _active(dms)
+    parity.compare_fields(dref.diag, dgot.diag, parity.TOL_TEND, "DMS diagnostics", mask=act)
+    parity.compare_fields(mref.diag, mgot.diag, parity.TOL_TEND, "MACROS diagnostics", mask=act)
+    for nm, a in list(dgot.diag.items()) + list(mgot.diag.items()):
+        assert np.all(a[~act] == -777.0), nm
+    ctx.close()
+
+
 # ------------------------------------------------------------------ inventory
 def test_inventory_vector_matches_the_outputs():
     nL, nC, nCols = 36, 514, 500
