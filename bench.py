@@ -180,7 +180,9 @@ def workload_config(args, world):
             "sharding": "contiguous column slabs, one process per GPU, no halo",
             "cache": "inputs+outputs per step (%.1f GB per GPU) far exceed the 126 MB L2; no flush needed"
                      % (args.columns * args.levels * B_API / 1e9),
-            "ph_brackets": "warm (PH_PREV from the untimed cold pass), as in a running model"}
+            "ph_brackets": "warm (PH_PREV from the untimed cold pass), as in a running model",
+            "carbonate_join": "strict (inside BGC_SourceSink)" if getattr(args, "strict_join", False)
+                              else "deferred to the end of the step (bgc_ctx_set_deferred_join)"}
 
 
 # ------------------------------------------------------------------ device-resident arm
@@ -274,6 +276,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-inventory", action="store_true")
+    ap.add_argument("--strict-join", action="store_true",
+                    help="join the carbonate side stream inside every BGC_SourceSink call (library default)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3   # timing rule: at least 3 warm-up steps
@@ -303,6 +307,9 @@ def main():
         dist.broadcast_object_list(uid, src=0)
         ctx.comm_init_rank(world, rank, uid[0])
     ctx.inventory_enable(not args.no_inventory)
+    # the carbonate solve of BGC_SourceSink overlaps the DMS / MACROS / surface-flux kernels that
+    # follow it; it is joined at the step's inventory all-reduce (or the explicit join below)
+    ctx.set_deferred_join(not args.strict_join)
 
     bgc = host.DeviceBgcColumns(nL, nC, device=dev)
     dms = host.DeviceDmsColumns(nL, nC, device=dev)
@@ -319,7 +326,8 @@ def main():
         host.DMS_SurfaceFluxes(ctx, dms)
         host.MACROS_SourceSink(ctx, mac, True)
         if not args.no_inventory:
-            return ctx.inventory_allreduce()   # NCCL all-reduce (N > 1) + 512 B to the host
+            return ctx.inventory_allreduce()   # join point; NCCL all-reduce (N > 1) + 512 B to the host
+        ctx.carbonate_join()
         return None
 
     def barrier():

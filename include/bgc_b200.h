@@ -291,6 +291,17 @@ int bgc_ctx_create(int device, int nLevelsMax, int nColumnsMax, bgc_ctx **out);
 int bgc_ctx_destroy(bgc_ctx *ctx);
 int bgc_ctx_set_stream(bgc_ctx *ctx, void *cuda_stream);   /* cudaStream_t; NULL = ctx-owned stream */
 int bgc_ctx_synchronize(bgc_ctx *ctx);
+/* bgc_source_sink (BGC_MEM_DEVICE_SOA) runs the carbonate kernel on an internal side stream
+ * beside the column sweep and, by default, joins it to the ctx stream before returning, so
+ * the call is stream-ordered as a whole.  With the deferred join enabled the join moves to
+ * the next JOIN POINT: bgc_carbonate_join (stream-ordered, no host wait), bgc_ctx_synchronize,
+ * bgc_get_status, bgc_inventory_get / bgc_inventory_allreduce, bgc_ctx_set_stream, the next
+ * bgc_source_sink or any BGC_MEM_HOST_FORTRAN call.  Until then the caller must neither
+ * overwrite the inputs of that bgc_source_sink call nor read PH_PREV_*, the ten carbonate
+ * diagnostics and diag_zsatcalc / diag_zsatarag on the ctx stream; in exchange the FP64-bound
+ * carbonate solve overlaps the HBM-bound DMS / MACROS / surface-flux kernels that follow. */
+int bgc_ctx_set_deferred_join(bgc_ctx *ctx, int enable);
+int bgc_carbonate_join(bgc_ctx *ctx);
 int bgc_get_status(bgc_ctx *ctx, BgcStatus *out, int reset);
 
 int bgc_set_params(bgc_ctx *ctx, const BgcParams *p,
@@ -333,7 +344,7 @@ int macros_source_sink(bgc_ctx *ctx, const MacrosInput *in, MacrosOutput *out,
 enum {
   BGC_K_CO3_CELLS = 0, BGC_K_ECO_COLUMNS = 1, BGC_K_DMS_COLUMNS = 2, BGC_K_MACROS_CELLS = 3,
   BGC_K_SURFACE_FLUXES = 4, BGC_K_DMS_SURFACE = 5, BGC_K_CO2CALC_POINTS = 6, BGC_K_INVENTORY = 7,
-  BGC_K_TRANSPOSE = 8, BGC_KERNEL_ID_COUNT = 9
+  BGC_K_TRANSPOSE = 8, BGC_K_ZSAT_COLUMNS = 9, BGC_KERNEL_ID_COUNT = 10
 };
 int bgc_timing_enable(bgc_ctx *ctx, int enable);
 int bgc_timing_reset(bgc_ctx *ctx);   /* zeroes times AND launch counters */

@@ -96,6 +96,13 @@ struct bgc_ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t pipe_stream = nullptr;       // second slot of the host-layout pipeline
   cudaEvent_t pipe_event = nullptr;
+  // bgc_source_sink runs the carbonate kernel (+ saturation-depth scan) beside the column
+  // sweep: one side stream per pipeline slot, forked from / joined to the slot's stream
+  cudaStream_t side_stream[2] = {nullptr, nullptr};
+  cudaEvent_t fork_event[2] = {nullptr, nullptr}, join_event[2] = {nullptr, nullptr};
+  int concurrent_co3 = 1;                   // BGC_CONCURRENT_CO3=0 serialises the two (tuning / debugging)
+  bool defer_join = false;                  // bgc_ctx_set_deferred_join
+  bool pending_join = false;                // a carbonate side stream has not been joined to the ctx stream yet
   int host_chunk_columns = 0;               // columns per pipeline chunk (0 = automatic; BGC_HOST_CHUNK_COLUMNS)
   bgc::BgcTables bgc_tab;
   bgc::DmsTables dms_tab;
@@ -161,6 +168,15 @@ static int use_device(bgc_ctx *c) {
   return BGC_OK;
 }
 
+// Join point of the deferred carbonate join: the ctx stream waits for the side stream.
+static int join_pending(bgc_ctx *c) {
+  if (c->pending_join) {
+    CU(cudaStreamWaitEvent(c->stream, c->join_event[0], 0));
+    c->pending_join = false;
+  }
+  return BGC_OK;
+}
+
 static int arena_get(bgc_ctx *c, const std::string &key, size_t bytes, void **out) {
   DevBuf &b = c->arena[key];
   if (b.bytes < bytes) {
@@ -198,6 +214,16 @@ extern "C" int bgc_ctx_create(int device, int nLevelsMax, int nColumnsMax, bgc_c
   CU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
   CU(cudaStreamCreateWithFlags(&c->pipe_stream, cudaStreamNonBlocking));
   CU(cudaEventCreateWithFlags(&c->pipe_event, cudaEventDisableTiming));
+  if (const char *v = getenv("BGC_CONCURRENT_CO3")) c->concurrent_co3 = atoi(v);
+  {
+    int lo = 0, hi = 0;   // the side stream gets the LOWER priority: the sweep's blocks are placed first
+    CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    for (int i = 0; i < 2; ++i) {
+      CU(cudaStreamCreateWithPriority(&c->side_stream[i], cudaStreamNonBlocking, lo));
+      CU(cudaEventCreateWithFlags(&c->fork_event[i], cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&c->join_event[i], cudaEventDisableTiming));
+    }
+  }
   c->stream = c->own_stream;
   CU(cudaMalloc(&c->d_status, 4 * sizeof(unsigned long long)));
   CU(cudaMemset(c->d_status, 0, 4 * sizeof(unsigned long long)));
@@ -213,6 +239,8 @@ extern "C" int bgc_ctx_destroy(bgc_ctx *c) {
   cudaSetDevice(c->device);
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   cudaStreamSynchronize(c->stream);
+  for (int i = 0; i < 2; ++i) if (c->side_stream[i]) cudaStreamSynchronize(c->side_stream[i]);
+  if (c->pipe_stream) cudaStreamSynchronize(c->pipe_stream);
   for (auto &kv : c->arena) if (kv.second.p) cudaFree(kv.second.p);
   cudaFree(c->d_status); cudaFree(c->d_inventory);
   for (auto &sp : c->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
@@ -220,6 +248,11 @@ extern "C" int bgc_ctx_destroy(bgc_ctx *c) {
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   if (c->pipe_stream) cudaStreamDestroy(c->pipe_stream);
   if (c->pipe_event) cudaEventDestroy(c->pipe_event);
+  for (int i = 0; i < 2; ++i) {
+    if (c->side_stream[i]) cudaStreamDestroy(c->side_stream[i]);
+    if (c->fork_event[i]) cudaEventDestroy(c->fork_event[i]);
+    if (c->join_event[i]) cudaEventDestroy(c->join_event[i]);
+  }
   std::lock_guard<std::mutex> lock(g_mu);
   g_versions.erase(c);
   for (auto *m : {&g_const_owner_bgc, &g_const_owner_dms, &g_const_owner_macros}) {
@@ -232,12 +265,26 @@ extern "C" int bgc_ctx_destroy(bgc_ctx *c) {
 
 extern "C" int bgc_ctx_set_stream(bgc_ctx *c, void *cuda_stream) {
   if (!c) return fail(BGC_ERR_ARG, "null ctx");
+  RC(join_pending(c));
   c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
   return BGC_OK;
 }
 
+extern "C" int bgc_ctx_set_deferred_join(bgc_ctx *c, int enable) {
+  RC(use_device(c));
+  if (!enable) RC(join_pending(c));
+  c->defer_join = enable != 0;
+  return BGC_OK;
+}
+
+extern "C" int bgc_carbonate_join(bgc_ctx *c) {
+  RC(use_device(c));
+  return join_pending(c);
+}
+
 extern "C" int bgc_ctx_synchronize(bgc_ctx *c) {
   RC(use_device(c));
+  RC(join_pending(c));
   CU(cudaStreamSynchronize(c->stream));
   return BGC_OK;
 }
@@ -246,6 +293,7 @@ extern "C" int bgc_get_status(bgc_ctx *c, BgcStatus *out, int reset) {
   RC(use_device(c));
   if (!out) return fail(BGC_ERR_ARG, "null out");
   unsigned long long h[4];
+  RC(join_pending(c));
   CU(cudaMemcpyAsync(h, c->d_status, sizeof h, cudaMemcpyDeviceToHost, c->stream));
   if (reset) CU(cudaMemsetAsync(c->d_status, 0, sizeof h, c->stream));
   CU(cudaStreamSynchronize(c->stream));
@@ -256,6 +304,7 @@ extern "C" int bgc_get_status(bgc_ctx *c, BgcStatus *out, int reset) {
 // ------------------------------------------------------------------ launch accounting / timing
 static int resolve_spans(bgc_ctx *c) {
   if (c->spans.empty()) return BGC_OK;
+  RC(join_pending(c));
   CU(cudaStreamSynchronize(c->stream));
   for (auto &sp : c->spans) {
     float ms = 0.f;
@@ -294,7 +343,7 @@ extern "C" const char *bgc_kernel_name(int kernel_id) {
   static const char *names[BGC_KERNEL_ID_COUNT] = {
       "co3_cells_kernel", "eco_columns_kernel", "dms_columns_kernel", "macros_cells_kernel",
       "surface_fluxes_kernel", "dms_surface_kernel", "co2calc_points_kernel", "inventory kernels",
-      "transpose_kernel"};
+      "transpose_kernel", "zsat_columns_kernel"};
   return (kernel_id >= 0 && kernel_id < BGC_KERNEL_ID_COUNT) ? names[kernel_id] : "";
 }
 
@@ -506,6 +555,7 @@ static int chunk_columns(const bgc_ctx *c, int nC) {
 // goes through slot 0 (sequential, still chunked).
 template <class Body>
 static int host_pipeline(bgc_ctx *c, int nL, int nC, Body body) {
+  RC(join_pending(c));
   const int cc = chunk_columns(c, nC);
   const int nchunks = (nC + cc - 1) / cc;
   cudaStream_t user = c->stream;
@@ -577,6 +627,7 @@ extern "C" int bgc_inventory_reset(bgc_ctx *c) {
 extern "C" int bgc_inventory_get(bgc_ctx *c, double out[BGC_INVENTORY_LEN]) {
   RC(use_device(c));
   if (!out) return fail(BGC_ERR_ARG, "null out");
+  RC(join_pending(c));
   CU(cudaMemcpyAsync(out, c->d_inventory, BGC_INVENTORY_LEN * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   return BGC_OK;
@@ -589,7 +640,8 @@ extern "C" int bgc_inventory_device_ptr(bgc_ctx *c, double **dev_ptr) {
 
 // ------------------------------------------------------------------ BGC_SourceSink
 static int source_sink_device(bgc_ctx *c, const BgcInput *in, const BgcForcing *fo, BgcOutput *out,
-                              const BgcDiagnostics *diag, int nL, int nC, int nCols, int alt_co2_use_eco) {
+                              const BgcDiagnostics *diag, int nL, int nC, int nCols, int alt_co2_use_eco,
+                              bool host_call = false) {
   RC(ensure_bgc_tables(c));
   const size_t n2 = (size_t)nL * nC;
   BgcDiagnostics d;
@@ -610,22 +662,19 @@ static int source_sink_device(bgc_ctx *c, const BgcInput *in, const BgcForcing *
   if ((P.lrest_no3 && !fo->NO3_CLIM) || (P.lrest_po4 && !fo->PO4_CLIM) || (P.lrest_sio3 && !fo->SiO3_CLIM))
     return fail(BGC_ERR_ARG, "bgc_source_sink: lrest_* set but the climatology array is NULL");
 
-  // carbonate chemistry, cell-parallel
-  bgc::Co3Args ca;
-  ca.nL = nL; ca.nC = nC; ca.nColumns = nCols;
-  ca.tracers = in->BGC_tracers; ca.T = in->PotentialTemperature; ca.S = in->Salinity;
-  ca.zmid = in->cell_center_depth; ca.kmax = in->number_of_active_levels;
-  ca.ph_prev = out->PH_PREV_3D; ca.ph_prev_alt = out->PH_PREV_ALT_CO2_3D;
-  ca.co3 = d.diag_CO3; ca.hco3 = d.diag_HCO3; ca.h2co3 = d.diag_H2CO3; ca.ph = d.diag_pH_3D;
-  ca.co3_alt = d.diag_CO3_ALT_CO2; ca.hco3_alt = d.diag_HCO3_ALT_CO2; ca.h2co3_alt = d.diag_H2CO3_ALT_CO2;
-  ca.ph_alt = d.diag_pH_3D_ALT_CO2; ca.sat_calc = d.diag_co3_sat_calc; ca.sat_arag = d.diag_co3_sat_arag;
-  ca.status = c->d_status;
-  if (any_diag) {   // the column sweep's saturation-depth scan consumes these three
-    if (!ca.co3) RC(arena_d(c, "scratch_co3", n2, &ca.co3));
-    if (!ca.sat_calc) RC(arena_d(c, "scratch_satc", n2, &ca.sat_calc));
-    if (!ca.sat_arag) RC(arena_d(c, "scratch_sata", n2, &ca.sat_arag));
+  // The column sweep does not depend on the carbonate kernel: it is launched FIRST on the ctx
+  // stream, the carbonate kernel and the saturation-depth scan follow on a lower-priority side
+  // stream forked here and joined before returning.  The sweep's last, partial wave leaves
+  // most SMs idle (6.2 waves of 148 blocks on the EC60to30 mesh) and the FP64-bound carbonate
+  // blocks fill them.
+  RC(join_pending(c));   // a deferred join of the previous call ends here at the latest
+  const int slot = (c->stream == c->pipe_stream) ? 1 : 0;
+  cudaStream_t main_stream = c->stream;
+  cudaStream_t co3_stream = c->concurrent_co3 ? c->side_stream[slot] : main_stream;
+  if (c->concurrent_co3) {
+    CU(cudaEventRecord(c->fork_event[slot], main_stream));
+    CU(cudaStreamWaitEvent(co3_stream, c->fork_event[slot], 0));
   }
-  LAUNCH(BGC_K_CO3_CELLS, 1, bgc::launch_co3_cells(ca, c->stream));
 
   // ecosystem + particle sweep, column-parallel
   bgc::EcoArgs ea;
@@ -636,31 +685,33 @@ static int source_sink_device(bgc_ctx *c, const BgcInput *in, const BgcForcing *
   ea.fesedflux = fo->FESEDFLUX; ea.rtau = fo->NUTR_RESTORE_RTAU; ea.no3_clim = fo->NO3_CLIM;
   ea.po4_clim = fo->PO4_CLIM; ea.sio3_clim = fo->SiO3_CLIM;
   ea.dust_flux_in = fo->dust_FLUX_IN; ea.sw_flux = fo->ShortWaveFlux_surface;
-  ea.co3 = ca.co3; ea.sat_calc = ca.sat_calc; ea.sat_arag = ca.sat_arag;
   ea.tend = out->BGC_tendencies;
   ea.d = d;
-  // written by the carbonate kernel
+  // written by the carbonate kernel / the saturation-depth scan
   ea.d.diag_CO3 = ea.d.diag_HCO3 = ea.d.diag_H2CO3 = ea.d.diag_pH_3D = nullptr;
   ea.d.diag_CO3_ALT_CO2 = ea.d.diag_HCO3_ALT_CO2 = ea.d.diag_H2CO3_ALT_CO2 = ea.d.diag_pH_3D_ALT_CO2 = nullptr;
   ea.d.diag_co3_sat_calc = ea.d.diag_co3_sat_arag = nullptr;
+  ea.d.diag_zsatcalc = ea.d.diag_zsatarag = nullptr;
   // declared in BGC_diagnostics_type but never zeroed nor written by the reference
   ea.d.diag_POC_ACCUM = ea.d.diag_DONr_remin = ea.d.diag_DOPr_remin = nullptr;
   ea.status = c->d_status;
-  // diag_mode 2 = every array the sweep owns is present -> unchecked stores.  The ten
-  // carbonate arrays belong to co3_cells_kernel and the three never-touched members of
-  // the reference type may be NULL without leaving that mode.
+  // diag_mode 2 = every array the sweep owns is present -> unchecked stores.  The arrays of
+  // the other two kernels and the three never-touched members of the reference type may be
+  // NULL without leaving that mode.
   int diag_mode = 0;
   if (any_diag) {
     diag_mode = 2;
     double *const *pp = (double *const *)&ea.d;
     const size_t first_carb = offsetof(BgcDiagnostics, diag_CO3) / sizeof(double *);
     const size_t last_carb = offsetof(BgcDiagnostics, diag_co3_sat_arag) / sizeof(double *);
-    const size_t untouched[3] = {offsetof(BgcDiagnostics, diag_POC_ACCUM) / sizeof(double *),
-                                 offsetof(BgcDiagnostics, diag_DONr_remin) / sizeof(double *),
-                                 offsetof(BgcDiagnostics, diag_DOPr_remin) / sizeof(double *)};
+    const size_t other[5] = {offsetof(BgcDiagnostics, diag_POC_ACCUM) / sizeof(double *),
+                             offsetof(BgcDiagnostics, diag_DONr_remin) / sizeof(double *),
+                             offsetof(BgcDiagnostics, diag_DOPr_remin) / sizeof(double *),
+                             offsetof(BgcDiagnostics, diag_zsatcalc) / sizeof(double *),
+                             offsetof(BgcDiagnostics, diag_zsatarag) / sizeof(double *)};
     for (size_t i = 0; i < sizeof(BgcDiagnostics) / sizeof(double *); ++i) {
       if (pp[i] || (i >= first_carb && i <= last_carb)) continue;
-      if (i == untouched[0] || i == untouched[1] || i == untouched[2]) continue;
+      if (i == other[0] || i == other[1] || i == other[2] || i == other[3] || i == other[4]) continue;
       diag_mode = 1;
       break;
     }
@@ -672,6 +723,44 @@ static int source_sink_device(bgc_ctx *c, const BgcInput *in, const BgcForcing *
     RC(arena_d(c, "inv_partials_bgc", (size_t)inv_parts * bgc::kEcoInvGroups * bgc::kInvGroup, &ea.inv_partials));
   }
   LAUNCH(BGC_K_ECO_COLUMNS, 1, bgc::launch_eco_columns(ea, diag_mode, c->eco_variant, c->stream));
+
+  // carbonate chemistry, cell-parallel, then the saturation-depth scan (side stream)
+  bgc::Co3Args ca;
+  ca.nL = nL; ca.nC = nC; ca.nColumns = nCols;
+  ca.tracers = in->BGC_tracers; ca.T = in->PotentialTemperature; ca.S = in->Salinity;
+  ca.zmid = in->cell_center_depth; ca.kmax = in->number_of_active_levels;
+  ca.ph_prev = out->PH_PREV_3D; ca.ph_prev_alt = out->PH_PREV_ALT_CO2_3D;
+  ca.co3 = d.diag_CO3; ca.hco3 = d.diag_HCO3; ca.h2co3 = d.diag_H2CO3; ca.ph = d.diag_pH_3D;
+  ca.co3_alt = d.diag_CO3_ALT_CO2; ca.hco3_alt = d.diag_HCO3_ALT_CO2; ca.h2co3_alt = d.diag_H2CO3_ALT_CO2;
+  ca.ph_alt = d.diag_pH_3D_ALT_CO2; ca.sat_calc = d.diag_co3_sat_calc; ca.sat_arag = d.diag_co3_sat_arag;
+  ca.status = c->d_status;
+  const bool want_zsat = d.diag_zsatcalc || d.diag_zsatarag;
+  if (want_zsat) {   // the scan consumes these three: ctx scratch where the caller has no array
+    const std::string sfx = slot ? "#1" : "#0";
+    if (!ca.co3) RC(arena_d(c, "scratch_co3" + sfx, n2, &ca.co3));
+    if (!ca.sat_calc) RC(arena_d(c, "scratch_satc" + sfx, n2, &ca.sat_calc));
+    if (!ca.sat_arag) RC(arena_d(c, "scratch_sata" + sfx, n2, &ca.sat_arag));
+  }
+  c->stream = co3_stream;   // LAUNCH brackets its timing events on c->stream
+  int rc_side = [&]() -> int {
+    LAUNCH(BGC_K_CO3_CELLS, 1, bgc::launch_co3_cells(ca, c->stream));
+    if (want_zsat) {
+      bgc::ZsatArgs za;
+      za.nL = nL; za.nC = nC; za.nColumns = nCols; za.kmax = in->number_of_active_levels;
+      za.co3 = ca.co3; za.sat_calc = ca.sat_calc; za.sat_arag = ca.sat_arag;
+      za.zmid = in->cell_center_depth; za.zbot = in->cell_bottom_depth;
+      za.zsatcalc = d.diag_zsatcalc; za.zsatarag = d.diag_zsatarag;
+      LAUNCH(BGC_K_ZSAT_COLUMNS, 1, bgc::launch_zsat_columns(za, c->stream));
+    }
+    return BGC_OK;
+  }();
+  c->stream = main_stream;
+  if (rc_side != BGC_OK) return rc_side;
+  if (c->concurrent_co3) {
+    CU(cudaEventRecord(c->join_event[slot], co3_stream));
+    if (c->defer_join && !host_call && slot == 0) c->pending_join = true;   // joined at the next join point
+    else CU(cudaStreamWaitEvent(main_stream, c->join_event[slot], 0));
+  }
   if (c->inventory_on) {
     // destination of every value the sweep produced (layout: bgc_kernels.cuh, kEcoInvGroups)
     int oi[bgc::kEcoInvGroups][bgc::kInvGroup];
@@ -741,7 +830,7 @@ extern "C" int bgc_source_sink(bgc_ctx *c, const BgcInput *in, const BgcForcing 
 #undef DEV_C1
     }
 
-    RC(source_sink_device(c, &din, &dfo, &dout, diag ? &dd : nullptr, h.nL, h.cc, cols, alt_co2_use_eco));
+    RC(source_sink_device(c, &din, &dfo, &dout, diag ? &dd : nullptr, h.nL, h.cc, cols, alt_co2_use_eco, true));
 
     RC(down_k(c, h, dout.BGC_tendencies, out->BGC_tendencies, BGC_TRACER_CNT));
     RC(down_k(c, h, dout.PH_PREV_3D, out->PH_PREV_3D, 1));
@@ -1089,6 +1178,7 @@ extern "C" int bgc_inventory_allreduce(bgc_ctx *c, double out[BGC_INVENTORY_LEN]
   RC(use_device(c));
   if (!out) return fail(BGC_ERR_ARG, "null out");
   double *buf = nullptr;
+  RC(join_pending(c));
   RC(arena_d(c, "inv_reduced", BGC_INVENTORY_LEN, &buf));
   if (c->comm) {
     NC(g_nccl.AllReduce(c->d_inventory, buf, BGC_INVENTORY_LEN, kNcclFloat64, kNcclSum, c->comm, c->stream));

@@ -38,12 +38,22 @@ struct Co3Args {
   const int *kmax;                       // (col)
   double *ph_prev, *ph_prev_alt;         // (k,col) read-modify-write on active cells
   // outputs; any may be NULL.  co3/sat_calc/sat_arag are also consumed by the
-  // column sweep (saturation-depth scan), so the caller always provides them
-  // (diagnostic arrays or ctx scratch).
+  // saturation-depth scan (zsat_columns_kernel), so the caller provides them
+  // (diagnostic arrays or ctx scratch) whenever diag_zsatcalc / diag_zsatarag are wanted.
   double *co3, *hco3, *h2co3, *ph, *co3_alt, *hco3_alt, *h2co3_alt, *ph_alt, *sat_calc, *sat_arag;
   unsigned long long *status;            // BgcStatus counters
 };
 cudaError_t launch_co3_cells(const Co3Args &a, cudaStream_t s);
+
+// ---- saturation-depth scan (BGC_mod.F90:1003-1032), one thread per COLUMN, after the carbonate kernel
+struct ZsatArgs {
+  int nL, nC, nColumns;
+  const int *kmax;
+  const double *co3, *sat_calc, *sat_arag;   // from launch_co3_cells
+  const double *zmid, *zbot;
+  double *zsatcalc, *zsatarag;               // (col); either may be NULL
+};
+cudaError_t launch_zsat_columns(const ZsatArgs &a, cudaStream_t s);
 
 // ---- ecosystem + particulate column sweep, one thread per COLUMN
 struct EcoArgs {
@@ -54,9 +64,8 @@ struct EcoArgs {
   const int *kmax;
   const double *fesedflux, *rtau, *no3_clim, *po4_clim, *sio3_clim;   // (k,col); *_clim only if lrest_*
   const double *dust_flux_in, *sw_flux;  // (col)
-  const double *co3, *sat_calc, *sat_arag;   // from launch_co3_cells
   double *tend;                          // (k,col,30)
-  BgcDiagnostics d;                      // carbonate + never-touched members nulled by the caller
+  BgcDiagnostics d;                      // carbonate, zsat* and never-touched members nulled by the caller
   unsigned long long *status;
   double *inv_partials;                  // NULL, or the fused stage 1 of the inventory reduction
 };

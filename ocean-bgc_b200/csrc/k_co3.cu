@@ -137,6 +137,45 @@ co3_cells_kernel(const __grid_constant__ Co3Args A) {
   }
 }
 
+// Saturation-depth scan (BGC_mod.F90:1003-1032): the depth at which CO3 first falls to the
+// calcite / aragonite saturation concentration, linearly interpolated between cell centres;
+// -1 while still supersaturated, 0 for a column undersaturated at the surface, the bottom
+// depth if the whole column is supersaturated.  Per-column diagnostics (zero-filled for
+// inactive columns, :625-727).
+__global__ void __launch_bounds__(128)
+zsat_columns_kernel(const __grid_constant__ ZsatArgs A) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= A.nC) return;
+  int kmax = (col < A.nColumns) ? A.kmax[col] : 0;
+  if (kmax > A.nL) kmax = A.nL;
+  double ZSATCALC = 0.0, ZSATARAG = 0.0, CALC_ANOM_km1 = 0.0, ARAG_ANOM_km1 = 0.0, zmid_km1 = 0.0;
+#pragma unroll 4
+  for (int k = 0; k < kmax; ++k) {
+    const unsigned i2 = (unsigned)col + (unsigned)A.nC * (unsigned)k;
+    const double CO3 = A.co3[i2], sat_c = A.sat_calc[i2], sat_a = A.sat_arag[i2], zmid = A.zmid[i2];
+    if (k == 0) {
+      ZSATCALC = (CO3 > sat_c) ? -1.0 : 0.0;
+      ZSATARAG = (CO3 > sat_a) ? -1.0 : 0.0;
+    } else {
+      const double w4 = zmid_km1 + (zmid - zmid_km1);   // as written in the reference (:1009)
+      if (ZSATCALC == -1.0 && CO3 <= sat_c)
+        ZSATCALC = fdiv(w4 * CALC_ANOM_km1, (CALC_ANOM_km1 - (CO3 - sat_c)));
+      if (ZSATARAG == -1.0 && CO3 <= sat_a)
+        ZSATARAG = fdiv(w4 * ARAG_ANOM_km1, (ARAG_ANOM_km1 - (CO3 - sat_a)));
+      if (k == kmax - 1 && (ZSATCALC == -1.0 || ZSATARAG == -1.0)) {
+        const double zbot = A.zbot[i2];
+        if (ZSATCALC == -1.0) ZSATCALC = zbot;
+        if (ZSATARAG == -1.0) ZSATARAG = zbot;
+      }
+    }
+    CALC_ANOM_km1 = CO3 - sat_c;
+    ARAG_ANOM_km1 = CO3 - sat_a;
+    zmid_km1 = zmid;
+  }
+  if (A.zsatcalc) A.zsatcalc[col] = ZSATCALC;
+  if (A.zsatarag) A.zsatarag[col] = ZSATARAG;
+}
+
 // co2calc_1point (co2calc.F90:75-210): always level 1 => no pressure correction.
 // The reference converts depth -> press_bar and then passes press_bar as the
 // `depth` of comp_co3_coeffs (:156-160); with k = 1 neither value is used.
@@ -311,6 +350,12 @@ cudaError_t launch_co3_cells(const Co3Args &a, cudaStream_t s) {
   const size_t ncell = (size_t)a.nL * (size_t)a.nC;
   if (ncell == 0) return cudaSuccess;
   co3_cells_kernel<<<ceil_div_sz(ncell, 256), 256, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_zsat_columns(const ZsatArgs &a, cudaStream_t s) {
+  if (a.nC <= 0) return cudaSuccess;
+  zsat_columns_kernel<<<ceil_div_sz((size_t)a.nC, 128), 128, 0, s>>>(a);
   return cudaGetLastError();
 }
 

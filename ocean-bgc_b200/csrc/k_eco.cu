@@ -26,7 +26,7 @@
 // Input staging.  With ~8 resident warps per SM (255 registers per thread) nothing
 // hides an HBM round trip, and a level has ~8 dependent batches of loads.  So one
 // elected thread per block fetches the NEXT level's slab of every input array -
-// 27 tracers, T, S, zmid, dz, zbot, FESEDFLUX, CO3 and the two saturation values,
+// 27 tracers, T, S, zmid, dz, zbot, FESEDFLUX,
 // BLOCK consecutive columns = one contiguous BLOCK*8-byte run each - with
 // cp.async.bulk (the TMA unit's 1-D bulk copy) into a double-buffered shared-memory
 // stage, completion signalled on an mbarrier; the compute threads only ever read
@@ -34,8 +34,11 @@
 // aligned (odd nColumnsMax or a misaligned caller pointer).
 //
 // The carbonate solve of each cell has no vertical coupling and runs in the
-// cell-parallel kernel of k_co3.cu; this kernel only consumes CO3 and the two
-// saturation concentrations for the saturation-depth scan (:1003-1032).
+// cell-parallel kernel of k_co3.cu, and the saturation-depth scan (:1003-1032) that
+// consumes its results is a separate small column kernel there: this kernel does not
+// depend on the carbonate kernel at all, so the two run concurrently (bgc_capi.cu) and
+// the FP64-bound carbonate work fills the SMs that the last, partial wave of this kernel
+// leaves idle (235 160 columns = 6.2 waves of 148 blocks x 256 columns).
 #include "bgc_kernels.cuh"
 #include "bgc_math.cuh"
 #include "bgc_reduce.cuh"
@@ -172,7 +175,17 @@ constexpr int NA = BGC_AUTOTROPH_CNT;
   X(diag_calcToSed) X(diag_pocToSed) X(diag_ponToSed) \
   X(diag_popToSed) X(diag_bsiToSed) X(diag_dustToSed) X(diag_pfeToSed) \
   X(diag_SedDenitrif) X(diag_OtherRemin) X(diag_tot_CaCO3_form)
+// The per-column diagnostics this kernel owns: BGC_DIAG_C1_LIST minus the two saturation
+// depths (zsat_columns_kernel, k_co3.cu).
+#define ECO_DIAG_C1_LIST(X) \
+  X(diag_photoC_TOT_zint) X(diag_photoC_NO3_TOT_zint) X(diag_Jint_Ctot) \
+  X(diag_Jint_100m_Ctot) X(diag_Jint_Ntot) X(diag_Jint_100m_Ntot) X(diag_Jint_Ptot) \
+  X(diag_Jint_100m_Ptot) X(diag_Jint_Sitot) X(diag_Jint_100m_Sitot) \
+  X(diag_Chl_TOT_zint_100m) X(diag_tot_CaCO3_form_zint) X(diag_tot_bSi_form) \
+  X(diag_O2_ZMIN) X(diag_O2_ZMIN_DEPTH)
 #define COUNT_ONE(name) +1
+static_assert((0 ECO_DIAG_C1_LIST(COUNT_ONE)) + 2 == (0 BGC_DIAG_C1_LIST(COUNT_ONE)),
+              "ECO_DIAG_C1_LIST is out of step with BGC_DIAG_C1_LIST");
 static_assert((0 ECO_DIAG_K2_LIST(COUNT_ONE)) + 13 == (0 BGC_DIAG_K2_LIST(COUNT_ONE)),
               "ECO_DIAG_K2_LIST is out of step with BGC_DIAG_K2_LIST");
 
@@ -190,7 +203,7 @@ static_assert((0 ECO_DIAG_K2_LIST(COUNT_ONE)) + 13 == (0 BGC_DIAG_K2_LIST(COUNT_
 //                       held across the whole level body (they used to spill to local memory,
 //                       which misses the few KB of L1 left beside a 221 KB carve-out)
 //   2 mbarriers
-enum { R_T = BGC_TRACER_CNT, R_ZMID, R_DZ, R_ZBOT, R_FESED, R_S, R_CO3, R_SATC, R_SATA, R_ROWS };
+enum { R_T = BGC_TRACER_CNT, R_ZMID, R_DZ, R_ZBOT, R_FESED, R_S, R_ROWS };
 enum { X_PPRIME = 0, X_ZPHOTO = 4, X_ZNO3 = 8, X_ZCACO3 = 12,
        X_JC = 16, X_JC100, X_JN, X_JN100, X_JP, X_JP100, X_JSI, X_JSI100,
        X_CHL100, X_BSI, X_CACO3ZINT, X_PHOTOCZINT, X_PHOTOCNO3ZINT, X_O2MIN, X_ROWS };
@@ -268,8 +281,7 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
   const bool north = lat >= 0.0;
 
   // ---- column integrals / scan state (diagnostics only)
-  double ZSATCALC = 0.0, ZSATARAG = 0.0, CALC_ANOM_km1 = 0.0, ARAG_ANOM_km1 = 0.0;
-  double zmid_km1 = 0.0, zbot_km1 = 0.0;
+  double zbot_km1 = 0.0;
   double O2_min_depth = 0.0;
 #pragma unroll
   for (int r = X_ZPHOTO; r < X_ROWS; ++r) XS(r) = 0.0;
@@ -308,7 +320,7 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
     double *dst = smem + (size_t)(kk & 1) * R_ROWS * BLOCK;
     const unsigned bar = smem_u32(&bars[kk & 1]);
     const size_t off = (size_t)nC * (size_t)kk + (size_t)col0;
-    if (tid == 0) mbar_expect_tx(bar, slab_bytes * (unsigned)((BGC_TRACER_CNT - 3) + 5 + (DIAG ? 4 : 0)));
+    if (tid == 0) mbar_expect_tx(bar, slab_bytes * (unsigned)((BGC_TRACER_CNT - 3) + 5 + (DIAG ? 1 : 0)));
 #pragma unroll 1
     for (int r = tid >> 5; r < (DIAG ? R_ROWS : R_S); r += NW) {
       const double *src;
@@ -322,10 +334,7 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
           case R_DZ:    src = A.dz; break;
           case R_ZBOT:  src = A.zbot; break;
           case R_FESED: src = A.fesedflux; break;
-          case R_S:     src = A.S; break;
-          case R_CO3:   src = A.co3; break;
-          case R_SATC:  src = A.sat_calc; break;
-          default:      src = A.sat_arag; break;
+          default:      src = A.S; break;
         }
       }
       bulk_g2s(smem_u32(dst + r * BLOCK), src + off, slab_bytes, bar);
@@ -350,7 +359,7 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
         if (!((skip_slots >> n) & 1u)) IN(n) = *src;
       IN(R_T) = A.T[i2]; IN(R_ZMID) = A.zmid[i2]; IN(R_DZ) = A.dz[i2]; IN(R_ZBOT) = A.zbot[i2];
       IN(R_FESED) = A.fesedflux[i2];
-      if (DIAG) { IN(R_S) = A.S[i2]; IN(R_CO3) = A.co3[i2]; IN(R_SATC) = A.sat_calc[i2]; IN(R_SATA) = A.sat_arag[i2]; }
+      if (DIAG) IN(R_S) = A.S[i2];
     }
 
     if (k >= kmax) {
@@ -438,25 +447,6 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
     const double eKPAR = bexp(-KPARdz);
     PAR_out = PAR_in * eKPAR;
     const double PAR_avg = fdiv(PAR_in * (1.0 - eKPAR), KPARdz);
-
-    // ---- saturation-depth scan (:1003-1032); CO3 & saturation values come from k_co3
-    if (DIAG) {
-      const double CO3 = IN(R_CO3), sat_c = IN(R_SATC), sat_a = IN(R_SATA);
-      if (k == 0) {
-        ZSATCALC = (CO3 > sat_c) ? -1.0 : 0.0;
-        ZSATARAG = (CO3 > sat_a) ? -1.0 : 0.0;
-      } else {
-        const double w4 = zmid_km1 + (zmid - zmid_km1);
-        if (ZSATCALC == -1.0 && CO3 <= sat_c)
-          ZSATCALC = fdiv(w4 * CALC_ANOM_km1, (CALC_ANOM_km1 - (CO3 - sat_c)));
-        if (ZSATARAG == -1.0 && CO3 <= sat_a)
-          ZSATARAG = fdiv(w4 * ARAG_ANOM_km1, (ARAG_ANOM_km1 - (CO3 - sat_a)));
-        if (ZSATCALC == -1.0 && k == kmax - 1) ZSATCALC = zbot;
-        if (ZSATARAG == -1.0 && k == kmax - 1) ZSATARAG = zbot;
-      }
-      CALC_ANOM_km1 = CO3 - sat_c;
-      ARAG_ANOM_km1 = CO3 - sat_a;
-    }
 
     // ---- running sums over the functional groups.  Fortran's SUM(x(:)) adds the
     //      elements left to right starting from zero: so do these accumulators.
@@ -1173,8 +1163,6 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
 
       // O2 minimum scan (:1954-1968)
       if (k == 0 || O2_loc < XS(X_O2MIN)) { XS(X_O2MIN) = O2_loc; O2_min_depth = IN(R_ZMID); }
-
-      zmid_km1 = IN(R_ZMID);
     }
     zbot_km1 = zbot;
 #undef TR
@@ -1214,8 +1202,6 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
       STC(diag_Chl_TOT_zint_100m, XS(X_CHL100));
       STC(diag_tot_CaCO3_form_zint, XS(X_CACO3ZINT));
       STC(diag_tot_bSi_form, XS(X_BSI));
-      STC(diag_zsatcalc, ZSATCALC);
-      STC(diag_zsatarag, ZSATARAG);
       STC(diag_O2_ZMIN, XS(X_O2MIN));
       STC(diag_O2_ZMIN_DEPTH, O2_min_depth);
 #pragma unroll
@@ -1225,7 +1211,7 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
         STCA(diag_CaCO3_form_zint, a, XS(X_ZCACO3 + a));
       }
     } else {
-      BGC_DIAG_C1_LIST(ZERO_C1)
+      ECO_DIAG_C1_LIST(ZERO_C1)
       BGC_DIAG_CA_LIST(ZERO_CA)
     }
   }
@@ -1273,8 +1259,7 @@ cudaError_t launch_variant(const EcoArgs &a, cudaStream_t s) {
 // base + 8*(k*nC + 128*j), so nC must be even and every base pointer 16-byte aligned.
 bool slabs_are_bulk_copyable(const EcoArgs &a, bool diag) {
   if (a.nC & 1) return false;
-  const void *p[] = {a.tracers, a.T, a.zmid, a.dz, a.zbot, a.fesedflux,
-                     diag ? a.S : a.T, diag ? a.co3 : a.T, diag ? a.sat_calc : a.T, diag ? a.sat_arag : a.T};
+  const void *p[] = {a.tracers, a.T, a.zmid, a.dz, a.zbot, a.fesedflux, diag ? a.S : a.T};
   for (const void *q : p) if (((size_t)q) & 15u) return false;
   return true;
 }

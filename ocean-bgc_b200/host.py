@@ -35,6 +35,7 @@ ABI_SYMBOLS = [
     "bgc_comm_init_rank", "bgc_inventory_allreduce", "bgc_host_alloc", "bgc_host_free",
     "bgc_host_register", "bgc_host_unregister", "bgc_layout_to_soa", "bgc_layout_to_fortran",
     "bgc_timing_enable", "bgc_timing_reset", "bgc_timing_get", "bgc_kernel_name",
+    "bgc_ctx_set_deferred_join", "bgc_carbonate_join",
 ]
 
 
@@ -126,6 +127,13 @@ class Context:
 
     def synchronize(self):
         check(self.L, self.L.bgc_ctx_synchronize(self.ptr))
+
+    def set_deferred_join(self, on=True):
+        """Defer the join of the carbonate side stream to the next join point (bgc_b200.h)."""
+        check(self.L, self.L.bgc_ctx_set_deferred_join(self.ptr, C.c_int(int(on))))
+
+    def carbonate_join(self):
+        check(self.L, self.L.bgc_carbonate_join(self.ptr))
 
     def status(self, reset=False):
         st = abi.BgcStatus()
@@ -359,6 +367,7 @@ class DeviceBgcColumns(_DeviceMixin):
             put(t, host.flux_diag[n])
         self.nColumns = host.nColumns
         self.lcalc_O2_gas_flux, self.lcalc_CO2_gas_flux = host.lcalc_O2_gas_flux, host.lcalc_CO2_gas_flux
+        torch.cuda.synchronize()   # torch copies run on torch's stream, library calls on the ctx stream
         return self
 
     def store(self, host):
@@ -461,6 +470,7 @@ class DeviceDmsColumns(_DeviceMixin):
             put(t, host.flux_diag[n])
         self.nColumns = host.nColumns
         self.lcalc_DMS_gas_flux = host.lcalc_DMS_gas_flux
+        torch.cuda.synchronize()   # torch copies run on torch's stream, library calls on the ctx stream
         return self
 
     def store(self, host):
@@ -538,6 +548,7 @@ class DeviceMacrosColumns(_DeviceMixin):
         for n, t in self.diag.items():
             put(t, self._soa(host.diag[n]))
         self.nColumns = host.nColumns
+        torch.cuda.synchronize()   # torch copies run on torch's stream, library calls on the ctx stream
         return self
 
     def store(self, host):
