@@ -301,6 +301,9 @@ int bgc_ctx_synchronize(bgc_ctx *ctx);
  * diagnostics and diag_zsatcalc / diag_zsatarag on the ctx stream; in exchange the FP64-bound
  * carbonate solve overlaps the HBM-bound DMS / MACROS / surface-flux kernels that follow. */
 int bgc_ctx_set_deferred_join(bgc_ctx *ctx, int enable);
+/* enable = 0 launches the carbonate kernel on the ctx stream after the sweep (no side stream):
+ * for per-kernel timing and debugging.  Default: 1 (or the environment BGC_CONCURRENT_CO3). */
+int bgc_ctx_set_concurrency(bgc_ctx *ctx, int enable);
 int bgc_carbonate_join(bgc_ctx *ctx);
 int bgc_get_status(bgc_ctx *ctx, BgcStatus *out, int reset);
 

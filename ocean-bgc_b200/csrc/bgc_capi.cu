@@ -277,6 +277,13 @@ extern "C" int bgc_ctx_set_deferred_join(bgc_ctx *c, int enable) {
   return BGC_OK;
 }
 
+extern "C" int bgc_ctx_set_concurrency(bgc_ctx *c, int enable) {
+  RC(use_device(c));
+  RC(join_pending(c));
+  c->concurrent_co3 = enable != 0;
+  return BGC_OK;
+}
+
 extern "C" int bgc_carbonate_join(bgc_ctx *c) {
   RC(use_device(c));
   return join_pending(c);

@@ -465,7 +465,7 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
 
     // ---- per functional group: quotas (:850-898), uptake, photosynthesis, losses,
     //      grazing, routing (:1107-1388), tendencies (:1700-1745)
-#pragma unroll 1
+#pragma unroll
     for (int a = 0; a < NA; ++a) {
       const BgcAutotroph &at = c_eco.a[a];
       const unsigned ia = i2 + (unsigned)a * nLnC;

@@ -59,7 +59,7 @@ __device__ __forceinline__ void dms_attenuation(double totalChl, double dz, doub
 // The nine tracers one cell consumes (raw; the clamp is applied in dms_cell).  NO3 and DOC are
 // copied by the reference (:471-472) but reach no output (DOC feeds only the unused UV_avg,
 // :531-536): not read here.
-struct DmsCellIn { double zooC, spC, diatC, diazC, phaeoC, spChl, spCaCO3, dms, dmsp; };
+struct DmsCellIn { double zooC, spC, diatC, diazC, phaeoC, spChl, spCaCO3, dms, dmsp, dz; };   // dz: inventory only
 
 __device__ __forceinline__ DmsCellIn dms_load_cell(const DmsArgs &A, unsigned i2, unsigned nLnC) {
   const DmsIndices &I = c_dms.ind;
@@ -70,6 +70,7 @@ __device__ __forceinline__ DmsCellIn dms_load_cell(const DmsArgs &A, unsigned i2
   c.phaeoC = TR(I.phaeoC_ind); c.spChl = TR(I.spChl_ind); c.spCaCO3 = TR(I.spCaCO3_ind);
   c.dms = TR(I.dms_ind); c.dmsp = TR(I.dmsp_ind);
 #undef TR
+  c.dz = A.inv_partials ? A.dz[i2] : 0.0;
   return c;
 }
 
@@ -225,15 +226,26 @@ dms_cells_kernel(const __grid_constant__ DmsArgs A) {
   if (kmax > 0) SST_loc = A.sst[col];
   const DmsColumnConsts cc = dms_column_consts(SST_loc);
 
-  for (int k = w; k < kmax; k += kDmsTileWarps) {
-    const unsigned i2 = (unsigned)col + (unsigned)nC * (unsigned)k;
-#define TR(ind_) fmax(0.0, A.tracers[i2 + (unsigned)((ind_) - 1) * nLnC])
-    const double totalChl = TR(I.spChl_ind) + TR(I.diatChl_ind) + TR(I.diazChl_ind) + TR(I.phaeoChl_ind);
+  {   // phase 1, software-pipelined like phase 3: the next level's five loads are in flight
+    struct ChlIn { double a, b, c, d, dz; };
+    auto load_chl = [&](int k) {
+      const unsigned i2 = (unsigned)col + (unsigned)nC * (unsigned)k;
+#define TR(ind_) A.tracers[i2 + (unsigned)((ind_) - 1) * nLnC]
+      ChlIn r = {TR(I.spChl_ind), TR(I.diatChl_ind), TR(I.diazChl_ind), TR(I.phaeoChl_ind), A.dz[i2]};
 #undef TR
-    double kp, ek;
-    dms_attenuation(totalChl, A.dz[i2], kp, ek);
-    s_kp[k * 32 + lane] = kp;
-    s_ek[k * 32 + lane] = ek;
+      return r;
+    };
+    ChlIn cur = {}, nxt = {};
+    if (w < kmax) cur = load_chl(w);
+    for (int k = w; k < kmax; k += kDmsTileWarps) {
+      if (k + kDmsTileWarps < kmax) nxt = load_chl(k + kDmsTileWarps);
+      const double totalChl = fmax(0.0, cur.a) + fmax(0.0, cur.b) + fmax(0.0, cur.c) + fmax(0.0, cur.d);
+      double kp, ek;
+      dms_attenuation(totalChl, cur.dz, kp, ek);
+      s_kp[k * 32 + lane] = kp;
+      s_ek[k * 32 + lane] = ek;
+      cur = nxt;
+    }
   }
   __syncthreads();
   if (w == 0 && kmax > 0) {
@@ -260,11 +272,8 @@ dms_cells_kernel(const __grid_constant__ DmsArgs A) {
       if (active) {   // diagnostics keep their previous contents outside active cells
         const double PAR_avg = fdiv(s_pin[k * 32 + lane] * (1.0 - s_ek[k * 32 + lane]), s_kp[k * 32 + lane]);
         dms_cell<ALLDIAG>(A, i2, cur, PAR_avg, cc, t_dms, t_dmsp);
-        if (A.inv_partials) {
-          const double dz = A.dz[i2];
-          inv_dms += t_dms * dz;
-          inv_dmsp += t_dmsp * dz;
-        }
+        inv_dms += t_dms * cur.dz;     // cur.dz is 0 without the inventory
+        inv_dmsp += t_dmsp * cur.dz;
       }
       dms_store_tendencies(A, i2, nLnC, active, t_dms, t_dmsp);
       cur = nxt;

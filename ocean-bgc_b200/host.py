@@ -35,7 +35,7 @@ ABI_SYMBOLS = [
     "bgc_comm_init_rank", "bgc_inventory_allreduce", "bgc_host_alloc", "bgc_host_free",
     "bgc_host_register", "bgc_host_unregister", "bgc_layout_to_soa", "bgc_layout_to_fortran",
     "bgc_timing_enable", "bgc_timing_reset", "bgc_timing_get", "bgc_kernel_name",
-    "bgc_ctx_set_deferred_join", "bgc_carbonate_join",
+    "bgc_ctx_set_deferred_join", "bgc_carbonate_join", "bgc_ctx_set_concurrency",
 ]
 
 
@@ -131,6 +131,9 @@ class Context:
     def set_deferred_join(self, on=True):
         """Defer the join of the carbonate side stream to the next join point (bgc_b200.h)."""
         check(self.L, self.L.bgc_ctx_set_deferred_join(self.ptr, C.c_int(int(on))))
+
+    def set_concurrency(self, on=True):
+        check(self.L, self.L.bgc_ctx_set_concurrency(self.ptr, C.c_int(int(on))))
 
     def carbonate_join(self):
         check(self.L, self.L.bgc_carbonate_join(self.ptr))
