@@ -206,8 +206,10 @@ static_assert((0 ECO_DIAG_K2_LIST(COUNT_ONE)) + 13 == (0 BGC_DIAG_K2_LIST(COUNT_
 enum { R_T = BGC_TRACER_CNT, R_ZMID, R_DZ, R_ZBOT, R_FESED, R_S, R_ROWS };
 enum { X_PPRIME = 0, X_ZPHOTO = 4, X_ZNO3 = 8, X_ZCACO3 = 12,
        X_JC = 16, X_JC100, X_JN, X_JN100, X_JP, X_JP100, X_JSI, X_JSI100,
-       X_CHL100, X_BSI, X_CACO3ZINT, X_PHOTOCZINT, X_PHOTOCNO3ZINT, X_O2MIN, X_ROWS };
-static_assert(X_ROWS == 30, "shared-memory budget of the column sweep: 2*R_ROWS + X_ROWS rows of BLOCK doubles");
+       X_CHL100, X_BSI, X_CACO3ZINT, X_PHOTOCZINT, X_PHOTOCNO3ZINT, X_O2MIN,
+       // carried column state that is touched once per level (registers are the scarce resource)
+       X_PAROUT, X_QADUST, X_ZBOTKM1, X_O2MINDEPTH, X_DUS, X_DUH, X_ROWS };
+static_assert(X_ROWS == 36, "shared-memory budget of the column sweep: 2*R_ROWS + X_ROWS rows of BLOCK doubles");
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
@@ -264,27 +266,30 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
   const double T0K = P.T0_Kelvin_BGC;
 
   // ---- various k==1 initialisations (BGC_mod.F90:808-814, :2046-2104)
-  double lat = 0.0, PAR_out = 0.0;
-  double POC_s = 0.0, POC_h = 0.0, Ca_s = 0.0, Ca_h = 0.0, Si_s = 0.0, Si_h = 0.0,
-         du_s = 0.0, du_h = 0.0, Fe_s = 0.0, Fe_h = 0.0, QA_dust_def = 0.0;
+  // P_iron's hard flux is identically zero: it starts at zero and P_iron%gamma = 0 (:2066, :2483)
+  constexpr double Fe_h = 0.0;
+  double lat = 0.0;
+  double POC_s = 0.0, POC_h = 0.0, Ca_s = 0.0, Ca_h = 0.0, Si_s = 0.0, Si_h = 0.0, Fe_s = 0.0;
+#pragma unroll
+  for (int r = X_ZPHOTO; r < X_ROWS; ++r) XS(r) = 0.0;
   if (kmax > 0) {
     lat = A.lat[col];
     const double dust_in = fmax(0.0, A.dust_flux_in[col]);
+    double du_s = 0.0, du_h = 0.0;
     if (dust_in != 0.0) {
       du_s = (1.0 - dust_gamma) * dust_in;
       du_h = dust_gamma * dust_in;
     }
-    QA_dust_def = dust_rho * (du_s + du_h);
-    PAR_out = fmax(0.0, A.sw_flux[col]);
+    XS(X_DUS) = du_s;
+    XS(X_DUH) = du_h;
+    XS(X_QADUST) = dust_rho * (du_s + du_h);
+    double PAR_out = fmax(0.0, A.sw_flux[col]);
     PAR_out = PAR_out * f_qsw_par;
+    XS(X_PAROUT) = PAR_out;
   }
   const bool north = lat >= 0.0;
 
   // ---- column integrals / scan state (diagnostics only)
-  double zbot_km1 = 0.0;
-  double O2_min_depth = 0.0;
-#pragma unroll
-  for (int r = X_ZPHOTO; r < X_ROWS; ++r) XS(r) = 0.0;
 
 
   // ---- inventory (fused stage 1): sum_k tendency*dz.  Every tendency*dz of a level is written
@@ -402,12 +407,13 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
       f_loss_thres = 1.0;
     }
 
-    const double ztop = (k > 0) ? zbot_km1 : 0.0;
+    const double ztop = (k > 0) ? XS(X_ZBOTKM1) : 0.0;
     const double pt100 = fmax(fmin(100.0e2 - ztop, dz), 0.0);   // upper-100 m part of this layer (:1880-1885)
 
     // ---- functional-group tracers: clamp, zero mask (:826-844), Pprime (:1083-1094);
     //      staged in shared memory for the rolled group loop below
     double Chl_sum = 0.0, Chl_100 = 0.0;
+    double Pp[NA];   // Pprime of the four groups (the group loops are fully unrolled: registers)
 #pragma unroll
     for (int a = 0; a < NA; ++a) {
       const BgcAutotroph &at = c_eco.a[a];
@@ -431,12 +437,12 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
         const double tmpTmax = north ? at.temp_thresN : at.temp_thresS;
         if (TEMP > tmpTmax) C_loss_thres = f_loss_thres * at.loss_thres2;
       }
-      XS(X_PPRIME + a) = fmax(vC - C_loss_thres, 0.0);
+      Pp[a] = fmax(vC - C_loss_thres, 0.0);
     }
     if (DIAG) XS(X_CHL100) = XS(X_CHL100) + Chl_100;
 
     // ---- PAR (Morel & Maritorena 2001), :907-924
-    const double PAR_in = PAR_out;
+    const double PAR_in = XS(X_PAROUT);
     double KPARdz;
     {
       const double w = fmax(Chl_sum, 0.02);
@@ -445,8 +451,17 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
     }
     KPARdz = KPARdz * dz;
     const double eKPAR = bexp(-KPARdz);
-    PAR_out = PAR_in * eKPAR;
+    const double PAR_out = PAR_in * eKPAR;
+    XS(X_PAROUT) = PAR_out;
     const double PAR_avg = fdiv(PAR_in * (1.0 - eKPAR), KPARdz);
+    // light factor of the nitrification term (:1545-1556), formed here so that PAR_in, PAR_out and
+    // KPARdz need not stay in registers across the functional-group loop
+    double nitrif_light = 0.0;
+    if (PAR_out < P.parm_nitrif_par_lim) {
+      nitrif_light = 1.0;
+      if (PAR_in > P.parm_nitrif_par_lim)
+        nitrif_light = fdiv(log(fdiv(PAR_out, P.parm_nitrif_par_lim)), (-KPARdz));
+    }
 
     // ---- running sums over the functional groups.  Fortran's SUM(x(:)) adds the
     //      elements left to right starting from zero: so do these accumulators.
@@ -469,7 +484,7 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
     for (int a = 0; a < NA; ++a) {
       const BgcAutotroph &at = c_eco.a[a];
       const unsigned ia = i2 + (unsigned)a * nLnC;
-      const double aChl = IN(at.Chl_ind - 1), aC = IN(at.C_ind - 1), aFe = IN(at.Fe_ind - 1), Pprime = XS(X_PPRIME + a);
+      const double aChl = IN(at.Chl_ind - 1), aC = IN(at.C_ind - 1), aFe = IN(at.Fe_ind - 1), Pprime = Pp[a];
       const bool has_Si = at.Si_ind > 0, has_Ca = at.CaCO3_ind > 0;
 
       const double rCden = frcp(aC + epsC);
@@ -641,7 +656,7 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
       double grazee_C = 0.0;
 #pragma unroll
       for (int b = 0; b < NA; ++b)
-        if (c_eco.same_grazee[a][b]) grazee_C = grazee_C + XS(X_PPRIME + b);
+        if (c_eco.same_grazee[a][b]) grazee_C = grazee_C + Pp[b];
 
       double z_umax = at.z_umax_0 * Tfunc;
       if (a + 1 == I.diat_ind) {
@@ -845,7 +860,7 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
         ((POC_s + POC_h) * 120.1 +
          (Ca_s + Ca_h) * CaCO3_mass +
          (Si_s + Si_h) * SiO2_mass +
-         (du_s + du_h) * P.dust_fescav_scale);
+         (XS(X_DUS) + XS(X_DUH)) * P.dust_fescav_scale);
     if (Fe_loc > fe_scavenge_thres1)
       Fe_scavenge_rate = Fe_scavenge_rate + (Fe_loc - fe_scavenge_thres1) * fe_max_scale2;
     const double Fe_scavenge = yps * Fe_loc * Fe_scavenge_rate;
@@ -855,8 +870,9 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
     // compute_particulate_terms (BGC_mod.F90:2116-2699) for this level
     // =====================================================================
     const double Ca_s_in = Ca_s, Ca_h_in = Ca_h, Si_s_in = Si_s, Si_h_in = Si_h,
-                 du_s_in = du_s, du_h_in = du_h, POC_s_in = POC_s, POC_h_in = POC_h,
+                 du_s_in = XS(X_DUS), du_h_in = XS(X_DUH), POC_s_in = POC_s, POC_h_in = POC_h,
                  Fe_s_in = Fe_s, Fe_h_in = Fe_h;
+    double du_s, du_h;
     double POC_sed = 0.0, Ca_sed = 0.0, Si_sed = 0.0, du_sed = 0.0, Fe_sed = 0.0;
     double SED_DENITRIF = 0.0, OTHER_REMIN = 0.0;
     double POC_remin, Ca_remin, Si_remin, du_remin, Fe_remin;
@@ -912,6 +928,7 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
       if (POC_PROD_avail < 0.0 && A.status) atomicAdd(&A.status[2], 1ull);   // computed and never reported by the reference (:2381-2383)
 
       double new_QA_dust_def;
+      const double QA_dust_def = XS(X_QADUST);
       if (QA_dust_def > 0.0) {
         new_QA_dust_def = fdiv(QA_dust_def * (du_s + du_h), (du_s_in + du_h_in));
       } else {
@@ -926,7 +943,7 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
           POC_PROD_avail = 0.0;
         }
       }
-      QA_dust_def = new_QA_dust_def;
+      XS(X_QADUST) = new_QA_dust_def;
 
       if (POC_h_in == 0.0 && POC_prod == 0.0) {
         POC_h = 0.0;
@@ -954,7 +971,6 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
         Fe_remin = Fe_s_in * dzr + (1.0 - P_iron_gamma) * Fe_prod;
       }
       Fe_remin = Fe_remin + du_remin * dust_to_Fe + (fesed * dzr);
-      Fe_h = Fe_h_in;
 
       if (k == kmax - 1) {   // bottom cell: burial, sediment denitrification (:2522-2631)
         double flux = POC_s + POC_h;
@@ -991,8 +1007,10 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
         du_sed = du_s + du_h;
 
         Ca_s = 0.0; Ca_h = 0.0; Si_s = 0.0; Si_h = 0.0; du_s = 0.0; du_h = 0.0;
-        POC_s = 0.0; POC_h = 0.0; Fe_s = 0.0; Fe_h = 0.0;
+        POC_s = 0.0; POC_h = 0.0; Fe_s = 0.0;
       }
+      XS(X_DUS) = du_s;
+      XS(X_DUH) = du_h;
 
       if (DIAG) {   // :2637-2694
         ST2(diag_POC_FLUX_IN, POC_s_in + POC_h_in);
@@ -1027,14 +1045,7 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
     if (P.lrest_sio3) RESTORE_SiO3 = A.rtau[i2] * (A.sio3_clim[i2] - SiO3_loc);
     if (P.lrest_po4) RESTORE_PO4 = A.rtau[i2] * (A.po4_clim[i2] - PO4_loc);
 
-    double NITRIF;
-    if (PAR_out < P.parm_nitrif_par_lim) {
-      NITRIF = P.parm_kappa_nitrif * NH4_loc;
-      if (PAR_in > P.parm_nitrif_par_lim)
-        NITRIF = fdiv(NITRIF * log(fdiv(PAR_out, P.parm_nitrif_par_lim)), (-KPARdz));
-    } else {
-      NITRIF = 0.0;
-    }
+    const double NITRIF = (P.parm_kappa_nitrif * NH4_loc) * nitrif_light;
 
     double DENITRIF;
     {
@@ -1162,9 +1173,9 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
       XS(X_JSI100) = XS(X_JSI100) + w1 * pt100 + (shallow ? Si_sed : 0.0);
 
       // O2 minimum scan (:1954-1968)
-      if (k == 0 || O2_loc < XS(X_O2MIN)) { XS(X_O2MIN) = O2_loc; O2_min_depth = IN(R_ZMID); }
+      if (k == 0 || O2_loc < XS(X_O2MIN)) { XS(X_O2MIN) = O2_loc; XS(X_O2MINDEPTH) = IN(R_ZMID); }
     }
-    zbot_km1 = zbot;
+    XS(X_ZBOTKM1) = zbot;
 #undef TR
 #undef TEND
     }   // active cell
@@ -1203,7 +1214,7 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
       STC(diag_tot_CaCO3_form_zint, XS(X_CACO3ZINT));
       STC(diag_tot_bSi_form, XS(X_BSI));
       STC(diag_O2_ZMIN, XS(X_O2MIN));
-      STC(diag_O2_ZMIN_DEPTH, O2_min_depth);
+      STC(diag_O2_ZMIN_DEPTH, XS(X_O2MINDEPTH));
 #pragma unroll
       for (int a = 0; a < NA; ++a) {
         STCA(diag_photoC_zint, a, XS(X_ZPHOTO + a));
