@@ -92,7 +92,13 @@ class ClockSampler:
 
     def _read(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.time(), ln.strip()))
+
+    def mark(self):
+        """Start of the timed region: samples from here on are preferred (the sampler itself is
+        started before the warm-up steps, which run the same load, so that a short timed region
+        still has samples)."""
+        self.t_mark = time.time()
 
     def stop(self):
         if not self.proc:
@@ -104,7 +110,13 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, smax, pw, reasons = [], [], [], set()
-        for ln in self.lines:
+        t_mark = getattr(self, "t_mark", 0.0)
+        timed = [ln for (t, ln) in self.lines if t >= t_mark]
+        window = "timed region"
+        if len(timed) < 2:   # too short for the 100 ms sampling period: use warm-up + timed region
+            timed = [ln for (_, ln) in self.lines]
+            window = "warm-up + timed region (same load)"
+        for ln in timed:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -118,7 +130,7 @@ class ClockSampler:
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "power_w_max": float(max(pw)),
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
 # ------------------------------------------------------------------ reference arm / cpu baseline
@@ -265,7 +277,7 @@ def mem_available_gb():
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--columns", type=int, default=EC_COLUMNS, help="columns per GPU")
@@ -336,14 +348,15 @@ def main():
         torch.cuda.synchronize()
 
     step()                       # cold pass: PH_PREV = 0 -> wide brackets (not timed)
-    for _ in range(args.warmup):
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    for _ in range(max(args.warmup, 25)):   # >= W warm-up steps; at least ~0.2 s so the clock sampler sees the load
         step()
     barrier()
     ctx.timing_reset()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark()
     e0.record(stream)
     inv = None
     for _ in range(args.steps):

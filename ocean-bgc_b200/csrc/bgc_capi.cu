@@ -485,48 +485,75 @@ struct HostChunk {
   int nL, nC;      // the caller's extents (host pitch)
   int c0, cc;      // first column and number of columns of this chunk
   int slot;        // pipeline slot: selects the stream and the arena buffer set
+  // Batched transfers.  Copies and transposes of a chunk are issued in two passes so that the
+  // copy engine never waits for a transpose between two arrays: uploads are copied into
+  // consecutive slabs of the slot's staging area first and transposed afterwards
+  // (flush_up); downloads are transposed into the staging area first and copied afterwards
+  // (flush_down).
+  struct Xfer { double *host; double *dev; int nSlabs; size_t stage_slab; };
+  std::vector<Xfer> ups, downs;
+  size_t up_slabs = 0, down_slabs = 0;   // staging slabs used so far
+  size_t stage_slabs = 0;                // capacity of the slot's staging area, in (k,col) slabs
+  double *stage = nullptr;
 };
-
-static const int kStageSlabs = 4;
 
 static std::string slot_key(const HostChunk &h, const char *key) { return std::string(key) + (h.slot ? "#1" : "#0"); }
 
-static int stage_buf(bgc_ctx *c, const HostChunk &h, double **out) {
-  return arena_d(c, slot_key(h, "stage"), (size_t)h.nL * h.cc * kStageSlabs, out);
+// Reserve the slot's staging area: `slabs` (k,col) slabs of the chunk (the larger of what the
+// call uploads and what it downloads).
+static int stage_reserve(bgc_ctx *c, HostChunk &h, size_t slabs) {
+  h.stage_slabs = slabs;
+  return arena_d(c, slot_key(h, "stage"), (size_t)h.nL * h.cc * slabs, &h.stage);
 }
 
-// Upload the chunk of a (k,col,n) array and transpose it to SoA.  Slabs whose bit is set in
-// skip_mask are not transferred (inputs no kernel reads); their device slab keeps stale data.
-static int up_k(bgc_ctx *c, const HostChunk &h, const char *key, const double *host, int nSlabs, double **dev_out,
+// Upload the chunk of a (k,col,n) array (copy now, transpose in flush_up).  Slabs whose bit is
+// set in skip_mask are not transferred (inputs no kernel reads); their device slab keeps stale data.
+static int up_k(bgc_ctx *c, HostChunk &h, const char *key, const double *host, int nSlabs, double **dev_out,
                 unsigned skip_mask = 0u) {
   const size_t n2c = (size_t)h.nL * h.cc, n2 = (size_t)h.nL * h.nC;
-  double *dev = nullptr, *stage = nullptr;
+  double *dev = nullptr;
   RC(arena_d(c, slot_key(h, key), n2c * nSlabs, &dev));
   *dev_out = dev;
   if (!host) return fail(BGC_ERR_ARG, "null host array for %s", key);
-  RC(stage_buf(c, h, &stage));
   for (int s0 = 0; s0 < nSlabs;) {
     if (s0 < 32 && ((skip_mask >> s0) & 1u)) { ++s0; continue; }
     int ns = 1;
-    while (ns < kStageSlabs && s0 + ns < nSlabs && !((s0 + ns) < 32 && ((skip_mask >> (s0 + ns)) & 1u))) ++ns;
-    CU(cudaMemcpy2DAsync(stage, n2c * sizeof(double), host + (size_t)s0 * n2 + (size_t)h.c0 * h.nL, n2 * sizeof(double),
+    while (s0 + ns < nSlabs && !((s0 + ns) < 32 && ((skip_mask >> (s0 + ns)) & 1u))) ++ns;
+    if (h.up_slabs + ns > h.stage_slabs) return fail(BGC_ERR_ARG, "internal: staging area too small (%s)", key);
+    double *st = h.stage + h.up_slabs * n2c;
+    CU(cudaMemcpy2DAsync(st, n2c * sizeof(double), host + (size_t)s0 * n2 + (size_t)h.c0 * h.nL, n2 * sizeof(double),
                          n2c * sizeof(double), (size_t)ns, cudaMemcpyHostToDevice, c->stream));
-    LAUNCH(BGC_K_TRANSPOSE, 1, bgc::launch_transpose(stage, dev + (size_t)s0 * n2c, h.nL, h.cc, ns, c->stream));
+    h.ups.push_back({nullptr, dev + (size_t)s0 * n2c, ns, h.up_slabs});
+    h.up_slabs += ns;
     s0 += ns;
   }
   return BGC_OK;
 }
 
-static int down_k(bgc_ctx *c, const HostChunk &h, const double *dev, double *host, int nSlabs) {
+static int flush_up(bgc_ctx *c, HostChunk &h) {
+  const size_t n2c = (size_t)h.nL * h.cc;
+  for (const auto &x : h.ups)
+    LAUNCH(BGC_K_TRANSPOSE, 1, bgc::launch_transpose(h.stage + x.stage_slab * n2c, x.dev, h.nL, h.cc, x.nSlabs, c->stream));
+  h.ups.clear();
+  return BGC_OK;
+}
+
+// Download the chunk of a (k,col,n) array (transpose now, copy in flush_down).
+static int down_k(bgc_ctx *c, HostChunk &h, const double *dev, double *host, int nSlabs) {
+  const size_t n2c = (size_t)h.nL * h.cc;
+  if (h.down_slabs + nSlabs > h.stage_slabs) return fail(BGC_ERR_ARG, "internal: staging area too small (download)");
+  LAUNCH(BGC_K_TRANSPOSE, 1, bgc::launch_transpose(dev, h.stage + h.down_slabs * n2c, h.cc, h.nL, nSlabs, c->stream));
+  h.downs.push_back({host, nullptr, nSlabs, h.down_slabs});
+  h.down_slabs += nSlabs;
+  return BGC_OK;
+}
+
+static int flush_down(bgc_ctx *c, HostChunk &h) {
   const size_t n2c = (size_t)h.nL * h.cc, n2 = (size_t)h.nL * h.nC;
-  double *stage = nullptr;
-  RC(stage_buf(c, h, &stage));
-  for (int s0 = 0; s0 < nSlabs; s0 += kStageSlabs) {
-    const int ns = (nSlabs - s0 < kStageSlabs) ? nSlabs - s0 : kStageSlabs;
-    LAUNCH(BGC_K_TRANSPOSE, 1, bgc::launch_transpose(dev + (size_t)s0 * n2c, stage, h.cc, h.nL, ns, c->stream));
-    CU(cudaMemcpy2DAsync(host + (size_t)s0 * n2 + (size_t)h.c0 * h.nL, n2 * sizeof(double), stage, n2c * sizeof(double),
-                         n2c * sizeof(double), (size_t)ns, cudaMemcpyDeviceToHost, c->stream));
-  }
+  for (const auto &x : h.downs)
+    CU(cudaMemcpy2DAsync(x.host + (size_t)h.c0 * h.nL, n2 * sizeof(double), h.stage + x.stage_slab * n2c,
+                         n2c * sizeof(double), n2c * sizeof(double), (size_t)x.nSlabs, cudaMemcpyDeviceToHost, c->stream));
+  h.downs.clear();
   return BGC_OK;
 }
 
@@ -798,7 +825,7 @@ extern "C" int bgc_source_sink(bgc_ctx *c, const BgcInput *in, const BgcForcing 
   const BgcParams &P = c->bgc_tab.p;
   // DIC_ALT_CO2 is clamped and then never read by BGC_SourceSink (BGC_mod.F90:748): not uploaded
   const unsigned dead_slabs = 1u << (c->bgc_tab.ind.dic_alt_co2_ind - 1);
-  return host_pipeline(c, nL, nC, [&](const HostChunk &h) -> int {
+  return host_pipeline(c, nL, nC, [&](HostChunk &h) -> int {
     const size_t n2 = (size_t)h.nL * h.cc;
     int cols = nCols - h.c0;
     if (cols < 0) cols = 0;
@@ -806,6 +833,8 @@ extern "C" int bgc_source_sink(bgc_ctx *c, const BgcInput *in, const BgcForcing 
     BgcInput din; BgcForcing dfo; BgcOutput dout; BgcDiagnostics dd;
     memset(&din, 0, sizeof din); memset(&dfo, 0, sizeof dfo); memset(&dout, 0, sizeof dout); memset(&dd, 0, sizeof dd);
     double *t = nullptr; void *v = nullptr;
+    // staging: 30 + 5 + 1 + 4 + 2 slabs up at most; 30 + 2 + 61 + 18*4 down at most
+    RC(stage_reserve(c, h, BGC_TRACER_CNT + 2 + 61 + 18 * BGC_AUTOTROPH_CNT));
     RC(up_k(c, h, "bgc.tracers", in->BGC_tracers, BGC_TRACER_CNT, &t, dead_slabs)); din.BGC_tracers = t;
     RC(up_k(c, h, "bgc.T", in->PotentialTemperature, 1, &t)); din.PotentialTemperature = t;
     RC(up_k(c, h, "bgc.S", in->Salinity, 1, &t)); din.Salinity = t;
@@ -837,6 +866,7 @@ extern "C" int bgc_source_sink(bgc_ctx *c, const BgcInput *in, const BgcForcing 
 #undef DEV_C1
     }
 
+    RC(flush_up(c, h));
     RC(source_sink_device(c, &din, &dfo, &dout, diag ? &dd : nullptr, h.nL, h.cc, cols, alt_co2_use_eco, true));
 
     RC(down_k(c, h, dout.BGC_tendencies, out->BGC_tendencies, BGC_TRACER_CNT));
@@ -855,7 +885,7 @@ extern "C" int bgc_source_sink(bgc_ctx *c, const BgcInput *in, const BgcForcing 
 #undef DN_CA
 #undef DN_C1
     }
-    return BGC_OK;
+    return flush_down(c, h);
   });
 }
 
@@ -1006,7 +1036,7 @@ extern "C" int dms_source_sink(bgc_ctx *c, const DmsInput *in, const DmsForcing 
   RC(ensure_dms_tables(c));
   // NO3 and DOC are copied by the reference and never reach an output (DMS_mod.F90:471-472): not uploaded
   const unsigned dead_slabs = (1u << (c->dms_tab.ind.no3_ind - 1)) | (1u << (c->dms_tab.ind.doc_ind - 1));
-  return host_pipeline(c, nL, nC, [&](const HostChunk &h) -> int {
+  return host_pipeline(c, nL, nC, [&](HostChunk &h) -> int {
     const size_t n2 = (size_t)h.nL * h.cc;
     int cols = nCols - h.c0;
     if (cols < 0) cols = 0;
@@ -1014,6 +1044,7 @@ extern "C" int dms_source_sink(bgc_ctx *c, const DmsInput *in, const DmsForcing 
     DmsInput din; DmsForcing dfo; DmsOutput dout; DmsDiagnostics dd;
     memset(&din, 0, sizeof din); memset(&dfo, 0, sizeof dfo); memset(&dout, 0, sizeof dout); memset(&dd, 0, sizeof dd);
     double *t = nullptr; void *v = nullptr;
+    RC(stage_reserve(c, h, DMS_TRACER_CNT + 1 + sizeof(DmsDiagnostics) / sizeof(double *)));
     RC(up_k(c, h, "dms.tracers", in->DMS_tracers, DMS_TRACER_CNT, &t, dead_slabs)); din.DMS_tracers = t;
     RC(up_k(c, h, "dms.dz", in->cell_thickness, 1, &t)); din.cell_thickness = t;
     RC(up_c(c, h, "dms.kmax", in->number_of_active_levels, sizeof(int), 1, &v)); din.number_of_active_levels = (int *)v;
@@ -1030,6 +1061,7 @@ extern "C" int dms_source_sink(bgc_ctx *c, const DmsInput *in, const DmsForcing 
       DMS_DIAG_LIST(UP_D)
 #undef UP_D
     }
+    RC(flush_up(c, h));
     RC(dms_source_sink_device(c, &din, &dfo, &dout, diag ? &dd : nullptr, h.nL, h.cc, cols));
     RC(down_k(c, h, dout.DMS_tendencies, out->DMS_tendencies, DMS_TRACER_CNT));
     if (diag) {
@@ -1037,7 +1069,7 @@ extern "C" int dms_source_sink(bgc_ctx *c, const DmsInput *in, const DmsForcing 
       DMS_DIAG_LIST(DN_D)
 #undef DN_D
     }
-    return BGC_OK;
+    return flush_down(c, h);
   });
 }
 
@@ -1130,7 +1162,7 @@ extern "C" int macros_source_sink(bgc_ctx *c, const MacrosInput *in, MacrosOutpu
   if (mem_space != BGC_MEM_HOST_FORTRAN) return fail(BGC_ERR_ARG, "unknown mem_space %d", mem_space);
   if (!in->number_of_active_levels) return fail(BGC_ERR_ARG, "macros_source_sink: number_of_active_levels is NULL");
   RC(ensure_macros_tables(c));
-  return host_pipeline(c, nL, nC, [&](const HostChunk &h) -> int {
+  return host_pipeline(c, nL, nC, [&](HostChunk &h) -> int {
     const size_t n2 = (size_t)h.nL * h.cc;
     int cols = nCols - h.c0;
     if (cols < 0) cols = 0;
@@ -1138,6 +1170,7 @@ extern "C" int macros_source_sink(bgc_ctx *c, const MacrosInput *in, MacrosOutpu
     MacrosInput din; MacrosOutput dout; MacrosDiagnostics dd;
     memset(&din, 0, sizeof din); memset(&dout, 0, sizeof dout); memset(&dd, 0, sizeof dd);
     double *t = nullptr; void *v = nullptr;
+    RC(stage_reserve(c, h, MACROS_TRACER_CNT + 1 + sizeof(MacrosDiagnostics) / sizeof(double *)));
     RC(up_k(c, h, "mac.tracers", in->MACROS_tracers, MACROS_TRACER_CNT, &t)); din.MACROS_tracers = t;
     if (c->inventory_on && in->cell_thickness) { RC(up_k(c, h, "mac.dz", in->cell_thickness, 1, &t)); din.cell_thickness = t; }
     RC(up_c(c, h, "mac.kmax", in->number_of_active_levels, sizeof(int), 1, &v)); din.number_of_active_levels = (int *)v;
@@ -1149,6 +1182,7 @@ extern "C" int macros_source_sink(bgc_ctx *c, const MacrosInput *in, MacrosOutpu
       MACROS_DIAG_LIST(UP_D)
 #undef UP_D
     }
+    RC(flush_up(c, h));
     RC(macros_device(c, &din, &dout, diag ? &dd : nullptr, h.nL, h.cc, cols));
     RC(down_k(c, h, dout.MACROS_tendencies, out->MACROS_tendencies, MACROS_TRACER_CNT));
     if (diag) {
@@ -1156,7 +1190,7 @@ extern "C" int macros_source_sink(bgc_ctx *c, const MacrosInput *in, MacrosOutpu
       MACROS_DIAG_LIST(DN_D)
 #undef DN_D
     }
-    return BGC_OK;
+    return flush_down(c, h);
   });
 }
 
