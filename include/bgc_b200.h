@@ -347,7 +347,7 @@ int macros_source_sink(bgc_ctx *ctx, const MacrosInput *in, MacrosOutput *out,
 enum {
   BGC_K_CO3_CELLS = 0, BGC_K_ECO_COLUMNS = 1, BGC_K_DMS_COLUMNS = 2, BGC_K_MACROS_CELLS = 3,
   BGC_K_SURFACE_FLUXES = 4, BGC_K_DMS_SURFACE = 5, BGC_K_CO2CALC_POINTS = 6, BGC_K_INVENTORY = 7,
-  BGC_K_TRANSPOSE = 8, BGC_K_ZSAT_COLUMNS = 9, BGC_KERNEL_ID_COUNT = 10
+  BGC_K_TRANSPOSE = 8, BGC_K_ZSAT_COLUMNS = 9, BGC_K_ACCUMULATE = 10, BGC_KERNEL_ID_COUNT = 11
 };
 int bgc_timing_enable(bgc_ctx *ctx, int enable);
 int bgc_timing_reset(bgc_ctx *ctx);   /* zeroes times AND launch counters */
@@ -369,6 +369,20 @@ int bgc_inventory_device_ptr(bgc_ctx *ctx, double **dev_ptr);
 int bgc_comm_unique_id(unsigned char id[128]);
 int bgc_comm_init_rank(bgc_ctx *ctx, int nranks, int rank, const unsigned char id[128]);
 int bgc_inventory_allreduce(bgc_ctx *ctx, double out[BGC_INVENTORY_LEN]);
+
+/* Diagnostics accumulation for BGC_MEM_HOST_FORTRAN callers (extension).
+ * The host model time-averages the ~160 diagnostic arrays for its history files, yet they
+ * are 3/4 of what a host-layout step moves over PCIe.  With accumulation enabled the
+ * *_source_sink host calls still return tendencies and PH_PREV_* every step, but add each
+ * diagnostic into a device-resident accumulator instead of downloading it (the caller's
+ * diagnostic arrays are left untouched; a non-NULL member still selects the array).
+ * bgc_diag_flush downloads scale * accumulated sum into the given host arrays (Fortran layout,
+ * same extents as the calls that accumulated) and optionally resets the accumulators; any of
+ * the three blocks may be NULL.  DMS / MACROS diagnostics accumulate over active cells only
+ * (the reference leaves them undefined elsewhere) and are zero there after a flush. */
+int bgc_diag_accumulate_enable(bgc_ctx *ctx, int enable);
+int bgc_diag_flush(bgc_ctx *ctx, BgcDiagnostics *bgc, DmsDiagnostics *dms, MacrosDiagnostics *macros,
+                   int nLevelsMax, int nColumnsMax, double scale, int reset);
 
 /* Page-locked host memory for the HOST_FORTRAN path: arrays allocated here (or
  * registered with bgc_host_register) move over PCIe/NVLink-C2C by DMA at full

@@ -101,6 +101,7 @@ struct bgc_ctx {
   cudaStream_t side_stream[2] = {nullptr, nullptr};
   cudaEvent_t fork_event[2] = {nullptr, nullptr}, join_event[2] = {nullptr, nullptr};
   int concurrent_co3 = 1;                   // BGC_CONCURRENT_CO3=0 serialises the two (tuning / debugging)
+  bool diag_accumulate = false;             // bgc_diag_accumulate_enable
   bool defer_join = false;                  // bgc_ctx_set_deferred_join
   bool pending_join = false;                // a carbonate side stream has not been joined to the ctx stream yet
   int host_chunk_columns = 0;               // columns per pipeline chunk (0 = automatic; BGC_HOST_CHUNK_COLUMNS)
@@ -350,7 +351,7 @@ extern "C" const char *bgc_kernel_name(int kernel_id) {
   static const char *names[BGC_KERNEL_ID_COUNT] = {
       "co3_cells_kernel", "eco_columns_kernel", "dms_columns_kernel", "macros_cells_kernel",
       "surface_fluxes_kernel", "dms_surface_kernel", "co2calc_points_kernel", "inventory kernels",
-      "transpose_kernel", "zsat_columns_kernel"};
+      "transpose_kernel", "zsat_columns_kernel", "accumulate_kernel"};
   return (kernel_id >= 0 && kernel_id < BGC_KERNEL_ID_COUNT) ? names[kernel_id] : "";
 }
 
@@ -554,6 +555,27 @@ static int flush_down(bgc_ctx *c, HostChunk &h) {
     CU(cudaMemcpy2DAsync(x.host + (size_t)h.c0 * h.nL, n2 * sizeof(double), h.stage + x.stage_slab * n2c,
                          n2c * sizeof(double), n2c * sizeof(double), (size_t)x.nSlabs, cudaMemcpyDeviceToHost, c->stream));
   h.downs.clear();
+  return BGC_OK;
+}
+
+// Diagnostics accumulation: full-size, zero-initialised accumulator of a diagnostic array
+// (SoA layout of the caller's whole block) and the add of one chunk into it.
+static int acc_buffer(bgc_ctx *c, const char *key, size_t n, double **out) {
+  const std::string k = std::string("acc.") + key;
+  const bool fresh = c->arena.find(k) == c->arena.end() || c->arena[k].bytes < n * sizeof(double);
+  RC(arena_d(c, k, n, out));
+  if (fresh) {   // both pipeline slots add into this buffer: the zero fill must be complete before either does
+    CU(cudaMemsetAsync(*out, 0, n * sizeof(double), c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  }
+  return BGC_OK;
+}
+static int acc_add(bgc_ctx *c, const HostChunk &h, const char *key, const double *dev_chunk, int rows, int nSlabs,
+                   const int *dev_kmax, int cols) {
+  // rows = nL for (k,col[,n]) arrays, 1 for per-column arrays
+  double *acc = nullptr;
+  RC(acc_buffer(c, key, (size_t)rows * h.nC * nSlabs, &acc));
+  LAUNCH(BGC_K_ACCUMULATE, 1, bgc::launch_accumulate(dev_chunk, acc, rows, h.cc, h.nC, h.c0, nSlabs, dev_kmax, cols, 1.0, c->stream));
   return BGC_OK;
 }
 
@@ -872,7 +894,18 @@ extern "C" int bgc_source_sink(bgc_ctx *c, const BgcInput *in, const BgcForcing 
     RC(down_k(c, h, dout.BGC_tendencies, out->BGC_tendencies, BGC_TRACER_CNT));
     RC(down_k(c, h, dout.PH_PREV_3D, out->PH_PREV_3D, 1));
     RC(down_k(c, h, dout.PH_PREV_ALT_CO2_3D, out->PH_PREV_ALT_CO2_3D, 1));
-    if (diag) {
+    if (diag && c->diag_accumulate) {
+      dd.diag_POC_ACCUM = dd.diag_DONr_remin = dd.diag_DOPr_remin = nullptr;
+#define AC_K2(name) if (dd.name) RC(acc_add(c, h, "bgc." #name, dd.name, h.nL, 1, nullptr, cols));
+#define AC_KA(name) if (dd.name) RC(acc_add(c, h, "bgc." #name, dd.name, h.nL, BGC_AUTOTROPH_CNT, nullptr, cols));
+#define AC_CA(name) if (dd.name) RC(acc_add(c, h, "bgc." #name, dd.name, 1, BGC_AUTOTROPH_CNT, nullptr, cols));
+#define AC_C1(name) if (dd.name) RC(acc_add(c, h, "bgc." #name, dd.name, 1, 1, nullptr, cols));
+      BGC_DIAG_K2_LIST(AC_K2) BGC_DIAG_KA_LIST(AC_KA) BGC_DIAG_CA_LIST(AC_CA) BGC_DIAG_C1_LIST(AC_C1)
+#undef AC_K2
+#undef AC_KA
+#undef AC_CA
+#undef AC_C1
+    } else if (diag) {
       // the three never-touched arrays stay exactly as the caller left them
       dd.diag_POC_ACCUM = dd.diag_DONr_remin = dd.diag_DOPr_remin = nullptr;
 #define DN_K2(name) if (dd.name) RC(down_k(c, h, dd.name, diag->name, 1));
@@ -1055,7 +1088,7 @@ extern "C" int dms_source_sink(bgc_ctx *c, const DmsInput *in, const DmsForcing 
       // DMS diagnostics are NOT zeroed by the reference: inactive cells keep the caller's
       // values, so the caller's arrays are uploaded first - unless every cell of the chunk is
       // active, in which case every element is overwritten anyway.
-      const bool keep = !chunk_fully_active(h, in->number_of_active_levels, nCols);
+      const bool keep = !c->diag_accumulate && !chunk_fully_active(h, in->number_of_active_levels, nCols);
 #define UP_D(name) if (diag->name) { if (keep) { RC(up_k(c, h, "dms.d." #name, diag->name, 1, &t)); } \
                                      else { RC(arena_d(c, slot_key(h, "dms.d." #name), n2, &t)); } dd.name = t; }
       DMS_DIAG_LIST(UP_D)
@@ -1064,7 +1097,11 @@ extern "C" int dms_source_sink(bgc_ctx *c, const DmsInput *in, const DmsForcing 
     RC(flush_up(c, h));
     RC(dms_source_sink_device(c, &din, &dfo, &dout, diag ? &dd : nullptr, h.nL, h.cc, cols));
     RC(down_k(c, h, dout.DMS_tendencies, out->DMS_tendencies, DMS_TRACER_CNT));
-    if (diag) {
+    if (diag && c->diag_accumulate) {
+#define AC_D(name) if (dd.name) RC(acc_add(c, h, "dms." #name, dd.name, h.nL, 1, din.number_of_active_levels, cols));
+      DMS_DIAG_LIST(AC_D)
+#undef AC_D
+    } else if (diag) {
 #define DN_D(name) if (dd.name) RC(down_k(c, h, dd.name, diag->name, 1));
       DMS_DIAG_LIST(DN_D)
 #undef DN_D
@@ -1176,7 +1213,7 @@ extern "C" int macros_source_sink(bgc_ctx *c, const MacrosInput *in, MacrosOutpu
     RC(up_c(c, h, "mac.kmax", in->number_of_active_levels, sizeof(int), 1, &v)); din.number_of_active_levels = (int *)v;
     RC(arena_d(c, slot_key(h, "mac.tend"), n2 * MACROS_TRACER_CNT, &dout.MACROS_tendencies));
     if (diag) {   // not zeroed by the reference either: see dms_source_sink
-      const bool keep = !chunk_fully_active(h, in->number_of_active_levels, nCols);
+      const bool keep = !c->diag_accumulate && !chunk_fully_active(h, in->number_of_active_levels, nCols);
 #define UP_D(name) if (diag->name) { if (keep) { RC(up_k(c, h, "mac.d." #name, diag->name, 1, &t)); } \
                                      else { RC(arena_d(c, slot_key(h, "mac.d." #name), n2, &t)); } dd.name = t; }
       MACROS_DIAG_LIST(UP_D)
@@ -1185,13 +1222,75 @@ extern "C" int macros_source_sink(bgc_ctx *c, const MacrosInput *in, MacrosOutpu
     RC(flush_up(c, h));
     RC(macros_device(c, &din, &dout, diag ? &dd : nullptr, h.nL, h.cc, cols));
     RC(down_k(c, h, dout.MACROS_tendencies, out->MACROS_tendencies, MACROS_TRACER_CNT));
-    if (diag) {
+    if (diag && c->diag_accumulate) {
+#define AC_D(name) if (dd.name) RC(acc_add(c, h, "mac." #name, dd.name, h.nL, 1, din.number_of_active_levels, cols));
+      MACROS_DIAG_LIST(AC_D)
+#undef AC_D
+    } else if (diag) {
 #define DN_D(name) if (dd.name) RC(down_k(c, h, dd.name, diag->name, 1));
       MACROS_DIAG_LIST(DN_D)
 #undef DN_D
     }
     return flush_down(c, h);
   });
+}
+
+// ------------------------------------------------------------------ diagnostics accumulation
+extern "C" int bgc_diag_accumulate_enable(bgc_ctx *c, int enable) {
+  RC(use_device(c));
+  c->diag_accumulate = enable != 0;
+  return BGC_OK;
+}
+
+extern "C" int bgc_diag_flush(bgc_ctx *c, BgcDiagnostics *bgc, DmsDiagnostics *dms, MacrosDiagnostics *macros,
+                              int nL, int nC, double scale, int reset) {
+  RC(use_device(c));
+  RC(check_dims(c, nL, nC, nC));
+  RC(join_pending(c));
+  // one array at a time through a single-slab staging area (flushes are rare)
+  auto flush_one = [&](const char *key, double *host, int rows, int nSlabs) -> int {
+    if (!host) return BGC_OK;
+    const std::string k = std::string("acc.") + key;
+    auto it = c->arena.find(k);
+    const size_t n = (size_t)rows * nC * nSlabs;
+    if (it == c->arena.end() || it->second.bytes < n * sizeof(double))
+      return fail(BGC_ERR_ARG, "bgc_diag_flush: nothing accumulated for %s at these extents", key);
+    double *acc = (double *)it->second.p;
+    // transpose into the staging area (a per-column array is a 1-row transpose), scale the
+    // staged copy, download; the accumulator itself keeps the unscaled sum
+    HostChunk h; h.nL = rows; h.nC = nC; h.c0 = 0; h.cc = nC; h.slot = 0;
+    RC(stage_reserve(c, h, (size_t)nSlabs));
+    RC(down_k(c, h, acc, host, nSlabs));
+    if (scale != 1.0) LAUNCH(BGC_K_ACCUMULATE, 1, bgc::launch_scale(h.stage, n, scale, c->stream));
+    RC(flush_down(c, h));
+    if (reset) CU(cudaMemsetAsync(acc, 0, n * sizeof(double), c->stream));
+    return BGC_OK;
+  };
+  if (bgc) {
+    BgcDiagnostics d = *bgc;
+    d.diag_POC_ACCUM = d.diag_DONr_remin = d.diag_DOPr_remin = nullptr;   // never touched by the reference
+#define FL_K2(name) RC(flush_one("bgc." #name, d.name, nL, 1));
+#define FL_KA(name) RC(flush_one("bgc." #name, d.name, nL, BGC_AUTOTROPH_CNT));
+#define FL_CA(name) RC(flush_one("bgc." #name, d.name, 1, BGC_AUTOTROPH_CNT));
+#define FL_C1(name) RC(flush_one("bgc." #name, d.name, 1, 1));
+    BGC_DIAG_K2_LIST(FL_K2) BGC_DIAG_KA_LIST(FL_KA) BGC_DIAG_CA_LIST(FL_CA) BGC_DIAG_C1_LIST(FL_C1)
+#undef FL_K2
+#undef FL_KA
+#undef FL_CA
+#undef FL_C1
+  }
+  if (dms) {
+#define FL_D(name) RC(flush_one("dms." #name, dms->name, nL, 1));
+    DMS_DIAG_LIST(FL_D)
+#undef FL_D
+  }
+  if (macros) {
+#define FL_D(name) RC(flush_one("mac." #name, macros->name, nL, 1));
+    MACROS_DIAG_LIST(FL_D)
+#undef FL_D
+  }
+  CU(cudaStreamSynchronize(c->stream));
+  return BGC_OK;
 }
 
 // ------------------------------------------------------------------ multi-GPU

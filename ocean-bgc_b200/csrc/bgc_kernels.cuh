@@ -129,6 +129,15 @@ cudaError_t launch_macros_cells(const MacrosArgs &a, cudaStream_t s);
 cudaError_t launch_transpose(const double *src, double *dst, int rows_fast_src, int cols_slow_src,
                              int nSlabs, cudaStream_t s);
 
+// ---- on-device accumulation of diagnostics (the host time-averages the
+// diagnostics for history files; accumulating on the device and downloading at output
+// frequency removes their PCIe traffic from every step).  acc(k, c0+col, slab) += w * src(k, col, slab)
+// for a chunk of `cc` columns of a mesh of `nC` columns; kmax != NULL restricts the update to
+// active cells (k < kmax[col], col < nColumns) for diagnostics the reference leaves undefined elsewhere.
+cudaError_t launch_accumulate(const double *src, double *acc, int nL, int cc, int nC, int c0, int nSlabs,
+                              const int *kmax, int nColumns, double w, cudaStream_t s);
+cudaError_t launch_scale(double *a, size_t n, double w, cudaStream_t s);
+
 // ---- inventory: sum_col sum_k tend(n)*dz over active cells (+ sums of per-column
 // diagnostics).  Stage 1 is fused into the source-sink kernels (block partials); stage 2:
 struct InventoryFoldArgs {

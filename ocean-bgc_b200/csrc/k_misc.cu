@@ -477,6 +477,24 @@ transpose_kernel(const double *__restrict__ src, double *__restrict__ dst, int R
   }
 }
 
+// ---------------------------------------------------------------- diagnostics accumulation
+__global__ void __launch_bounds__(256)
+accumulate_kernel(const double *__restrict__ src, double *__restrict__ acc, int nL, int cc, int nC, int c0,
+                  const int *__restrict__ kmax, int nColumns, double w) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = blockIdx.y, slab = blockIdx.z;
+  if (col >= cc) return;
+  if (kmax && !(col < nColumns && k < kmax[col])) return;
+  const size_t is = (size_t)col + (size_t)cc * ((size_t)k + (size_t)nL * slab);
+  const size_t ia = (size_t)(c0 + col) + (size_t)nC * ((size_t)k + (size_t)nL * slab);
+  acc[ia] += w * src[is];
+}
+__global__ void __launch_bounds__(256)
+scale_kernel(double *a, size_t n, double w) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] *= w;
+}
+
 // ---------------------------------------------------------------- inventory
 // Stage 1 of the inventory reduction is fused into the source-sink kernels: every block
 // writes its partial sums, [nParts][nGroups][kInvGroup].  Stage 2 below adds the partials
@@ -560,6 +578,20 @@ cudaError_t launch_transpose(const double *src, double *dst, int R, int C, int n
   dim3 grid(cdiv((size_t)R, 32), cdiv((size_t)C, 32), (unsigned)nSlabs);
   if (grid.y > 65535u || grid.z > 65535u) return cudaErrorInvalidConfiguration;
   transpose_kernel<<<grid, 256, 0, s>>>(src, dst, R, C);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_accumulate(const double *src, double *acc, int nL, int cc, int nC, int c0, int nSlabs,
+                              const int *kmax, int nColumns, double w, cudaStream_t s) {
+  if (nL <= 0 || cc <= 0 || nSlabs <= 0) return cudaSuccess;
+  dim3 grid(cdiv((size_t)cc, 256), (unsigned)nL, (unsigned)nSlabs);
+  if (grid.y > 65535u || grid.z > 65535u) return cudaErrorInvalidConfiguration;
+  accumulate_kernel<<<grid, 256, 0, s>>>(src, acc, nL, cc, nC, c0, kmax, nColumns, w);
+  return cudaGetLastError();
+}
+cudaError_t launch_scale(double *a, size_t n, double w, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  scale_kernel<<<cdiv(n, 256), 256, 0, s>>>(a, n, w);
   return cudaGetLastError();
 }
 

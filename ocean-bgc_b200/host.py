@@ -36,6 +36,7 @@ ABI_SYMBOLS = [
     "bgc_host_register", "bgc_host_unregister", "bgc_layout_to_soa", "bgc_layout_to_fortran",
     "bgc_timing_enable", "bgc_timing_reset", "bgc_timing_get", "bgc_kernel_name",
     "bgc_ctx_set_deferred_join", "bgc_carbonate_join", "bgc_ctx_set_concurrency",
+    "bgc_diag_accumulate_enable", "bgc_diag_flush",
 ]
 
 
@@ -134,6 +135,20 @@ class Context:
 
     def set_concurrency(self, on=True):
         check(self.L, self.L.bgc_ctx_set_concurrency(self.ptr, C.c_int(int(on))))
+
+    def diag_accumulate(self, on=True):
+        """Host-layout calls add their diagnostics into device accumulators instead of downloading
+        them (bgc_b200.h, "Diagnostics accumulation")."""
+        check(self.L, self.L.bgc_diag_accumulate_enable(self.ptr, C.c_int(int(on))))
+
+    def diag_flush(self, bgc=None, dms=None, macros=None, scale=1.0, reset=True):
+        """Download scale * accumulated sums into the diag arrays of the given host containers."""
+        ref = bgc or dms or macros
+        nL, nC = ref.nLevelsMax, ref.nColumnsMax
+        keep = [x.c_diag(True) if x is not None else None for x in (bgc, dms, macros)]
+        args = [C.byref(k) if k is not None else None for k in keep]
+        check(self.L, self.L.bgc_diag_flush(self.ptr, args[0], args[1], args[2], C.c_int(nL), C.c_int(nC),
+                                            C.c_double(scale), C.c_int(int(reset))))
 
     def carbonate_join(self):
         check(self.L, self.L.bgc_carbonate_join(self.ptr))

@@ -332,6 +332,47 @@ def test_deferred_carbonate_join_gives_the_same_bits():
     ctx.close()
 
 
+def test_device_side_diagnostics_accumulation(monkeypatch):
+    """bgc_diag_accumulate_enable: host-layout calls keep returning tendencies every step but
+    add the diagnostics into device accumulators; bgc_diag_flush returns scale * sum.  Must equal
+    the average of the per-step diagnostics of the plain calls (several chunks, ragged columns)."""
+    monkeypatch.setenv("BGC_HOST_CHUNK_COLUMNS", "64")
+    nL, nC, nCols, steps = 30, 200, 190, 3
+    ctx, parms = _ctx(nL, nC)
+    cols, dms, mac = parity.make_bgc(nL, nC, parms, nColumns=nCols, ragged=True, with_dms=True, with_macros=True)
+    act = _active(dms)
+    # plain calls: per-step diagnostics (PH_PREV evolves cold -> warm, so the steps differ)
+    a, ad, am = cols.copy(), dms.copy(), mac.copy()
+    sums, tend_steps = {}, []
+    for _ in range(steps):
+        host.BGC_SourceSink(ctx, a); host.DMS_SourceSink(ctx, ad); host.MACROS_SourceSink(ctx, am)
+        tend_steps.append(a.BGC_tendencies.copy())
+        for pre, c_ in (("b.", a), ("d.", ad), ("m.", am)):
+            for n, v in c_.diag.items():
+                w = v if pre == "b." else np.where(act, v, 0.0)
+                sums[pre + n] = sums.get(pre + n, 0.0) + w
+    # accumulating calls
+    b, bd, bm = cols.copy(), dms.copy(), mac.copy()
+    for c_ in (b, bd, bm):
+        for v in c_.diag.values():
+            v[...] = -5.0
+    ctx.diag_accumulate(True)
+    for i in range(steps):
+        host.BGC_SourceSink(ctx, b); host.DMS_SourceSink(ctx, bd); host.MACROS_SourceSink(ctx, bm)
+        assert np.array_equal(b.BGC_tendencies, tend_steps[i])          # tendencies still come back every step
+        assert np.all(b.diag["diag_PAR_avg"] == -5.0)                   # the caller's diagnostics are not touched
+    ctx.diag_flush(b, bd, bm, scale=1.0 / steps, reset=True)
+    ctx.diag_accumulate(False)
+    never = ("diag_POC_ACCUM", "diag_DONr_remin", "diag_DOPr_remin")
+    for pre, c_ in (("b.", b), ("d.", bd), ("m.", bm)):
+        for n, v in c_.diag.items():
+            if n in never:
+                assert np.all(v == -5.0), n
+                continue
+            assert parity.nerr(v, sums[pre + n] / steps) <= 1e-14, (pre, n)
+    ctx.close()
+
+
 # ------------------------------------------------------------------ inventory
 def test_inventory_vector_matches_the_outputs():
     nL, nC, nCols = 36, 514, 500
