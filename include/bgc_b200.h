@@ -398,6 +398,20 @@ int bgc_layout_to_soa(bgc_ctx *ctx, const double *dev_fortran, double *dev_soa,
 int bgc_layout_to_fortran(bgc_ctx *ctx, const double *dev_soa, double *dev_fortran,
                           int nLevelsMax, int nColumnsMax, int nSlabs);
 
+/* MPAS tracer layout (extension).  MPAS-Ocean stores a tracer group
+ * as T(iTracer, k, iCell), tracer index fastest.  These stream-ordered device kernels move such
+ * an array to / from the library's SoA layout without the (k,col,tracer) intermediate of the
+ * reference API.  slot_of_tracer[n] (n = 0 .. nTracers-1) is the 1-based SoA slot that MPAS
+ * tracer n feeds (0 = tracer not used).  bgc_layout_soa_to_mpas computes
+ *     T(n,k,cell) = beta * T(n,k,cell) + alpha * soa(cell,k,slot[n]);
+ * with soa = the tendency array, alpha = dt and beta = 1 it is the explicit tracer update fused
+ * with the layout change (beta = 0 just converts).  All pointers are device pointers. */
+int bgc_layout_mpas_to_soa(bgc_ctx *ctx, const double *dev_mpas, double *dev_soa, int nTracers,
+                           const int *slot_of_tracer, int nLevelsMax, int nColumnsMax);
+int bgc_layout_soa_to_mpas(bgc_ctx *ctx, const double *dev_soa, double *dev_mpas, int nTracers,
+                           const int *slot_of_tracer, int nLevelsMax, int nColumnsMax,
+                           double alpha, double beta);
+
 #ifdef __cplusplus
 }
 #endif

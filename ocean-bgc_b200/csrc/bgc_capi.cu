@@ -1235,6 +1235,36 @@ extern "C" int macros_source_sink(bgc_ctx *c, const MacrosInput *in, MacrosOutpu
   });
 }
 
+// ------------------------------------------------------------------ MPAS tracer layout
+static int mpas_map(int nT, const int *slot, bgc::MpasMap *m) {
+  if (nT < 1 || nT > bgc::kMpasMaxTracers || !slot) return fail(BGC_ERR_ARG, "MPAS layout: 1..%d tracers and a slot map are required", bgc::kMpasMaxTracers);
+  m->nT = nT;
+  for (int n = 0; n < bgc::kMpasMaxTracers; ++n) m->slot[n] = (n < nT) ? slot[n] : 0;
+  for (int n = 0; n < nT; ++n)
+    if (slot[n] < 0 || slot[n] > bgc::kMpasMaxTracers) return fail(BGC_ERR_ARG, "MPAS layout: slot %d of tracer %d out of range", slot[n], n);
+  return BGC_OK;
+}
+extern "C" int bgc_layout_mpas_to_soa(bgc_ctx *c, const double *mpas, double *soa, int nT, const int *slot, int nL,
+                                      int nC) {
+  RC(use_device(c));
+  if (!mpas || !soa) return fail(BGC_ERR_ARG, "bgc_layout_mpas_to_soa: null array");
+  RC(check_dims(c, nL, nC, nC));
+  bgc::MpasMap m;
+  RC(mpas_map(nT, slot, &m));
+  LAUNCH(BGC_K_TRANSPOSE, 1, bgc::launch_mpas_to_soa(mpas, soa, m, nL, nC, c->stream));
+  return BGC_OK;
+}
+extern "C" int bgc_layout_soa_to_mpas(bgc_ctx *c, const double *soa, double *mpas, int nT, const int *slot, int nL,
+                                      int nC, double alpha, double beta) {
+  RC(use_device(c));
+  if (!mpas || !soa) return fail(BGC_ERR_ARG, "bgc_layout_soa_to_mpas: null array");
+  RC(check_dims(c, nL, nC, nC));
+  bgc::MpasMap m;
+  RC(mpas_map(nT, slot, &m));
+  LAUNCH(BGC_K_TRANSPOSE, 1, bgc::launch_soa_to_mpas(soa, mpas, m, nL, nC, alpha, beta, c->stream));
+  return BGC_OK;
+}
+
 // ------------------------------------------------------------------ diagnostics accumulation
 extern "C" int bgc_diag_accumulate_enable(bgc_ctx *c, int enable) {
   RC(use_device(c));

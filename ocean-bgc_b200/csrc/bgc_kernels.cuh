@@ -129,6 +129,17 @@ cudaError_t launch_macros_cells(const MacrosArgs &a, cudaStream_t s);
 cudaError_t launch_transpose(const double *src, double *dst, int rows_fast_src, int cols_slow_src,
                              int nSlabs, cudaStream_t s);
 
+// ---- MPAS tracer layout (tracer index fastest: T(n, k, cell) at n + nT*(k + nL*cell)) <-> SoA
+// (the caller side of the boundary).  slot[n] = 1-based SoA slot of MPAS
+// tracer n, 0 = not part of this tracer group.
+constexpr int kMpasMaxTracers = 64;
+struct MpasMap { int nT; int slot[kMpasMaxTracers]; };
+cudaError_t launch_mpas_to_soa(const double *mpas, double *soa, const MpasMap &m, int nL, int nC, cudaStream_t s);
+// mpas(n,k,cell) = beta * mpas(n,k,cell) + alpha * soa(cell,k,slot[n]); alpha = dt, beta = 1 is the
+// explicit tracer update fused with the layout change
+cudaError_t launch_soa_to_mpas(const double *soa, double *mpas, const MpasMap &m, int nL, int nC, double alpha,
+                               double beta, cudaStream_t s);
+
 // ---- on-device accumulation of diagnostics (the host time-averages the
 // diagnostics for history files; accumulating on the device and downloading at output
 // frequency removes their PCIe traffic from every step).  acc(k, c0+col, slab) += w * src(k, col, slab)

@@ -7,6 +7,7 @@
 //
 // Both source-sink kernels are HBM-bound streaming kernels: each input element
 // is read once and each output element written once, coalesced.
+#include <stdlib.h>
 #include "bgc_kernels.cuh"
 #include "bgc_math.cuh"
 #include "bgc_reduce.cuh"
@@ -477,6 +478,56 @@ transpose_kernel(const double *__restrict__ src, double *__restrict__ dst, int R
   }
 }
 
+// ---------------------------------------------------------------- MPAS tracer layout
+// One block = KB levels x 32 cells x all tracers through a padded shared-memory tile.  In the MPAS
+// array the (tracer, level) pairs of one cell are contiguous, so the block moves 32 runs of
+// KB*nT doubles on that side (~2 KB each) and runs of 32 consecutive cells on the SoA side.
+template <bool TO_SOA>
+__global__ void __launch_bounds__(256)
+mpas_layout_kernel(const double *__restrict__ src, double *__restrict__ dst, const __grid_constant__ MpasMap M,
+                   int nL, int nC, int KB, double alpha, double beta) {
+  extern __shared__ double tile[];   // [32][KB*nT + 1]
+  const int c0 = blockIdx.x * 32, k0 = blockIdx.y * KB, nT = M.nT;
+  const int ncell = min(32, nC - c0), nk = min(KB, nL - k0);
+  const int run = nk * nT, pitch = KB * nT + 1;
+  const size_t nLnC = (size_t)nL * (size_t)nC;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  // MPAS side: warp w takes cells w, w + nw, ...; its lanes walk the cell's contiguous run.
+  // SoA side: warp w takes (level, tracer) pairs; its lanes are the 32 cells.  No divisions.
+  if (TO_SOA) {
+    for (int c = w; c < ncell; c += nw) {
+      const double *p = src + (size_t)nT * ((size_t)k0 + (size_t)nL * (size_t)(c0 + c));
+      for (int r = lane; r < run; r += 32) tile[c * pitch + r] = p[r];
+    }
+    __syncthreads();
+    if (lane < ncell) {
+      for (int kk = 0; kk < nk; ++kk)
+        for (int n = w; n < nT; n += nw)
+          if (M.slot[n] > 0)
+            dst[(size_t)(c0 + lane) + (size_t)nC * (size_t)(k0 + kk) + (size_t)(M.slot[n] - 1) * nLnC] =
+                tile[lane * pitch + kk * nT + n];
+    }
+  } else {
+    if (lane < ncell) {
+      for (int kk = 0; kk < nk; ++kk)
+        for (int n = w; n < nT; n += nw)
+          if (M.slot[n] > 0)
+            tile[lane * pitch + kk * nT + n] =
+                src[(size_t)(c0 + lane) + (size_t)nC * (size_t)(k0 + kk) + (size_t)(M.slot[n] - 1) * nLnC];
+    }
+    __syncthreads();
+    for (int c = w; c < ncell; c += nw) {
+      double *p = dst + (size_t)nT * ((size_t)k0 + (size_t)nL * (size_t)(c0 + c));
+      for (int r = lane, n = lane % nT; r < run; r += 32, n = (n + 32) % nT) {
+        if (M.slot[n] > 0) {
+          const double v = tile[c * pitch + r];
+          p[r] = (beta == 0.0) ? alpha * v : beta * p[r] + alpha * v;
+        }
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------- diagnostics accumulation
 __global__ void __launch_bounds__(256)
 accumulate_kernel(const double *__restrict__ src, double *__restrict__ acc, int nL, int cc, int nC, int c0,
@@ -579,6 +630,36 @@ cudaError_t launch_transpose(const double *src, double *dst, int R, int C, int n
   if (grid.y > 65535u || grid.z > 65535u) return cudaErrorInvalidConfiguration;
   transpose_kernel<<<grid, 256, 0, s>>>(src, dst, R, C);
   return cudaGetLastError();
+}
+
+// levels per block (measured on B200, 30 tracers: 4 is best towards SoA, 2 for the read-modify-
+// write direction; larger tiles lose more to the load/store phase split than they gain in DRAM locality)
+static int mpas_levels_per_block(int nT, bool to_soa) {
+  const int cap = to_soa ? 4 : 2;
+  int kb = (96 * 1024 / 8 / 32 - 1) / nT;
+  return kb < 1 ? 1 : (kb > cap ? cap : kb);
+}
+template <bool TO_SOA>
+static cudaError_t launch_mpas_layout(const double *src, double *dst, const MpasMap &m, int nL, int nC, double alpha,
+                                      double beta, cudaStream_t s) {
+  if (nL <= 0 || nC <= 0 || m.nT <= 0) return cudaSuccess;
+  if (m.nT > kMpasMaxTracers) return cudaErrorInvalidValue;
+  const int KB = mpas_levels_per_block(m.nT, TO_SOA);
+  const size_t smem = (size_t)32 * (KB * m.nT + 1) * sizeof(double);
+  auto kern = mpas_layout_kernel<TO_SOA>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  dim3 grid(cdiv((size_t)nC, 32), cdiv((size_t)nL, (size_t)KB));
+  if (grid.y > 65535u) return cudaErrorInvalidConfiguration;
+  kern<<<grid, 256, smem, s>>>(src, dst, m, nL, nC, KB, alpha, beta);
+  return cudaGetLastError();
+}
+cudaError_t launch_mpas_to_soa(const double *mpas, double *soa, const MpasMap &m, int nL, int nC, cudaStream_t s) {
+  return launch_mpas_layout<true>(mpas, soa, m, nL, nC, 1.0, 0.0, s);
+}
+cudaError_t launch_soa_to_mpas(const double *soa, double *mpas, const MpasMap &m, int nL, int nC, double alpha,
+                               double beta, cudaStream_t s) {
+  return launch_mpas_layout<false>(soa, mpas, m, nL, nC, alpha, beta, s);
 }
 
 cudaError_t launch_accumulate(const double *src, double *acc, int nL, int cc, int nC, int c0, int nSlabs,

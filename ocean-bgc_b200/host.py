@@ -36,7 +36,7 @@ ABI_SYMBOLS = [
     "bgc_host_register", "bgc_host_unregister", "bgc_layout_to_soa", "bgc_layout_to_fortran",
     "bgc_timing_enable", "bgc_timing_reset", "bgc_timing_get", "bgc_kernel_name",
     "bgc_ctx_set_deferred_join", "bgc_carbonate_join", "bgc_ctx_set_concurrency",
-    "bgc_diag_accumulate_enable", "bgc_diag_flush",
+    "bgc_diag_accumulate_enable", "bgc_diag_flush", "bgc_layout_mpas_to_soa", "bgc_layout_soa_to_mpas",
 ]
 
 
@@ -149,6 +149,19 @@ class Context:
         args = [C.byref(k) if k is not None else None for k in keep]
         check(self.L, self.L.bgc_diag_flush(self.ptr, args[0], args[1], args[2], C.c_int(nL), C.c_int(nC),
                                             C.c_double(scale), C.c_int(int(reset))))
+
+    def mpas_to_soa(self, dev_mpas, dev_soa, slot_of_tracer, nL, nC):
+        """T(tracer,k,cell) device array -> SoA device array (raw device addresses)."""
+        m = (C.c_int * len(slot_of_tracer))(*[int(x) for x in slot_of_tracer])
+        check(self.L, self.L.bgc_layout_mpas_to_soa(self.ptr, abi.raw_dptr(dev_mpas), abi.raw_dptr(dev_soa),
+                                                    C.c_int(len(slot_of_tracer)), m, C.c_int(nL), C.c_int(nC)))
+
+    def soa_to_mpas(self, dev_soa, dev_mpas, slot_of_tracer, nL, nC, alpha=1.0, beta=0.0):
+        """T(n,k,cell) = beta*T + alpha*soa(cell,k,slot[n]): layout change fused with the tracer update."""
+        m = (C.c_int * len(slot_of_tracer))(*[int(x) for x in slot_of_tracer])
+        check(self.L, self.L.bgc_layout_soa_to_mpas(self.ptr, abi.raw_dptr(dev_soa), abi.raw_dptr(dev_mpas),
+                                                    C.c_int(len(slot_of_tracer)), m, C.c_int(nL), C.c_int(nC),
+                                                    C.c_double(alpha), C.c_double(beta)))
 
     def carbonate_join(self):
         check(self.L, self.L.bgc_carbonate_join(self.ptr))

@@ -373,6 +373,44 @@ def test_device_side_diagnostics_accumulation(monkeypatch):
     ctx.close()
 
 
+def test_mpas_tracer_layout_adapter():
+    """bgc_layout_mpas_to_soa / bgc_layout_soa_to_mpas: T(tracer,k,cell) <-> SoA with a slot map,
+    the reverse direction fused with the explicit tracer update (alpha = dt, beta = 1)."""
+    import torch
+    nT, nL, nC, nS = 33, 7, 1000 + 13, 30
+    ctx, _ = _ctx(nL, nC)
+    g = torch.Generator(device="cpu").manual_seed(7)
+    mpas = torch.rand((nC, nL, nT), generator=g, dtype=torch.float64).cuda()      # (cell,k,n): n fastest
+    perm = torch.randperm(nS, generator=g).tolist()
+    slot = [0, 0, 0] + [p + 1 for p in perm]                                      # three tracers of another group
+    soa = torch.full((nS, nL, nC), -1.0, dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    ctx.mpas_to_soa(mpas.data_ptr(), soa.data_ptr(), slot, nL, nC)
+    ctx.synchronize()
+    for n in range(nT):
+        if slot[n]:
+            assert torch.equal(soa[slot[n] - 1], mpas[:, :, n].T.contiguous()), n
+    # tendencies in SoA -> tracer update in MPAS layout
+    tend = torch.rand((nS, nL, nC), generator=g, dtype=torch.float64).cuda()
+    dt = 1800.0
+    want = mpas.clone()
+    for n in range(nT):
+        if slot[n]:
+            want[:, :, n] = want[:, :, n] + dt * tend[slot[n] - 1].T   # one multiply and one add: fma or not
+    got = mpas.clone()
+    torch.cuda.synchronize()
+    ctx.soa_to_mpas(tend.data_ptr(), got.data_ptr(), slot, nL, nC, alpha=dt, beta=1.0)
+    ctx.synchronize()
+    assert torch.equal(got[:, :, :3], mpas[:, :, :3])                  # tracers outside the group untouched
+    assert (got - want).abs().max().item() <= 1e-12 * want.abs().max().item()
+    # beta = 0: pure layout change, bit exact round trip
+    back = torch.zeros_like(mpas)
+    ctx.soa_to_mpas(soa.data_ptr(), back.data_ptr(), slot, nL, nC, alpha=1.0, beta=0.0)
+    ctx.synchronize()
+    assert torch.equal(back[:, :, 3:], mpas[:, :, 3:])
+    ctx.close()
+
+
 # ------------------------------------------------------------------ inventory
 def test_inventory_vector_matches_the_outputs():
     nL, nC, nCols = 36, 514, 500
