@@ -219,6 +219,7 @@ extern "C" int bgc_ctx_create(int device, int nLevelsMax, int nColumnsMax, bgc_c
   {
     int lo = 0, hi = 0;   // the side stream gets the LOWER priority: the sweep's blocks are placed first
     CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    if (const char *v = getenv("BGC_SIDE_PRIORITY")) lo = atoi(v);   // tuning only
     for (int i = 0; i < 2; ++i) {
       CU(cudaStreamCreateWithPriority(&c->side_stream[i], cudaStreamNonBlocking, lo));
       CU(cudaEventCreateWithFlags(&c->fork_event[i], cudaEventDisableTiming));
