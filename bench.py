@@ -523,9 +523,17 @@ def run_e2e(args, pkg, host, ctx, parms, rank, world, local_rank, dev):
         t = torch.empty(int(n), dtype=torch.float64 if dtype == np.float64 else torch.int32, pin_memory=True)
         pinned.append(t)
         return t.numpy()
-    bgc = pkg.BgcColumns(nL, nC, alloc=alloc)
-    dms = pkg.DmsColumns(nL, nC, alloc=alloc)
-    mac = pkg.MacrosColumns(nL, nC, alloc=alloc)
+    while True:   # page-locking tens of GB can fail on a loaded host: halve the sample and say so
+        try:
+            bgc = pkg.BgcColumns(nL, nC, alloc=alloc)
+            dms = pkg.DmsColumns(nL, nC, alloc=alloc)
+            mac = pkg.MacrosColumns(nL, nC, alloc=alloc)
+            break
+        except RuntimeError:
+            pinned.clear()
+            if nC <= 4096:
+                raise
+            nC = max(4096, nC // 2)
     pkg.synth_fill(bgc, dms, mac, bgc_ind=parms.ind, dms_ind=parms.dms_ind, macros_ind=parms.macros_ind,
                    column0=rank * args.columns)
     cells = int(bgc.active_mask().sum())
