@@ -338,7 +338,10 @@ def main():
         host.DMS_SurfaceFluxes(ctx, dms)
         host.MACROS_SourceSink(ctx, mac, True)
         if not args.no_inventory:
-            return ctx.inventory_allreduce()   # join point; NCCL all-reduce (N > 1) + 512 B to the host
+            # join point; NCCL all-reduce (N > 1) + 512 B to a page-locked host buffer, stream-ordered:
+            # the host reads the vector after the last step (bgc_inventory_allreduce_end)
+            ctx.inventory_allreduce_begin()
+            return None
         ctx.carbonate_join()
         return None
 
@@ -360,9 +363,11 @@ def main():
     e0.record(stream)
     inv = None
     for _ in range(args.steps):
-        inv = step()
+        step()
     e1.record(stream)
     barrier()
+    if not args.no_inventory:
+        inv = ctx.inventory_allreduce_end()
     clocks = sampler.stop()
     ms = e0.elapsed_time(e1)
     launches = ctx.launch_count()

@@ -368,7 +368,11 @@ int bgc_inventory_device_ptr(bgc_ctx *ctx, double **dev_ptr);
  * transport (MPI_Bcast in MPAS; torch.distributed in bench.py). */
 int bgc_comm_unique_id(unsigned char id[128]);
 int bgc_comm_init_rank(bgc_ctx *ctx, int nranks, int rank, const unsigned char id[128]);
-int bgc_inventory_allreduce(bgc_ctx *ctx, double out[BGC_INVENTORY_LEN]);
+int bgc_inventory_allreduce(bgc_ctx *ctx, double out[BGC_INVENTORY_LEN]);   /* begin + end */
+/* Stream-ordered form: _begin enqueues the all-reduce and the copy of its 512-byte result to a
+ * page-locked buffer and returns at once; _end waits for that copy (of the latest _begin) only. */
+int bgc_inventory_allreduce_begin(bgc_ctx *ctx);
+int bgc_inventory_allreduce_end(bgc_ctx *ctx, double out[BGC_INVENTORY_LEN]);
 
 /* Diagnostics accumulation for BGC_MEM_HOST_FORTRAN callers (extension).
  * The host model time-averages the ~160 diagnostic arrays for its history files, yet they

@@ -112,6 +112,9 @@ struct bgc_ctx {
   unsigned long long *d_status = nullptr;   // 4 counters
   double *d_inventory = nullptr;            // BGC_INVENTORY_LEN
   bool inventory_on = false;
+  double *h_inventory = nullptr;            // page-locked landing buffer of bgc_inventory_allreduce_begin
+  cudaEvent_t inventory_event = nullptr;
+  bool inventory_pending = false;
   int eco_variant = 0;                      // launch shape of the column sweep (BGC_ECO_VARIANT, tuning only)
   int dms_variant = 0;                      // launch shape of the DMS tile kernel (BGC_DMS_VARIANT, tuning only)
   std::map<std::string, DevBuf> arena;      // persistent device buffers (host-layout mode, scratch)
@@ -245,6 +248,8 @@ extern "C" int bgc_ctx_destroy(bgc_ctx *c) {
   if (c->pipe_stream) cudaStreamSynchronize(c->pipe_stream);
   for (auto &kv : c->arena) if (kv.second.p) cudaFree(kv.second.p);
   cudaFree(c->d_status); cudaFree(c->d_inventory);
+  if (c->h_inventory) cudaFreeHost(c->h_inventory);
+  if (c->inventory_event) cudaEventDestroy(c->inventory_event);
   for (auto &sp : c->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
   for (auto e : c->ev_pool) cudaEventDestroy(e);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -1345,20 +1350,44 @@ extern "C" int bgc_comm_init_rank(bgc_ctx *c, int nranks, int rank, const unsign
   return BGC_OK;
 }
 
-extern "C" int bgc_inventory_allreduce(bgc_ctx *c, double out[BGC_INVENTORY_LEN]) {
+// The all-reduce is stream-ordered: bgc_inventory_allreduce_begin enqueues the NCCL all-reduce
+// (a device copy for a single rank) and the copy of the 512-byte result into a page-locked
+// buffer of the ctx, and returns without waiting; bgc_inventory_allreduce_end waits for that
+// copy only.  A model that consumes the inventory once per output interval keeps issuing
+// steps without a host synchronisation in between.
+extern "C" int bgc_inventory_allreduce_begin(bgc_ctx *c) {
   RC(use_device(c));
-  if (!out) return fail(BGC_ERR_ARG, "null out");
   double *buf = nullptr;
   RC(join_pending(c));
   RC(arena_d(c, "inv_reduced", BGC_INVENTORY_LEN, &buf));
+  if (!c->h_inventory) {
+    CU(cudaHostAlloc((void **)&c->h_inventory, BGC_INVENTORY_LEN * sizeof(double), cudaHostAllocDefault));
+    CU(cudaEventCreateWithFlags(&c->inventory_event, cudaEventDisableTiming));
+  }
   if (c->comm) {
     NC(g_nccl.AllReduce(c->d_inventory, buf, BGC_INVENTORY_LEN, kNcclFloat64, kNcclSum, c->comm, c->stream));
   } else {
     CU(cudaMemcpyAsync(buf, c->d_inventory, BGC_INVENTORY_LEN * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
   }
-  CU(cudaMemcpyAsync(out, buf, BGC_INVENTORY_LEN * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaMemcpyAsync(c->h_inventory, buf, BGC_INVENTORY_LEN * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaEventRecord(c->inventory_event, c->stream));
+  c->inventory_pending = true;
   return BGC_OK;
+}
+
+extern "C" int bgc_inventory_allreduce_end(bgc_ctx *c, double out[BGC_INVENTORY_LEN]) {
+  RC(use_device(c));
+  if (!out) return fail(BGC_ERR_ARG, "null out");
+  if (!c->inventory_pending) return fail(BGC_ERR_ARG, "bgc_inventory_allreduce_end without a begin");
+  CU(cudaEventSynchronize(c->inventory_event));
+  memcpy(out, c->h_inventory, BGC_INVENTORY_LEN * sizeof(double));
+  return BGC_OK;
+}
+
+extern "C" int bgc_inventory_allreduce(bgc_ctx *c, double out[BGC_INVENTORY_LEN]) {
+  if (!out) return fail(BGC_ERR_ARG, "null out");
+  RC(bgc_inventory_allreduce_begin(c));
+  return bgc_inventory_allreduce_end(c, out);
 }
 
 // ------------------------------------------------------------------ host memory, layout helpers

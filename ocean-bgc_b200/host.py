@@ -37,6 +37,7 @@ ABI_SYMBOLS = [
     "bgc_timing_enable", "bgc_timing_reset", "bgc_timing_get", "bgc_kernel_name",
     "bgc_ctx_set_deferred_join", "bgc_carbonate_join", "bgc_ctx_set_concurrency",
     "bgc_diag_accumulate_enable", "bgc_diag_flush", "bgc_layout_mpas_to_soa", "bgc_layout_soa_to_mpas",
+    "bgc_inventory_allreduce_begin", "bgc_inventory_allreduce_end",
 ]
 
 
@@ -204,6 +205,14 @@ class Context:
         out = (C.c_double * abi.BGC_INVENTORY_LEN)()
         check(self.L, self.L.bgc_inventory_allreduce(self.ptr, out))
         return np.array(out[:])
+
+    def inventory_allreduce_begin(self):
+        check(self.L, self.L.bgc_inventory_allreduce_begin(self.ptr))
+
+    def inventory_allreduce_end(self):
+        out = (C.c_double * abi.BGC_INVENTORY_LEN)()
+        check(self.L, self.L.bgc_inventory_allreduce_end(self.ptr, out))
+        return np.array(out[:], dtype=np.float64)
 
     def comm_unique_id(self):
         buf = (C.c_ubyte * 128)()

@@ -446,6 +446,10 @@ def test_inventory_vector_matches_the_outputs():
     ctx.inventory_reset()
     host.BGC_SourceSink(ctx, cols)
     assert np.array_equal(ctx.inventory_get(), inv3)
+    # single rank: the all-reduce is the identity; the stream-ordered form returns the same vector
+    assert np.array_equal(ctx.inventory_allreduce(), inv3)
+    ctx.inventory_allreduce_begin()
+    assert np.array_equal(ctx.inventory_allreduce_end(), inv3)
     ctx.close()
 
 
