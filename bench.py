@@ -193,6 +193,7 @@ def workload_config(args, world):
             "cache": "inputs+outputs per step (%.1f GB per GPU) far exceed the 126 MB L2; no flush needed"
                      % (args.columns * args.levels * B_API / 1e9),
             "ph_brackets": "warm (PH_PREV from the untimed cold pass), as in a running model",
+            "cuda_graph": not getattr(args, "no_graph", False),
             "carbonate_join": "strict (inside BGC_SourceSink)" if getattr(args, "strict_join", False)
                               else "deferred to the end of the step (bgc_ctx_set_deferred_join)"}
 
@@ -288,6 +289,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-inventory", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="issue every step call by call instead of replaying a CUDA graph")
     ap.add_argument("--strict-join", action="store_true",
                     help="join the carbonate side stream inside every BGC_SourceSink call (library default)")
     args = ap.parse_args()
@@ -356,6 +358,15 @@ def main():
     for _ in range(max(args.warmup, 25)):   # >= W warm-up steps; at least ~0.2 s so the clock sampler sees the load
         step()
     barrier()
+    # one step = ~15 dependent launches on two streams: captured once, replayed as a CUDA graph
+    graph = None
+    if not args.no_graph:
+        ctx.graph_capture_begin()
+        step()
+        graph = ctx.graph_capture_end()
+        for _ in range(3):
+            ctx.graph_launch(graph)
+    barrier()
     ctx.timing_reset()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -363,7 +374,10 @@ def main():
     e0.record(stream)
     inv = None
     for _ in range(args.steps):
-        step()
+        if graph is not None:
+            ctx.graph_launch(graph)
+        else:
+            step()
     e1.record(stream)
     barrier()
     if not args.no_inventory:

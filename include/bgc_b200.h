@@ -402,6 +402,19 @@ int bgc_layout_to_soa(bgc_ctx *ctx, const double *dev_fortran, double *dev_soa,
 int bgc_layout_to_fortran(bgc_ctx *ctx, const double *dev_soa, double *dev_fortran,
                           int nLevelsMax, int nColumnsMax, int nSlabs);
 
+/* CUDA graphs.  Everything the BGC_MEM_DEVICE_SOA entry points enqueue between _begin and _end
+ * (on the ctx stream and the library's side stream) is captured into one graph instead of
+ * being executed; bgc_graph_launch replays it on the ctx stream.  The same calls must have run
+ * once before (the device arena may not grow and per-kernel timing must be off while
+ * capturing); the captured pointers and extents are baked in.  Synchronising entry points
+ * (bgc_ctx_synchronize, bgc_inventory_get, bgc_inventory_allreduce[_end], bgc_get_status, any
+ * BGC_MEM_HOST_FORTRAN call) must not be called while capturing. */
+typedef struct bgc_graph bgc_graph;
+int bgc_graph_capture_begin(bgc_ctx *ctx);
+int bgc_graph_capture_end(bgc_ctx *ctx, bgc_graph **out);
+int bgc_graph_launch(bgc_ctx *ctx, bgc_graph *graph);
+int bgc_graph_destroy(bgc_graph *graph);
+
 /* MPAS tracer layout (extension).  MPAS-Ocean stores a tracer group
  * as T(iTracer, k, iCell), tracer index fastest.  These stream-ordered device kernels move such
  * an array to / from the library's SoA layout without the (k,col,tracer) intermediate of the

@@ -113,8 +113,9 @@ struct bgc_ctx {
   double *d_inventory = nullptr;            // BGC_INVENTORY_LEN
   bool inventory_on = false;
   double *h_inventory = nullptr;            // page-locked landing buffer of bgc_inventory_allreduce_begin
-  cudaEvent_t inventory_event = nullptr;
   bool inventory_pending = false;
+  bool capturing = false;                   // between bgc_graph_capture_begin and _end
+  unsigned long long capture_base[BGC_KERNEL_ID_COUNT] = {0};
   int eco_variant = 0;                      // launch shape of the column sweep (BGC_ECO_VARIANT, tuning only)
   int dms_variant = 0;                      // launch shape of the DMS tile kernel (BGC_DMS_VARIANT, tuning only)
   std::map<std::string, DevBuf> arena;      // persistent device buffers (host-layout mode, scratch)
@@ -183,6 +184,8 @@ static int join_pending(bgc_ctx *c) {
 
 static int arena_get(bgc_ctx *c, const std::string &key, size_t bytes, void **out) {
   DevBuf &b = c->arena[key];
+  if (b.bytes < bytes && c->capturing)
+    return fail(BGC_ERR_ARG, "device arena would grow during graph capture (%s): run the same calls once before capturing", key.c_str());
   if (b.bytes < bytes) {
     if (b.p) CU(cudaFree(b.p));
     b.p = nullptr; b.bytes = 0;
@@ -249,7 +252,6 @@ extern "C" int bgc_ctx_destroy(bgc_ctx *c) {
   for (auto &kv : c->arena) if (kv.second.p) cudaFree(kv.second.p);
   cudaFree(c->d_status); cudaFree(c->d_inventory);
   if (c->h_inventory) cudaFreeHost(c->h_inventory);
-  if (c->inventory_event) cudaEventDestroy(c->inventory_event);
   for (auto &sp : c->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
   for (auto e : c->ev_pool) cudaEventDestroy(e);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -1241,6 +1243,65 @@ extern "C" int macros_source_sink(bgc_ctx *c, const MacrosInput *in, MacrosOutpu
   });
 }
 
+// ------------------------------------------------------------------ CUDA graphs
+// A model step is a fixed sequence of ~15 dependent launches on two streams; replaying it
+// as one CUDA graph removes the launch gaps between them.  Everything the BGC_MEM_DEVICE_SOA
+// entry points enqueue is capturable once the ctx is warm (no arena growth, tables uploaded).
+struct bgc_graph {
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  unsigned long long launches[BGC_KERNEL_ID_COUNT] = {0};   // kernel launches one replay stands for
+};
+
+extern "C" int bgc_graph_capture_begin(bgc_ctx *c) {
+  RC(use_device(c));
+  if (c->capturing) return fail(BGC_ERR_ARG, "bgc_graph_capture_begin: already capturing");
+  if (c->timing_on) return fail(BGC_ERR_ARG, "bgc_graph_capture_begin: disable per-kernel timing first");
+  RC(join_pending(c));
+  CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed));
+  c->capturing = true;
+  for (int i = 0; i < BGC_KERNEL_ID_COUNT; ++i) c->capture_base[i] = c->launches[i];
+  return BGC_OK;
+}
+
+extern "C" int bgc_graph_capture_end(bgc_ctx *c, bgc_graph **out) {
+  RC(use_device(c));
+  if (!c->capturing || !out) return fail(BGC_ERR_ARG, "bgc_graph_capture_end: not capturing / null out");
+  int rc = join_pending(c);   // a deferred carbonate join must close inside the graph
+  c->capturing = false;
+  cudaGraph_t g = nullptr;
+  cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+  if (rc != BGC_OK) { if (g) cudaGraphDestroy(g); return rc; }
+  if (e != cudaSuccess) return fail(BGC_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
+  bgc_graph *bg = new bgc_graph();
+  bg->graph = g;
+  e = cudaGraphInstantiate(&bg->exec, g, 0);
+  if (e != cudaSuccess) { cudaGraphDestroy(g); delete bg; return fail(BGC_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e)); }
+  for (int i = 0; i < BGC_KERNEL_ID_COUNT; ++i) {
+    bg->launches[i] = c->launches[i] - c->capture_base[i];
+    c->launches[i] = c->capture_base[i];   // captured, not executed: counted per replay instead
+  }
+  *out = bg;
+  return BGC_OK;
+}
+
+extern "C" int bgc_graph_launch(bgc_ctx *c, bgc_graph *g) {
+  RC(use_device(c));
+  if (!g || !g->exec) return fail(BGC_ERR_ARG, "bgc_graph_launch: null graph");
+  RC(join_pending(c));
+  CU(cudaGraphLaunch(g->exec, c->stream));
+  for (int i = 0; i < BGC_KERNEL_ID_COUNT; ++i) c->launches[i] += g->launches[i];
+  return BGC_OK;
+}
+
+extern "C" int bgc_graph_destroy(bgc_graph *g) {
+  if (!g) return BGC_OK;
+  if (g->exec) cudaGraphExecDestroy(g->exec);
+  if (g->graph) cudaGraphDestroy(g->graph);
+  delete g;
+  return BGC_OK;
+}
+
 // ------------------------------------------------------------------ MPAS tracer layout
 static int mpas_map(int nT, const int *slot, bgc::MpasMap *m) {
   if (nT < 1 || nT > bgc::kMpasMaxTracers || !slot) return fail(BGC_ERR_ARG, "MPAS layout: 1..%d tracers and a slot map are required", bgc::kMpasMaxTracers);
@@ -1360,17 +1421,14 @@ extern "C" int bgc_inventory_allreduce_begin(bgc_ctx *c) {
   double *buf = nullptr;
   RC(join_pending(c));
   RC(arena_d(c, "inv_reduced", BGC_INVENTORY_LEN, &buf));
-  if (!c->h_inventory) {
+  if (!c->h_inventory)
     CU(cudaHostAlloc((void **)&c->h_inventory, BGC_INVENTORY_LEN * sizeof(double), cudaHostAllocDefault));
-    CU(cudaEventCreateWithFlags(&c->inventory_event, cudaEventDisableTiming));
-  }
   if (c->comm) {
     NC(g_nccl.AllReduce(c->d_inventory, buf, BGC_INVENTORY_LEN, kNcclFloat64, kNcclSum, c->comm, c->stream));
   } else {
     CU(cudaMemcpyAsync(buf, c->d_inventory, BGC_INVENTORY_LEN * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
   }
   CU(cudaMemcpyAsync(c->h_inventory, buf, BGC_INVENTORY_LEN * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaEventRecord(c->inventory_event, c->stream));
   c->inventory_pending = true;
   return BGC_OK;
 }
@@ -1379,7 +1437,7 @@ extern "C" int bgc_inventory_allreduce_end(bgc_ctx *c, double out[BGC_INVENTORY_
   RC(use_device(c));
   if (!out) return fail(BGC_ERR_ARG, "null out");
   if (!c->inventory_pending) return fail(BGC_ERR_ARG, "bgc_inventory_allreduce_end without a begin");
-  CU(cudaEventSynchronize(c->inventory_event));
+  CU(cudaStreamSynchronize(c->stream));   // (also correct when the _begin was replayed from a captured graph)
   memcpy(out, c->h_inventory, BGC_INVENTORY_LEN * sizeof(double));
   return BGC_OK;
 }

@@ -38,6 +38,7 @@ ABI_SYMBOLS = [
     "bgc_ctx_set_deferred_join", "bgc_carbonate_join", "bgc_ctx_set_concurrency",
     "bgc_diag_accumulate_enable", "bgc_diag_flush", "bgc_layout_mpas_to_soa", "bgc_layout_soa_to_mpas",
     "bgc_inventory_allreduce_begin", "bgc_inventory_allreduce_end",
+    "bgc_graph_capture_begin", "bgc_graph_capture_end", "bgc_graph_launch", "bgc_graph_destroy",
 ]
 
 
@@ -213,6 +214,20 @@ class Context:
         out = (C.c_double * abi.BGC_INVENTORY_LEN)()
         check(self.L, self.L.bgc_inventory_allreduce_end(self.ptr, out))
         return np.array(out[:], dtype=np.float64)
+
+    def graph_capture_begin(self):
+        check(self.L, self.L.bgc_graph_capture_begin(self.ptr))
+
+    def graph_capture_end(self):
+        g = C.c_void_p()
+        check(self.L, self.L.bgc_graph_capture_end(self.ptr, C.byref(g)))
+        return g
+
+    def graph_launch(self, g):
+        check(self.L, self.L.bgc_graph_launch(self.ptr, g))
+
+    def graph_destroy(self, g):
+        check(self.L, self.L.bgc_graph_destroy(g))
 
     def comm_unique_id(self):
         buf = (C.c_ubyte * 128)()

@@ -411,6 +411,51 @@ def test_mpas_tracer_layout_adapter():
     ctx.close()
 
 
+def test_cuda_graph_replay_gives_the_same_bits():
+    """bgc_graph_capture_begin/_end + bgc_graph_launch: one captured step (two streams, deferred
+    carbonate join, inventory) replayed twice equals the same step issued call by call."""
+    import torch
+    nL, nC = 60, 4096
+    ctx, parms = _ctx(nL, nC)
+    ctx.inventory_enable(True)
+    ctx.set_deferred_join(True)
+    cols, dms, mac = parity.make_bgc(nL, nC, parms, ragged=True, with_dms=True, with_macros=True)
+    d = host.DeviceBgcColumns(nL, nC).load(cols)
+    dd = host.DeviceDmsColumns(nL, nC).load(dms)
+    md = host.DeviceMacrosColumns(nL, nC).load(mac)
+
+    def step():
+        ctx.inventory_reset()
+        host.BGC_SourceSink(ctx, d); host.BGC_SurfaceFluxes(ctx, d)
+        host.DMS_SourceSink(ctx, dd); host.DMS_SurfaceFluxes(ctx, dd); host.MACROS_SourceSink(ctx, md)
+        ctx.inventory_allreduce_begin()
+    step(); step(); step()                      # cold + two warm steps, call by call
+    inv_ref = ctx.inventory_allreduce_end()
+    ref = {"tend": d.BGC_tendencies.clone(), "ph": d.PH_PREV_3D.clone(), "co3": d.diag["diag_CO3"].clone(),
+           "dms": dd.DMS_tendencies.clone(), "mac": md.MACROS_tendencies.clone(), "net": d.forcing["netFlux"].clone()}
+    n_calls = ctx.launch_count()
+    # same state again, this time: cold + warm call by call, then capture and replay
+    d.load(cols); dd.load(dms); md.load(mac)
+    step()
+    ctx.synchronize()
+    ctx.timing_reset()
+    ctx.graph_capture_begin()
+    step()
+    g = ctx.graph_capture_end()
+    assert ctx.launch_count() == 0              # captured, not executed
+    ctx.graph_launch(g); ctx.graph_launch(g)
+    inv = ctx.inventory_allreduce_end()
+    assert ctx.launch_count() > 0
+    got = {"tend": d.BGC_tendencies, "ph": d.PH_PREV_3D, "co3": d.diag["diag_CO3"], "dms": dd.DMS_tendencies,
+           "mac": md.MACROS_tendencies, "net": d.forcing["netFlux"]}
+    for k in ref:
+        assert torch.equal(ref[k], got[k]), k
+    assert np.array_equal(inv, inv_ref)
+    ctx.graph_destroy(g)
+    ctx.close()
+    assert n_calls > 0
+
+
 # ------------------------------------------------------------------ inventory
 def test_inventory_vector_matches_the_outputs():
     nL, nC, nCols = 36, 514, 500
