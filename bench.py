@@ -187,13 +187,14 @@ def run_reference(args, rank, world):
 def workload_config(args, world):
     return {"workload": "EC60to30 full BGC+DMS+MACROS tendency update (BASELINE.json configs[3])",
             "columns_per_gpu": args.columns, "levels": args.levels, "n_gpus": world,
-            "cells_total": args.columns * args.levels * world,
+            "cells_total": (getattr(args, "mesh_columns", args.columns) if getattr(args, "strong", False)
+                            else args.columns * world) * args.levels,
             "diagnostics": "all (BGC 130 + DMS 27 + MACROS 6 arrays per cell)",
             "sharding": "contiguous column slabs, one process per GPU, no halo",
             "cache": "inputs+outputs per step (%.1f GB per GPU) far exceed the 126 MB L2; no flush needed"
                      % (args.columns * args.levels * B_API / 1e9),
             "ph_brackets": "warm (PH_PREV from the untimed cold pass), as in a running model",
-            "cuda_graph": not getattr(args, "no_graph", False),
+            "cuda_graph": (not getattr(args, "no_graph", False)) and world == 1,
             "carbonate_join": "strict (inside BGC_SourceSink)" if getattr(args, "strict_join", False)
                               else "deferred to the end of the step (bgc_ctx_set_deferred_join)"}
 
@@ -289,6 +290,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-inventory", action="store_true")
+    ap.add_argument("--strong", action="store_true",
+                    help="strong scaling: ONE mesh of --columns columns split into contiguous slabs over the ranks "
+                         "(default: weak scaling, --columns columns per GPU)")
     ap.add_argument("--no-graph", action="store_true", help="issue every step call by call instead of replaying a CUDA graph")
     ap.add_argument("--strict-join", action="store_true",
                     help="join the carbonate side stream inside every BGC_SourceSink call (library default)")
@@ -297,6 +301,12 @@ def main():
         args.warmup = 3   # timing rule: at least 3 warm-up steps
 
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    args.mesh_columns = args.columns
+    column0 = rank * args.columns
+    if args.strong and args.impl != "reference":   # contiguous slabs of ceil(columns / N), the last one shorter
+        per = (args.columns + world - 1) // world
+        column0 = rank * per
+        args.columns = max(0, min(per, args.mesh_columns - column0))
     if args.impl == "reference":
         return run_reference(args, rank, world)
 
@@ -328,7 +338,7 @@ def main():
     bgc = host.DeviceBgcColumns(nL, nC, device=dev)
     dms = host.DeviceDmsColumns(nL, nC, device=dev)
     mac = host.DeviceMacrosColumns(nL, nC, device=dev)
-    cells = fill_device_inputs(pkg, parms, bgc, dms, mac, column0=rank * nC)
+    cells = fill_device_inputs(pkg, parms, bgc, dms, mac, column0=column0)
     torch.cuda.synchronize()
 
     def step():
@@ -360,7 +370,9 @@ def main():
     barrier()
     # one step = ~15 dependent launches on two streams: captured once, replayed as a CUDA graph
     graph = None
-    if not args.no_graph:
+    # (single process only: a captured NCCL all-reduce keeps the communicator alive until the
+    #  graph is destroyed, and a rank that exits in a different order can stall the others)
+    if not args.no_graph and world == 1:
         ctx.graph_capture_begin()
         step()
         graph = ctx.graph_capture_end()
@@ -454,16 +466,23 @@ def main():
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+                "scaling": "strong" if args.strong else "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": workload_config(args, world), "clocks": clocks, "gpu_launches": int(launches),
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
                 "inventory_check": None if inv is None else {"active_cells": float(inv[60]), "columns": float(inv[61])},
                 "secondary": pts_line}
         print(json.dumps(line), flush=True)
+    # orderly teardown: graph, then the ctx (its NCCL communicator), then torch's process group
+    if graph is not None:
+        ctx.graph_destroy(graph)
+    ctx.synchronize()
+    ctx.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    sys.stdout.flush()
     return 0
 
 
