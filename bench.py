@@ -305,6 +305,7 @@ def main():
     column0 = rank * args.columns
     if args.strong and args.impl != "reference":   # contiguous slabs of ceil(columns / N), the last one shorter
         per = (args.columns + world - 1) // world
+        per += per & 1   # even slabs keep every level row 16-byte aligned (bulk-copy path of the sweep)
         column0 = rank * per
         args.columns = max(0, min(per, args.mesh_columns - column0))
     if args.impl == "reference":
