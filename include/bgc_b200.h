@@ -34,7 +34,11 @@
  *                             A(k,col[,n]) at  col + nColumnsMax*(k + nLevelsMax*n)
  *                             F(col[,n])   at  col + nColumnsMax*n   (unchanged).
  *                             The call is stream-ordered on the ctx stream and
- *                             returns without synchronising.
+ *                             returns without synchronising.  An even nColumnsMax and
+ *                             16-byte aligned arrays let the column sweep stage its
+ *                             inputs with bulk (TMA) copies; otherwise it falls back to
+ *                             per-thread loads (same results up to the last bit of a few
+ *                             tendencies, about half the speed).
  *   - the caller owns every array; the library never frees caller memory.
  */
 #ifndef BGC_B200_H
