@@ -140,7 +140,12 @@ def cpu_oracle_throughput(pkg, columns, levels, steps, warmup):
     sys.path.insert(0, os.path.join(REPO, "oracle"))
     import oracle as o   # cpu_baseline / --impl reference leg only
     po = o.Parms()
-    nthreads = o.max_threads()
+    # every host thread the process may use (torchrun exports OMP_NUM_THREADS=1, which would
+    # otherwise reduce the reference arm to one core)
+    try:
+        nthreads = max(o.max_threads(), len(os.sched_getaffinity(0)))
+    except AttributeError:
+        nthreads = max(o.max_threads(), os.cpu_count() or 1)
     bgc = pkg.BgcColumns(levels, columns)
     dms = pkg.DmsColumns(levels, columns)
     mac = pkg.MacrosColumns(levels, columns)
