@@ -200,6 +200,10 @@ def workload_config(args, world):
                      % (args.columns * args.levels * B_API / 1e9),
             "ph_brackets": "warm (PH_PREV from the untimed cold pass), as in a running model",
             "cuda_graph": (not getattr(args, "no_graph", False)) and world == 1,
+            "zero_biomass_shortcut": "on (library default): functional-group bodies are skipped where the biomass of a "
+                                     "whole warp is exactly zero (the synthetic columns are zero below 300 m by "
+                                     "construction, SURVEY.md 8(d)); see without_zero_biomass_shortcut for the cost with "
+                                     "every body executed",
             "carbonate_join": "strict (inside BGC_SourceSink)" if getattr(args, "strict_join", False)
                               else "deferred to the end of the step (bgc_ctx_set_deferred_join)"}
 
@@ -451,6 +455,28 @@ def main():
                                   "pass); in the timed steps the carbonate kernel overlaps the sweep's last wave, so "
                                   "ms_per_step is less than the sum"}
 
+    # ---- the same step with the zero-biomass shortcut of the sweep switched off (every functional-group
+    #      body executed even where the whole warp's biomass is exactly zero): the data-independent cost
+    noshort = None
+    if True:
+        ctx.set_zero_shortcut(False)
+        for _ in range(3):
+            step()
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record(stream)
+        for _ in range(min(args.steps, 20)):
+            step()
+        f1.record(stream)
+        barrier()
+        tt = torch.tensor([f0.elapsed_time(f1) / min(args.steps, 20)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        noshort = {"ms_per_step": float(tt.item()), "value": total_cells / (float(tt.item()) * 1e-3), "unit": UNIT}
+        ctx.set_zero_shortcut(True)
+        if not args.no_inventory:
+            ctx.inventory_allreduce_end()
+
     # ---- BASELINE.json configs[1]: the surface carbonate solve alone, 1 M points (secondary number)
     pts_line = None
     if rank == 0:
@@ -478,7 +504,7 @@ def main():
                 "config": workload_config(args, world), "clocks": clocks, "gpu_launches": int(launches),
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
                 "inventory_check": None if inv is None else {"active_cells": float(inv[60]), "columns": float(inv[61])},
-                "secondary": pts_line}
+                "secondary": pts_line, "without_zero_biomass_shortcut": noshort}
         print(json.dumps(line), flush=True)
     # orderly teardown: graph, then the ctx (its NCCL communicator), then torch's process group
     if graph is not None:

@@ -308,6 +308,12 @@ int bgc_ctx_set_deferred_join(bgc_ctx *ctx, int enable);
 /* enable = 0 launches the carbonate kernel on the ctx stream after the sweep (no side stream):
  * for per-kernel timing and debugging.  Default: 1 (or the environment BGC_CONCURRENT_CO3). */
 int bgc_ctx_set_concurrency(bgc_ctx *ctx, int enable);
+/* Zero-biomass shortcut of the column sweep (default on).  The reference zeroes a functional
+ * group whose Chl, C or Fe is exactly zero in a cell (BGC_mod.F90:826-844) and then spends
+ * the whole group body producing zeros.  Where that holds for all 32 columns of a warp at a
+ * level the sweep skips the body and writes the zeros directly; results are bit-identical.
+ * enable = 0 executes the full body everywhere (for measuring the data-independent cost). */
+int bgc_ctx_set_zero_shortcut(bgc_ctx *ctx, int enable);
 int bgc_carbonate_join(bgc_ctx *ctx);
 int bgc_get_status(bgc_ctx *ctx, BgcStatus *out, int reset);
 

@@ -101,6 +101,7 @@ struct bgc_ctx {
   cudaStream_t side_stream[2] = {nullptr, nullptr};
   cudaEvent_t fork_event[2] = {nullptr, nullptr}, join_event[2] = {nullptr, nullptr};
   int concurrent_co3 = 1;                   // BGC_CONCURRENT_CO3=0 serialises the two (tuning / debugging)
+  int zero_shortcut = 1;                    // bgc_ctx_set_zero_shortcut / BGC_ZERO_SHORTCUT
   bool diag_accumulate = false;             // bgc_diag_accumulate_enable
   bool defer_join = false;                  // bgc_ctx_set_deferred_join
   bool pending_join = false;                // a carbonate side stream has not been joined to the ctx stream yet
@@ -222,6 +223,7 @@ extern "C" int bgc_ctx_create(int device, int nLevelsMax, int nColumnsMax, bgc_c
   CU(cudaStreamCreateWithFlags(&c->pipe_stream, cudaStreamNonBlocking));
   CU(cudaEventCreateWithFlags(&c->pipe_event, cudaEventDisableTiming));
   if (const char *v = getenv("BGC_CONCURRENT_CO3")) c->concurrent_co3 = atoi(v);
+  if (const char *v = getenv("BGC_ZERO_SHORTCUT")) c->zero_shortcut = atoi(v);
   {
     int lo = 0, hi = 0;   // the side stream gets the LOWER priority: the sweep's blocks are placed first
     CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
@@ -290,6 +292,12 @@ extern "C" int bgc_ctx_set_concurrency(bgc_ctx *c, int enable) {
   RC(use_device(c));
   RC(join_pending(c));
   c->concurrent_co3 = enable != 0;
+  return BGC_OK;
+}
+
+extern "C" int bgc_ctx_set_zero_shortcut(bgc_ctx *c, int enable) {
+  if (!c) return fail(BGC_ERR_ARG, "null ctx");
+  c->zero_shortcut = enable != 0;
   return BGC_OK;
 }
 
@@ -743,6 +751,7 @@ static int source_sink_device(bgc_ctx *c, const BgcInput *in, const BgcForcing *
   // ecosystem + particle sweep, column-parallel
   bgc::EcoArgs ea;
   ea.nL = nL; ea.nC = nC; ea.nColumns = nCols; ea.alt_co2_use_eco = alt_co2_use_eco;
+  ea.zero_shortcut = c->zero_shortcut;
   ea.tracers = in->BGC_tracers; ea.T = in->PotentialTemperature; ea.S = in->Salinity;
   ea.zmid = in->cell_center_depth; ea.dz = in->cell_thickness; ea.zbot = in->cell_bottom_depth;
   ea.lat = in->cell_latitude; ea.kmax = in->number_of_active_levels;

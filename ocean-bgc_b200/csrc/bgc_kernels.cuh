@@ -58,6 +58,7 @@ cudaError_t launch_zsat_columns(const ZsatArgs &a, cudaStream_t s);
 // ---- ecosystem + particulate column sweep, one thread per COLUMN
 struct EcoArgs {
   int nL, nC, nColumns, alt_co2_use_eco;
+  int zero_shortcut;                     // skip the body of a functional group whose biomass is zero in a whole warp
   const double *tracers;                 // (k,col,30)
   const double *T, *S, *zmid, *dz, *zbot;
   const double *lat;

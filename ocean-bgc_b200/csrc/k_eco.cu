@@ -487,6 +487,56 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
       const double aChl = IN(at.Chl_ind - 1), aC = IN(at.C_ind - 1), aFe = IN(at.Fe_ind - 1), Pprime = Pp[a];
       const bool has_Si = at.Si_ind > 0, has_Ca = at.CaCO3_ind > 0;
 
+      // ---- zero-biomass shortcut.  A group whose Chl, C or Fe is exactly zero has been zeroed
+      //      as a whole (:826-844: clamped undershoots and the lightless deep ocean), and then every
+      //      product of the group body below is exactly zero: the only things that survive are
+      //      the nutrient-limitation diagnostics (they do not involve the biomass), the
+      //      epsC*epsTinv terms of f_zoo_detr (:1395-1401) and the running NO3 integral (:1844-1846).
+      //      When that holds for every active lane of the warp the body is skipped; the bits
+      //      produced are the same (x*0 = 0 and s+0 = s for the finite values that occur here).
+      if (A.zero_shortcut && !__any_sync(__activemask(), aC != 0.0)) {
+        if (DIAG) {
+          const double rNO3 = cdiv(NO3_loc, at.kNO3, D.r_kNO3[a]), rNH4 = cdiv(NH4_loc, at.kNH4, D.r_kNH4[a]);
+#ifdef BGC_STRICT
+          double VNtot = rNO3 / (1.0 + rNO3 + rNH4) + rNH4 / (1.0 + rNO3 + rNH4);
+#else
+          const double rN = frcp(1.0 + rNO3 + rNH4);
+          double VNtot = rNO3 * rN + rNH4 * rN;
+#endif
+          if (at.Nfixer) VNtot = 1.0;
+          const double rPO4 = cdiv(PO4_loc, at.kPO4, D.r_kPO4[a]), rDOP = cdiv(DOP_loc, at.kDOP, D.r_kDOP[a]);
+#ifdef BGC_STRICT
+          const double VPtot = rPO4 / (1.0 + rPO4 + rDOP) + rDOP / (1.0 + rPO4 + rDOP);
+#else
+          const double rPd = frcp(1.0 + rPO4 + rDOP);
+          const double VPtot = rPO4 * rPd + rDOP * rPd;
+#endif
+          STA(diag_N_lim, VNtot);
+          STA(diag_Fe_lim, fdiv(Fe_loc, Fe_loc + at.kFe));
+          STA(diag_P_lim, VPtot);
+          STA(diag_SiO3_lim, (at.kSiO3 > 0.0) ? fdiv(SiO3_loc, SiO3_loc + at.kSiO3) : 0.0);
+          STA(diag_light_lim, 0.0);
+          STA(diag_photoNO3, 0.0); STA(diag_photoNH4, 0.0); STA(diag_PO4_uptake, 0.0); STA(diag_DOP_uptake, 0.0);
+          STA(diag_photoFe, 0.0); STA(diag_bSi_form, 0.0); STA(diag_CaCO3_form, 0.0); STA(diag_Nfix, 0.0);
+          STA(diag_auto_graze, 0.0); STA(diag_auto_loss, 0.0); STA(diag_auto_agg, 0.0);
+          STA(diag_photoC, 0.0); STA(diag_photoC_NO3, 0.0);
+          NO3_zint_k = NO3_zint_k + XS(X_ZNO3 + a);
+        }
+        zd_num = zd_num + at.f_zoo_detr * (0.0 + epsC * epsTinv);
+        zd_den = zd_den + (0.0 + epsC * epsTinv);
+        if (has_Ca) Ca_prod = 0.0;
+        if (has_Si) Si_prod = 0.0;
+        TEND(at.C_ind) = 0.0; TEND(at.Chl_ind) = 0.0; TEND(at.Fe_ind) = 0.0;
+        if (has_Si) TEND(at.Si_ind) = 0.0;
+        if (has_Ca) TEND(at.CaCO3_ind) = 0.0;
+        if (inv) {
+          IN(at.Chl_ind - 1) = 0.0; IN(at.C_ind - 1) = 0.0; IN(at.Fe_ind - 1) = 0.0;
+          if (has_Si) IN(at.Si_ind - 1) = 0.0;
+          if (has_Ca) IN(at.CaCO3_ind - 1) = 0.0;
+        }
+        continue;
+      }
+
       const double rCden = frcp(aC + epsC);
 #ifdef BGC_STRICT
       const double thetaC = aChl / (aC + epsC), Qfe = aFe / (aC + epsC);

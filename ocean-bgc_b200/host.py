@@ -39,6 +39,7 @@ ABI_SYMBOLS = [
     "bgc_diag_accumulate_enable", "bgc_diag_flush", "bgc_layout_mpas_to_soa", "bgc_layout_soa_to_mpas",
     "bgc_inventory_allreduce_begin", "bgc_inventory_allreduce_end",
     "bgc_graph_capture_begin", "bgc_graph_capture_end", "bgc_graph_launch", "bgc_graph_destroy",
+    "bgc_ctx_set_zero_shortcut",
 ]
 
 
@@ -164,6 +165,9 @@ class Context:
         check(self.L, self.L.bgc_layout_soa_to_mpas(self.ptr, abi.raw_dptr(dev_soa), abi.raw_dptr(dev_mpas),
                                                     C.c_int(len(slot_of_tracer)), m, C.c_int(nL), C.c_int(nC),
                                                     C.c_double(alpha), C.c_double(beta)))
+
+    def set_zero_shortcut(self, on=True):
+        check(self.L, self.L.bgc_ctx_set_zero_shortcut(self.ptr, C.c_int(int(on))))
 
     def carbonate_join(self):
         check(self.L, self.L.bgc_carbonate_join(self.ptr))

@@ -456,6 +456,40 @@ def test_cuda_graph_replay_gives_the_same_bits():
     assert n_calls > 0
 
 
+def test_zero_biomass_shortcut_changes_nothing():
+    """bgc_ctx_set_zero_shortcut: skipping the body of a functional group whose biomass is zero in
+    a whole warp must give the same tendencies bit for bit, and the same diagnostics (the four
+    nutrient-limitation diagnostics are recomputed in the shortcut: last-bit FMA differences allowed)."""
+    import torch
+    nL, nC = 60, 2048 + 64
+    ctx, parms = _ctx(nL, nC)
+    ctx.inventory_enable(True)
+    cols, _, _ = parity.make_bgc(nL, nC, parms, ragged=True)
+    outs = []
+    for on in (True, False):
+        ctx.set_zero_shortcut(on)
+        d = host.DeviceBgcColumns(nL, nC).load(cols)
+        ctx.inventory_reset()
+        host.BGC_SourceSink(ctx, d)
+        host.BGC_SourceSink(ctx, d)
+        inv = ctx.inventory_get()
+        ctx.synchronize()
+        outs.append((d, inv))
+    (a, inv_a), (b, inv_b) = outs
+    assert torch.equal(a.BGC_tendencies, b.BGC_tendencies)
+    assert torch.equal(a.PH_PREV_3D, b.PH_PREV_3D)
+    assert np.array_equal(inv_a, inv_b)
+    masked_cells = (a.BGC_tracers[16] == 0).float().mean().item()      # spC == 0: the shortcut had work to skip
+    assert masked_cells > 0.3, masked_cells
+    for n, v in a.diag.items():
+        w = b.diag[n]
+        if n in ("diag_N_lim", "diag_P_lim", "diag_Fe_lim", "diag_SiO3_lim"):
+            assert (v - w).abs().max().item() <= 4e-16, n
+        else:
+            assert torch.equal(v, w), n
+    ctx.close()
+
+
 # ------------------------------------------------------------------ inventory
 def test_inventory_vector_matches_the_outputs():
     nL, nC, nCols = 36, 514, 500
