@@ -2,26 +2,28 @@
 //
 // Replaces the column_loop of BGC_SourceSink (BGC_mod.F90:799-1970) together
 // with init_particulate_terms (:2006-2109) and compute_particulate_terms
-// (:2116-2699).  One thread owns one ocean column and walks it top to bottom;
-// everything the level loop carries (PAR, the ten particle fluxes, the QA dust
-// deficit, saturation-depth scan state, the column integrals) lives in that
-// thread's registers.  The setup_loop clamp pass (:733-789) and the whole-array
-// zero fills (:570, :625-727) are folded into the same sweep: a cell is read
-// once and every output element is written exactly once.
+// (:2116-2699).  One thread owns one ocean column and walks it top to bottom.
+// The setup_loop clamp pass (:733-789) and the whole-array zero fills (:570,
+// :625-727) are folded into the same sweep: a cell is read once and every output
+// element is written exactly once.
 //
-// Code-footprint design.  The reference's per-cell arithmetic is ~9k SASS
-// instructions when the loop over the four functional groups is unrolled and
-// every divide is the IEEE sequence: a 200 KB loop body that streams through the
-// 32 KB L1.5 instruction cache once per level per warp (ncu on the first version:
-// "no instruction" was the top stall, 4.8 cycles per issue).  Here
-//   * the functional-group loop is ROLLED: its body exists once, the group's
-//     parameters come from __constant__ memory by run-time index, the group's
-//     tracers are staged in shared memory, and every SUM(x(:)) of the reference
-//     is a running accumulator (same left-to-right order as Fortran's SUM);
-//   * divides use bgc_math.cuh (reciprocal seed + Newton, shared reciprocals where
-//     the reference divides several numerators by one denominator);
-//   * a block-wide barrier per level keeps the warps of a block on the same
-//     stretch of code so that one I-cache fill serves all of them.
+// What bounds it.  ~3.6-4.5 k instructions per cell, of which a third are FP64 with
+// an 8-cycle dependent latency (scripts/micro/fp64_lat.cu), at 255 registers per
+// thread = 8 warps per SM: the kernel is bound by exposed dependency latency, not by
+// HBM or by the FP64 pipe (profiles/README.md).  Registers are the scarce resource
+// (a thread's state is ~1.5 KB across registers and shared memory), so
+//   * only the particle fluxes stay in registers across levels; the column state that
+//     is touched once per level (PAR, dust fluxes, the QA deficit, the previous zbot)
+//     and the fourteen column integrals live in per-thread shared-memory rows;
+//   * the loop over the four functional groups is unrolled, so the group's table
+//     fields are constant-bank operands; every SUM(x(:)) of the reference is a
+//     running accumulator in the same left-to-right order as Fortran's SUM;
+//   * exp / log / reciprocal come from bgc_math.cuh (constant-bank coefficients,
+//     Estrin evaluation, one Newton step on the MUFU seed, no slow-path branches);
+//   * a functional group whose biomass is exactly zero in a whole warp skips its body
+//     (zero-biomass shortcut, see the group loop);
+//   * a block-wide barrier per level (needed by the stage hand-over below) also keeps
+//     the warps of a block on the same stretch of code, which the instruction cache likes.
 //
 // Input staging.  With ~8 resident warps per SM (255 registers per thread) nothing
 // hides an HBM round trip, and a level has ~8 dependent batches of loads.  So one
