@@ -434,12 +434,14 @@ def main():
     eco_ms, eco_n, _ = ktimes["eco_columns_kernel"]
     eco_ms_per = eco_ms / max(1, eco_n)
     achieved = cells * B_ECO / (eco_ms_per * 1e-3) / 1e9
-    traffic = None
+    traffic, ncu_counters = None, None
     tp = os.path.join(REPO, "profiles", "traffic.json")
-    if os.path.exists(tp):
+    if os.path.exists(tp):   # from the committed ncu --set full capture (not measured in this run)
         try:
-            traffic = json.load(open(tp)).get("eco_columns_kernel_bytes_per_cell")
+            tj = json.load(open(tp))
+            traffic = tj.get("eco_columns_kernel_bytes_per_cell")
             traffic = traffic * cells if traffic is not None else None
+            ncu_counters = {"source": tj.get("ncu_counters_source"), "kernels": tj.get("ncu_counters")}
         except Exception:
             traffic = None
     kernel_ms = {k: (v[0] / max(1, v[1])) for k, v in ktimes.items() if v[1]}
@@ -450,7 +452,7 @@ def main():
                 "step": {"algorithmic_bytes_per_cell": B_API,
                          "achieved": cells * B_API / (ms_step * 1e-3) / 1e9,
                          "frac": cells * B_API / (ms_step * 1e-3) / 1e9 / peak},
-                "kernel_ms_per_launch": kernel_ms,
+                "kernel_ms_per_launch": kernel_ms, "ncu_counters": ncu_counters,
                 "kernel_ms_note": "each kernel timed alone (carbonate kernel serialised behind the sweep for this "
                                   "pass); in the timed steps the carbonate kernel overlaps the sweep's last wave, so "
                                   "ms_per_step is less than the sum"}
