@@ -413,6 +413,9 @@ class DeviceBgcColumns(_DeviceMixin):
             put(getattr(self, n), self._soa(getattr(host, n)))
         put(self.cell_latitude, host.cell_latitude)
         put(self.number_of_active_levels, host.number_of_active_levels)
+        for n in abi.BGC_FORCING_K2[1:]:   # nutrient-restoring fields: resident only when the host uses them
+            if n not in self.forcing and np.any(host.forcing[n]):
+                self.forcing[n] = self._alloc((self.nLevelsMax, self.nColumnsMax))
         for n, t in self.forcing.items():
             a = host.forcing[n]
             put(t, self._flux(a) if n in abi.BGC_FORCING_FLUX else self._soa(a))

@@ -155,6 +155,63 @@ def test_untouched_members_and_inactive_cells(o):
     ctx.close()
 
 
+def _retune(parms):
+    """Non-default run-time parameters and a modified functional-group table: every branch that
+    is keyed on a table value (not on the group's name) must follow."""
+    b = parms.bgc
+    b.parm_o2_min, b.parm_o2_min_delta = 6.0, 3.0
+    b.parm_labile_ratio = 0.7
+    b.parm_POMbury, b.parm_BSIbury = 1.3, 0.8
+    b.parm_nitrif_par_lim = 2.5
+    b.parm_kappa_nitrif *= 1.7
+    b.parm_z_mort_0 *= 0.6
+    b.parm_z_mort2_0 *= 1.4
+    b.parm_fe_scavenge_rate0 *= 2.0
+    b.parm_f_prod_sp_CaCO3 = 0.055
+    b.parm_POC_diss, b.parm_SiO2_diss, b.parm_CaCO3_diss = 70.0e2, 300.0e2, 450.0e2
+    for i in range(4):
+        b.parm_scalelen_vals[i] *= (1.0 + 0.15 * i)
+    b.lrest_no3 = b.lrest_po4 = b.lrest_sio3 = 1           # never set by the reference (Q8): the code path exists
+    a = parms.autotrophs
+    sp, diat, diaz, phaeo = a[parms.ind.sp_ind - 1], a[parms.ind.diat_ind - 1], a[parms.ind.diaz_ind - 1], a[parms.ind.phaeo_ind - 1]
+    sp.temp_function, sp.temp_thresN, sp.temp_thresS, sp.temp_optN, sp.temp_optS = abi.DEFINES["BGC_TFNC_QUASI_MMRT"], 27.0, 26.0, 18.0, 17.0
+    phaeo.temp_function, phaeo.temp_thres = abi.DEFINES["BGC_TFNC_Q10"], 1.0
+    diat.Qp = 0.0061                                       # != Qp_zoo_pom: the remaining_P routing
+    sp.kSiO3 = 0.4                                         # a silicate-limited group that carries no Si tracer
+    diaz.graze_zoo, diaz.graze_poc, diaz.graze_doc = 0.25, 0.08, 0.10
+    phaeo.grazee_ind = sp.grazee_ind                       # two groups share a grazer
+    diat.agg_rate_max, diat.agg_rate_min, diat.mort2 = 0.7, 0.03, 0.012
+    for g in (sp, diat, diaz, phaeo):
+        g.PCref *= 1.1
+        g.alphaPI *= 0.9
+
+
+def test_non_default_parameters_and_group_table(o):
+    nL, nC = 40, 512
+    po = o.Parms()
+    _retune(po)
+    parms = host.Parms()
+    _retune(parms)
+    ctx, _ = _ctx(nL, nC, parms=parms)
+    cols, _, _ = parity.make_bgc(nL, nC, parms, ragged=True, seed=0x5EED)
+    rng = np.random.default_rng(11)
+    cols.forcing["NUTR_RESTORE_RTAU"][...] = rng.uniform(0.0, 1.0e-6, size=(nL, nC))
+    tr = cols.BGC_tracers
+    cols.forcing["NO3_CLIM"][...] = tr[:, :, parms.ind.no3_ind - 1] * rng.uniform(0.8, 1.2, size=(nL, nC))
+    cols.forcing["PO4_CLIM"][...] = tr[:, :, parms.ind.po4_ind - 1] * rng.uniform(0.8, 1.2, size=(nL, nC))
+    cols.forcing["SiO3_CLIM"][...] = tr[:, :, parms.ind.sio3_ind - 1] * rng.uniform(0.8, 1.2, size=(nL, nC))
+    parity.poison_outputs(cols)
+    for device_mode in (True, False):
+        ref = cols.copy()
+        o.BGC_SourceSink(po, ref, True, nthreads=o.max_threads())
+        got = parity.run_gpu_bgc(ctx, cols.copy(), device_mode=device_mode)
+        parity.compare_bgc_source_sink(ref, got)
+        assert np.abs(ref.diag["diag_NO3_RESTORE"]).max() > 0 and np.abs(ref.diag["diag_PO4_RESTORE"]).max() > 0
+    st = ctx.status()
+    assert st["no_bracket"] == 0 and st["no_convergence"] == 0 and st["nonfinite"] == 0, st
+    ctx.close()
+
+
 def test_permuted_tracer_slots(o):
     """The host chooses the tracer slots (BGC_indices_type): a permutation must only
     permute the outputs."""
@@ -205,6 +262,43 @@ def test_surface_fluxes_and_side_effects(o):
         parity.compare_fields(ref.flux_diag, got.flux_diag, parity.TOL_TEND, "BGC_flux_diagnostics",
                               solver_keys=parity.SOLVER_FLUX)
         assert np.array_equal(got.forcing["iceFraction"][:7], [0.0, 1.0, 0.3, 0.0, 1.0, 1.0, 0.0])
+    ctx.close()
+
+
+@pytest.mark.parametrize("o2,co2", [(0, 1), (1, 0), (0, 0)])
+def test_surface_flux_switches(o, o2, co2):
+    """lcalc_O2_gas_flux / lcalc_CO2_gas_flux off (BGC_mod.F90:2847, :2871) and
+    lcalc_DMS_gas_flux off (DMS_mod.F90:846: the routine then does nothing at all)."""
+    nL, nC = 12, 200
+    ctx, parms = _ctx(nL, nC)
+    po = o.Parms()
+    cols, dms, _ = parity.make_bgc(nL, nC, parms, with_dms=True)
+    cols.lcalc_O2_gas_flux, cols.lcalc_CO2_gas_flux = o2, co2
+    dms.lcalc_DMS_gas_flux = 0
+    parity.poison_outputs(cols)
+    for a in dms.flux_diag.values():
+        a[...] = 3.5
+    dms.forcing["netFlux"][...] = 1.25
+    for dev in (True, False):
+        ref, got = cols.copy(), cols.copy()
+        o.BGC_SurfaceFluxes(po, ref, nthreads=o.max_threads())
+        dref, dgot = dms.copy(), dms.copy()
+        o.DMS_SurfaceFluxes(po, dref)
+        if dev:
+            d = host.DeviceBgcColumns(nL, nC).load(got)
+            dd = host.DeviceDmsColumns(nL, nC).load(dgot)
+            host.BGC_SurfaceFluxes(ctx, d); host.DMS_SurfaceFluxes(ctx, dd)
+            ctx.synchronize()
+            d.store(got); dd.store(dgot)
+        else:
+            host.BGC_SurfaceFluxes(ctx, got); host.DMS_SurfaceFluxes(ctx, dgot)
+        parity.compare_fields(ref.forcing, got.forcing, parity.TOL_TEND, "BGC_forcing",
+                              solver_keys=("gasFlux", "netFlux", "surface_pH", "surface_pH_alt_co2"))
+        parity.compare_fields(ref.flux_diag, got.flux_diag, parity.TOL_TEND, "BGC_flux_diagnostics",
+                              solver_keys=parity.SOLVER_FLUX)
+        assert np.array_equal(dgot.forcing["netFlux"], dref.forcing["netFlux"])
+        for n in dref.flux_diag:
+            assert np.array_equal(dgot.flux_diag[n], dref.flux_diag[n]), n
     ctx.close()
 
 
