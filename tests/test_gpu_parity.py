@@ -322,6 +322,60 @@ def test_co2calc_points(o, warm):
 
 
 # ------------------------------------------------------------------ DMS / MACROS
+def test_co2calc_points_extreme_inputs(o):
+    """Floors (dic_min, alk_min, salt_min: co2calc.F90:57-59, :843-846), brackets that do not
+    contain the root (the growth loop, :920-938), polar and tropical temperatures, fresh water."""
+    ctx, _ = _ctx(2, 64)
+    n = 4096
+    rng = np.random.default_rng(5)
+    pts = pkg.synth_co2_points(n)
+    pts["temp"] = rng.choice([-1.9, 0.0, 12.0, 30.0, 35.0], size=n)
+    pts["salt"] = rng.choice([0.02, 0.5, 5.0, 20.0, 35.0, 41.0], size=n)     # 0.02 < salt_min
+    pts["dic"] = rng.choice([0.5, 3.0, 800.0, 2000.0, 2600.0], size=n)       # 0.5, 3.0 < dic_min = 5.55
+    pts["ta"] = pts["dic"] * rng.uniform(0.9, 1.4, size=n)
+    pts["pt"] = rng.choice([0.0, 0.5, 5.0], size=n)
+    pts["sit"] = rng.choice([0.0, 20.0, 200.0], size=n)
+    lo = rng.choice([3.0, 6.0, 7.0, 9.5], size=n)                            # many brackets miss the root
+    pts["phlo"], pts["phhi"] = lo, lo + rng.choice([0.4, 1.0, 2.0], size=n)
+    r = o.co2calc_points(pts, nthreads=o.max_threads())
+    g = host.co2calc_points(ctx, pts)
+    ok = np.isfinite(r["ph"])
+    assert ok.mean() > 0.9
+    for k in ("ph", "co2star", "dco2star", "pco2surf", "dpco2"):
+        assert parity.nerr(g[k][ok], r[k][ok]) <= parity.TOL_SOLVER, k
+    assert np.array_equal(np.isfinite(g["ph"]), ok)
+    ctx.close()
+
+
+def test_block_without_active_cells(o):
+    """numColumns = 0, and a block whose columns all have zero active levels: the whole-array zero
+    fills of the reference (BGC_mod.F90:570, :625-727) are all that happens; PH_PREV_* stay."""
+    nL, nC = 17, 130
+    ctx, parms = _ctx(nL, nC)
+    po = o.Parms()
+    for case in ("numColumns=0", "kmax=0"):
+        cols, dms, mac = parity.make_bgc(nL, nC, parms, with_dms=True, with_macros=True,
+                                         nColumns=0 if case == "numColumns=0" else nC)
+        if case == "kmax=0":
+            cols.number_of_active_levels[:] = 0
+            dms.number_of_active_levels[:] = 0
+            mac.number_of_active_levels[:] = 0
+        parity.poison_outputs(cols); parity.poison_outputs(dms); parity.poison_outputs(mac)
+        cols.PH_PREV_3D[...] = 8.1
+        for device_mode in (True, False):
+            ref = cols.copy()
+            o.BGC_SourceSink(po, ref, True)
+            got = parity.run_gpu_bgc(ctx, cols.copy(), device_mode=device_mode)
+            parity.compare_bgc_source_sink(ref, got)
+            assert np.all(got.BGC_tendencies == 0.0) and np.all(got.PH_PREV_3D == 8.1), case
+            assert np.all(got.diag["diag_POC_ACCUM"] == 7.25), case      # never touched by the reference
+        dgot, mgot = dms.copy(), mac.copy()
+        host.DMS_SourceSink(ctx, dgot); host.MACROS_SourceSink(ctx, mgot)
+        assert np.all(dgot.DMS_tendencies == 0.0) and np.all(mgot.MACROS_tendencies == 0.0), case
+        assert all(np.all(a == 7.25) for a in dgot.diag.values()), case   # DMS diagnostics are not zeroed
+    ctx.close()
+
+
 def _active(c):
     k = np.arange(1, c.nLevelsMax + 1)[:, None]
     kmax = c.number_of_active_levels.copy()
