@@ -1,0 +1,48 @@
+"""bench.py contract checks that need no GPU: the reference arm prints ONE JSON line with the
+agreed keys, and the B200 arm refuses to run (no CPU fallback) when there is no CUDA device."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(*args, env=None):
+    e = dict(os.environ)
+    e.update(env or {})
+    return subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), *args], capture_output=True, text=True,
+                          cwd=REPO, env=e, timeout=600)
+
+
+def test_reference_arm_prints_one_json_line(built):
+    r = _run("--impl", "reference", "--steps", "1", "--warmup", "1", "--cpu-columns", "256", "--gpus", "1")
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+              "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["unit"] == "cell-updates/s" and d["dtype"] == "f64"
+    assert d["vs_baseline"] is None and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert d["value"] > 0 and "workload" in d["config"]
+
+
+def test_reference_arm_other_ranks_exit_quietly(built):
+    r = _run("--impl", "reference", "--steps", "1", "--warmup", "1", "--cpu-columns", "256", "--gpus", "2",
+             env={"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
+    assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_b200_arm_has_no_cpu_fallback(built):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    r = _run("--steps", "1")
+    assert r.returncode != 0
+    assert "no CUDA device" in (r.stderr + r.stdout)
