@@ -1139,6 +1139,12 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
     }
     const double t_o2 = O2_PRODUCTION - O2_CONSUMPTION;
 
+    {   // BgcStatus.nonfinite: NaN / Inf in any tendency of the cell shows up in their sum
+      const double chk = (((t_no3 + t_nh4) + (t_fe + t_sio3)) + ((t_po4 + t_zooC) + (t_doc + t_don))) +
+                         (((t_donr + t_dop) + (t_dopr + t_dofe)) + ((t_dic + t_alk) + (t_o2 + s_tC))) +
+                         (s_tCaCO3 + s_tSi);
+      if (!(fabs(chk) <= 1.7976931348623157e308) && A.status) atomicAdd(&A.status[3], 1ull);
+    }
     TEND(I.no3_ind) = t_no3;
     TEND(I.nh4_ind) = t_nh4;
     TEND(I.fe_ind) = t_fe;

@@ -756,6 +756,26 @@ def test_ec60to30_full_size_properties():
 
 
 # ------------------------------------------------------------------ error behaviour
+def test_status_counts_nonfinite_cells():
+    """BgcStatus.nonfinite: a NaN that reaches a tendency is counted (the reference has no error
+    reporting at all); the other columns are unaffected."""
+    nL, nC = 20, 256
+    ctx, parms = _ctx(nL, nC)
+    cols, _, _ = parity.make_bgc(nL, nC, parms)
+    clean = parity.run_gpu_bgc(ctx, cols.copy(), device_mode=True)
+    assert ctx.status(reset=True)["nonfinite"] == 0
+    bad = cols.copy()
+    bad.PotentialTemperature[3, 17] = np.nan
+    bad.BGC_tracers[5, 101, parms.ind.doc_ind - 1] = np.inf
+    got = parity.run_gpu_bgc(ctx, bad, device_mode=True)
+    st = ctx.status(reset=True)
+    assert st["nonfinite"] >= 2, st
+    keep = np.ones(nC, bool); keep[[17, 101]] = False
+    assert np.array_equal(got.BGC_tendencies[:, keep, :], clean.BGC_tendencies[:, keep, :])
+    assert ctx.status()["nonfinite"] == 0
+    ctx.close()
+
+
 def test_error_codes():
     L = host.lib()
     ctx = host.Context(8, 32, device=0)          # no parameters yet
