@@ -776,6 +776,55 @@ def test_status_counts_nonfinite_cells():
     ctx.close()
 
 
+def test_no_kernel_writes_outside_its_arrays(monkeypatch):
+    """Guard bands: every device array of the containers is carved out of one pool with 64
+    sentinel doubles before and after it; no kernel may touch a sentinel (partial last block,
+    ragged columns, numColumns < numColumnsMax, odd and even extents, inventory on).
+    (compute-sanitizer is not available on the GPU pool: this is the in-tree substitute for
+    out-of-bounds stores.)"""
+    import torch
+    GUARD, SENT = 64, -123456.5
+    pool = torch.full((40_000_000,), SENT, dtype=torch.float64, device="cuda")
+    ipool = torch.full((200_000,), -77, dtype=torch.int32, device="cuda")
+    state = {"off": GUARD, "ioff": GUARD, "spans": [], "ispans": []}
+
+    def alloc(self, shape, dtype=None):
+        n = int(np.prod(shape))
+        if dtype is not None and dtype != torch.float64:
+            a = ipool[state["ioff"]:state["ioff"] + n]
+            state["ispans"].append((state["ioff"], n)); state["ioff"] += n + GUARD
+            a.zero_()
+            return a.view(shape)
+        off = (state["off"] + 1) & ~1          # keep 16-byte alignment (bulk-copy path)
+        a = pool[off:off + n]
+        state["spans"].append((off, n)); state["off"] = off + n + GUARD
+        a.zero_()
+        return a.view(shape)
+    monkeypatch.setattr(host._DeviceMixin, "_alloc", alloc)
+    for nL, nC, nCols in ((9, 300, 290), (7, 129, 129)):
+        ctx, parms = _ctx(nL, nC)
+        ctx.inventory_enable(True)
+        cols, dms, mac = parity.make_bgc(nL, nC, parms, nColumns=nCols, ragged=True, with_dms=True, with_macros=True)
+        d = host.DeviceBgcColumns(nL, nC, nCols).load(cols)
+        dd = host.DeviceDmsColumns(nL, nC, nCols).load(dms)
+        md = host.DeviceMacrosColumns(nL, nC, nCols).load(mac)
+        for _ in range(2):
+            host.BGC_SourceSink(ctx, d); host.BGC_SurfaceFluxes(ctx, d)
+            host.DMS_SourceSink(ctx, dd); host.DMS_SurfaceFluxes(ctx, dd); host.MACROS_SourceSink(ctx, md)
+        ctx.inventory_allreduce()
+        ctx.synchronize()
+        ctx.close()
+    mask = torch.ones_like(pool, dtype=torch.bool)
+    for off, n in state["spans"]:
+        mask[off:off + n] = False
+    assert bool((pool[mask] == SENT).all()), "a kernel wrote outside its FP64 arrays"
+    imask = torch.ones_like(ipool, dtype=torch.bool)
+    for off, n in state["ispans"]:
+        imask[off:off + n] = False
+    assert bool((ipool[imask] == -77).all())
+    assert len(state["spans"]) > 300
+
+
 def test_error_codes():
     L = host.lib()
     ctx = host.Context(8, 32, device=0)          # no parameters yet
