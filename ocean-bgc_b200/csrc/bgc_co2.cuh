@@ -60,23 +60,25 @@ struct Co3Consts {
 struct Co3Totals { double dic, ta, pt, sit; };   // mol/kg, after the floors of co2calc.F90:843-846
 
 // POP ref_pressure fit, co2calc.F90:371-372 (depth in m -> bar)
-__device__ __forceinline__ double press_bar_of_depth(double depth) {
-  return 0.059808 * (bexp(-0.025 * depth) - 1.0) + 0.100766 * depth + 2.28405e-7 * (depth * depth);
+template <class EXP>
+__device__ __forceinline__ double press_bar_of_depth(double depth, const EXP &ex) {
+  return 0.059808 * (ex(-0.025 * depth) - 1.0) + 0.100766 * depth + 2.28405e-7 * (depth * depth);
 }
 
 // Pressure factor bexp((-deltaV + 0.5*Kappa*P)*P/(R*T)), Millero 1995.
-__device__ __forceinline__ double kfac(double deltaV, double Kappa, double press_bar, double invRtk) {
-  return bexp((-deltaV + 0.5 * Kappa * press_bar) * press_bar * invRtk);
+template <class EXP>
+__device__ __forceinline__ double kfac(double deltaV, double Kappa, double press_bar, double invRtk, const EXP &ex) {
+  return ex((-deltaV + 0.5 * Kappa * press_bar) * press_bar * invRtk);
 }
 
 // `deep` is the reference's (k > 1): the pressure correction is keyed on the
 // LEVEL INDEX, not on depth (co2calc.F90:480 ...), so level 1 is never corrected.
 // K0 is never consumed by any caller and the Kfac factors of k1/k2 never leave
 // comp_co3_coeffs (sk1/sk2 are captured first) -> neither is computed.
-template <bool WANT_FF>
+template <bool WANT_FF, class EXP>
 __device__ __forceinline__ void co3_coeffs(bool deep, double depth, double temp, double salt,
-                                           Co3Consts &c) {
-  const double press_bar = press_bar_of_depth(depth);
+                                           Co3Consts &c, const EXP &ex) {
+  const double press_bar = press_bar_of_depth(depth, ex);
 
   const double salt_lim = fmax(salt, kSaltMin);
   const double tk = kT0Kelvin + temp;
@@ -99,7 +101,7 @@ __device__ __forceinline__ void co3_coeffs(bool deep, double depth, double temp,
   if (WANT_FF) {   // Weiss & Price 1980, co2calc.F90:423-431
     arg = -162.8301 + fdiv(218.2968, tk100) + 90.9241 * (dlogtk + kLn1em2) - 1.47696 * tk1002 +
           salt_lim * (.025695 - .025225 * tk100 + 0.0049867 * tk1002);
-    c.ff = bexp(arg);
+    c.ff = ex(arg);
   } else {
     c.ff = 0.0;
   }
@@ -107,9 +109,9 @@ __device__ __forceinline__ void co3_coeffs(bool deep, double depth, double temp,
   // k1, k2: Lueker et al. 2000, total pH scale (k1_k2_pH_tot = .true. at every
   // call site on this path: co2calc.F90:285, BGC_mod.F90:2764)
   arg = 3633.86 * invtk - 61.2172 + 9.67770 * dlogtk - 0.011555 * salt_lim + 0.0001152 * s2;
-  c.k1 = bexp(-kLn10 * arg);
+  c.k1 = ex(-kLn10 * arg);
   arg = 471.78 * invtk + 25.9290 - 3.16967 * dlogtk - 0.01781 * salt_lim + 0.0001122 * s2;
-  c.k2 = bexp(-kLn10 * arg);
+  c.k2 = ex(-kLn10 * arg);
 
   // kb, Dickson 1990 (co2calc.F90:529-551)
   arg = (-8966.90 - 2890.53 * sqrts - 77.942 * salt_lim + 1.728 * salt_lim * sqrts - 0.0996 * s2) * invtk +
@@ -120,9 +122,9 @@ __device__ __forceinline__ void co3_coeffs(bool deep, double depth, double temp,
   // reference's two factors.  Production build: one exponential of the summed argument
   // (identical up to the rounding of one addition, ~1e-16 relative * |arg|).
 #ifdef BGC_STRICT
-#define K_OF(arg_, dV_, Kap_) (bexp(arg_) * (deep ? kfac((dV_), (Kap_), press_bar, invRtk) : 1.0))
+#define K_OF(arg_, dV_, Kap_) (ex(arg_) * (deep ? kfac((dV_), (Kap_), press_bar, invRtk, ex) : 1.0))
 #else
-#define K_OF(arg_, dV_, Kap_) bexp((arg_) + (deep ? (-(dV_) + 0.5 * (Kap_) * press_bar) * press_bar * invRtk : 0.0))
+#define K_OF(arg_, dV_, Kap_) ex((arg_) + (deep ? (-(dV_) + 0.5 * (Kap_) * press_bar) * press_bar * invRtk : 0.0))
 #endif
   c.kb = K_OF(arg, -29.48 + (0.1622 - 0.002608 * temp) * temp, -2.84 * 0.001);
   // k1p, k2p, k3p: DOE 1994 (co2calc.F90:560-637)
@@ -342,9 +344,10 @@ __device__ __forceinline__ double solve_htotal(const Co3Consts &k, const Co3Tota
 }
 
 // comp_co3_sat_vals, Mucci 1983 + Millero 1979 (co2calc.F90:1096-1238)
+template <class EXP>
 __device__ __forceinline__ void co3_sat_vals(bool deep, double depth, double temp, double salt,
-                                             double &co3_sat_calc, double &co3_sat_arag) {
-  const double press_bar = press_bar_of_depth(depth);
+                                             double &co3_sat_calc, double &co3_sat_arag, const EXP &ex) {
+  const double press_bar = press_bar_of_depth(depth, ex);
   const double salt_lim = fmax(salt, kSaltMin);
   const double tk = kT0Kelvin + temp;
   const double log10tk = cdiv(blog(tk), kLn10, 1.0 / kLn10);   // :1161-1164
@@ -364,14 +367,14 @@ __device__ __forceinline__ void co3_sat_vals(bool deep, double depth, double tem
   const double deltaV = -48.76 + 0.5304 * temp;
   const double Kappa = (-11.76 + 0.3692 * temp) * 0.001;
 #ifdef BGC_STRICT
-  double K_calc = bexp(arg_calc), K_arag = bexp(arg_arag);
+  double K_calc = ex(arg_calc), K_arag = ex(arg_arag);
   if (deep) {
-    K_calc *= kfac(deltaV, Kappa, press_bar, invRtk);
-    K_arag *= kfac(deltaV + 2.8, Kappa, press_bar, invRtk);
+    K_calc *= kfac(deltaV, Kappa, press_bar, invRtk, ex);
+    K_arag *= kfac(deltaV + 2.8, Kappa, press_bar, invRtk, ex);
   }
 #else   // one exponential of the summed argument, as in co3_coeffs
-  const double K_calc = bexp(arg_calc + (deep ? (-deltaV + 0.5 * Kappa * press_bar) * press_bar * invRtk : 0.0));
-  const double K_arag = bexp(arg_arag + (deep ? (-(deltaV + 2.8) + 0.5 * Kappa * press_bar) * press_bar * invRtk : 0.0));
+  const double K_calc = ex(arg_calc + (deep ? (-deltaV + 0.5 * Kappa * press_bar) * press_bar * invRtk : 0.0));
+  const double K_arag = ex(arg_arag + (deep ? (-(deltaV + 2.8) + 0.5 * Kappa * press_bar) * press_bar * invRtk : 0.0));
 #endif
 
   const double inv_Ca = fdiv((35.0 / 0.01028), salt_lim);

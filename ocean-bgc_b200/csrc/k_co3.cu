@@ -64,12 +64,15 @@ co3_cells_kernel(const __grid_constant__ Co3Args A) {
     ph_prev_alt = A.ph_prev_alt[cell];
   }
   const bool deep = k > 0;   // the reference's (k > 1), 1-based
+  __shared__ double s_exp2[64];
+  exp_table_load(s_exp2);
+  const ExpTable ex{s_exp2};
 
   // Both comp_CO3terms calls of a cell receive the SAME DIC/ALK/PO4/SiO3/T/S
   // (BGC_mod.F90:953 vs :975 — the alternative-CO2 call passes DIC_loc, not
   // DIC_ALT_CO2_loc), so the equilibrium constants are computed once.
   Co3Consts K;
-  co3_coeffs<false>(deep, depth, temp, salt, K);
+  co3_coeffs<false>(deep, depth, temp, salt, K, ex);
   const Co3Totals tot = co3_totals(dic, alk, po4, sio3);
 
   double lo, hi;
@@ -92,7 +95,7 @@ co3_cells_kernel(const __grid_constant__ Co3Args A) {
   }
 
   double sat_c, sat_a;
-  co3_sat_vals(deep, depth, temp, salt, sat_c, sat_a);
+  co3_sat_vals(deep, depth, temp, salt, sat_c, sat_a, ex);
 
   if (!in_range) return;
   if (active) {
@@ -185,7 +188,7 @@ __device__ __forceinline__ SurfaceCo2 co2calc_1point(double temp, double salt, d
                                                      double pt_in, double sit_in, double phlo, double phhi,
                                                      double xco2_in, double atmpres, unsigned &st) {
   Co3Consts K;
-  co3_coeffs<true>(false, 0.0, temp, salt, K);
+  co3_coeffs<true>(false, 0.0, temp, salt, K, ExpPoly());
   const Co3Totals tot = co3_totals(dic_in, ta_in, pt_in, sit_in);
   const double htotal = solve_htotal(K, tot, phlo, phhi, st);
 
