@@ -312,11 +312,8 @@ def main():
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     args.mesh_columns = args.columns
     column0 = rank * args.columns
-    if args.strong and args.impl != "reference":   # contiguous slabs of ceil(columns / N), the last one shorter
-        per = (args.columns + world - 1) // world
-        per += per & 1   # even slabs keep every level row 16-byte aligned (bulk-copy path of the sweep)
-        column0 = rank * per
-        args.columns = max(0, min(per, args.mesh_columns - column0))
+    if args.strong and args.impl != "reference":   # contiguous even slabs, the last one shorter (sharding.slab)
+        column0, args.columns = ge.load_package().sharding.slab(rank, world, args.mesh_columns, even=True)
     if args.impl == "reference":
         return run_reference(args, rank, world)
 

@@ -8,15 +8,23 @@ vector (bgc_inventory_allreduce).
 """
 
 
-def slab(rank, world, n_columns):
-    """(first_column, n_local) of rank's contiguous slab; slabs differ by at most one column."""
+def slab(rank, world, n_columns, even=False):
+    """(first_column, n_local) of rank's contiguous slab.  By default the slabs differ by at most
+    one column.  even=True makes every slab but the last an even number of columns
+    (ceil(n/world) rounded up to even): with an even numColumnsMax every level row of the device
+    arrays stays 16-byte aligned, which the column sweep needs for its bulk (TMA) copies."""
     if world < 1 or not (0 <= rank < world) or n_columns < 0:
         raise ValueError("bad slab request rank=%r world=%r n=%r" % (rank, world, n_columns))
+    if even:
+        per = -(-n_columns // world)
+        per += per & 1
+        first = min(rank * per, n_columns)
+        return first, max(0, min(per, n_columns - first))
     base, rem = divmod(n_columns, world)
     n_local = base + (1 if rank < rem else 0)
     first = rank * base + min(rank, rem)
     return first, n_local
 
 
-def slabs(world, n_columns):
-    return [slab(r, world, n_columns) for r in range(world)]
+def slabs(world, n_columns, even=False):
+    return [slab(r, world, n_columns, even) for r in range(world)]

@@ -64,3 +64,21 @@ def test_two_rank_slabs_reproduce_the_unsharded_mesh(tmp_path):
     for p in parts:
         np.testing.assert_allclose(p["inv"][:30], want[:30], rtol=1e-12, atol=1e-18)
         assert p["inv"][60] == want[60] and p["inv"][61] == want[61]
+
+
+def test_slab_plans():
+    sh = parity.pkg.sharding
+    for n in (0, 1, 7, 101, 235160):
+        for w in (1, 2, 3, 8):
+            for even in (False, True):
+                plan = sh.slabs(w, n, even)
+                assert sum(c for _, c in plan) == n
+                pos = 0
+                for first, c in plan:          # contiguous, in rank order, no overlap
+                    assert first == pos or c == 0
+                    pos += c
+                if even:                       # every non-empty slab but the last one is even
+                    nonempty = [c for _, c in plan if c]
+                    assert all(c % 2 == 0 for c in nonempty[:-1])
+    assert sh.slabs(8, 235160, even=True)[0] == (0, 29396)
+    assert sh.slabs(8, 235160)[0] == (0, 29395)
