@@ -1,0 +1,1563 @@
+#!/usr/bin/env python3
+"""f90c — a Fortran-90-subset to C translator, written for ONE purpose: to turn the
+unmodified reference sources of E3SM-Project/Ocean-BGC (/root/reference/*.F90) into a
+shared library that can be RUN in an image that has no Fortran compiler.
+
+TEST INFRASTRUCTURE ONLY (see bgc_oracle.h).  The output goes to oracle/_ref/ (git-ignored;
+nothing derived from the reference sources is committed) and is used to PIN the hand-written
+oracle: the translation is mechanical — statement by statement, expression by expression,
+parentheses and left-to-right evaluation order kept, `x**n` handed to the same GCC builtin
+(`__builtin_powi`) that gfortran's front end emits, literals kept in the precision they are
+written in (a `1.00e-8` stays a float32 constant) — and the C is compiled by the same GCC
+middle/back end that `gfortran -O2` uses (`gcc -O2 -ffp-contract=off -fno-math-errno`, no
+`-march`: plain x86-64 has no FMA, so gfortran contracts nothing either).
+
+Supported subset = what the reference uses, nothing more: modules, `use`, named constants,
+derived types with scalar / fixed-shape / allocatable components, module variables (emitted
+thread-local: the reference keeps solver state in module SAVE variables), subroutines and
+functions with by-reference arguments, `if / else if / else`, counted and endless `do`,
+`exit`, `cycle`, `return`, `select case` on integers, `allocate / deallocate`, whole-array and
+`(:)`-section assignments, `sum`, `merge`, `max`, `min`, `size`, array constructors, character
+assignment with `trim` and `//`.  Anything else stops the translation with the file and line.
+
+Usage:  f90c.py -o OUT.c -m META.json  A.F90 B.F90 ...   (files in module-dependency order)
+"""
+import json
+import re
+import sys
+
+# ----------------------------------------------------------------------------- source reader
+
+
+class Line:
+    __slots__ = ("text", "file", "no")
+
+    def __init__(self, text, file, no):
+        self.text, self.file, self.no = text, file, no
+
+
+def strip_comment(s):
+    out, q = [], None
+    for ch in s:
+        if q:
+            out.append(ch)
+            if ch == q:
+                q = None
+        elif ch in "'\"":
+            q = ch
+            out.append(ch)
+        elif ch == "!":
+            break
+        else:
+            out.append(ch)
+    return "".join(out)
+
+
+def read_source(path, defines=()):
+    """cpp conditionals (#ifdef/#ifndef/#else/#endif), comments, continuation lines."""
+    short = path.rsplit("/", 1)[-1]
+    lines, stack, active = [], [], True
+    cur, cur_no = "", 0
+    for no, raw in enumerate(open(path, encoding="latin-1"), 1):
+        s = raw.rstrip("\n")
+        if s.lstrip().startswith("#"):
+            d = s.lstrip()[1:].split()
+            if d[0] in ("ifdef", "ifndef"):
+                stack.append(active)
+                cond = d[1] in defines
+                active = active and (cond if d[0] == "ifdef" else not cond)
+            elif d[0] == "else":
+                active = stack[-1] and not active
+            elif d[0] == "endif":
+                active = stack.pop()
+            else:
+                raise SystemExit(f"{short}:{no}: unsupported cpp directive {s!r}")
+            continue
+        if not active:
+            continue
+        s = strip_comment(s).replace("\t", " ").rstrip()
+        if not s.strip():
+            continue
+        if cur:
+            t = s.lstrip()
+            if t.startswith("&"):
+                t = t[1:]
+            cur += " " + t
+        else:
+            cur, cur_no = s, no
+        if cur.endswith("&"):
+            cur = cur[:-1]
+            continue
+        lines.append(Line(cur.strip(), short, cur_no))
+        cur = ""
+    return lines
+
+
+# ----------------------------------------------------------------------------- tokens
+
+TOK = re.compile(r"""
+   (?P<str>'(?:[^']|'')*'|"(?:[^"]|"")*")
+ | (?P<dot>\.(?:and|or|not|eqv|neqv|eq|ne|lt|le|gt|ge|true|false)\.)
+ | (?P<num>(?:\d+\.(?![a-zA-Z]+\.)\d*|\.\d+|\d+)(?:[edED][+-]?\d+)?(?:_\w+)?)
+ | (?P<id>[A-Za-z]\w*)
+ | (?P<op>\*\*|//|==|/=|<=|>=|=>|::|\(/|/\)|[-+*/()=,:%<>])
+ | (?P<ws>\s+)
+""", re.X | re.I)
+
+
+def tokenize(s, where):
+    out, pos = [], 0
+    while pos < len(s):
+        m = TOK.match(s, pos)
+        if not m:
+            raise SystemExit(f"{where}: cannot tokenize at {s[pos:pos+20]!r}")
+        pos = m.end()
+        k = m.lastgroup
+        v = m.group(k)
+        if k == "ws":
+            continue
+        if k in ("id", "dot"):
+            v = v.lower()
+        if k == "num":
+            v = v.lower()
+        out.append((k, v))
+    return out
+
+
+# ----------------------------------------------------------------------------- AST
+
+class Node:
+    pass
+
+
+class Num(Node):
+    def __init__(self, text):
+        self.text = text
+
+
+class Str(Node):
+    def __init__(self, val):
+        self.val = val
+
+
+class Log(Node):
+    def __init__(self, val):
+        self.val = val
+
+
+class Bin(Node):
+    def __init__(self, op, l, r):
+        self.op, self.l, self.r = op, l, r
+
+
+class Un(Node):
+    def __init__(self, op, e):
+        self.op, self.e = op, e
+
+
+class Paren(Node):
+    def __init__(self, e):
+        self.e = e
+
+
+class ArrCons(Node):
+    def __init__(self, items):
+        self.items = items
+
+
+class Colon(Node):
+    def __init__(self, lo=None, hi=None):
+        self.lo, self.hi = lo, hi
+
+
+class Kw(Node):
+    def __init__(self, name, e):
+        self.name, self.e = name, e
+
+
+class Ref(Node):
+    """designator: parts = [(name, args|None), ...] joined by %"""
+
+    def __init__(self, parts):
+        self.parts = parts
+
+
+class Parser:
+    def __init__(self, toks, where):
+        self.t, self.i, self.where = toks, 0, where
+
+    def peek(self, k=0):
+        return self.t[self.i + k] if self.i + k < len(self.t) else (None, None)
+
+    def next(self):
+        tk = self.peek()
+        self.i += 1
+        return tk
+
+    def accept(self, v):
+        if self.peek()[1] == v and self.peek()[0] != "str":
+            self.i += 1
+            return True
+        return False
+
+    def expect(self, v):
+        if not self.accept(v):
+            raise SystemExit(f"{self.where}: expected {v!r}, found {self.peek()[1]!r}")
+
+    def at_end(self):
+        return self.i >= len(self.t)
+
+    # precedence climbing, Fortran order
+    def expr(self):
+        l = self.p_or()
+        while self.peek()[1] in (".eqv.", ".neqv."):
+            op = self.next()[1]
+            l = Bin(op, l, self.p_or())
+        return l
+
+    def p_or(self):
+        l = self.p_and()
+        while self.peek()[1] == ".or.":
+            self.next()
+            l = Bin(".or.", l, self.p_and())
+        return l
+
+    def p_and(self):
+        l = self.p_not()
+        while self.peek()[1] == ".and.":
+            self.next()
+            l = Bin(".and.", l, self.p_not())
+        return l
+
+    def p_not(self):
+        if self.peek()[1] == ".not.":
+            self.next()
+            return Un(".not.", self.p_not())
+        return self.p_rel()
+
+    REL = {"==": "==", "/=": "!=", "<": "<", "<=": "<=", ">": ">", ">=": ">=",
+           ".eq.": "==", ".ne.": "!=", ".lt.": "<", ".le.": "<=", ".gt.": ">", ".ge.": ">="}
+
+    def p_rel(self):
+        l = self.p_cat()
+        k, v = self.peek()
+        if k != "str" and v in self.REL:
+            self.next()
+            return Bin(self.REL[v], l, self.p_cat())
+        return l
+
+    def p_cat(self):
+        l = self.p_add()
+        while self.peek()[1] == "//" and self.peek()[0] == "op":
+            self.next()
+            l = Bin("//", l, self.p_add())
+        return l
+
+    def p_add(self):
+        k, v = self.peek()
+        if k == "op" and v in "+-":
+            self.next()
+            l = self.p_mul()
+            if v == "-":
+                l = Un("-", l)
+        else:
+            l = self.p_mul()
+        while self.peek()[0] == "op" and self.peek()[1] in ("+", "-"):
+            op = self.next()[1]
+            l = Bin(op, l, self.p_mul())
+        return l
+
+    def p_mul(self):
+        l = self.p_pow()
+        while self.peek()[0] == "op" and self.peek()[1] in ("*", "/"):
+            op = self.next()[1]
+            l = Bin(op, l, self.p_pow())
+        return l
+
+    def p_pow(self):
+        l = self.p_primary()
+        if self.peek() == ("op", "**"):
+            self.next()
+            k, v = self.peek()
+            if k == "op" and v in "+-":      # a ** -b (extension); keep it working
+                self.next()
+                r = self.p_pow()
+                r = Un("-", r) if v == "-" else r
+            else:
+                r = self.p_pow()             # right associative
+            return Bin("**", l, r)
+        return l
+
+    def p_primary(self):
+        k, v = self.next()
+        if k == "num":
+            return Num(v)
+        if k == "str":
+            q = v[0]
+            return Str(v[1:-1].replace(q + q, q))
+        if k == "dot" and v in (".true.", ".false."):
+            return Log(v == ".true.")
+        if k == "op" and v == "(":
+            e = self.expr()
+            self.expect(")")
+            return Paren(e)
+        if k == "op" and v == "(/":
+            items = [self.expr()]
+            while self.accept(","):
+                items.append(self.expr())
+            self.expect("/)")
+            return ArrCons(items)
+        if k == "id":
+            parts = []
+            name = v
+            while True:
+                args = None
+                if self.peek() == ("op", "("):
+                    self.next()
+                    args = self.arglist()
+                parts.append((name, args))
+                if self.peek() == ("op", "%"):
+                    self.next()
+                    k2, name = self.next()
+                    if k2 != "id":
+                        raise SystemExit(f"{self.where}: component name expected")
+                    continue
+                break
+            return Ref(parts)
+        raise SystemExit(f"{self.where}: unexpected token {v!r}")
+
+    def arglist(self):
+        args = []
+        if self.accept(")"):
+            return args
+        while True:
+            args.append(self.arg())
+            if self.accept(","):
+                continue
+            self.expect(")")
+            return args
+
+    def arg(self):
+        if self.peek()[0] == "id" and self.peek(1) == ("op", "="):
+            name = self.next()[1]
+            self.next()
+            return Kw(name, self.expr())
+        if self.peek() == ("op", ":"):
+            self.next()
+            if self.peek()[1] in (",", ")"):
+                return Colon()
+            return Colon(None, self.expr())
+        e = self.expr()
+        if self.peek() == ("op", ":"):
+            self.next()
+            if self.peek()[1] in (",", ")"):
+                return Colon(e, None)
+            return Colon(e, self.expr())
+        return e
+
+
+# ----------------------------------------------------------------------------- types / symbols
+
+class T:
+    """base: int | real | logical | char | type ; kind in bytes ; rank"""
+
+    def __init__(self, base, kind=4, rank=0, tname=None, clen=None):
+        self.base, self.kind, self.rank, self.tname, self.clen = base, kind, rank, tname, clen
+
+    def scalar(self):
+        return T(self.base, self.kind, 0, self.tname, self.clen)
+
+    def ctype(self):
+        if self.base == "int":
+            return "long long" if self.kind == 8 else "int"
+        if self.base == "real":
+            return "double" if self.kind == 8 else "float"
+        if self.base == "logical":
+            return "int"
+        if self.base == "char":
+            return "char"
+        return f"struct {self.tname}"
+
+    def code(self):
+        if self.base == "int":
+            return "i8" if self.kind == 8 else "i4"
+        if self.base == "real":
+            return "r8" if self.kind == 8 else "r4"
+        if self.base == "logical":
+            return "log"
+        if self.base == "char":
+            return f"char{self.clen}"
+        return f"type:{self.tname}"
+
+
+class Sym:
+    def __init__(self, name, typ, dims=None, alloc=False, param=False, init=None, intent=None,
+                 private=False):
+        self.name, self.typ, self.dims, self.alloc = name, typ, dims, alloc
+        self.param, self.init, self.intent, self.private = param, init, intent, private
+        self.dummy = False
+        self.cname = None        # C identifier of the object
+        self.module = None
+        self.is_result = False
+        self.local_const = False
+
+
+class DType:
+    def __init__(self, name, cname):
+        self.name, self.cname, self.fields = name, cname, []   # list of Sym
+
+
+class Proc:
+    def __init__(self, name, kind, args, result, module, line):
+        self.name, self.kind, self.args, self.result, self.module, self.line = \
+            name, kind, args, result, module, line
+        self.syms, self.body, self.decl_lines = {}, [], []
+        self.cname = f"{module.name}__{name}"
+        self.rtype = None
+
+
+class Module:
+    def __init__(self, name):
+        self.name, self.uses, self.syms, self.types, self.procs = name, [], {}, {}, {}
+        self.decl_lines = []
+        self.default_private = False
+
+
+# ----------------------------------------------------------------------------- translator
+
+INTRINSIC_ELEMENTAL = {"exp": "exp", "log": "log", "log10": "log10", "sqrt": "sqrt",
+                       "tanh": "tanh", "sin": "sin", "cos": "cos", "atan": "atan"}
+
+PRELUDE = r"""/* GENERATED by oracle/f90c.py from the reference Fortran sources — do not edit, do not commit. */
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#ifndef REF_TLS
+#define REF_TLS __thread
+#endif
+typedef struct { void *p; int n1, n2, n3; } fa_t;
+typedef struct { int n; char s[1024]; } fstr_t;
+static inline fstr_t f_lit(const char *s, int n) { fstr_t r; r.n = n; memcpy(r.s, s, n); return r; }
+static inline fstr_t f_var(const char *s, int n) { fstr_t r; r.n = n; memcpy(r.s, s, n); return r; }
+static inline fstr_t f_trim(fstr_t a) { while (a.n > 0 && a.s[a.n - 1] == ' ') a.n--; return a; }
+static inline fstr_t f_cat(fstr_t a, fstr_t b) { memcpy(a.s + a.n, b.s, b.n); a.n += b.n; return a; }
+static inline void f_assign(char *d, int dn, fstr_t v) {
+  int n = v.n < dn ? v.n : dn; memcpy(d, v.s, n); if (n < dn) memset(d + n, ' ', dn - n); }
+/* MAX/MIN as gfortran expands them without -ffast-math: m = a1; if (a2 > m) m = a2; ... */
+#define F_MAX2(T, a, b) ({ T _m = (a); T _b = (b); if (_b > _m) _m = _b; _m; })
+#define F_MIN2(T, a, b) ({ T _m = (a); T _b = (b); if (_b < _m) _m = _b; _m; })
+static inline long long f_ipow(long long b, long long e) {
+  long long r = 1; if (e < 0) return (b == 1) ? 1 : (b == -1 ? ((e & 1) ? -1 : 1) : 0);
+  while (e) { if (e & 1) r *= b; b *= b; e >>= 1; } return r; }
+#ifdef REF_POISON
+static void *f_alloc(size_t nbytes) { void *p = malloc(nbytes ? nbytes : 1); memset(p, 0xFF, nbytes); return p; }
+#else
+static void *f_alloc(size_t nbytes) { return malloc(nbytes ? nbytes : 1); }
+#endif
+"""
+
+
+class Translator:
+    def __init__(self):
+        self.modules = {}
+        self.order = []
+        self.out = []
+        self.tmp = 0
+        self.cur_line = None
+        self.scope_proc = None
+        self.scope_mod = None
+
+    # ---------------------------------------------------------------- errors
+    def err(self, msg):
+        ln = self.cur_line
+        raise SystemExit(f"{ln.file}:{ln.no}: {msg}\n    {ln.text}")
+
+    # ---------------------------------------------------------------- pass 1: structure
+    def load(self, path):
+        lines = read_source(path)
+        i = 0
+        mod = proc = dtype = None
+        in_contains = False
+        while i < len(lines):
+            ln = lines[i]
+            self.cur_line = ln
+            i += 1
+            toks = tokenize(ln.text, f"{ln.file}:{ln.no}")
+            w0 = toks[0][1] if toks[0][0] == "id" else None
+            w1 = toks[1][1] if len(toks) > 1 and toks[1][0] == "id" else None
+            if w0 == "module" and w1 and w1 != "procedure":
+                mod = Module(w1)
+                self.modules[w1] = mod
+                self.order.append(mod)
+                in_contains = False
+                continue
+            if w0 == "end" or (w0 and w0.startswith("end") and w0 in
+                               ("endmodule", "endsubroutine", "endfunction", "endtype")):
+                what = w1 if w0 == "end" else w0[3:]
+                if what == "module":
+                    mod = None
+                    continue
+                if what in ("subroutine", "function"):
+                    proc = None
+                    continue
+                if what == "type":
+                    dtype = None
+                    continue
+                if proc is None:
+                    self.err("unexpected END")
+            if mod is None:
+                self.err("statement outside a module")
+            self.scope_mod, self.scope_proc = mod, None
+            if dtype is not None:
+                self.decl(toks, dtype=dtype, mod=mod)
+                continue
+            if proc is None:
+                if w0 == "contains":
+                    in_contains = True
+                    continue
+                if self.proc_header(toks, mod, ln) is not None:
+                    proc = self.proc_header_result
+                    continue
+                if w0 == "use":
+                    mod.uses.append(toks[1][1])
+                    continue
+                if w0 == "implicit" or w0 == "save":
+                    continue
+                if w0 == "private" and len(toks) == 1:
+                    mod.default_private = True
+                    continue
+                if w0 in ("private", "public") and (len(toks) == 1 or toks[1][1] == "::"):
+                    continue
+                if w0 == "type" and toks[1][1] != "(":
+                    name = [v for k, v in toks if k == "id"][-1]
+                    dtype = DType(name, f"{mod.name}__{name}")
+                    mod.types[name] = dtype
+                    continue
+                self.decl(toks, mod=mod)
+                continue
+            # inside a procedure: keep the raw statement, classify in pass 2
+            proc.body.append((ln, toks))
+        return self
+
+    def proc_header(self, toks, mod, ln):
+        ids = [v for k, v in toks]
+        self.proc_header_result = None
+        for kw in ("subroutine", "function"):
+            if kw in ids and toks[ids.index(kw)][0] == "id":
+                j = ids.index(kw)
+                # `real(r8) function f(x)` allowed; a declaration would have '::' before
+                if "::" in ids[:j] or (j > 0 and ids[0] not in
+                                       ("real", "integer", "logical", "pure", "elemental", "recursive")):
+                    return None
+                name = ids[j + 1]
+                args, result = [], name
+                k = j + 2
+                if k < len(ids) and ids[k] == "(":
+                    k += 1
+                    while ids[k] != ")":
+                        if ids[k] != ",":
+                            args.append(ids[k])
+                        k += 1
+                    k += 1
+                if k < len(ids) and ids[k] == "result":
+                    result = ids[k + 2]
+                p = Proc(name, kw, args, result if kw == "function" else None, mod, ln)
+                mod.procs[name] = p
+                self.proc_header_result = p
+                return p
+        return None
+
+    # ---------------------------------------------------------------- declarations
+    def const_int(self, e, scope_syms):
+        """Integer constant folding for kinds, lengths and extents."""
+        if isinstance(e, Num):
+            if re.fullmatch(r"\d+", e.text):
+                return int(e.text)
+            self.err(f"integer constant expected, got {e.text}")
+        if isinstance(e, Paren):
+            return self.const_int(e.e, scope_syms)
+        if isinstance(e, Un) and e.op == "-":
+            return -self.const_int(e.e, scope_syms)
+        if isinstance(e, Bin) and e.op in "+-*/":
+            a, b = self.const_int(e.l, scope_syms), self.const_int(e.r, scope_syms)
+            return {"+": a + b, "-": a - b, "*": a * b, "/": int(a / b) if b else 0}[e.op]
+        if isinstance(e, Kw):
+            return self.const_int(e.e, scope_syms)
+        if isinstance(e, Ref) and len(e.parts) == 1:
+            name, args = e.parts[0]
+            if args is None:
+                s = self.lookup(name)
+                if s is None or not s.param or s.init is None:
+                    self.err(f"{name} is not a named integer constant")
+                return self.const_int(s.init, scope_syms)
+            if name == "kind":
+                a = args[0]
+                if isinstance(a, Log):
+                    return 4
+                if isinstance(a, Num):
+                    return self.num_type(a.text).kind
+            if name == "selected_int_kind":
+                r = self.const_int(args[0], scope_syms)
+                return 1 if r <= 2 else 2 if r <= 4 else 4 if r <= 9 else 8
+            if name == "selected_real_kind":
+                p = self.const_int(args[0], scope_syms)
+                return 4 if p <= 6 else 8 if p <= 15 else 16
+        self.err("unsupported constant expression")
+
+    def parse_typespec(self, p):
+        """p: Parser positioned at the type keyword.  Returns T (scalar)."""
+        k, w = p.next()
+        if w == "double":
+            p.next()
+            return T("real", 8)
+        if w == "type":
+            p.expect("(")
+            name = p.next()[1]
+            p.expect(")")
+            return T("type", 0, 0, self.find_type(name).cname)
+        base = {"real": "real", "integer": "int", "logical": "logical", "character": "char"}[w]
+        kind, clen = 4, 1
+        if p.accept("*"):
+            kind = int(p.next()[1])
+        elif p.peek() == ("op", "("):
+            p.next()
+            if p.peek()[0] == "id" and p.peek()[1] in ("kind", "len") and p.peek(1) == ("op", "="):
+                p.next()
+                p.next()
+            e = p.expr()
+            p.expect(")")
+            v = self.const_int(e, None)
+            if base == "char":
+                clen = v
+            else:
+                kind = v
+        if base == "char":
+            return T("char", 1, 0, None, clen)
+        return T(base, kind)
+
+    def decl(self, toks, dtype=None, mod=None, proc=None):
+        p = Parser(toks, f"{self.cur_line.file}:{self.cur_line.no}")
+        typ = self.parse_typespec(p)
+        attrs = {"dims": None}
+        while p.accept(","):
+            a = p.next()[1]
+            if a == "dimension":
+                p.expect("(")
+                attrs["dims"] = p.arglist()
+            elif a == "intent":
+                p.expect("(")
+                attrs["intent"] = p.next()[1]
+                if attrs["intent"] == "in" and p.peek()[1] == "out":
+                    p.next()
+                    attrs["intent"] = "inout"
+                p.expect(")")
+            elif a in ("parameter", "allocatable", "public", "private", "save", "target"):
+                attrs[a] = True
+            else:
+                self.err(f"unsupported attribute {a}")
+        p.accept("::")
+        while True:
+            k, name = p.next()
+            if k != "id":
+                self.err("entity name expected")
+            dims = attrs["dims"]
+            if p.peek() == ("op", "("):
+                p.next()
+                dims = p.arglist()
+            init = None
+            if p.accept("="):
+                init = p.expr()
+            t = T(typ.base, typ.kind, len(dims) if dims else 0, typ.tname, typ.clen)
+            s = Sym(name, t, dims, attrs.get("allocatable", False), attrs.get("parameter", False),
+                    init, attrs.get("intent"), attrs.get("private", False))
+            if dtype is not None:
+                s.cname = name
+                dtype.fields.append(s)
+            elif proc is not None:
+                if name in proc.syms:
+                    self.err(f"duplicate declaration of {name}")
+                s.cname = name + "_"
+                proc.syms[name] = s
+            else:
+                s.cname = f"{mod.name}__{name}"
+                s.module = mod
+                mod.syms[name] = s
+            if not p.accept(","):
+                break
+        if not p.at_end():
+            self.err(f"trailing tokens in declaration: {p.peek()[1]!r}")
+
+    # ---------------------------------------------------------------- lookup
+    def find_type(self, name, mod=None, seen=None):
+        mod = mod or self.scope_mod
+        seen = seen if seen is not None else set()
+        if mod.name in seen:
+            return None
+        seen.add(mod.name)
+        if name in mod.types:
+            return mod.types[name]
+        for u in mod.uses:
+            if u in self.modules:
+                r = self.find_type(name, self.modules[u], seen)
+                if r:
+                    return r
+        if len(seen) == 1:
+            self.err(f"unknown derived type {name}")
+        return None
+
+    def type_by_cname(self, cname):
+        for m in self.order:
+            for d in m.types.values():
+                if d.cname == cname:
+                    return d
+        self.err(f"unknown struct {cname}")
+
+    def lookup_mod(self, name, mod, seen, through_use):
+        if mod.name in seen:
+            return None
+        seen.add(mod.name)
+        s = mod.syms.get(name)
+        if s is not None and not (through_use and s.private):
+            return s
+        for u in mod.uses:
+            if u in self.modules:
+                r = self.lookup_mod(name, self.modules[u], seen, True)
+                if r is not None:
+                    return r
+        return None
+
+    def lookup(self, name):
+        if self.scope_proc is not None and name in self.scope_proc.syms:
+            return self.scope_proc.syms[name]
+        return self.lookup_mod(name, self.scope_mod, set(), False)
+
+    def lookup_proc(self, name, mod=None, seen=None):
+        mod = mod or self.scope_mod
+        seen = seen if seen is not None else set()
+        if mod.name in seen:
+            return None
+        seen.add(mod.name)
+        if name in mod.procs:
+            return mod.procs[name]
+        for u in mod.uses:
+            if u in self.modules:
+                r = self.lookup_proc(name, self.modules[u], seen)
+                if r:
+                    return r
+        return None
+
+    # ---------------------------------------------------------------- expression typing / emission
+    def num_type(self, text):
+        m = re.fullmatch(r"([\d.]+)(?:([ed])([+-]?\d+))?(?:_(\w+))?", text)
+        if not m:
+            self.err(f"bad numeric literal {text}")
+        mant, ech, ex, ksuf = m.groups()
+        is_real = "." in mant or ech is not None
+        kind = 4
+        if ech == "d":
+            kind = 8
+        if ksuf:
+            kind = int(ksuf) if ksuf.isdigit() else self.const_int(Ref([(ksuf, None)]), None)
+        return T("real" if is_real else "int", kind)
+
+    def num_c(self, text):
+        m = re.fullmatch(r"([\d.]+)(?:([ed])([+-]?\d+))?(?:_(\w+))?", text)
+        mant, ech, ex, ksuf = m.groups()
+        t = self.num_type(text)
+        if t.base == "int":
+            return (mant + "LL") if t.kind == 8 else mant, t
+        if "." not in mant:
+            mant += "."
+        s = mant + (("e" + ex) if ex is not None else "")
+        if s.startswith("."):
+            s = "0" + s
+        if s.endswith(".") or ".e" in s:
+            s = s.replace(".e", ".0e") if ".e" in s else s + "0"
+        return (s + "f") if t.kind == 4 else s, t
+
+    @staticmethod
+    def promote(a, b):
+        order = {"int": 0, "real": 1}
+        if a.base not in order or b.base not in order:
+            return a
+        if a.base == b.base:
+            return T(a.base, max(a.kind, b.kind))
+        r = a if a.base == "real" else b
+        return T("real", r.kind)
+
+    def sym_total_size(self, s, obj):
+        """C expression: number of elements of array object `obj` (C lvalue / name) of Sym s."""
+        if s.alloc:
+            return " * ".join(f"({obj}).n{d + 1}" for d in range(s.typ.rank))
+        return " * ".join(f"({self.const_int(d, None)})" for d in s.dims)
+
+    def sym_extent(self, s, obj, d):
+        if s.alloc:
+            return f"({obj}).n{d + 1}"
+        return str(self.const_int(s.dims[d], None))
+
+    def resolve_ref(self, ref, ivar):
+        """Walk a designator.  Returns (cexpr, T, is_lvalue).  `ivar`: loop index (0-based C
+        expression) that replaces whole-array references and `:` subscripts, or None."""
+        name, args = ref.parts[0]
+        s = self.lookup(name)
+        if s is None:
+            return None
+        if s.param and not s.local_const and s.typ.rank == 0 and s.module is not None:
+            obj, typ, lval = s.cname, s.typ, False
+        else:
+            obj = s.cname
+            if s.dummy and s.typ.rank == 0:
+                obj = f"(*{s.cname})"
+            typ, lval = s.typ, not s.param
+        cur = s
+        parts = ref.parts
+        for pi, (pname, pargs) in enumerate(parts):
+            if pi > 0:
+                d = self.type_by_cname(typ.tname)
+                f = next((x for x in d.fields if x.name == pname), None)
+                if f is None:
+                    self.err(f"type {d.name} has no component {pname}")
+                obj = f"{obj}.{f.cname}"
+                cur, typ = f, f.typ
+            if pargs is not None:
+                if typ.rank == 0:
+                    self.err(f"{pname} is not an array")
+                if len(pargs) != typ.rank:
+                    self.err(f"rank mismatch on {pname}")
+                idx, stride = [], "1"
+                for dnum, a in enumerate(pargs):
+                    if isinstance(a, Colon):
+                        if a.lo is not None or a.hi is not None:
+                            self.err("only full-range (:) sections are supported")
+                        if ivar is None:
+                            self.err("array section in scalar context")
+                        sub = f"({ivar})"
+                    else:
+                        ce, ct = self.emit(a, ivar)
+                        sub = f"(({ce}) - 1)"
+                    idx.append(sub if stride == "1" else f"{stride} * {sub}")
+                    stride = (f"{stride} * {self.sym_extent(cur, obj, dnum)}" if stride != "1"
+                              else self.sym_extent(cur, obj, dnum))
+                flat = " + ".join(idx)
+                obj = self.elem(cur, obj, flat)
+                typ = typ.scalar()
+            elif typ.rank > 0 and (ivar is not None) and not self.want_whole:
+                obj = self.elem(cur, obj, f"({ivar})")
+                typ = typ.scalar()
+        return obj, typ, lval
+
+    def elem(self, s, obj, flat):
+        et = s.typ.scalar()
+        if s.alloc:
+            if et.base == "char":
+                return f"((char (*)[{et.clen}])({obj}).p)[{flat}]"
+            return f"(({et.ctype()} *)({obj}).p)[{flat}]"
+        return f"{obj}[{flat}]"
+
+    want_whole = False
+
+    def extent_of(self, e):
+        """C expression for the element count if `e` is array-valued, else None."""
+        if isinstance(e, (Num, Str, Log)):
+            return None
+        if isinstance(e, Paren):
+            return self.extent_of(e.e)
+        if isinstance(e, Un):
+            return self.extent_of(e.e)
+        if isinstance(e, Bin):
+            return self.extent_of(e.l) or self.extent_of(e.r)
+        if isinstance(e, ArrCons):
+            return str(len(e.items))
+        if isinstance(e, Kw):
+            return self.extent_of(e.e)
+        if isinstance(e, Ref):
+            name, args = e.parts[0]
+            s = self.lookup(name)
+            if s is None:
+                if name in ("sum", "size", "maxval", "minval", "trim"):
+                    return None
+                if args is not None:
+                    for a in args:
+                        x = self.extent_of(a)
+                        if x:
+                            return x
+                return None
+            obj = f"(*{s.cname})" if (s.dummy and s.typ.rank == 0) else s.cname
+            cur, typ = s, s.typ
+            for pi, (pname, pargs) in enumerate(e.parts):
+                if pi > 0:
+                    d = self.type_by_cname(typ.tname)
+                    f = next((x for x in d.fields if x.name == pname), None)
+                    if f is None:
+                        self.err(f"type {d.name} has no component {pname}")
+                    obj = f"{obj}.{f.cname}"
+                    cur, typ = f, f.typ
+                if pargs is None:
+                    if typ.rank > 0:
+                        return self.sym_total_size(cur, obj)
+                else:
+                    for dnum, a in enumerate(pargs):
+                        if isinstance(a, Colon):
+                            return self.sym_extent(cur, obj, dnum)
+                        x = self.extent_of(a)      # vector subscript
+                        if x is not None:
+                            return x
+                    # element selected: continue into components with a scalar object
+                    obj = self.elem(cur, obj, "0")
+                    typ = typ.scalar()
+            return None
+        return None
+
+    def newtmp(self, base="_t"):
+        self.tmp += 1
+        return f"{base}{self.tmp}"
+
+    def emit(self, e, ivar=None):
+        """Returns (C expression string, T)."""
+        if isinstance(e, Num):
+            return self.num_c(e.text)
+        if isinstance(e, Log):
+            return ("1" if e.val else "0"), T("logical")
+        if isinstance(e, Str):
+            esc = e.val.replace("\\", "\\\\").replace('"', '\\"')
+            return f'f_lit("{esc}", {len(e.val)})', T("char", 1, 0, None, len(e.val))
+        if isinstance(e, Paren):
+            c, t = self.emit(e.e, ivar)
+            return f"({c})", t
+        if isinstance(e, Kw):
+            return self.emit(e.e, ivar)
+        if isinstance(e, Un):
+            c, t = self.emit(e.e, ivar)
+            if e.op == ".not.":
+                return f"(!({c}))", T("logical")
+            return f"(-({c}))", t
+        if isinstance(e, Bin):
+            lc, lt = self.emit(e.l, ivar)
+            rc, rt = self.emit(e.r, ivar)
+            if e.op in (".and.", ".or."):
+                # Fortran does not short-circuit by rule, but every operand here is side-effect free
+                return f"(({lc}) {'&&' if e.op == '.and.' else '||'} ({rc}))", T("logical")
+            if e.op in (".eqv.", ".neqv."):
+                return f"((!!({lc})) {'==' if e.op == '.eqv.' else '!='} (!!({rc})))", T("logical")
+            if e.op in ("==", "!=", "<", "<=", ">", ">="):
+                return f"(({lc}) {e.op} ({rc}))", T("logical")
+            if e.op == "//":
+                lc = self.as_fstr(lc, lt)
+                rc = self.as_fstr(rc, rt)
+                return f"f_cat({lc}, {rc})", T("char", 1, 0, None, 0)
+            if e.op == "**":
+                if rt.base == "int":
+                    if lt.base == "int":
+                        return f"(({lt.ctype()})f_ipow({lc}, {rc}))", lt
+                    fn = "__builtin_powi" if lt.kind == 8 else "__builtin_powif"
+                    return f"{fn}({lc}, {rc})", lt
+                pt = self.promote(lt, rt)
+                fn = "pow" if pt.kind == 8 else "powf"
+                return f"{fn}({lc}, {rc})", pt
+            pt = self.promote(lt, rt)
+            return f"(({lc}) {e.op} ({rc}))", pt
+        if isinstance(e, ArrCons):
+            if ivar is None:
+                self.err("array constructor in scalar context")
+            items = [self.emit(x, None) for x in e.items]
+            t = items[0][1]
+            for _, it in items[1:]:
+                t = self.promote(t, it)
+            arr = ", ".join(c for c, _ in items)
+            return f"(({t.ctype()}[]){{{arr}}})[{ivar}]", t
+        if isinstance(e, Ref):
+            return self.emit_ref(e, ivar)
+        self.err("unsupported expression node")
+
+    def as_fstr(self, c, t):
+        if c.startswith("f_"):
+            return c
+        return f"f_var({c}, {t.clen})"
+
+    def emit_ref(self, e, ivar):
+        name, args = e.parts[0]
+        r = self.resolve_ref(e, ivar)
+        if r is not None:
+            c, t, _ = r
+            if t.rank > 0:
+                self.err(f"whole array {name} in scalar context")
+            return c, t
+        if len(e.parts) != 1 or args is None:
+            self.err(f"unknown name {name}")
+        # user function
+        pr = self.lookup_proc(name)
+        if pr is not None:
+            if pr.kind != "function":
+                self.err(f"{name} is a subroutine")
+            return f"{pr.cname}({self.call_args(pr, args, ivar)})", pr.rtype
+        # intrinsics
+        if name in INTRINSIC_ELEMENTAL:
+            c, t = self.emit(args[0], ivar)
+            if t.base != "real":
+                self.err(f"{name} of a non-real")
+            return f"{INTRINSIC_ELEMENTAL[name]}{'f' if t.kind == 4 else ''}({c})", t
+        if name == "abs":
+            c, t = self.emit(args[0], ivar)
+            if t.base == "real":
+                return f"{'fabs' if t.kind == 8 else 'fabsf'}({c})", t
+            return f"{'llabs' if t.kind == 8 else 'abs'}({c})", t
+        if name in ("max", "min"):
+            parts = [self.emit(a, ivar) for a in args]
+            t = parts[0][1]
+            for _, pt in parts[1:]:
+                t = self.promote(t, pt)
+            mac = "F_MAX2" if name == "max" else "F_MIN2"
+            c = parts[0][0]
+            for pc, _ in parts[1:]:
+                c = f"{mac}({t.ctype()}, {c}, {pc})"
+            return c, t
+        if name == "merge":
+            tc, tt = self.emit(args[0], ivar)
+            fc, ft = self.emit(args[1], ivar)
+            mc, _ = self.emit(args[2], ivar)
+            t = tt
+            return f"(({mc}) ? ({t.ctype()})({tc}) : ({t.ctype()})({fc}))", t
+        if name == "sum":
+            arr = args[0]
+            n = self.extent_of(arr)
+            if n is None:
+                self.err("sum of a scalar")
+            iv = self.newtmp("_i")
+            c, t = self.emit(arr, iv)
+            acc = self.newtmp("_s")
+            zero = "0"
+            return (f"({{ {t.ctype()} {acc} = {zero}; for (int {iv} = 0; {iv} < ({n}); {iv}++) "
+                    f"{acc} += ({c}); {acc}; }})"), t
+        if name == "size":
+            self.want_whole = True
+            n = self.extent_of(args[0])
+            self.want_whole = False
+            if n is None:
+                self.err("size of a scalar")
+            return f"((int)({n}))", T("int", 4)
+        if name == "trim":
+            c, t = self.emit(args[0], ivar)
+            return f"f_trim({self.as_fstr(c, t)})", T("char", 1, 0, None, 0)
+        if name == "real":
+            c, t = self.emit(args[0], ivar)
+            kind = self.const_int(args[1], None) if len(args) > 1 else 4
+            rt = T("real", kind)
+            return f"(({rt.ctype()})({c}))", rt
+        if name == "int":
+            c, t = self.emit(args[0], ivar)
+            return f"((int)({c}))", T("int", 4)
+        if name == "mod":
+            ac, at = self.emit(args[0], ivar)
+            bc, bt = self.emit(args[1], ivar)
+            pt = self.promote(at, bt)
+            if pt.base == "int":
+                return f"(({ac}) % ({bc}))", pt
+            return f"fmod({ac}, {bc})", pt
+        self.err(f"unknown function or intrinsic {name}")
+
+    def call_args(self, pr, args, ivar=None):
+        if len(args) != len(pr.args):
+            self.err(f"{pr.name}: {len(args)} actual arguments for {len(pr.args)} dummies")
+        out = []
+        ordered = [None] * len(pr.args)
+        for pos, a in enumerate(args):
+            if isinstance(a, Kw):
+                if a.name not in pr.args:
+                    self.err(f"{pr.name} has no dummy argument {a.name}")
+                pos, a = pr.args.index(a.name), a.e
+            if ordered[pos] is not None:
+                self.err("argument given twice")
+            ordered[pos] = a
+        for a, dn in zip(ordered, pr.args):
+            ds = pr.syms[dn]
+            if ds.typ.rank > 0:
+                # whole-array actual
+                if not isinstance(a, Ref):
+                    self.err("array actual argument must be a name")
+                self.want_whole = True
+                r = self.resolve_ref(a, None)
+                self.want_whole = False
+                c, t, _ = r
+                out.append(c if not ds.alloc else f"&({c})")
+                continue
+            lv = None
+            if isinstance(a, Ref):
+                r = self.resolve_ref(a, ivar)
+                if r is not None and r[2] and r[1].rank == 0:
+                    lv = r
+            if lv is not None and (lv[1].base, lv[1].kind, lv[1].tname) == \
+                    (ds.typ.base, ds.typ.kind, ds.typ.tname):
+                out.append(f"&({lv[0]})")
+            else:
+                if ds.typ.base == "type":
+                    self.err("derived-type actual must be a variable")
+                if ds.intent in ("out", "inout"):
+                    self.err(f"non-variable actual for intent({ds.intent}) dummy {dn}")
+                c, t = self.emit(a, ivar)
+                out.append(f"&({ds.typ.ctype()}){{{c}}}")
+        return ", ".join(out)
+
+    # ---------------------------------------------------------------- statements
+    def w(self, s):
+        self.out.append("  " * self.ind + s)
+
+    def stmt(self, toks):
+        label = None
+        if (len(toks) > 2 and toks[0][0] == "id" and toks[1] == ("op", ":")
+                and toks[2][0] == "id" and toks[2][1] in ("do", "if", "select")):
+            label, toks = toks[0][1], toks[2:]
+        if (toks[0][0] == "id" and toks[0][1] in ("enddo", "endif", "endselect") and len(toks) == 2
+                and toks[1][0] == "id"):
+            toks = toks[:1]
+        if (toks[0] == ("id", "end") and len(toks) == 3 and toks[2][0] == "id"
+                and toks[1][1] in ("do", "if", "select")):
+            toks = toks[:2]
+        p = Parser(toks, f"{self.cur_line.file}:{self.cur_line.no}")
+        k0, w0 = toks[0]
+        w1 = toks[1][1] if len(toks) > 1 else None
+        # --- block ends
+        if k0 == "id" and w0 in ("end", "enddo", "endif", "endselect"):
+            what = w1 if w0 == "end" else w0[3:]
+            if what == "select":
+                kind = self.blocks.pop()
+                if kind == "case":
+                    self.ind -= 1
+                    self.w("}")
+                else:
+                    assert kind == "select0"
+                self.selvar.pop()
+                self.ind -= 1
+                self.w("}")
+                return
+            kind = self.blocks.pop()
+            if (what, kind) not in (("do", "do"), ("if", "if")):
+                self.err(f"END {what} closes a {kind} block")
+            if kind == "do":
+                lab = self.loopnames.pop()
+                if lab and lab[1]:
+                    self.w(f"_cyc_{lab[0]}: ;")
+            self.ind -= 1
+            self.w("}")
+            if kind == "do":
+                self.ind -= 1
+                self.w("}")
+                if lab and lab[2]:
+                    self.w(f"_brk_{lab[0]}: ;")
+            return
+        if k0 == "id" and w0 == "else" and (len(toks) == 1):
+            self.ind -= 1
+            self.w("} else {")
+            self.ind += 1
+            return
+        if k0 == "id" and (w0 == "elseif" or (w0 == "else" and w1 == "if")):
+            p.next()
+            if w0 == "else":
+                p.next()
+            p.expect("(")
+            c, _ = self.emit(p.expr())
+            p.expect(")")
+            self.ind -= 1
+            self.w(f"}} else if ({c}) {{")
+            self.ind += 1
+            return
+        if k0 == "id" and w0 == "if" and w1 == "(":
+            p.next()
+            p.next()
+            cond = p.expr()
+            p.expect(")")
+            c, _ = self.emit(cond)
+            if p.peek() == ("id", "then") and p.i == len(toks) - 1:
+                self.w(f"if ({c}) {{")
+                self.ind += 1
+                self.blocks.append("if")
+                return
+            self.w(f"if ({c}) {{")
+            self.ind += 1
+            self.stmt(toks[p.i:])
+            self.ind -= 1
+            self.w("}")
+            return
+        if k0 == "id" and w0 == "do" and (len(toks) == 1 or (toks[1][0] == "id" and w1 != "while"
+                                                            and len(toks) > 2 and toks[2][1] == "=")):
+            self.w("{")
+            self.ind += 1
+            if len(toks) == 1:
+                self.w("for (;;) {")
+            else:
+                p.next()
+                var = p.next()[1]
+                p.expect("=")
+                lo = p.expr()
+                p.expect(",")
+                hi = p.expr()
+                step = None
+                if p.accept(","):
+                    step = p.expr()
+                vs = self.lookup(var)
+                vc = f"(*{vs.cname})" if vs.dummy else vs.cname
+                loc, _ = self.emit(lo)
+                hic, _ = self.emit(hi)
+                e_ = self.newtmp("_e")
+                self.w(f"const int {e_} = {hic};")
+                if step is None:
+                    self.w(f"for ({vc} = {loc}; {vc} <= {e_}; {vc}++) {{")
+                else:
+                    sc = self.const_int(step, None)
+                    cmp_ = "<=" if sc > 0 else ">="
+                    self.w(f"for ({vc} = {loc}; {vc} {cmp_} {e_}; {vc} += ({sc})) {{")
+            self.ind += 1
+            self.blocks.append("do")
+            self.tmp += 1
+            self.loopnames.append([f"{label}_{self.tmp}", False, False, label] if label else None)
+            return
+        if k0 == "id" and w0 == "select" and w1 == "case":
+            p.next()
+            p.next()
+            p.expect("(")
+            c, t = self.emit(p.expr())
+            p.expect(")")
+            sv = self.newtmp("_sel")
+            self.w("{")
+            self.ind += 1
+            self.w(f"const {t.ctype()} {sv} = {c};")
+            self.blocks.append("select0")
+            self.selvar.append(sv)
+            return
+        if k0 == "id" and w0 == "case":
+            first = self.blocks[-1] == "select0"
+            sv = self.selvar[-1]
+            if w1 == "default":
+                head = "{" if first else "} else {"
+            else:
+                p.next()
+                p.expect("(")
+                conds = []
+                while True:
+                    a = p.arg()
+                    if isinstance(a, Colon):
+                        cc = []
+                        if a.lo is not None:
+                            cc.append(f"{sv} >= ({self.emit(a.lo)[0]})")
+                        if a.hi is not None:
+                            cc.append(f"{sv} <= ({self.emit(a.hi)[0]})")
+                        conds.append("(" + " && ".join(cc) + ")")
+                    else:
+                        conds.append(f"({sv} == ({self.emit(a)[0]}))")
+                    if not p.accept(","):
+                        break
+                p.expect(")")
+                head = ("if (" if first else "} else if (") + " || ".join(conds) + ") {"
+            if first:
+                self.blocks[-1] = "case"
+            else:
+                self.ind -= 1
+            self.w(head)
+            self.ind += 1
+            return
+        if k0 == "id" and w0 in ("exit", "cycle") and len(toks) == 1:
+            self.w("break;" if w0 == "exit" else "continue;")
+            return
+        if k0 == "id" and w0 in ("exit", "cycle") and len(toks) == 2 and toks[1][0] == "id":
+            lab = next((x for x in reversed(self.loopnames) if x and x[3] == w1), None)
+            if lab is None:
+                self.err(f"no enclosing loop named {w1}")
+            if w0 == "cycle":
+                lab[1] = True
+                self.w(f"goto _cyc_{lab[0]};")
+            else:
+                lab[2] = True
+                self.w(f"goto _brk_{lab[0]};")
+            return
+        if k0 == "id" and w0 == "return" and len(toks) == 1:
+            self.w("goto _ret;")
+            self.uses_ret = True
+            return
+        if k0 == "id" and w0 == "call":
+            p.next()
+            name = p.next()[1]
+            args = []
+            if p.accept("("):
+                args = p.arglist()
+            pr = self.lookup_proc(name)
+            if pr is None:
+                self.err(f"unknown subroutine {name}")
+            self.w(f"{pr.cname}({self.call_args(pr, args)});")
+            return
+        if k0 == "id" and w0 in ("allocate", "deallocate") and w1 == "(":
+            p.next()
+            p.next()
+            items = p.arglist()
+            for it in items:
+                if not isinstance(it, Ref):
+                    self.err("bad allocate item")
+                if w0 == "allocate":
+                    shape = it.parts[-1][1]
+                    base = Ref(it.parts[:-1] + [(it.parts[-1][0], None)])
+                    self.want_whole = True
+                    c, t, _ = self.resolve_ref(base, None)
+                    self.want_whole = False
+                    dims = [self.emit(d)[0] for d in shape]
+                    et = t.scalar()
+                    esz = f"sizeof({et.ctype()})" + (f" * {et.clen}" if et.base == "char" else "")
+                    for dnum, d in enumerate(dims):
+                        self.w(f"({c}).n{dnum + 1} = {d};")
+                    prod = " * ".join(f"(size_t)({c}).n{dnum + 1}" for dnum in range(len(dims)))
+                    self.w(f"({c}).p = f_alloc({esz} * {prod});")
+                else:
+                    self.want_whole = True
+                    c, t, _ = self.resolve_ref(it, None)
+                    self.want_whole = False
+                    self.w(f"free(({c}).p); ({c}).p = 0;")
+            return
+        # --- assignment
+        depth, eq = 0, None
+        for i, (k, v) in enumerate(toks):
+            if k == "op" and v in ("(", "(/"):
+                depth += 1
+            elif k == "op" and v in (")", "/)"):
+                depth -= 1
+            elif k == "op" and v == "=" and depth == 0:
+                eq = i
+                break
+        if eq is None:
+            self.err("unrecognised statement")
+        lhs = Parser(toks[:eq], p.where).expr()
+        rp = Parser(toks[eq + 1:], p.where)
+        rhs = rp.expr()
+        if not rp.at_end():
+            self.err("trailing tokens after expression")
+        if not isinstance(lhs, Ref):
+            self.err("bad assignment target")
+        n = self.extent_of(lhs)
+        if n is not None:
+            iv = self.newtmp("_i")
+            lc, lt, lv = self.resolve_ref(lhs, iv)
+            rc, rt = self.emit(rhs, iv)
+            if lt.base == "char":
+                self.w(f"for (int {iv} = 0; {iv} < ({n}); {iv}++) "
+                       f"f_assign({lc}, {lt.clen}, {self.as_fstr(rc, rt)});")
+            else:
+                self.w(f"for (int {iv} = 0; {iv} < ({n}); {iv}++) {lc} = {rc};")
+            return
+        lc, lt, lv = self.resolve_ref(lhs, None)
+        if not lv:
+            self.err("assignment to a constant")
+        if self.extent_of(rhs) is not None:
+            self.err("array expression assigned to a scalar")
+        rc, rt = self.emit(rhs, None)
+        if lt.base == "char":
+            self.w(f"f_assign({lc}, {lt.clen}, {self.as_fstr(rc, rt)});")
+        else:
+            self.w(f"{lc} = {rc};")
+
+    # ---------------------------------------------------------------- driver
+    def cdecl(self, s, name=None, static_tls=False):
+        """C declaration of a variable / component."""
+        name = name or s.cname
+        t = s.typ
+        pre = "REF_TLS " if static_tls else ""
+        if s.alloc:
+            return f"{pre}fa_t {name};"
+        dim = ""
+        if t.rank > 0:
+            n = 1
+            for d in s.dims:
+                n *= self.const_int(d, None)
+            dim = f"[{n}]"
+        if t.base == "char":
+            dim += f"[{t.clen}]"
+        return f"{pre}{t.ctype()} {name}{dim};"
+
+    def proto(self, pr):
+        args = []
+        for a in pr.args:
+            s = pr.syms[a]
+            if s.alloc:
+                args.append(f"fa_t *{s.cname}")
+            elif s.typ.base == "char":
+                self.err("character dummy arguments are not supported")
+            else:
+                args.append(f"{s.typ.ctype()} *{s.cname}")
+        r = pr.rtype.ctype() if pr.kind == "function" else "void"
+        return f"{r} {pr.cname}({', '.join(args) if args else 'void'})"
+
+    def prepare_proc(self, pr):
+        """Split declarations from executable statements; fill the symbol table."""
+        self.scope_mod, self.scope_proc = pr.module, pr
+        body = []
+        decl_heads = ("real", "integer", "logical", "character", "double")
+        for ln, toks in pr.body:
+            self.cur_line = ln
+            w0 = toks[0][1]
+            if toks[0][0] == "id" and not body:
+                if w0 in ("implicit", "use", "save"):
+                    if w0 == "use":
+                        self.err("procedure-level USE is not supported")
+                    continue
+                is_decl = (w0 in decl_heads) or (w0 == "type" and toks[1][1] == "(")
+                if is_decl:
+                    self.decl(toks, proc=pr)
+                    continue
+            body.append((ln, toks))
+        pr.body = body
+        for a in pr.args:
+            if a not in pr.syms:
+                self.cur_line = pr.line
+                self.err(f"dummy argument {a} is not declared")
+            pr.syms[a].dummy = True
+        if pr.kind == "function":
+            if pr.result not in pr.syms:
+                self.cur_line = pr.line
+                self.err("function result is not declared in the body")
+            pr.syms[pr.result].is_result = True
+            pr.rtype = pr.syms[pr.result].typ
+        for s in pr.syms.values():
+            if s.param:
+                s.local_const = True
+
+    @staticmethod
+    def _first_dcolon(toks):
+        for i, (k, v) in enumerate(toks):
+            if v == "::":
+                return i
+        return min(len(toks), 3)
+
+    def emit_proc(self, pr):
+        self.scope_mod, self.scope_proc = pr.module, pr
+        self.blocks, self.selvar, self.ind, self.uses_ret = [], [], 0, False
+        self.loopnames = []
+        self.cur_line = pr.line
+        self.w(f"/* {pr.line.file}:{pr.line.no} {pr.kind} {pr.name} */")
+        self.w(self.proto(pr) + " {")
+        self.ind = 1
+        allocs = []
+        for s in pr.syms.values():
+            if s.dummy:
+                continue
+            if s.param:
+                c, t = self.emit(s.init)
+                self.w(f"const {s.typ.ctype()} {s.cname} = {c};")
+                continue
+            if s.init is not None:
+                self.err(f"initialised (SAVE) local {s.name} is not supported")
+            d = self.cdecl(s)
+            if s.alloc:
+                d = d[:-1] + " = {0, 0, 0, 0};"
+                allocs.append(s)
+            self.w(d)
+        for ln, toks in pr.body:
+            self.cur_line = ln
+            mark = len(self.out)
+            self.stmt(toks)
+            self.out.insert(mark, "  " * self.ind + f"/* {ln.file}:{ln.no} */")
+        if self.blocks:
+            self.cur_line = pr.line
+            self.err("unterminated block")
+        self.ind = 1
+        if self.uses_ret:
+            self.w("_ret: ;")
+        for s in allocs:       # gfortran frees allocatable locals on exit
+            self.w(f"if ({s.cname}.p) free({s.cname}.p);")
+        if pr.kind == "function":
+            self.w(f"return {pr.syms[pr.result].cname};")
+        self.ind = 0
+        self.w("}")
+        self.w("")
+
+    def translate(self):
+        self.ind = 0
+        self.out.append(PRELUDE)
+        # structs
+        for m in self.order:
+            self.scope_mod, self.scope_proc = m, None
+            for d in m.types.values():
+                self.out.append(f"struct {d.cname} {{")
+                for f in d.fields:
+                    self.out.append("  " + self.cdecl(f))
+                self.out.append("};")
+        # module variables / named constants
+        for m in self.order:
+            self.scope_mod, self.scope_proc = m, None
+            for s in m.syms.values():
+                if s.param:
+                    if s.typ.rank > 0:
+                        self.err(f"array named constant {s.name} is not supported")
+                    if s.typ.base == "int" and s.typ.kind == 4:
+                        c = str(self.const_int(s.init, None))
+                    else:
+                        c, t = self.emit(s.init)
+                    self.out.append(f"#define {s.cname} (({s.typ.ctype()})({c}))")
+                    self.out.append(f"{s.typ.ctype()} ref_const__{s.cname}(void) {{ return {s.cname}; }}")
+                else:
+                    if s.init is not None:
+                        c, t = self.emit(s.init)
+                        self.out.append(self.cdecl(s, static_tls=True)[:-1] + f" = {c};")
+                    else:
+                        self.out.append(self.cdecl(s, static_tls=True))
+                    at = "fa_t" if s.alloc else s.typ.ctype()
+                    self.out.append(f"void *ref_addr__{s.cname}(void) {{ return (void *)&{s.cname}; }}")
+        # procedures
+        for m in self.order:
+            for pr in m.procs.values():
+                self.prepare_proc(pr)
+        for m in self.order:
+            for pr in m.procs.values():
+                self.scope_mod, self.scope_proc = m, pr
+                self.out.append(self.proto(pr) + ";")
+        for m in self.order:
+            for pr in m.procs.values():
+                self.emit_proc(pr)
+        return "\n".join(self.out) + "\n"
+
+    def meta(self):
+        def fld(s):
+            dims = None
+            if s.typ.rank > 0 and not s.alloc:
+                self.scope_proc = None
+                dims = [self.const_int(d, None) for d in s.dims]
+            return {"name": s.name, "cname": s.cname, "type": s.typ.code(), "rank": s.typ.rank,
+                    "alloc": s.alloc, "dims": dims, "intent": s.intent}
+        out = {"types": {}, "procs": {}, "vars": {}, "consts": {}}
+        for m in self.order:
+            self.scope_mod = m
+            for d in m.types.values():
+                out["types"][d.cname] = [fld(f) for f in d.fields]
+            for s in m.syms.values():
+                if not s.param:
+                    out["vars"][s.cname] = fld(s)
+                else:
+                    out["consts"][s.cname] = s.typ.code()
+            for pr in m.procs.values():
+                out["procs"][pr.cname] = {
+                    "kind": pr.kind, "args": [fld(pr.syms[a]) for a in pr.args],
+                    "result": pr.rtype.code() if pr.rtype else None,
+                    "where": f"{pr.line.file}:{pr.line.no}"}
+        return out
+
+
+def main(argv):
+    out_c = out_meta = None
+    files = []
+    it = iter(argv)
+    for a in it:
+        if a == "-o":
+            out_c = next(it)
+        elif a == "-m":
+            out_meta = next(it)
+        else:
+            files.append(a)
+    tr = Translator()
+    for f in files:
+        tr.load(f)
+    c = tr.translate()
+    with open(out_c, "w") as fh:
+        fh.write(c)
+    if out_meta:
+        with open(out_meta, "w") as fh:
+            json.dump(tr.meta(), fh, indent=1)
+    print(f"f90c: {len(files)} files -> {out_c} ({c.count(chr(10))} lines)")
+
+
+if __name__ == "__main__":
+    main(sys.argv[1:])

@@ -1,0 +1,307 @@
+"""ctypes binding of oracle/_ref/libbgc_ref.so — the UNMODIFIED reference Fortran
+(/root/reference/*.F90) machine-translated to C by oracle/f90c.py and compiled by gcc.
+
+TEST INFRASTRUCTURE ONLY.  This is what pins the hand-written oracle: the same inputs go
+through the translated reference and through oracle/libbgc_oracle.so and the results are
+compared bit for bit (tests/test_reference_translated.py); tests/golden/*.npz are generated
+from the translated reference (tests/golden/make_golden.py).  The library and the generated C
+live in oracle/_ref/ (git-ignored: nothing derived from the reference sources is committed);
+`build()` regenerates them wherever /root/reference exists, and the prebuilt files travel to
+the GPU box with the snapshot.
+
+The reference keeps state in module variables; the translation makes them thread-local, so a
+thread that wants to compute must run `RefParms()` (the *_parms_init / *_init calls) itself.
+"""
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REFDIR = os.path.join(HERE, "_ref")
+LIB_PATH = os.path.join(REFDIR, "libbgc_ref.so")
+META_PATH = os.path.join(REFDIR, "meta.json")
+REFERENCE_SRC = os.environ.get("BGC_REFERENCE_SRC", "/root/reference")
+
+_lib = None
+_meta = None
+_structs = {}
+
+
+def available():
+    return os.path.exists(LIB_PATH) and os.path.exists(META_PATH)
+
+
+def can_build():
+    return os.path.exists(os.path.join(REFERENCE_SRC, "BGC_mod.F90"))
+
+
+def build():
+    """Translate + compile (needs the reference sources; a no-op when up to date)."""
+    subprocess.check_call(["make", "-s", "-C", HERE, "ref", f"REFERENCE_SRC={REFERENCE_SRC}"])
+
+
+class FA(C.Structure):
+    """array descriptor of the translation: base pointer + up to three extents"""
+    _fields_ = [("p", C.c_void_p), ("n1", C.c_int), ("n2", C.c_int), ("n3", C.c_int)]
+
+
+_SCALAR = {"i4": C.c_int, "i8": C.c_longlong, "r4": C.c_float, "r8": C.c_double, "log": C.c_int}
+
+
+def _ctype(code):
+    if code in _SCALAR:
+        return _SCALAR[code]
+    if code.startswith("char"):
+        return C.c_char * int(code[4:])
+    if code.startswith("type:"):
+        return struct(code[5:])
+    raise KeyError(code)
+
+
+def _field_ctype(f):
+    if f["alloc"]:
+        return FA
+    t = _ctype(f["type"])
+    if f["rank"] > 0:
+        t = t * int(np.prod(f["dims"]))
+    return t
+
+
+def meta():
+    global _meta
+    if _meta is None:
+        _meta = json.load(open(META_PATH))
+    return _meta
+
+
+def struct(cname):
+    """ctypes mirror of a translated derived type (fields in declaration order)."""
+    if cname not in _structs:
+        fields = [(f["cname"], _field_ctype(f)) for f in meta()["types"][cname]]
+        _structs[cname] = type(cname, (C.Structure,), {"_fields_": fields})
+    return _structs[cname]
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not available():
+            if not can_build():
+                raise RuntimeError("oracle/_ref/libbgc_ref.so is missing and the reference sources "
+                                   "are not available to rebuild it")
+            build()
+        _lib = C.CDLL(LIB_PATH)
+    return _lib
+
+
+def const(cname):
+    """value of a module-level named constant (e.g. 'bgc_parms__epsc')"""
+    f = getattr(lib(), "ref_const__" + cname)
+    f.restype = _ctype(meta()["consts"][cname])
+    return f()
+
+
+def var(cname):
+    """ctypes object aliasing a module variable OF THE CALLING THREAD"""
+    f = getattr(lib(), "ref_addr__" + cname)
+    f.restype = C.c_void_p
+    return _field_ctype(meta()["vars"][cname]).from_address(f())
+
+
+def call(cname, *args):
+    """Call a translated procedure.  Scalars may be given as Python numbers (wrapped, passed by
+    reference; the ctypes objects are returned so that intent(out) values can be read), derived
+    types as ctypes Structures / arrays of them."""
+    pm = meta()["procs"][cname]
+    fn = getattr(lib(), cname)
+    fn.restype = _ctype(pm["result"]) if pm["result"] else None
+    if len(args) != len(pm["args"]):
+        raise TypeError(f"{cname}: {len(args)} arguments for {len(pm['args'])} dummies")
+    boxed = []
+    for a, am in zip(args, pm["args"]):
+        if isinstance(a, (C.Structure, C.Array, C._SimpleCData)):
+            boxed.append(a)
+        else:
+            boxed.append(_ctype(am["type"])(a))
+    r = fn(*[C.byref(b) for b in boxed])
+    return r, boxed
+
+
+def describe(arr):
+    """descriptor of a Fortran-ordered numpy array (no copy: the routine works in place)"""
+    assert arr.flags["F_CONTIGUOUS"] or arr.ndim == 1
+    d = FA()
+    d.p = arr.ctypes.data
+    sh = list(arr.shape) + [1, 1, 1]
+    d.n1, d.n2, d.n3 = sh[0], sh[1], sh[2]
+    return d
+
+
+def fill(cname, arrays, scalars=None):
+    """Build a translated derived type whose allocatable components alias the numpy arrays in
+    `arrays` (component names compared case-insensitively) and whose scalar components come from
+    `scalars`.  Returns (struct, keepalive)."""
+    s = struct(cname)()
+    low = {k.lower(): v for k, v in arrays.items()}
+    sc = {k.lower(): v for k, v in (scalars or {}).items()}
+    keep = []
+    for f in meta()["types"][cname]:
+        n = f["name"]
+        if f["alloc"]:
+            if n in low and low[n] is not None:
+                a = low[n]
+                if f["type"].startswith("r8"):
+                    assert a.dtype == np.float64, n
+                elif f["type"] == "i4":
+                    assert a.dtype == np.int32, n
+                assert a.ndim == f["rank"], (n, a.shape, f["rank"])
+                setattr(s, f["cname"], describe(a))
+                keep.append(a)
+        elif n in sc:
+            setattr(s, f["cname"], sc[n])
+    return s, keep
+
+
+def _arrays_of(cols):
+    out = {}
+    for k, v in vars(cols).items():
+        if isinstance(v, np.ndarray):
+            out[k] = v
+        elif isinstance(v, dict):
+            for kk, vv in v.items():
+                if isinstance(vv, np.ndarray):
+                    out[kk] = vv
+    return out
+
+
+def _scalars_of(cols):
+    return {k: int(v) for k, v in vars(cols).items() if k.startswith("lcalc_")}
+
+
+class RefParms:
+    """BGC_parms_init + BGC_init + DMS_parms_init + DMS_init + MACROS_parms_init + MACROS_init
+    of the translated reference, with the host-chosen tracer slots of `parms` (an
+    oracle.Parms) and the host-set T0_Kelvin_BGC (quirk Q7)."""
+
+    def __init__(self, parms=None, t0_kelvin=273.15):
+        m = meta()
+        self.ind = struct("bgc_parms__bgc_indices_type")()
+        self.autotrophs = (struct("bgc_parms__autotroph_type") * 4)()
+        self._names = {}
+        for tname, obj_name, n in (("bgc_parms__bgc_indices_type", "ind", 30),
+                                   ("dms_parms__dms_indices_type", "dms_ind", 14),
+                                   ("macros_parms__macros_indices_type", "macros_ind", 8)):
+            obj = struct(tname)() if obj_name != "ind" else self.ind
+            setattr(self, obj_name, obj)
+            for f in m["types"][tname]:
+                if f["alloc"] and f["type"].startswith("char"):
+                    buf = np.full((n, int(f["type"][4:])), ord(" "), dtype=np.uint8)
+                    d = FA()
+                    d.p, d.n1, d.n2, d.n3 = buf.ctypes.data, n, 1, 1
+                    setattr(obj, f["cname"], d)
+                    self._names[(obj_name, f["name"])] = buf
+        # the host (MPAS) assigns the tracer slots before calling *_init
+        if parms is not None:
+            self._copy_slots(parms.ind, self.ind, 30)
+            self._copy_slots(parms.dms_ind, self.dms_ind, None)
+            self._copy_slots(parms.macros_ind, self.macros_ind, None)
+        else:
+            for obj in (self.ind, self.dms_ind, self.macros_ind):
+                i = 0
+                for fname, ft in obj._fields_:
+                    if ft is C.c_int and fname.endswith("_ind") and i < {id(self.ind): 30}.get(id(obj), 99):
+                        i += 1
+                        setattr(obj, fname, i)
+        var("bgc_parms__t0_kelvin_bgc").value = t0_kelvin
+        call("bgc_parms__bgc_parms_init", self.ind, self.autotrophs)
+        call("bgc_mod__bgc_init", self.ind, self.autotrophs)
+        call("dms_parms__dms_parms_init")
+        call("dms_mod__dms_init", self.dms_ind)
+        call("macros_parms__macros_parms_init")
+        call("macros_mod__macros_init", self.macros_ind)
+
+    @staticmethod
+    def _copy_slots(src, dst, limit):
+        names = [n for n, _ in src._fields_]
+        if limit is not None:
+            names = names[:limit]
+        for n in names:
+            setattr(dst, n.lower(), getattr(src, n))
+
+    def name(self, which, field, i):
+        return bytes(self._names[(which, field)][i]).decode().rstrip()
+
+
+def BGC_SourceSink(rp, cols, alt_co2_use_eco=True):
+    arrs = _arrays_of(cols)
+    cin, k1 = fill("bgc_parms__bgc_input_type", arrs)
+    cfo, k2 = fill("bgc_parms__bgc_forcing_type", arrs, _scalars_of(cols))
+    cout, k3 = fill("bgc_parms__bgc_output_type", arrs)
+    cdg, k4 = fill("bgc_parms__bgc_diagnostics_type", arrs)
+    call("bgc_mod__bgc_sourcesink", rp.autotrophs, rp.ind, cin, cfo, cout, cdg,
+         cols.nLevelsMax, cols.nColumnsMax, cols.nColumns, int(alt_co2_use_eco))
+
+
+def BGC_SurfaceFluxes(rp, cols):
+    arrs = _arrays_of(cols)
+    cin, k1 = fill("bgc_parms__bgc_input_type", arrs)
+    cfo, k2 = fill("bgc_parms__bgc_forcing_type", arrs, _scalars_of(cols))
+    cfd, k3 = fill("bgc_parms__bgc_flux_diagnostics_type", arrs)
+    call("bgc_mod__bgc_surfacefluxes", rp.ind, cin, cfo, cfd, cols.nColumnsMax, cols.nColumns)
+
+
+def DMS_SourceSink(rp, cols):
+    arrs = _arrays_of(cols)
+    cin, k1 = fill("dms_parms__dms_input_type", arrs)
+    cfo, k2 = fill("dms_parms__dms_forcing_type", arrs, _scalars_of(cols))
+    cout, k3 = fill("dms_parms__dms_output_type", arrs)
+    cdg, k4 = fill("dms_parms__dms_diagnostics_type", arrs)
+    call("dms_mod__dms_sourcesink", rp.dms_ind, cin, cfo, cout, cdg,
+         cols.nLevelsMax, cols.nColumnsMax, cols.nColumns)
+
+
+def DMS_SurfaceFluxes(rp, cols):
+    arrs = _arrays_of(cols)
+    cin, k1 = fill("dms_parms__dms_input_type", arrs)
+    cfo, k2 = fill("dms_parms__dms_forcing_type", arrs, _scalars_of(cols))
+    cfd, k3 = fill("dms_parms__dms_flux_diagnostics_type", arrs)
+    call("dms_mod__dms_surfacefluxes", rp.dms_ind, cin, cfo, cfd, cols.nColumnsMax, cols.nColumns)
+
+
+def MACROS_SourceSink(rp, cols):
+    arrs = _arrays_of(cols)
+    cin, k1 = fill("macros_parms__macros_input_type", arrs)
+    cout, k2 = fill("macros_parms__macros_output_type", arrs)
+    cdg, k3 = fill("macros_parms__macros_diagnostics_type", arrs)
+    call("macros_mod__macros_sourcesink", rp.macros_ind, cin, cout, cdg,
+         cols.nLevelsMax, cols.nColumnsMax, cols.nColumns)
+
+
+def co2calc_1point(depth, temp, salt, dic, ta, pt, sit, phlo, phhi, xco2, atmpres,
+                   locmip_k1_k2_bug_fix=True, lcomp_co3_coeffs=True):
+    _, b = call("co2calc__co2calc_1point", depth, int(locmip_k1_k2_bug_fix), int(lcomp_co3_coeffs),
+                temp, salt, dic, ta, pt, sit, phlo, phhi, 0.0, xco2, atmpres, 0.0, 0.0, 0.0, 0.0)
+    return dict(phlo=b[9].value, phhi=b[10].value, ph=b[11].value, co2star=b[14].value,
+                dco2star=b[15].value, pco2surf=b[16].value, dpco2=b[17].value)
+
+
+def comp_CO3terms(k, depth, temp, salt, dic, ta, pt, sit, phlo, phhi, lcomp_co3_coeffs=True):
+    _, b = call("co2calc__comp_co3terms", int(k), depth, int(lcomp_co3_coeffs), temp, salt, dic, ta,
+                pt, sit, phlo, phhi, 0.0, 0.0, 0.0, 0.0)
+    return dict(phlo=b[9].value, phhi=b[10].value, pH=b[11].value, H2CO3=b[12].value,
+                HCO3=b[13].value, CO3=b[14].value)
+
+
+def comp_co3_sat_vals(k, depth, temp, salt):
+    _, b = call("co2calc__comp_co3_sat_vals", int(k), depth, temp, salt, 0.0, 0.0)
+    return b[4].value, b[5].value
+
+
+if __name__ == "__main__":
+    if "--build" in sys.argv:
+        build()
+    print("available:", available(), LIB_PATH)
