@@ -232,6 +232,29 @@ class RefParms:
         for n in names:
             setattr(dst, n.lower(), getattr(src, n))
 
+    def sync_from(self, parms):
+        """Copy the run-time tunables and the functional-group table of an oracle.Parms /
+        host.Parms into the module variables of the translated reference (what a namelist read
+        does upstream).  Compile-time constants (epsC ...) are not settable and are skipped."""
+        m = meta()
+        for src, mod in ((parms.bgc, "bgc_parms"), (parms.dms, "dms_parms"), (parms.macros, "macros_parms")):
+            for n, _ in src._fields_:
+                cn = f"{mod}__{n.lower()}"
+                if n.startswith("lrest_"):
+                    cn = f"bgc_mod__{n.lower()}"
+                if cn not in m["vars"]:
+                    continue
+                v, dst = getattr(src, n), var(cn)
+                if hasattr(v, "__len__"):
+                    for i, x in enumerate(v):
+                        dst[i] = x
+                else:
+                    dst.value = v
+        for i in range(4):
+            for n, _ in parms.autotrophs[i]._fields_:
+                setattr(self.autotrophs[i], n.lower(), getattr(parms.autotrophs[i], n))
+        return self
+
     def name(self, which, field, i):
         return bytes(self._names[(which, field)][i]).decode().rstrip()
 
@@ -299,6 +322,45 @@ def comp_CO3terms(k, depth, temp, salt, dic, ta, pt, sit, phlo, phhi, lcomp_co3_
 def comp_co3_sat_vals(k, depth, temp, salt):
     _, b = call("co2calc__comp_co3_sat_vals", int(k), depth, temp, salt, 0.0, 0.0)
     return b[4].value, b[5].value
+
+
+# ------------------------------------------------------------------ threaded driver (bench.py)
+
+class SlabRunner:
+    """Runs the translated reference on column slabs from a pool of threads.  The reference is
+    serial and not re-entrant (module SAVE state); the translation makes that state thread-local,
+    so every worker thread initialises its own copy (RefParms) once and then works through slabs.
+    ctypes releases the GIL for the duration of each call."""
+
+    def __init__(self, parms, nthreads):
+        import threading
+        from concurrent.futures import ThreadPoolExecutor
+        self.parms, self.nthreads = parms, int(nthreads)
+        self._tls = threading.local()
+        self._pool = ThreadPoolExecutor(max_workers=self.nthreads)
+
+    def _rp(self):
+        if not hasattr(self._tls, "rp"):
+            self._tls.rp = RefParms(self.parms)
+        return self._tls.rp
+
+    def _one(self, slab):
+        rp = self._rp()
+        bgc, dms, mac = slab
+        BGC_SourceSink(rp, bgc, True)
+        BGC_SurfaceFluxes(rp, bgc)
+        if dms is not None:
+            DMS_SourceSink(rp, dms)
+            DMS_SurfaceFluxes(rp, dms)
+        if mac is not None:
+            MACROS_SourceSink(rp, mac)
+
+    def step(self, slabs):
+        """one BGC + DMS + MACROS step over every (bgc, dms, macros) slab"""
+        list(self._pool.map(self._one, slabs))
+
+    def close(self):
+        self._pool.shutdown()
 
 
 if __name__ == "__main__":

@@ -1,11 +1,14 @@
-"""Regenerates tests/golden/*.npz from the CPU oracle.
+"""Regenerates tests/golden/*.npz by RUNNING THE REFERENCE.
 
-The reference ships no tests, fixtures or golden vectors and cannot be built in
-this image (no Fortran compiler), so these fixtures do NOT come from the
-reference itself: they freeze the oracle's answers at the commit that produced
-them.  They serve two purposes: (1) any later edit of the oracle that changes
-its results is caught on CPU (tests/test_golden.py), (2) the GPU path is checked
-against fixed numbers on the GPU box as well as against the live oracle.
+The reference ships no tests, fixtures or golden vectors of its own, and the image has no
+Fortran compiler; these fixtures are the outputs of the unmodified reference sources
+(/root/reference/*.F90) machine-translated to C by oracle/f90c.py and compiled with gcc
+(oracle/_ref/libbgc_ref.so, see oracle/ref_translated.py), on the seeded synthetic inputs of
+SURVEY.md 8(d).  They serve two purposes: (1) the hand-written oracle must reproduce them bit
+for bit on CPU, here and on the GPU box, where /root/reference does not exist
+(tests/test_golden.py), (2) the GPU path is checked against fixed numbers as well as against
+the live oracle.  `--from-oracle` regenerates them from the oracle instead (for a machine
+without the reference sources); the two give identical files.
 
     python tests/golden/make_golden.py
 """
@@ -19,7 +22,57 @@ sys.path.insert(0, os.path.dirname(HERE))
 import parity  # noqa: E402
 
 pkg = parity.pkg
-o = parity.oracle()
+o = oracle_mod = parity.oracle()
+sys.path.insert(0, os.path.join(parity.REPO, "oracle"))
+import ref_translated as rt   # noqa: E402
+
+
+class _Ref:
+    """the translated reference behind the oracle module's call signatures"""
+
+    def __init__(self):
+        self._rp = {}
+
+    def Parms(self):
+        po = oracle_mod.Parms()
+        self._rp[id(po)] = rt.RefParms(po)
+        self._keep = po
+        return po
+
+    def BGC_SourceSink(self, po, cols, alt=True):
+        rt.BGC_SourceSink(self._rp[id(po)], cols, alt)
+
+    def BGC_SurfaceFluxes(self, po, cols):
+        rt.BGC_SurfaceFluxes(self._rp[id(po)], cols)
+
+    def DMS_SourceSink(self, po, cols):
+        rt.DMS_SourceSink(self._rp[id(po)], cols)
+
+    def DMS_SurfaceFluxes(self, po, cols):
+        rt.DMS_SurfaceFluxes(self._rp[id(po)], cols)
+
+    def MACROS_SourceSink(self, po, cols):
+        rt.MACROS_SourceSink(self._rp[id(po)], cols)
+
+    def co2calc_points(self, pts):
+        n = len(pts["temp"])
+        out = {k: np.zeros(n) for k in ("ph", "co2star", "dco2star", "pco2surf", "dpco2")}
+        rt.RefParms(oracle_mod.Parms())
+        for i in range(n):
+            r = rt.co2calc_1point(*[float(pts[k][i]) for k in ("depth", "temp", "salt", "dic", "ta", "pt",
+                                                               "sit", "phlo", "phhi", "xco2", "atmpres")])
+            for k in out:
+                out[k][i] = r[k]
+        return out
+
+
+if "--from-oracle" not in sys.argv:
+    if not rt.available():
+        rt.build()
+    o = _Ref()
+    SOURCE = "translated reference (oracle/_ref/libbgc_ref.so)"
+else:
+    SOURCE = "oracle (oracle/libbgc_oracle.so)"
 
 
 def single_column():
@@ -69,4 +122,4 @@ def ragged_block():
 
 if __name__ == "__main__":
     single_column(); co2_points(); ragged_block()
-    print("golden fixtures written to", HERE)
+    print("golden fixtures written to", HERE, "from the", SOURCE)
