@@ -209,6 +209,8 @@ def cpu_baseline_throughput(pkg, columns, levels, steps, warmup):
     """(value, dt, threads, cells, kind, note): the translated reference when oracle/_ref holds it,
     otherwise the hand-written oracle port."""
     try:
+        if os.environ.get("BGC_BENCH_CPU_KIND", "") == "port":
+            raise RuntimeError("BGC_BENCH_CPU_KIND=port")
         v, dt, nthreads, cells = cpu_reference_throughput(pkg, columns, levels, steps, warmup)
         return v, dt, nthreads, cells, "reference", (
             "reference = the unmodified Fortran sources machine-translated to C (oracle/f90c.py) and compiled "

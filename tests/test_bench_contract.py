@@ -28,9 +28,22 @@ def test_reference_arm_prints_one_json_line(built):
         assert k in d, k
     assert d["impl"] == "reference" and d["unit"] == "cell-updates/s" and d["dtype"] == "f64"
     assert d["vs_baseline"] is None and d["higher_is_better"] is True
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    # "reference" when oracle/_ref holds the translated reference (built wherever the reference
+    # sources exist and shipped with the snapshot), otherwise the oracle port
+    ref_built = os.path.exists(os.path.join(REPO, "oracle", "_ref", "libbgc_ref.so"))
+    assert d["cpu_baseline"]["kind"] == ("reference" if ref_built else "port")
+    assert d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert d["value"] > 0 and "workload" in d["config"]
+
+
+def test_reference_arm_can_time_the_port(built):
+    """BGC_BENCH_CPU_KIND=port (or a missing oracle/_ref) times the hand-written oracle and says so"""
+    r = _run("--impl", "reference", "--steps", "1", "--warmup", "1", "--cpu-columns", "256", "--gpus", "1",
+             env={"BGC_BENCH_CPU_KIND": "port"})
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d["cpu_baseline"]["kind"] == "port" and d["value"] > 0
 
 
 def test_reference_arm_other_ranks_exit_quietly(built):
