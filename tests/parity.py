@@ -154,6 +154,25 @@ def run_gpu_bgc(ctx, cols, *, device_mode, alt_co2_use_eco=True, diagnostics=Tru
     return out
 
 
+def reference_check(po, cols, oracle_result):
+    """When oracle/_ref holds the translated reference (oracle/ref_translated.py), the oracle's
+    answer for this block must equal the reference's bit for bit.  Returns a short verdict."""
+    sys.path.insert(0, os.path.join(REPO, "oracle"))
+    try:
+        import ref_translated as rt   # test infrastructure only
+    except Exception as exc:          # noqa: BLE001
+        return "unavailable (%s)" % exc
+    if not rt.available():
+        return "unavailable (oracle/_ref not shipped)"
+    r = cols.copy()
+    rt.BGC_SourceSink(rt.RefParms(po), r, True)
+    assert np.array_equal(r.BGC_tendencies, oracle_result.BGC_tendencies), "oracle != reference (tendencies)"
+    assert np.array_equal(r.PH_PREV_3D, oracle_result.PH_PREV_3D), "oracle != reference (pH)"
+    for n, a in r.diag.items():
+        assert np.array_equal(a, oracle_result.diag[n]), "oracle != reference (%s)" % n
+    return "bit-identical"
+
+
 def smoke(pkg_=None):
     """One small invocation of the hot path on cuda:0, checked against the oracle."""
     o = oracle()
@@ -164,6 +183,7 @@ def smoke(pkg_=None):
     cols, dms, mac = make_bgc(nL, nC, parms, ragged=True, with_dms=True, with_macros=True)
     ref = cols.copy()
     o.BGC_SourceSink(po, ref, True, nthreads=o.max_threads())
+    pinned = reference_check(po, cols, ref)
     ctx = host.Context(nL, nC, device=0, parms=parms)
     got = run_gpu_bgc(ctx, cols, device_mode=True)
     errs = compare_bgc_source_sink(ref, got)
@@ -200,5 +220,6 @@ def smoke(pkg_=None):
 
     st = ctx.status()
     assert st["no_bracket"] == 0 and st["no_convergence"] == 0, st
-    print("smoke: worst normalised error %.3e; status %s" % (worst, st))
+    print("smoke: worst normalised error %.3e; status %s; oracle vs translated reference on the same block: %s"
+          % (worst, st, pinned))
     ctx.close()

@@ -1,0 +1,135 @@
+"""The CUDA path against THE REFERENCE ITSELF: oracle/_ref/libbgc_ref.so is the unmodified
+reference Fortran machine-translated to C (oracle/f90c.py) and compiled by gcc; it is built
+where the reference sources exist and travels to the GPU box with the snapshot (the box has no
+/root/reference and nothing here reads it).  Same seeded inputs, same tolerances as the
+oracle-based tests (tests/parity.py); the oracle and this library agree bit for bit
+(tests/test_reference_translated.py), so these tests close the chain reference -> CUDA without
+the hand-written restatement in between.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import parity
+
+pkg = parity.pkg
+abi = pkg.abi
+host = pkg.host
+sys.path.insert(0, os.path.join(parity.REPO, "oracle"))
+import ref_translated as rt   # noqa: E402  (test infrastructure only)
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not rt.available(), reason="oracle/_ref/libbgc_ref.so not shipped")]
+
+
+def _active(c):
+    k = np.arange(1, c.nLevelsMax + 1)[:, None]
+    kmax = c.number_of_active_levels.copy()
+    kmax[c.nColumns:] = 0
+    return k <= kmax[None, :]
+
+
+def check_bgc(run, parms, rp, nL, nC, nCols, ragged, seed=None, prepare=None):
+    """cold pass, warm pass and surface fluxes of `run` (the implementation under test) against
+    the translated reference"""
+    cols, _, _ = parity.make_bgc(nL, nC, parms, nColumns=nCols, ragged=ragged, seed=seed)
+    if prepare:
+        prepare(cols)
+    parity.poison_outputs(cols)
+    ref = cols.copy()
+    rt.BGC_SourceSink(rp, ref, True)
+    got = run(cols.copy(), False)
+    parity.compare_bgc_source_sink(ref, got)
+    ref2 = ref.copy()
+    rt.BGC_SourceSink(rp, ref2, True)
+    rt.BGC_SurfaceFluxes(rp, ref2)
+    got2 = run(got.copy(), True)
+    parity.compare_bgc_source_sink(ref2, got2)
+    cm = np.arange(nC) < nCols
+    solver = ("gasFlux", "netFlux", "surface_pH", "surface_pH_alt_co2")
+    for nm, a in ref2.forcing.items():
+        if a.shape[0] == nC:
+            e = parity.nerr(got2.forcing[nm][cm], a[cm])
+            assert e <= (parity.TOL_SOLVER if nm in solver else parity.TOL_TEND), (nm, e)
+    for nm, a in ref2.flux_diag.items():
+        e = parity.nerr(got2.flux_diag[nm][cm], a[cm])
+        assert e <= (parity.TOL_SOLVER if nm in parity.SOLVER_FLUX else parity.TOL_TEND), (nm, e)
+    return ref2, got2
+
+
+def check_dms_macros(run, parms, rp, nL, nC, nCols):
+    _, dms, mac = parity.make_bgc(nL, nC, parms, nColumns=nCols, ragged=True, with_dms=True, with_macros=True)
+    dref, mref = dms.copy(), mac.copy()
+    rt.DMS_SourceSink(rp, dref); rt.DMS_SurfaceFluxes(rp, dref); rt.MACROS_SourceSink(rp, mref)
+    dgot, mgot = run(dms.copy(), mac.copy())
+    for n in range(abi.DMS_TRACER_CNT):
+        assert parity.nerr(dgot.DMS_tendencies[:, :, n], dref.DMS_tendencies[:, :, n]) <= parity.TOL_TEND, n
+    for n in range(abi.MACROS_TRACER_CNT):
+        assert parity.nerr(mgot.MACROS_tendencies[:, :, n], mref.MACROS_tendencies[:, :, n]) <= parity.TOL_TEND, n
+    parity.compare_fields(dref.diag, dgot.diag, parity.TOL_TEND, "DMS diagnostics", mask=_active(dms))
+    parity.compare_fields(mref.diag, mgot.diag, parity.TOL_TEND, "MACROS diagnostics", mask=_active(mac))
+    cm = np.arange(nC) < nCols
+    for nm in dref.flux_diag:
+        assert parity.nerr(dgot.flux_diag[nm][cm], dref.flux_diag[nm][cm]) <= parity.TOL_TEND, nm
+    assert parity.nerr(dgot.forcing["netFlux"][cm], dref.forcing["netFlux"][cm]) <= parity.TOL_TEND
+
+
+def ref_points(pts):
+    n = len(pts["temp"])
+    out = {k: np.zeros(n) for k in ("ph", "co2star", "dco2star", "pco2surf", "dpco2")}
+    for i in range(n):
+        r = rt.co2calc_1point(*[float(pts[k][i]) for k in ("depth", "temp", "salt", "dic", "ta", "pt", "sit",
+                                                           "phlo", "phhi", "xco2", "atmpres")])
+        for k in out:
+            out[k][i] = r[k]
+    return out
+
+
+# ------------------------------------------------------------------ the GPU as the implementation under test
+def _gpu_bgc_runner(ctx, device_mode):
+    def run(cols, surface):
+        return parity.run_gpu_bgc(ctx, cols, device_mode=device_mode, surface=surface)
+    return run
+
+
+@pytest.mark.parametrize("nL,nC,nCols,ragged", [(60, 256, 256, False), (60, 258, 250, True), (80, 130, 130, True)])
+@pytest.mark.parametrize("device_mode", [True, False])
+def test_bgc_source_sink_and_surface_fluxes(nL, nC, nCols, ragged, device_mode):
+    parms = host.Parms()
+    rp = rt.RefParms(parms)
+    ctx = host.Context(nL, nC, device=0, parms=parms)
+    check_bgc(_gpu_bgc_runner(ctx, device_mode), parms, rp, nL, nC, nCols, ragged)
+    st = ctx.status()
+    assert st["no_bracket"] == 0 and st["no_convergence"] == 0 and st["nonfinite"] == 0, st
+    ctx.close()
+
+
+def test_dms_and_macros():
+    nL, nC, nCols = 45, 258, 255
+    parms = host.Parms()
+    rp = rt.RefParms(parms)
+    ctx = host.Context(nL, nC, device=0, parms=parms)
+
+    def run(dgot, mgot):
+        host.DMS_SourceSink(ctx, dgot); host.DMS_SurfaceFluxes(ctx, dgot); host.MACROS_SourceSink(ctx, mgot)
+        return dgot, mgot
+    check_dms_macros(run, parms, rp, nL, nC, nCols)
+    ctx.close()
+
+
+@pytest.mark.parametrize("warm", [False, True])
+def test_co2calc_points(warm):
+    """BASELINE.json configs[1] (a 4096-point sample of the 1M points; the reference is scalar)"""
+    parms = host.Parms()
+    rt.RefParms(parms)
+    ctx = host.Context(2, 64, device=0, parms=parms)
+    pts = pkg.synth_co2_points(4096)
+    if warm:
+        ph = ref_points(pts)["ph"]
+        pts["phlo"], pts["phhi"] = ph - 0.2, ph + 0.2
+    r, g = ref_points(pts), host.co2calc_points(ctx, pts)
+    for k in r:
+        assert parity.nerr(g[k], r[k]) <= parity.TOL_SOLVER, k
+    ctx.close()

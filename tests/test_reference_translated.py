@@ -103,6 +103,28 @@ def test_functional_group_table_and_init(po, rp):
     assert rp.name("ind", "units", 0) == "mmol/m^3"
 
 
+def test_product_parameter_init_matches_the_reference(rp):
+    """The C-ABI's own bgc_parms_init / bgc_init / dms_parms_init / macros_parms_init (host C in
+    the product library, no GPU needed) against the reference's module variables and tables."""
+    hp = pkg.host.Parms()
+    m = rt.meta()
+    for src, mod in ((hp.bgc, "bgc_parms"), (hp.dms, "dms_parms"), (hp.macros, "macros_parms")):
+        for n, _ in src._fields_:
+            cn = "%s__%s" % (mod, n.lower())
+            v = getattr(src, n)
+            v = list(v) if hasattr(v, "__len__") else v
+            if cn in m["vars"]:
+                r = rt.var(cn)
+                assert v == (list(r) if hasattr(r, "__len__") else r.value), n
+            elif cn in m["consts"]:
+                assert v == rt.const(cn), n
+    for i in range(4):
+        for n, _ in abi.BgcAutotroph._fields_:
+            assert getattr(hp.autotrophs[i], n) == getattr(rp.autotrophs[i], n.lower()), (i, n)
+    for n, _ in abi.BgcIndices._fields_:
+        assert getattr(hp.ind, n) == getattr(rp.ind, n.lower()), n
+
+
 def test_named_constants_quirks():
     # Q6: single-precision literals widened (BGC_parms.F90:373, :480-486)
     assert rt.const("bgc_parms__epsc") == float(np.float32(1.00e-8)) != 1.00e-8
