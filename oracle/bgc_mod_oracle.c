@@ -1,7 +1,7 @@
 /* bgc_mod_oracle.c — restatement of module BGC_mod (BGC_mod.F90):
  * BGC_SourceSink, init_particulate_terms, compute_particulate_terms,
  * BGC_SurfaceFluxes, SCHMIDT_O2/CO2_singleValue, O2SAT_singleValue.
- * TEST INFRASTRUCTURE ONLY (see bgc_oracle.h).  PARITY UNPINNED.
+ * TEST INFRASTRUCTURE ONLY (see bgc_oracle.h).  Pinned bit for bit against the machine-translated reference (bgc_oracle.h).
  *
  * Arrays keep the reference's Fortran layout (level fastest).  Indices in the
  * macros below are 1-based like the Fortran they restate.  Expressions keep the

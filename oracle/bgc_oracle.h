@@ -6,16 +6,17 @@
  * and as the `cpu_baseline` / `--impl reference` leg of bench.py.  Nothing in
  * the product path (ocean-bgc_b200/, include/) links, imports or calls it.
  *
- * PARITY UNPINNED: the reference ships no tests, fixtures or golden vectors and
- * no Fortran compiler exists in this image, so the restatement cannot be run
- * against the reference itself.  Its fidelity rests on (1) line-by-line
- * restatement with file:line citations, (2) the comment-level known answers in
- * the reference (O2SAT(10,35)=282.015, dust_to_Fe=626712, solver iteration
- * counts), (3) published check values of the carbonate constants, (4) the
- * code's own conservation diagnostics Jint_*tot ~ 0, (5) an independent NumPy
- * restatement of co2calc (oracle/co2calc_numpy.py), and (6) agreement with the
- * separately written CUDA implementation.  tests/fortran/ holds a driver that
- * pins it against the real reference whenever gfortran is available.
+ * PINNED AGAINST THE REFERENCE RUN THROUGH A SOURCE TRANSLATION: the reference ships no
+ * tests, fixtures or golden vectors and no Fortran compiler exists in this image, so the
+ * reference's own sources are machine-translated to C (oracle/f90c.py) and compiled with gcc
+ * into oracle/_ref/libbgc_ref.so; every routine of this oracle is compared with it BIT FOR BIT
+ * on the same inputs (tests/test_reference_translated.py) and tests/golden/ holds outputs of
+ * that library.  Caveat: a translation by the same author, not a gfortran build
+ * (DESIGN.md section 4 lists what could still slip through; tests/fortran/ closes it wherever
+ * gfortran exists).  Further anchors: the comment-level known answers in the reference
+ * (O2SAT(10,35)=282.015, dust_to_Fe=626712), published check values of the carbonate
+ * constants, the code's own conservation diagnostics Jint_*tot ~ 0, an independent NumPy
+ * restatement of co2calc (oracle/co2calc_numpy.py).
  *
  * Build: gcc -O2 -ffp-contract=off (mirrors gfortran -O2 on x86-64: no FMA
  * contraction, no reassociation); see oracle/Makefile.

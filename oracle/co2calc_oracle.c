@@ -1,6 +1,6 @@
 /* co2calc_oracle.c — restatement of module co2calc (co2calc.F90), default
  * (non-CCSMCOUPLED) build: intrinsics EXP/LOG/SQRT -> libm.
- * TEST INFRASTRUCTURE ONLY (see bgc_oracle.h).  PARITY UNPINNED.
+ * TEST INFRASTRUCTURE ONLY (see bgc_oracle.h).  Pinned bit for bit against the machine-translated reference (bgc_oracle.h).
  *
  * Every expression keeps the reference's left-to-right evaluation order;
  * compile with -O2 -ffp-contract=off. */

@@ -1,6 +1,6 @@
 /* dms_macros_oracle.c — restatement of DMS_SourceSink, DMS_SurfaceFluxes
  * (DMS_mod.F90) and MACROS_SourceSink (MACROS_mod.F90).
- * TEST INFRASTRUCTURE ONLY (see bgc_oracle.h).  PARITY UNPINNED. */
+ * TEST INFRASTRUCTURE ONLY (see bgc_oracle.h).  Pinned against the translated reference. */
 #include "bgc_oracle.h"
 #include <math.h>
 #include <stdlib.h>

@@ -1,9 +1,10 @@
 """ctypes binding of the CPU oracle (oracle/libbgc_oracle.so).
 
 TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and the
-cpu_baseline / --impl reference legs of bench.py.  PARITY UNPINNED (see
-bgc_oracle.h): no reference test vectors exist and no Fortran compiler is
-available to run the reference itself.
+cpu_baseline / --impl reference legs of bench.py.  Pinned bit for bit against
+the reference's own sources machine-translated to C (oracle/f90c.py ->
+oracle/_ref/libbgc_ref.so, oracle/ref_translated.py); see bgc_oracle.h for the
+caveat (a translation, not a gfortran build).
 """
 import ctypes as C
 import os

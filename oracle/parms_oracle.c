@@ -1,6 +1,6 @@
 /* parms_oracle.c — restatement of BGC_parms_init / DMS_parms_init /
  * MACROS_parms_init and the index wiring of BGC_init.
- * TEST INFRASTRUCTURE ONLY (see bgc_oracle.h).  PARITY UNPINNED. */
+ * TEST INFRASTRUCTURE ONLY (see bgc_oracle.h).  Pinned against the translated reference. */
 #include "bgc_oracle.h"
 #include <string.h>
 #ifdef _OPENMP

@@ -1,6 +1,7 @@
 """Pins the CPU oracle against the UNMODIFIED reference Fortran - wherever a Fortran compiler
 and the reference tree exist (neither does in the image this repository is developed in, nor
-on the GPU box: the test then skips and the oracle stays "parity unpinned").
+on the GPU box: the test then skips and the pinning rests on the translated reference,
+tests/test_reference_translated.py and DESIGN.md section 4).
 
 tests/fortran/ref_driver.F90 links the reference's own objects; nothing of the reference is
 copied into this repository.
