@@ -53,13 +53,38 @@ def strip_comment(s):
     return "".join(out)
 
 
+def split_semicolons(s):
+    out, cur, q = [], [], None
+    for ch in s:
+        if q:
+            cur.append(ch)
+            if ch == q:
+                q = None
+        elif ch in "'\"":
+            q = ch
+            cur.append(ch)
+        elif ch == ";":
+            out.append("".join(cur))
+            cur = []
+        else:
+            cur.append(ch)
+    out.append("".join(cur))
+    return [x.strip() for x in out if x.strip()]
+
+
 def read_source(path, defines=()):
-    """cpp conditionals (#ifdef/#ifndef/#else/#endif), comments, continuation lines."""
+    """cpp conditionals (#ifdef/#ifndef/#else/#endif), comments, continuation lines, INCLUDE
+    lines, `;` statement separators."""
     short = path.rsplit("/", 1)[-1]
     lines, stack, active = [], [], True
     cur, cur_no = "", 0
     for no, raw in enumerate(open(path, encoding="latin-1"), 1):
         s = raw.rstrip("\n")
+        m = re.match(r"""\s*include\s+(['"])(.+?)\1\s*$""", s, re.I)
+        if m and active and not cur:
+            inc = path.rsplit("/", 1)[0] + "/" + m.group(2) if "/" in path else m.group(2)
+            lines.extend(read_source(inc, defines))
+            continue
         if s.lstrip().startswith("#"):
             d = s.lstrip()[1:].split()
             if d[0] in ("ifdef", "ifndef"):
@@ -88,7 +113,8 @@ def read_source(path, defines=()):
         if cur.endswith("&"):
             cur = cur[:-1]
             continue
-        lines.append(Line(cur.strip(), short, cur_no))
+        for part in split_semicolons(cur):
+            lines.append(Line(part, short, cur_no))
         cur = ""
     return lines
 
@@ -100,7 +126,7 @@ TOK = re.compile(r"""
  | (?P<dot>\.(?:and|or|not|eqv|neqv|eq|ne|lt|le|gt|ge|true|false)\.)
  | (?P<num>(?:\d+\.(?![a-zA-Z]+\.)\d*|\.\d+|\d+)(?:[edED][+-]?\d+)?(?:_\w+)?)
  | (?P<id>[A-Za-z]\w*)
- | (?P<op>\*\*|//|==|/=|<=|>=|=>|::|\(/|/\)|[-+*/()=,:%<>])
+ | (?P<op>\*\*|//|==|/=|<=|>=|=>|::|\(/|/\)|[-+*/()=,:%<>\[\]])
  | (?P<ws>\s+)
 """, re.X | re.I)
 
@@ -301,11 +327,11 @@ class Parser:
             e = self.expr()
             self.expect(")")
             return Paren(e)
-        if k == "op" and v == "(/":
+        if k == "op" and v in ("(/", "["):
             items = [self.expr()]
             while self.accept(","):
                 items.append(self.expr())
-            self.expect("/)")
+            self.expect("/)" if v == "(/" else "]")
             return ArrCons(items)
         if k == "id":
             parts = []
@@ -338,6 +364,9 @@ class Parser:
             return args
 
     def arg(self):
+        if self.peek() == ("op", "*") and self.peek(1)[1] in (",", ")"):
+            self.next()
+            return Colon()            # assumed size / assumed length
         if self.peek()[0] == "id" and self.peek(1) == ("op", "="):
             name = self.next()[1]
             self.next()
@@ -368,8 +397,10 @@ class T:
         return T(self.base, self.kind, 0, self.tname, self.clen)
 
     def ctype(self):
+        if self.base == "cptr":
+            return "void *"
         if self.base == "int":
-            return "long long" if self.kind == 8 else "int"
+            return {8: "long long", 1: "signed char", 2: "short"}.get(self.kind, "int")
         if self.base == "real":
             return "double" if self.kind == 8 else "float"
         if self.base == "logical":
@@ -379,8 +410,10 @@ class T:
         return f"struct {self.tname}"
 
     def code(self):
+        if self.base == "cptr":
+            return "cptr"
         if self.base == "int":
-            return "i8" if self.kind == 8 else "i4"
+            return {8: "i8", 1: "i1", 2: "i2"}.get(self.kind, "i4")
         if self.base == "real":
             return "r8" if self.kind == 8 else "r4"
         if self.base == "logical":
@@ -400,6 +433,8 @@ class Sym:
         self.module = None
         self.is_result = False
         self.local_const = False
+        self.pointer = False
+        self.value = False
 
 
 class DType:
@@ -414,6 +449,10 @@ class Proc:
         self.syms, self.body, self.decl_lines = {}, [], []
         self.cname = f"{module.name}__{name}"
         self.rtype = None
+        self.parent = None       # host procedure of an internal procedure
+        self.children = []
+        self.external = False    # interface body with bind(C): a C function defined elsewhere
+        self.prefix_type = None
 
 
 class Module:
@@ -430,6 +469,7 @@ INTRINSIC_ELEMENTAL = {"exp": "exp", "log": "log", "log10": "log10", "sqrt": "sq
 
 PRELUDE = r"""/* GENERATED by oracle/f90c.py from the reference Fortran sources — do not edit, do not commit. */
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #ifndef REF_TLS
@@ -441,6 +481,11 @@ static inline fstr_t f_lit(const char *s, int n) { fstr_t r; r.n = n; memcpy(r.s
 static inline fstr_t f_var(const char *s, int n) { fstr_t r; r.n = n; memcpy(r.s, s, n); return r; }
 static inline fstr_t f_trim(fstr_t a) { while (a.n > 0 && a.s[a.n - 1] == ' ') a.n--; return a; }
 static inline fstr_t f_cat(fstr_t a, fstr_t b) { memcpy(a.s + a.n, b.s, b.n); a.n += b.n; return a; }
+static inline int f_cmp(fstr_t a, fstr_t b) {   /* blank-padded comparison */
+  int n = a.n > b.n ? a.n : b.n;
+  for (int i = 0; i < n; i++) { unsigned char x = i < a.n ? a.s[i] : ' ', y = i < b.n ? b.s[i] : ' ';
+    if (x != y) return x < y ? -1 : 1; }
+  return 0; }
 static inline void f_assign(char *d, int dn, fstr_t v) {
   int n = v.n < dn ? v.n : dn; memcpy(d, v.s, n); if (n < dn) memset(d + n, ' ', dn - n); }
 /* MAX/MIN as gfortran expands them without -ffast-math: m = a1; if (a2 > m) m = a2; ... */
@@ -457,10 +502,26 @@ static void *f_alloc(size_t nbytes) { return malloc(nbytes ? nbytes : 1); }
 """
 
 
+ISO_C_KINDS = {"c_int": 4, "c_long_long": 8, "c_size_t": 8, "c_double": 8, "c_float": 4, "c_char": 1,
+               "c_signed_char": 1, "c_short": 2, "c_long": 8, "c_int64_t": 8, "c_int32_t": 4, "c_bool": 1}
+
+
 class Translator:
     def __init__(self):
         self.modules = {}
         self.order = []
+        iso = Module("iso_c_binding")
+        for n, v in ISO_C_KINDS.items():
+            sy = Sym(n, T("int", 4), param=True, init=Num(str(v)))
+            sy.cname, sy.module = str(v), iso
+            iso.syms[n] = sy
+        sy = Sym("c_null_ptr", T("cptr", 8), param=True, init=Num("0"))
+        sy.cname, sy.module = "((void *)0)", iso
+        iso.syms["c_null_ptr"] = sy
+        sy = Sym("c_null_char", T("char", 1, 0, None, 1), param=True, init=Str("\0"))
+        sy.cname, sy.module = "f_lit(\"\\0\", 1)", iso
+        iso.syms["c_null_char"] = sy
+        self.modules["iso_c_binding"] = iso
         self.out = []
         self.tmp = 0
         self.cur_line = None
@@ -475,33 +536,33 @@ class Translator:
     # ---------------------------------------------------------------- pass 1: structure
     def load(self, path):
         lines = read_source(path)
-        i = 0
-        mod = proc = dtype = None
-        in_contains = False
-        while i < len(lines):
-            ln = lines[i]
+        mod = dtype = None
+        stack = []            # open procedures: [module procedure, internal procedure]
+        in_interface = False
+        for ln in lines:
             self.cur_line = ln
-            i += 1
             toks = tokenize(ln.text, f"{ln.file}:{ln.no}")
             w0 = toks[0][1] if toks[0][0] == "id" else None
             w1 = toks[1][1] if len(toks) > 1 and toks[1][0] == "id" else None
+            proc = stack[-1] if stack else None
             if w0 == "module" and w1 and w1 != "procedure":
                 mod = Module(w1)
                 self.modules[w1] = mod
                 self.order.append(mod)
-                in_contains = False
                 continue
-            if w0 == "end" or (w0 and w0.startswith("end") and w0 in
-                               ("endmodule", "endsubroutine", "endfunction", "endtype")):
+            if w0 == "end" or w0 in ("endmodule", "endsubroutine", "endfunction", "endtype", "endinterface"):
                 what = w1 if w0 == "end" else w0[3:]
                 if what == "module":
                     mod = None
                     continue
                 if what in ("subroutine", "function"):
-                    proc = None
+                    stack.pop()
                     continue
                 if what == "type":
                     dtype = None
+                    continue
+                if what == "interface":
+                    in_interface = False
                     continue
                 if proc is None:
                     self.err("unexpected END")
@@ -511,15 +572,23 @@ class Translator:
             if dtype is not None:
                 self.decl(toks, dtype=dtype, mod=mod)
                 continue
-            if proc is None:
+            if w0 == "interface" and len(toks) == 1:
+                in_interface = True
+                continue
+            if proc is None or (w0 == "contains") or self._is_proc_header(toks):
                 if w0 == "contains":
-                    in_contains = True
                     continue
-                if self.proc_header(toks, mod, ln) is not None:
-                    proc = self.proc_header_result
+                hdr = self.proc_header(toks, mod, ln, parent=proc)
+                if hdr is not None:
+                    hdr.external = in_interface
+                    stack.append(hdr)
                     continue
+            if proc is None:
                 if w0 == "use":
-                    mod.uses.append(toks[1][1])
+                    i = 1
+                    if toks[1][1] == ",":          # use, intrinsic :: name
+                        i = [v for _, v in toks].index("::") + 1
+                    mod.uses.append(toks[i][1])
                     continue
                 if w0 == "implicit" or w0 == "save":
                     continue
@@ -527,6 +596,8 @@ class Translator:
                     mod.default_private = True
                     continue
                 if w0 in ("private", "public") and (len(toks) == 1 or toks[1][1] == "::"):
+                    continue
+                if w0 == "public" and len(toks) > 1 and toks[1][0] == "id":
                     continue
                 if w0 == "type" and toks[1][1] != "(":
                     name = [v for k, v in toks if k == "id"][-1]
@@ -539,15 +610,24 @@ class Translator:
             proc.body.append((ln, toks))
         return self
 
-    def proc_header(self, toks, mod, ln):
+    @staticmethod
+    def _is_proc_header(toks):
+        ids = [v for k, v in toks if k == "id"]
+        if not ids or "::" in [v for _, v in toks]:
+            return False
+        if ids[0] in ("subroutine", "function"):
+            return True
+        return ids[0] in ("real", "integer", "logical", "type", "pure", "elemental", "recursive") \
+            and "function" in ids and "=" not in [v for k, v in toks if k == "op"][:1]
+
+    def proc_header(self, toks, mod, ln, parent=None):
         ids = [v for k, v in toks]
-        self.proc_header_result = None
         for kw in ("subroutine", "function"):
             if kw in ids and toks[ids.index(kw)][0] == "id":
                 j = ids.index(kw)
-                # `real(r8) function f(x)` allowed; a declaration would have '::' before
+                # `integer(c_int) function f(x)` allowed; a declaration would have '::' before
                 if "::" in ids[:j] or (j > 0 and ids[0] not in
-                                       ("real", "integer", "logical", "pure", "elemental", "recursive")):
+                                       ("real", "integer", "logical", "type", "pure", "elemental", "recursive")):
                     return None
                 name = ids[j + 1]
                 args, result = [], name
@@ -559,11 +639,31 @@ class Translator:
                             args.append(ids[k])
                         k += 1
                     k += 1
-                if k < len(ids) and ids[k] == "result":
-                    result = ids[k + 2]
+                bind_name = None
+                while k < len(ids):
+                    if ids[k] == "result":
+                        result = ids[k + 2]
+                        k += 4
+                    elif ids[k] == "bind":
+                        e = ids.index(")", k)
+                        for t in range(k, e):
+                            if toks[t][0] == "str":
+                                bind_name = toks[t][1][1:-1]
+                        k = e + 1
+                    else:
+                        k += 1
                 p = Proc(name, kw, args, result if kw == "function" else None, mod, ln)
-                mod.procs[name] = p
-                self.proc_header_result = p
+                if j > 0 and ids[0] in ("real", "integer", "logical", "type"):
+                    self.scope_mod = mod
+                    p.prefix_type = self.parse_typespec(Parser(toks[:j], f"{ln.file}:{ln.no}"))
+                if bind_name:
+                    p.cname = bind_name
+                if parent is not None:
+                    p.parent = parent
+                    p.cname = f"{parent.cname}__{name}"
+                    parent.children.append(p)
+                else:
+                    mod.procs[name] = p
                 return p
         return None
 
@@ -614,6 +714,8 @@ class Translator:
             p.expect("(")
             name = p.next()[1]
             p.expect(")")
+            if name == "c_ptr":
+                return T("cptr", 8)
             return T("type", 0, 0, self.find_type(name).cname)
         base = {"real": "real", "integer": "int", "logical": "logical", "character": "char"}[w]
         kind, clen = 4, 1
@@ -624,6 +726,10 @@ class Translator:
             if p.peek()[0] == "id" and p.peek()[1] in ("kind", "len") and p.peek(1) == ("op", "="):
                 p.next()
                 p.next()
+            if p.peek() == ("op", "*"):
+                p.next()
+                p.expect(")")
+                return T("char", 1, 0, None, -1)      # assumed length: travels as an fstr_t value
             e = p.expr()
             p.expect(")")
             v = self.const_int(e, None)
@@ -651,7 +757,7 @@ class Translator:
                     p.next()
                     attrs["intent"] = "inout"
                 p.expect(")")
-            elif a in ("parameter", "allocatable", "public", "private", "save", "target"):
+            elif a in ("parameter", "allocatable", "public", "private", "save", "target", "pointer", "value"):
                 attrs[a] = True
             else:
                 self.err(f"unsupported attribute {a}")
@@ -668,8 +774,13 @@ class Translator:
             if p.accept("="):
                 init = p.expr()
             t = T(typ.base, typ.kind, len(dims) if dims else 0, typ.tname, typ.clen)
-            s = Sym(name, t, dims, attrs.get("allocatable", False), attrs.get("parameter", False),
-                    init, attrs.get("intent"), attrs.get("private", False))
+            s = Sym(name, t, dims, attrs.get("allocatable", False) or attrs.get("pointer", False),
+                    attrs.get("parameter", False), init, attrs.get("intent"), attrs.get("private", False))
+            s.pointer, s.value = attrs.get("pointer", False), attrs.get("value", False)
+            if dims and not s.alloc and any(isinstance(d, Colon) for d in dims):
+                s.assumed = True          # assumed size / shape dummy: a bare pointer
+            else:
+                s.assumed = False
             if dtype is not None:
                 s.cname = name
                 dtype.fields.append(s)
@@ -727,11 +838,21 @@ class Translator:
         return None
 
     def lookup(self, name):
-        if self.scope_proc is not None and name in self.scope_proc.syms:
-            return self.scope_proc.syms[name]
+        pr = self.scope_proc
+        while pr is not None:
+            if name in pr.syms:
+                return pr.syms[name]
+            pr = pr.parent
         return self.lookup_mod(name, self.scope_mod, set(), False)
 
     def lookup_proc(self, name, mod=None, seen=None):
+        if mod is None:
+            pr = self.scope_proc
+            while pr is not None:
+                for ch in pr.children:
+                    if ch.name == name:
+                        return ch
+                pr = pr.parent
         mod = mod or self.scope_mod
         seen = seen if seen is not None else set()
         if mod.name in seen:
@@ -807,7 +928,7 @@ class Translator:
             obj, typ, lval = s.cname, s.typ, False
         else:
             obj = s.cname
-            if s.dummy and s.typ.rank == 0:
+            if s.dummy and (s.typ.rank == 0 or s.alloc) and not s.value and s.typ.base != "char":
                 obj = f"(*{s.cname})"
             typ, lval = s.typ, not s.param
         cur = s
@@ -820,6 +941,7 @@ class Translator:
                     self.err(f"type {d.name} has no component {pname}")
                 obj = f"{obj}.{f.cname}"
                 cur, typ = f, f.typ
+            self.last_sym = cur
             if pargs is not None:
                 if typ.rank == 0:
                     self.err(f"{pname} is not an array")
@@ -875,15 +997,17 @@ class Translator:
             name, args = e.parts[0]
             s = self.lookup(name)
             if s is None:
-                if name in ("sum", "size", "maxval", "minval", "trim"):
-                    return None
+                elemental = name in INTRINSIC_ELEMENTAL or name in ("abs", "max", "min", "merge", "real",
+                                                                   "int", "mod")
+                if not elemental:
+                    return None          # inquiry / transformational intrinsics, user functions
                 if args is not None:
                     for a in args:
                         x = self.extent_of(a)
                         if x:
                             return x
                 return None
-            obj = f"(*{s.cname})" if (s.dummy and s.typ.rank == 0) else s.cname
+            obj = f"(*{s.cname})" if (s.dummy and (s.typ.rank == 0 or s.alloc) and not s.value) else s.cname
             cur, typ = s, s.typ
             for pi, (pname, pargs) in enumerate(e.parts):
                 if pi > 0:
@@ -921,7 +1045,7 @@ class Translator:
             return ("1" if e.val else "0"), T("logical")
         if isinstance(e, Str):
             esc = e.val.replace("\\", "\\\\").replace('"', '\\"')
-            return f'f_lit("{esc}", {len(e.val)})', T("char", 1, 0, None, len(e.val))
+            return f'f_lit("{esc}", {len(e.val)})', T("char", 1, 0, None, 0)
         if isinstance(e, Paren):
             c, t = self.emit(e.e, ivar)
             return f"({c})", t
@@ -941,6 +1065,8 @@ class Translator:
             if e.op in (".eqv.", ".neqv."):
                 return f"((!!({lc})) {'==' if e.op == '.eqv.' else '!='} (!!({rc})))", T("logical")
             if e.op in ("==", "!=", "<", "<=", ">", ">="):
+                if lt.base == "char" or rt.base == "char":
+                    return f"(f_cmp({self.as_fstr(lc, lt)}, {self.as_fstr(rc, rt)}) {e.op} 0)", T("logical")
                 return f"(({lc}) {e.op} ({rc}))", T("logical")
             if e.op == "//":
                 lc = self.as_fstr(lc, lt)
@@ -971,7 +1097,7 @@ class Translator:
         self.err("unsupported expression node")
 
     def as_fstr(self, c, t):
-        if c.startswith("f_"):
+        if t.clen is None or t.clen <= 0 or c.startswith(("f_lit(", "f_cat(", "f_trim(", "f_var(")):
             return c
         return f"f_var({c}, {t.clen})"
 
@@ -1030,12 +1156,36 @@ class Translator:
             return (f"({{ {t.ctype()} {acc} = {zero}; for (int {iv} = 0; {iv} < ({n}); {iv}++) "
                     f"{acc} += ({c}); {acc}; }})"), t
         if name == "size":
+            if len(args) == 2:
+                self.want_whole = True
+                c, t, _ = self.resolve_ref(args[0], None)
+                self.want_whole = False
+                sym = self.last_sym
+                return f"((int)({self.sym_extent(sym, c, self.const_int(args[1], None) - 1)}))", T("int", 4)
             self.want_whole = True
             n = self.extent_of(args[0])
             self.want_whole = False
             if n is None:
                 self.err("size of a scalar")
             return f"((int)({n}))", T("int", 4)
+        if name in ("allocated", "associated"):
+            self.want_whole = True
+            c, t, _ = self.resolve_ref(args[0], None)
+            self.want_whole = False
+            return f"(({c}).p != 0)", T("logical")
+        if name == "c_associated":
+            c, t = self.emit(args[0], ivar)
+            return f"(({c}) != 0)", T("logical")
+        if name == "c_loc":
+            self.want_whole = True
+            c, t, _ = self.resolve_ref(args[0], None)
+            self.want_whole = False
+            sym = self.last_sym
+            if t.rank > 0 and sym.alloc:
+                return f"((void *)({c}).p)", T("cptr", 8)
+            if t.rank > 0:
+                return f"((void *)({c}))", T("cptr", 8)
+            return f"((void *)&({c}))", T("cptr", 8)
         if name == "trim":
             c, t = self.emit(args[0], ivar)
             return f"f_trim({self.as_fstr(c, t)})", T("char", 1, 0, None, 0)
@@ -1046,7 +1196,8 @@ class Translator:
             return f"(({rt.ctype()})({c}))", rt
         if name == "int":
             c, t = self.emit(args[0], ivar)
-            return f"((int)({c}))", T("int", 4)
+            rt_ = T("int", self.const_int(args[1], None) if len(args) > 1 else 4)
+            return f"(({rt_.ctype()})({c}))", rt_
         if name == "mod":
             ac, at = self.emit(args[0], ivar)
             bc, bt = self.emit(args[1], ivar)
@@ -1071,6 +1222,14 @@ class Translator:
             ordered[pos] = a
         for a, dn in zip(ordered, pr.args):
             ds = pr.syms[dn]
+            if ds.typ.base == "char" and ds.typ.rank == 0:
+                c, t = self.emit(a, ivar)
+                out.append(self.as_fstr(c, t))
+                continue
+            if ds.value:
+                c, t = self.emit(a, ivar)
+                out.append(f"({ds.typ.ctype()})({c})")
+                continue
             if ds.typ.rank > 0:
                 # whole-array actual
                 if not isinstance(a, Ref):
@@ -1086,8 +1245,9 @@ class Translator:
                 r = self.resolve_ref(a, ivar)
                 if r is not None and r[2] and r[1].rank == 0:
                     lv = r
-            if lv is not None and (lv[1].base, lv[1].kind, lv[1].tname) == \
-                    (ds.typ.base, ds.typ.kind, ds.typ.tname):
+            if lv is not None and (lv[1].base in ("cptr",) and ds.typ.base == "cptr" or
+                                   (lv[1].base, lv[1].kind, lv[1].tname) ==
+                                   (ds.typ.base, ds.typ.kind, ds.typ.tname)):
                 out.append(f"&({lv[0]})")
             else:
                 if ds.typ.base == "type":
@@ -1211,6 +1371,100 @@ class Translator:
             self.tmp += 1
             self.loopnames.append([f"{label}_{self.tmp}", False, False, label] if label else None)
             return
+        if k0 == "id" and w0 == "do" and w1 == "while":
+            p.next()
+            p.next()
+            p.expect("(")
+            c, _ = self.emit(p.expr())
+            p.expect(")")
+            self.w("{")
+            self.ind += 1
+            self.w(f"while ({c}) {{")
+            self.ind += 1
+            self.blocks.append("do")
+            self.loopnames.append(None)
+            return
+        if k0 == "id" and (w0 == "stop" or (w0 == "error" and w1 == "stop")):
+            msg = next((v[1:-1] for k, v in toks if k == "str"), "STOP")
+            esc = msg.replace("\\", "\\\\").replace('"', '\\"')
+            self.w(f'fputs("{esc}\\n", stderr); abort();')
+            return
+        if k0 == "id" and w0 == "write" and w1 == "(":
+            # unit and format are ignored: every item goes to stderr in list order (error paths only)
+            depth, j = 0, 1
+            while True:
+                if toks[j][1] == "(" and toks[j][0] == "op":
+                    depth += 1
+                elif toks[j][1] == ")" and toks[j][0] == "op":
+                    depth -= 1
+                    if depth == 0:
+                        break
+                j += 1
+            ip = Parser(toks[j + 1:], p.where)
+            while not ip.at_end():
+                a = ip.arg()
+                if isinstance(a, Ref) and a.parts[-1][1] and isinstance(a.parts[-1][1][0], Colon) \
+                        and a.parts[-1][1][0].hi is not None:
+                    sec = a.parts[-1][1][0]
+                    base = Ref(a.parts[:-1] + [(a.parts[-1][0], [sec.lo or Num("1")])])
+                    bc, bt, _ = self.resolve_ref(base, None)
+                    hi, _ = self.emit(sec.hi)
+                    lo, _ = self.emit(sec.lo or Num("1"))
+                    self.w(f"fwrite((const char *)({bc}), 1, (size_t)(({hi}) - ({lo}) + 1), stderr);")
+                else:
+                    c, t = self.emit(a)
+                    if t.base == "char":
+                        tv = self.newtmp("_w")
+                        self.w(f"{{ fstr_t {tv} = {self.as_fstr(c, t)}; fwrite({tv}.s, 1, {tv}.n, stderr); }}")
+                    elif t.base == "real":
+                        self.w(f'fprintf(stderr, " %.17g", (double)({c}));')
+                    else:
+                        self.w(f'fprintf(stderr, " %lld", (long long)({c}));')
+                ip.accept(",")
+            self.w('fputc(10, stderr);')
+            return
+        if k0 == "id" and w0 == "read" and w1 == "(":
+            # only: read(<character variable>, *, iostat=<int>) <integer variable>
+            ip = Parser(toks[2:], p.where)
+            items = ip.arglist()
+            src, st_ = items[0], next((x.e for x in items if isinstance(x, Kw) and x.name == "iostat"), None)
+            tgt = ip.expr()
+            sc, stt = self.emit(src)
+            tc, tt, _ = self.resolve_ref(tgt, None)
+            if stt.base != "char" or tt.base != "int":
+                self.err("unsupported READ")
+            tv = self.newtmp("_r")
+            self.w(f"{{ fstr_t {tv} = {self.as_fstr(sc, stt)}; {tv}.s[{tv}.n] = 0; long long _v; "
+                   f"int _ok = sscanf({tv}.s, \"%lld\", &_v) == 1; if (_ok) {tc} = _v;")
+            if st_ is not None:
+                self.w(f"  {self.resolve_ref(st_, None)[0]} = _ok ? 0 : 1;")
+            self.w("}")
+            return
+        if k0 == "id" and w0 == "call" and w1 == "get_environment_variable":
+            ip = Parser(toks[3:], p.where)
+            items = ip.arglist()
+            nm, _t = self.emit(items[0])
+            val = self.resolve_ref(items[1], None)
+            st_ = next((x.e for x in items if isinstance(x, Kw) and x.name == "status"), None)
+            tv = self.newtmp("_g")
+            self.w(f"{{ fstr_t {tv} = {self.as_fstr(nm, _t)}; {tv}.s[{tv}.n] = 0; const char *_e = getenv({tv}.s);")
+            self.w(f"  f_assign({val[0]}, {val[1].clen}, _e ? f_lit(_e, (int)strlen(_e)) : f_lit(\"\", 0));")
+            if st_ is not None:
+                self.w(f"  {self.resolve_ref(st_, None)[0]} = _e ? 0 : 1;")
+            self.w("}")
+            return
+        if k0 == "id" and w0 == "call" and w1 == "c_f_pointer":
+            ip = Parser(toks[3:], p.where)
+            items = ip.arglist()
+            pc, _t = self.emit(items[0])
+            self.want_whole = True
+            fc, ft, _ = self.resolve_ref(items[1], None)
+            self.want_whole = False
+            self.w(f"({fc}).p = {pc};")
+            if len(items) > 2 and isinstance(items[2], ArrCons):
+                for dnum, d in enumerate(items[2].items):
+                    self.w(f"({fc}).n{dnum + 1} = {self.emit(d)[0]};")
+            return
         if k0 == "id" and w0 == "select" and w1 == "case":
             p.next()
             p.next()
@@ -1270,7 +1524,7 @@ class Translator:
                 self.w(f"goto _brk_{lab[0]};")
             return
         if k0 == "id" and w0 == "return" and len(toks) == 1:
-            self.w("goto _ret;")
+            self.w(f"goto {self.retlabel};")
             self.uses_ret = True
             return
         if k0 == "id" and w0 == "call":
@@ -1369,14 +1623,19 @@ class Translator:
             dim += f"[{t.clen}]"
         return f"{pre}{t.ctype()} {name}{dim};"
 
+    def has_default_init(self, t):
+        return t.base == "type" and any(f.init is not None for f in self.type_by_cname(t.tname).fields)
+
     def proto(self, pr):
         args = []
         for a in pr.args:
             s = pr.syms[a]
             if s.alloc:
                 args.append(f"fa_t *{s.cname}")
-            elif s.typ.base == "char":
-                self.err("character dummy arguments are not supported")
+            elif s.typ.base == "char" and s.typ.rank == 0:
+                args.append(f"fstr_t {s.cname}")       # character(len=*) dummy: by value
+            elif s.value:
+                args.append(f"{s.typ.ctype()} {s.cname}")
             else:
                 args.append(f"{s.typ.ctype()} *{s.cname}")
         r = pr.rtype.ctype() if pr.kind == "function" else "void"
@@ -1390,8 +1649,8 @@ class Translator:
         for ln, toks in pr.body:
             self.cur_line = ln
             w0 = toks[0][1]
-            if toks[0][0] == "id" and not body:
-                if w0 in ("implicit", "use", "save"):
+            if toks[0][0] == "id":
+                if w0 in ("implicit", "use", "save", "import"):
                     if w0 == "use":
                         self.err("procedure-level USE is not supported")
                     continue
@@ -1401,36 +1660,38 @@ class Translator:
                     continue
             body.append((ln, toks))
         pr.body = body
+        self.cur_line = pr.line
         for a in pr.args:
             if a not in pr.syms:
-                self.cur_line = pr.line
                 self.err(f"dummy argument {a} is not declared")
             pr.syms[a].dummy = True
         if pr.kind == "function":
             if pr.result not in pr.syms:
-                self.cur_line = pr.line
-                self.err("function result is not declared in the body")
+                if pr.prefix_type is None:
+                    self.err("function result is not declared")
+                rs = Sym(pr.result, pr.prefix_type)
+                rs.cname = pr.result + "_"
+                pr.syms[pr.result] = rs
             pr.syms[pr.result].is_result = True
             pr.rtype = pr.syms[pr.result].typ
         for s in pr.syms.values():
             if s.param:
                 s.local_const = True
+        for ch in pr.children:
+            self.prepare_proc(ch)
 
-    @staticmethod
-    def _first_dcolon(toks):
-        for i, (k, v) in enumerate(toks):
-            if v == "::":
-                return i
-        return min(len(toks), 3)
-
-    def emit_proc(self, pr):
+    def emit_proc(self, pr, nested=False):
+        saved = None
+        if nested:      # an internal procedure becomes a GCC nested function of its host
+            saved = (self.scope_proc, self.blocks, self.selvar, self.ind, self.uses_ret, self.loopnames)
+        base_ind = self.ind if nested else 0
         self.scope_mod, self.scope_proc = pr.module, pr
-        self.blocks, self.selvar, self.ind, self.uses_ret = [], [], 0, False
-        self.loopnames = []
+        self.blocks, self.selvar, self.uses_ret, self.loopnames = [], [], False, []
+        self.ind = base_ind
         self.cur_line = pr.line
         self.w(f"/* {pr.line.file}:{pr.line.no} {pr.kind} {pr.name} */")
-        self.w(self.proto(pr) + " {")
-        self.ind = 1
+        self.w(("auto " if nested else "") + self.proto(pr) + " {")
+        self.ind = base_ind + 1
         allocs = []
         for s in pr.syms.values():
             if s.dummy:
@@ -1444,8 +1705,16 @@ class Translator:
             d = self.cdecl(s)
             if s.alloc:
                 d = d[:-1] + " = {0, 0, 0, 0};"
-                allocs.append(s)
+                if not s.pointer:
+                    allocs.append(s)
+            elif s.typ.rank == 0 and self.has_default_init(s.typ):
+                d = d[:-1] + " = {0};"       # the only default initialiser in use is c_null_ptr
             self.w(d)
+        retlabel = "_ret" if not nested else f"_ret_{pr.name}"
+        for ch in pr.children:
+            self.emit_proc(ch, nested=True)
+            self.scope_mod, self.scope_proc = pr.module, pr
+        self.retlabel = retlabel
         for ln, toks in pr.body:
             self.cur_line = ln
             mark = len(self.out)
@@ -1454,16 +1723,19 @@ class Translator:
         if self.blocks:
             self.cur_line = pr.line
             self.err("unterminated block")
-        self.ind = 1
+        self.ind = base_ind + 1
         if self.uses_ret:
-            self.w("_ret: ;")
+            self.w(f"{retlabel}: ;")
         for s in allocs:       # gfortran frees allocatable locals on exit
             self.w(f"if ({s.cname}.p) free({s.cname}.p);")
         if pr.kind == "function":
             self.w(f"return {pr.syms[pr.result].cname};")
-        self.ind = 0
+        self.ind = base_ind
         self.w("}")
-        self.w("")
+        if not nested:
+            self.w("")
+        else:
+            self.scope_proc, self.blocks, self.selvar, self.ind, self.uses_ret, self.loopnames = saved
 
     def translate(self):
         self.ind = 0
@@ -1495,7 +1767,6 @@ class Translator:
                         self.out.append(self.cdecl(s, static_tls=True)[:-1] + f" = {c};")
                     else:
                         self.out.append(self.cdecl(s, static_tls=True))
-                    at = "fa_t" if s.alloc else s.typ.ctype()
                     self.out.append(f"void *ref_addr__{s.cname}(void) {{ return (void *)&{s.cname}; }}")
         # procedures
         for m in self.order:
@@ -1504,20 +1775,21 @@ class Translator:
         for m in self.order:
             for pr in m.procs.values():
                 self.scope_mod, self.scope_proc = m, pr
-                self.out.append(self.proto(pr) + ";")
+                self.out.append(("extern " if pr.external else "") + self.proto(pr) + ";")
         for m in self.order:
             for pr in m.procs.values():
-                self.emit_proc(pr)
+                if not pr.external:
+                    self.emit_proc(pr)
         return "\n".join(self.out) + "\n"
 
     def meta(self):
         def fld(s):
             dims = None
-            if s.typ.rank > 0 and not s.alloc:
+            if s.typ.rank > 0 and not s.alloc and not getattr(s, "assumed", False):
                 self.scope_proc = None
                 dims = [self.const_int(d, None) for d in s.dims]
             return {"name": s.name, "cname": s.cname, "type": s.typ.code(), "rank": s.typ.rank,
-                    "alloc": s.alloc, "dims": dims, "intent": s.intent}
+                    "alloc": s.alloc, "dims": dims, "intent": s.intent, "value": s.value}
         out = {"types": {}, "procs": {}, "vars": {}, "consts": {}}
         for m in self.order:
             self.scope_mod = m
@@ -1531,7 +1803,7 @@ class Translator:
             for pr in m.procs.values():
                 out["procs"][pr.cname] = {
                     "kind": pr.kind, "args": [fld(pr.syms[a]) for a in pr.args],
-                    "result": pr.rtype.code() if pr.rtype else None,
+                    "result": pr.rtype.code() if pr.rtype else None, "external": pr.external,
                     "where": f"{pr.line.file}:{pr.line.no}"}
         return out
 

@@ -26,13 +26,126 @@ LIB_PATH = os.path.join(REFDIR, "libbgc_ref.so")
 META_PATH = os.path.join(REFDIR, "meta.json")
 REFERENCE_SRC = os.environ.get("BGC_REFERENCE_SRC", "/root/reference")
 
-_lib = None
-_meta = None
-_structs = {}
+class FA(C.Structure):
+    """array descriptor of the translation: base pointer + up to three extents"""
+    _fields_ = [("p", C.c_void_p), ("n1", C.c_int), ("n2", C.c_int), ("n3", C.c_int)]
+
+
+_SCALAR = {"i1": C.c_byte, "i2": C.c_short, "i4": C.c_int, "i8": C.c_longlong, "r4": C.c_float,
+           "r8": C.c_double, "log": C.c_int, "cptr": C.c_void_p}
+
+
+class TLib:
+    """One translated library (shared object + the translator's metadata)."""
+
+    def __init__(self, lib_path, meta_path, preload=()):
+        self.lib_path, self.meta_path, self.preload = lib_path, meta_path, list(preload)
+        self._lib = self._meta = None
+        self._structs = {}
+
+    def available(self):
+        return os.path.exists(self.lib_path) and os.path.exists(self.meta_path)
+
+    def ctype(self, code):
+        if code in _SCALAR:
+            return _SCALAR[code]
+        if code.startswith("char"):
+            return C.c_char * int(code[4:])
+        if code.startswith("type:"):
+            return self.struct(code[5:])
+        raise KeyError(code)
+
+    def field_ctype(self, f):
+        if f["alloc"]:
+            return FA
+        t = self.ctype(f["type"])
+        if f["rank"] > 0:
+            t = t * int(np.prod(f["dims"]))
+        return t
+
+    def meta(self):
+        if self._meta is None:
+            self._meta = json.load(open(self.meta_path))
+        return self._meta
+
+    def struct(self, cname):
+        """ctypes mirror of a translated derived type (fields in declaration order)."""
+        if cname not in self._structs:
+            fields = [(f["cname"], self.field_ctype(f)) for f in self.meta()["types"][cname]]
+            self._structs[cname] = type(cname, (C.Structure,), {"_fields_": fields})
+        return self._structs[cname]
+
+    def lib(self):
+        if self._lib is None:
+            if not self.available():
+                if not can_build():
+                    raise RuntimeError(self.lib_path + " is missing and the reference sources are not "
+                                       "available to rebuild it")
+                build()
+            self._keep = [C.CDLL(p, mode=C.RTLD_GLOBAL) for p in self.preload]
+            self._lib = C.CDLL(self.lib_path)
+        return self._lib
+
+    def const(self, cname):
+        """value of a module-level named constant (e.g. 'bgc_parms__epsc')"""
+        f = getattr(self.lib(), "ref_const__" + cname)
+        f.restype = self.ctype(self.meta()["consts"][cname])
+        return f()
+
+    def var(self, cname):
+        """ctypes object aliasing a module variable OF THE CALLING THREAD"""
+        f = getattr(self.lib(), "ref_addr__" + cname)
+        f.restype = C.c_void_p
+        return self.field_ctype(self.meta()["vars"][cname]).from_address(f())
+
+    def call(self, cname, *args):
+        """Call a translated procedure.  Scalars may be given as Python numbers (wrapped, passed
+        by reference; the ctypes objects are returned so that intent(out) values can be read),
+        derived types as ctypes Structures / arrays of them."""
+        pm = self.meta()["procs"][cname]
+        fn = getattr(self.lib(), cname)
+        fn.restype = self.ctype(pm["result"]) if pm["result"] else None
+        if len(args) != len(pm["args"]):
+            raise TypeError(f"{cname}: {len(args)} arguments for {len(pm['args'])} dummies")
+        boxed = []
+        for a, am in zip(args, pm["args"]):
+            if isinstance(a, (C.Structure, C.Array, C._SimpleCData)):
+                boxed.append(a)
+            else:
+                boxed.append(self.ctype(am["type"])(a))
+        r = fn(*[C.byref(b) for b in boxed])
+        return r, boxed
+
+    def fill(self, cname, arrays, scalars=None):
+        """Build a translated derived type whose allocatable components alias the numpy arrays
+        in `arrays` (component names compared case-insensitively) and whose scalar components
+        come from `scalars`.  Returns (struct, keepalive)."""
+        s = self.struct(cname)()
+        low = {k.lower(): v for k, v in arrays.items()}
+        sc = {k.lower(): v for k, v in (scalars or {}).items()}
+        keep = []
+        for f in self.meta()["types"][cname]:
+            n = f["name"]
+            if f["alloc"]:
+                if n in low and low[n] is not None:
+                    a = low[n]
+                    if f["type"].startswith("r8"):
+                        assert a.dtype == np.float64, n
+                    elif f["type"] == "i4":
+                        assert a.dtype == np.int32, n
+                    assert a.ndim == f["rank"], (n, a.shape, f["rank"])
+                    setattr(s, f["cname"], describe(a))
+                    keep.append(a)
+            elif n in sc:
+                setattr(s, f["cname"], sc[n])
+        return s, keep
+
+
+REF = TLib(LIB_PATH, META_PATH)
 
 
 def available():
-    return os.path.exists(LIB_PATH) and os.path.exists(META_PATH)
+    return REF.available()
 
 
 def can_build():
@@ -44,91 +157,32 @@ def build():
     subprocess.check_call(["make", "-s", "-C", HERE, "ref", f"REFERENCE_SRC={REFERENCE_SRC}"])
 
 
-class FA(C.Structure):
-    """array descriptor of the translation: base pointer + up to three extents"""
-    _fields_ = [("p", C.c_void_p), ("n1", C.c_int), ("n2", C.c_int), ("n3", C.c_int)]
-
-
-_SCALAR = {"i4": C.c_int, "i8": C.c_longlong, "r4": C.c_float, "r8": C.c_double, "log": C.c_int}
-
-
-def _ctype(code):
-    if code in _SCALAR:
-        return _SCALAR[code]
-    if code.startswith("char"):
-        return C.c_char * int(code[4:])
-    if code.startswith("type:"):
-        return struct(code[5:])
-    raise KeyError(code)
-
-
-def _field_ctype(f):
-    if f["alloc"]:
-        return FA
-    t = _ctype(f["type"])
-    if f["rank"] > 0:
-        t = t * int(np.prod(f["dims"]))
-    return t
-
-
 def meta():
-    global _meta
-    if _meta is None:
-        _meta = json.load(open(META_PATH))
-    return _meta
+    return REF.meta()
 
 
 def struct(cname):
-    """ctypes mirror of a translated derived type (fields in declaration order)."""
-    if cname not in _structs:
-        fields = [(f["cname"], _field_ctype(f)) for f in meta()["types"][cname]]
-        _structs[cname] = type(cname, (C.Structure,), {"_fields_": fields})
-    return _structs[cname]
+    return REF.struct(cname)
 
 
 def lib():
-    global _lib
-    if _lib is None:
-        if not available():
-            if not can_build():
-                raise RuntimeError("oracle/_ref/libbgc_ref.so is missing and the reference sources "
-                                   "are not available to rebuild it")
-            build()
-        _lib = C.CDLL(LIB_PATH)
-    return _lib
+    return REF.lib()
 
 
 def const(cname):
-    """value of a module-level named constant (e.g. 'bgc_parms__epsc')"""
-    f = getattr(lib(), "ref_const__" + cname)
-    f.restype = _ctype(meta()["consts"][cname])
-    return f()
+    return REF.const(cname)
 
 
 def var(cname):
-    """ctypes object aliasing a module variable OF THE CALLING THREAD"""
-    f = getattr(lib(), "ref_addr__" + cname)
-    f.restype = C.c_void_p
-    return _field_ctype(meta()["vars"][cname]).from_address(f())
+    return REF.var(cname)
 
 
 def call(cname, *args):
-    """Call a translated procedure.  Scalars may be given as Python numbers (wrapped, passed by
-    reference; the ctypes objects are returned so that intent(out) values can be read), derived
-    types as ctypes Structures / arrays of them."""
-    pm = meta()["procs"][cname]
-    fn = getattr(lib(), cname)
-    fn.restype = _ctype(pm["result"]) if pm["result"] else None
-    if len(args) != len(pm["args"]):
-        raise TypeError(f"{cname}: {len(args)} arguments for {len(pm['args'])} dummies")
-    boxed = []
-    for a, am in zip(args, pm["args"]):
-        if isinstance(a, (C.Structure, C.Array, C._SimpleCData)):
-            boxed.append(a)
-        else:
-            boxed.append(_ctype(am["type"])(a))
-    r = fn(*[C.byref(b) for b in boxed])
-    return r, boxed
+    return REF.call(cname, *args)
+
+
+def fill(cname, arrays, scalars=None):
+    return REF.fill(cname, arrays, scalars)
 
 
 def describe(arr):
@@ -139,31 +193,6 @@ def describe(arr):
     sh = list(arr.shape) + [1, 1, 1]
     d.n1, d.n2, d.n3 = sh[0], sh[1], sh[2]
     return d
-
-
-def fill(cname, arrays, scalars=None):
-    """Build a translated derived type whose allocatable components alias the numpy arrays in
-    `arrays` (component names compared case-insensitively) and whose scalar components come from
-    `scalars`.  Returns (struct, keepalive)."""
-    s = struct(cname)()
-    low = {k.lower(): v for k, v in arrays.items()}
-    sc = {k.lower(): v for k, v in (scalars or {}).items()}
-    keep = []
-    for f in meta()["types"][cname]:
-        n = f["name"]
-        if f["alloc"]:
-            if n in low and low[n] is not None:
-                a = low[n]
-                if f["type"].startswith("r8"):
-                    assert a.dtype == np.float64, n
-                elif f["type"] == "i4":
-                    assert a.dtype == np.int32, n
-                assert a.ndim == f["rank"], (n, a.shape, f["rank"])
-                setattr(s, f["cname"], describe(a))
-                keep.append(a)
-        elif n in sc:
-            setattr(s, f["cname"], sc[n])
-    return s, keep
 
 
 def _arrays_of(cols):
@@ -187,8 +216,9 @@ class RefParms:
     of the translated reference, with the host-chosen tracer slots of `parms` (an
     oracle.Parms) and the host-set T0_Kelvin_BGC (quirk Q7)."""
 
-    def __init__(self, parms=None, t0_kelvin=273.15):
-        m = meta()
+    def __init__(self, parms=None, t0_kelvin=273.15, L=None):
+        self.L = L = L or REF
+        m, struct, var, call = L.meta(), L.struct, L.var, L.call
         self.ind = struct("bgc_parms__bgc_indices_type")()
         self.autotrophs = (struct("bgc_parms__autotroph_type") * 4)()
         self._names = {}
@@ -236,7 +266,7 @@ class RefParms:
         """Copy the run-time tunables and the functional-group table of an oracle.Parms /
         host.Parms into the module variables of the translated reference (what a namelist read
         does upstream).  Compile-time constants (epsC ...) are not settable and are skipped."""
-        m = meta()
+        m, var = self.L.meta(), self.L.var
         for src, mod in ((parms.bgc, "bgc_parms"), (parms.dms, "dms_parms"), (parms.macros, "macros_parms")):
             for n, _ in src._fields_:
                 cn = f"{mod}__{n.lower()}"
@@ -261,6 +291,7 @@ class RefParms:
 
 def BGC_SourceSink(rp, cols, alt_co2_use_eco=True):
     arrs = _arrays_of(cols)
+    fill, call = rp.L.fill, rp.L.call
     cin, k1 = fill("bgc_parms__bgc_input_type", arrs)
     cfo, k2 = fill("bgc_parms__bgc_forcing_type", arrs, _scalars_of(cols))
     cout, k3 = fill("bgc_parms__bgc_output_type", arrs)
@@ -271,6 +302,7 @@ def BGC_SourceSink(rp, cols, alt_co2_use_eco=True):
 
 def BGC_SurfaceFluxes(rp, cols):
     arrs = _arrays_of(cols)
+    fill, call = rp.L.fill, rp.L.call
     cin, k1 = fill("bgc_parms__bgc_input_type", arrs)
     cfo, k2 = fill("bgc_parms__bgc_forcing_type", arrs, _scalars_of(cols))
     cfd, k3 = fill("bgc_parms__bgc_flux_diagnostics_type", arrs)
@@ -279,6 +311,7 @@ def BGC_SurfaceFluxes(rp, cols):
 
 def DMS_SourceSink(rp, cols):
     arrs = _arrays_of(cols)
+    fill, call = rp.L.fill, rp.L.call
     cin, k1 = fill("dms_parms__dms_input_type", arrs)
     cfo, k2 = fill("dms_parms__dms_forcing_type", arrs, _scalars_of(cols))
     cout, k3 = fill("dms_parms__dms_output_type", arrs)
@@ -289,6 +322,7 @@ def DMS_SourceSink(rp, cols):
 
 def DMS_SurfaceFluxes(rp, cols):
     arrs = _arrays_of(cols)
+    fill, call = rp.L.fill, rp.L.call
     cin, k1 = fill("dms_parms__dms_input_type", arrs)
     cfo, k2 = fill("dms_parms__dms_forcing_type", arrs, _scalars_of(cols))
     cfd, k3 = fill("dms_parms__dms_flux_diagnostics_type", arrs)
@@ -297,6 +331,7 @@ def DMS_SurfaceFluxes(rp, cols):
 
 def MACROS_SourceSink(rp, cols):
     arrs = _arrays_of(cols)
+    fill, call = rp.L.fill, rp.L.call
     cin, k1 = fill("macros_parms__macros_input_type", arrs)
     cout, k2 = fill("macros_parms__macros_output_type", arrs)
     cdg, k3 = fill("macros_parms__macros_diagnostics_type", arrs)

@@ -1,0 +1,100 @@
+/* mock_bgc_b200.c — a CPU stand-in for the handful of C-ABI entry points the Fortran shim binds
+ * (include/bgc_b200.h), backed by the CPU oracle.
+ *
+ * TEST INFRASTRUCTURE ONLY.  The product (ocean-bgc_b200/csrc/libbgc_b200.so) has no CPU path and
+ * fails loudly without a CUDA device; this file exists so that the MARSHALLING of the shim
+ * (ocean-bgc_b200/fortran/: which component goes to which struct member, in which order, with
+ * which extents and flags) can be exercised on a machine without a GPU
+ * (tests/test_fortran_shim.py).  On the GPU box the same shim is loaded against the real library.
+ * It also records what it was handed, so that the test can check the call sequence.
+ */
+#include <stdlib.h>
+#include <string.h>
+#include "bgc_b200.h"
+#include "bgc_oracle.h"
+
+struct bgc_ctx {
+  int device, nLevelsMax, nColumnsMax;
+  int have_bgc, have_dms, have_macros;
+  BgcParams p; BgcAutotroph a[4]; BgcIndices ind;
+  DmsParams dp; DmsIndices dind;
+  MacrosParams mp; MacrosIndices mind;
+};
+
+static char g_err[512] = "";
+static int g_live = 0, g_created = 0, g_calls = 0;
+
+const char *bgc_last_error(void) { return g_err; }
+int mock_live_contexts(void) { return g_live; }
+int mock_created_contexts(void) { return g_created; }
+int mock_compute_calls(void) { return g_calls; }
+
+static int fail(int code, const char *msg) { strncpy(g_err, msg, sizeof g_err - 1); return code; }
+
+int bgc_ctx_create(int device, int nLevelsMax, int nColumnsMax, bgc_ctx **out) {
+  if (!out || nLevelsMax < 1 || nColumnsMax < 1) return fail(BGC_ERR_ARG, "mock: bad ctx_create arguments");
+  bgc_ctx *c = calloc(1, sizeof *c);
+  c->device = device; c->nLevelsMax = nLevelsMax; c->nColumnsMax = nColumnsMax;
+  *out = c; g_live++; g_created++;
+  return BGC_OK;
+}
+int bgc_ctx_destroy(bgc_ctx *c) { if (!c) return fail(BGC_ERR_ARG, "mock: null ctx"); free(c); g_live--; return BGC_OK; }
+
+int bgc_set_params(bgc_ctx *c, const BgcParams *p, const BgcAutotroph a[4], const BgcIndices *ind) {
+  if (!c || !p || !a || !ind) return fail(BGC_ERR_ARG, "mock: null argument to bgc_set_params");
+  c->p = *p; memcpy(c->a, a, sizeof c->a); c->ind = *ind; c->have_bgc = 1; return BGC_OK;
+}
+int dms_set_params(bgc_ctx *c, const DmsParams *p, const DmsIndices *ind) {
+  if (!c || !p || !ind) return fail(BGC_ERR_ARG, "mock: null argument to dms_set_params");
+  c->dp = *p; c->dind = *ind; c->have_dms = 1; return BGC_OK;
+}
+int macros_set_params(bgc_ctx *c, const MacrosParams *p, const MacrosIndices *ind) {
+  if (!c || !p || !ind) return fail(BGC_ERR_ARG, "mock: null argument to macros_set_params");
+  c->mp = *p; c->mind = *ind; c->have_macros = 1; return BGC_OK;
+}
+
+static int check(bgc_ctx *c, int have, int nL, int nC, int n, int mem_space) {
+  if (!c) return fail(BGC_ERR_ARG, "mock: null ctx");
+  if (!have) return fail(BGC_ERR_PARAMS, "mock: *_set_params not called");
+  if (mem_space != BGC_MEM_HOST_FORTRAN) return fail(BGC_ERR_ARG, "mock: host layout only");
+  if (nL > c->nLevelsMax || nC > c->nColumnsMax || n > nC || n < 0)
+    return fail(BGC_ERR_ARG, "mock: block larger than the ctx");
+  g_calls++;
+  return BGC_OK;
+}
+
+int bgc_source_sink(bgc_ctx *c, const BgcInput *in, const BgcForcing *fo, BgcOutput *out, BgcDiagnostics *dg,
+                    int nL, int nC, int n, int alt, int mem_space) {
+  int rc = check(c, c ? c->have_bgc : 0, nL, nC, n, mem_space);
+  if (rc) return rc;
+  oracle_BGC_SourceSink(&c->p, c->a, &c->ind, in, fo, out, dg, nL, nC, n, alt, 1, NULL);
+  return BGC_OK;
+}
+int bgc_surface_fluxes(bgc_ctx *c, const BgcInput *in, BgcForcing *fo, BgcFluxDiagnostics *dg,
+                       int nL, int nC, int n, int mem_space) {
+  int rc = check(c, c ? c->have_bgc : 0, nL, nC, n, mem_space);
+  if (rc) return rc;
+  oracle_BGC_SurfaceFluxes(&c->p, &c->ind, in, fo, dg, nL, nC, n, 1);
+  return BGC_OK;
+}
+int dms_source_sink(bgc_ctx *c, const DmsInput *in, const DmsForcing *fo, DmsOutput *out, DmsDiagnostics *dg,
+                    int nL, int nC, int n, int mem_space) {
+  int rc = check(c, c ? c->have_dms : 0, nL, nC, n, mem_space);
+  if (rc) return rc;
+  oracle_DMS_SourceSink(&c->dp, &c->dind, in, fo, out, dg, nL, nC, n, 1);
+  return BGC_OK;
+}
+int dms_surface_fluxes(bgc_ctx *c, const DmsInput *in, DmsForcing *fo, DmsFluxDiagnostics *dg,
+                       int nL, int nC, int n, int mem_space) {
+  int rc = check(c, c ? c->have_dms : 0, nL, nC, n, mem_space);
+  if (rc) return rc;
+  oracle_DMS_SurfaceFluxes(&c->dp, &c->dind, in, fo, dg, nL, nC, n);
+  return BGC_OK;
+}
+int macros_source_sink(bgc_ctx *c, const MacrosInput *in, MacrosOutput *out, MacrosDiagnostics *dg,
+                       int nL, int nC, int n, int mem_space) {
+  int rc = check(c, c ? c->have_macros : 0, nL, nC, n, mem_space);
+  if (rc) return rc;
+  oracle_MACROS_SourceSink(&c->mp, &c->mind, in, out, dg, nL, nC, n, 1);
+  return BGC_OK;
+}

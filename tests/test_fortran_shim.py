@@ -1,0 +1,169 @@
+"""The drop-in Fortran shim (ocean-bgc_b200/fortran/: modules BGC_mod, DMS_mod, MACROS_mod with the
+reference's procedure names, argument lists and derived types, forwarding to the C ABI through
+ISO_C_BINDING) EXECUTED, not just written.
+
+The image has no Fortran compiler, so the shim is translated to C by oracle/f90c.py together with
+the reference's own unchanged BGC_parms / DMS_parms / MACROS_parms (the module set its Makefile
+compiles) -> oracle/_ref/libbgc_shim.so.  The caller side below does what MPAS does: it fills the
+reference's derived types (allocatable components, level index fastest), runs the reference's
+*_parms_init, the shim's *_init, and then calls BGC_SourceSink & co with the reference signatures.
+Underneath, the C-ABI symbols resolve to
+
+  * on CPU (this file's non-gpu tests): tests/mock_abi/mock_bgc_b200.c, a stand-in backed by the
+    oracle - the answers must equal the oracle's bit for bit, which checks every component ->
+    struct-member assignment, the extents, the flags, the parameter flattening and the ctx
+    life cycle of the shim;
+  * on the GPU box (`-m gpu`): the real libbgc_b200.so - the complete drop-in chain
+    reference-typed caller -> shim -> C ABI -> CUDA, compared with the translated reference.
+"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import parity
+
+pkg = parity.pkg
+abi = pkg.abi
+o = parity.oracle()
+sys.path.insert(0, os.path.join(parity.REPO, "oracle"))
+import ref_translated as rt   # noqa: E402  (test infrastructure only)
+
+SHIM = os.path.join(rt.REFDIR, "libbgc_shim.so")
+SHIM_META = os.path.join(rt.REFDIR, "shim_meta.json")
+MOCK = os.path.join(rt.REFDIR, "libmock_bgc_b200.so")
+REAL = os.path.join(parity.REPO, "ocean-bgc_b200", "csrc", "libbgc_b200.so")
+
+if not os.path.exists(SHIM) and rt.can_build():
+    rt.build()
+pytestmark = pytest.mark.skipif(not (os.path.exists(SHIM) and os.path.exists(SHIM_META)),
+                                reason="oracle/_ref/libbgc_shim.so not built (needs the reference sources once)")
+
+
+def _same(a, b, what):
+    if not np.array_equal(a, b, equal_nan=True):
+        raise AssertionError("%s differs: max |d| = %.3e" % (what, float(np.nanmax(np.abs(a - b)))))
+
+
+def run_through_shim(L, po, cols, dms, mac, passes=2):
+    """What an MPAS-like caller does, through the reference API names."""
+    rp = rt.RefParms(po, L=L)              # BGC_parms_init, BGC_init (shim), DMS_*, MACROS_*
+    for _ in range(passes):
+        rt.BGC_SourceSink(rp, cols, True)  # shim BGC_mod::BGC_SourceSink
+    rt.BGC_SurfaceFluxes(rp, cols)
+    rt.DMS_SourceSink(rp, dms)
+    rt.DMS_SurfaceFluxes(rp, dms)
+    rt.MACROS_SourceSink(rp, mac)
+    return rp
+
+
+def test_shim_marshalling_against_the_oracle():
+    L = rt.TLib(SHIM, SHIM_META, preload=[MOCK])
+    mock = C.CDLL(MOCK, mode=C.RTLD_GLOBAL)
+    po = o.Parms()
+    nL, nC, nCols = 24, 96, 90
+    cols, dms, mac = parity.make_bgc(nL, nC, po, ragged=True, nColumns=nCols, with_dms=True, with_macros=True)
+    for c in (cols, dms, mac):
+        parity.poison_outputs(c)
+    a, da, ma = cols.copy(), dms.copy(), mac.copy()
+    o.BGC_SourceSink(po, a, True); o.BGC_SourceSink(po, a, True); o.BGC_SurfaceFluxes(po, a)
+    o.DMS_SourceSink(po, da); o.DMS_SurfaceFluxes(po, da); o.MACROS_SourceSink(po, ma)
+    b, db, mb = cols.copy(), dms.copy(), mac.copy()
+    calls0 = mock.mock_compute_calls()
+    rp = run_through_shim(L, po, b, db, mb)
+    assert mock.mock_compute_calls() - calls0 == 6
+    _same(b.BGC_tendencies, a.BGC_tendencies, "BGC tendencies")
+    _same(b.PH_PREV_3D, a.PH_PREV_3D, "PH_PREV_3D")
+    _same(b.PH_PREV_ALT_CO2_3D, a.PH_PREV_ALT_CO2_3D, "PH_PREV_ALT_CO2_3D")
+    for n in a.diag:
+        _same(b.diag[n], a.diag[n], n)
+    for n in a.forcing:
+        _same(b.forcing[n], a.forcing[n], "forcing " + n)
+    for n in a.flux_diag:
+        _same(b.flux_diag[n], a.flux_diag[n], "flux diag " + n)
+    _same(db.DMS_tendencies, da.DMS_tendencies, "DMS tendencies")
+    for n in da.diag:
+        _same(db.diag[n], da.diag[n], "DMS " + n)
+    for n in da.flux_diag:
+        _same(db.flux_diag[n], da.flux_diag[n], "DMS flux diag " + n)
+    _same(db.forcing["netFlux"], da.forcing["netFlux"], "DMS netFlux")
+    _same(mb.MACROS_tendencies, ma.MACROS_tendencies, "MACROS tendencies")
+    for n in ma.diag:
+        _same(mb.diag[n], ma.diag[n], "MACROS " + n)
+    # BGC_init of the shim: same index wiring and names as the reference's
+    ref = rt.RefParms(po)
+    for i in range(4):
+        for f in ("chl_ind", "c_ind", "fe_ind", "si_ind", "caco3_ind"):
+            assert getattr(rp.autotrophs[i], f) == getattr(ref.autotrophs[i], f), (i, f)
+    for which, n in (("ind", 30), ("dms_ind", 14), ("macros_ind", 8)):
+        for i in range(n):
+            assert rp.name(which, "short_name", i) == ref.name(which, "short_name", i), (which, i)
+            assert rp.name(which, "units", i) == ref.name(which, "units", i), (which, i)
+
+
+def test_shim_context_life_cycle_and_parameter_changes():
+    """One ctx per (thread of the) host, re-created only when a larger block shows up; parameter
+    changes made through the reference's module variables reach the library on the next call."""
+    L = rt.TLib(SHIM, SHIM_META, preload=[MOCK])
+    mock = C.CDLL(MOCK, mode=C.RTLD_GLOBAL)
+    po = o.Parms()
+    rp = rt.RefParms(po, L=L)
+    L.call("bgc_b200_runtime__bgc_b200_finalize")      # whatever an earlier test left behind
+    assert mock.mock_live_contexts() == 0
+    created0 = mock.mock_created_contexts()
+    small, _, _ = parity.make_bgc(10, 16, po)
+    rt.BGC_SourceSink(rp, small, True)
+    rt.BGC_SourceSink(rp, small, True)
+    n1 = mock.mock_created_contexts() - created0
+    big, _, _ = parity.make_bgc(20, 64, po)
+    rt.BGC_SourceSink(rp, big, True)
+    n2 = mock.mock_created_contexts() - created0
+    rt.BGC_SourceSink(rp, small, True)           # fits the larger ctx: no new one
+    assert (n1, n2, mock.mock_created_contexts() - created0) == (1, 2, 2)
+    assert mock.mock_live_contexts() == 1
+    assert L.var("bgc_b200_runtime__ctx_levels").value == 20
+    assert L.var("bgc_b200_runtime__ctx_columns").value == 64
+    # a namelist-style change of a module variable
+    po2 = o.Parms()
+    po2.bgc.parm_labile_ratio = 0.6
+    po2.bgc.parm_o2_min = 7.0
+    rp.sync_from(po2)
+    a, b = big.copy(), big.copy()
+    o.BGC_SourceSink(po2, a, True)
+    rt.BGC_SourceSink(rp, b, True)
+    _same(b.BGC_tendencies, a.BGC_tendencies, "tendencies after a parameter change")
+    L.call("bgc_b200_runtime__bgc_b200_finalize")
+    assert mock.mock_live_contexts() == 0
+
+
+@pytest.mark.gpu
+def test_shim_drop_in_chain_on_the_gpu():
+    """reference-typed caller -> shim -> C ABI -> CUDA, against the translated reference."""
+    if "libmock_bgc_b200" in open("/proc/self/maps").read():
+        pytest.skip("the CPU mock of the C ABI is loaded in this process (run with -m gpu)")
+    L = rt.TLib(SHIM, SHIM_META, preload=[REAL])
+    po = pkg.host.Parms()
+    nL, nC, nCols = 40, 258, 250
+    cols, dms, mac = parity.make_bgc(nL, nC, po, ragged=True, nColumns=nCols, with_dms=True, with_macros=True)
+    for c in (cols, dms, mac):
+        parity.poison_outputs(c)
+    rr = rt.RefParms(po)
+    a, da, ma = cols.copy(), dms.copy(), mac.copy()
+    rt.BGC_SourceSink(rr, a, True)
+    b, db, mb = cols.copy(), dms.copy(), mac.copy()
+    rp = rt.RefParms(po, L=L)
+    rt.BGC_SourceSink(rp, b, True)
+    parity.compare_bgc_source_sink(a, b)              # cold pass
+    rt.BGC_SourceSink(rr, a, True); rt.BGC_SurfaceFluxes(rr, a)
+    rt.BGC_SourceSink(rp, b, True); rt.BGC_SurfaceFluxes(rp, b)
+    parity.compare_bgc_source_sink(a, b)              # warm pass
+    cm = np.arange(nC) < nCols
+    assert parity.nerr(b.forcing["netFlux"][cm], a.forcing["netFlux"][cm]) <= parity.TOL_SOLVER
+    rt.DMS_SourceSink(rr, da); rt.DMS_SurfaceFluxes(rr, da); rt.MACROS_SourceSink(rr, ma)
+    rt.DMS_SourceSink(rp, db); rt.DMS_SurfaceFluxes(rp, db); rt.MACROS_SourceSink(rp, mb)
+    assert parity.nerr(db.DMS_tendencies, da.DMS_tendencies) <= parity.TOL_TEND
+    assert parity.nerr(mb.MACROS_tendencies, ma.MACROS_tendencies) <= parity.TOL_TEND
+    assert parity.nerr(db.forcing["netFlux"][cm], da.forcing["netFlux"][cm]) <= parity.TOL_TEND
+    L.call("bgc_b200_runtime__bgc_b200_finalize")

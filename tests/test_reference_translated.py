@@ -443,29 +443,14 @@ def test_blocks_without_active_cells(po, rp):
 def test_no_result_depends_on_unset_memory(po):
     """libbgc_ref_poison.so fills every ALLOCATE with NaN bit patterns (gfortran leaves garbage):
     the outputs must not change, i.e. the reference reads no local array element it never set."""
-    import ctypes as C
     path = os.path.join(rt.REFDIR, "libbgc_ref_poison.so")
     if not os.path.exists(path):
         pytest.skip("poisoned build not present")
     cols, _, _ = parity.make_bgc(24, 96, po, ragged=True, nColumns=90)
-    a = cols.copy()
-    res = {}
-
-    def run():
-        keep = rt._lib
-        try:
-            rt._lib = C.CDLL(path)
-            rpp = rt.RefParms(po)
-            b = cols.copy()
-            rt.BGC_SourceSink(rpp, b, True)
-            res["b"] = b
-        finally:
-            rt._lib = keep
-
-    t = threading.Thread(target=run)
-    t.start(); t.join()
+    a, b = cols.copy(), cols.copy()
     rt.BGC_SourceSink(rt.RefParms(po), a, True)
-    same_bgc(res["b"], a, "poisoned allocations")
+    rt.BGC_SourceSink(rt.RefParms(po, L=rt.TLib(path, rt.META_PATH)), b, True)
+    same_bgc(b, a, "poisoned allocations")
 
 
 def test_thread_local_module_state(po):
