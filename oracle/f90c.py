@@ -1576,13 +1576,18 @@ class Translator:
                 break
         if eq is None:
             self.err("unrecognised statement")
-        lhs = Parser(toks[:eq], p.where).expr()
+        lp = Parser(toks[:eq], p.where)
+        lhs = lp.expr()
+        if not lp.at_end():
+            self.err("unsupported statement")
         rp = Parser(toks[eq + 1:], p.where)
         rhs = rp.expr()
         if not rp.at_end():
             self.err("trailing tokens after expression")
         if not isinstance(lhs, Ref):
             self.err("bad assignment target")
+        if self.lookup(lhs.parts[0][0]) is None:
+            self.err(f"assignment to an undeclared name {lhs.parts[0][0]}")
         n = self.extent_of(lhs)
         if n is not None:
             iv = self.newtmp("_i")
