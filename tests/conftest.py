@@ -24,3 +24,10 @@ def built():
     if not all(os.path.exists(p) for p in need):
         ge.build()
     return ge.load_package()
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _libraries_present(built):
+    """Every test file may run on its own: build the in-tree libraries first when they are missing
+    (a no-op on the GPU box, where the prebuilt files travel with the snapshot)."""
+    return built
