@@ -497,6 +497,18 @@ def main():
         except Exception:
             traffic = None
     kernel_ms = {k: (v[0] / max(1, v[1])) for k, v in ktimes.items() if v[1]}
+    # what a compute-free kernel with the sweep's read:write mix and access pattern sustains on
+    # this GPU (committed microbenchmark, not measured in this run): context for `frac`, whose
+    # denominator stays the 1:1 copy bandwidth of MEASURED_PEAKS.json
+    stream_ceiling = None
+    try:
+        sc = json.load(open(os.path.join(REPO, "profiles", "stream_ceiling.json")))
+        stream_ceiling = {"same_mix_same_occupancy_GBps": sc["same_occupancy_GBps"],
+                          "same_mix_best_GBps": sc["best_GBps"],
+                          "frac_of_same_occupancy": achieved / sc["same_occupancy_GBps"],
+                          "frac_of_best": achieved / sc["best_GBps"], "source": sc["source"]}
+    except Exception:
+        stream_ceiling = None
     roofline = {"bound": "hbm", "kernel": "eco_columns_kernel", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "algorithmic_bytes_per_cell": B_ECO, "cells_per_launch": cells,
@@ -505,6 +517,7 @@ def main():
                          "achieved": cells * B_API / (ms_step * 1e-3) / 1e9,
                          "frac": cells * B_API / (ms_step * 1e-3) / 1e9 / peak},
                 "kernel_ms_per_launch": kernel_ms, "ncu_counters": ncu_counters,
+                "stream_ceiling": stream_ceiling,
                 "kernel_ms_note": "each kernel timed alone (carbonate kernel serialised behind the sweep for this "
                                   "pass); in the timed steps the carbonate kernel overlaps the sweep's last wave, so "
                                   "ms_per_step is less than the sum"}

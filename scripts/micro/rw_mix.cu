@@ -1,0 +1,169 @@
+// HBM bandwidth for the read:write mix and the access pattern of the column sweep
+// (eco_columns_kernel): thread = column, levels in order, NR input arrays read and NW output
+// arrays written per level, each array a (level, column) slab set with the column index fastest.
+// The sweep moves 37 reads + 146 writes per cell (1464 B) and the whole BGC_SourceSink 37 + 162;
+// MEASURED_PEAKS.json's 6548 GB/s is a 1:1 copy, so this microbenchmark answers: what does the
+// memory system sustain for an 80 % write stream spread over ~180 concurrently open arrays, and
+// how much of that needs more than the sweep's 8 warps per SM?
+//   nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o rw_mix rw_mix.cu && ./rw_mix
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include <cuda_runtime.h>
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", \
+  cudaGetErrorString(e_), __FILE__, __LINE__); exit(1); } } while (0)
+
+struct Ptrs { const double *in; double *out; };
+
+// flat grid-stride streams (the shape MEASURED_PEAKS was taken with)
+__global__ void flat_copy(const double2 *__restrict__ a, double2 *__restrict__ b, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) b[i] = a[i];
+}
+__global__ void flat_write(double2 *__restrict__ b, size_t n, double v) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    b[i] = make_double2(v, v);
+}
+__global__ void flat_read(const double2 *__restrict__ a, double *sink, size_t n) {
+  double s = 0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    double2 x = a[i]; s += x.x + x.y; }
+  if (s == 1.2345e300) *sink = s;
+}
+
+// the sweep's pattern: one thread per column, NR + NW arrays touched at every level
+template <int NR, int NW>
+__global__ void column_streams(Ptrs p, int nL, int nC, double *sink) {
+  extern __shared__ double pad[];
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= nC) return;
+  const size_t slab = (size_t)nL * nC;
+  double s = 0;
+  for (int k = 0; k < nL; ++k) {
+    const size_t e = (size_t)k * nC + col;
+#pragma unroll
+    for (int r = 0; r < NR; ++r) s += p.in[r * slab + e];
+#pragma unroll
+    for (int w = 0; w < NW; ++w) p.out[w * slab + e] = s + w;
+  }
+  if (s == 1.2345e300) *sink = s + pad[0];
+}
+
+// Same traffic, three layouts, occupancy forced by __launch_bounds__ (registers capped):
+//   LAYOUT 0: the C ABI's SoA   [array][level][column]              (2 KB runs, 183 streams)
+//   LAYOUT 1: block-tiled SoA   [array][block][level][256 columns]  (consecutive levels adjacent)
+//   LAYOUT 2: AoSoA             [block][level][array][256 columns]  (one flat stream per block)
+template <int NR, int NW, int MINB, int LAYOUT>
+__global__ void __launch_bounds__(256, MINB) column_layouts(Ptrs p, int nL, int nC, double *sink) {
+  const int tid = threadIdx.x, blk = blockIdx.x;
+  const int col = blk * 256 + tid;
+  if (col >= nC) return;
+  const size_t slab = (size_t)nL * nC;
+  const size_t nB = (nC + 255) / 256;
+  double s = 0;
+  for (int k = 0; k < nL; ++k) {
+    size_t e, stride;
+    if (LAYOUT == 0) { e = (size_t)k * nC + col; stride = slab; }
+    else if (LAYOUT == 1) { e = ((size_t)blk * nL + k) * 256 + tid; stride = nB * nL * 256; }
+    else { e = 0; stride = 256; }
+    const size_t rbase = LAYOUT == 2 ? (((size_t)blk * nL + k) * NR) * 256 + tid : e;
+    const size_t wbase = LAYOUT == 2 ? (((size_t)blk * nL + k) * NW) * 256 + tid : e;
+#pragma unroll 8
+    for (int r = 0; r < NR; ++r) s += p.in[rbase + r * stride];
+#pragma unroll 8
+    for (int w = 0; w < NW; ++w) p.out[wbase + w * stride] = s + w;
+  }
+  if (s == 1.2345e300) *sink = s;
+}
+
+template <typename F>
+static float time_ms(F launch, int reps = 5) {
+  cudaEvent_t a, b; CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+  launch(); CK(cudaDeviceSynchronize());
+  float best = 1e30f;
+  for (int i = 0; i < reps; ++i) {
+    CK(cudaEventRecord(a)); launch(); CK(cudaEventRecord(b)); CK(cudaEventSynchronize(b));
+    float ms; CK(cudaEventElapsedTime(&ms, a, b)); if (ms < best) best = ms;
+  }
+  CK(cudaGetLastError());
+  return best;
+}
+
+template <int NR, int NW>
+static void run_columns(const double *in, double *out, double *sink, int nL, int nC, int block, int smem_kb,
+                        const char *what) {
+  auto kern = column_streams<NR, NW>;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_kb * 1024));
+  int perSM = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, block, smem_kb * 1024));
+  Ptrs p{in, out};
+  const int grid = (nC + block - 1) / block;
+  float ms = time_ms([&] { kern<<<grid, block, smem_kb * 1024>>>(p, nL, nC, sink); });
+  const double bytes = (double)(NR + NW) * 8.0 * nL * nC;
+  printf("columns %3dR+%3dW block %4d, %2d blocks/SM (%2d warps/SM): %7.3f ms  %7.1f GB/s   %s\n", NR, NW, block, perSM,
+         perSM * block / 32, ms, bytes / ms * 1e-6, what);
+}
+
+template <int NR, int NW, int MINB, int LAYOUT>
+static void run_layout(const double *in, double *out, double *sink, int nL, int nC, const char *what) {
+  auto kern = column_layouts<NR, NW, MINB, LAYOUT>;
+  // occupancy is pinned by a dynamic shared-memory reservation (the kernels need few registers)
+  const int smem = (MINB == 1 ? 200 : MINB == 2 ? 100 : MINB == 4 ? 50 : 0) * 1024;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  int perSM = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, 256, smem));
+  Ptrs p{in, out};
+  const int grid = (nC + 255) / 256;
+  float ms = time_ms([&] { kern<<<grid, 256, smem>>>(p, nL, nC, sink); });
+  const double bytes = (double)(NR + NW) * 8.0 * nL * nC;
+  printf("layout %d %3dR+%3dW, %2d blocks/SM (%2d warps/SM): %7.3f ms  %7.1f GB/s   %s\n", LAYOUT, NR, NW, perSM,
+         perSM * 8, ms, bytes / ms * 1e-6, what);
+}
+
+int main() {
+  const int nL = 60, nC = 235160;              // EC60to30
+  const size_t cells = (size_t)nL * nC;
+  const int NRMAX = 37, NWMAX = 162;
+  double *in, *out, *sink;
+  CK(cudaMalloc(&in, NRMAX * cells * 8)); CK(cudaMalloc(&out, NWMAX * cells * 8)); CK(cudaMalloc(&sink, 8));
+  CK(cudaMemset(in, 0, NRMAX * cells * 8));
+  const size_t n2 = (size_t)16 * cells / 2;    // 16 slabs = 1.8 GB per stream (>> 126 MB L2)
+  int sms = 0; CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
+  float ms;
+  ms = time_ms([&] { flat_copy<<<sms * 16, 512>>>((const double2 *)in, (double2 *)out, n2); });
+  printf("flat copy 1R+1W : %7.3f ms  %7.1f GB/s\n", ms, 2.0 * n2 * 16 / ms * 1e-6);
+  ms = time_ms([&] { flat_write<<<sms * 16, 512>>>((double2 *)out, n2, 1.0); });
+  printf("flat write      : %7.3f ms  %7.1f GB/s\n", ms, 1.0 * n2 * 16 / ms * 1e-6);
+  ms = time_ms([&] { flat_read<<<sms * 16, 512>>>((const double2 *)in, sink, n2); });
+  printf("flat read       : %7.3f ms  %7.1f GB/s\n", ms, 1.0 * n2 * 16 / ms * 1e-6);
+  ms = time_ms([&] { CK(cudaMemsetAsync(out, 0, n2 * 16)); });
+  printf("cudaMemset      : %7.3f ms  %7.1f GB/s\n", ms, 1.0 * n2 * 16 / ms * 1e-6);
+
+  // the sweep's mix at the sweep's occupancy (one 256-thread block per SM) and above it
+  run_columns<37, 146>(in, out, sink, nL, nC, 256, 200, "sweep mix, sweep occupancy");
+  run_columns<37, 146>(in, out, sink, nL, nC, 256, 100, "sweep mix, 2 blocks/SM");
+  run_columns<37, 146>(in, out, sink, nL, nC, 256, 48, "sweep mix, 4 blocks/SM");
+  run_columns<37, 146>(in, out, sink, nL, nC, 256, 0, "sweep mix, full occupancy");
+  run_columns<37, 146>(in, out, sink, nL, nC, 128, 0, "sweep mix, 128-thread blocks");
+  run_columns<37, 162>(in, out, sink, nL, nC, 256, 0, "BGC_SourceSink mix");
+  run_columns<13, 41>(in, out, sink, nL, nC, 256, 0, "DMS mix");
+  run_columns<8, 14>(in, out, sink, nL, nC, 256, 0, "MACROS mix");
+  run_columns<1, 1>(in, out, sink, nL, nC, 256, 0, "copy, column pattern");
+  run_columns<0, 16>(in, out, sink, nL, nC, 256, 0, "16 write streams");
+  run_columns<0, 146>(in, out, sink, nL, nC, 256, 0, "146 write streams");
+  run_columns<37, 0>(in, out, sink, nL, nC, 256, 0, "37 read streams");
+
+  // occupancy and layout: tiles need whole blocks, so use a column count that is a multiple of 256
+  const int nCt = 235008;
+  run_layout<37, 146, 1, 0>(in, out, sink, nL, nCt, "SoA, 1 block/SM");
+  run_layout<37, 146, 2, 0>(in, out, sink, nL, nCt, "SoA, 2 blocks/SM");
+  run_layout<37, 146, 4, 0>(in, out, sink, nL, nCt, "SoA, 4 blocks/SM");
+  run_layout<37, 146, 8, 0>(in, out, sink, nL, nCt, "SoA, 8 blocks/SM");
+  run_layout<37, 146, 1, 1>(in, out, sink, nL, nCt, "block-tiled SoA, 1 block/SM");
+  run_layout<37, 146, 4, 1>(in, out, sink, nL, nCt, "block-tiled SoA, 4 blocks/SM");
+  run_layout<37, 146, 1, 2>(in, out, sink, nL, nCt, "AoSoA, 1 block/SM");
+  run_layout<37, 146, 2, 2>(in, out, sink, nL, nCt, "AoSoA, 2 blocks/SM");
+  run_layout<37, 146, 4, 2>(in, out, sink, nL, nCt, "AoSoA, 4 blocks/SM");
+  run_layout<37, 146, 8, 2>(in, out, sink, nL, nCt, "AoSoA, 8 blocks/SM");
+  return 0;
+}
