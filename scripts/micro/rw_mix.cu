@@ -76,6 +76,69 @@ __global__ void __launch_bounds__(256, MINB) column_layouts(Ptrs p, int nL, int 
   if (s == 1.2345e300) *sink = s;
 }
 
+// ---- how the stores are issued (write-only, the sweep's 146 output streams, SoA layout) ----
+//   MODE 0: one 8-byte st.global per thread and array (what the sweep does)
+//   MODE 1: the same with the streaming hint (st.global.cs)
+//   MODE 2: a thread owns two adjacent columns: 16-byte stores, half the store instructions
+//   MODE 3: values staged in shared memory, one elected thread hands 2-KB runs to the TMA unit
+//           (cp.async.bulk shared -> global), double-buffered in groups of 8 arrays
+__device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+template <int NW, int MODE>
+__global__ void __launch_bounds__(256, 1) store_paths(double *out, int nL, int nC, double seed) {
+  extern __shared__ __align__(128) double stage[];       // MODE 3: 2 x 8 x 256 doubles
+  const int tid = threadIdx.x;
+  const size_t slab = (size_t)nL * nC;
+  if (MODE == 2) {
+    const int col = (blockIdx.x * 256 + tid) * 2;
+    if (col >= nC) return;
+    for (int k = 0; k < nL; ++k) {
+      const size_t e = (size_t)k * nC + col;
+#pragma unroll 8
+      for (int w = 0; w < NW; ++w) *reinterpret_cast<double2 *>(out + w * slab + e) = make_double2(seed + w, seed - w);
+    }
+    return;
+  }
+  const int col = blockIdx.x * 256 + tid;
+  if (MODE != 3) {
+    if (col >= nC) return;
+    for (int k = 0; k < nL; ++k) {
+      const size_t e = (size_t)k * nC + col;
+#pragma unroll 8
+      for (int w = 0; w < NW; ++w) {
+        if (MODE == 1) __stcs(out + w * slab + e, seed + w);
+        else out[w * slab + e] = seed + w;
+      }
+    }
+    return;
+  }
+  // MODE 3 (whole blocks only: nC is a multiple of 256)
+  constexpr int G = 8;
+  int phase = 0;
+  for (int k = 0; k < nL; ++k) {
+    const size_t e0 = (size_t)k * nC + (size_t)blockIdx.x * 256;
+    for (int w0 = 0; w0 < NW; w0 += G, phase ^= 1) {
+      double *st = stage + phase * G * 256;
+      // the bulk copies that read this half two rounds ago must have finished reading it
+      if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+      __syncthreads();
+#pragma unroll
+      for (int g = 0; g < G; ++g) if (w0 + g < NW) st[g * 256 + tid] = seed + (w0 + g);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncthreads();
+      if (tid == 0) {
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+          if (w0 + g < NW)
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::
+                         "l"(out + (size_t)(w0 + g) * slab + e0), "r"(smem_addr(st + g * 256)), "n"(2048) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    }
+  }
+  if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 template <typename F>
 static float time_ms(F launch, int reps = 5) {
   cudaEvent_t a, b; CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
@@ -120,6 +183,18 @@ static void run_layout(const double *in, double *out, double *sink, int nL, int 
          perSM * 8, ms, bytes / ms * 1e-6, what);
 }
 
+template <int NW, int MODE>
+static void run_stores(double *out, int nL, int nC, const char *what) {
+  auto kern = store_paths<NW, MODE>;
+  const int smem = 200 * 1024;               // one block per SM, as the sweep
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int cols_per_block = MODE == 2 ? 512 : 256;
+  const int grid = (nC + cols_per_block - 1) / cols_per_block;
+  float ms = time_ms([&] { kern<<<grid, 256, smem>>>(out, nL, nC, 1.0); });
+  printf("stores mode %d, %3d write streams, 1 block/SM: %7.3f ms  %7.1f GB/s   %s\n", MODE, NW, ms,
+         (double)NW * 8.0 * nL * nC / ms * 1e-6, what);
+}
+
 int main() {
   const int nL = 60, nC = 235160;              // EC60to30
   const size_t cells = (size_t)nL * nC;
@@ -139,6 +214,14 @@ int main() {
   ms = time_ms([&] { CK(cudaMemsetAsync(out, 0, n2 * 16)); });
   printf("cudaMemset      : %7.3f ms  %7.1f GB/s\n", ms, 1.0 * n2 * 16 / ms * 1e-6);
 
+  const int nCt = 235008;                    // whole 256-column blocks for the tiled / bulk variants
+  if (getenv("RW_MIX_STORES") && !getenv("RW_MIX_ALL")) {
+    run_stores<146, 0>(out, nL, nCt, "st.global, 8 B per thread");
+    run_stores<146, 1>(out, nL, nCt, "st.global.cs");
+    run_stores<146, 2>(out, nL, nCt, "16-byte stores, two columns per thread");
+    run_stores<146, 3>(out, nL, nCt, "cp.async.bulk shared -> global (TMA), 2-KB runs");
+    return 0;
+  }
   // the sweep's mix at the sweep's occupancy (one 256-thread block per SM) and above it
   run_columns<37, 146>(in, out, sink, nL, nC, 256, 200, "sweep mix, sweep occupancy");
   run_columns<37, 146>(in, out, sink, nL, nC, 256, 100, "sweep mix, 2 blocks/SM");
@@ -153,8 +236,7 @@ int main() {
   run_columns<0, 146>(in, out, sink, nL, nC, 256, 0, "146 write streams");
   run_columns<37, 0>(in, out, sink, nL, nC, 256, 0, "37 read streams");
 
-  // occupancy and layout: tiles need whole blocks, so use a column count that is a multiple of 256
-  const int nCt = 235008;
+  // occupancy and layout: tiles need whole blocks (nCt is a multiple of 256)
   run_layout<37, 146, 1, 0>(in, out, sink, nL, nCt, "SoA, 1 block/SM");
   run_layout<37, 146, 2, 0>(in, out, sink, nL, nCt, "SoA, 2 blocks/SM");
   run_layout<37, 146, 4, 0>(in, out, sink, nL, nCt, "SoA, 4 blocks/SM");
@@ -165,5 +247,12 @@ int main() {
   run_layout<37, 146, 2, 2>(in, out, sink, nL, nCt, "AoSoA, 2 blocks/SM");
   run_layout<37, 146, 4, 2>(in, out, sink, nL, nCt, "AoSoA, 4 blocks/SM");
   run_layout<37, 146, 8, 2>(in, out, sink, nL, nCt, "AoSoA, 8 blocks/SM");
+
+  if (getenv("RW_MIX_STORES")) {
+    run_stores<146, 0>(out, nL, nCt, "st.global, 8 B per thread");
+    run_stores<146, 1>(out, nL, nCt, "st.global.cs");
+    run_stores<146, 2>(out, nL, nCt, "16-byte stores, two columns per thread");
+    run_stores<146, 3>(out, nL, nCt, "cp.async.bulk shared -> global (TMA), 2-KB runs");
+  }
   return 0;
 }
