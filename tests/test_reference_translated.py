@@ -439,6 +439,31 @@ def test_blocks_without_active_cells(po, rp):
         assert all(np.all(x == 7.25) for x in db.diag.values())
 
 
+def test_the_comparison_has_teeth(po, rp):
+    """The bit-exact comparison must notice a restatement that reads the source differently.  Two
+    plausible misreadings, both produced with the oracle's own switches / inputs: (1) the
+    single-precision literals of BGC_parms.F90:480-482 taken as doubles (what -fdefault-real-8
+    would give, quirk Q6): epsTinv moves light_lim at the 1e-10 level; (2) T0_Kelvin_BGC left at 0
+    instead of the host-set 273.15 (quirk Q7): it does not cancel in Tfunc in floating point."""
+    cols, _, _ = parity.make_bgc(24, 64, po, ragged=True)
+    ref = cols.copy()
+    rt.BGC_SourceSink(rp, ref, True)
+    a = cols.copy()
+    o.BGC_SourceSink(po, a, True)
+    assert np.array_equal(a.BGC_tendencies, ref.BGC_tendencies)
+    p8 = o.Parms(default_real_8=True)
+    b = cols.copy()
+    o.BGC_SourceSink(p8, b, True)
+    assert not np.array_equal(b.BGC_tendencies, ref.BGC_tendencies)
+    d = np.abs(b.BGC_tendencies - ref.BGC_tendencies).max() / np.abs(ref.BGC_tendencies).max()
+    assert 0 < d < 1e-6          # a last-digits effect: exactly what only a bit-exact check sees
+    p0 = o.Parms()
+    p0.bgc.T0_Kelvin_BGC = 0.0
+    c = cols.copy()
+    o.BGC_SourceSink(p0, c, True)
+    assert not np.array_equal(c.BGC_tendencies, ref.BGC_tendencies)
+
+
 # ------------------------------------------------------------------ properties of the reference itself
 def test_no_result_depends_on_unset_memory(po):
     """libbgc_ref_poison.so fills every ALLOCATE with NaN bit patterns (gfortran leaves garbage):
