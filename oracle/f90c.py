@@ -494,6 +494,17 @@ static inline void f_assign(char *d, int dn, fstr_t v) {
 static inline long long f_ipow(long long b, long long e) {
   long long r = 1; if (e < 0) return (b == 1) ? 1 : (b == -1 ? ((e & 1) ? -1 : 1) : 0);
   while (e) { if (e & 1) r *= b; b *= b; e >>= 1; } return r; }
+/* -DREF_PROFILE: inclusive cycles (rdtsc) and call counts per procedure, per thread */
+#ifdef REF_PROFILE
+#include <x86intrin.h>
+#define REF_PROF_MAX 256
+REF_TLS unsigned long long ref_prof_cyc[REF_PROF_MAX], ref_prof_calls[REF_PROF_MAX];
+#define PROF_ENTER(id) const unsigned long long _pt0 = __rdtsc(); ref_prof_calls[id]++;
+#define PROF_EXIT(id) ref_prof_cyc[id] += __rdtsc() - _pt0;
+#else
+#define PROF_ENTER(id)
+#define PROF_EXIT(id)
+#endif
 #ifdef REF_POISON
 static void *f_alloc(size_t nbytes) { void *p = malloc(nbytes ? nbytes : 1); memset(p, 0xFF, nbytes); return p; }
 #else
@@ -1697,6 +1708,9 @@ class Translator:
         self.w(f"/* {pr.line.file}:{pr.line.no} {pr.kind} {pr.name} */")
         self.w(("auto " if nested else "") + self.proto(pr) + " {")
         self.ind = base_ind + 1
+        pid = len(self.prof_names)
+        self.prof_names.append(pr.cname)
+        self.w(f"PROF_ENTER({pid})")
         allocs = []
         for s in pr.syms.values():
             if s.dummy:
@@ -1733,6 +1747,7 @@ class Translator:
             self.w(f"{retlabel}: ;")
         for s in allocs:       # gfortran frees allocatable locals on exit
             self.w(f"if ({s.cname}.p) free({s.cname}.p);")
+        self.w(f"PROF_EXIT({pid})")
         if pr.kind == "function":
             self.w(f"return {pr.syms[pr.result].cname};")
         self.ind = base_ind
@@ -1781,10 +1796,21 @@ class Translator:
             for pr in m.procs.values():
                 self.scope_mod, self.scope_proc = m, pr
                 self.out.append(("extern " if pr.external else "") + self.proto(pr) + ";")
+        self.prof_names = []
         for m in self.order:
             for pr in m.procs.values():
                 if not pr.external:
                     self.emit_proc(pr)
+        names = ", ".join(f'"{n}"' for n in self.prof_names)
+        self.out.append("#ifdef REF_PROFILE")
+        self.out.append(f"static const char *ref_prof_names[] = {{{names}}};")
+        self.out.append(f"int ref_prof_count(void) {{ return {len(self.prof_names)}; }}")
+        self.out.append("const char *ref_prof_name(int i) { return ref_prof_names[i]; }")
+        self.out.append("unsigned long long ref_prof_cycles(int i) { return ref_prof_cyc[i]; }")
+        self.out.append("unsigned long long ref_prof_ncalls(int i) { return ref_prof_calls[i]; }")
+        self.out.append("void ref_prof_reset(void) { memset(ref_prof_cyc, 0, sizeof ref_prof_cyc); "
+                        "memset(ref_prof_calls, 0, sizeof ref_prof_calls); }")
+        self.out.append("#endif")
         return "\n".join(self.out) + "\n"
 
     def meta(self):
