@@ -446,7 +446,7 @@ class Proc:
     def __init__(self, name, kind, args, result, module, line):
         self.name, self.kind, self.args, self.result, self.module, self.line = \
             name, kind, args, result, module, line
-        self.syms, self.body, self.decl_lines = {}, [], []
+        self.syms, self.body = {}, []
         self.cname = f"{module.name}__{name}"
         self.rtype = None
         self.parent = None       # host procedure of an internal procedure
@@ -458,7 +458,6 @@ class Proc:
 class Module:
     def __init__(self, name):
         self.name, self.uses, self.syms, self.types, self.procs = name, [], {}, {}, {}
-        self.decl_lines = []
         self.default_private = False
 
 

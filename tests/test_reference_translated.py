@@ -11,7 +11,6 @@ The library is built wherever the reference sources exist and travels with the s
 otherwise; with neither, the tests are skipped (and the committed golden vectors, which were
 produced by this library, still pin the oracle: tests/test_golden.py).
 """
-import math
 import os
 import sys
 import threading
