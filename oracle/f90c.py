@@ -15,10 +15,21 @@ middle/back end that `gfortran -O2` uses (`gcc -O2 -ffp-contract=off -fno-math-e
 Supported subset = what the reference uses, nothing more: modules, `use`, named constants,
 derived types with scalar / fixed-shape / allocatable components, module variables (emitted
 thread-local: the reference keeps solver state in module SAVE variables), subroutines and
-functions with by-reference arguments, `if / else if / else`, counted and endless `do`,
-`exit`, `cycle`, `return`, `select case` on integers, `allocate / deallocate`, whole-array and
-`(:)`-section assignments, `sum`, `merge`, `max`, `min`, `size`, array constructors, character
-assignment with `trim` and `//`.  Anything else stops the translation with the file and line.
+functions with by-reference arguments (positional and keyword), `if / else if / else`, counted,
+endless and `while` loops, construct names with `exit` / `cycle`, `return`, `select case` on
+integers, `allocate / deallocate`, whole-array and `(:)`-section assignments, vector subscripts
+inside `sum(..., dim=1)`, `merge`, `max`, `min`, `size`, array constructors, character assignment
+with `trim` and `//`.  A second group of constructs exists so that the drop-in shim of
+ocean-bgc_b200/fortran/ can be executed as well: `use, intrinsic :: iso_c_binding`, `type, bind(C)`,
+interface bodies with `bind(C, name=...)` and `value` dummies (external C functions), `c_ptr`,
+`c_loc`, `c_associated`, `c_f_pointer`, internal procedures (emitted as GCC nested functions),
+`character(len=*)` dummies, pointer arrays, default-initialised components, `include`, `;`, and
+the little I/O an error path needs (`write` to a unit, internal `read` of an integer,
+`get_environment_variable`, `error stop`).  Anything else stops the translation with the file
+and line.  The translator is lenient where a compiler is strict: it does not check conformance.
+
+-DREF_POISON fills every ALLOCATE with NaN patterns; -DREF_PROFILE counts inclusive cycles and
+calls per procedure (ref_prof_*); -DREF_TLS= makes the module variables plain globals.
 
 Usage:  f90c.py -o OUT.c -m META.json  A.F90 B.F90 ...   (files in module-dependency order)
 """
