@@ -477,6 +477,37 @@ def test_no_result_depends_on_unset_memory(po):
     same_bgc(b, a, "poisoned allocations")
 
 
+def test_columns_are_independent_in_the_reference(po, rp):
+    """no routine reads another column.  Shown with the reference itself: a block
+    computed in one call equals the same columns computed one call per column (numColumnsMax = 1,
+    the way upstream MPAS drives the library), cold and warm - which is what makes contiguous
+    column slabs per GPU, with no halo and no exchange, exact."""
+    nL, nC = 30, 12
+    cols, dms, mac = parity.make_bgc(nL, nC, po, ragged=True, with_dms=True, with_macros=True)
+    whole, dwhole, mwhole = cols.copy(), dms.copy(), mac.copy()
+    for _ in range(2):
+        rt.BGC_SourceSink(rp, whole, True)
+    rt.BGC_SurfaceFluxes(rp, whole)
+    rt.DMS_SourceSink(rp, dwhole)
+    rt.MACROS_SourceSink(rp, mwhole)
+    for c in range(nC):
+        one, d1, m1 = parity.make_bgc(nL, 1, po, ragged=True, column0=c, with_dms=True, with_macros=True)
+        # same ragged depth as in the block (the generator keys everything on the global column)
+        assert one.number_of_active_levels[0] == cols.number_of_active_levels[c]
+        for _ in range(2):
+            rt.BGC_SourceSink(rp, one, True)
+        rt.BGC_SurfaceFluxes(rp, one)
+        rt.DMS_SourceSink(rp, d1)
+        rt.MACROS_SourceSink(rp, m1)
+        same(one.BGC_tendencies[:, 0, :], whole.BGC_tendencies[:, c, :], "column %d tendencies" % c)
+        same(one.PH_PREV_3D[:, 0], whole.PH_PREV_3D[:, c], "column %d pH" % c)
+        same(one.forcing["netFlux"][0], whole.forcing["netFlux"][c], "column %d netFlux" % c)
+        for n in ("diag_photoC", "diag_POC_FLUX_IN", "diag_CO3"):
+            same(one.diag[n][:, 0], whole.diag[n][:, c], "column %d %s" % (c, n))
+        same(d1.DMS_tendencies[:, 0, :], dwhole.DMS_tendencies[:, c, :], "column %d DMS" % c)
+        same(m1.MACROS_tendencies[:, 0, :], mwhole.MACROS_tendencies[:, c, :], "column %d MACROS" % c)
+
+
 def test_thread_local_module_state(po):
     """The reference is not re-entrant (solver state in module SAVE variables, co2calc.F90:65-67);
     the translation makes that state thread-local.  Slabs computed concurrently must equal the
