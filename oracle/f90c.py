@@ -463,6 +463,7 @@ class Proc:
         self.parent = None       # host procedure of an internal procedure
         self.children = []
         self.external = False    # interface body with bind(C): a C function defined elsewhere
+        self.is_program = False  # the body of a main PROGRAM
         self.prefix_type = None
 
 
@@ -515,6 +516,16 @@ REF_TLS unsigned long long ref_prof_cyc[REF_PROF_MAX], ref_prof_calls[REF_PROF_M
 #define PROF_ENTER(id)
 #define PROF_EXIT(id)
 #endif
+/* unformatted stream I/O and the command line (only a main PROGRAM uses them) */
+static FILE *f_units[100];
+static int f_argc; static char **f_argv;
+static void f_open(int u, fstr_t name, int old) {
+  name = f_trim(name); name.s[name.n] = 0;
+  f_units[u] = fopen(name.s, old ? "rb" : "wb");
+  if (!f_units[u]) { fprintf(stderr, "cannot open %s\n", name.s); abort(); } }
+static void f_io(int u, void *p, size_t bytes, int wr) {
+  size_t n = wr ? fwrite(p, 1, bytes, f_units[u]) : fread(p, 1, bytes, f_units[u]);
+  if (n != bytes) { fprintf(stderr, "unit %d: short %s (%zu of %zu bytes)\n", u, wr ? "write" : "read", n, bytes); abort(); } }
 #ifdef REF_POISON
 static void *f_alloc(size_t nbytes) { void *p = malloc(nbytes ? nbytes : 1); memset(p, 0xFF, nbytes); return p; }
 #else
@@ -571,9 +582,23 @@ class Translator:
                 self.modules[w1] = mod
                 self.order.append(mod)
                 continue
-            if w0 == "end" or w0 in ("endmodule", "endsubroutine", "endfunction", "endtype", "endinterface"):
+            if w0 == "program" and w1 and len(toks) == 2:
+                mod = Module(w1)
+                self.modules[w1] = mod
+                self.order.append(mod)
+                pr = Proc("main", "subroutine", [], None, mod, ln)
+                pr.is_program = True
+                mod.procs["main"] = pr
+                stack.append(pr)
+                continue
+            if w0 == "end" or w0 in ("endmodule", "endsubroutine", "endfunction", "endtype", "endinterface",
+                                     "endprogram"):
                 what = w1 if w0 == "end" else w0[3:]
                 if what == "module":
+                    mod = None
+                    continue
+                if what == "program":
+                    stack.pop()
                     mod = None
                     continue
                 if what in ("subroutine", "function"):
@@ -628,6 +653,9 @@ class Translator:
                 self.decl(toks, mod=mod)
                 continue
             # inside a procedure: keep the raw statement, classify in pass 2
+            if proc.is_program and w0 == "use":
+                mod.uses.append(toks[1][1])
+                continue
             proc.body.append((ln, toks))
         return self
 
@@ -1410,6 +1438,46 @@ class Translator:
             esc = msg.replace("\\", "\\\\").replace('"', '\\"')
             self.w(f'fputs("{esc}\\n", stderr); abort();')
             return
+        if k0 == "id" and w0 in ("read", "write") and w1 == "(" and self._ctl_items(toks) == 1:
+            # unformatted stream transfer: read(u) a, b, ...   /   write(u) a, b, ...
+            ip = Parser(toks[2:], p.where)
+            unit, _ = self.emit(ip.arglist()[0])
+            while not ip.at_end():
+                a = ip.expr()
+                if not isinstance(a, Ref):
+                    self.err("I/O list items must be variables")
+                self.want_whole = True
+                c, t, _ = self.resolve_ref(a, None)
+                self.want_whole = False
+                sym = self.last_sym
+                esz = f"sizeof({t.scalar().ctype()})" + (f" * {t.clen}" if t.base == "char" else "")
+                if t.rank > 0:
+                    ptr = f"({c}).p" if sym.alloc else f"({c})"
+                    n = self.sym_total_size(sym, c)
+                    self.w(f"f_io({unit}, {ptr}, {esz} * (size_t)({n}), {int(w0 == 'write')});")
+                else:
+                    self.w(f"f_io({unit}, &({c}), {esz}, {int(w0 == 'write')});")
+                ip.accept(",")
+            return
+        if k0 == "id" and w0 == "open" and w1 == "(":
+            items = Parser(toks[2:], p.where).arglist()
+            unit, _ = self.emit(items[0])
+            kw = {x.name: x.e for x in items if isinstance(x, Kw)}
+            fc, ft = self.emit(kw["file"])
+            old = isinstance(kw.get("status"), Str) and kw["status"].val.lower() == "old"
+            self.w(f"f_open({unit}, {self.as_fstr(fc, ft)}, {int(old)});")
+            return
+        if k0 == "id" and w0 == "close" and w1 == "(":
+            unit, _ = self.emit(Parser(toks[2:], p.where).arglist()[0])
+            self.w(f"fclose(f_units[{unit}]); f_units[{unit}] = 0;")
+            return
+        if k0 == "id" and w0 == "call" and w1 == "get_command_argument":
+            items = Parser(toks[3:], p.where).arglist()
+            ic, _ = self.emit(items[0])
+            vc, vt, _ = self.resolve_ref(items[1], None)
+            self.w(f"f_assign({vc}, {vt.clen}, ({ic}) < f_argc ? f_lit(f_argv[{ic}], (int)strlen(f_argv[{ic}])) "
+                   f": f_lit(\"\", 0));")
+            return
         if k0 == "id" and w0 == "write" and w1 == "(":
             # unit and format are ignored: every item goes to stderr in list order (error paths only)
             depth, j = 0, 1
@@ -1631,6 +1699,21 @@ class Translator:
         else:
             self.w(f"{lc} = {rc};")
 
+    @staticmethod
+    def _ctl_items(toks):
+        """number of items in the parenthesised control list that follows READ / WRITE"""
+        depth, n = 0, 1
+        for k, v in toks[1:]:
+            if k == "op" and v == "(":
+                depth += 1
+            elif k == "op" and v == ")":
+                depth -= 1
+                if depth == 0:
+                    return n
+            elif k == "op" and v == "," and depth == 1:
+                n += 1
+        return n
+
     # ---------------------------------------------------------------- driver
     def cdecl(self, s, name=None, static_tls=False):
         """C declaration of a variable / component."""
@@ -1732,6 +1815,9 @@ class Translator:
             if s.init is not None:
                 self.err(f"initialised (SAVE) local {s.name} is not supported")
             d = self.cdecl(s)
+            if pr.is_program:
+                self.w("static " + d)      # a main program's variables are SAVEd: zero-initialised
+                continue
             if s.alloc:
                 d = d[:-1] + " = {0, 0, 0, 0};"
                 if not s.pointer:
@@ -1762,6 +1848,8 @@ class Translator:
             self.w(f"return {pr.syms[pr.result].cname};")
         self.ind = base_ind
         self.w("}")
+        if pr.is_program:
+            self.w(f"int main(int argc, char **argv) {{ f_argc = argc; f_argv = argv; {pr.cname}(); return 0; }}")
         if not nested:
             self.w("")
         else:
