@@ -25,7 +25,9 @@ interface bodies with `bind(C, name=...)` and `value` dummies (external C functi
 `c_loc`, `c_associated`, `c_f_pointer`, internal procedures (emitted as GCC nested functions),
 `character(len=*)` dummies, pointer arrays, default-initialised components, `include`, `;`, and
 the little I/O an error path needs (`write` to a unit, internal `read` of an integer,
-`get_environment_variable`, `error stop`).  Anything else stops the translation with the file
+`get_environment_variable`, `error stop`).  A third, small group runs the stand-alone driver of
+tests/fortran/: a main `program`, `open / read / write / close` of unformatted stream files,
+`get_command_argument`.  Anything else stops the translation with the file
 and line.  The translator is lenient where a compiler is strict: it does not check conformance.
 
 -DREF_POISON fills every ALLOCATE with NaN patterns; -DREF_PROFILE counts inclusive cycles and
