@@ -239,13 +239,11 @@ class RefParms:
             self._copy_slots(parms.ind, self.ind, 30)
             self._copy_slots(parms.dms_ind, self.dms_ind, None)
             self._copy_slots(parms.macros_ind, self.macros_ind, None)
-        else:
-            for obj in (self.ind, self.dms_ind, self.macros_ind):
-                i = 0
-                for fname, ft in obj._fields_:
-                    if ft is C.c_int and fname.endswith("_ind") and i < {id(self.ind): 30}.get(id(obj), 99):
-                        i += 1
-                        setattr(obj, fname, i)
+        else:      # declaration order 1..N (the autotroph indices sp_ind.. are set by BGC_parms_init)
+            for obj, count in ((self.ind, 30), (self.dms_ind, 14), (self.macros_ind, 8)):
+                slots = [n for n, t in obj._fields_ if t is C.c_int and n.endswith("_ind")][:count]
+                for i, fname in enumerate(slots):
+                    setattr(obj, fname, i + 1)
         var("bgc_parms__t0_kelvin_bgc").value = t0_kelvin
         call("bgc_parms__bgc_parms_init", self.ind, self.autotrophs)
         call("bgc_mod__bgc_init", self.ind, self.autotrophs)
