@@ -22,7 +22,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REFDIR = os.path.join(HERE, "_ref")
-LIB_PATH = os.path.join(REFDIR, "libbgc_ref.so")
+LIB_PATH = os.environ.get("BGC_REF_LIB", os.path.join(REFDIR, "libbgc_ref.so"))   # override: coverage / profile builds
 META_PATH = os.path.join(REFDIR, "meta.json")
 REFERENCE_SRC = os.environ.get("BGC_REFERENCE_SRC", "/root/reference")
 

@@ -185,6 +185,39 @@ def test_comp_co3terms(rp):
             assert r[nm] == g[nm], (i, nm, r[nm], g[nm])
 
 
+def _oracle_1point(depth, temp, salt, dic, ta, pt, sit, phlo, phhi, xco2, atmpres, locmip=True):
+    import ctypes as C
+    lo, hi = C.c_double(phlo), C.c_double(phhi)
+    out = [C.c_double() for _ in range(5)]
+    o.lib().oracle_co2calc_1point(C.c_double(depth), C.c_int(int(locmip)), C.c_int(1), C.c_double(temp),
+                                  C.c_double(salt), C.c_double(dic), C.c_double(ta), C.c_double(pt),
+                                  C.c_double(sit), C.byref(lo), C.byref(hi), C.byref(out[0]), C.c_double(xco2),
+                                  C.c_double(atmpres), *[C.byref(x) for x in out[1:]], None)
+    return dict(zip(("ph", "co2star", "dco2star", "pco2surf", "dpco2"), (x.value for x in out)),
+                phlo=lo.value, phhi=hi.value)
+
+
+def test_branches_no_caller_takes(rp):
+    """Statements of the reference that neither BGC_SourceSink nor BGC_SurfaceFluxes ever reach
+    (found with gcov on the translated reference): the seawater-scale K1/K2 of
+    comp_co3_coeffs (k1_k2_pH_tot = .false., co2calc.F90:466-469, :495-498) and the swapped-bracket
+    branch of drtsafe_row (:940-947, entered when the caller's phlo > phhi)."""
+    rng = np.random.default_rng(8)
+    for i in range(200):
+        a = (5.0, rng.uniform(-1.8, 31), rng.uniform(30, 38), rng.uniform(1800, 2300))
+        a = a + (a[3] + rng.uniform(80, 420), rng.uniform(0, 3), rng.uniform(0, 150))
+        lo, hi = (7.0, 9.0) if i % 2 == 0 else (9.0, 7.0)
+        tail = (rng.uniform(280, 560), rng.uniform(0.95, 1.05))
+        for locmip in (False, True):
+            r = rt.co2calc_1point(*a, lo, hi, *tail, locmip_k1_k2_bug_fix=locmip)
+            g = _oracle_1point(*a, lo, hi, *tail, locmip=locmip)
+            for k in g:
+                assert r[k] == g[k], (i, locmip, k, r[k], g[k])
+    # the two pH scales differ, so the flag is not a no-op
+    assert rt.co2calc_1point(*a, 7.0, 9.0, *tail, locmip_k1_k2_bug_fix=False)["ph"] != \
+        rt.co2calc_1point(*a, 7.0, 9.0, *tail, locmip_k1_k2_bug_fix=True)["ph"]
+
+
 def _ref_points(pts):
     n = len(pts["temp"])
     out = {k: np.zeros(n) for k in ("ph", "co2star", "dco2star", "pco2surf", "dpco2")}
