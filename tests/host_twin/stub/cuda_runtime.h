@@ -19,3 +19,6 @@ static inline double host_rcp_seed(double b) {
 struct HostTid { int x; };
 static HostTid threadIdx = {0};
 static inline void __syncthreads() {}
+// warp votes of a one-lane "warp"
+static inline bool __any_sync(unsigned, bool p) { return p; }
+static inline bool __all_sync(unsigned, bool p) { return p; }
