@@ -1194,6 +1194,8 @@ class Translator:
             fc, ft = self.emit(args[1], ivar)
             mc, _ = self.emit(args[2], ivar)
             t = tt
+            if t.base == "char":
+                return f"(({mc}) ? {self.as_fstr(tc, tt)} : {self.as_fstr(fc, ft)})", T("char", 1, 0, None, 0)
             return f"(({mc}) ? ({t.ctype()})({tc}) : ({t.ctype()})({fc}))", t
         if name == "sum":
             arr = args[0]

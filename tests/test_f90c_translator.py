@@ -166,6 +166,60 @@ def test_named_constants_are_exported(L):
     assert L.const("kinds_mod__single_lit") == float(np.float32(1e-8))
 
 
+@pytest.fixture(scope="module")
+def LI(tmp_path_factory):
+    """tests/f90c_cases/interop.F90 + its C side: the ISO_C_BINDING group of constructs"""
+    d = tmp_path_factory.mktemp("f90c_interop")
+    c, meta, so = str(d / "interop.c"), str(d / "interop.json"), str(d / "libinterop.so")
+    subprocess.check_call([sys.executable, os.path.join(REPO, "oracle", "f90c.py"), "-o", c, "-m", meta,
+                           os.path.join(HERE, "f90c_cases", "interop.F90")], stdout=subprocess.DEVNULL)
+    subprocess.check_call(["gcc", "-O2", "-fPIC", "-w", "-shared", "-o", so, c,
+                           os.path.join(HERE, "f90c_cases", "interop_c.c"), "-lm"])
+    return rt.TLib(so, meta)
+
+
+def test_c_interoperability(LI):
+    """bind(C) types with default-initialised c_ptr components, interface bodies with value and
+    by-reference dummies, c_loc of an allocatable component, c_associated, array constructors with
+    kind suffixes, module variables with initialisers."""
+    h = LI.struct("interop_mod__holder")()
+    vals = np.arange(1.0, 6.0)
+    h.values = rt.describe(vals)
+    rc, _ = LI.call("interop_mod__scale_through_c", h, 2.5)
+    assert rc == 5 + 1000 * 6                       # n, spare was set by C (no +100), c_sum3 = 6
+    assert np.array_equal(vals, 2.5 * np.arange(1.0, 6.0))
+    empty = LI.struct("interop_mod__holder")()      # not allocated -> NULL data, n = 0
+    rc, _ = LI.call("interop_mod__scale_through_c", empty, 2.0)
+    assert rc == 0 + 1000 * 6
+    assert LI.var("interop_mod__calls").value == 2 and LI.var("interop_mod__seen").value == 1
+
+
+def test_internal_procedures_and_character_dummies(LI):
+    h = LI.struct("interop_mod__holder")()
+    tags = np.full((3, 8), ord("?"), dtype=np.uint8)
+    d = rt.FA()
+    d.p, d.n1, d.n2, d.n3 = tags.ctypes.data, 3, 1, 1
+    h.tags = d
+    # a character(len=*) dummy travels as the translator's string value {int n; char s[1024]}
+    class FStr(rt.C.Structure):
+        _fields_ = [("n", rt.C.c_int), ("s", rt.C.c_char * 1024)]
+    f = FStr(4, b"ab  ")
+    fn = getattr(LI.lib(), "interop_mod__label_all")
+    fn.restype = None
+    fn(rt.C.byref(h), f)
+    assert [bytes(r).decode() for r in tags] == ["ab-odd  ", "ab-even ", "ab-odd  "]
+
+
+def test_c_strings_and_while_loops(LI):
+    n, _ = LI.call("interop_mod__read_c_string")
+    assert n == len("thirteen char")
+    calls = LI.var("interop_mod__calls").value
+    r, _ = LI.call("interop_mod__count_to", 10)
+    assert r == 12 + calls                          # 3, 6, 9, 12
+    r, _ = LI.call("interop_mod__count_to", 1000)
+    assert r == 102 + calls                         # the `;`-separated exit inside the loop
+
+
 def test_unsupported_constructs_stop_the_translation(tmp_path):
     src = tmp_path / "bad.F90"
     src.write_text("module m\n implicit none\ncontains\n subroutine s(x)\n  real(8) :: x\n"
