@@ -138,6 +138,38 @@ def test_shim_context_life_cycle_and_parameter_changes():
     assert mock.mock_live_contexts() == 0
 
 
+def test_shim_forwards_every_parameter():
+    """push_params / the DMS and MACROS flattening list every field by hand: perturb ALL tunables,
+    the whole functional-group table and the restoring switches at random and demand the oracle's
+    bits - a field forwarded to the wrong member (or not at all) changes the answer."""
+    sys.path.insert(0, os.path.join(parity.REPO, "scripts"))
+    import fuzz_oracle_vs_reference as gen
+    L = rt.TLib(SHIM, SHIM_META, preload=[MOCK])
+    for seed in (1, 2, 4, 5):
+        rng = np.random.default_rng(seed)
+        po = o.Parms()
+        gen.perturb_parms(po, rng)
+        rp = rt.RefParms(po, L=L).sync_from(po)
+        cols, dms, mac = parity.make_bgc(17, 40, po, ragged=True, with_dms=True, with_macros=True, seed=77 + seed)
+        cols.forcing["NUTR_RESTORE_RTAU"][...] = rng.uniform(0.0, 1e-6, cols.forcing["NUTR_RESTORE_RTAU"].shape)
+        for nm, slot in (("NO3_CLIM", po.ind.no3_ind), ("PO4_CLIM", po.ind.po4_ind), ("SiO3_CLIM", po.ind.sio3_ind)):
+            cols.forcing[nm][...] = cols.BGC_tracers[:, :, slot - 1] * 1.1
+        a, da, ma = cols.copy(), dms.copy(), mac.copy()
+        o.BGC_SourceSink(po, a, True); o.BGC_SurfaceFluxes(po, a)
+        o.DMS_SourceSink(po, da); o.DMS_SurfaceFluxes(po, da); o.MACROS_SourceSink(po, ma)
+        b, db, mb = cols.copy(), dms.copy(), mac.copy()
+        rt.BGC_SourceSink(rp, b, True); rt.BGC_SurfaceFluxes(rp, b)
+        rt.DMS_SourceSink(rp, db); rt.DMS_SurfaceFluxes(rp, db); rt.MACROS_SourceSink(rp, mb)
+        _same(b.BGC_tendencies, a.BGC_tendencies, "seed %d BGC tendencies" % seed)
+        for n in a.diag:
+            _same(b.diag[n], a.diag[n], "seed %d %s" % (seed, n))
+        _same(b.forcing["netFlux"], a.forcing["netFlux"], "seed %d netFlux" % seed)
+        _same(db.DMS_tendencies, da.DMS_tendencies, "seed %d DMS tendencies" % seed)
+        _same(db.forcing["netFlux"], da.forcing["netFlux"], "seed %d DMS netFlux" % seed)
+        _same(mb.MACROS_tendencies, ma.MACROS_tendencies, "seed %d MACROS tendencies" % seed)
+    L.call("bgc_b200_runtime__bgc_b200_finalize")
+
+
 @pytest.mark.gpu
 def test_shim_drop_in_chain_on_the_gpu():
     """reference-typed caller -> shim -> C ABI -> CUDA, against the translated reference."""
