@@ -36,3 +36,11 @@ for f in ("gpurun_out/bench_$TAG.json", "gpurun_out/bench_ref_$TAG.json"):
     except Exception as e:
         print(f, "no result:", e)
 PY
+# optional extras (each a few seconds of box time): FUZZ=300 runs the differential fuzzer against the CUDA path,
+# MICRO=1 the read/write-mix micro-benchmark (scripts/micro/rw_mix must have been built: see its header)
+if [ -n "${FUZZ:-}" ]; then
+  python scripts/fuzz_gpu_vs_reference.py $FUZZ > gpurun_out/fuzz_gpu_$TAG.txt 2>&1; echo "fuzz exit $?"; tail -3 gpurun_out/fuzz_gpu_$TAG.txt
+fi
+if [ "${MICRO:-0}" = "1" ] && [ -x scripts/micro/rw_mix ]; then
+  scripts/micro/rw_mix > gpurun_out/rw_mix_$TAG.txt 2>&1; RW_MIX_STORES=1 scripts/micro/rw_mix > gpurun_out/rw_mix_stores_$TAG.txt 2>&1; tail -4 gpurun_out/rw_mix_stores_$TAG.txt
+fi
