@@ -22,12 +22,13 @@ struct bgc_ctx {
 };
 
 static char g_err[512] = "";
-static int g_live = 0, g_created = 0, g_calls = 0;
+static int g_live = 0, g_created = 0, g_calls = 0, g_last_device = -1;
 
 const char *bgc_last_error(void) { return g_err; }
 int mock_live_contexts(void) { return g_live; }
 int mock_created_contexts(void) { return g_created; }
 int mock_compute_calls(void) { return g_calls; }
+int mock_last_device(void) { return g_last_device; }
 
 static int fail(int code, const char *msg) { strncpy(g_err, msg, sizeof g_err - 1); return code; }
 
@@ -35,7 +36,7 @@ int bgc_ctx_create(int device, int nLevelsMax, int nColumnsMax, bgc_ctx **out) {
   if (!out || nLevelsMax < 1 || nColumnsMax < 1) return fail(BGC_ERR_ARG, "mock: bad ctx_create arguments");
   bgc_ctx *c = calloc(1, sizeof *c);
   c->device = device; c->nLevelsMax = nLevelsMax; c->nColumnsMax = nColumnsMax;
-  *out = c; g_live++; g_created++;
+  *out = c; g_live++; g_created++; g_last_device = device;
   return BGC_OK;
 }
 int bgc_ctx_destroy(bgc_ctx *c) { if (!c) return fail(BGC_ERR_ARG, "mock: null ctx"); free(c); g_live--; return BGC_OK; }
@@ -67,6 +68,7 @@ int bgc_source_sink(bgc_ctx *c, const BgcInput *in, const BgcForcing *fo, BgcOut
                     int nL, int nC, int n, int alt, int mem_space) {
   int rc = check(c, c ? c->have_bgc : 0, nL, nC, n, mem_space);
   if (rc) return rc;
+  if (getenv("MOCK_BGC_FAIL")) return fail(BGC_ERR_CUDA, "mock: simulated CUDA failure in bgc_source_sink");
   oracle_BGC_SourceSink(&c->p, c->a, &c->ind, in, fo, out, dg, nL, nC, n, alt, 1, NULL);
   return BGC_OK;
 }

@@ -138,6 +138,69 @@ def test_shim_context_life_cycle_and_parameter_changes():
     assert mock.mock_live_contexts() == 0
 
 
+def test_shim_device_selection(monkeypatch):
+    """bgc_b200_runtime: the device comes from bgc_b200_set_device, else from BGC_B200_DEVICE, else 0
+    (one MPI rank per GPU passes its node-local rank).  Module state is per thread in the translation,
+    so every case runs in a thread of its own, as a fresh process would."""
+    import threading
+    L = rt.TLib(SHIM, SHIM_META, preload=[MOCK])
+    mock = C.CDLL(MOCK, mode=C.RTLD_GLOBAL)
+    po = o.Parms()
+    seen = {}
+
+    def case(name, env, set_device):
+        def run():
+            if env is None:
+                os.environ.pop("BGC_B200_DEVICE", None)
+            else:
+                os.environ["BGC_B200_DEVICE"] = env
+            rp = rt.RefParms(po, L=L)
+            if set_device is not None:
+                L.call("bgc_b200_runtime__bgc_b200_set_device", set_device)
+            cols, _, _ = parity.make_bgc(5, 8, po)
+            rt.BGC_SourceSink(rp, cols, True)
+            seen[name] = mock.mock_last_device()
+            L.call("bgc_b200_runtime__bgc_b200_finalize")
+        t = threading.Thread(target=run)
+        t.start(); t.join()
+
+    keep = os.environ.get("BGC_B200_DEVICE")
+    try:
+        case("default", None, None)
+        case("env", "3", None)
+        case("env garbage", "gpu-one", None)
+        case("explicit beats env", "3", 5)
+    finally:
+        if keep is None:
+            os.environ.pop("BGC_B200_DEVICE", None)
+        else:
+            os.environ["BGC_B200_DEVICE"] = keep
+    assert seen == {"default": 0, "env": 3, "env garbage": 0, "explicit beats env": 5}, seen
+
+
+def test_shim_fails_loudly(tmp_path):
+    """The reference has no error reporting; the shim must not swallow a failed GPU call (there is no
+    CPU fallback): message of the library on stderr, then `error stop`.  Run in a child process."""
+    import subprocess
+    prog = (
+        "import sys, os\n"
+        "sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import parity, ref_translated as rt\n"
+        "o = parity.oracle(); po = o.Parms()\n"
+        "L = rt.TLib(%r, %r, preload=[%r])\n"
+        "rp = rt.RefParms(po, L=L)\n"
+        "cols, _, _ = parity.make_bgc(5, 8, po)\n"
+        "rt.BGC_SourceSink(rp, cols, True)\n"
+        "print('survived')\n") % (parity.HERE, os.path.join(parity.REPO, "oracle"), SHIM, SHIM_META, MOCK)
+    env = dict(os.environ, MOCK_BGC_FAIL="1")
+    r = subprocess.run([sys.executable, "-c", prog], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode != 0 and "survived" not in r.stdout
+    assert "bgc_source_sink failed with code" in r.stderr and "-2" in r.stderr
+    assert "simulated CUDA failure" in r.stderr and "GPU hot path failed" in r.stderr
+    ok = subprocess.run([sys.executable, "-c", prog], capture_output=True, text=True, timeout=300)
+    assert ok.returncode == 0 and "survived" in ok.stdout
+
+
 def test_shim_forwards_every_parameter():
     """push_params / the DMS and MACROS flattening list every field by hand: perturb ALL tunables,
     the whole functional-group table and the restoring switches at random and demand the oracle's
