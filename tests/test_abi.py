@@ -117,3 +117,25 @@ def test_sharding_slabs():
                 assert b == a + na and 0 <= na - nb <= 1
     with pytest.raises(ValueError):
         sh.slab(2, 2, 10)
+
+
+def test_generated_fortran_bindings_are_in_sync_with_the_header(tmp_path):
+    """ocean-bgc_b200/fortran/bgc_b200_capi.F90 and the *_ptrs.inc files are generated from the
+    X-macro lists of include/bgc_b200.h (gen_capi.py): regenerating them must change nothing."""
+    import hashlib
+    import shutil
+    import sys
+    pkg_dir = os.path.join(parity.REPO, "ocean-bgc_b200")
+    shutil.copytree(os.path.join(parity.REPO, "include"), tmp_path / "include")
+    os.makedirs(tmp_path / "ocean-bgc_b200")
+    shutil.copy(os.path.join(pkg_dir, "abi.py"), tmp_path / "ocean-bgc_b200" / "abi.py")
+    shutil.copytree(os.path.join(pkg_dir, "fortran"), tmp_path / "ocean-bgc_b200" / "fortran")
+    work = tmp_path / "ocean-bgc_b200" / "fortran"
+    subprocess.check_call([sys.executable, str(work / "gen_capi.py")], stdout=subprocess.DEVNULL)
+    fdir = os.path.join(pkg_dir, "fortran")
+    names = ["bgc_b200_capi.F90"] + sorted(n for n in os.listdir(fdir) if n.endswith(".inc"))
+    assert len(names) == 6
+    for n in names:
+        a = hashlib.sha256(open(os.path.join(fdir, n), "rb").read()).hexdigest()
+        b = hashlib.sha256((work / n).read_bytes()).hexdigest()
+        assert a == b, "%s is out of date: run ocean-bgc_b200/fortran/gen_capi.py" % n
