@@ -40,7 +40,7 @@ def one_round(seed, report):
     if seed % 3:
         gen.perturb_parms(parms, rng)
     rp = rt.RefParms(parms).sync_from(parms)
-    nL, nC = int(rng.choice([3, 17, 60])), 256
+    nL, nC = int(rng.choice([3, 17, 60])), int(rng.choice([1, 7, 256, 256, 257]))   # incl. the one-column calls of upstream MPAS
     cols, dms, mac = parity.make_bgc(nL, nC, parms, with_dms=True, with_macros=True, seed=1000 + seed)
     gen.perturb_inputs(cols, dms, mac, rng)
     alt = bool(rng.integers(0, 2))
