@@ -120,6 +120,33 @@ def ragged_block():
                         o2min=np.stack([cols.diag["diag_O2_ZMIN"], cols.diag["diag_O2_ZMIN_DEPTH"]]))
 
 
+def surface_dms_macros_block():
+    """Everything except BGC_SourceSink on a ragged 20 x 64 block: BGC_SurfaceFluxes with its in-place
+    side effects on the forcing, DMS_SourceSink / DMS_SurfaceFluxes, MACROS_SourceSink (their
+    diagnostics on active cells only: the reference leaves the rest untouched)."""
+    po = o.Parms()
+    cols, dms, mac = parity.make_bgc(20, 64, po, ragged=True, nColumns=61, with_dms=True, with_macros=True)
+    cols.forcing["iceFraction"][:7] = [-0.2, 1.4, 0.3, 0.0, 1.0, 2.0, -1.0]
+    o.BGC_SurfaceFluxes(po, cols)
+    o.DMS_SourceSink(po, dms); o.DMS_SurfaceFluxes(po, dms)
+    o.MACROS_SourceSink(po, mac)
+    act = dms.active_mask() if hasattr(dms, "active_mask") else cols.active_mask()
+    out = {"netFlux": cols.forcing["netFlux"], "gasFlux": cols.forcing["gasFlux"],
+           "iceFraction": cols.forcing["iceFraction"], "surface_pH": cols.forcing["surface_pH"],
+           "depositionFlux": cols.forcing["depositionFlux"],
+           "dms_tend": dms.DMS_tendencies, "dms_netFlux": dms.forcing["netFlux"],
+           "macros_tend": mac.MACROS_tendencies}
+    for n, a in cols.flux_diag.items():
+        out["bflux_" + n] = a
+    for n, a in dms.diag.items():
+        out["dms_" + n] = np.where(act, a, 0.0)
+    for n, a in dms.flux_diag.items():
+        out["dflux_" + n] = a[:61]
+    for n, a in mac.diag.items():
+        out["mac_" + n] = np.where(act, a, 0.0)
+    np.savez_compressed(os.path.join(HERE, "surface_dms_macros_20x64.npz"), **out)
+
+
 if __name__ == "__main__":
-    single_column(); co2_points(); ragged_block()
+    single_column(); co2_points(); ragged_block(); surface_dms_macros_block()
     print("golden fixtures written to", HERE, "from the", SOURCE)

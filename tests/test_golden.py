@@ -63,6 +63,33 @@ def test_oracle_reproduces_golden_points_and_block():
     assert np.array_equal(cols.BGC_tendencies, b["tend"]) and np.array_equal(cols.PH_PREV_3D, b["ph"])
 
 
+def test_oracle_reproduces_golden_surface_dms_macros():
+    """BGC_SurfaceFluxes, DMS_*, MACROS_SourceSink against the vectors the translated reference produced"""
+    o = parity.oracle()
+    po = o.Parms()
+    g = np.load(os.path.join(G, "surface_dms_macros_20x64.npz"))
+    cols, dms, mac = parity.make_bgc(20, 64, po, ragged=True, nColumns=61, with_dms=True, with_macros=True)
+    cols.forcing["iceFraction"][:7] = [-0.2, 1.4, 0.3, 0.0, 1.0, 2.0, -1.0]
+    o.BGC_SurfaceFluxes(po, cols)
+    o.DMS_SourceSink(po, dms); o.DMS_SurfaceFluxes(po, dms)
+    o.MACROS_SourceSink(po, mac)
+    k = np.arange(1, 21)[:, None]
+    kmax = dms.number_of_active_levels.copy(); kmax[61:] = 0
+    act = k <= kmax[None, :]
+    for nm in ("netFlux", "gasFlux", "iceFraction", "surface_pH", "depositionFlux"):
+        assert np.array_equal(cols.forcing[nm], g[nm]), nm
+    assert np.array_equal(dms.DMS_tendencies, g["dms_tend"]) and np.array_equal(dms.forcing["netFlux"], g["dms_netFlux"])
+    assert np.array_equal(mac.MACROS_tendencies, g["macros_tend"])
+    for n, a in cols.flux_diag.items():
+        assert np.array_equal(a, g["bflux_" + n]), n
+    for n, a in dms.diag.items():
+        assert np.array_equal(np.where(act, a, 0.0), g["dms_" + n]), n
+    for n, a in dms.flux_diag.items():
+        assert np.array_equal(a[:61], g["dflux_" + n]), n
+    for n, a in mac.diag.items():
+        assert np.array_equal(np.where(act, a, 0.0), g["mac_" + n]), n
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("flavour", ["prod", "strict"])
 def test_gpu_reproduces_golden(flavour):
