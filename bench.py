@@ -6,18 +6,23 @@ Workload (config 4 of BASELINE.json): an EC60to30-sized mesh, 235 160 columns x
 tendency update = BGC_SourceSink + BGC_SurfaceFluxes + DMS_SourceSink +
 DMS_SurfaceFluxes + MACROS_SourceSink with every diagnostic produced, plus the
 tracer-inventory reduction (all-reduced over NCCL when N > 1).  One "step" is
-one such update of the whole mesh.  Columns are independent, so at N GPUs every
-rank owns a contiguous slab of 235 160 columns of an N-times larger mesh (weak
-scaling, no data-path collective; the 64-double inventory all-reduce is the only
-exchange).
+one such update of the whole mesh.  Columns are independent: at N GPUs the ONE
+mesh is split into N contiguous column slabs, one per rank (strong scaling, as
+north_star states it; no halo, no data-path collective; the 64-double inventory
+all-reduce is the only exchange).  `--weak` gives every rank a whole EC60to30
+mesh of its own instead.  At N = 1 and N = 8 the line also carries config 5
+(`secondary.rrs18to6_slab`): one GPU's slab of the RRS18to6 mesh, 461 654
+columns x 80 levels per GPU, with the inventory all-reduce.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
 Prints ONE JSON line (rank 0).  `value` is device-resident throughput (inputs in
 HBM when the clock starts); `e2e` is the same update through the C ABI's host
 (Fortran-layout) entry points with pinned host arrays, H2D/D2H inside the timed
-region.  `--impl reference` times the CPU oracle (the C restatement of the
-reference Fortran; no Fortran compiler exists in this image) on the host cores.
+region.  `--impl reference` times the reference's own sources (machine-translated
+to C by oracle/f90c.py and compiled by gcc: oracle/_ref/libbgc_ref.so; the image
+has no Fortran compiler) on the host cores, or the C oracle port when oracle/_ref
+is absent.
 """
 import argparse
 import json
@@ -35,6 +40,8 @@ import __graft_entry__ as ge  # noqa: E402
 
 EC_COLUMNS = 235160
 EC_LEVELS = 60
+RRS_COLUMNS = 3693225     # RRS18to6: 8 slabs of 461 654 columns x 80 levels
+RRS_LEVELS = 80
 METRIC = "BGC_SourceSink cell-updates/s (cols x levels), full BGC+DMS+MACROS tendency update"
 UNIT = "cell-updates/s"
 
@@ -234,8 +241,8 @@ def run_reference(args, rank, world):
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, world),
+        "scaling": "weak" if (args.weak and world > 1) else "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": workload_config(args, world),
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": nthreads, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": note,
@@ -250,11 +257,14 @@ def workload_config(args, world):
             "cells_total": (getattr(args, "mesh_columns", args.columns) if getattr(args, "strong", False)
                             else args.columns * world) * args.levels,
             "diagnostics": "all (BGC 130 + DMS 27 + MACROS 6 arrays per cell)",
-            "sharding": "contiguous column slabs, one process per GPU, no halo",
+            "sharding": ("ONE mesh split into contiguous column slabs, one process per GPU, no halo (strong scaling)"
+                         if (getattr(args, "strong", False) or world == 1) else
+                         "one whole mesh per GPU (weak scaling, --weak)"),
             "cache": "inputs+outputs per step (%.1f GB per GPU) far exceed the 126 MB L2; no flush needed"
                      % (args.columns * args.levels * B_API / 1e9),
             "ph_brackets": "warm (PH_PREV from the untimed cold pass), as in a running model",
-            "cuda_graph": (not getattr(args, "no_graph", False)) and world == 1,
+            "mesh_columns": getattr(args, "mesh_columns", args.columns),
+            "cuda_graph": (not getattr(args, "no_graph", False)),
             "zero_biomass_shortcut": "on (library default): functional-group bodies are skipped where the biomass of a "
                                      "whole warp is exactly zero (the synthetic columns are zero below 300 m by "
                                      "construction, SURVEY.md 8(d)); see without_zero_biomass_shortcut for the cost with "
@@ -265,69 +275,9 @@ def workload_config(args, world):
 
 # ------------------------------------------------------------------ device-resident arm
 def fill_device_inputs(pkg, parms, bgc, dms, mac, column0, nthreads=0):
-    """Generate this rank's synthetic columns directly in the SoA layout on the host
-    and copy the INPUT members to the device containers."""
-    import ctypes as C
-    import torch
-    abi = pkg.abi
-    nL, nC = bgc.nLevelsMax, bgc.nColumnsMax
-    h = {}
-
-    def arr(shape, dtype=np.float64):
-        return np.zeros(shape, dtype=dtype)
-    # host staging in SoA layout (inputs only)
-    h["tr"] = arr((abi.BGC_TRACER_CNT, nL, nC))
-    for n in bgc.K2_IN:
-        h[n] = arr((nL, nC))
-    h["lat"] = arr((nC,)); h["kmax"] = arr((nC,), np.int32)
-    hf = {n: arr((nL, nC)) for n in ("FESEDFLUX",)}
-    hf.update({n: arr((nC,)) for n in abi.BGC_FORCING_C1})
-    hf.update({n: arr((abi.BGC_TRACER_CNT, nC)) for n in abi.BGC_FORCING_FLUX})
-    h["dtr"] = arr((abi.DMS_TRACER_CNT, nL, nC)); h["ddz"] = arr((nL, nC)); h["dkmax"] = arr((nC,), np.int32)
-    hdf = {n: arr((nC,)) for n in abi.DMS_FORCING_C1}
-    hdf["netFlux"] = arr((abi.DMS_TRACER_CNT, nC))
-    h["mtr"] = arr((abi.MACROS_TRACER_CNT, nL, nC)); h["mdz"] = arr((nL, nC)); h["mkmax"] = arr((nC,), np.int32)
-
-    cin = abi.BgcInput()
-    cin.BGC_tracers = abi.dptr(h["tr"])
-    for n in bgc.K2_IN:
-        setattr(cin, n, abi.dptr(h[n]))
-    cin.cell_latitude = abi.dptr(h["lat"]); cin.number_of_active_levels = abi.iptr(h["kmax"])
-    cfo = abi.BgcForcing()
-    for n, a in hf.items():
-        setattr(cfo, n, abi.dptr(a))
-    din = abi.DmsInput()
-    din.DMS_tracers = abi.dptr(h["dtr"]); din.cell_thickness = abi.dptr(h["ddz"])
-    din.number_of_active_levels = abi.iptr(h["dkmax"])
-    dfo = abi.DmsForcing()
-    for n, a in hdf.items():
-        setattr(dfo, n, abi.dptr(a))
-    min_ = abi.MacrosInput()
-    min_.MACROS_tracers = abi.dptr(h["mtr"]); min_.cell_thickness = abi.dptr(h["mdz"])
-    min_.number_of_active_levels = abi.iptr(h["mkmax"])
-
-    from importlib import import_module
-    colmod = import_module(pkg.__name__ + ".columns")
-    sp = colmod._SynthSpec(colmod.SEED_COLUMNS, nL, nC, bgc.nColumns, column0, nL, 0, 1, 1, nthreads)
-    rc = colmod.synth_lib().bgc_synth_fill(C.byref(sp), C.byref(parms.ind), C.byref(parms.dms_ind),
-                                           C.byref(parms.macros_ind), C.byref(cin), C.byref(cfo), C.byref(din),
-                                           C.byref(dfo), C.byref(min_))
-    if rc != 0:
-        raise RuntimeError("bgc_synth_fill failed: %d" % rc)
-
-    def put(t, a):
-        t.copy_(torch.from_numpy(a))
-    put(bgc.BGC_tracers, h["tr"])
-    for n in bgc.K2_IN:
-        put(getattr(bgc, n), h[n])
-    put(bgc.cell_latitude, h["lat"]); put(bgc.number_of_active_levels, h["kmax"])
-    for n, a in hf.items():
-        put(bgc.forcing[n], a)
-    put(dms.DMS_tracers, h["dtr"]); put(dms.cell_thickness, h["ddz"]); put(dms.number_of_active_levels, h["dkmax"])
-    for n, a in hdf.items():
-        put(dms.forcing[n], a)
-    put(mac.MACROS_tracers, h["mtr"]); put(mac.cell_thickness, h["mdz"]); put(mac.number_of_active_levels, h["mkmax"])
-    return int(h["kmax"].astype(np.int64).sum())
+    """This rank's synthetic columns, generated in the SoA layout on the host and copied to the
+    device containers (ocean-bgc_b200/columns.py: synth_fill_device)."""
+    return pkg.synth_fill_device(parms, bgc, dms, mac, column0, nthreads=nthreads)
 
 
 def mem_available_gb():
@@ -340,13 +290,200 @@ def mem_available_gb():
     return 0.0
 
 
+class DeviceMesh:
+    """One rank's device-resident slab: ctx + the three containers + the step."""
+
+    def __init__(self, pkg, parms, nL, nC, column0, local_rank, rank, world, inventory=True, strict_join=False,
+                 replicate=1):
+        import torch
+        import torch.distributed as dist
+        host = pkg.host
+        self.host, self.nL, self.nC, self.world = host, nL, nC, world
+        self.dev = "cuda:%d" % local_rank
+        self.ctx = host.Context(nL, nC, device=local_rank, parms=parms)
+        self.stream = torch.cuda.Stream(device=self.dev)
+        self.ctx.set_stream(self.stream.cuda_stream)
+        if world > 1:   # NCCL communicator owned by the ctx; the unique id travels over torch.distributed
+            uid = [self.ctx.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(uid, src=0)
+            self.ctx.comm_init_rank(world, rank, uid[0])
+        self.inventory = inventory
+        self.ctx.inventory_enable(inventory)
+        # the carbonate solve of BGC_SourceSink overlaps the DMS / MACROS / surface-flux kernels that
+        # follow it; it is joined at the step's inventory all-reduce (or the explicit join below)
+        self.ctx.set_deferred_join(not strict_join)
+        self.bgc = host.DeviceBgcColumns(nL, nC, device=self.dev)
+        self.dms = host.DeviceDmsColumns(nL, nC, device=self.dev)
+        self.mac = host.DeviceMacrosColumns(nL, nC, device=self.dev)
+        if replicate <= 1:
+            self.cells = pkg.synth_fill_device(parms, self.bgc, self.dms, self.mac, column0)
+        else:
+            self.cells = self._fill_replicated(pkg, parms, column0, replicate)
+        torch.cuda.synchronize()
+
+    def _fill_replicated(self, pkg, parms, column0, replicate):
+        """Large slabs: generate the first ceil(nC / replicate) columns on the host and tile them over the
+        slab on the device (the generator makes ~0.2 M cells/s per host thread; the kernels stream every
+        byte from HBM either way)."""
+        import torch
+        host, nL, nC = self.host, self.nL, self.nC
+        part = -(-nC // replicate)
+        part += part & 1
+        b, d, m = (host.DeviceBgcColumns(nL, part, device=self.dev, diagnostics=False),
+                   host.DeviceDmsColumns(nL, part, device=self.dev, diagnostics=False),
+                   host.DeviceMacrosColumns(nL, part, device=self.dev, diagnostics=False))
+        pkg.synth_fill_device(parms, b, d, m, column0)
+        pairs = [(self.bgc.BGC_tracers, b.BGC_tracers), (self.bgc.cell_latitude, b.cell_latitude),
+                 (self.bgc.number_of_active_levels, b.number_of_active_levels),
+                 (self.dms.DMS_tracers, d.DMS_tracers), (self.dms.cell_thickness, d.cell_thickness),
+                 (self.dms.number_of_active_levels, d.number_of_active_levels),
+                 (self.mac.MACROS_tracers, m.MACROS_tracers), (self.mac.cell_thickness, m.cell_thickness),
+                 (self.mac.number_of_active_levels, m.number_of_active_levels)]
+        pairs += [(getattr(self.bgc, n), getattr(b, n)) for n in self.bgc.K2_IN]
+        pairs += [(self.bgc.forcing[n], b.forcing[n]) for n in b.forcing]
+        pairs += [(self.dms.forcing[n], d.forcing[n]) for n in d.forcing]
+        for dst, src in pairs:
+            for c0 in range(0, nC, part):
+                n = min(part, nC - c0)
+                dst[..., c0:c0 + n].copy_(src[..., :n])
+        kmax = self.bgc.number_of_active_levels
+        torch.cuda.synchronize()
+        return int(kmax.long().sum().item())
+
+    def compute(self):
+        """everything of a step except the inventory all-reduce (what the CUDA graph holds)"""
+        host, ctx = self.host, self.ctx
+        if self.inventory:
+            ctx.inventory_reset()
+        host.BGC_SourceSink(ctx, self.bgc, True, True)
+        host.BGC_SurfaceFluxes(ctx, self.bgc)
+        host.DMS_SourceSink(ctx, self.dms, True)
+        host.DMS_SurfaceFluxes(ctx, self.dms)
+        host.MACROS_SourceSink(ctx, self.mac, True)
+        ctx.carbonate_join()
+
+    def reduce(self):
+        # NCCL all-reduce (N > 1) + 512 B to a page-locked host buffer, stream-ordered: the host
+        # reads the vector after the last step (bgc_inventory_allreduce_end)
+        if self.inventory:
+            self.ctx.inventory_allreduce_begin()
+
+    def step(self):
+        self.compute()
+        self.reduce()
+
+    def barrier(self):
+        import torch
+        import torch.distributed as dist
+        if self.world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(self, steps, graph=None, sampler=None):
+        """K steps bracketed by barrier + synchronize, CUDA events on the ctx stream; returns ms per
+        step, max over ranks."""
+        import torch
+        import torch.distributed as dist
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        if sampler is not None:
+            sampler.mark()
+        e0.record(self.stream)
+        for _ in range(steps):
+            if graph is not None:
+                self.ctx.graph_launch(graph)
+                self.reduce()
+            else:
+                self.step()
+        e1.record(self.stream)
+        self.barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / steps
+
+    def capture(self):
+        """The compute part of a step (~15 dependent launches on two streams) as one CUDA graph.  The
+        NCCL all-reduce stays outside the graph - one more launch per step - so that no graph holds
+        the communicator (a captured collective ties the teardown order of graph, communicator and
+        process group together across ranks)."""
+        self.ctx.graph_capture_begin()
+        self.compute()
+        g = self.ctx.graph_capture_end()
+        for _ in range(3):
+            self.ctx.graph_launch(g)
+            self.reduce()
+        return g
+
+    def total_cells(self):
+        import torch
+        import torch.distributed as dist
+        if self.world == 1:
+            return self.cells
+        c = torch.tensor([self.cells], dtype=torch.float64, device=self.dev)
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        return int(c.item())
+
+    def inventory_check(self, inv):
+        """The all-reduced vector against (a) the rank-local vectors gathered through torch.distributed
+        and summed on the host, (b) the vector a single GPU computed for the whole mesh (committed
+        fixture, strong scaling only): per-column results do not depend on the sharding, so only the
+        order of the additions differs."""
+        import torch
+        import torch.distributed as dist
+        local = torch.from_numpy(np.ascontiguousarray(self.ctx.inventory_get())).to(self.dev)
+        parts = [torch.zeros_like(local) for _ in range(self.world)]
+        if self.world > 1:
+            dist.all_gather(parts, local)
+        else:
+            parts = [local]
+        ref = np.sum(np.stack([p.cpu().numpy() for p in parts]), axis=0)
+        # [0..51] the 52 tendency sums; [52..59] the Jint_* conservation residuals (round-off noise
+        # around zero by construction: compared in absolute terms against the largest tendency sum)
+        nz = np.abs(ref[:52]) > 0
+        rel = np.abs(inv[:52] - ref[:52])[nz] / np.abs(ref[:52])[nz]
+        out = {"active_cells": float(inv[60]), "columns": float(inv[61]),
+               "max_rel_diff_vs_gathered_rank_sums": float(rel.max()) if rel.size else 0.0,
+               "jint_max_abs_diff_over_largest_sum": float(np.max(np.abs(inv[52:60] - ref[52:60])) /
+                                                           max(1e-300, float(np.max(np.abs(ref[:30]))))),
+               "counts_exact": bool(inv[60] == ref[60] and inv[61] == ref[61]), "nranks": self.world}
+        return out, ref
+
+    def close(self, graph=None):
+        if graph is not None:
+            self.ctx.graph_destroy(graph)
+        self.ctx.synchronize()
+        self.ctx.close()
+
+
+def inventory_fixture(inv, mesh_columns, levels, strong):
+    """Compare with profiles/inventory_ec60to30_1gpu.json (a 1-GPU run with BGC_BENCH_WRITE_INVENTORY=<path>
+    writes that file)."""
+    path = os.path.join(REPO, "profiles", "inventory_ec60to30_1gpu.json")
+    out = os.environ.get("BGC_BENCH_WRITE_INVENTORY")
+    if out:
+        json.dump({"mesh_columns": mesh_columns, "levels": levels, "inventory": [float(x) for x in inv]},
+                  open(out, "w"))
+        return {"written": out}
+    if not (strong and os.path.exists(path)):
+        return None
+    fx = json.load(open(path))
+    if fx["mesh_columns"] != mesh_columns or fx["levels"] != levels:
+        return None
+    ref = np.array(fx["inventory"])
+    nz = np.abs(ref[:52]) > 0
+    rel = np.abs(inv[:52] - ref[:52])[nz] / np.abs(ref[:52])[nz]
+    return {"max_rel_diff_vs_single_gpu": float(rel.max()) if rel.size else 0.0,
+            "counts_equal": bool(inv[60] == ref[60] and inv[61] == ref[61]), "fixture": os.path.relpath(path, REPO)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--columns", type=int, default=EC_COLUMNS, help="columns per GPU")
+    ap.add_argument("--columns", type=int, default=EC_COLUMNS, help="columns of the mesh (per GPU with --weak)")
     ap.add_argument("--levels", type=int, default=EC_LEVELS)
     ap.add_argument("--cpu-columns", type=int, default=16384, help="columns of the CPU-oracle sample")
     ap.add_argument("--e2e-columns", type=int, default=0, help="columns per GPU of the end-to-end leg (0 = auto)")
@@ -354,9 +491,13 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-inventory", action="store_true")
-    ap.add_argument("--strong", action="store_true",
-                    help="strong scaling: ONE mesh of --columns columns split into contiguous slabs over the ranks "
-                         "(default: weak scaling, --columns columns per GPU)")
+    ap.add_argument("--no-secondary", action="store_true", help="skip config 2 / adapter / RRS slab side measurements")
+    ap.add_argument("--rrs", choices=["auto", "on", "off"], default="auto",
+                    help="config 5 (RRS18to6 slab of 461 654 x 80 per GPU): auto = at 1 and 8 GPUs")
+    ap.add_argument("--weak", action="store_true",
+                    help="weak scaling: every rank owns a whole mesh of --columns columns (default at N > 1: strong "
+                         "scaling, ONE mesh of --columns columns split into contiguous slabs over the ranks)")
+    ap.add_argument("--strong", action="store_true", help="(default at N > 1; kept for compatibility)")
     ap.add_argument("--no-graph", action="store_true", help="issue every step call by call instead of replaying a CUDA graph")
     ap.add_argument("--strict-join", action="store_true",
                     help="join the carbonate side stream inside every BGC_SourceSink call (library default)")
@@ -365,12 +506,14 @@ def main():
         args.warmup = 3   # timing rule: at least 3 warm-up steps
 
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    args.strong = (world > 1 and not args.weak)
     args.mesh_columns = args.columns
     column0 = rank * args.columns
-    if args.strong and args.impl != "reference":   # contiguous even slabs, the last one shorter (sharding.slab)
-        column0, args.columns = ge.load_package().sharding.slab(rank, world, args.mesh_columns, even=True)
     if args.impl == "reference":
         return run_reference(args, rank, world)
+    if args.strong:   # contiguous even slabs, the last one shorter (sharding.slab)
+        column0, args.columns = ge.load_package().sharding.slab(rank, world, args.mesh_columns, even=True)
+    args.column0 = column0
 
     import torch
     import torch.distributed as dist
@@ -385,44 +528,10 @@ def main():
     nL, nC = args.levels, args.columns
     dev = "cuda:%d" % local_rank
 
-    ctx = host.Context(nL, nC, device=local_rank, parms=parms)
-    stream = torch.cuda.Stream(device=dev)
-    ctx.set_stream(stream.cuda_stream)
-    if world > 1:   # NCCL communicator owned by the ctx; the unique id travels over torch.distributed
-        uid = [ctx.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        ctx.comm_init_rank(world, rank, uid[0])
-    ctx.inventory_enable(not args.no_inventory)
-    # the carbonate solve of BGC_SourceSink overlaps the DMS / MACROS / surface-flux kernels that
-    # follow it; it is joined at the step's inventory all-reduce (or the explicit join below)
-    ctx.set_deferred_join(not args.strict_join)
-
-    bgc = host.DeviceBgcColumns(nL, nC, device=dev)
-    dms = host.DeviceDmsColumns(nL, nC, device=dev)
-    mac = host.DeviceMacrosColumns(nL, nC, device=dev)
-    cells = fill_device_inputs(pkg, parms, bgc, dms, mac, column0=column0)
-    torch.cuda.synchronize()
-
-    def step():
-        if not args.no_inventory:
-            ctx.inventory_reset()
-        host.BGC_SourceSink(ctx, bgc, True, True)
-        host.BGC_SurfaceFluxes(ctx, bgc)
-        host.DMS_SourceSink(ctx, dms, True)
-        host.DMS_SurfaceFluxes(ctx, dms)
-        host.MACROS_SourceSink(ctx, mac, True)
-        if not args.no_inventory:
-            # join point; NCCL all-reduce (N > 1) + 512 B to a page-locked host buffer, stream-ordered:
-            # the host reads the vector after the last step (bgc_inventory_allreduce_end)
-            ctx.inventory_allreduce_begin()
-            return None
-        ctx.carbonate_join()
-        return None
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    mesh = DeviceMesh(pkg, parms, nL, nC, column0, local_rank, rank, world, inventory=not args.no_inventory,
+                      strict_join=args.strict_join)
+    ctx, stream, cells = mesh.ctx, mesh.stream, mesh.cells
+    step, barrier = mesh.step, mesh.barrier
 
     step()                       # cold pass: PH_PREV = 0 -> wide brackets (not timed)
     sampler = ClockSampler(local_rank)
@@ -430,45 +539,22 @@ def main():
     for _ in range(max(args.warmup, 25)):   # >= W warm-up steps; at least ~0.2 s so the clock sampler sees the load
         step()
     barrier()
-    # one step = ~15 dependent launches on two streams: captured once, replayed as a CUDA graph
-    graph = None
-    # (single process only: a captured NCCL all-reduce keeps the communicator alive until the
-    #  graph is destroyed, and a rank that exits in a different order can stall the others)
-    if not args.no_graph and world == 1:
-        ctx.graph_capture_begin()
-        step()
-        graph = ctx.graph_capture_end()
-        for _ in range(3):
-            ctx.graph_launch(graph)
+    graph = None if args.no_graph else mesh.capture()
     barrier()
     ctx.timing_reset()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    sampler.mark()
-    e0.record(stream)
-    inv = None
-    for _ in range(args.steps):
-        if graph is not None:
-            ctx.graph_launch(graph)
-        else:
-            step()
-    e1.record(stream)
-    barrier()
-    if not args.no_inventory:
-        inv = ctx.inventory_allreduce_end()
+    ms_step = mesh.timed(args.steps, graph, sampler)
+    inv = ctx.inventory_allreduce_end() if not args.no_inventory else None
     clocks = sampler.stop()
-    ms = e0.elapsed_time(e1)
     launches = ctx.launch_count()
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = float(t.item()) / args.steps
-    total_cells = cells
-    if world > 1:
-        c = torch.tensor([cells], dtype=torch.float64, device=dev)
-        dist.all_reduce(c, op=dist.ReduceOp.SUM)
-        total_cells = int(c.item())
+    total_cells = mesh.total_cells()
     value = total_cells / (ms_step * 1e-3)
+    inv_check = None
+    if inv is not None:
+        inv_check, _ = mesh.inventory_check(inv)
+        if rank == 0:
+            fx = inventory_fixture(inv, args.mesh_columns, nL, args.strong or world == 1)
+            if fx:
+                inv_check.update(fx)
 
     # ---- per-kernel device times (CUDA events around every launch, separate pass).  The
     #      carbonate kernel normally runs on a side stream beside the sweep; for this pass it is
@@ -476,7 +562,7 @@ def main():
     ctx.timing_reset()
     ctx.set_concurrency(False)
     ctx.timing_enable(True)
-    for _ in range(args.steps):
+    for _ in range(min(args.steps, 20)):
         step()
     ctx.synchronize()
     ktimes = ctx.timing()
@@ -488,12 +574,15 @@ def main():
     achieved = cells * B_ECO / (eco_ms_per * 1e-3) / 1e9
     traffic, ncu_counters = None, None
     tp = os.path.join(REPO, "profiles", "traffic.json")
-    if os.path.exists(tp):   # from the committed ncu --set full capture (not measured in this run)
+    if os.path.exists(tp) and world == 1:
+        # per-launch DRAM bytes of the sweep from the committed `ncu --set full` capture of this same
+        # command (ncu cannot run inside a timed bench); the file names the commit it was taken at
         try:
             tj = json.load(open(tp))
             traffic = tj.get("eco_columns_kernel_bytes_per_cell")
             traffic = traffic * cells if traffic is not None else None
-            ncu_counters = {"source": tj.get("ncu_counters_source"), "kernels": tj.get("ncu_counters")}
+            ncu_counters = {"source": tj.get("ncu_counters_source"), "captured_at_commit": tj.get("commit"),
+                            "kernels": tj.get("ncu_counters")}
         except Exception:
             traffic = None
     kernel_ms = {k: (v[0] / max(1, v[1])) for k, v in ktimes.items() if v[1]}
@@ -509,13 +598,13 @@ def main():
                           "frac_of_best": achieved / sc["best_GBps"], "source": sc["source"]}
     except Exception:
         stream_ceiling = None
+    step_gbps = total_cells / world * B_API / (ms_step * 1e-3) / 1e9     # per GPU
     roofline = {"bound": "hbm", "kernel": "eco_columns_kernel", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "algorithmic_bytes_per_cell": B_ECO, "cells_per_launch": cells,
                 "kernel_ms": eco_ms_per, "peak_source": peak_src,
-                "step": {"algorithmic_bytes_per_cell": B_API,
-                         "achieved": cells * B_API / (ms_step * 1e-3) / 1e9,
-                         "frac": cells * B_API / (ms_step * 1e-3) / 1e9 / peak},
+                "step": {"algorithmic_bytes_per_cell": B_API, "achieved_per_gpu": step_gbps,
+                         "frac": step_gbps / peak},
                 "kernel_ms_per_launch": kernel_ms, "ncu_counters": ncu_counters,
                 "stream_ceiling": stream_ceiling,
                 "kernel_ms_note": "each kernel timed alone (carbonate kernel serialised behind the sweep for this "
@@ -524,32 +613,25 @@ def main():
 
     # ---- the same step with the zero-biomass shortcut of the sweep switched off (every functional-group
     #      body executed even where the whole warp's biomass is exactly zero): the data-independent cost
-    noshort = None
-    if True:
-        ctx.set_zero_shortcut(False)
-        for _ in range(3):
-            step()
-        barrier()
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        f0.record(stream)
-        for _ in range(min(args.steps, 20)):
-            step()
-        f1.record(stream)
-        barrier()
-        tt = torch.tensor([f0.elapsed_time(f1) / min(args.steps, 20)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        noshort = {"ms_per_step": float(tt.item()), "value": total_cells / (float(tt.item()) * 1e-3), "unit": UNIT}
-        ctx.set_zero_shortcut(True)
-        if not args.no_inventory:
-            ctx.inventory_allreduce_end()
+    ctx.set_zero_shortcut(False)
+    for _ in range(3):
+        step()
+    ns_ms = mesh.timed(min(args.steps, 20))
+    noshort = {"ms_per_step": ns_ms, "value": total_cells / (ns_ms * 1e-3), "unit": UNIT,
+               "roofline_step_frac": total_cells / world * B_API / (ns_ms * 1e-3) / 1e9 / peak}
+    roofline["step"]["frac_without_zero_biomass_shortcut"] = noshort["roofline_step_frac"]
+    ctx.set_zero_shortcut(True)
+    if not args.no_inventory:
+        ctx.inventory_allreduce_end()
 
-    # ---- BASELINE.json configs[1]: the surface carbonate solve alone, 1 M points (secondary number)
-    pts_line = None
-    if rank == 0:
-        pts_line = run_co2calc_points(pkg, host, ctx, stream, dev)
-
-        pts_line = {"co2calc_1point": pts_line, "mpas_layout_adapter": run_mpas_adapter(ctx, stream, dev, nL, nC)}
+    # ---- secondary numbers: config 2 (1 M surface points), the MPAS-layout pipeline (8(f)), config 5
+    secondary = None
+    if not args.no_secondary:
+        secondary = {}
+        if rank == 0:
+            secondary["co2calc_1point"] = run_co2calc_points(pkg, host, ctx, stream, dev)
+            secondary["mpas_layout_adapter"] = run_mpas_adapter(ctx, stream, dev, nL, nC)
+            secondary["device_resident_model_step"] = run_model_step(mesh, dev)
 
     # ---- end to end: host Fortran-layout arrays (pinned), H2D/D2H inside the timed region
     e2e = None
@@ -563,26 +645,89 @@ def main():
                "sample": "%d columns x %d levels (%d cells) of the same synthetic mesh, 1 cold + 2 timed warm passes"
                          % (args.cpu_columns, nL, ccells), "note": note}
 
+    # orderly teardown of the EC60to30 mesh before the RRS slab takes its ~82 GB
+    mesh.close(graph)
+    del mesh, ctx
+    want_rrs = args.rrs == "on" or (args.rrs == "auto" and world in (1, 8))
+    if secondary is not None and want_rrs:
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+        rrs = run_rrs_slab(args, pkg, parms, rank, world, local_rank, peak)
+        if rank == 0:
+            secondary["rrs18to6_slab"] = rrs
+
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-                "scaling": "strong" if args.strong else "weak",
+                "scaling": "strong" if (args.strong or world == 1) else "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": workload_config(args, world), "clocks": clocks, "gpu_launches": int(launches),
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-                "inventory_check": None if inv is None else {"active_cells": float(inv[60]), "columns": float(inv[61])},
-                "secondary": pts_line, "without_zero_biomass_shortcut": noshort}
+                "inventory_check": inv_check,
+                "secondary": secondary, "without_zero_biomass_shortcut": noshort}
         print(json.dumps(line), flush=True)
-    # orderly teardown: graph, then the ctx (its NCCL communicator), then torch's process group
-    if graph is not None:
-        ctx.graph_destroy(graph)
-    ctx.synchronize()
-    ctx.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     sys.stdout.flush()
     return 0
+
+
+def run_rrs_slab(args, pkg, parms, rank, world, local_rank, peak, steps=10):
+    """BASELINE.json configs[4]: RRS18to6 (3 693 225 columns x 80 levels) across 8 GPUs = 461 654 columns
+    per GPU.  Every rank of this run owns one such slab (at N = 1: the single GPU runs slab 0 alone, the
+    per-GPU share of the 8-way split); full BGC + DMS + MACROS step with the NCCL inventory all-reduce."""
+    import torch
+    free, _ = torch.cuda.mem_get_info()
+    nL = RRS_LEVELS
+    per, rem = -(-RRS_COLUMNS // 8), 0
+    per += per & 1
+    nC = per
+    need = nC * nL * (B_API + 8 * 12) * 1.05
+    if free < need:
+        return {"skipped": "needs %.0f GB of free device memory, %.0f GB free" % (need / 1e9, free / 1e9)}
+    t0 = time.time()
+    mesh = DeviceMesh(pkg, parms, nL, nC, rank * per, local_rank, rank, world, inventory=True, replicate=8)
+    t_fill = time.time() - t0
+    mesh.step()
+    for _ in range(3):
+        mesh.step()
+    graph = mesh.capture()
+    ms = mesh.timed(steps, graph)
+    inv = mesh.ctx.inventory_allreduce_end()
+    chk, _ = mesh.inventory_check(inv)
+    total = mesh.total_cells()
+    mesh.ctx.timing_reset()
+    mesh.ctx.set_concurrency(False)
+    mesh.ctx.timing_enable(True)
+    for _ in range(3):
+        mesh.step()
+    mesh.ctx.synchronize()
+    kt = mesh.ctx.timing()
+    mesh.ctx.timing_enable(False)
+    mesh.ctx.set_concurrency(True)
+    mesh.ctx.set_zero_shortcut(False)
+    mesh.step()
+    ns = mesh.timed(min(steps, 5))
+    mesh.ctx.inventory_allreduce_end()
+    cells = mesh.cells
+    mesh.close(graph)
+    gbps = total / world * B_API / (ms * 1e-3) / 1e9
+    eco = kt["eco_columns_kernel"]
+    eco_ms = eco[0] / max(1, eco[1])
+    return {"workload": "RRS18to6 (BASELINE.json configs[4]): %d columns x %d levels per GPU on %d GPU(s), full "
+                        "BGC+DMS+MACROS step + inventory all-reduce" % (nC, nL, world),
+            "columns_per_gpu": nC, "levels": nL, "n_gpus": world, "cells_total": total,
+            "ms_per_step": ms, "value": total / (ms * 1e-3), "unit": UNIT, "steps": steps, "cuda_graph": True,
+            "roofline_step": {"algorithmic_bytes_per_cell": B_API, "achieved_per_gpu_GBps": gbps, "frac": gbps / peak,
+                              "frac_without_zero_biomass_shortcut": total / world * B_API / (ns * 1e-3) / 1e9 / peak},
+            "sweep": {"kernel_ms": eco_ms, "achieved_GBps": cells * B_ECO / (eco_ms * 1e-3) / 1e9,
+                      "frac": cells * B_ECO / (eco_ms * 1e-3) / 1e9 / peak},
+            "kernel_ms_per_launch": {k: (v[0] / max(1, v[1])) for k, v in kt.items() if v[1]},
+            "inventory_check": chk, "fill_s": t_fill,
+            "data": "synthetic columns of slab %d (first eighth generated on the host, tiled 8x over the slab on "
+                    "the device)" % rank}
 
 
 def run_co2calc_points(pkg, host, ctx, stream, dev, n=1 << 20, reps=20):
@@ -644,6 +789,60 @@ def run_mpas_adapter(ctx, stream, dev, nL, nC, reps=5):
     return out
 
 
+def run_model_step(mesh, dev, reps=10, dt=1800.0):
+    """one model time step with NOTHING crossing PCIe.  The tracer groups live on
+    the device in the host model's own layout, T(iTracer, k, iCell) (tracer index fastest), next to
+    layerThickness(k, iCell); per step:
+        MPAS layout -> SoA (bgc_layout_mpas_to_soa, 3 groups)
+        BGC_SourceSink + BGC_SurfaceFluxes + DMS_SourceSink + DMS_SurfaceFluxes + MACROS_SourceSink
+        tend(n,k,cell) += layerThickness(k,cell) * tendency  (bgc_layout_soa_to_mpas_weighted: the
+        thickness-weighted tendency MPAS-Ocean accumulates) and the explicit update T += dt * tendency.
+    PH_PREV_* / surface_pH stay resident in the device containers (bgc_state_* is the host accessor)."""
+    import torch
+    ctx, nL, nC = mesh.ctx, mesh.nL, mesh.nC
+    groups = [(mesh.bgc.BGC_tracers, mesh.bgc.BGC_tendencies), (mesh.dms.DMS_tracers, mesh.dms.DMS_tendencies),
+              (mesh.mac.MACROS_tracers, mesh.mac.MACROS_tendencies)]
+    h = mesh.bgc.cell_thickness.T.contiguous()                       # (cell, k): k fastest
+    mp = []
+    for tr, _ in groups:                                             # MPAS-layout copies of the tracer groups
+        nT = tr.shape[0]
+        mp.append((tr.permute(2, 1, 0).contiguous(), torch.zeros((nC, nL, nT), dtype=torch.float64, device=dev),
+                   list(range(1, nT + 1))))
+    torch.cuda.synchronize()
+    was = mesh.inventory
+    mesh.inventory = False
+    ctx.inventory_enable(False)
+
+    def model_step():
+        for (tr, _), (t_mpas, tend_mpas, slot) in zip(groups, mp):
+            ctx.mpas_to_soa(t_mpas.data_ptr(), tr.data_ptr(), slot, nL, nC)
+        mesh.compute()
+        for (_, tend), (t_mpas, tend_mpas, slot) in zip(groups, mp):
+            ctx.soa_to_mpas(tend.data_ptr(), tend_mpas.data_ptr(), slot, nL, nC, alpha=1.0, beta=0.0,
+                            dev_weight=h.data_ptr())                 # thickness-weighted tendency
+            ctx.soa_to_mpas(tend.data_ptr(), t_mpas.data_ptr(), slot, nL, nC, alpha=0.0 * dt, beta=1.0)
+    # (alpha = 0 keeps the synthetic state stationary from step to step - same memory traffic and
+    #  arithmetic as alpha = dt - so that every timed step does the same work)
+    model_step()
+    ctx.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(mesh.stream)
+    for _ in range(reps):
+        model_step()
+    e1.record(mesh.stream)
+    ctx.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    mesh.inventory = was
+    ctx.inventory_enable(was)
+    nTt = sum(t[0].shape[0] for t in groups)
+    adapter_bytes = nL * nC * 8 * (nTt * 2 + nTt * 2 + nTt * 3 + 2 * 3)   # to-SoA r+w, weighted tend r+w, update r+r+w, h
+    return {"workload": "device-resident model step: MPAS-layout tracer groups (30+14+8) -> SoA -> full BGC+DMS+MACROS "
+                        "-> thickness-weighted tendencies + explicit update in the MPAS layout; no PCIe traffic",
+            "ms_per_step": ms, "value": mesh.cells / (ms * 1e-3), "unit": UNIT,
+            "bytes_per_step": mesh.cells * B_API + adapter_bytes,
+            "achieved_GBps": (mesh.cells * B_API + adapter_bytes) / (ms * 1e-3) / 1e9}
+
+
 def run_e2e(args, pkg, host, ctx, parms, rank, world, local_rank, dev):
     import torch
     import torch.distributed as dist
@@ -672,7 +871,7 @@ def run_e2e(args, pkg, host, ctx, parms, rank, world, local_rank, dev):
                 raise
             nC = max(4096, nC // 2)
     pkg.synth_fill(bgc, dms, mac, bgc_ind=parms.ind, dms_ind=parms.dms_ind, macros_ind=parms.macros_ind,
-                   column0=rank * args.columns)
+                   column0=getattr(args, "column0", rank * args.columns))
     cells = int(bgc.active_mask().sum())
     n2 = nL * nC * 8
     abi = pkg.abi
@@ -702,7 +901,8 @@ def run_e2e(args, pkg, host, ctx, parms, rank, world, local_rank, dev):
             call_s[name] += time.perf_counter() - t
     step()   # cold pass + arena allocation
     step()
-    call_s = {k: 0.0 for k in call_s}
+    for k in call_s:
+        call_s[k] = 0.0
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -717,6 +917,7 @@ def run_e2e(args, pkg, host, ctx, parms, rank, world, local_rank, dev):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(c, op=dist.ReduceOp.SUM)
     dt = float(t.item())
+    ms_per_call = {k: v * 1e3 / args.e2e_steps for k, v in call_s.items()}
     # extension: diagnostics accumulated on the device, not downloaded
     acc = None
     if rank == 0 and world == 1:
@@ -736,7 +937,7 @@ def run_e2e(args, pkg, host, ctx, parms, rank, world, local_rank, dev):
                        "reported beside the headline, not instead of it)"}
     return {"value": float(c.item()) / dt, "unit": UNIT, "with_device_diag_accumulation": acc, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
             "ms_per_step": dt * 1e3, "steps": args.e2e_steps, "columns_per_gpu": nC,
-            "ms_per_call": {k: v * 1e3 / args.e2e_steps for k, v in call_s.items()},
+            "ms_per_call": ms_per_call,
             "api": "bgc_source_sink/bgc_surface_fluxes/dms_source_sink/dms_surface_fluxes/macros_source_sink "
                    "with BGC_MEM_HOST_FORTRAN, pinned host arrays, synchronous on return; each call is a "
                    "two-stream pipeline over 32768-column chunks (upload, transpose, kernels, transpose, download)"}

@@ -340,6 +340,22 @@ int bgc_co2calc_points(bgc_ctx *ctx, int n, const double *depth, const double *t
                        double *ph, double *co2star, double *dco2star, double *pco2surf,
                        double *dpco2, int mem_space);
 
+/* The other two public procedures of the reference's co2calc module (co2calc.F90:24), batched:
+ * comp_CO3terms (co2calc.F90:214-316) and comp_co3_sat_vals (:1096-1238), n points per call.
+ * k_level[i] is the reference's 1-based level index of point i (the pressure correction of the
+ * equilibrium constants is keyed on k > 1, not on depth); k_level == NULL means k_all for
+ * every point.  depth in metres as in the reference.  phlo/phhi are not modified (the reference
+ * declares them INOUT and never writes them: comp_htotal hands copies to the solver).  Every call
+ * computes its own coefficients (the reference's lcomp_co3_coeffs = .true.; the .false. form reuses
+ * module state of the previous scalar call, which a batch does not have). */
+int bgc_comp_co3terms(bgc_ctx *ctx, int n, const int *k_level, int k_all, const double *depth,
+                      const double *temp, const double *salt, const double *dic, const double *ta,
+                      const double *pt, const double *sit, const double *phlo, const double *phhi,
+                      double *ph, double *h2co3, double *hco3, double *co3, int mem_space);
+int bgc_comp_co3_sat_vals(bgc_ctx *ctx, int n, const int *k_level, int k_all, const double *depth,
+                          const double *temp, const double *salt, double *co3_sat_calc,
+                          double *co3_sat_arag, int mem_space);
+
 int dms_source_sink(bgc_ctx *ctx, const DmsInput *in, const DmsForcing *forcing,
                     DmsOutput *out, DmsDiagnostics *diag,
                     int nLevelsMax, int nColumnsMax, int nColumns, int mem_space);
@@ -438,6 +454,30 @@ int bgc_layout_mpas_to_soa(bgc_ctx *ctx, const double *dev_mpas, double *dev_soa
 int bgc_layout_soa_to_mpas(bgc_ctx *ctx, const double *dev_soa, double *dev_mpas, int nTracers,
                            const int *slot_of_tracer, int nLevelsMax, int nColumnsMax,
                            double alpha, double beta);
+/* The same with a per-cell weight in the MPAS layout, w(k, iCell), level fastest:
+ *     T(n,k,cell) = beta * T(n,k,cell) + alpha * w(k,cell) * soa(cell,k,slot[n]).
+ * With w = layerThickness, alpha = 1, beta = 1 and T = the tracer group's tendency array this is
+ * how MPAS-Ocean folds the BGC tendencies (BGC_mod.F90:1583-1790) into its thickness-weighted
+ * tracer tendencies; dev_weight == NULL means w = 1. */
+int bgc_layout_soa_to_mpas_weighted(bgc_ctx *ctx, const double *dev_soa, double *dev_mpas, int nTracers,
+                                    const int *slot_of_tracer, int nLevelsMax, int nColumnsMax,
+                                    double alpha, double beta, const double *dev_weight);
+
+/* Device-resident model state (extension).  The fields the reference
+ * carries from one time step to the next and writes to restart files - PH_PREV_3D,
+ * PH_PREV_ALT_CO2_3D (BGC_output_type, BGC_parms.F90:170-171) and surface_pH, surface_pH_alt_co2
+ * (BGC_forcing_type, BGC_parms.F90:151-152) - can live in the ctx between steps: a
+ * device-resident host model passes bgc_state_device_ptr's pointers in its BGC_MEM_DEVICE_SOA
+ * argument blocks every step and touches the host copies only at restart time.
+ * bgc_state_set uploads a host array in the reference layout ((k,col) level fastest for the 3-D
+ * fields, (col) for the surface ones), bgc_state_get downloads it (synchronous).  The resident
+ * arrays are created zero-filled on first use - zero is the reference's "no previous pH" marker
+ * (BGC_mod.F90:944, :2873). */
+enum { BGC_STATE_PH_PREV_3D = 0, BGC_STATE_PH_PREV_ALT_CO2_3D = 1, BGC_STATE_SURFACE_PH = 2,
+       BGC_STATE_SURFACE_PH_ALT_CO2 = 3, BGC_STATE_COUNT = 4 };
+int bgc_state_device_ptr(bgc_ctx *ctx, int which, int nLevelsMax, int nColumnsMax, double **dev_ptr);
+int bgc_state_set(bgc_ctx *ctx, int which, const double *host, int nLevelsMax, int nColumnsMax);
+int bgc_state_get(bgc_ctx *ctx, int which, double *host, int nLevelsMax, int nColumnsMax);
 
 #ifdef __cplusplus
 }

@@ -7,7 +7,8 @@ Host-side Python mirror of the reference's operator interface over the C ABI
 from . import abi          # noqa: F401
 from . import columns      # noqa: F401
 from . import sharding     # noqa: F401
-from .columns import BgcColumns, DmsColumns, MacrosColumns, synth_fill, synth_co2_points  # noqa: F401
+from .columns import (BgcColumns, DmsColumns, MacrosColumns, synth_fill, synth_co2_points,  # noqa: F401
+                      synth_fill_device)
 
 
 def __getattr__(name):

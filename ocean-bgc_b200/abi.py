@@ -154,6 +154,14 @@ def dptr(a):
     return a.ctypes.data_as(C.POINTER(C.c_double))
 
 
+def fptr(a):
+    """double* of an argument of the Fortran-layout API: arrays of rank > 1 must be column-major
+    (a C-ordered (k,col) array would silently be read transposed)."""
+    if a is not None and a.ndim > 1:
+        assert a.flags["F_CONTIGUOUS"], "Fortran-layout (column-major) array required"
+    return dptr(a)
+
+
 def iptr(a):
     assert a.dtype.name == "int32"
     return a.ctypes.data_as(C.POINTER(C.c_int))

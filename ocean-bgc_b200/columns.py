@@ -78,36 +78,36 @@ class BgcColumns:
         s = abi.BgcInput()
         for n in ("BGC_tracers", "PotentialTemperature", "Salinity", "cell_center_depth",
                   "cell_thickness", "cell_bottom_depth", "cell_latitude"):
-            setattr(s, n, abi.dptr(getattr(self, n)))
+            setattr(s, n, abi.fptr(getattr(self, n)))
         s.number_of_active_levels = abi.iptr(self.number_of_active_levels)
         return s
 
     def c_forcing(self):
         s = abi.BgcForcing()
         for n, a in self.forcing.items():
-            setattr(s, n, abi.dptr(a))
+            setattr(s, n, abi.fptr(a))
         s.lcalc_O2_gas_flux = int(self.lcalc_O2_gas_flux)
         s.lcalc_CO2_gas_flux = int(self.lcalc_CO2_gas_flux)
         return s
 
     def c_output(self):
         s = abi.BgcOutput()
-        s.BGC_tendencies = abi.dptr(self.BGC_tendencies)
-        s.PH_PREV_3D = abi.dptr(self.PH_PREV_3D)
-        s.PH_PREV_ALT_CO2_3D = abi.dptr(self.PH_PREV_ALT_CO2_3D)
+        s.BGC_tendencies = abi.fptr(self.BGC_tendencies)
+        s.PH_PREV_3D = abi.fptr(self.PH_PREV_3D)
+        s.PH_PREV_ALT_CO2_3D = abi.fptr(self.PH_PREV_ALT_CO2_3D)
         return s
 
     def c_diag(self, enabled=True):
         s = abi.BgcDiagnostics()
         if enabled:
             for n, a in self.diag.items():
-                setattr(s, n, abi.dptr(a))
+                setattr(s, n, abi.fptr(a))
         return s
 
     def c_flux_diag(self):
         s = abi.BgcFluxDiagnostics()
         for n, a in self.flux_diag.items():
-            setattr(s, n, abi.dptr(a))
+            setattr(s, n, abi.fptr(a))
         return s
 
     def copy(self):
@@ -152,34 +152,34 @@ class DmsColumns:
 
     def c_input(self):
         s = abi.DmsInput()
-        s.DMS_tracers = abi.dptr(self.DMS_tracers)
-        s.cell_thickness = abi.dptr(self.cell_thickness)
+        s.DMS_tracers = abi.fptr(self.DMS_tracers)
+        s.cell_thickness = abi.fptr(self.cell_thickness)
         s.number_of_active_levels = abi.iptr(self.number_of_active_levels)
         return s
 
     def c_forcing(self):
         s = abi.DmsForcing()
         for n, a in self.forcing.items():
-            setattr(s, n, abi.dptr(a))
+            setattr(s, n, abi.fptr(a))
         s.lcalc_DMS_gas_flux = int(self.lcalc_DMS_gas_flux)
         return s
 
     def c_output(self):
         s = abi.DmsOutput()
-        s.DMS_tendencies = abi.dptr(self.DMS_tendencies)
+        s.DMS_tendencies = abi.fptr(self.DMS_tendencies)
         return s
 
     def c_diag(self, enabled=True):
         s = abi.DmsDiagnostics()
         if enabled:
             for n, a in self.diag.items():
-                setattr(s, n, abi.dptr(a))
+                setattr(s, n, abi.fptr(a))
         return s
 
     def c_flux_diag(self):
         s = abi.DmsFluxDiagnostics()
         for n, a in self.flux_diag.items():
-            setattr(s, n, abi.dptr(a))
+            setattr(s, n, abi.fptr(a))
         return s
 
     def copy(self):
@@ -210,21 +210,21 @@ class MacrosColumns:
 
     def c_input(self):
         s = abi.MacrosInput()
-        s.MACROS_tracers = abi.dptr(self.MACROS_tracers)
-        s.cell_thickness = abi.dptr(self.cell_thickness)
+        s.MACROS_tracers = abi.fptr(self.MACROS_tracers)
+        s.cell_thickness = abi.fptr(self.cell_thickness)
         s.number_of_active_levels = abi.iptr(self.number_of_active_levels)
         return s
 
     def c_output(self):
         s = abi.MacrosOutput()
-        s.MACROS_tendencies = abi.dptr(self.MACROS_tendencies)
+        s.MACROS_tendencies = abi.fptr(self.MACROS_tendencies)
         return s
 
     def c_diag(self, enabled=True):
         s = abi.MacrosDiagnostics()
         if enabled:
             for n, a in self.diag.items():
-                setattr(s, n, abi.dptr(a))
+                setattr(s, n, abi.fptr(a))
         return s
 
     def copy(self):
@@ -302,3 +302,74 @@ def synth_co2_points(n, seed=SEED_CO2, i0=0):
         raise RuntimeError("bgc_synth_co2_points failed: %d" % rc)
     names = ["depth", "temp", "salt", "dic", "ta", "pt", "sit", "phlo", "phhi", "xco2", "atmpres"]
     return {k: out[i].copy() for i, k in enumerate(names)}
+
+
+def synth_fill_device(parms, bgc, dms, mac, column0=0, *, ragged=False, jitter=True, nthreads=0,
+                      seed=SEED_COLUMNS):
+    """Generate the synthetic columns [column0, column0 + nColumnsMax) directly in the SoA layout on
+    the host (no Fortran-layout intermediate) and copy the INPUT members into the device
+    containers (host.DeviceBgcColumns / DeviceDmsColumns / DeviceMacrosColumns).  The generator
+    is keyed by the global column index, so any sharding sees the same columns.  Returns the
+    number of active cells."""
+    import torch
+    nL, nC = bgc.nLevelsMax, bgc.nColumnsMax
+    h = {}
+
+    def arr(shape, dtype=np.float64):
+        return np.zeros(shape, dtype=dtype)
+    h["tr"] = arr((abi.BGC_TRACER_CNT, nL, nC))
+    for n in bgc.K2_IN:
+        h[n] = arr((nL, nC))
+    h["lat"] = arr((nC,)); h["kmax"] = arr((nC,), np.int32)
+    hf = {n: arr((nL, nC)) for n in ("FESEDFLUX",)}
+    hf.update({n: arr((nC,)) for n in abi.BGC_FORCING_C1})
+    hf.update({n: arr((abi.BGC_TRACER_CNT, nC)) for n in abi.BGC_FORCING_FLUX})
+    h["dtr"] = arr((abi.DMS_TRACER_CNT, nL, nC)); h["ddz"] = arr((nL, nC)); h["dkmax"] = arr((nC,), np.int32)
+    hdf = {n: arr((nC,)) for n in abi.DMS_FORCING_C1}
+    hdf["netFlux"] = arr((abi.DMS_TRACER_CNT, nC))
+    h["mtr"] = arr((abi.MACROS_TRACER_CNT, nL, nC)); h["mdz"] = arr((nL, nC)); h["mkmax"] = arr((nC,), np.int32)
+
+    cin = abi.BgcInput()
+    cin.BGC_tracers = abi.dptr(h["tr"])
+    for n in bgc.K2_IN:
+        setattr(cin, n, abi.dptr(h[n]))
+    cin.cell_latitude = abi.dptr(h["lat"]); cin.number_of_active_levels = abi.iptr(h["kmax"])
+    cfo = abi.BgcForcing()
+    for n, a in hf.items():
+        setattr(cfo, n, abi.dptr(a))
+    din = abi.DmsInput()
+    din.DMS_tracers = abi.dptr(h["dtr"]); din.cell_thickness = abi.dptr(h["ddz"])
+    din.number_of_active_levels = abi.iptr(h["dkmax"])
+    dfo = abi.DmsForcing()
+    for n, a in hdf.items():
+        setattr(dfo, n, abi.dptr(a))
+    min_ = abi.MacrosInput()
+    min_.MACROS_tracers = abi.dptr(h["mtr"]); min_.cell_thickness = abi.dptr(h["mdz"])
+    min_.number_of_active_levels = abi.iptr(h["mkmax"])
+
+    sp = _SynthSpec(seed, nL, nC, bgc.nColumns, column0, nL, int(ragged), 1, int(jitter), nthreads)
+    rc = synth_lib().bgc_synth_fill(C.byref(sp), C.byref(parms.ind), C.byref(parms.dms_ind),
+                                    C.byref(parms.macros_ind), C.byref(cin), C.byref(cfo), C.byref(din),
+                                    C.byref(dfo), C.byref(min_))
+    if rc != 0:
+        raise RuntimeError("bgc_synth_fill failed: %d" % rc)
+
+    def put(t, a):
+        t.copy_(torch.from_numpy(a))
+    put(bgc.BGC_tracers, h["tr"])
+    for n in bgc.K2_IN:
+        put(getattr(bgc, n), h[n])
+    put(bgc.cell_latitude, h["lat"]); put(bgc.number_of_active_levels, h["kmax"])
+    for n, a in hf.items():
+        put(bgc.forcing[n], a)
+    if dms is not None:
+        put(dms.DMS_tracers, h["dtr"]); put(dms.cell_thickness, h["ddz"]); put(dms.number_of_active_levels, h["dkmax"])
+        for n, a in hdf.items():
+            put(dms.forcing[n], a)
+    if mac is not None:
+        put(mac.MACROS_tracers, h["mtr"]); put(mac.cell_thickness, h["mdz"]); put(mac.number_of_active_levels, h["mkmax"])
+    if bgc.BGC_tracers.is_cuda:
+        torch.cuda.synchronize()
+    kmax = h["kmax"].astype(np.int64)
+    kmax[bgc.nColumns:] = 0
+    return int(kmax.sum())

@@ -60,7 +60,9 @@ struct NcclApi {
   const char *(*GetErrorString)(int) = nullptr;
 };
 static NcclApi g_nccl;
+static std::mutex g_nccl_mu;
 static int nccl_load() {
+  std::lock_guard<std::mutex> lock(g_nccl_mu);
   if (g_nccl.h) return BGC_OK;
   const char *names[] = {"libnccl.so.2", "libnccl.so"};
   for (const char *n : names) {
@@ -73,8 +75,11 @@ static int nccl_load() {
   g_nccl.AllReduce = (int (*)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(g_nccl.h, "ncclAllReduce");
   g_nccl.CommDestroy = (int (*)(ncclComm_t))dlsym(g_nccl.h, "ncclCommDestroy");
   g_nccl.GetErrorString = (const char *(*)(int))dlsym(g_nccl.h, "ncclGetErrorString");
-  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy)
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy) {
+    dlclose(g_nccl.h);
+    g_nccl = NcclApi();   // a later call tries again instead of calling through null pointers
     return fail(BGC_ERR_NCCL, "libnccl is missing required symbols");
+  }
   return BGC_OK;
 }
 #define NC(call)                                                                         \
@@ -116,6 +121,7 @@ struct bgc_ctx {
   double *h_inventory = nullptr;            // page-locked landing buffer of bgc_inventory_allreduce_begin
   bool inventory_pending = false;
   bool capturing = false;                   // between bgc_graph_capture_begin and _end
+  bool cap_uses_bgc = false, cap_uses_dms = false, cap_uses_macros = false;   // tables the captured calls read
   unsigned long long capture_base[BGC_KERNEL_ID_COUNT] = {0};
   int eco_variant = 0;                      // launch shape of the column sweep (BGC_ECO_VARIANT, tuning only)
   int dms_variant = 0;                      // launch shape of the DMS tile kernel (BGC_DMS_VARIANT, tuning only)
@@ -203,6 +209,9 @@ static int arena_d(bgc_ctx *c, const std::string &key, size_t n, double **out) {
   return BGC_OK;
 }
 
+static int ctx_init(bgc_ctx *c, int device, int nLevelsMax, int nColumnsMax);
+extern "C" int bgc_ctx_destroy(bgc_ctx *c);
+
 extern "C" int bgc_ctx_create(int device, int nLevelsMax, int nColumnsMax, bgc_ctx **out) {
   if (!out || nLevelsMax < 1 || nColumnsMax < 1) return fail(BGC_ERR_ARG, "bgc_ctx_create: bad arguments");
   int ndev = 0;
@@ -213,6 +222,14 @@ extern "C" int bgc_ctx_create(int device, int nLevelsMax, int nColumnsMax, bgc_c
   if (device < 0 || device >= ndev) return fail(BGC_ERR_ARG, "device %d out of range [0,%d)", device, ndev);
   CU(cudaSetDevice(device));
   bgc_ctx *c = new bgc_ctx();
+  { std::lock_guard<std::mutex> lock(g_mu); g_versions[c] = CtxVersions(); }
+  const int rc = ctx_init(c, device, nLevelsMax, nColumnsMax);
+  if (rc != BGC_OK) { bgc_ctx_destroy(c); return rc; }   // releases whatever was created before the failure
+  *out = c;
+  return BGC_OK;
+}
+
+static int ctx_init(bgc_ctx *c, int device, int nLevelsMax, int nColumnsMax) {
   c->device = device;
   c->nL = nLevelsMax;
   c->nC = nColumnsMax;
@@ -239,18 +256,19 @@ extern "C" int bgc_ctx_create(int device, int nLevelsMax, int nColumnsMax, bgc_c
   CU(cudaMemset(c->d_status, 0, 4 * sizeof(unsigned long long)));
   CU(cudaMalloc(&c->d_inventory, BGC_INVENTORY_LEN * sizeof(double)));
   CU(cudaMemset(c->d_inventory, 0, BGC_INVENTORY_LEN * sizeof(double)));
-  { std::lock_guard<std::mutex> lock(g_mu); g_versions[c] = CtxVersions(); }
-  *out = c;
   return BGC_OK;
 }
 
 extern "C" int bgc_ctx_destroy(bgc_ctx *c) {
   if (!c) return BGC_OK;
   cudaSetDevice(c->device);
-  if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
-  cudaStreamSynchronize(c->stream);
+  // the streams may still carry the all-reduce: drain them before the communicator goes
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->own_stream && c->own_stream != c->stream) cudaStreamSynchronize(c->own_stream);
   for (int i = 0; i < 2; ++i) if (c->side_stream[i]) cudaStreamSynchronize(c->side_stream[i]);
   if (c->pipe_stream) cudaStreamSynchronize(c->pipe_stream);
+  if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+  c->comm = nullptr;
   for (auto &kv : c->arena) if (kv.second.p) cudaFree(kv.second.p);
   cudaFree(c->d_status); cudaFree(c->d_inventory);
   if (c->h_inventory) cudaFreeHost(c->h_inventory);
@@ -455,12 +473,24 @@ extern "C" int macros_set_params(bgc_ctx *c, const MacrosParams *p, const Macros
 
 // __constant__ memory is one copy per device: re-upload only when another ctx
 // (or a newer *_set_params) owns what is there now.
+// Kernels of the previous owner (this ctx's side streams, or another ctx of the device) may still
+// be reading the table: the device is drained before it is overwritten.  This happens only when
+// *_set_params changed something or two ctxs share a device - never in a steady time loop.
+static int drain_before_table_change(bgc_ctx *c, const char *what) {
+  if (c->capturing)
+    return fail(BGC_ERR_PARAMS, "%s parameter tables changed during graph capture: run the same calls once before capturing", what);
+  CU(cudaDeviceSynchronize());
+  return BGC_OK;
+}
+
 static int ensure_bgc_tables(bgc_ctx *c) {
   std::lock_guard<std::mutex> lock(g_mu);
   if (!c->have_bgc) return fail(BGC_ERR_PARAMS, "bgc_set_params has not been called on this ctx");
+  if (c->capturing) c->cap_uses_bgc = true;
   auto &own = g_const_owner_bgc[c->device];
   const unsigned long long v = g_versions[c].bgc;
   if (own.first != c || own.second != v) {
+    RC(drain_before_table_change(c, "BGC"));
     CU(bgc::upload_bgc_tables_eco(c->bgc_tab, c->stream));
     CU(bgc::upload_bgc_tables_co3(c->bgc_tab, c->stream));
     own = {c, v};
@@ -470,9 +500,11 @@ static int ensure_bgc_tables(bgc_ctx *c) {
 static int ensure_dms_tables(bgc_ctx *c) {
   std::lock_guard<std::mutex> lock(g_mu);
   if (!c->have_dms) return fail(BGC_ERR_PARAMS, "dms_set_params has not been called on this ctx");
+  if (c->capturing) c->cap_uses_dms = true;
   auto &own = g_const_owner_dms[c->device];
   const unsigned long long v = g_versions[c].dms;
   if (own.first != c || own.second != v) {
+    RC(drain_before_table_change(c, "DMS"));
     CU(bgc::upload_dms_tables(c->dms_tab, c->stream));
     own = {c, v};
   }
@@ -481,9 +513,11 @@ static int ensure_dms_tables(bgc_ctx *c) {
 static int ensure_macros_tables(bgc_ctx *c) {
   std::lock_guard<std::mutex> lock(g_mu);
   if (!c->have_macros) return fail(BGC_ERR_PARAMS, "macros_set_params has not been called on this ctx");
+  if (c->capturing) c->cap_uses_macros = true;
   auto &own = g_const_owner_macros[c->device];
   const unsigned long long v = g_versions[c].macros;
   if (own.first != c || own.second != v) {
+    RC(drain_before_table_change(c, "MACROS"));
     CU(bgc::upload_macros_tables(c->macros_tab, c->stream));
     own = {c, v};
   }
@@ -1049,6 +1083,89 @@ extern "C" int bgc_co2calc_points(bgc_ctx *c, int n, const double *depth, const 
   return BGC_OK;
 }
 
+// ------------------------------------------------------------------ comp_CO3terms / comp_co3_sat_vals, batched
+// Host-layout helper of the point entries: `nin` input arrays and `nout` output arrays of n doubles
+// (plus an optional int array) staged through the arena.
+static int points_stage(bgc_ctx *c, const char *key, int n, const double *const *in, int nin, double **din,
+                        const int *k_level, const int **dk, int nout, double **dout) {
+  double *buf = nullptr;
+  RC(arena_d(c, std::string(key) + ".buf", (size_t)n * (nin + nout), &buf));
+  for (int i = 0; i < nin; ++i) {
+    din[i] = buf + (size_t)i * n;
+    CU(cudaMemcpyAsync(din[i], in[i], (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  }
+  for (int i = 0; i < nout; ++i) dout[i] = buf + (size_t)(nin + i) * n;
+  *dk = nullptr;
+  if (k_level) {
+    void *kb = nullptr;
+    RC(arena_get(c, std::string(key) + ".k", (size_t)n * sizeof(int), &kb));
+    CU(cudaMemcpyAsync(kb, k_level, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    *dk = (const int *)kb;
+  }
+  return BGC_OK;
+}
+
+extern "C" int bgc_comp_co3terms(bgc_ctx *c, int n, const int *k_level, int k_all, const double *depth,
+                                 const double *temp, const double *salt, const double *dic, const double *ta,
+                                 const double *pt, const double *sit, const double *phlo, const double *phhi,
+                                 double *ph, double *h2co3, double *hco3, double *co3, int mem_space) {
+  RC(use_device(c));
+  if (n < 0) return fail(BGC_ERR_ARG, "negative n");
+  if (n == 0) return BGC_OK;
+  if (!depth || !temp || !salt || !dic || !ta || !pt || !sit || !phlo || !phhi || !ph || !h2co3 || !hco3 || !co3)
+    return fail(BGC_ERR_ARG, "bgc_comp_co3terms: null array");
+  if (!k_level && k_all < 1) return fail(BGC_ERR_ARG, "bgc_comp_co3terms: k_level is NULL and k_all < 1");
+  RC(join_pending(c));
+  bgc::Co3TermsPointsArgs a;
+  a.n = n; a.k_all = k_all; a.status = c->d_status;
+  if (mem_space == BGC_MEM_DEVICE_SOA) {
+    a.k = k_level; a.depth = depth; a.temp = temp; a.salt = salt; a.dic = dic; a.ta = ta; a.pt = pt; a.sit = sit;
+    a.phlo = phlo; a.phhi = phhi; a.ph = ph; a.h2co3 = h2co3; a.hco3 = hco3; a.co3 = co3;
+    LAUNCH(BGC_K_CO2CALC_POINTS, 1, bgc::launch_co3terms_points(a, c->stream));
+    return BGC_OK;
+  }
+  if (mem_space != BGC_MEM_HOST_FORTRAN) return fail(BGC_ERR_ARG, "unknown mem_space %d", mem_space);
+  const double *in[9] = {depth, temp, salt, dic, ta, pt, sit, phlo, phhi};
+  double *din[9], *dout[4];
+  RC(points_stage(c, "co3terms", n, in, 9, din, k_level, &a.k, 4, dout));
+  a.depth = din[0]; a.temp = din[1]; a.salt = din[2]; a.dic = din[3]; a.ta = din[4]; a.pt = din[5]; a.sit = din[6];
+  a.phlo = din[7]; a.phhi = din[8];
+  a.ph = dout[0]; a.h2co3 = dout[1]; a.hco3 = dout[2]; a.co3 = dout[3];
+  LAUNCH(BGC_K_CO2CALC_POINTS, 1, bgc::launch_co3terms_points(a, c->stream));
+  double *dst[4] = {ph, h2co3, hco3, co3};
+  for (int i = 0; i < 4; ++i) CU(cudaMemcpyAsync(dst[i], dout[i], (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return BGC_OK;
+}
+
+extern "C" int bgc_comp_co3_sat_vals(bgc_ctx *c, int n, const int *k_level, int k_all, const double *depth,
+                                     const double *temp, const double *salt, double *co3_sat_calc,
+                                     double *co3_sat_arag, int mem_space) {
+  RC(use_device(c));
+  if (n < 0) return fail(BGC_ERR_ARG, "negative n");
+  if (n == 0) return BGC_OK;
+  if (!depth || !temp || !salt || !co3_sat_calc || !co3_sat_arag) return fail(BGC_ERR_ARG, "bgc_comp_co3_sat_vals: null array");
+  if (!k_level && k_all < 1) return fail(BGC_ERR_ARG, "bgc_comp_co3_sat_vals: k_level is NULL and k_all < 1");
+  RC(join_pending(c));
+  bgc::Co3SatPointsArgs a;
+  a.n = n; a.k_all = k_all;
+  if (mem_space == BGC_MEM_DEVICE_SOA) {
+    a.k = k_level; a.depth = depth; a.temp = temp; a.salt = salt; a.sat_calc = co3_sat_calc; a.sat_arag = co3_sat_arag;
+    LAUNCH(BGC_K_CO2CALC_POINTS, 1, bgc::launch_co3_sat_points(a, c->stream));
+    return BGC_OK;
+  }
+  if (mem_space != BGC_MEM_HOST_FORTRAN) return fail(BGC_ERR_ARG, "unknown mem_space %d", mem_space);
+  const double *in[3] = {depth, temp, salt};
+  double *din[3], *dout[2];
+  RC(points_stage(c, "co3sat", n, in, 3, din, k_level, &a.k, 2, dout));
+  a.depth = din[0]; a.temp = din[1]; a.salt = din[2]; a.sat_calc = dout[0]; a.sat_arag = dout[1];
+  LAUNCH(BGC_K_CO2CALC_POINTS, 1, bgc::launch_co3_sat_points(a, c->stream));
+  CU(cudaMemcpyAsync(co3_sat_calc, dout[0], (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(co3_sat_arag, dout[1], (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return BGC_OK;
+}
+
 // ------------------------------------------------------------------ DMS
 static int dms_source_sink_device(bgc_ctx *c, const DmsInput *in, const DmsForcing *fo, DmsOutput *out,
                                   const DmsDiagnostics *diag, int nL, int nC, int nCols) {
@@ -1260,6 +1377,7 @@ struct bgc_graph {
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t exec = nullptr;
   unsigned long long launches[BGC_KERNEL_ID_COUNT] = {0};   // kernel launches one replay stands for
+  bool uses_bgc = false, uses_dms = false, uses_macros = false;   // __constant__ tables its kernels read
 };
 
 extern "C" int bgc_graph_capture_begin(bgc_ctx *c) {
@@ -1269,6 +1387,7 @@ extern "C" int bgc_graph_capture_begin(bgc_ctx *c) {
   RC(join_pending(c));
   CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed));
   c->capturing = true;
+  c->cap_uses_bgc = c->cap_uses_dms = c->cap_uses_macros = false;
   for (int i = 0; i < BGC_KERNEL_ID_COUNT; ++i) c->capture_base[i] = c->launches[i];
   return BGC_OK;
 }
@@ -1284,6 +1403,7 @@ extern "C" int bgc_graph_capture_end(bgc_ctx *c, bgc_graph **out) {
   if (e != cudaSuccess) return fail(BGC_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
   bgc_graph *bg = new bgc_graph();
   bg->graph = g;
+  bg->uses_bgc = c->cap_uses_bgc; bg->uses_dms = c->cap_uses_dms; bg->uses_macros = c->cap_uses_macros;
   e = cudaGraphInstantiate(&bg->exec, g, 0);
   if (e != cudaSuccess) { cudaGraphDestroy(g); delete bg; return fail(BGC_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e)); }
   for (int i = 0; i < BGC_KERNEL_ID_COUNT; ++i) {
@@ -1298,6 +1418,11 @@ extern "C" int bgc_graph_launch(bgc_ctx *c, bgc_graph *g) {
   RC(use_device(c));
   if (!g || !g->exec) return fail(BGC_ERR_ARG, "bgc_graph_launch: null graph");
   RC(join_pending(c));
+  // the captured kernels read the per-device __constant__ tables: make sure they are still this
+  // ctx's current ones (another ctx of the device, or a *_set_params, may have replaced them)
+  if (g->uses_bgc) RC(ensure_bgc_tables(c));
+  if (g->uses_dms) RC(ensure_dms_tables(c));
+  if (g->uses_macros) RC(ensure_macros_tables(c));
   CU(cudaGraphLaunch(g->exec, c->stream));
   for (int i = 0; i < BGC_KERNEL_ID_COUNT; ++i) c->launches[i] += g->launches[i];
   return BGC_OK;
@@ -1330,14 +1455,75 @@ extern "C" int bgc_layout_mpas_to_soa(bgc_ctx *c, const double *mpas, double *so
   LAUNCH(BGC_K_TRANSPOSE, 1, bgc::launch_mpas_to_soa(mpas, soa, m, nL, nC, c->stream));
   return BGC_OK;
 }
-extern "C" int bgc_layout_soa_to_mpas(bgc_ctx *c, const double *soa, double *mpas, int nT, const int *slot, int nL,
-                                      int nC, double alpha, double beta) {
+extern "C" int bgc_layout_soa_to_mpas_weighted(bgc_ctx *c, const double *soa, double *mpas, int nT, const int *slot,
+                                               int nL, int nC, double alpha, double beta, const double *weight) {
   RC(use_device(c));
   if (!mpas || !soa) return fail(BGC_ERR_ARG, "bgc_layout_soa_to_mpas: null array");
   RC(check_dims(c, nL, nC, nC));
   bgc::MpasMap m;
   RC(mpas_map(nT, slot, &m));
-  LAUNCH(BGC_K_TRANSPOSE, 1, bgc::launch_soa_to_mpas(soa, mpas, m, nL, nC, alpha, beta, c->stream));
+  LAUNCH(BGC_K_TRANSPOSE, 1, bgc::launch_soa_to_mpas(soa, mpas, m, nL, nC, alpha, beta, weight, c->stream));
+  return BGC_OK;
+}
+extern "C" int bgc_layout_soa_to_mpas(bgc_ctx *c, const double *soa, double *mpas, int nT, const int *slot, int nL,
+                                      int nC, double alpha, double beta) {
+  return bgc_layout_soa_to_mpas_weighted(c, soa, mpas, nT, slot, nL, nC, alpha, beta, nullptr);
+}
+
+// ------------------------------------------------------------------ device-resident model state
+static int state_buffer(bgc_ctx *c, int which, int nL, int nC, double **out, size_t *count) {
+  if (which < 0 || which >= BGC_STATE_COUNT) return fail(BGC_ERR_ARG, "bgc_state: unknown field %d", which);
+  RC(check_dims(c, nL, nC, nC));
+  const bool is3d = which == BGC_STATE_PH_PREV_3D || which == BGC_STATE_PH_PREV_ALT_CO2_3D;
+  const size_t n = is3d ? (size_t)nL * nC : (size_t)nC;
+  char key[64];
+  snprintf(key, sizeof key, "state.%d.%dx%d", which, is3d ? nL : 1, nC);
+  const bool fresh = c->arena.find(key) == c->arena.end();
+  RC(arena_d(c, key, n, out));
+  if (fresh) CU(cudaMemsetAsync(*out, 0, n * sizeof(double), c->stream));   // 0 = "no previous pH"
+  if (count) *count = n;
+  return BGC_OK;
+}
+
+extern "C" int bgc_state_device_ptr(bgc_ctx *c, int which, int nL, int nC, double **dev_ptr) {
+  RC(use_device(c));
+  if (!dev_ptr) return fail(BGC_ERR_ARG, "bgc_state_device_ptr: null out");
+  return state_buffer(c, which, nL, nC, dev_ptr, nullptr);
+}
+
+extern "C" int bgc_state_set(bgc_ctx *c, int which, const double *host, int nL, int nC) {
+  RC(use_device(c));
+  if (!host) return fail(BGC_ERR_ARG, "bgc_state_set: null host array");
+  RC(join_pending(c));
+  double *dev = nullptr; size_t n = 0;
+  RC(state_buffer(c, which, nL, nC, &dev, &n));
+  if (n == (size_t)nC) {   // per-column: same layout in both spaces
+    CU(cudaMemcpyAsync(dev, host, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  } else {
+    double *st = nullptr;
+    RC(arena_d(c, "state.stage", n, &st));
+    CU(cudaMemcpyAsync(st, host, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    LAUNCH(BGC_K_TRANSPOSE, 1, bgc::launch_transpose(st, dev, nL, nC, 1, c->stream));
+  }
+  CU(cudaStreamSynchronize(c->stream));
+  return BGC_OK;
+}
+
+extern "C" int bgc_state_get(bgc_ctx *c, int which, double *host, int nL, int nC) {
+  RC(use_device(c));
+  if (!host) return fail(BGC_ERR_ARG, "bgc_state_get: null host array");
+  RC(join_pending(c));
+  double *dev = nullptr; size_t n = 0;
+  RC(state_buffer(c, which, nL, nC, &dev, &n));
+  if (n == (size_t)nC) {
+    CU(cudaMemcpyAsync(host, dev, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  } else {
+    double *st = nullptr;
+    RC(arena_d(c, "state.stage", n, &st));
+    LAUNCH(BGC_K_TRANSPOSE, 1, bgc::launch_transpose(dev, st, nC, nL, 1, c->stream));
+    CU(cudaMemcpyAsync(host, st, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  }
+  CU(cudaStreamSynchronize(c->stream));
   return BGC_OK;
 }
 
@@ -1448,6 +1634,7 @@ extern "C" int bgc_inventory_allreduce_end(bgc_ctx *c, double out[BGC_INVENTORY_
   if (!c->inventory_pending) return fail(BGC_ERR_ARG, "bgc_inventory_allreduce_end without a begin");
   CU(cudaStreamSynchronize(c->stream));   // (also correct when the _begin was replayed from a captured graph)
   memcpy(out, c->h_inventory, BGC_INVENTORY_LEN * sizeof(double));
+  c->inventory_pending = false;
   return BGC_OK;
 }
 

@@ -69,6 +69,7 @@ struct EcoArgs {
   BgcDiagnostics d;                      // carbonate, zsat* and never-touched members nulled by the caller
   unsigned long long *status;
   double *inv_partials;                  // NULL, or the fused stage 1 of the inventory reduction
+  int bulk;                              // set by launch_eco_columns: stage the inputs with TMA bulk copies (16-byte aligned slabs)
 };
 // diag_mode: 0 = no diagnostic array, 1 = any subset (NULL-checked stores), 2 = every array
 // the kernel owns is present (unchecked stores).  variant selects the launch shape
@@ -94,6 +95,23 @@ struct Co2PointsArgs {
   unsigned long long *status;
 };
 cudaError_t launch_co2calc_points(const Co2PointsArgs &a, cudaStream_t s);
+
+// ---- batched comp_CO3terms / comp_co3_sat_vals (the rest of the co2calc module's public trio)
+struct Co3TermsPointsArgs {
+  int n, k_all;                 // k_all: the level index of every point when k == NULL
+  const int *k;                 // 1-based level index per point, or NULL
+  const double *depth, *temp, *salt, *dic, *ta, *pt, *sit, *phlo, *phhi;
+  double *ph, *h2co3, *hco3, *co3;
+  unsigned long long *status;
+};
+cudaError_t launch_co3terms_points(const Co3TermsPointsArgs &a, cudaStream_t s);
+struct Co3SatPointsArgs {
+  int n, k_all;
+  const int *k;
+  const double *depth, *temp, *salt;
+  double *sat_calc, *sat_arag;
+};
+cudaError_t launch_co3_sat_points(const Co3SatPointsArgs &a, cudaStream_t s);
 
 // ---- DMS / MACROS
 struct DmsArgs {
@@ -136,10 +154,11 @@ cudaError_t launch_transpose(const double *src, double *dst, int rows_fast_src, 
 constexpr int kMpasMaxTracers = 64;
 struct MpasMap { int nT; int slot[kMpasMaxTracers]; };
 cudaError_t launch_mpas_to_soa(const double *mpas, double *soa, const MpasMap &m, int nL, int nC, cudaStream_t s);
-// mpas(n,k,cell) = beta * mpas(n,k,cell) + alpha * soa(cell,k,slot[n]); alpha = dt, beta = 1 is the
-// explicit tracer update fused with the layout change
+// mpas(n,k,cell) = beta * mpas(n,k,cell) + alpha * weight(k,cell) * soa(cell,k,slot[n]); weight = NULL
+// means 1.  alpha = dt, beta = 1 is the explicit tracer update fused with the layout change; with
+// weight = layerThickness(k,cell) it accumulates the thickness-weighted tendency the way MPAS-Ocean does.
 cudaError_t launch_soa_to_mpas(const double *soa, double *mpas, const MpasMap &m, int nL, int nC, double alpha,
-                               double beta, cudaStream_t s);
+                               double beta, const double *weight, cudaStream_t s);
 
 // ---- on-device accumulation of diagnostics (the host time-averages the
 // diagnostics for history files; accumulating on the device and downloading at output

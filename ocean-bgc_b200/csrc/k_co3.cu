@@ -230,6 +230,53 @@ co2calc_points_kernel(const __grid_constant__ Co2PointsArgs A) {
   }
 }
 
+// Batched comp_CO3terms (co2calc.F90:214-316) and comp_co3_sat_vals (:1096-1238): the two other
+// public procedures of the reference's co2calc module, one point per thread.  k is the
+// reference's 1-based level index: the pressure correction is keyed on (k > 1), not on depth.
+__global__ void __launch_bounds__(256)
+co3terms_points_kernel(const __grid_constant__ Co3TermsPointsArgs A) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = i < A.n;
+  double temp = 10.0, salt = 35.0, depth = 100.0, dic = 2000.0, ta = 2300.0, pt = 1.0, sit = 10.0, lo = 7.0, hi = 9.0;
+  int k = 1;
+  if (active) {
+    k = A.k ? A.k[i] : A.k_all;
+    depth = A.depth[i]; temp = A.temp[i]; salt = A.salt[i]; dic = A.dic[i]; ta = A.ta[i]; pt = A.pt[i];
+    sit = A.sit[i]; lo = A.phlo[i]; hi = A.phhi[i];
+  }
+  __shared__ double s_exp2[64];
+  exp_table_load(s_exp2);
+  const ExpTable ex{s_exp2};
+  Co3Consts K;
+  co3_coeffs<false>(k > 1, depth, temp, salt, K, ex);
+  const Co3Totals tot = co3_totals(dic, ta, pt, sit);
+  unsigned st = 0;
+  const double h = solve_htotal(K, tot, lo, hi, st);
+  if (active) {
+    const double h2 = h * h;
+    const double denom = frcp(h2 + K.k1 * h + K.k1 * K.k2);
+    A.ph[i] = ph_of_h(h);
+    A.h2co3[i] = (tot.dic * h2 * denom) * kMassToVol;
+    A.hco3[i] = (tot.dic * K.k1 * h * denom) * kMassToVol;
+    A.co3[i] = (tot.dic * K.k1 * K.k2 * denom) * kMassToVol;
+    report(A.status, st);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+co3_sat_points_kernel(const __grid_constant__ Co3SatPointsArgs A) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ double s_exp2[64];
+  exp_table_load(s_exp2);
+  const ExpTable ex{s_exp2};
+  if (i >= A.n) return;
+  const int k = A.k ? A.k[i] : A.k_all;
+  double sat_c, sat_a;
+  co3_sat_vals(k > 1, A.depth[i], A.temp[i], A.salt[i], sat_c, sat_a, ex);
+  A.sat_calc[i] = sat_c;
+  A.sat_arag[i] = sat_a;
+}
+
 __device__ __forceinline__ double schmidt_o2(double SST) {   // Keeling et al. 1998 (BGC_mod.F90:2965-3005)
   return 1638.0 + SST * (-81.83 + SST * (1.483 + SST * (-0.008004)));
 }
@@ -365,6 +412,18 @@ cudaError_t launch_zsat_columns(const ZsatArgs &a, cudaStream_t s) {
 cudaError_t launch_co2calc_points(const Co2PointsArgs &a, cudaStream_t s) {
   if (a.n <= 0) return cudaSuccess;
   co2calc_points_kernel<<<ceil_div_sz((size_t)a.n, 256), 256, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_co3terms_points(const Co3TermsPointsArgs &a, cudaStream_t s) {
+  if (a.n <= 0) return cudaSuccess;
+  co3terms_points_kernel<<<(a.n + 255) / 256, 256, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_co3_sat_points(const Co3SatPointsArgs &a, cudaStream_t s) {
+  if (a.n <= 0) return cudaSuccess;
+  co3_sat_points_kernel<<<(a.n + 255) / 256, 256, 0, s>>>(a);
   return cudaGetLastError();
 }
 

@@ -32,8 +32,11 @@
 // BLOCK consecutive columns = one contiguous BLOCK*8-byte run each - with
 // cp.async.bulk (the TMA unit's 1-D bulk copy) into a double-buffered shared-memory
 // stage, completion signalled on an mbarrier; the compute threads only ever read
-// shared memory.  Falls back to per-thread loads when the slabs are not 16-byte
-// aligned (odd nColumnsMax or a misaligned caller pointer).
+// shared memory.  When the slabs are not 16-byte aligned (odd nColumnsMax or a
+// misaligned caller pointer) the same stage is filled by 8-byte cp.async copies
+// (LDGSTS), one column per thread, two levels ahead as well: the staging differs,
+// the arithmetic is the SAME instantiation, so results do not depend on the width
+// of the block a host happens to pick.
 //
 // The carbonate solve of each cell has no vertical coupling and runs in the
 // cell-parallel kernel of k_co3.cu, and the saturation-depth scan (:1003-1032) that
@@ -198,7 +201,7 @@ static_assert((0 ECO_DIAG_K2_LIST(COUNT_ONE)) + 13 == (0 BGC_DIAG_K2_LIST(COUNT_
 
 // Shared memory of a block, in rows of BLOCK doubles (one slot per thread):
 //   2 stages x R_ROWS   the level's input slab: rows 0..29 = tracer slots, then the rows below
-//   X_ROWS              per-thread scratch: Pprime(4); DIAG: the three per-group column
+//   X_ROWS              per-thread scratch: the column's depth (as an int; rows 1-3 spare); DIAG: the three per-group column
 //                       integrals (:1838-1846, :1268), 4 each, and the fourteen column integrals
 //                       that are touched once per level (Jint_*, the z-integrals, the O2 minimum):
 //                       one shared-memory read-modify-write per level each instead of 28 registers
@@ -206,7 +209,7 @@ static_assert((0 ECO_DIAG_K2_LIST(COUNT_ONE)) + 13 == (0 BGC_DIAG_K2_LIST(COUNT_
 //                       which misses the few KB of L1 left beside a 221 KB carve-out)
 //   2 mbarriers
 enum { R_T = BGC_TRACER_CNT, R_ZMID, R_DZ, R_ZBOT, R_FESED, R_S, R_ROWS };
-enum { X_PPRIME = 0, X_ZPHOTO = 4, X_ZNO3 = 8, X_ZCACO3 = 12,
+enum { X_KMAX = 0, X_ZPHOTO = 4, X_ZNO3 = 8, X_ZCACO3 = 12,
        X_JC = 16, X_JC100, X_JN, X_JN100, X_JP, X_JP100, X_JSI, X_JSI100,
        X_CHL100, X_BSI, X_CACO3ZINT, X_PHOTOCZINT, X_PHOTOCNO3ZINT, X_O2MIN,
        // carried column state that is touched once per level (registers are the scarce resource)
@@ -237,9 +240,16 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+// 8-byte asynchronous copy global -> shared (SASS: LDGSTS), per thread; groups are committed
+// once per level and waited for with cp.async.wait_group
+__device__ __forceinline__ void cp_async8(unsigned dst, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_but_one() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-template <int DIAG, int BLOCK, int MINB, bool TMA>
+template <int DIAG, int BLOCK, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB)
 eco_columns_kernel(const __grid_constant__ EcoArgs A) {
   extern __shared__ __align__(128) double smem[];
@@ -257,9 +267,16 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
 #define XS(row) xs[(row) * BLOCK + tid]
 #define IN(row) st[(row) * BLOCK + tid]
 
-  int kmax = (in_range && col < A.nColumns) ? A.kmax[col] : 0;
-  if (kmax > nL) kmax = nL;
-  if (kmax < 0) kmax = 0;
+  // The column's depth is compared once or twice per level and would otherwise be spilled to
+  // local memory (every register is taken): it lives in a shared-memory row of its own.
+  int *const kmax_row = (int *)(xs + X_KMAX * BLOCK);
+  {
+    int km = (in_range && col < A.nColumns) ? A.kmax[col] : 0;
+    if (km > nL) km = nL;
+    if (km < 0) km = 0;
+    kmax_row[tid] = km;
+  }
+#define kmax (kmax_row[tid])
 
   const BgcParams &P = c_eco.p;
   const BgcIndices &I = c_eco.ind;
@@ -303,13 +320,14 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
 
   // ---- deepest active level of the block: nothing below it is fetched
   __shared__ int s_kmax_blk;
+  const bool bulk = A.bulk != 0;   // 16-byte aligned slabs: TMA bulk copies; otherwise 8-byte cp.async per thread
   if (tid == 0) {
     s_kmax_blk = 0;
-    if (TMA) { mbar_init(smem_u32(&bars[0]), 1); mbar_init(smem_u32(&bars[1]), 1); }
+    if (bulk) { mbar_init(smem_u32(&bars[0]), 1); mbar_init(smem_u32(&bars[1]), 1); }
   }
   __syncthreads();
   if (kmax > 0) atomicMax(&s_kmax_blk, kmax);
-  if (TMA && tid == 0) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  if (bulk && tid == 0) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
   const int kmax_blk = s_kmax_blk;
   const unsigned slab_bytes = (unsigned)(min(BLOCK, nC - col0) * (int)sizeof(double));
@@ -322,51 +340,52 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
   // copy that lands before the arm only drives the transaction count negative for a moment:
   // the phase cannot complete before thread 0's arrival.)
   constexpr int NW = BLOCK / 32;
-  auto fetch_level = [&](int kk) {
-    if (tid & 31) return;
-    double *dst = smem + (size_t)(kk & 1) * R_ROWS * BLOCK;
-    const unsigned bar = smem_u32(&bars[kk & 1]);
-    const size_t off = (size_t)nC * (size_t)kk + (size_t)col0;
-    if (tid == 0) mbar_expect_tx(bar, slab_bytes * (unsigned)((BGC_TRACER_CNT - 3) + 5 + (DIAG ? 1 : 0)));
-#pragma unroll 1
-    for (int r = tid >> 5; r < (DIAG ? R_ROWS : R_S); r += NW) {
-      const double *src;
-      if (r < BGC_TRACER_CNT) {
-        if ((skip_slots >> r) & 1u) continue;
-        src = A.tracers + (size_t)r * (size_t)nLnC;
-      } else {
-        switch (r) {
-          case R_T:     src = A.T; break;
-          case R_ZMID:  src = A.zmid; break;
-          case R_DZ:    src = A.dz; break;
-          case R_ZBOT:  src = A.zbot; break;
-          case R_FESED: src = A.fesedflux; break;
-          default:      src = A.S; break;
-        }
-      }
-      bulk_g2s(smem_u32(dst + r * BLOCK), src + off, slab_bytes, bar);
+  auto row_src = [&](int r) -> const double * {
+    if (r < BGC_TRACER_CNT) return A.tracers + (size_t)r * (size_t)nLnC;
+    switch (r) {
+      case R_T:     return A.T;
+      case R_ZMID:  return A.zmid;
+      case R_DZ:    return A.dz;
+      case R_ZBOT:  return A.zbot;
+      case R_FESED: return A.fesedflux;
+      default:      return A.S;
     }
   };
-  if (TMA) {
-    if (kmax_blk > 0) fetch_level(0);
-    if (kmax_blk > 1) fetch_level(1);
-  }
+  auto fetch_level = [&](int kk) {
+    double *dst = smem + (size_t)(kk & 1) * R_ROWS * BLOCK;
+    const size_t off = (size_t)nC * (size_t)kk + (size_t)col0;
+    if (bulk) {
+      if (tid & 31) return;
+      const unsigned bar = smem_u32(&bars[kk & 1]);
+      if (tid == 0) mbar_expect_tx(bar, slab_bytes * (unsigned)((BGC_TRACER_CNT - 3) + 5 + (DIAG ? 1 : 0)));
+#pragma unroll 1
+      for (int r = tid >> 5; r < (DIAG ? R_ROWS : R_S); r += NW) {
+        if (r < BGC_TRACER_CNT && ((skip_slots >> r) & 1u)) continue;
+        bulk_g2s(smem_u32(dst + r * BLOCK), row_src(r) + off, slab_bytes, bar);
+      }
+    } else if (in_range) {
+#pragma unroll 1
+      for (int r = 0; r < (DIAG ? R_ROWS : R_S); ++r) {
+        if (r < BGC_TRACER_CNT && ((skip_slots >> r) & 1u)) continue;
+        cp_async8(smem_u32(dst + r * BLOCK + tid), row_src(r) + off + tid);
+      }
+    }
+  };
+  // (cp.async mode: one group is committed per level whether or not anything was fetched, so
+  //  that "all but the most recent group" always means "this level has landed")
+  if (kmax_blk > 0) fetch_level(0);
+  if (!bulk) cp_async_commit();
+  if (kmax_blk > 1) fetch_level(1);
+  if (!bulk) cp_async_commit();
 
   for (int k = 0; k < nL; ++k) {
     const unsigned i2 = (unsigned)col + (unsigned)nC * (unsigned)k;
     double *const st = smem + (size_t)(k & 1) * R_ROWS * BLOCK;
 
-    if (TMA) {
+    if (bulk) {
       if (k < kmax_blk) mbar_wait(smem_u32(&bars[k & 1]), (unsigned)((k >> 1) & 1));
-    } else if (k < kmax) {
-      // fallback: every thread loads its own column's slab entries
-      const double *src = A.tracers + i2;
-#pragma unroll 1
-      for (int n = 0; n < BGC_TRACER_CNT; ++n, src += nLnC)
-        if (!((skip_slots >> n) & 1u)) IN(n) = *src;
-      IN(R_T) = A.T[i2]; IN(R_ZMID) = A.zmid[i2]; IN(R_DZ) = A.dz[i2]; IN(R_ZBOT) = A.zbot[i2];
-      IN(R_FESED) = A.fesedflux[i2];
-      if (DIAG) IN(R_S) = A.S[i2];
+    } else {
+      cp_async_wait_but_one();   // this thread's own column of level k has landed (it reads no other)
     }
 
     if (k >= kmax) {
@@ -1254,9 +1273,10 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
     // ---- end of level: every thread is done with stage k&1 (generic-proxy reads and the
     //      in-place mask writes) before the TMA unit refills it with level k+2.  The same
     //      barrier keeps the block's warps on one stretch of code (I-cache).
-    if (TMA) fence_proxy_async();
+    if (bulk) fence_proxy_async();
     __syncthreads();
-    if (TMA && k + 2 < kmax_blk) fetch_level(k + 2);
+    if (k + 2 < kmax_blk) fetch_level(k + 2);
+    if (!bulk) cp_async_commit();
   }   // level loop
 
   // ---- per-column diagnostics
@@ -1310,12 +1330,13 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
   }
 #undef XS
 #undef IN
+#undef kmax
 }
 
-template <int DIAG, int BLOCK, int MINB, bool TMA>
+template <int DIAG, int BLOCK, int MINB>
 cudaError_t launch_variant(const EcoArgs &a, cudaStream_t s) {
   const size_t smem = (size_t)(2 * R_ROWS + X_ROWS) * BLOCK * sizeof(double) + 2 * sizeof(unsigned long long);
-  auto kern = eco_columns_kernel<DIAG, BLOCK, MINB, TMA>;
+  auto kern = eco_columns_kernel<DIAG, BLOCK, MINB>;
   // > 48 KB of dynamic shared memory is opt-in, per device: cheap enough to set on every launch
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
@@ -1325,7 +1346,8 @@ cudaError_t launch_variant(const EcoArgs &a, cudaStream_t s) {
 }
 
 // cp.async.bulk needs 16-byte aligned global addresses and sizes: every slab starts at
-// base + 8*(k*nC + 128*j), so nC must be even and every base pointer 16-byte aligned.
+// base + 8*(k*nC + BLOCK*j), so nC must be even and every base pointer 16-byte aligned.
+// Otherwise the stage is filled with 8-byte cp.async copies (same kernel, same arithmetic).
 bool slabs_are_bulk_copyable(const EcoArgs &a, bool diag) {
   if (a.nC & 1) return false;
   const void *p[] = {a.tracers, a.T, a.zmid, a.dz, a.zbot, a.fesedflux, diag ? a.S : a.T};
@@ -1333,27 +1355,23 @@ bool slabs_are_bulk_copyable(const EcoArgs &a, bool diag) {
   return true;
 }
 
-// 0 (default): one 8-warp block per SM; 1: two 4-warp blocks per SM; 9: force the per-thread
-// load path (also taken whenever the slabs are not bulk-copyable)
-int block_of(const EcoArgs &a, bool diag, int variant, bool *tma_out) {
-  const bool tma = slabs_are_bulk_copyable(a, diag) && variant != 9;
-  if (tma_out) *tma_out = tma;
-  return (tma && variant != 1) ? 256 : 128;
-}
+// 0 (default): one 8-warp block per SM; 1: two 4-warp blocks per SM; 9: force the cp.async
+// staging (also taken whenever the slabs are not bulk-copyable)
+int block_of(int variant) { return variant == 1 ? 128 : 256; }
 
 template <int DIAG>
-cudaError_t launch_diag(const EcoArgs &a, int variant, cudaStream_t s) {
-  bool tma;
-  const int block = block_of(a, DIAG != 0, variant, &tma);
-  if (!tma) return launch_variant<DIAG, 128, 2, false>(a, s);
-  if (block == 256) return launch_variant<DIAG, 256, 1, true>(a, s);
-  return launch_variant<DIAG, 128, 2, true>(a, s);
+cudaError_t launch_diag(const EcoArgs &a0, int variant, cudaStream_t s) {
+  EcoArgs a = a0;
+  a.bulk = (slabs_are_bulk_copyable(a, DIAG != 0) && variant != 9) ? 1 : 0;
+  if (block_of(variant) == 256) return launch_variant<DIAG, 256, 1>(a, s);
+  return launch_variant<DIAG, 128, 2>(a, s);
 }
 
 }  // namespace
 
 int eco_inventory_parts(const EcoArgs &a, int diag_mode, int variant) {
-  const int block = block_of(a, diag_mode != 0, variant, nullptr);
+  (void)diag_mode;
+  const int block = block_of(variant);
   return (a.nC + block - 1) / block;
 }
 

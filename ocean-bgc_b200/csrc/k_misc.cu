@@ -485,7 +485,7 @@ transpose_kernel(const double *__restrict__ src, double *__restrict__ dst, int R
 template <bool TO_SOA>
 __global__ void __launch_bounds__(256)
 mpas_layout_kernel(const double *__restrict__ src, double *__restrict__ dst, const __grid_constant__ MpasMap M,
-                   int nL, int nC, int KB, double alpha, double beta) {
+                   int nL, int nC, int KB, double alpha, double beta, const double *__restrict__ weight) {
   extern __shared__ double tile[];   // [32][KB*nT + 1]
   const int c0 = blockIdx.x * 32, k0 = blockIdx.y * KB, nT = M.nT;
   const int ncell = min(32, nC - c0), nk = min(KB, nL - k0);
@@ -518,11 +518,16 @@ mpas_layout_kernel(const double *__restrict__ src, double *__restrict__ dst, con
     __syncthreads();
     for (int c = w; c < ncell; c += nw) {
       double *p = dst + (size_t)nT * ((size_t)k0 + (size_t)nL * (size_t)(c0 + c));
-      for (int r = lane, n = lane % nT; r < run; r += 32, n = (n + 32) % nT) {
+      // weight(k, cell), level fastest (MPAS layerThickness): the thickness-weighted tendency
+      const double *wp = weight ? weight + (size_t)k0 + (size_t)nL * (size_t)(c0 + c) : nullptr;
+      for (int r = lane, n = lane % nT, kk = lane / nT; r < run; r += 32) {
         if (M.slot[n] > 0) {
-          const double v = tile[c * pitch + r];
+          double v = tile[c * pitch + r];
+          if (wp) v = wp[kk] * v;
           p[r] = (beta == 0.0) ? alpha * v : beta * p[r] + alpha * v;
         }
+        n += 32;
+        while (n >= nT) { n -= nT; ++kk; }
       }
     }
   }
@@ -641,7 +646,7 @@ static int mpas_levels_per_block(int nT, bool to_soa) {
 }
 template <bool TO_SOA>
 static cudaError_t launch_mpas_layout(const double *src, double *dst, const MpasMap &m, int nL, int nC, double alpha,
-                                      double beta, cudaStream_t s) {
+                                      double beta, const double *weight, cudaStream_t s) {
   if (nL <= 0 || nC <= 0 || m.nT <= 0) return cudaSuccess;
   if (m.nT > kMpasMaxTracers) return cudaErrorInvalidValue;
   const int KB = mpas_levels_per_block(m.nT, TO_SOA);
@@ -651,15 +656,15 @@ static cudaError_t launch_mpas_layout(const double *src, double *dst, const Mpas
   if (e != cudaSuccess) return e;
   dim3 grid(cdiv((size_t)nC, 32), cdiv((size_t)nL, (size_t)KB));
   if (grid.y > 65535u) return cudaErrorInvalidConfiguration;
-  kern<<<grid, 256, smem, s>>>(src, dst, m, nL, nC, KB, alpha, beta);
+  kern<<<grid, 256, smem, s>>>(src, dst, m, nL, nC, KB, alpha, beta, weight);
   return cudaGetLastError();
 }
 cudaError_t launch_mpas_to_soa(const double *mpas, double *soa, const MpasMap &m, int nL, int nC, cudaStream_t s) {
-  return launch_mpas_layout<true>(mpas, soa, m, nL, nC, 1.0, 0.0, s);
+  return launch_mpas_layout<true>(mpas, soa, m, nL, nC, 1.0, 0.0, nullptr, s);
 }
 cudaError_t launch_soa_to_mpas(const double *soa, double *mpas, const MpasMap &m, int nL, int nC, double alpha,
-                               double beta, cudaStream_t s) {
-  return launch_mpas_layout<false>(soa, mpas, m, nL, nC, alpha, beta, s);
+                               double beta, const double *weight, cudaStream_t s) {
+  return launch_mpas_layout<false>(soa, mpas, m, nL, nC, alpha, beta, weight, s);
 }
 
 cudaError_t launch_accumulate(const double *src, double *acc, int nL, int cc, int nC, int c0, int nSlabs,

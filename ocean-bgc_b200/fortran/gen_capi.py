@@ -141,6 +141,41 @@ IFACES = r'''
                                     xco2(*), atmpres(*)
       real(c_double), intent(inout) :: ph(*), co2star(*), dco2star(*), pco2surf(*), dpco2(*)
     end function
+    integer(c_int) function bgc_comp_co3terms(ctx, n, k_level, k_all, depth, temp, salt, dic, ta, pt, sit, phlo, phhi, &
+                                              ph, h2co3, hco3, co3, mem_space) bind(C, name="bgc_comp_co3terms")
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: ctx
+      integer(c_int), value :: n, k_all, mem_space
+      integer(c_int), intent(in) :: k_level(*)
+      real(c_double), intent(in) :: depth(*), temp(*), salt(*), dic(*), ta(*), pt(*), sit(*), phlo(*), phhi(*)
+      real(c_double), intent(inout) :: ph(*), h2co3(*), hco3(*), co3(*)
+    end function
+    integer(c_int) function bgc_comp_co3_sat_vals(ctx, n, k_level, k_all, depth, temp, salt, co3_sat_calc, &
+                                                  co3_sat_arag, mem_space) bind(C, name="bgc_comp_co3_sat_vals")
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: ctx
+      integer(c_int), value :: n, k_all, mem_space
+      integer(c_int), intent(in) :: k_level(*)
+      real(c_double), intent(in) :: depth(*), temp(*), salt(*)
+      real(c_double), intent(inout) :: co3_sat_calc(*), co3_sat_arag(*)
+    end function
+    integer(c_int) function bgc_state_set(ctx, which, host, nLevelsMax, nColumnsMax) bind(C, name="bgc_state_set")
+      import :: c_int, c_ptr
+      type(c_ptr), value :: ctx, host
+      integer(c_int), value :: which, nLevelsMax, nColumnsMax
+    end function
+    integer(c_int) function bgc_state_get(ctx, which, host, nLevelsMax, nColumnsMax) bind(C, name="bgc_state_get")
+      import :: c_int, c_ptr
+      type(c_ptr), value :: ctx, host
+      integer(c_int), value :: which, nLevelsMax, nColumnsMax
+    end function
+    integer(c_int) function bgc_state_device_ptr(ctx, which, nLevelsMax, nColumnsMax, dev_ptr) &
+        bind(C, name="bgc_state_device_ptr")
+      import :: c_int, c_ptr
+      type(c_ptr), value :: ctx
+      integer(c_int), value :: which, nLevelsMax, nColumnsMax
+      type(c_ptr), intent(out) :: dev_ptr
+    end function
     integer(c_int) function bgc_inventory_enable(ctx, enable) bind(C, name="bgc_inventory_enable")
       import :: c_int, c_ptr
       type(c_ptr), value :: ctx
@@ -183,7 +218,9 @@ def main():
            "  public",
            "  integer(c_int), parameter :: BGC_MEM_HOST_FORTRAN = %d, BGC_MEM_DEVICE_SOA = %d" %
            (abi.BGC_MEM_HOST_FORTRAN, abi.BGC_MEM_DEVICE_SOA),
-           "  integer(c_int), parameter :: BGC_OK = 0, BGC_INVENTORY_LEN = %d" % abi.BGC_INVENTORY_LEN, ""]
+           "  integer(c_int), parameter :: BGC_OK = 0, BGC_INVENTORY_LEN = %d" % abi.BGC_INVENTORY_LEN,
+           "  integer(c_int), parameter :: BGC_STATE_PH_PREV_3D = 0, BGC_STATE_PH_PREV_ALT_CO2_3D = 1, &",
+           "                               BGC_STATE_SURFACE_PH = 2, BGC_STATE_SURFACE_PH_ALT_CO2 = 3", ""]
     for s in STRUCTS:
         out.append(ftype(s, abi._STRUCT_FIELDS[s]))
         out.append("")

@@ -39,7 +39,8 @@ ABI_SYMBOLS = [
     "bgc_diag_accumulate_enable", "bgc_diag_flush", "bgc_layout_mpas_to_soa", "bgc_layout_soa_to_mpas",
     "bgc_inventory_allreduce_begin", "bgc_inventory_allreduce_end",
     "bgc_graph_capture_begin", "bgc_graph_capture_end", "bgc_graph_launch", "bgc_graph_destroy",
-    "bgc_ctx_set_zero_shortcut",
+    "bgc_ctx_set_zero_shortcut", "bgc_comp_co3terms", "bgc_comp_co3_sat_vals",
+    "bgc_layout_soa_to_mpas_weighted", "bgc_state_device_ptr", "bgc_state_set", "bgc_state_get",
 ]
 
 
@@ -159,12 +160,32 @@ class Context:
         check(self.L, self.L.bgc_layout_mpas_to_soa(self.ptr, abi.raw_dptr(dev_mpas), abi.raw_dptr(dev_soa),
                                                     C.c_int(len(slot_of_tracer)), m, C.c_int(nL), C.c_int(nC)))
 
-    def soa_to_mpas(self, dev_soa, dev_mpas, slot_of_tracer, nL, nC, alpha=1.0, beta=0.0):
-        """T(n,k,cell) = beta*T + alpha*soa(cell,k,slot[n]): layout change fused with the tracer update."""
+    def soa_to_mpas(self, dev_soa, dev_mpas, slot_of_tracer, nL, nC, alpha=1.0, beta=0.0, dev_weight=None):
+        """T(n,k,cell) = beta*T + alpha*w(k,cell)*soa(cell,k,slot[n]): layout change fused with the tracer
+        update; dev_weight = device address of w(k,cell) (MPAS layerThickness layout) or None for w = 1."""
         m = (C.c_int * len(slot_of_tracer))(*[int(x) for x in slot_of_tracer])
-        check(self.L, self.L.bgc_layout_soa_to_mpas(self.ptr, abi.raw_dptr(dev_soa), abi.raw_dptr(dev_mpas),
-                                                    C.c_int(len(slot_of_tracer)), m, C.c_int(nL), C.c_int(nC),
-                                                    C.c_double(alpha), C.c_double(beta)))
+        check(self.L, self.L.bgc_layout_soa_to_mpas_weighted(
+            self.ptr, abi.raw_dptr(dev_soa), abi.raw_dptr(dev_mpas), C.c_int(len(slot_of_tracer)), m, C.c_int(nL),
+            C.c_int(nC), C.c_double(alpha), C.c_double(beta), abi.raw_dptr(dev_weight or 0)))
+
+    # ---- device-resident model state (restart fields): bgc_b200.h "Device-resident model state"
+    STATE = {"PH_PREV_3D": 0, "PH_PREV_ALT_CO2_3D": 1, "surface_pH": 2, "surface_pH_alt_co2": 3}
+
+    def state_device_ptr(self, name, nL, nC):
+        p = C.POINTER(C.c_double)()
+        check(self.L, self.L.bgc_state_device_ptr(self.ptr, C.c_int(self.STATE[name]), C.c_int(nL), C.c_int(nC),
+                                                  C.byref(p)))
+        return C.cast(p, C.c_void_p).value
+
+    def state_set(self, name, host_array, nL, nC):
+        a = np.asfortranarray(host_array, dtype=np.float64)
+        check(self.L, self.L.bgc_state_set(self.ptr, C.c_int(self.STATE[name]), abi.fptr(a), C.c_int(nL), C.c_int(nC)))
+
+    def state_get(self, name, nL, nC):
+        shape = (nL, nC) if self.STATE[name] < 2 else (nC,)
+        a = np.zeros(shape, dtype=np.float64, order="F")
+        check(self.L, self.L.bgc_state_get(self.ptr, C.c_int(self.STATE[name]), abi.fptr(a), C.c_int(nL), C.c_int(nC)))
+        return a
 
     def set_zero_shortcut(self, on=True):
         check(self.L, self.L.bgc_ctx_set_zero_shortcut(self.ptr, C.c_int(int(on))))
@@ -316,6 +337,38 @@ def co2calc_points(ctx, pts):
     return out
 
 
+def comp_CO3terms_points(ctx, k, depth, temp, salt, dic, ta, pt, sit, phlo, phhi):
+    """Batched comp_CO3terms(k, depth, .true., temp, salt, dic_in, ta_in, pt_in, sit_in, phlo, phhi, ph,
+    H2CO3, HCO3, CO3) (co2calc.F90:214) over host numpy arrays; k = array of 1-based level indices or an int."""
+    arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (depth, temp, salt, dic, ta, pt, sit, phlo, phhi)]
+    n = len(arrs[1])
+    out = {nm: np.zeros(n) for nm in ("pH", "H2CO3", "HCO3", "CO3")}
+    if np.ndim(k) == 0:
+        kp, k_all, keep = C.POINTER(C.c_int)(), int(k), None
+    else:
+        keep = np.ascontiguousarray(k, dtype=np.int32)
+        kp, k_all = abi.iptr(keep), 1
+    check(ctx.L, ctx.L.bgc_comp_co3terms(ctx.ptr, C.c_int(n), kp, C.c_int(k_all), *[abi.dptr(a) for a in arrs],
+                                         *[abi.dptr(out[nm]) for nm in ("pH", "H2CO3", "HCO3", "CO3")],
+                                         C.c_int(abi.BGC_MEM_HOST_FORTRAN)))
+    return out
+
+
+def comp_co3_sat_vals_points(ctx, k, depth, temp, salt):
+    """Batched comp_co3_sat_vals(k, depth, temp, salt, co3_sat_calc, co3_sat_arag) (co2calc.F90:1096)."""
+    arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (depth, temp, salt)]
+    n = len(arrs[1])
+    calc, arag = np.zeros(n), np.zeros(n)
+    if np.ndim(k) == 0:
+        kp, k_all, keep = C.POINTER(C.c_int)(), int(k), None
+    else:
+        keep = np.ascontiguousarray(k, dtype=np.int32)
+        kp, k_all = abi.iptr(keep), 1
+    check(ctx.L, ctx.L.bgc_comp_co3_sat_vals(ctx.ptr, C.c_int(n), kp, C.c_int(k_all), *[abi.dptr(a) for a in arrs],
+                                             abi.dptr(calc), abi.dptr(arag), C.c_int(abi.BGC_MEM_HOST_FORTRAN)))
+    return calc, arag
+
+
 def co2calc_points_device(ctx, dev_in, dev_out, n):
     """Same on device arrays: dev_in / dev_out are dicts of raw device addresses."""
     check(ctx.L, ctx.L.bgc_co2calc_points(ctx.ptr, C.c_int(n), *[abi.raw_dptr(dev_in[k]) for k in _PT_IN],
@@ -330,6 +383,13 @@ def co2calc_points_device(ctx, dev_in, dev_out, n):
 def _torch():
     import torch
     return torch
+
+
+def _sync(device):
+    """(containers on device "cpu" exist only for dry runs of the test harness)"""
+    torch = _torch()
+    if torch.device(device).type == "cuda":
+        torch.cuda.synchronize(device)
 
 
 class _DeviceMixin:
@@ -429,28 +489,28 @@ class DeviceBgcColumns(_DeviceMixin):
             put(t, host.flux_diag[n])
         self.nColumns = host.nColumns
         self.lcalc_O2_gas_flux, self.lcalc_CO2_gas_flux = host.lcalc_O2_gas_flux, host.lcalc_CO2_gas_flux
-        torch.cuda.synchronize()   # torch copies run on torch's stream, library calls on the ctx stream
+        _sync(self.device)   # torch copies run on torch's stream, library calls on the ctx stream
         return self
 
     def store(self, host):
         """Copy outputs / in-out members back into a host BgcColumns."""
-        def get(t, like):
+        def get(t, like, per_column_n=False):
             a = t.cpu().numpy()
             if like.ndim == 3:
-                like[...] = np.transpose(a, (1, 2, 0))
-            elif like.ndim == 2 and a.shape != like.shape:
-                like[...] = a.T
+                like[...] = np.transpose(a, (1, 2, 0))     # (n,k,col) -> (k,col,n)
+            elif per_column_n:
+                like[...] = a.T                            # (n,col) -> (col,n), whatever the extents are
             else:
                 like[...] = a
         get(self.BGC_tendencies, host.BGC_tendencies)
         get(self.PH_PREV_3D, host.PH_PREV_3D)
         get(self.PH_PREV_ALT_CO2_3D, host.PH_PREV_ALT_CO2_3D)
         for n, t in self.diag.items():
-            get(t, host.diag[n])
+            get(t, host.diag[n], n in abi.BGC_DIAG_CA)
         for n, t in self.flux_diag.items():
             get(t, host.flux_diag[n])
         for n, t in self.forcing.items():
-            get(t, host.forcing[n])
+            get(t, host.forcing[n], n in abi.BGC_FORCING_FLUX)
         return host
 
     # ---- C-ABI argument blocks
@@ -532,7 +592,7 @@ class DeviceDmsColumns(_DeviceMixin):
             put(t, host.flux_diag[n])
         self.nColumns = host.nColumns
         self.lcalc_DMS_gas_flux = host.lcalc_DMS_gas_flux
-        torch.cuda.synchronize()   # torch copies run on torch's stream, library calls on the ctx stream
+        _sync(self.device)   # torch copies run on torch's stream, library calls on the ctx stream
         return self
 
     def store(self, host):
@@ -610,7 +670,7 @@ class DeviceMacrosColumns(_DeviceMixin):
         for n, t in self.diag.items():
             put(t, self._soa(host.diag[n]))
         self.nColumns = host.nColumns
-        torch.cuda.synchronize()   # torch copies run on torch's stream, library calls on the ctx stream
+        _sync(self.device)   # torch copies run on torch's stream, library calls on the ctx stream
         return self
 
     def store(self, host):
@@ -641,5 +701,6 @@ class DeviceMacrosColumns(_DeviceMixin):
 
 __all__ = ["BgcError", "Parms", "BGC_parms_init", "Context", "BGC_SourceSink", "BGC_SurfaceFluxes",
            "DMS_SourceSink", "DMS_SurfaceFluxes", "MACROS_SourceSink", "co2calc_points",
+           "comp_CO3terms_points", "comp_co3_sat_vals_points",
            "co2calc_points_device", "DeviceBgcColumns", "DeviceDmsColumns", "DeviceMacrosColumns",
            "BgcColumns", "DmsColumns", "MacrosColumns", "lib", "ABI_SYMBOLS"]

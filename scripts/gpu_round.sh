@@ -11,9 +11,9 @@ if [ "${SKIP_TESTS:-0}" != "1" ]; then
   tail -3 gpurun_out/pytest_gpu_$TAG.log
 fi
 python __graft_entry__.py smoke > gpurun_out/smoke_$TAG.log 2>&1; echo "smoke exit $?"
-python bench.py > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; echo "bench exit $?"
+BGC_BENCH_WRITE_INVENTORY=${WRITE_INV:-} python bench.py > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; echo "bench exit $?"
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref_$TAG.json 2> gpurun_out/bench_ref_$TAG.err; echo "ref exit $?"
-CMD="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu"
+CMD="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --no-secondary"
 $CMD > gpurun_out/plain.log 2>&1 || { echo "plain run failed"; tail -20 gpurun_out/plain.log; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -s ${SKIP:-48} -c ${COUNT:-24} --csv \
     --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_launches.log 2>&1

@@ -100,3 +100,43 @@ int macros_source_sink(bgc_ctx *c, const MacrosInput *in, MacrosOutput *out, Mac
   oracle_MACROS_SourceSink(&c->mp, &c->mind, in, out, dg, nL, nC, n, 1);
   return BGC_OK;
 }
+
+/* the two other public procedures of the reference's co2calc module, batched (host arrays only) */
+int bgc_comp_co3terms(bgc_ctx *c, int n, const int *k_level, int k_all, const double *depth, const double *temp,
+                      const double *salt, const double *dic, const double *ta, const double *pt, const double *sit,
+                      const double *phlo, const double *phhi, double *ph, double *h2co3, double *hco3, double *co3,
+                      int mem_space) {
+  if (!c) return fail(BGC_ERR_ARG, "mock: null ctx");
+  if (mem_space != BGC_MEM_HOST_FORTRAN) return fail(BGC_ERR_ARG, "mock: host arrays only");
+  g_calls++;
+  for (int i = 0; i < n; ++i) {
+    double lo = phlo[i], hi = phhi[i];
+    OracleSolverStats st = {0};
+    oracle_comp_CO3terms(k_level ? k_level[i] : k_all, depth[i], 1, temp[i], salt[i], dic[i], ta[i], pt[i], sit[i],
+                         &lo, &hi, &ph[i], &h2co3[i], &hco3[i], &co3[i], &st);
+  }
+  return BGC_OK;
+}
+
+int bgc_comp_co3_sat_vals(bgc_ctx *c, int n, const int *k_level, int k_all, const double *depth, const double *temp,
+                          const double *salt, double *co3_sat_calc, double *co3_sat_arag, int mem_space) {
+  if (!c) return fail(BGC_ERR_ARG, "mock: null ctx");
+  if (mem_space != BGC_MEM_HOST_FORTRAN) return fail(BGC_ERR_ARG, "mock: host arrays only");
+  g_calls++;
+  for (int i = 0; i < n; ++i)
+    oracle_comp_co3_sat_vals(k_level ? k_level[i] : k_all, depth[i], temp[i], salt[i], &co3_sat_calc[i], &co3_sat_arag[i]);
+  return BGC_OK;
+}
+
+int bgc_co2calc_points(bgc_ctx *c, int n, const double *depth, const double *temp, const double *salt,
+                       const double *dic, const double *ta, const double *pt, const double *sit, const double *phlo,
+                       const double *phhi, const double *xco2, const double *atmpres, double *ph, double *co2star,
+                       double *dco2star, double *pco2surf, double *dpco2, int mem_space) {
+  if (!c) return fail(BGC_ERR_ARG, "mock: null ctx");
+  if (mem_space != BGC_MEM_HOST_FORTRAN) return fail(BGC_ERR_ARG, "mock: host arrays only");
+  g_calls++;
+  OracleSolverStats st = {0};
+  oracle_co2calc_points(n, depth, temp, salt, dic, ta, pt, sit, phlo, phhi, xco2, atmpres, ph, co2star, dco2star,
+                        pco2surf, dpco2, &st, 1);
+  return BGC_OK;
+}

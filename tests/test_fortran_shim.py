@@ -262,3 +262,76 @@ def test_shim_drop_in_chain_on_the_gpu():
     assert parity.nerr(mb.MACROS_tendencies, ma.MACROS_tendencies) <= parity.TOL_TEND
     assert parity.nerr(db.forcing["netFlux"][cm], da.forcing["netFlux"][cm]) <= parity.TOL_TEND
     L.call("bgc_b200_runtime__bgc_b200_finalize")
+
+
+def _co2calc_trio_through(L, pts, k, n):
+    """co2calc_1point, comp_CO3terms, comp_co3_sat_vals of module co2calc with the reference's scalar
+    argument lists (co2calc.F90:75, :214, :1096), point by point."""
+    out = {nm: np.zeros(n) for nm in ("ph1", "co2star", "dco2star", "pco2surf", "dpco2", "ph", "h2co3", "hco3",
+                                      "co3", "sat_calc", "sat_arag")}
+    for i in range(n):
+        a = {nm: float(pts[nm][i]) for nm in pts}
+        _, b = L.call("co2calc__co2calc_1point", a["depth"], 1, 1, a["temp"], a["salt"], a["dic"], a["ta"], a["pt"],
+                      a["sit"], a["phlo"], a["phhi"], 0.0, a["xco2"], a["atmpres"], 0.0, 0.0, 0.0, 0.0)
+        out["ph1"][i], out["co2star"][i], out["dco2star"][i] = b[11].value, b[14].value, b[15].value
+        out["pco2surf"][i], out["dpco2"][i] = b[16].value, b[17].value
+        _, b = L.call("co2calc__comp_co3terms", int(k[i]), a["depth"], 1, a["temp"], a["salt"], a["dic"], a["ta"],
+                      a["pt"], a["sit"], a["phlo"], a["phhi"], 0.0, 0.0, 0.0, 0.0)
+        assert (b[9].value, b[10].value) == (a["phlo"], a["phhi"])      # the brackets come back unchanged
+        out["ph"][i], out["h2co3"][i], out["hco3"][i], out["co3"][i] = (x.value for x in b[11:15])
+        _, b = L.call("co2calc__comp_co3_sat_vals", int(k[i]), a["depth"], a["temp"], a["salt"], 0.0, 0.0)
+        out["sat_calc"][i], out["sat_arag"][i] = b[4].value, b[5].value
+    return out
+
+
+def _co2calc_trio_reference(pts, k, n):
+    out = {nm: np.zeros(n) for nm in ("ph1", "co2star", "dco2star", "pco2surf", "dpco2", "ph", "h2co3", "hco3",
+                                      "co3", "sat_calc", "sat_arag")}
+    for i in range(n):
+        a = {nm: float(pts[nm][i]) for nm in pts}
+        r = rt.co2calc_1point(*[a[nm] for nm in ("depth", "temp", "salt", "dic", "ta", "pt", "sit", "phlo", "phhi",
+                                                  "xco2", "atmpres")])
+        out["ph1"][i], out["co2star"][i], out["dco2star"][i] = r["ph"], r["co2star"], r["dco2star"]
+        out["pco2surf"][i], out["dpco2"][i] = r["pco2surf"], r["dpco2"]
+        r = rt.comp_CO3terms(int(k[i]), a["depth"], a["temp"], a["salt"], a["dic"], a["ta"], a["pt"], a["sit"],
+                             a["phlo"], a["phhi"])
+        out["ph"][i], out["h2co3"][i], out["hco3"][i], out["co3"][i] = r["pH"], r["H2CO3"], r["HCO3"], r["CO3"]
+        out["sat_calc"][i], out["sat_arag"][i] = rt.comp_co3_sat_vals(int(k[i]), a["depth"], a["temp"], a["salt"])
+    return out
+
+
+def _trio_points(n):
+    pts = pkg.synth_co2_points(n)
+    rng = np.random.default_rng(5)
+    k = rng.integers(1, 61, n).astype(np.int32)
+    k[:4] = 1
+    pts["depth"] = np.where(k == 1, 5.0, rng.uniform(10.0, 5500.0, n))
+    return pts, k
+
+
+def test_shim_co2calc_module_against_the_reference():
+    """module co2calc of the shim (the reference's public trio, co2calc.F90:24) over the mock C ABI:
+    the reference's bits (the mock is the oracle, and oracle == translated reference)."""
+    L = rt.TLib(SHIM, SHIM_META, preload=[MOCK])
+    C.CDLL(MOCK, mode=C.RTLD_GLOBAL)
+    n = 48
+    pts, k = _trio_points(n)
+    got, ref = _co2calc_trio_through(L, pts, k, n), _co2calc_trio_reference(pts, k, n)
+    for nm in ref:
+        _same(got[nm], ref[nm], "co2calc module: " + nm)
+    L.call("bgc_b200_runtime__bgc_b200_finalize")
+
+
+@pytest.mark.gpu
+def test_shim_co2calc_module_on_the_gpu():
+    """the same scalar calls, reference-typed caller -> shim module co2calc -> C ABI -> CUDA"""
+    if "libmock_bgc_b200" in open("/proc/self/maps").read():
+        pytest.skip("the CPU mock of the C ABI is loaded in this process (run with -m gpu)")
+    L = rt.TLib(SHIM, SHIM_META, preload=[REAL])
+    n = 24
+    pts, k = _trio_points(n)
+    got, ref = _co2calc_trio_through(L, pts, k, n), _co2calc_trio_reference(pts, k, n)
+    for nm in ref:
+        e = parity.nerr(got[nm], ref[nm])
+        assert e <= parity.TOL_SOLVER, (nm, e)
+    L.call("bgc_b200_runtime__bgc_b200_finalize")

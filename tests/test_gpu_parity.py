@@ -3,8 +3,8 @@ oracle on the same seeded synthetic columns (tolerances: tests/parity.py), plus
 size-independent properties at the full EC60to30 size.
 
 Covers the edge cases the reference's own semantics create: ragged bathymetry, land
-columns (kmax = 0), numColumns < numColumnsMax, odd numColumnsMax (per-thread load
-path instead of the bulk-copy path), cold and warm pH brackets, diagnostics absent /
+columns (kmax = 0), numColumns < numColumnsMax, odd numColumnsMax (cp.async
+staging instead of the TMA bulk-copy staging), cold and warm pH brackets, diagnostics absent /
 partially present, permuted tracer slots, dark columns, negative tracers, the
 zero-mask of a functional group.
 """
@@ -36,7 +36,7 @@ def _ctx(nL, nC, flavour=None, parms=None):
 @pytest.mark.parametrize("nL,nC,nCols,ragged", [
     (60, 256, 256, False),    # two full blocks, bulk-copy path
     (60, 258, 250, True),     # partial last block, numColumns < numColumnsMax, land columns
-    (33, 257, 257, True),     # odd numColumnsMax -> per-thread load path
+    (33, 257, 257, True),     # odd numColumnsMax -> cp.async staging instead of TMA bulk copies
     (80, 130, 130, True),     # RRS18to6 level count
     (2, 64, 64, False),       # kmax forced to 1 below: level 1 is surface AND bottom
 ])
@@ -727,12 +727,11 @@ def test_ec60to30_full_size_properties():
         tot = d.diag["diag_Jint_%stot" % el].abs().max().item()
         part = d.diag["diag_Jint_100m_%stot" % el].abs().max().item()
         assert tot <= 1e-10 * part, (el, tot, part)
-    # slab independence: columns [2*slab, 3*slab) alone, bit for bit.  The slab is padded by one
-    # land column so that numColumnsMax stays even: an odd extent selects the per-thread-load
-    # instantiation of the sweep, whose FMA contraction differs from the bulk-copy one in the
-    # last bit of a few tendencies (same source, different template instance).
+    # slab independence: columns [2*slab, 3*slab) alone, bit for bit.  The slab is 29 395 columns
+    # wide - ODD, so its level rows are not 16-byte aligned and the sweep stages them with 8-byte
+    # cp.async copies instead of TMA bulk copies: the staging differs, the arithmetic does not.
     sl = slice(2 * slab, 3 * slab)
-    sub = host.DeviceBgcColumns(nL, slab + 1, nColumns=slab)
+    sub = host.DeviceBgcColumns(nL, slab)
     own = slice(0, slab)
     sub.BGC_tracers[:, :, own].copy_(d.BGC_tracers[:, :, sl])
     for n in d.K2_IN:
@@ -744,12 +743,13 @@ def test_ec60to30_full_size_properties():
         sub.forcing[n][own].copy_(d.forcing[n][sl])
     sub.PH_PREV_3D[:, own].copy_(ph_cold[:, sl])
     sub.PH_PREV_ALT_CO2_3D[:, own].copy_(ph_cold[:, sl])   # both solves share inputs (BGC_mod.F90:975): same root
-    ctx2 = host.Context(nL, slab + 1, device=0, parms=parms)
+    ctx2 = host.Context(nL, slab, device=0, parms=parms)
     torch.cuda.synchronize()   # the copies above ran on torch's stream, the ctx has its own
     host.BGC_SourceSink(ctx2, sub)
     ctx2.synchronize()
     assert torch.equal(sub.BGC_tendencies[:, :, own], d.BGC_tendencies[:, :, sl])
-    assert torch.equal(sub.diag["diag_POC_REMIN"][:, own], d.diag["diag_POC_REMIN"][:, sl])
+    for nm in ("diag_POC_REMIN", "diag_photoC", "diag_Jint_Ctot", "diag_CO3", "diag_zsatcalc"):
+        assert torch.equal(sub.diag[nm][..., own], d.diag[nm][..., sl]), nm
     assert torch.equal(sub.PH_PREV_3D[:, own], d.PH_PREV_3D[:, sl])
     ctx2.close()
     ctx.close()
@@ -841,4 +841,178 @@ def test_error_codes():
     rc = L.bgc_source_sink(ctx.ptr, C.byref(cols.c_input()), C.byref(cfo), C.byref(cout), C.byref(cdg), C.c_int(8),
                            C.c_int(32), C.c_int(33), C.c_int(1), C.c_int(abi.BGC_MEM_HOST_FORTRAN))
     assert rc == abi.DEFINES["BGC_ERR_ARG"]       # numColumns > numColumnsMax
+    ctx.close()
+
+
+# ------------------------------------------------------------------ round 2
+@pytest.mark.parametrize("nC_a,nC_b", [(257, 258), (301, 512), (1, 2)])
+def test_block_width_does_not_change_the_bits(nC_a, nC_b):
+    """The same columns computed in blocks of different numColumnsMax - odd (8-byte cp.async staging)
+    and even (TMA bulk copies), one block and several - give identical bits in every output: there
+    is ONE instantiation of the sweep's arithmetic (k_eco.cu)."""
+    import torch
+    nL = 37
+    parms = host.Parms()
+    n = min(nC_a, nC_b)
+    base, _, _ = parity.make_bgc(nL, n, parms, ragged=True)
+    outs = []
+    for nC in (nC_a, nC_b):
+        cols = pkg.BgcColumns(nL, nC, n)
+        for nm in ("BGC_tracers", "PotentialTemperature", "Salinity", "cell_center_depth", "cell_thickness",
+                   "cell_bottom_depth"):
+            getattr(cols, nm)[:, :n] = getattr(base, nm)
+        cols.cell_latitude[:n] = base.cell_latitude
+        cols.number_of_active_levels[:n] = base.number_of_active_levels
+        for nm, a in base.forcing.items():
+            if a.ndim == 2 and a.shape[0] == nL:
+                cols.forcing[nm][:, :n] = a
+            else:
+                cols.forcing[nm][:n] = a
+        ctx = host.Context(nL, nC, device=0, parms=parms)
+        got = parity.run_gpu_bgc(ctx, cols, device_mode=True)
+        got = parity.run_gpu_bgc(ctx, got, device_mode=True)      # warm pass as well
+        outs.append(got)
+        ctx.close()
+    a, b = outs
+    assert np.array_equal(a.BGC_tendencies[:, :n], b.BGC_tendencies[:, :n])
+    assert np.array_equal(a.PH_PREV_3D[:, :n], b.PH_PREV_3D[:, :n])
+    for nm in a.diag:
+        x, y = a.diag[nm], b.diag[nm]
+        if x.ndim >= 2 and x.shape[0] == nL:
+            assert np.array_equal(x[:, :n], y[:, :n]), nm
+        else:
+            assert np.array_equal(x[:n], y[:n]), nm
+
+
+def test_comp_co3terms_and_sat_vals_points(o):
+    """The rest of the co2calc module's public trio on the GPU (co2calc.F90:214-316, :1096-1238), batched,
+    against the oracle point by point: surface and deep levels, cold and warm brackets."""
+    ctx, parms = _ctx(2, 64)
+    n = 6000
+    pts = pkg.synth_co2_points(n)
+    rng = np.random.default_rng(11)
+    k = rng.integers(1, 81, n).astype(np.int32)
+    k[:100] = 1
+    depth = np.where(k == 1, 5.0, rng.uniform(10.0, 6000.0, n))
+    for warm in (False, True):
+        lo, hi = (pts["phlo"] - 1.0, pts["phhi"]) if not warm else (pts["phlo"], pts["phhi"])
+        ref = {nm: np.zeros(n) for nm in ("pH", "H2CO3", "HCO3", "CO3")}
+        sat_c, sat_a = np.zeros(n), np.zeros(n)
+        for i in range(n):
+            r = o.comp_CO3terms(int(k[i]), depth[i], pts["temp"][i], pts["salt"][i], pts["dic"][i], pts["ta"][i],
+                                pts["pt"][i], pts["sit"][i], lo[i], hi[i])
+            for nm in ref:
+                ref[nm][i] = r[nm]
+            sat_c[i], sat_a[i] = o.co3_sat_vals(int(k[i]), depth[i], pts["temp"][i], pts["salt"][i])
+        got = host.comp_CO3terms_points(ctx, k, depth, pts["temp"], pts["salt"], pts["dic"], pts["ta"], pts["pt"],
+                                        pts["sit"], lo, hi)
+        for nm in ref:
+            assert parity.nerr(got[nm], ref[nm]) <= parity.TOL_SOLVER, (warm, nm)
+        assert np.max(np.abs(10.0 ** -got["pH"] - 10.0 ** -ref["pH"])) <= 1e-10
+        gc, ga = host.comp_co3_sat_vals_points(ctx, k, depth, pts["temp"], pts["salt"])
+        assert parity.nerr(gc, sat_c) <= parity.TOL_TEND and parity.nerr(ga, sat_a) <= parity.TOL_TEND
+        pts["phlo"], pts["phhi"] = ref["pH"] - 0.2, ref["pH"] + 0.2
+    # scalar level index for the whole batch
+    g1 = host.comp_co3_sat_vals_points(ctx, 1, depth, pts["temp"], pts["salt"])
+    g2 = host.comp_co3_sat_vals_points(ctx, np.ones(n, np.int32), depth, pts["temp"], pts["salt"])
+    assert np.array_equal(g1[0], g2[0]) and np.array_equal(g1[1], g2[1])
+    st = ctx.status()
+    assert st["no_bracket"] == 0 and st["no_convergence"] == 0, st
+    ctx.close()
+
+
+class _RawDevice:
+    """a raw device address as something torch.as_tensor understands"""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f8", "data": (int(ptr), False),
+                                         "version": 2}
+
+
+def test_resident_state_and_restart_round_trip(o):
+    """bgc_state_*: PH_PREV_3D / PH_PREV_ALT_CO2_3D / surface_pH / surface_pH_alt_co2 (the fields the
+    reference carries between steps and writes to restart files, BGC_parms.F90:151-152, :170-171) live
+    in the ctx; a device-resident model passes the state pointers every step.  A run that is stopped
+    after two steps, written out with bgc_state_get and restarted in a NEW ctx with bgc_state_set
+    continues with the bits of the uninterrupted run; the reference agrees at the usual tolerances."""
+    import torch
+    nL, nC = 31, 200
+    parms = host.Parms()
+    po = o.Parms()
+    cols, _, _ = parity.make_bgc(nL, nC, parms, ragged=True)
+
+    def resident(ctx):
+        dev = host.DeviceBgcColumns(nL, nC).load(cols)
+        dev.PH_PREV_3D = torch.as_tensor(_RawDevice(ctx.state_device_ptr("PH_PREV_3D", nL, nC), (nL, nC)), device="cuda")
+        dev.PH_PREV_ALT_CO2_3D = torch.as_tensor(_RawDevice(ctx.state_device_ptr("PH_PREV_ALT_CO2_3D", nL, nC), (nL, nC)),
+                                                 device="cuda")
+        dev.forcing["surface_pH"] = torch.as_tensor(_RawDevice(ctx.state_device_ptr("surface_pH", nL, nC), (nC,)), device="cuda")
+        dev.forcing["surface_pH_alt_co2"] = torch.as_tensor(
+            _RawDevice(ctx.state_device_ptr("surface_pH_alt_co2", nL, nC), (nC,)), device="cuda")
+        return dev
+
+    def step(ctx, dev):
+        host.BGC_SourceSink(ctx, dev, True, True)
+        host.BGC_SurfaceFluxes(ctx, dev)
+        ctx.synchronize()
+
+    ctx = host.Context(nL, nC, device=0, parms=parms)
+    dev = resident(ctx)
+    ctx.synchronize()
+    assert float(dev.PH_PREV_3D.abs().max()) == 0.0          # created zero-filled: "no previous pH"
+    step(ctx, dev); step(ctx, dev)
+    names = ("PH_PREV_3D", "PH_PREV_ALT_CO2_3D", "surface_pH", "surface_pH_alt_co2")
+    saved = {nm: ctx.state_get(nm, nL, nC) for nm in names}          # what a restart file holds
+    assert np.array_equal(saved["PH_PREV_3D"], dev.PH_PREV_3D.cpu().numpy())
+    assert np.array_equal(saved["surface_pH"], dev.forcing["surface_pH"].cpu().numpy())
+    step(ctx, dev)                                                   # step 3 of the uninterrupted run
+    want = dev.store(cols.copy())
+    ctx.close()
+
+    ctx2 = host.Context(nL, nC, device=0, parms=parms)                 # the restarted run
+    dev2 = resident(ctx2)
+    for nm in names:
+        ctx2.state_set(nm, saved[nm], nL, nC)
+        assert np.array_equal(ctx2.state_get(nm, nL, nC), saved[nm])
+    step(ctx2, dev2)
+    got = dev2.store(cols.copy())
+    assert np.array_equal(got.BGC_tendencies, want.BGC_tendencies)
+    assert np.array_equal(got.PH_PREV_3D, want.PH_PREV_3D)
+    assert np.array_equal(got.forcing["netFlux"], want.forcing["netFlux"])
+    assert np.array_equal(got.forcing["surface_pH"], want.forcing["surface_pH"])
+    ctx2.close()
+    # and the reference, three steps
+    ref = cols.copy()
+    for _ in range(3):
+        o.BGC_SourceSink(po, ref, True, nthreads=o.max_threads())
+        o.BGC_SurfaceFluxes(po, ref, nthreads=o.max_threads())
+    parity.compare_bgc_source_sink(ref, want)
+    assert parity.nerr(want.forcing["surface_pH"], ref.forcing["surface_pH"]) <= parity.TOL_SOLVER
+
+
+def test_mpas_thickness_weighted_tendency():
+    """bgc_layout_soa_to_mpas_weighted: tend_mpas(n,k,cell) += layerThickness(k,cell) * tend_soa(cell,k,slot[n]),
+    the way MPAS-Ocean folds the BGC tendencies into its thickness-weighted tracer tendencies."""
+    import torch
+    nT, nL, nC, nS = 30, 9, 777, 30
+    ctx, _ = _ctx(nL, nC)
+    g = torch.Generator(device="cpu").manual_seed(3)
+    tend_mpas = torch.rand((nC, nL, nT), generator=g, dtype=torch.float64).cuda()
+    h = (torch.rand((nC, nL), generator=g, dtype=torch.float64) * 100.0 + 1.0).cuda()     # (cell,k): k fastest
+    soa = torch.rand((nS, nL, nC), generator=g, dtype=torch.float64).cuda()
+    slot = [int(x) + 1 for x in torch.randperm(nS, generator=g)]
+    want = tend_mpas.clone()
+    for n in range(nT):
+        want[:, :, n] = want[:, :, n] + (h * soa[slot[n] - 1].T)
+    got = tend_mpas.clone()
+    torch.cuda.synchronize()
+    ctx.soa_to_mpas(soa.data_ptr(), got.data_ptr(), slot, nL, nC, alpha=1.0, beta=1.0, dev_weight=h.data_ptr())
+    ctx.synchronize()
+    assert (got - want).abs().max().item() <= 1e-13 * want.abs().max().item()
+    # alpha scales the weighted term; weight = None is the unweighted form
+    got2 = tend_mpas.clone()
+    ctx.soa_to_mpas(soa.data_ptr(), got2.data_ptr(), slot, nL, nC, alpha=0.5, beta=0.0, dev_weight=h.data_ptr())
+    ctx.synchronize()
+    for n in range(nT):
+        assert torch.allclose(got2[:, :, n], 0.5 * h * soa[slot[n] - 1].T, rtol=1e-15, atol=0)
     ctx.close()

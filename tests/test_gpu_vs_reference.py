@@ -133,3 +133,20 @@ def test_co2calc_points(warm):
     for k in r:
         assert parity.nerr(g[k], r[k]) <= parity.TOL_SOLVER, k
     ctx.close()
+
+
+@pytest.mark.parametrize("seed0", [0, 12, 24, 36])
+def test_differential_fuzz_slice(seed0):
+    """A fixed-seed slice of scripts/fuzz_gpu_vs_reference.py (the whole campaign's log is under
+    profiles/): random parameter and functional-group tables, switches, zero / tiny / huge
+    concentrations, anoxic, fresh and hot water, shallow bottoms, dark and bright columns, cold /
+    warm / off-target brackets, block widths 1, 7, 256, 257, device-resident and host-layout calls -
+    inputs that reach the bracket-growth loop (co2calc.F90:920-938) and the bottom-cell branches
+    (BGC_mod.F90:2522-2631) far from the synthetic profiles."""
+    sys.path.insert(0, os.path.join(parity.REPO, "scripts"))
+    import fuzz_gpu_vs_reference as fz
+    report = {}
+    for seed in range(seed0, seed0 + 12):
+        fz.one_round(seed, report)
+    bad = {s: r for s, r in report.items() if not (r["worst"] <= parity.TOL_TEND and r["ph"] <= parity.TOL_SOLVER)}
+    assert not bad, bad
