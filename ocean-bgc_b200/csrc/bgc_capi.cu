@@ -802,6 +802,8 @@ static int source_sink_device(bgc_ctx *c, const BgcInput *in, const BgcForcing *
   // declared in BGC_diagnostics_type but never zeroed nor written by the reference
   ea.d.diag_POC_ACCUM = ea.d.diag_DONr_remin = ea.d.diag_DOPr_remin = nullptr;
   ea.status = c->d_status;
+  if (!bgc::eco_rows_from_tables(c->bgc_tab, ea))
+    return fail(BGC_ERR_PARAMS, "bgc_source_sink: the tracer index tables do not cover the %d tracer slots", BGC_TRACER_CNT);
   // diag_mode 2 = every array the sweep owns is present -> unchecked stores.  The arrays of
   // the other two kernels and the three never-touched members of the reference type may be
   // NULL without leaving that mode.

@@ -70,7 +70,14 @@ struct EcoArgs {
   unsigned long long *status;
   double *inv_partials;                  // NULL, or the fused stage 1 of the inventory reduction
   int bulk;                              // set by launch_eco_columns: stage the inputs with TMA bulk copies (16-byte aligned slabs)
+  // Canonical stage row -> 1-based tracer slot (k_eco.cu: rows 0..15 the plain tracers in BgcIndices
+  // order, 16+3a+{0,1,2} = C, Chl, Fe of group a, 28 = the Si tracer, 29 = the CaCO3 tracer); filled by
+  // eco_rows_from_tables.  tend_off[row] = (slot - 1) * nL * nC is set by launch_eco_columns.
+  int slot_of_row[BGC_TRACER_CNT];
+  unsigned tend_off[BGC_TRACER_CNT];
 };
+// fills a.slot_of_row from the ctx's index and functional-group tables; false if they do not cover the 30 slots
+bool eco_rows_from_tables(const BgcTables &t, EcoArgs &a);
 // diag_mode: 0 = no diagnostic array, 1 = any subset (NULL-checked stores), 2 = every array
 // the kernel owns is present (unchecked stores).  variant selects the launch shape
 // (k_eco.cu: launch_diag); 0 = default.

@@ -209,6 +209,19 @@ static_assert((0 ECO_DIAG_K2_LIST(COUNT_ONE)) + 13 == (0 BGC_DIAG_K2_LIST(COUNT_
 //                       which misses the few KB of L1 left beside a 221 KB carve-out)
 //   2 mbarriers
 enum { R_T = BGC_TRACER_CNT, R_ZMID, R_DZ, R_ZBOT, R_FESED, R_S, R_ROWS };
+// Canonical stage rows of the 30 tracers.  The host chooses the tracer slots (BGC_indices_type), so a
+// slot number is a run-time value; the stage is filled through a row -> slot table instead
+// (EcoArgs::slot_of_row, built by bgc_capi.cu from the ctx's index tables), and from there on every
+// tracer is a compile-time row: one LDS / STS with an immediate offset, no index arithmetic.
+//   rows 0..15  the plain tracers in the declaration order of BgcIndices
+//   rows 16+3a+{0,1,2}  C, Chl, Fe of functional group a
+//   row 28 / 29 the Si tracer of the silicifier / the CaCO3 tracer of the calcifier
+enum { po4_row = 0, no3_row, sio3_row, nh4_row, fe_row, o2_row, dic_row, dic_alt_co2_row, alk_row, doc_row,
+       don_row, dofe_row, dop_row, dopr_row, donr_row, zooC_row, GROUP_ROW0 = 16, SI_ROW = 28, CA_ROW = 29 };
+#define G_C(a_) (GROUP_ROW0 + 3 * (a_))
+#define G_CHL(a_) (GROUP_ROW0 + 3 * (a_) + 1)
+#define G_FE(a_) (GROUP_ROW0 + 3 * (a_) + 2)
+static_assert(G_FE(BGC_AUTOTROPH_CNT - 1) + 1 == SI_ROW && CA_ROW + 1 == BGC_TRACER_CNT, "canonical tracer rows");
 enum { X_KMAX = 0, X_ZPHOTO = 4, X_ZNO3 = 8, X_ZCACO3 = 12,
        X_JC = 16, X_JC100, X_JN, X_JN100, X_JP, X_JP100, X_JSI, X_JSI100,
        X_CHL100, X_BSI, X_CACO3ZINT, X_PHOTOCZINT, X_PHOTOCNO3ZINT, X_O2MIN,
@@ -246,7 +259,7 @@ __device__ __forceinline__ void cp_async8(unsigned dst, const void *src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_but_one() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 template <int DIAG, int BLOCK, int MINB>
@@ -331,52 +344,59 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
   __syncthreads();
   const int kmax_blk = s_kmax_blk;
   const unsigned slab_bytes = (unsigned)(min(BLOCK, nC - col0) * (int)sizeof(double));
-  // tracer slots the sweep never reads: DIC, ALK (carbonate kernel only) and DIC_ALT_CO2 (dead, :748)
-  const unsigned skip_slots = (1u << (I.dic_ind - 1)) | (1u << (I.alk_ind - 1)) | (1u << (I.dic_alt_co2_ind - 1));
+
+  // Source of every stage row (level 0, this block's first column): the tracer rows go through the
+  // row -> slot table, the rest are the caller's separate arrays.
+  __shared__ const double *s_rowsrc[R_ROWS];
+  if (tid < R_ROWS) {
+    const double *p;
+    if (tid < BGC_TRACER_CNT) p = A.tracers + (size_t)(A.slot_of_row[tid] - 1) * (size_t)nLnC;
+    else if (tid == R_T) p = A.T;
+    else if (tid == R_ZMID) p = A.zmid;
+    else if (tid == R_DZ) p = A.dz;
+    else if (tid == R_ZBOT) p = A.zbot;
+    else if (tid == R_FESED) p = A.fesedflux;
+    else p = A.S;
+    s_rowsrc[tid] = p + col0;
+  }
+  __syncthreads();
 
   // Fetch level `kk` of every input array into stage `kk & 1`.  Lane 0 of every warp issues a
   // share of the bulk copies (rows w, w + NW, ...) so that no single warp carries the whole
   // issue cost; thread 0 also arms the mbarrier with the byte count of the whole level.  (A
   // copy that lands before the arm only drives the transaction count negative for a moment:
-  // the phase cannot complete before thread 0's arrival.)
+  // the phase cannot complete before thread 0's arrival.)  Rows the sweep never reads are not
+  // fetched: DIC, ALK (carbonate kernel only), DIC_ALT_CO2 (dead, :748), S without diagnostics.
   constexpr int NW = BLOCK / 32;
-  auto row_src = [&](int r) -> const double * {
-    if (r < BGC_TRACER_CNT) return A.tracers + (size_t)r * (size_t)nLnC;
-    switch (r) {
-      case R_T:     return A.T;
-      case R_ZMID:  return A.zmid;
-      case R_DZ:    return A.dz;
-      case R_ZBOT:  return A.zbot;
-      case R_FESED: return A.fesedflux;
-      default:      return A.S;
-    }
-  };
+  constexpr int N_FETCH_ROWS = DIAG ? R_ROWS : R_S;
+  auto row_is_fetched = [](int r) { return r != dic_row && r != dic_alt_co2_row && r != alk_row; };
   auto fetch_level = [&](int kk) {
     double *dst = smem + (size_t)(kk & 1) * R_ROWS * BLOCK;
-    const size_t off = (size_t)nC * (size_t)kk + (size_t)col0;
+    const size_t off = (size_t)nC * (size_t)kk;
     if (bulk) {
       if (tid & 31) return;
       const unsigned bar = smem_u32(&bars[kk & 1]);
-      if (tid == 0) mbar_expect_tx(bar, slab_bytes * (unsigned)((BGC_TRACER_CNT - 3) + 5 + (DIAG ? 1 : 0)));
-#pragma unroll 1
-      for (int r = tid >> 5; r < (DIAG ? R_ROWS : R_S); r += NW) {
-        if (r < BGC_TRACER_CNT && ((skip_slots >> r) & 1u)) continue;
-        bulk_g2s(smem_u32(dst + r * BLOCK), row_src(r) + off, slab_bytes, bar);
+      if (tid == 0) mbar_expect_tx(bar, slab_bytes * (unsigned)(N_FETCH_ROWS - 3));
+#pragma unroll
+      for (int j = 0; j < (N_FETCH_ROWS + NW - 1) / NW; ++j) {
+        const int r = (tid >> 5) + j * NW;
+        if (r < N_FETCH_ROWS && row_is_fetched(r))
+          bulk_g2s(smem_u32(dst + r * BLOCK), s_rowsrc[r] + off, slab_bytes, bar);
       }
-    } else if (in_range) {
+    } else {
+      if (in_range) {
 #pragma unroll 1
-      for (int r = 0; r < (DIAG ? R_ROWS : R_S); ++r) {
-        if (r < BGC_TRACER_CNT && ((skip_slots >> r) & 1u)) continue;
-        cp_async8(smem_u32(dst + r * BLOCK + tid), row_src(r) + off + tid);
+        for (int r = 0; r < N_FETCH_ROWS; ++r)
+          if (row_is_fetched(r)) cp_async8(smem_u32(dst + r * BLOCK + tid), s_rowsrc[r] + off + tid);
       }
+      cp_async_commit();
     }
   };
-  // (cp.async mode: one group is committed per level whether or not anything was fetched, so
-  //  that "all but the most recent group" always means "this level has landed")
+  // Level 0 is fetched here; level k + 1 is requested from the middle of level k (fetch_next below):
+  // right after a block barrier every warp would stall on the issue latency at the same time, while
+  // half a level later the warps have drifted apart and the other warp of the scheduler has work.
+  // Half a level (~10 k cycles) is several HBM round trips, so the data is there in time.
   if (kmax_blk > 0) fetch_level(0);
-  if (!bulk) cp_async_commit();
-  if (kmax_blk > 1) fetch_level(1);
-  if (!bulk) cp_async_commit();
 
   for (int k = 0; k < nL; ++k) {
     const unsigned i2 = (unsigned)col + (unsigned)nC * (unsigned)k;
@@ -385,10 +405,13 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
     if (bulk) {
       if (k < kmax_blk) mbar_wait(smem_u32(&bars[k & 1]), (unsigned)((k >> 1) & 1));
     } else {
-      cp_async_wait_but_one();   // this thread's own column of level k has landed (it reads no other)
+      cp_async_wait_all();       // this thread's own column of level k has landed (it reads no other)
     }
+    bool fetched_next = false;
+#define FETCH_NEXT() do { if (!fetched_next) { fetched_next = true; if (k + 1 < kmax_blk) fetch_level(k + 1); } } while (0)
 
     if (k >= kmax) {
+      FETCH_NEXT();
       // ---- inactive cell: the reference's whole-array zero fills
       if (inv && k < kmax_blk) {
 #pragma unroll
@@ -404,8 +427,8 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
       }
     } else {
 
-#define TR(ind_) fmax(0.0, IN((ind_) - 1))
-#define TEND(ind_) A.tend[i2 + (unsigned)((ind_) - 1) * nLnC]
+#define TR(row_) fmax(0.0, IN(row_))
+#define TEND(row_) A.tend[i2 + A.tend_off[row_]]
 
     // ---- this level's inputs (setup_loop clamp folded in, :747-783)
     const double TEMP = IN(R_T);
@@ -414,9 +437,9 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
     const double zbot = IN(R_ZBOT);
     // (the tracers that only the code after the functional-group loop needs are read from the
     //  stage there: they would otherwise sit in registers across the whole loop)
-    const double PO4_loc = TR(I.po4_ind), NO3_loc = TR(I.no3_ind), SiO3_loc = TR(I.sio3_ind),
-                 NH4_loc = TR(I.nh4_ind), Fe_loc = TR(I.fe_ind), DOP_loc = TR(I.dop_ind),
-                 zooC_loc = TR(I.zooC_ind);
+    const double PO4_loc = TR(po4_row), NO3_loc = TR(no3_row), SiO3_loc = TR(sio3_row),
+                 NH4_loc = TR(nh4_row), Fe_loc = TR(fe_row), DOP_loc = TR(dop_row),
+                 zooC_loc = TR(zooC_row);
 
     // ---- temperature function, loss thresholds (:1041-1094)
     const double Tfunc = fpow_base(Q_10, kLnQ10, cdiv(((TEMP + T0K) - (Tref + T0K)), 10.0, 0.1));
@@ -438,16 +461,16 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
 #pragma unroll
     for (int a = 0; a < NA; ++a) {
       const BgcAutotroph &at = c_eco.a[a];
-      double vChl = TR(at.Chl_ind), vC = TR(at.C_ind), vFe = TR(at.Fe_ind);
-      double vSi = (at.Si_ind > 0) ? TR(at.Si_ind) : 0.0;
-      double vCa = (at.CaCO3_ind > 0) ? TR(at.CaCO3_ind) : 0.0;
+      double vChl = TR(G_CHL(a)), vC = TR(G_C(a)), vFe = TR(G_FE(a));
+      double vSi = (at.Si_ind > 0) ? TR(SI_ROW) : 0.0;
+      double vCa = (at.CaCO3_ind > 0) ? TR(CA_ROW) : 0.0;
       bool zero_mask = vChl == 0.0 || vC == 0.0 || vFe == 0.0;
       if (at.Si_ind > 0) zero_mask = zero_mask || vSi == 0.0;
       if (zero_mask) { vChl = 0.0; vC = 0.0; vFe = 0.0; vSi = 0.0; vCa = 0.0; }
       // masked values go back into the stage rows, where the rolled loop picks them up
-      IN(at.Chl_ind - 1) = vChl; IN(at.C_ind - 1) = vC; IN(at.Fe_ind - 1) = vFe;
-      if (at.Si_ind > 0) IN(at.Si_ind - 1) = vSi;
-      if (at.CaCO3_ind > 0) IN(at.CaCO3_ind - 1) = vCa;
+      IN(G_CHL(a)) = vChl; IN(G_C(a)) = vC; IN(G_FE(a)) = vFe;
+      if (at.Si_ind > 0) IN(SI_ROW) = vSi;
+      if (at.CaCO3_ind > 0) IN(CA_ROW) = vCa;
       Chl_sum = Chl_sum + vChl;
       if (DIAG) Chl_100 = Chl_100 + vChl * pt100;
 
@@ -505,7 +528,7 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
     for (int a = 0; a < NA; ++a) {
       const BgcAutotroph &at = c_eco.a[a];
       const unsigned ia = i2 + (unsigned)a * nLnC;
-      const double aChl = IN(at.Chl_ind - 1), aC = IN(at.C_ind - 1), aFe = IN(at.Fe_ind - 1), Pprime = Pp[a];
+      const double aChl = IN(G_CHL(a)), aC = IN(G_C(a)), aFe = IN(G_FE(a)), Pprime = Pp[a];
       const bool has_Si = at.Si_ind > 0, has_Ca = at.CaCO3_ind > 0;
 
       // ---- zero-biomass shortcut.  A group whose Chl, C or Fe is exactly zero has been zeroed
@@ -547,13 +570,13 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
         zd_den = zd_den + (0.0 + epsC * epsTinv);
         if (has_Ca) Ca_prod = 0.0;
         if (has_Si) Si_prod = 0.0;
-        TEND(at.C_ind) = 0.0; TEND(at.Chl_ind) = 0.0; TEND(at.Fe_ind) = 0.0;
-        if (has_Si) TEND(at.Si_ind) = 0.0;
-        if (has_Ca) TEND(at.CaCO3_ind) = 0.0;
+        TEND(G_C(a)) = 0.0; TEND(G_CHL(a)) = 0.0; TEND(G_FE(a)) = 0.0;
+        if (has_Si) TEND(SI_ROW) = 0.0;
+        if (has_Ca) TEND(CA_ROW) = 0.0;
         if (inv) {
-          IN(at.Chl_ind - 1) = 0.0; IN(at.C_ind - 1) = 0.0; IN(at.Fe_ind - 1) = 0.0;
-          if (has_Si) IN(at.Si_ind - 1) = 0.0;
-          if (has_Ca) IN(at.CaCO3_ind - 1) = 0.0;
+          IN(G_CHL(a)) = 0.0; IN(G_C(a)) = 0.0; IN(G_FE(a)) = 0.0;
+          if (has_Si) IN(SI_ROW) = 0.0;
+          if (has_Ca) IN(CA_ROW) = 0.0;
         }
         continue;
       }
@@ -567,9 +590,9 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
       double Qsi = 0.0, gQsi = 0.0, QCaCO3 = 0.0;
       if (has_Si) {
 #ifdef BGC_STRICT
-        Qsi = fmin(IN(at.Si_ind - 1) / (aC + epsC), gQsi_max);
+        Qsi = fmin(IN(SI_ROW) / (aC + epsC), gQsi_max);
 #else
-        Qsi = fmin(IN(at.Si_ind - 1) * rCden, gQsi_max);
+        Qsi = fmin(IN(SI_ROW) * rCden, gQsi_max);
 #endif
       }
       double gQfe = at.gQfe_0;
@@ -586,9 +609,9 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
       }
       if (has_Ca) {
 #ifdef BGC_STRICT
-        QCaCO3 = IN(at.CaCO3_ind - 1) / (aC + epsC);
+        QCaCO3 = IN(CA_ROW) / (aC + epsC);
 #else
-        QCaCO3 = IN(at.CaCO3_ind - 1) * rCden;
+        QCaCO3 = IN(CA_ROW) * rCden;
 #endif
         if (QCaCO3 > QCaCO3_max) QCaCO3 = QCaCO3_max;
       }
@@ -850,27 +873,27 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
         const double w = auto_graze + auto_loss + auto_agg;
         const double t_autoC = photoC - w;
         const double t_autoChl = photoacc - thetaC * w, t_autoFe = photoFe - Qfe * w;
-        TEND(at.C_ind) = t_autoC;
-        TEND(at.Chl_ind) = t_autoChl;
-        TEND(at.Fe_ind) = t_autoFe;
+        TEND(G_C(a)) = t_autoC;
+        TEND(G_CHL(a)) = t_autoChl;
+        TEND(G_FE(a)) = t_autoFe;
         s_tC = s_tC + t_autoC;
         s_QpC = s_QpC + at.Qp * t_autoC;
         if (inv) {   // the group's inputs have been read: their rows carry tendency*dz from here on
-          IN(at.Chl_ind - 1) = t_autoChl * dz;
-          IN(at.C_ind - 1) = t_autoC * dz;
-          IN(at.Fe_ind - 1) = t_autoFe * dz;
+          IN(G_CHL(a)) = t_autoChl * dz;
+          IN(G_C(a)) = t_autoC * dz;
+          IN(G_FE(a)) = t_autoFe * dz;
         }
         if (has_Si) {
           const double t = photoSi - Qsi * w;
-          TEND(at.Si_ind) = t;
+          TEND(SI_ROW) = t;
           s_tSi = s_tSi + t;
-          if (inv) IN(at.Si_ind - 1) = t * dz;
+          if (inv) IN(SI_ROW) = t * dz;
         }
         if (has_Ca) {
           const double t = CaCO3_PROD - QCaCO3 * w;
-          TEND(at.CaCO3_ind) = t;
+          TEND(CA_ROW) = t;
           s_tCaCO3 = s_tCaCO3 + t;
-          if (inv) IN(at.CaCO3_ind - 1) = t * dz;
+          if (inv) IN(CA_ROW) = t * dz;
         }
       }
 
@@ -889,8 +912,10 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
       }
     }   // functional groups
 
-    const double O2_loc = TR(I.o2_ind), DOC_loc = TR(I.doc_ind), DON_loc = TR(I.don_ind),
-                 DOFe_loc = TR(I.dofe_ind), DOPr_loc = TR(I.dopr_ind), DONr_loc = TR(I.donr_ind);
+    FETCH_NEXT();   // request level k + 1 (see fetch_level)
+
+    const double O2_loc = TR(o2_row), DOC_loc = TR(doc_row), DON_loc = TR(don_row),
+                 DOFe_loc = TR(dofe_row), DOPr_loc = TR(dopr_row), DONr_loc = TR(donr_row);
     const double fesed = IN(R_FESED);
 
     // ---- zooplankton routing (:1395-1415)
@@ -1164,29 +1189,29 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
                          (s_tCaCO3 + s_tSi);
       if (!(fabs(chk) <= 1.7976931348623157e308) && A.status) atomicAdd(&A.status[3], 1ull);
     }
-    TEND(I.no3_ind) = t_no3;
-    TEND(I.nh4_ind) = t_nh4;
-    TEND(I.fe_ind) = t_fe;
-    TEND(I.sio3_ind) = t_sio3;
-    TEND(I.po4_ind) = t_po4;
-    TEND(I.zooC_ind) = t_zooC;
-    TEND(I.doc_ind) = t_doc;
-    TEND(I.don_ind) = t_don;
-    TEND(I.donr_ind) = t_donr;
-    TEND(I.dop_ind) = t_dop;
-    TEND(I.dopr_ind) = t_dopr;
-    TEND(I.dofe_ind) = t_dofe;
-    TEND(I.dic_ind) = t_dic;
-    TEND(I.dic_alt_co2_ind) = t_dic_alt;
-    TEND(I.alk_ind) = t_alk;
-    TEND(I.o2_ind) = t_o2;
+    TEND(no3_row) = t_no3;
+    TEND(nh4_row) = t_nh4;
+    TEND(fe_row) = t_fe;
+    TEND(sio3_row) = t_sio3;
+    TEND(po4_row) = t_po4;
+    TEND(zooC_row) = t_zooC;
+    TEND(doc_row) = t_doc;
+    TEND(don_row) = t_don;
+    TEND(donr_row) = t_donr;
+    TEND(dop_row) = t_dop;
+    TEND(dopr_row) = t_dopr;
+    TEND(dofe_row) = t_dofe;
+    TEND(dic_row) = t_dic;
+    TEND(dic_alt_co2_row) = t_dic_alt;
+    TEND(alk_row) = t_alk;
+    TEND(o2_row) = t_o2;
     if (inv) {   // every tracer input of this level has been consumed (see the group loop)
-      IN(I.no3_ind - 1) = t_no3 * dz; IN(I.nh4_ind - 1) = t_nh4 * dz; IN(I.fe_ind - 1) = t_fe * dz;
-      IN(I.sio3_ind - 1) = t_sio3 * dz; IN(I.po4_ind - 1) = t_po4 * dz; IN(I.zooC_ind - 1) = t_zooC * dz;
-      IN(I.doc_ind - 1) = t_doc * dz; IN(I.don_ind - 1) = t_don * dz; IN(I.donr_ind - 1) = t_donr * dz;
-      IN(I.dop_ind - 1) = t_dop * dz; IN(I.dopr_ind - 1) = t_dopr * dz; IN(I.dofe_ind - 1) = t_dofe * dz;
-      IN(I.dic_ind - 1) = t_dic * dz; IN(I.dic_alt_co2_ind - 1) = t_dic_alt * dz;
-      IN(I.alk_ind - 1) = t_alk * dz; IN(I.o2_ind - 1) = t_o2 * dz;
+      IN(no3_row) = t_no3 * dz; IN(nh4_row) = t_nh4 * dz; IN(fe_row) = t_fe * dz;
+      IN(sio3_row) = t_sio3 * dz; IN(po4_row) = t_po4 * dz; IN(zooC_row) = t_zooC * dz;
+      IN(doc_row) = t_doc * dz; IN(don_row) = t_don * dz; IN(donr_row) = t_donr * dz;
+      IN(dop_row) = t_dop * dz; IN(dopr_row) = t_dopr * dz; IN(dofe_row) = t_dofe * dz;
+      IN(dic_row) = t_dic * dz; IN(dic_alt_co2_row) = t_dic_alt * dz;
+      IN(alk_row) = t_alk * dz; IN(o2_row) = t_o2 * dz;
     }
 
     // ---- diagnostics and column integrals (:1796-1945)
@@ -1273,10 +1298,10 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
     // ---- end of level: every thread is done with stage k&1 (generic-proxy reads and the
     //      in-place mask writes) before the TMA unit refills it with level k+2.  The same
     //      barrier keeps the block's warps on one stretch of code (I-cache).
+    FETCH_NEXT();   // (not reached earlier only if a branch above was changed without its FETCH_NEXT)
+#undef FETCH_NEXT
     if (bulk) fence_proxy_async();
     __syncthreads();
-    if (k + 2 < kmax_blk) fetch_level(k + 2);
-    if (!bulk) cp_async_commit();
   }   // level loop
 
   // ---- per-column diagnostics
@@ -1312,11 +1337,11 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
     double *out = A.inv_partials + (size_t)blockIdx.x * (kEcoInvGroups * kInvGroup);
     s_slot[tid >> 5][tid & 31] = inv_acc;
     __syncthreads();
-    if (tid < BGC_TRACER_CNT) {
+    if (tid < BGC_TRACER_CNT) {   // lane = canonical row; the partials are indexed by tracer slot
       double t = 0.0;
 #pragma unroll
       for (int w = 0; w < BLOCK / 32; ++w) t += s_slot[w][tid];
-      out[tid] = t;
+      out[A.slot_of_row[tid] - 1] = t;
     }
     {
       const double cells = block_sum((double)kmax, s_red), cols = block_sum(kmax > 0 ? 1.0 : 0.0, s_red);
@@ -1363,11 +1388,39 @@ template <int DIAG>
 cudaError_t launch_diag(const EcoArgs &a0, int variant, cudaStream_t s) {
   EcoArgs a = a0;
   a.bulk = (slabs_are_bulk_copyable(a, DIAG != 0) && variant != 9) ? 1 : 0;
+  for (int r = 0; r < BGC_TRACER_CNT; ++r) {
+    if (a.slot_of_row[r] < 1 || a.slot_of_row[r] > BGC_TRACER_CNT) return cudaErrorInvalidValue;
+    a.tend_off[r] = (unsigned)(a.slot_of_row[r] - 1) * (unsigned)a.nL * (unsigned)a.nC;
+  }
   if (block_of(variant) == 256) return launch_variant<DIAG, 256, 1>(a, s);
   return launch_variant<DIAG, 128, 2>(a, s);
 }
 
 }  // namespace
+
+bool eco_rows_from_tables(const BgcTables &t, EcoArgs &a) {
+  const BgcIndices &I = t.ind;
+  const int plain[16] = {I.po4_ind, I.no3_ind, I.sio3_ind, I.nh4_ind, I.fe_ind, I.o2_ind, I.dic_ind, I.dic_alt_co2_ind,
+                         I.alk_ind, I.doc_ind, I.don_ind, I.dofe_ind, I.dop_ind, I.dopr_ind, I.donr_ind, I.zooC_ind};
+  bool seen[BGC_TRACER_CNT + 1] = {false};
+  auto put = [&](int row, int slot) {
+    a.slot_of_row[row] = slot;
+    if (slot >= 1 && slot <= BGC_TRACER_CNT) seen[slot] = true;
+  };
+  for (int r = 0; r < 16; ++r) put(r, plain[r]);
+  int si = 0, ca = 0;
+  for (int g = 0; g < BGC_AUTOTROPH_CNT; ++g) {
+    put(G_C(g), t.a[g].C_ind); put(G_CHL(g), t.a[g].Chl_ind); put(G_FE(g), t.a[g].Fe_ind);
+    if (t.a[g].Si_ind > 0) si = t.a[g].Si_ind;
+    if (t.a[g].CaCO3_ind > 0) ca = t.a[g].CaCO3_ind;
+  }
+  // a table without a silicifier / calcifier leaves that tracer unused by every group: its row takes
+  // the slot the index table names (it is still a tracer of the array: its tendency is written as zero)
+  put(SI_ROW, si > 0 ? si : I.diatSi_ind);
+  put(CA_ROW, ca > 0 ? ca : I.spCaCO3_ind);
+  for (int s = 1; s <= BGC_TRACER_CNT; ++s) if (!seen[s]) return false;
+  return true;
+}
 
 int eco_inventory_parts(const EcoArgs &a, int diag_mode, int variant) {
   (void)diag_mode;

@@ -26,11 +26,29 @@ DRY = "--dry" in sys.argv
 args = [a for a in sys.argv[1:] if a != "--dry"]
 
 
-def finite_nerr(got, ref):
+def finite_nerr(got, ref, floor=0.0):
+    """max |got - ref| / max(max |ref|, floor) over the cells where the reference is finite"""
     m = np.isfinite(ref)
     if not m.any():
         return 0.0
-    return parity.nerr(np.where(m, got, 0.0), np.where(m, ref, 0.0))
+    g, r = np.where(m, got, 0.0), np.where(m, ref, 0.0)
+    if floor > 0.0 and np.isfinite(g).all():
+        return float(np.max(np.abs(g - r)) / max(float(np.max(np.abs(r))), floor))
+    return parity.nerr(g, r)
+
+
+# Ill-conditioned by construction in the reference.  In the bottom cell OTHER_REMIN is
+# min(.., flux - POC_sed - SED_DENITRIF*dz*denitrif_C_N) / dz (BGC_mod.F90:2539-2549) and both
+# DENITRIF (:1574-1575) and O2_CONSUMPTION (:1786-1790, hence the O2 tendency) then form
+# (.. - OTHER_REMIN)/denitrif_C_N - SED_DENITRIF resp. (.. - SED_DENITRIF*denitrif_C_N - OTHER_REMIN):
+# whenever the second argument of that min() wins, +-SED_DENITRIF cancels and what remains is the
+# rounding noise of the cancelled terms.  SED_DENITRIF contains 0.99**(O2 - NO3) (:2532-2534), which the
+# fuzzer's NO3 of 10^4..10^5 mmol/m3 drives to 10^100..10^170; the reference's own result is then
+# noise of relative size 2^-53 * SED_DENITRIF (or an exact 0 where its IEEE division happens to
+# round back), and so is anybody's.  These three outputs are therefore measured against the
+# magnitude of the terms that cancel, like the conservation residuals in tests/parity.py.
+CANCELLING = ("diag_DENITRIF", "diag_O2_CONSUMPTION")
+DENITRIF_C_N = 117.0 / 136.0
 
 
 def one_round(seed, report):
@@ -55,14 +73,17 @@ def one_round(seed, report):
         got = parity.run_gpu_bgc(ctx, cols.copy(), device_mode=device_mode, alt_co2_use_eco=alt)
     worst, where = 0.0, ""
     act = ref.active_mask()
+    sed = np.where(act & np.isfinite(ref.diag["diag_SedDenitrif"]), ref.diag["diag_SedDenitrif"], 0.0)
+    cancel_scale = float(np.max(np.abs(sed / np.where(act, ref.cell_thickness, 1.0)), initial=0.0)) * DENITRIF_C_N
     for n in range(30):
-        e = finite_nerr(got.BGC_tendencies[:, :, n], ref.BGC_tendencies[:, :, n])
+        e = finite_nerr(got.BGC_tendencies[:, :, n], ref.BGC_tendencies[:, :, n],
+                        floor=cancel_scale if n + 1 == parms.ind.o2_ind else 0.0)
         if e > worst:
             worst, where = e, "tendency %d" % (n + 1)
     for nm, a in ref.diag.items():
         if nm in parity.SOLVER_DIAGS or nm.startswith("diag_Jint"):
             continue
-        e = finite_nerr(got.diag[nm], a)
+        e = finite_nerr(got.diag[nm], a, floor=cancel_scale if nm in CANCELLING else 0.0)
         if e > worst:
             worst, where = e, nm
     eph = finite_nerr(np.where(act, got.PH_PREV_3D, 0.0), np.where(act, ref.PH_PREV_3D, 0.0))
@@ -77,7 +98,7 @@ def one_round(seed, report):
     e = max(finite_nerr(dgot.DMS_tendencies, dref.DMS_tendencies), finite_nerr(mgot.MACROS_tendencies, mref.MACROS_tendencies))
     if e > worst:
         worst, where = e, "DMS/MACROS tendencies"
-    report[seed] = dict(worst=worst, where=where, ph=eph, nonfinite=int((~np.isfinite(ref.BGC_tendencies)).sum()),
+    report[seed] = dict(worst=worst, where=where, ph=eph, cancel_scale=cancel_scale, nonfinite=int((~np.isfinite(ref.BGC_tendencies)).sum()),
                         mode="device" if device_mode else "host", status=None if DRY else st)
 
 
