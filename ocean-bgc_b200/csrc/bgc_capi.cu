@@ -13,6 +13,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "bgc_b200.h"
@@ -93,6 +94,7 @@ enum { kNcclFloat64 = 8, kNcclSum = 0 };
 
 // ------------------------------------------------------------------ context
 struct DevBuf { void *p = nullptr; size_t bytes = 0; };
+struct HostStage { void *p = nullptr; size_t bytes = 0; };   // page-locked host staging
 
 struct bgc_ctx {
   int device = 0;
@@ -126,6 +128,7 @@ struct bgc_ctx {
   int eco_variant = 0;                      // launch shape of the column sweep (BGC_ECO_VARIANT, tuning only)
   int dms_variant = 0;                      // launch shape of the DMS tile kernel (BGC_DMS_VARIANT, tuning only)
   std::map<std::string, DevBuf> arena;      // persistent device buffers (host-layout mode, scratch)
+  std::map<std::string, HostStage> host_stage;   // page-locked staging buffers of the host-layout calls
   ncclComm_t comm = nullptr;
   int nranks = 1;
   // launch accounting (always on) and optional per-kernel CUDA-event timing
@@ -270,6 +273,7 @@ extern "C" int bgc_ctx_destroy(bgc_ctx *c) {
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   c->comm = nullptr;
   for (auto &kv : c->arena) if (kv.second.p) cudaFree(kv.second.p);
+  for (auto &kv : c->host_stage) if (kv.second.p) cudaFreeHost(kv.second.p);
   cudaFree(c->d_status); cudaFree(c->d_inventory);
   if (c->h_inventory) cudaFreeHost(c->h_inventory);
   for (auto &sp : c->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
@@ -975,6 +979,41 @@ extern "C" int bgc_source_sink(bgc_ctx *c, const BgcInput *in, const BgcForcing 
   });
 }
 
+
+// Level 1 of a host array A(k,col,n) (level fastest): nC*nSlabs doubles at a stride of nL.  The
+// copy engine handles an 8-byte-wide 2-D copy one row at a time (millions of rows on a full
+// mesh), so the surface-flux calls gather level 1 on the host instead - a few threads, each
+// striding through its share into a page-locked staging buffer of the ctx - and upload that
+// with ONE contiguous copy.
+static int gather_level1(bgc_ctx *c, const char *key, const double *host, int nL, size_t count, double *dev) {
+  HostStage &hs = c->host_stage[key];
+  if (hs.bytes < count * sizeof(double)) {
+    if (hs.p) cudaFreeHost(hs.p);
+    hs.p = nullptr; hs.bytes = 0;
+    CU(cudaHostAlloc(&hs.p, count * sizeof(double), cudaHostAllocDefault));
+    hs.bytes = count * sizeof(double);
+  }
+  double *st = (double *)hs.p;
+  // the previous call's upload from this buffer has completed: every host-layout call synchronises before returning
+  unsigned nthreads = std::thread::hardware_concurrency();
+  if (nthreads > 8) nthreads = 8;
+  if (count < (size_t)1 << 16 || nthreads < 2) nthreads = 1;
+  auto work = [=](size_t a, size_t b) { for (size_t i = a; i < b; ++i) st[i] = host[i * (size_t)nL]; };
+  if (nthreads == 1) {
+    work(0, count);
+  } else {
+    std::vector<std::thread> pool;
+    const size_t per = (count + nthreads - 1) / nthreads;
+    for (unsigned t = 0; t < nthreads; ++t) {
+      const size_t a = (size_t)t * per, b = a + per < count ? a + per : count;
+      if (a < b) pool.emplace_back(work, a, b);
+    }
+    for (auto &th : pool) th.join();
+  }
+  CU(cudaMemcpyAsync(dev, st, count * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  return BGC_OK;
+}
+
 // ------------------------------------------------------------------ BGC_SurfaceFluxes
 static int surface_fluxes_device(bgc_ctx *c, const BgcInput *in, BgcForcing *fo, BgcFluxDiagnostics *diag,
                                  int nL, int nC, int nCols) {
@@ -1012,9 +1051,7 @@ extern "C" int bgc_surface_fluxes(bgc_ctx *c, const BgcInput *in, BgcForcing *fo
   double *surf = nullptr;
   RC(arena_d(c, "surf.tracers", (size_t)nC * BGC_TRACER_CNT, &surf));
   if (!in->BGC_tracers) return fail(BGC_ERR_ARG, "bgc_surface_fluxes: BGC_tracers is NULL");
-  // host A(1,col,n) is strided by nL: a 2-D copy gathers level 1 of every (col,n)
-  CU(cudaMemcpy2DAsync(surf, sizeof(double), in->BGC_tracers, (size_t)nL * sizeof(double), sizeof(double),
-                       (size_t)nC * BGC_TRACER_CNT, cudaMemcpyHostToDevice, c->stream));
+  RC(gather_level1(c, "surf.tracers", in->BGC_tracers, nL, (size_t)nC * BGC_TRACER_CNT, surf));
   din.BGC_tracers = surf;
   void *v = nullptr;
 #define UPC(member, n) do { if (fo->member) { RC(up_c(c, h, "surf." #member, fo->member, sizeof(double), (n), &v)); dfo.member = (double *)v; } } while (0)
@@ -1274,8 +1311,7 @@ extern "C" int dms_surface_fluxes(bgc_ctx *c, const DmsInput *in, DmsForcing *fo
   if (!in->DMS_tracers) return fail(BGC_ERR_ARG, "dms_surface_fluxes: DMS_tracers is NULL");
   double *surf = nullptr;
   RC(arena_d(c, "dmssurf.tracers", (size_t)nC * DMS_TRACER_CNT, &surf));
-  CU(cudaMemcpy2DAsync(surf, sizeof(double), in->DMS_tracers, (size_t)nL * sizeof(double), sizeof(double),
-                       (size_t)nC * DMS_TRACER_CNT, cudaMemcpyHostToDevice, c->stream));
+  RC(gather_level1(c, "dmssurf.tracers", in->DMS_tracers, nL, (size_t)nC * DMS_TRACER_CNT, surf));
   din.DMS_tracers = surf;
   void *v = nullptr;
 #define UPC(member, n) do { if (fo->member) { RC(up_c(c, h, "dmssurf." #member, fo->member, sizeof(double), (n), &v)); dfo.member = (double *)v; } } while (0)

@@ -533,6 +533,109 @@ mpas_layout_kernel(const double *__restrict__ src, double *__restrict__ dst, con
   }
 }
 
+
+// Pipelined form of the same tile scheme: a persistent grid (a few blocks per SM) walks the
+// (cell block, level block) tiles, level blocks of one cell block first, and keeps TWO tiles in
+// shared memory - while the warps write tile i out, tile i + 1 is already landing through
+// cp.async (LDGSTS: no registers, no warp waiting).  The one-shot kernel above pays a full
+// HBM round trip between its load phase and its store phase in every block; here the only
+// exposed latency is the first tile of each block.  VEC = 2: 16-byte copies (even nT and a 16-byte
+// aligned array: every run starts aligned and holds whole pairs), VEC = 1: 8-byte copies.
+__device__ __forceinline__ void cp_async_8(double *dst, const double *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_16(double *dst, const double *src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+
+template <bool TO_SOA, int VEC>
+__global__ void __launch_bounds__(256)
+mpas_layout_pipe_kernel(const double *__restrict__ src, double *__restrict__ dst, const __grid_constant__ MpasMap M,
+                        int nL, int nC, int KB, double alpha, double beta, const double *__restrict__ weight,
+                        int ktiles, int ntiles) {
+  extern __shared__ __align__(16) double sm[];
+  const int nT = M.nT;
+  const int pitch = KB * nT + 2 + ((KB * nT) & 1);          // even (16-byte rows), 2 mod 4 mostly: 2-way conflicts at worst
+  const int tile_doubles = 32 * pitch;
+  // TO_SOA: [2][32][pitch] = the MPAS runs.  !TO_SOA: per buffer two planes, the SoA values
+  // (transposed into run order) and, when beta != 0, the old MPAS runs.
+  const int planes = TO_SOA ? 1 : 2;
+  const size_t nLnC = (size_t)nL * (size_t)nC;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const bool rmw = !TO_SOA && beta != 0.0;
+
+  auto issue = [&](int tile, int buf) {
+    const int cb = tile / ktiles, kb = tile - cb * ktiles;
+    const int c0 = cb * 32, k0 = kb * KB;
+    const int ncell = min(32, nC - c0), nk = min(KB, nL - k0);
+    const int run = nk * nT;
+    double *base = sm + (size_t)buf * planes * tile_doubles;
+    if (TO_SOA || rmw) {   // the cells' contiguous MPAS runs
+      double *plane = base + (TO_SOA ? 0 : tile_doubles);
+      const double *g = (TO_SOA ? src : dst);
+      for (int c = w; c < ncell; c += nw) {
+        const double *p = g + (size_t)nT * ((size_t)k0 + (size_t)nL * (size_t)(c0 + c));
+        double *q = plane + c * pitch;
+        if (VEC == 2) { for (int r = 2 * lane; r < run; r += 64) cp_async_16(q + r, p + r); }
+        else          { for (int r = lane; r < run; r += 32) cp_async_8(q + r, p + r); }
+      }
+    }
+    if (!TO_SOA && lane < ncell) {   // SoA rows: lanes are the 32 cells, 8-byte copies into run order
+      for (int kk = 0; kk < nk; ++kk)
+        for (int n = w; n < nT; n += nw)
+          if (M.slot[n] > 0)
+            cp_async_8(base + lane * pitch + kk * nT + n,
+                       src + (size_t)(c0 + lane) + (size_t)nC * (size_t)(k0 + kk) + (size_t)(M.slot[n] - 1) * nLnC);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  int tile = blockIdx.x, buf = 0;
+  if (tile < ntiles) issue(tile, 0);
+  while (tile < ntiles) {
+    const int next = tile + gridDim.x;
+    if (next < ntiles) {
+      issue(next, buf ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const int cb = tile / ktiles, kb = tile - cb * ktiles;
+    const int c0 = cb * 32, k0 = kb * KB;
+    const int ncell = min(32, nC - c0), nk = min(KB, nL - k0);
+    const int run = nk * nT;
+    const double *base = sm + (size_t)buf * planes * tile_doubles;
+    if (TO_SOA) {
+      if (lane < ncell) {
+        for (int kk = 0; kk < nk; ++kk)
+          for (int n = w; n < nT; n += nw)
+            if (M.slot[n] > 0)
+              dst[(size_t)(c0 + lane) + (size_t)nC * (size_t)(k0 + kk) + (size_t)(M.slot[n] - 1) * nLnC] =
+                  base[lane * pitch + kk * nT + n];
+      }
+    } else {
+      const double *old = base + tile_doubles;
+      for (int c = w; c < ncell; c += nw) {
+        double *p = dst + (size_t)nT * ((size_t)k0 + (size_t)nL * (size_t)(c0 + c));
+        const double *wp = weight ? weight + (size_t)k0 + (size_t)nL * (size_t)(c0 + c) : nullptr;
+        for (int r = lane, n = lane % nT, kk = lane / nT; r < run; r += 32) {
+          if (M.slot[n] > 0) {
+            double v = base[c * pitch + r];
+            if (wp) v = wp[kk] * v;
+            p[r] = rmw ? beta * old[c * pitch + r] + alpha * v : alpha * v;
+          }
+          n += 32;
+          while (n >= nT) { n -= nT; ++kk; }
+        }
+      }
+    }
+    __syncthreads();   // the buffer just consumed is refilled by the next iteration's issue
+    tile = next;
+    buf ^= 1;
+  }
+}
+
 // ---------------------------------------------------------------- diagnostics accumulation
 __global__ void __launch_bounds__(256)
 accumulate_kernel(const double *__restrict__ src, double *__restrict__ acc, int nL, int cc, int nC, int c0,
@@ -645,10 +748,8 @@ static int mpas_levels_per_block(int nT, bool to_soa) {
   return kb < 1 ? 1 : (kb > cap ? cap : kb);
 }
 template <bool TO_SOA>
-static cudaError_t launch_mpas_layout(const double *src, double *dst, const MpasMap &m, int nL, int nC, double alpha,
-                                      double beta, const double *weight, cudaStream_t s) {
-  if (nL <= 0 || nC <= 0 || m.nT <= 0) return cudaSuccess;
-  if (m.nT > kMpasMaxTracers) return cudaErrorInvalidValue;
+static cudaError_t launch_mpas_oneshot(const double *src, double *dst, const MpasMap &m, int nL, int nC, double alpha,
+                                       double beta, const double *weight, cudaStream_t s) {
   const int KB = mpas_levels_per_block(m.nT, TO_SOA);
   const size_t smem = (size_t)32 * (KB * m.nT + 1) * sizeof(double);
   auto kern = mpas_layout_kernel<TO_SOA>;
@@ -657,6 +758,59 @@ static cudaError_t launch_mpas_layout(const double *src, double *dst, const Mpas
   dim3 grid(cdiv((size_t)nC, 32), cdiv((size_t)nL, (size_t)KB));
   if (grid.y > 65535u) return cudaErrorInvalidConfiguration;
   kern<<<grid, 256, smem, s>>>(src, dst, m, nL, nC, KB, alpha, beta, weight);
+  return cudaGetLastError();
+}
+
+// BGC_MPAS_VARIANT (tuning only): 0 = pipelined kernel (default), 1 = one-shot tile kernel;
+// BGC_MPAS_KB / BGC_MPAS_BLOCKS_PER_SM override the level block and the persistent grid.
+static int env_int_or(const char *name, int dflt) {
+  const char *v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
+template <bool TO_SOA>
+static cudaError_t launch_mpas_layout(const double *src, double *dst, const MpasMap &m, int nL, int nC, double alpha,
+                                      double beta, const double *weight, cudaStream_t s) {
+  if (nL <= 0 || nC <= 0 || m.nT <= 0) return cudaSuccess;
+  if (m.nT > kMpasMaxTracers) return cudaErrorInvalidValue;
+  static const int variant = env_int_or("BGC_MPAS_VARIANT", 0);
+  if (variant == 1) return launch_mpas_oneshot<TO_SOA>(src, dst, m, nL, nC, alpha, beta, weight, s);
+  static const int kb_env = env_int_or("BGC_MPAS_KB", 0), bps_env = env_int_or("BGC_MPAS_BLOCKS_PER_SM", 0);
+  int KB = kb_env > 0 ? kb_env : (TO_SOA ? 4 : 2);
+  if (KB > nL) KB = nL;
+  const int planes = TO_SOA ? 1 : 2;
+  auto smem_of = [&](int kb) { return (size_t)2 * planes * 32 * (kb * m.nT + 2 + ((kb * m.nT) & 1)) * sizeof(double); };
+  while (KB > 1 && smem_of(KB) > 200 * 1024) --KB;
+  const size_t smem = smem_of(KB);
+  if (smem > 227 * 1024) return launch_mpas_oneshot<TO_SOA>(src, dst, m, nL, nC, alpha, beta, weight, s);
+  // 16-byte copies need every run to start 16-byte aligned on the MPAS side
+  const double *mp = TO_SOA ? src : dst;
+  const bool vec2 = (((size_t)mp) & 15u) == 0 && (m.nT & 1) == 0;   // even nT: every run is a whole number of 16-byte pairs
+  const int ktiles = (nL + KB - 1) / KB;
+  const long long ntiles_ll = (long long)((nC + 31) / 32) * ktiles;
+  if (ntiles_ll > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+  const int ntiles = (int)ntiles_ll;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int per_sm = (int)((227 * 1024) / (smem + 1024));
+  if (per_sm > 8) per_sm = 8;
+  if (per_sm < 1) per_sm = 1;
+  if (bps_env > 0) per_sm = bps_env;
+  int grid = sms * per_sm;
+  if (grid > ntiles) grid = ntiles;
+  cudaError_t e;
+  if (vec2) {
+    auto kern = mpas_layout_pipe_kernel<TO_SOA, 2>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, 256, smem, s>>>(src, dst, m, nL, nC, KB, alpha, beta, weight, ktiles, ntiles);
+  } else {
+    auto kern = mpas_layout_pipe_kernel<TO_SOA, 1>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, 256, smem, s>>>(src, dst, m, nL, nC, KB, alpha, beta, weight, ktiles, ntiles);
+  }
   return cudaGetLastError();
 }
 cudaError_t launch_mpas_to_soa(const double *mpas, double *soa, const MpasMap &m, int nL, int nC, cudaStream_t s) {

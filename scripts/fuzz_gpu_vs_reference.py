@@ -113,7 +113,8 @@ def main():
             print("seed", s, "crashed"); return 1
     bad = {s: r for s, r in report.items() if not (r["worst"] <= parity.TOL_TEND and r["ph"] <= parity.TOL_SOLVER)}
     print("%d rounds (%s), worst tendency/diagnostic error %.3e, worst pH error %.3e, %d rounds beyond tolerance"
-          % (rounds, "dry: oracle as the implementation" if DRY else "CUDA path",
+          % (rounds, "dry: oracle as the implementation" if DRY else
+             "CUDA path, %s flavour, seeds %d.." % (os.environ.get("BGC_B200_FLAVOUR", "prod"), seed0),
              max(r["worst"] for r in report.values()), max(r["ph"] for r in report.values()), len(bad)))
     for s, r in sorted(bad.items())[:20]:
         print("  seed %d (%s): %.3e at %s, pH %.3e, status %s" % (s, r["mode"], r["worst"], r["where"], r["ph"], r["status"]))

@@ -7,7 +7,7 @@ set -u
 TAG=${TAG:-r01}
 mkdir -p gpurun_out
 if [ "${SKIP_TESTS:-0}" != "1" ]; then
-  python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_$TAG.log 2>&1; echo "pytest exit $?" | tee -a gpurun_out/pytest_gpu_$TAG.log
+  python -m pytest tests -m gpu ${PYTEST_ARGS:--x} -q > gpurun_out/pytest_gpu_$TAG.log 2>&1; echo "pytest exit $?" | tee -a gpurun_out/pytest_gpu_$TAG.log
   tail -3 gpurun_out/pytest_gpu_$TAG.log
 fi
 python __graft_entry__.py smoke > gpurun_out/smoke_$TAG.log 2>&1; echo "smoke exit $?"
@@ -39,7 +39,11 @@ PY
 # optional extras (each a few seconds of box time): FUZZ=300 runs the differential fuzzer against the CUDA path,
 # MICRO=1 the read/write-mix micro-benchmark (scripts/micro/rw_mix must have been built: see its header)
 if [ -n "${FUZZ:-}" ]; then
-  python scripts/fuzz_gpu_vs_reference.py $FUZZ > gpurun_out/fuzz_gpu_$TAG.txt 2>&1; echo "fuzz exit $?"; tail -3 gpurun_out/fuzz_gpu_$TAG.txt
+  python scripts/fuzz_gpu_vs_reference.py $FUZZ ${FUZZ_SEED0:-0} > gpurun_out/fuzz_gpu_$TAG.txt 2>&1; echo "fuzz exit $?"; head -3 gpurun_out/fuzz_gpu_$TAG.txt
+  BGC_B200_FLAVOUR=strict python scripts/fuzz_gpu_vs_reference.py $FUZZ ${FUZZ_SEED0:-0} > gpurun_out/fuzz_gpu_strict_$TAG.txt 2>&1; echo "fuzz (strict flavour) exit $?"; head -3 gpurun_out/fuzz_gpu_strict_$TAG.txt
+fi
+if [ "${MPAS_SWEEP:-0}" = "1" ]; then
+  python scripts/micro/mpas_sweep.py > gpurun_out/mpas_sweep_$TAG.txt 2>&1; cat gpurun_out/mpas_sweep_$TAG.txt
 fi
 if [ "${MICRO:-0}" = "1" ] && [ -x scripts/micro/rw_mix ]; then
   scripts/micro/rw_mix > gpurun_out/rw_mix_$TAG.txt 2>&1; RW_MIX_STORES=1 scripts/micro/rw_mix > gpurun_out/rw_mix_stores_$TAG.txt 2>&1; tail -4 gpurun_out/rw_mix_stores_$TAG.txt
