@@ -498,6 +498,7 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
     const double PAR_out = PAR_in * eKPAR;
     XS(X_PAROUT) = PAR_out;
     const double PAR_avg = fdiv(PAR_in * (1.0 - eKPAR), KPARdz);
+    if (DIAG) ST2(diag_PAR_avg, PAR_avg);
     // light factor of the nitrification term (:1545-1556), formed here so that PAR_in, PAR_out and
     // KPARdz need not stay in registers across the functional-group loop
     double nitrif_light = 0.0;
@@ -913,6 +914,14 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
     }   // functional groups
 
     FETCH_NEXT();   // request level k + 1 (see fetch_level)
+    if (DIAG) {   // (every diagnostic is stored as soon as its value is final: short live ranges, no store bursts)
+      ST2(diag_tot_Nfix, tot_Nfix);
+      ST2(diag_tot_CaCO3_form, tot_CaCO3_form);
+      ST2(diag_auto_graze_TOT, s_auto_graze);
+      ST2(diag_photoC_TOT, s_photoC);
+      ST2(diag_photoC_NO3_TOT, photoC_NO3_TOT);
+      ST2(diag_O2_PRODUCTION, O2_PRODUCTION);
+    }
 
     const double O2_loc = TR(o2_row), DOC_loc = TR(doc_row), DON_loc = TR(don_row),
                  DOFe_loc = TR(dofe_row), DOPr_loc = TR(dopr_row), DONr_loc = TR(donr_row);
@@ -924,12 +933,14 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
     const double zoo_loss = (P.parm_z_mort2_0 * fpow15(Zprime) + P.parm_z_mort_0 * Zprime) * Tfunc;
     const double zoo_loss_doc = (1.0 - P.parm_labile_ratio) * (1.0 - f_zoo_detr) * zoo_loss;
     const double zoo_loss_dic = P.parm_labile_ratio * (1.0 - f_zoo_detr) * zoo_loss;
+    if (DIAG) ST2(diag_zoo_loss, zoo_loss);
 
     // ---- DOM (:1421-1461)
     const double DOC_prod = zoo_loss_doc + s_auto_loss_doc + s_auto_graze_doc;
     const double DON_prod = Qn * DOC_prod;
     const double DOP_prod = Qp_zoo_pom * zoo_loss_doc + acc_DOP_prod;
     const double DOFe_prod = Qfe_zoo * zoo_loss_doc + acc_DOFe_prod;
+    if (DIAG) { ST2(diag_DOC_prod, DOC_prod); ST2(diag_DON_prod, DON_prod); ST2(diag_DOP_prod, DOP_prod); ST2(diag_DOFe_prod, DOFe_prod); }
 
     double DOC_remin = DOC_loc * DOC_reminR;
     double DON_remin = DON_loc * DON_reminR;
@@ -948,6 +959,8 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
       DOP_remin = DOP_remin * 0.05;
     }
 
+    if (DIAG) { ST2(diag_DOC_remin, DOC_remin); ST2(diag_DON_remin, DON_remin); ST2(diag_DOP_remin, DOP_remin); ST2(diag_DOFe_remin, DOFe_remin); }
+
     // ---- particle production (:1467-1529)
     const double POC_prod = f_zoo_detr * zoo_loss + s_auto_graze_poc + s_auto_agg + s_auto_loss_poc;
 
@@ -961,6 +974,7 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
       Fe_scavenge_rate = Fe_scavenge_rate + (Fe_loc - fe_scavenge_thres1) * fe_max_scale2;
     const double Fe_scavenge = yps * Fe_loc * Fe_scavenge_rate;
     const double Fe_prod = ((zoo_loss * f_zoo_detr * Qfe_zoo) + Fe_scavenge) + acc_Fe_prod;
+    if (DIAG) { ST2(diag_Fe_scavenge, Fe_scavenge); ST2(diag_Fe_scavenge_rate, Fe_scavenge_rate); }
 
     // =====================================================================
     // compute_particulate_terms (BGC_mod.F90:2116-2699) for this level
@@ -972,6 +986,17 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
     double POC_sed = 0.0, Ca_sed = 0.0, Si_sed = 0.0, du_sed = 0.0, Fe_sed = 0.0;
     double SED_DENITRIF = 0.0, OTHER_REMIN = 0.0;
     double POC_remin, Ca_remin, Si_remin, du_remin, Fe_remin;
+    if (DIAG) {   // :2637-2694, the part that is known on entry
+      ST2(diag_POC_FLUX_IN, POC_s_in + POC_h_in);
+      ST2(diag_POC_PROD, POC_prod);
+      ST2(diag_CaCO3_FLUX_IN, Ca_s_in + Ca_h_in);
+      ST2(diag_CaCO3_PROD, Ca_prod);
+      ST2(diag_SiO2_FLUX_IN, Si_s_in + Si_h_in);
+      ST2(diag_SiO2_PROD, Si_prod);
+      ST2(diag_dust_FLUX_IN, du_s_in + du_h_in);
+      ST2(diag_P_iron_FLUX_IN, Fe_s_in + Fe_h_in);
+      ST2(diag_P_iron_PROD, Fe_prod);
+    }
     {
       double scalelength;   // piecewise-linear in zbot, :2273-2286
       if (zbot < P.parm_scalelen_z[0]) {
@@ -1109,19 +1134,10 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
       XS(X_DUH) = du_h;
 
       if (DIAG) {   // :2637-2694
-        ST2(diag_POC_FLUX_IN, POC_s_in + POC_h_in);
-        ST2(diag_POC_PROD, POC_prod);
         ST2(diag_POC_REMIN, POC_remin);
-        ST2(diag_CaCO3_FLUX_IN, Ca_s_in + Ca_h_in);
-        ST2(diag_CaCO3_PROD, Ca_prod);
         ST2(diag_CaCO3_REMIN, Ca_remin);
-        ST2(diag_SiO2_FLUX_IN, Si_s_in + Si_h_in);
-        ST2(diag_SiO2_PROD, Si_prod);
         ST2(diag_SiO2_REMIN, Si_remin);
-        ST2(diag_dust_FLUX_IN, du_s_in + du_h_in);
         ST2(diag_dust_REMIN, du_remin);
-        ST2(diag_P_iron_FLUX_IN, Fe_s_in + Fe_h_in);
-        ST2(diag_P_iron_PROD, Fe_prod);
         ST2(diag_P_iron_REMIN, Fe_remin);
         ST2(diag_calcToSed, Ca_sed);
         ST2(diag_bsiToSed, Si_sed);
@@ -1216,14 +1232,11 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
 
     // ---- diagnostics and column integrals (:1796-1945)
     if (DIAG) {
-      ST2(diag_tot_Nfix, tot_Nfix);
-      ST2(diag_tot_CaCO3_form, tot_CaCO3_form);
       ST2(diag_NO3_RESTORE, RESTORE_NO3);
       ST2(diag_SiO3_RESTORE, RESTORE_SiO3);
       ST2(diag_PO4_RESTORE, RESTORE_PO4);
       ST2(diag_NITRIF, NITRIF);
       ST2(diag_DENITRIF, DENITRIF);
-      ST2(diag_O2_PRODUCTION, O2_PRODUCTION);
       ST2(diag_O2_CONSUMPTION, O2_CONSUMPTION);
       if (HAS(diag_AOU)) {   // O2SAT_singleValue, Garcia & Gordon 1992 (:3012-3083)
         const double SALT = IN(R_S);
@@ -1234,26 +1247,11 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
         o2sat = cdiv(o2sat, 0.0223916, 1.0 / 0.0223916);
         A.d.diag_AOU[i2] = o2sat - O2_loc;
       }
-      ST2(diag_PAR_avg, PAR_avg);
-      ST2(diag_zoo_loss, zoo_loss);
-      ST2(diag_auto_graze_TOT, s_auto_graze);
-      ST2(diag_photoC_TOT, s_photoC);
       XS(X_PHOTOCZINT) = XS(X_PHOTOCZINT) + s_photoC * dz;
       XS(X_PHOTOCNO3ZINT) = XS(X_PHOTOCNO3ZINT) + NO3_zint_k;
       XS(X_BSI) = XS(X_BSI) + bSi_form_k;
       XS(X_CACO3ZINT) = XS(X_CACO3ZINT) + CaCO3_zint_k;
-      ST2(diag_photoC_NO3_TOT, photoC_NO3_TOT);
 
-      ST2(diag_DOC_prod, DOC_prod);
-      ST2(diag_DOC_remin, DOC_remin);
-      ST2(diag_DON_prod, DON_prod);
-      ST2(diag_DON_remin, DON_remin);
-      ST2(diag_DOP_prod, DOP_prod);
-      ST2(diag_DOP_remin, DOP_remin);
-      ST2(diag_DOFe_prod, DOFe_prod);
-      ST2(diag_DOFe_remin, DOFe_remin);
-      ST2(diag_Fe_scavenge, Fe_scavenge);
-      ST2(diag_Fe_scavenge_rate, Fe_scavenge_rate);
 
       const bool shallow = zbot <= 100.0e2;
 

@@ -761,8 +761,14 @@ static cudaError_t launch_mpas_oneshot(const double *src, double *dst, const Mpa
   return cudaGetLastError();
 }
 
-// BGC_MPAS_VARIANT (tuning only): 0 = pipelined kernel (default), 1 = one-shot tile kernel;
-// BGC_MPAS_KB / BGC_MPAS_BLOCKS_PER_SM override the level block and the persistent grid.
+// Measured on B200, 30 tracers x 60 levels x 235 160 cells (scripts/micro/mpas_sweep.py,
+// profiles/mpas_sweep_r02.txt): towards SoA the pipelined kernel with 4-level tiles and TWO
+// resident blocks per SM moves 5.87 TB/s (0.90 of the copy peak; 3 blocks: 4.6, the one-shot
+// kernel: 4.3); for the read-modify-write direction (SoA -> MPAS update) pipelining does not pay
+// (2.7 TB/s either way, 2-level tiles; larger tiles leave one block per SM and lose), so that
+// direction keeps the one-shot kernel.
+// BGC_MPAS_VARIANT (tuning only): 0 = as described, 1 = one-shot kernel for both directions,
+// 2 = pipelined kernel for both; BGC_MPAS_KB / BGC_MPAS_BLOCKS_PER_SM override tile and grid.
 static int env_int_or(const char *name, int dflt) {
   const char *v = getenv(name);
   return v ? atoi(v) : dflt;
@@ -774,7 +780,7 @@ static cudaError_t launch_mpas_layout(const double *src, double *dst, const Mpas
   if (nL <= 0 || nC <= 0 || m.nT <= 0) return cudaSuccess;
   if (m.nT > kMpasMaxTracers) return cudaErrorInvalidValue;
   static const int variant = env_int_or("BGC_MPAS_VARIANT", 0);
-  if (variant == 1) return launch_mpas_oneshot<TO_SOA>(src, dst, m, nL, nC, alpha, beta, weight, s);
+  if (variant == 1 || (variant == 0 && !TO_SOA)) return launch_mpas_oneshot<TO_SOA>(src, dst, m, nL, nC, alpha, beta, weight, s);
   static const int kb_env = env_int_or("BGC_MPAS_KB", 0), bps_env = env_int_or("BGC_MPAS_BLOCKS_PER_SM", 0);
   int KB = kb_env > 0 ? kb_env : (TO_SOA ? 4 : 2);
   if (KB > nL) KB = nL;
@@ -794,7 +800,7 @@ static cudaError_t launch_mpas_layout(const double *src, double *dst, const Mpas
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int per_sm = (int)((227 * 1024) / (smem + 1024));
-  if (per_sm > 8) per_sm = 8;
+  if (per_sm > 2) per_sm = 2;   // more resident blocks thrash the DRAM pages of the strided side
   if (per_sm < 1) per_sm = 1;
   if (bps_env > 0) per_sm = bps_env;
   int grid = sms * per_sm;

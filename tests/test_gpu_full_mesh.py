@@ -127,10 +127,15 @@ def _full_mesh(nL, nC, unit, stride, column0, what):
     status = ctx.status()
     assert status["no_bracket"] == 0 and status["no_convergence"] == 0 and status["nonfinite"] == 0, status
     ctx.close()
-    print("\n%s: %d active cells on the device, %d compared (cold) / %d (warm) in %d units; fill %.1f s, "
-          "reference cold %.1f s, warm %.1f s on %d threads; worst error cold %.2e (%s), warm %.2e (%s)"
-          % (what, cells, n_cold, n_warm, len(units), t_fill, t_cold, t_warm, chk.nthreads,
-             max(e_cold.values()), max(e_cold, key=e_cold.get), max(e_warm.values()), max(e_warm, key=e_warm.get)))
+    line = ("%s: %d active cells on the device, %d compared (cold) / %d (warm) in %d units; fill %.1f s, "
+            "reference cold %.1f s, warm %.1f s on %d threads; %d + %d arrays; worst error cold %.2e (%s), warm %.2e (%s)"
+            % (what, cells, n_cold, n_warm, len(units), t_fill, t_cold, t_warm, chk.nthreads, len(e_cold), len(e_warm),
+               max(e_cold.values()), max(e_cold, key=e_cold.get), max(e_warm.values()), max(e_warm, key=e_warm.get)))
+    print("\n" + line)
+    out = os.path.join(parity.REPO, "gpurun_out")
+    if os.path.isdir(out):     # the box's scratch directory: comes back with the run
+        with open(os.path.join(out, "full_mesh_parity.txt"), "a") as f:
+            f.write(line + "\n")
     return cells, n_cold, e_cold, e_warm
 
 

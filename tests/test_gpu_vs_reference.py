@@ -135,18 +135,35 @@ def test_co2calc_points(warm):
     ctx.close()
 
 
+# Tolerances of the fuzz slice.  The strict flavour (IEEE division in the reference's order, no FMA
+# contraction, libdevice exp/log/pow) follows the reference to 5e-13 on all 300 rounds of the campaign
+# (profiles/fuzz_gpu_strict_r02.txt).  The production flavour (reciprocal-multiply divisions, FMA
+# contraction) meets 1e-10 on 290 of them; the other ten lie between 1e-10 and 1.2e-8 - inputs with
+# concentration ratios of 1e12 where the reference's own formulas difference nearly equal fluxes
+# (P_iron remin, the group Fe tendency ...), so that ONE different rounding upstream shows at 1e-10
+# relative to the array's maximum; neither side is closer to the exact value there.  On the
+# BASELINE.json workloads the production flavour is held to 1e-10 cell for cell
+# (tests/test_gpu_full_mesh.py).
+FUZZ_TOL = {"prod": 1e-7, "strict": 1e-11}
+
+
+@pytest.mark.parametrize("flavour", ["strict", "prod"])
 @pytest.mark.parametrize("seed0", [0, 12, 24, 36])
-def test_differential_fuzz_slice(seed0):
-    """A fixed-seed slice of scripts/fuzz_gpu_vs_reference.py (the whole campaign's log is under
+def test_differential_fuzz_slice(seed0, flavour, monkeypatch):
+    """A fixed-seed slice of scripts/fuzz_gpu_vs_reference.py (the whole campaign's logs are under
     profiles/): random parameter and functional-group tables, switches, zero / tiny / huge
     concentrations, anoxic, fresh and hot water, shallow bottoms, dark and bright columns, cold /
     warm / off-target brackets, block widths 1, 7, 256, 257, device-resident and host-layout calls -
     inputs that reach the bracket-growth loop (co2calc.F90:920-938) and the bottom-cell branches
     (BGC_mod.F90:2522-2631) far from the synthetic profiles."""
+    monkeypatch.setenv("BGC_B200_FLAVOUR", flavour)
     sys.path.insert(0, os.path.join(parity.REPO, "scripts"))
     import fuzz_gpu_vs_reference as fz
     report = {}
     for seed in range(seed0, seed0 + 12):
         fz.one_round(seed, report)
-    bad = {s: r for s, r in report.items() if not (r["worst"] <= parity.TOL_TEND and r["ph"] <= parity.TOL_SOLVER)}
+    tol = FUZZ_TOL[flavour]
+    bad = {s: r for s, r in report.items() if not (r["worst"] <= tol and r["ph"] <= parity.TOL_SOLVER)}
     assert not bad, bad
+    n_tight = sum(1 for r in report.values() if r["worst"] <= parity.TOL_TEND)
+    assert n_tight >= 10, report       # at most two of twelve rounds may need the wide production bound
