@@ -44,6 +44,7 @@ static int fail(int code, const char *fmt, ...) {
 #define RC(call) do { int rc_ = (call); if (rc_ != BGC_OK) return rc_; } while (0)
 
 extern "C" const char *bgc_last_error(void) { return g_err; }
+extern "C" const char *bgc_kernel_name(int kernel_id);
 extern "C" const char *bgc_version(void) { return "ocean-bgc_b200 0.1 (sm_100a)"; }
 
 // ------------------------------------------------------------------ minimal NCCL binding (dlopen)
@@ -352,10 +353,22 @@ static int resolve_spans(bgc_ctx *c) {
   if (c->spans.empty()) return BGC_OK;
   RC(join_pending(c));
   CU(cudaStreamSynchronize(c->stream));
+  // BGC_TRACE_FILE=<path> (debugging / tuning): one line per timed launch, start and end in ms
+  // relative to the first launch of the batch - a poor man's timeline of the streams.
+  FILE *trace = nullptr;
+  if (const char *tf = getenv("BGC_TRACE_FILE")) trace = fopen(tf, "a");
   for (auto &sp : c->spans) {
     float ms = 0.f;
     CU(cudaEventElapsedTime(&ms, sp.a, sp.b));
     c->timed_ms[sp.kid] += (double)ms;
+    if (trace) {
+      float t0 = 0.f;
+      cudaEventElapsedTime(&t0, c->spans.front().a, sp.a);
+      fprintf(trace, "%-24s %10.4f %10.4f\n", bgc_kernel_name(sp.kid), (double)t0, (double)(t0 + ms));
+    }
+  }
+  if (trace) { fprintf(trace, "--\n"); fclose(trace); }
+  for (auto &sp : c->spans) {
     c->ev_pool.push_back(sp.a);
     c->ev_pool.push_back(sp.b);
   }
