@@ -108,7 +108,8 @@ struct bgc_ctx {
   // sweep: one side stream per pipeline slot, forked from / joined to the slot's stream
   cudaStream_t side_stream[2] = {nullptr, nullptr};
   cudaEvent_t fork_event[2] = {nullptr, nullptr}, join_event[2] = {nullptr, nullptr};
-  int concurrent_co3 = 1;                   // BGC_CONCURRENT_CO3=0 serialises the two (tuning / debugging)
+  int concurrent_co3 = 1;                   // bgc_ctx_set_concurrency / BGC_CONCURRENT_CO3 (0, 1, 2: see source_sink_device)
+  int sm_count = 148;
   int zero_shortcut = 1;                    // bgc_ctx_set_zero_shortcut / BGC_ZERO_SHORTCUT
   bool diag_accumulate = false;             // bgc_diag_accumulate_enable
   bool defer_join = false;                  // bgc_ctx_set_deferred_join
@@ -244,6 +245,7 @@ static int ctx_init(bgc_ctx *c, int device, int nLevelsMax, int nColumnsMax) {
   CU(cudaStreamCreateWithFlags(&c->pipe_stream, cudaStreamNonBlocking));
   CU(cudaEventCreateWithFlags(&c->pipe_event, cudaEventDisableTiming));
   if (const char *v = getenv("BGC_CONCURRENT_CO3")) c->concurrent_co3 = atoi(v);
+  CU(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
   if (const char *v = getenv("BGC_ZERO_SHORTCUT")) c->zero_shortcut = atoi(v);
   {
     int lo = 0, hi = 0;   // the side stream gets the LOWER priority: the sweep's blocks are placed first
@@ -314,7 +316,7 @@ extern "C" int bgc_ctx_set_deferred_join(bgc_ctx *c, int enable) {
 extern "C" int bgc_ctx_set_concurrency(bgc_ctx *c, int enable) {
   RC(use_device(c));
   RC(join_pending(c));
-  c->concurrent_co3 = enable != 0;
+  c->concurrent_co3 = enable;   // 0 = same stream, 1 = side stream beside the sweep, 2 = side stream after the sweep
   return BGC_OK;
 }
 
@@ -662,13 +664,19 @@ static int down_c(bgc_ctx *c, const HostChunk &h, const void *dev, void *host, s
   return BGC_OK;
 }
 
-// Chunk plan: about 32 k columns per chunk (large enough for full-speed DMA and kernels, small
+// Chunk plan: up to 32 k columns per chunk (large enough for full-speed DMA and kernels, small
 // enough that several chunks overlap), a multiple of 32 columns so every device slab stays
 // 256-byte aligned; BGC_HOST_CHUNK_COLUMNS overrides it (tests use tiny chunks).
 static int chunk_columns(const bgc_ctx *c, int nC) {
-  int cc = c->host_chunk_columns > 0 ? c->host_chunk_columns : 32768;
-  if (c->host_chunk_columns <= 0 && nC <= 49152) return nC;   // small blocks: one chunk
-  cc = (cc + 31) / 32 * 32;
+  if (c->host_chunk_columns > 0) {
+    const int cc = (c->host_chunk_columns + 31) / 32 * 32;
+    return cc < nC ? cc : nC;
+  }
+  if (nC <= 8192) return nC;                 // small blocks: one chunk
+  // at least four chunks, so that the download of one overlaps the upload and the kernels of the
+  // next also when a GPU owns only a slab of the mesh; at most 32 k columns
+  int cc = ((nC + 3) / 4 + 31) / 32 * 32;
+  if (cc > 32768) cc = 32768;
   return cc < nC ? cc : nC;
 }
 
@@ -793,8 +801,18 @@ static int source_sink_device(bgc_ctx *c, const BgcInput *in, const BgcForcing *
   RC(join_pending(c));   // a deferred join of the previous call ends here at the latest
   const int slot = (c->stream == c->pipe_stream) ? 1 : 0;
   cudaStream_t main_stream = c->stream;
-  cudaStream_t co3_stream = c->concurrent_co3 ? c->side_stream[slot] : main_stream;
-  if (c->concurrent_co3) {
+  // Placement of the carbonate kernel (measured, profiles/concurrency_sweep_r02.txt).  Beside the
+  // sweep (mode 1) it fills the SMs that the sweep's last, partial wave leaves idle: -0.35 ms on the
+  // full EC60to30 mesh, -0.4 ms at half the mesh.  But a sweep block needs a WHOLE SM (every register,
+  // 219 KB of shared memory) while a carbonate block fits into any SM that is still draining the
+  // previous kernel, and once carbonate blocks sit there the SM never empties: when the sweep is less
+  // than one wave (fewer blocks than SMs: a GPU's slab in an 8-way split) its blocks starve behind
+  // them and the sweep takes 1.06 instead of 0.58 ms.  There the fork moves behind the sweep
+  // (mode 2: the carbonate kernel runs beside the DMS / MACROS / surface kernels).
+  int co3_mode = c->concurrent_co3;
+  if (co3_mode == 1 && (nC + 255) / 256 < c->sm_count) co3_mode = 2;
+  cudaStream_t co3_stream = co3_mode ? c->side_stream[slot] : main_stream;
+  if (co3_mode == 1) {   // fork BEFORE the sweep: the carbonate kernel runs beside it
     CU(cudaEventRecord(c->fork_event[slot], main_stream));
     CU(cudaStreamWaitEvent(co3_stream, c->fork_event[slot], 0));
   }
@@ -849,6 +867,10 @@ static int source_sink_device(bgc_ctx *c, const BgcInput *in, const BgcForcing *
     RC(arena_d(c, "inv_partials_bgc", (size_t)inv_parts * bgc::kEcoInvGroups * bgc::kInvGroup, &ea.inv_partials));
   }
   LAUNCH(BGC_K_ECO_COLUMNS, 1, bgc::launch_eco_columns(ea, diag_mode, c->eco_variant, c->stream));
+  if (co3_mode >= 2) {   // fork AFTER the sweep: the carbonate kernel runs beside whatever follows on the ctx stream
+    CU(cudaEventRecord(c->fork_event[slot], main_stream));
+    CU(cudaStreamWaitEvent(co3_stream, c->fork_event[slot], 0));
+  }
 
   // carbonate chemistry, cell-parallel, then the saturation-depth scan (side stream)
   bgc::Co3Args ca;
@@ -882,7 +904,7 @@ static int source_sink_device(bgc_ctx *c, const BgcInput *in, const BgcForcing *
   }();
   c->stream = main_stream;
   if (rc_side != BGC_OK) return rc_side;
-  if (c->concurrent_co3) {
+  if (co3_mode) {
     CU(cudaEventRecord(c->join_event[slot], co3_stream));
     if (c->defer_join && !host_call && slot == 0) c->pending_join = true;   // joined at the next join point
     else CU(cudaStreamWaitEvent(main_stream, c->join_event[slot], 0));
