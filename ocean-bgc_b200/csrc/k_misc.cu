@@ -485,9 +485,12 @@ transpose_kernel(const double *__restrict__ src, double *__restrict__ dst, int R
 template <bool TO_SOA>
 __global__ void __launch_bounds__(256)
 mpas_layout_kernel(const double *__restrict__ src, double *__restrict__ dst, const __grid_constant__ MpasMap M,
-                   int nL, int nC, int KB, double alpha, double beta, const double *__restrict__ weight) {
+                   int nL, int nC, int KB, double alpha, double beta, const double *__restrict__ weight, int ktiles) {
   extern __shared__ double tile[];   // [32][KB*nT + 1]
-  const int c0 = blockIdx.x * 32, k0 = blockIdx.y * KB, nT = M.nT;
+  // 1-D grid, level blocks of one cell block first: the blocks that are resident at the same time
+  // work on the same cells' contiguous MPAS runs (DRAM page locality on the strided side)
+  const int cb = blockIdx.x / ktiles, kb = blockIdx.x - cb * ktiles;
+  const int c0 = cb * 32, k0 = kb * KB, nT = M.nT;
   const int ncell = min(32, nC - c0), nk = min(KB, nL - k0);
   const int run = nk * nT, pitch = KB * nT + 1;
   const size_t nLnC = (size_t)nL * (size_t)nC;
@@ -750,14 +753,17 @@ static int mpas_levels_per_block(int nT, bool to_soa) {
 template <bool TO_SOA>
 static cudaError_t launch_mpas_oneshot(const double *src, double *dst, const MpasMap &m, int nL, int nC, double alpha,
                                        double beta, const double *weight, cudaStream_t s) {
-  const int KB = mpas_levels_per_block(m.nT, TO_SOA);
+  int KB = mpas_levels_per_block(m.nT, TO_SOA);
+  if (const char *v = getenv("BGC_MPAS_KB1")) { const int kb = atoi(v); if (kb > 0 && (size_t)32 * (kb * m.nT + 1) * 8 <= 200 * 1024) KB = kb; }
+  if (KB > nL) KB = nL;
   const size_t smem = (size_t)32 * (KB * m.nT + 1) * sizeof(double);
   auto kern = mpas_layout_kernel<TO_SOA>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  dim3 grid(cdiv((size_t)nC, 32), cdiv((size_t)nL, (size_t)KB));
-  if (grid.y > 65535u) return cudaErrorInvalidConfiguration;
-  kern<<<grid, 256, smem, s>>>(src, dst, m, nL, nC, KB, alpha, beta, weight);
+  const int ktiles = (nL + KB - 1) / KB;
+  const long long ntiles = (long long)((nC + 31) / 32) * ktiles;
+  if (ntiles > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+  kern<<<(unsigned)ntiles, 256, smem, s>>>(src, dst, m, nL, nC, KB, alpha, beta, weight, ktiles);
   return cudaGetLastError();
 }
 
