@@ -774,7 +774,9 @@ def run_mpas_adapter(ctx, stream, dev, nL, nC, reps=5):
     out = {}
     for name, fn, passes in (("mpas_to_soa", lambda: ctx.mpas_to_soa(mpas.data_ptr(), soa.data_ptr(), slot, nL, nC), 2),
                              ("soa_to_mpas_update", lambda: ctx.soa_to_mpas(soa.data_ptr(), mpas.data_ptr(), slot, nL, nC,
-                                                                            alpha=1e-9, beta=1.0), 3)):
+                                                                            alpha=1e-9, beta=1.0), 3),
+                             ("soa_to_mpas_convert", lambda: ctx.soa_to_mpas(soa.data_ptr(), mpas.data_ptr(), slot, nL, nC,
+                                                                             alpha=1.0, beta=0.0), 2)):
         fn()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ctx.synchronize()

@@ -1513,7 +1513,11 @@ extern "C" int bgc_graph_destroy(bgc_graph *g) {
 static int mpas_map(int nT, const int *slot, bgc::MpasMap *m) {
   if (nT < 1 || nT > bgc::kMpasMaxTracers || !slot) return fail(BGC_ERR_ARG, "MPAS layout: 1..%d tracers and a slot map are required", bgc::kMpasMaxTracers);
   m->nT = nT;
-  for (int n = 0; n < bgc::kMpasMaxTracers; ++n) m->slot[n] = (n < nT) ? slot[n] : 0;
+  m->used = 0ull;
+  for (int n = 0; n < bgc::kMpasMaxTracers; ++n) {
+    m->slot[n] = (n < nT) ? slot[n] : 0;
+    if (n < nT && slot[n] > 0) m->used |= 1ull << n;
+  }
   for (int n = 0; n < nT; ++n)
     if (slot[n] < 0 || slot[n] > bgc::kMpasMaxTracers) return fail(BGC_ERR_ARG, "MPAS layout: slot %d of tracer %d out of range", slot[n], n);
   return BGC_OK;

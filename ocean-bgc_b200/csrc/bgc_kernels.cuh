@@ -159,7 +159,7 @@ cudaError_t launch_transpose(const double *src, double *dst, int rows_fast_src, 
 // (the caller side of the boundary).  slot[n] = 1-based SoA slot of MPAS
 // tracer n, 0 = not part of this tracer group.
 constexpr int kMpasMaxTracers = 64;
-struct MpasMap { int nT; int slot[kMpasMaxTracers]; };
+struct MpasMap { int nT; int slot[kMpasMaxTracers]; unsigned long long used; };   // used: bit n set <=> slot[n] > 0
 cudaError_t launch_mpas_to_soa(const double *mpas, double *soa, const MpasMap &m, int nL, int nC, cudaStream_t s);
 // mpas(n,k,cell) = beta * mpas(n,k,cell) + alpha * weight(k,cell) * soa(cell,k,slot[n]); weight = NULL
 // means 1.  alpha = dt, beta = 1 is the explicit tracer update fused with the layout change; with

@@ -497,6 +497,10 @@ mpas_layout_kernel(const double *__restrict__ src, double *__restrict__ dst, con
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
   // MPAS side: warp w takes cells w, w + nw, ...; its lanes walk the cell's contiguous run.
   // SoA side: warp w takes (level, tracer) pairs; its lanes are the 32 cells.  No divisions.
+  // The slot map is consulted per TRACER, not per element (a per-element lookup is an indexed
+  // constant load through the MIO pipe, and that pipe - not HBM - then bounds the kernel: measured
+  // 3100 thread instructions per cell and mio_throttle as the top stall before this was hoisted);
+  // on the MPAS side, where a lane walks a run of all tracers, membership is one bit of M.used.
   if (TO_SOA) {
     for (int c = w; c < ncell; c += nw) {
       const double *p = src + (size_t)nT * ((size_t)k0 + (size_t)nL * (size_t)(c0 + c));
@@ -504,30 +508,42 @@ mpas_layout_kernel(const double *__restrict__ src, double *__restrict__ dst, con
     }
     __syncthreads();
     if (lane < ncell) {
-      for (int kk = 0; kk < nk; ++kk)
-        for (int n = w; n < nT; n += nw)
-          if (M.slot[n] > 0)
-            dst[(size_t)(c0 + lane) + (size_t)nC * (size_t)(k0 + kk) + (size_t)(M.slot[n] - 1) * nLnC] =
-                tile[lane * pitch + kk * nT + n];
+      for (int n = w; n < nT; n += nw) {
+        const int sl = M.slot[n];
+        if (sl <= 0) continue;
+        double *q = dst + (size_t)(c0 + lane) + (size_t)nC * (size_t)k0 + (size_t)(sl - 1) * nLnC;
+        const double *t = tile + lane * pitch + n;
+        for (int kk = 0; kk < nk; ++kk, q += nC, t += nT) *q = *t;
+      }
     }
   } else {
     if (lane < ncell) {
-      for (int kk = 0; kk < nk; ++kk)
-        for (int n = w; n < nT; n += nw)
-          if (M.slot[n] > 0)
-            tile[lane * pitch + kk * nT + n] =
-                src[(size_t)(c0 + lane) + (size_t)nC * (size_t)(k0 + kk) + (size_t)(M.slot[n] - 1) * nLnC];
+      for (int n = w; n < nT; n += nw) {
+        const int sl = M.slot[n];
+        if (sl <= 0) continue;
+        const double *q = src + (size_t)(c0 + lane) + (size_t)nC * (size_t)k0 + (size_t)(sl - 1) * nLnC;
+        double *t = tile + lane * pitch + n;
+        double v[8];
+        for (int kk0 = 0; kk0 < nk; kk0 += 8) {   // loads first, then the shared-memory stores: up to 8 in flight
+#pragma unroll
+          for (int j = 0; j < 8; ++j) if (kk0 + j < nk) v[j] = q[(size_t)(kk0 + j) * nC];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) if (kk0 + j < nk) t[(kk0 + j) * nT] = v[j];
+        }
+      }
     }
     __syncthreads();
+    const unsigned long long used = M.used;
+    const bool rmw = beta != 0.0;
     for (int c = w; c < ncell; c += nw) {
       double *p = dst + (size_t)nT * ((size_t)k0 + (size_t)nL * (size_t)(c0 + c));
       // weight(k, cell), level fastest (MPAS layerThickness): the thickness-weighted tendency
       const double *wp = weight ? weight + (size_t)k0 + (size_t)nL * (size_t)(c0 + c) : nullptr;
       for (int r = lane, n = lane % nT, kk = lane / nT; r < run; r += 32) {
-        if (M.slot[n] > 0) {
+        if ((used >> n) & 1ull) {
           double v = tile[c * pitch + r];
           if (wp) v = wp[kk] * v;
-          p[r] = (beta == 0.0) ? alpha * v : beta * p[r] + alpha * v;
+          p[r] = rmw ? beta * p[r] + alpha * v : alpha * v;
         }
         n += 32;
         while (n >= nT) { n -= nT; ++kk; }
@@ -535,7 +551,6 @@ mpas_layout_kernel(const double *__restrict__ src, double *__restrict__ dst, con
     }
   }
 }
-
 
 // Pipelined form of the same tile scheme: a persistent grid (a few blocks per SM) walks the
 // (cell block, level block) tiles, level blocks of one cell block first, and keeps TWO tiles in
@@ -562,10 +577,10 @@ mpas_layout_pipe_kernel(const double *__restrict__ src, double *__restrict__ dst
   const int tile_doubles = 32 * pitch;
   // TO_SOA: [2][32][pitch] = the MPAS runs.  !TO_SOA: per buffer two planes, the SoA values
   // (transposed into run order) and, when beta != 0, the old MPAS runs.
-  const int planes = TO_SOA ? 1 : 2;
+  const bool rmw = !TO_SOA && beta != 0.0;
+  const int planes = rmw ? 2 : 1;
   const size_t nLnC = (size_t)nL * (size_t)nC;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  const bool rmw = !TO_SOA && beta != 0.0;
 
   auto issue = [&](int tile, int buf) {
     const int cb = tile / ktiles, kb = tile - cb * ktiles;
@@ -574,7 +589,7 @@ mpas_layout_pipe_kernel(const double *__restrict__ src, double *__restrict__ dst
     const int run = nk * nT;
     double *base = sm + (size_t)buf * planes * tile_doubles;
     if (TO_SOA || rmw) {   // the cells' contiguous MPAS runs
-      double *plane = base + (TO_SOA ? 0 : tile_doubles);
+      double *plane = base + (TO_SOA ? 0 : tile_doubles);   // (rmw: plane 1; TO_SOA: plane 0)
       const double *g = (TO_SOA ? src : dst);
       for (int c = w; c < ncell; c += nw) {
         const double *p = g + (size_t)nT * ((size_t)k0 + (size_t)nL * (size_t)(c0 + c));
@@ -584,11 +599,13 @@ mpas_layout_pipe_kernel(const double *__restrict__ src, double *__restrict__ dst
       }
     }
     if (!TO_SOA && lane < ncell) {   // SoA rows: lanes are the 32 cells, 8-byte copies into run order
-      for (int kk = 0; kk < nk; ++kk)
-        for (int n = w; n < nT; n += nw)
-          if (M.slot[n] > 0)
-            cp_async_8(base + lane * pitch + kk * nT + n,
-                       src + (size_t)(c0 + lane) + (size_t)nC * (size_t)(k0 + kk) + (size_t)(M.slot[n] - 1) * nLnC);
+      for (int n = w; n < nT; n += nw) {
+        const int sl = M.slot[n];
+        if (sl <= 0) continue;
+        const double *q = src + (size_t)(c0 + lane) + (size_t)nC * (size_t)k0 + (size_t)(sl - 1) * nLnC;
+        double *t = base + lane * pitch + n;
+        for (int kk = 0; kk < nk; ++kk, q += nC, t += nT) cp_async_8(t, q);
+      }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
@@ -610,7 +627,7 @@ mpas_layout_pipe_kernel(const double *__restrict__ src, double *__restrict__ dst
     const int run = nk * nT;
     const double *base = sm + (size_t)buf * planes * tile_doubles;
     if (TO_SOA) {
-      if (lane < ncell) {
+      if (lane < ncell) {   // (level outer, tracer inner: measured 20 % faster than the hoisted form here)
         for (int kk = 0; kk < nk; ++kk)
           for (int n = w; n < nT; n += nw)
             if (M.slot[n] > 0)
@@ -618,12 +635,13 @@ mpas_layout_pipe_kernel(const double *__restrict__ src, double *__restrict__ dst
                   base[lane * pitch + kk * nT + n];
       }
     } else {
+      const unsigned long long used = M.used;
       const double *old = base + tile_doubles;
       for (int c = w; c < ncell; c += nw) {
         double *p = dst + (size_t)nT * ((size_t)k0 + (size_t)nL * (size_t)(c0 + c));
         const double *wp = weight ? weight + (size_t)k0 + (size_t)nL * (size_t)(c0 + c) : nullptr;
         for (int r = lane, n = lane % nT, kk = lane / nT; r < run; r += 32) {
-          if (M.slot[n] > 0) {
+          if ((used >> n) & 1ull) {
             double v = base[c * pitch + r];
             if (wp) v = wp[kk] * v;
             p[r] = rmw ? beta * old[c * pitch + r] + alpha * v : alpha * v;
@@ -636,6 +654,48 @@ mpas_layout_pipe_kernel(const double *__restrict__ src, double *__restrict__ dst
     __syncthreads();   // the buffer just consumed is refilled by the next iteration's issue
     tile = next;
     buf ^= 1;
+  }
+}
+
+
+// SoA -> MPAS for WHOLE columns: a block owns CB cells over all levels, gathers their SoA values
+// into shared memory in MPAS order and then streams each cell's contiguous nL*nT run - the
+// MPAS side moves in 14-KB runs instead of tile-sized pieces.
+template <int CB>
+__global__ void __launch_bounds__(256)
+mpas_columns_kernel(const double *__restrict__ src, double *__restrict__ dst, const __grid_constant__ MpasMap M,
+                    int nL, int nC, double alpha, double beta, const double *__restrict__ weight) {
+  extern __shared__ double tile[];   // [CB][nL*nT + 1]
+  const int nT = M.nT, run = nL * nT, pitch = run + 1;
+  const int c0 = blockIdx.x * CB;
+  const int ncell = min(CB, nC - c0);
+  const size_t nLnC = (size_t)nL * (size_t)nC;
+  constexpr int PER = 32 / CB;                      // (level, tracer) pairs one warp instruction covers
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int cell = lane % CB, sub = lane / CB;
+  for (int k = w; k < nL; k += nw) {
+    for (int n = sub; n < nT; n += PER) {
+      if (cell < ncell && M.slot[n] > 0)
+        tile[cell * pitch + k * nT + n] =
+            src[(size_t)(c0 + cell) + (size_t)nC * (size_t)k + (size_t)(M.slot[n] - 1) * nLnC];
+    }
+  }
+  __syncthreads();
+  const bool rmw = beta != 0.0;
+  for (int c = w; c < ncell; c += nw) {
+    double *p = dst + (size_t)run * (size_t)(c0 + c);
+    const double *wp = weight ? weight + (size_t)nL * (size_t)(c0 + c) : nullptr;
+    int n = lane % nT, kk = lane / nT;
+#pragma unroll 4
+    for (int r = lane; r < run; r += 32) {
+      if ((M.used >> n) & 1ull) {
+        double v = tile[c * pitch + r];
+        if (wp) v = wp[kk] * v;
+        p[r] = rmw ? beta * p[r] + alpha * v : alpha * v;
+      }
+      n += 32;
+      while (n >= nT) { n -= nT; ++kk; }
+    }
   }
 }
 
@@ -768,13 +828,14 @@ static cudaError_t launch_mpas_oneshot(const double *src, double *dst, const Mpa
 }
 
 // Measured on B200, 30 tracers x 60 levels x 235 160 cells (scripts/micro/mpas_sweep.py,
-// profiles/mpas_sweep_r02.txt): towards SoA the pipelined kernel with 4-level tiles and TWO
-// resident blocks per SM moves 5.87 TB/s (0.90 of the copy peak; 3 blocks: 4.6, the one-shot
-// kernel: 4.3); for the read-modify-write direction (SoA -> MPAS update) pipelining does not pay
-// (2.7 TB/s either way, 2-level tiles; larger tiles leave one block per SM and lose), so that
-// direction keeps the one-shot kernel.
-// BGC_MPAS_VARIANT (tuning only): 0 = as described, 1 = one-shot kernel for both directions,
-// 2 = pipelined kernel for both; BGC_MPAS_KB / BGC_MPAS_BLOCKS_PER_SM override tile and grid.
+// profiles/mpas_sweep_r02.txt; ncu: profiles/ncu_r02_mpas_summary.json): the pipelined kernel moves
+// 5.86 TB/s towards SoA (0.90 of the copy peak; the one-shot kernel 4.6), 4.62 TB/s for the
+// read-modify-write update towards MPAS (0.71; one-shot 3.0) and 4.62 TB/s for the plain conversion.
+// Round 1's 2.7 TB/s in the MPAS direction was not a memory limit at all: the slot map was looked up
+// per ELEMENT (an indexed constant load through the MIO pipe, 3100 thread instructions per cell,
+// mio_throttle the top stall); it is now read once per tracer / tested as one bit of a mask.
+// BGC_MPAS_VARIANT (tuning only): 0 = pipelined kernel, 1 = one-shot kernel, 3 / 4 = whole-column
+// tiles; BGC_MPAS_KB / BGC_MPAS_BLOCKS_PER_SM override tile and grid.
 static int env_int_or(const char *name, int dflt) {
   const char *v = getenv(name);
   return v ? atoi(v) : dflt;
@@ -786,11 +847,32 @@ static cudaError_t launch_mpas_layout(const double *src, double *dst, const Mpas
   if (nL <= 0 || nC <= 0 || m.nT <= 0) return cudaSuccess;
   if (m.nT > kMpasMaxTracers) return cudaErrorInvalidValue;
   static const int variant = env_int_or("BGC_MPAS_VARIANT", 0);
-  if (variant == 1 || (variant == 0 && !TO_SOA)) return launch_mpas_oneshot<TO_SOA>(src, dst, m, nL, nC, alpha, beta, weight, s);
+  if (!TO_SOA && variant >= 3) {   // whole-column tiles (tuning; loses: 64-byte pieces on the SoA side)
+    const int CB = variant == 3 ? 8 : 4;
+    const size_t smem = (size_t)CB * ((size_t)nL * m.nT + 1) * sizeof(double);
+    if (smem <= 227 * 1024) {
+      cudaError_t e;
+      if (CB == 8) {
+        e = cudaFuncSetAttribute(mpas_columns_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        mpas_columns_kernel<8><<<cdiv((size_t)nC, 8), 256, smem, s>>>(src, dst, m, nL, nC, alpha, beta, weight);
+      } else {
+        e = cudaFuncSetAttribute(mpas_columns_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        mpas_columns_kernel<4><<<cdiv((size_t)nC, 4), 128, smem, s>>>(src, dst, m, nL, nC, alpha, beta, weight);
+      }
+      return cudaGetLastError();
+    }
+  }
+  if (variant == 1) return launch_mpas_oneshot<TO_SOA>(src, dst, m, nL, nC, alpha, beta, weight, s);
   static const int kb_env = env_int_or("BGC_MPAS_KB", 0), bps_env = env_int_or("BGC_MPAS_BLOCKS_PER_SM", 0);
-  int KB = kb_env > 0 ? kb_env : (TO_SOA ? 4 : 2);
+  const bool rmw = !TO_SOA && beta != 0.0;
+  // measured defaults (profiles/mpas_sweep_r02.txt): towards SoA 4-level tiles, 2 resident blocks per
+  // SM; read-modify-write towards MPAS 2-level tiles (two planes per buffer), 3 blocks; plain
+  // conversion towards MPAS 4-level tiles, 3 blocks
+  int KB = kb_env > 0 ? kb_env : (rmw ? 2 : 4);
   if (KB > nL) KB = nL;
-  const int planes = TO_SOA ? 1 : 2;
+  const int planes = rmw ? 2 : 1;
   auto smem_of = [&](int kb) { return (size_t)2 * planes * 32 * (kb * m.nT + 2 + ((kb * m.nT) & 1)) * sizeof(double); };
   while (KB > 1 && smem_of(KB) > 200 * 1024) --KB;
   const size_t smem = smem_of(KB);
@@ -806,7 +888,8 @@ static cudaError_t launch_mpas_layout(const double *src, double *dst, const Mpas
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int per_sm = (int)((227 * 1024) / (smem + 1024));
-  if (per_sm > 2) per_sm = 2;   // more resident blocks thrash the DRAM pages of the strided side
+  const int cap = TO_SOA ? 2 : 3;   // more resident blocks thrash the DRAM pages of the strided side
+  if (per_sm > cap) per_sm = cap;
   if (per_sm < 1) per_sm = 1;
   if (bps_env > 0) per_sm = bps_env;
   int grid = sms * per_sm;

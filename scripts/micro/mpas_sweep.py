@@ -18,9 +18,9 @@ st = torch.cuda.Stream(); ctx.set_stream(st.cuda_stream)
 print(json.dumps(bench.run_mpas_adapter(ctx, st, "cuda:0", nL, nC)))
 ''' % REPO
 
-SETTINGS = [{"BGC_MPAS_VARIANT": "1", "BGC_MPAS_KB1": str(kb)} for kb in (0, 1, 2, 3, 4, 6, 10)] + [
+SETTINGS = [{"BGC_MPAS_VARIANT": "0"}, {"BGC_MPAS_VARIANT": "1"}] + [
     {"BGC_MPAS_VARIANT": "0", "BGC_MPAS_KB": str(kb), "BGC_MPAS_BLOCKS_PER_SM": str(b)}
-    for kb in (2, 4) for b in (0, 2)]
+    for kb, b in ((2, 3), (2, 4), (3, 2), (3, 3), (4, 2), (4, 3), (6, 2))]
 for s in SETTINGS:
     env = dict(os.environ, **s)
     r = subprocess.run([sys.executable, "-c", PROG], capture_output=True, text=True, env=env)
