@@ -10,6 +10,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <atomic>
 #include <map>
 #include <mutex>
 #include <string>
@@ -131,6 +132,8 @@ struct bgc_ctx {
   int dms_variant = 0;                      // launch shape of the DMS tile kernel (BGC_DMS_VARIANT, tuning only)
   std::map<std::string, DevBuf> arena;      // persistent device buffers (host-layout mode, scratch)
   std::map<std::string, HostStage> host_stage;   // page-locked staging buffers of the host-layout calls
+  struct ZeroJob { char *p; size_t bytes; };
+  std::vector<ZeroJob> zero_jobs;                // host ranges a host-layout call fills with zeros itself (see down_k)
   ncclComm_t comm = nullptr;
   int nranks = 1;
   // launch accounting (always on) and optional per-kernel CUDA-event timing
@@ -608,14 +611,49 @@ static int flush_up(bgc_ctx *c, HostChunk &h) {
   return BGC_OK;
 }
 
-// Download the chunk of a (k,col,n) array (transpose now, copy in flush_down).
-static int down_k(bgc_ctx *c, HostChunk &h, const double *dev, double *host, int nSlabs) {
-  const size_t n2c = (size_t)h.nL * h.cc;
-  if (h.down_slabs + nSlabs > h.stage_slabs) return fail(BGC_ERR_ARG, "internal: staging area too small (download)");
-  LAUNCH(BGC_K_TRANSPOSE, 1, bgc::launch_transpose(dev, h.stage + h.down_slabs * n2c, h.cc, h.nL, nSlabs, c->stream));
-  h.downs.push_back({host, nullptr, nSlabs, h.down_slabs});
-  h.down_slabs += nSlabs;
+// Download the chunk of a (k,col,n) array (transpose now, copy in flush_down).  Slabs whose bit is
+// set in zero_mask are STRUCTURALLY zero - the reference assigns them the constant zero whatever the
+// inputs are (e.g. twelve of the fourteen DMS tendencies, DMS_mod.F90:413, :718-719) - and do not
+// cross PCIe: the host range is zero-filled by host threads while the other slabs are in flight
+// (run_zero_jobs).
+static int down_k(bgc_ctx *c, HostChunk &h, const double *dev, double *host, int nSlabs, unsigned long long zero_mask = 0ull) {
+  const size_t n2c = (size_t)h.nL * h.cc, n2 = (size_t)h.nL * h.nC;
+  for (int s0 = 0; s0 < nSlabs;) {
+    if (s0 < 64 && ((zero_mask >> s0) & 1ull)) {
+      c->zero_jobs.push_back({(char *)(host + (size_t)s0 * n2 + (size_t)h.c0 * h.nL), n2c * sizeof(double)});
+      ++s0;
+      continue;
+    }
+    int ns = 1;
+    while (s0 + ns < nSlabs && !((s0 + ns) < 64 && ((zero_mask >> (s0 + ns)) & 1ull))) ++ns;
+    if (h.down_slabs + ns > h.stage_slabs) return fail(BGC_ERR_ARG, "internal: staging area too small (download)");
+    LAUNCH(BGC_K_TRANSPOSE, 1, bgc::launch_transpose(dev + (size_t)s0 * n2c, h.stage + h.down_slabs * n2c, h.cc, h.nL, ns, c->stream));
+    h.downs.push_back({host + (size_t)s0 * n2, nullptr, ns, h.down_slabs});
+    h.down_slabs += ns;
+    s0 += ns;
+  }
   return BGC_OK;
+}
+
+// The zero fills collected by down_k, spread over a few host threads (the calling thread is one of
+// them); runs while the GPU and the copy engines work on what the call enqueued.
+static void run_zero_jobs(bgc_ctx *c) {
+  if (c->zero_jobs.empty()) return;
+  std::vector<bgc_ctx::ZeroJob> jobs;
+  jobs.swap(c->zero_jobs);
+  size_t total = 0;
+  for (const auto &j : jobs) total += j.bytes;
+  unsigned nthreads = std::thread::hardware_concurrency() / 2;
+  if (nthreads > 4) nthreads = 4;
+  if (total < ((size_t)8 << 20) || nthreads < 2) nthreads = 1;
+  std::atomic<size_t> next(0);
+  auto work = [&]() {
+    for (size_t i = next.fetch_add(1); i < jobs.size(); i = next.fetch_add(1)) memset(jobs[i].p, 0, jobs[i].bytes);
+  };
+  std::vector<std::thread> pool;
+  for (unsigned t = 1; t < nthreads; ++t) pool.emplace_back(work);
+  work();
+  for (auto &th : pool) th.join();
 }
 
 static int flush_down(bgc_ctx *c, HostChunk &h) {
@@ -704,6 +742,7 @@ static int host_pipeline(bgc_ctx *c, int nL, int nC, Body body) {
     rc = body(h);
   }
   c->stream = user;
+  if (rc == BGC_OK) run_zero_jobs(c); else c->zero_jobs.clear();
   // Fortran semantics: results are in host memory on return
   cudaError_t e1 = cudaStreamSynchronize(user), e2 = two ? cudaStreamSynchronize(c->pipe_stream) : cudaSuccess;
   if (rc != BGC_OK) return rc;
@@ -983,7 +1022,9 @@ extern "C" int bgc_source_sink(bgc_ctx *c, const BgcInput *in, const BgcForcing 
     RC(flush_up(c, h));
     RC(source_sink_device(c, &din, &dfo, &dout, diag ? &dd : nullptr, h.nL, h.cc, cols, alt_co2_use_eco, true));
 
-    RC(down_k(c, h, dout.BGC_tendencies, out->BGC_tendencies, BGC_TRACER_CNT));
+    // structurally zero: the DIC_ALT_CO2 tendency when alt_co2_use_eco is off (BGC_mod.F90:1741-1745)
+    const unsigned long long zero_tend = alt_co2_use_eco ? 0ull : (1ull << (c->bgc_tab.ind.dic_alt_co2_ind - 1));
+    RC(down_k(c, h, dout.BGC_tendencies, out->BGC_tendencies, BGC_TRACER_CNT, zero_tend));
     RC(down_k(c, h, dout.PH_PREV_3D, out->PH_PREV_3D, 1));
     RC(down_k(c, h, dout.PH_PREV_ALT_CO2_3D, out->PH_PREV_ALT_CO2_3D, 1));
     if (diag && c->diag_accumulate) {
@@ -1000,7 +1041,11 @@ extern "C" int bgc_source_sink(bgc_ctx *c, const BgcInput *in, const BgcForcing 
     } else if (diag) {
       // the three never-touched arrays stay exactly as the caller left them
       dd.diag_POC_ACCUM = dd.diag_DONr_remin = dd.diag_DOPr_remin = nullptr;
-#define DN_K2(name) if (dd.name) RC(down_k(c, h, dd.name, diag->name, 1));
+      // structurally zero: the three restoring terms when restoring is switched off (BGC_mod.F90:1545-1552
+      // and the like assign RESTORE = c0 then)
+      const double *const off_no3 = P.lrest_no3 ? nullptr : dd.diag_NO3_RESTORE, *const off_po4 = P.lrest_po4 ? nullptr : dd.diag_PO4_RESTORE,
+                   *const off_sio3 = P.lrest_sio3 ? nullptr : dd.diag_SiO3_RESTORE;
+#define DN_K2(name) if (dd.name) RC(down_k(c, h, dd.name, diag->name, 1, (dd.name == off_no3 || dd.name == off_po4 || dd.name == off_sio3) ? 1ull : 0ull));
 #define DN_KA(name) if (dd.name) RC(down_k(c, h, dd.name, diag->name, BGC_AUTOTROPH_CNT));
 #define DN_CA(name) if (dd.name) RC(down_c(c, h, dd.name, diag->name, sizeof(double), BGC_AUTOTROPH_CNT));
 #define DN_C1(name) if (dd.name) RC(down_c(c, h, dd.name, diag->name, sizeof(double), 1));
@@ -1304,7 +1349,9 @@ extern "C" int dms_source_sink(bgc_ctx *c, const DmsInput *in, const DmsForcing 
     }
     RC(flush_up(c, h));
     RC(dms_source_sink_device(c, &din, &dfo, &dout, diag ? &dd : nullptr, h.nL, h.cc, cols));
-    RC(down_k(c, h, dout.DMS_tendencies, out->DMS_tendencies, DMS_TRACER_CNT));
+    // only DMS and DMSP have tendencies; the other twelve slabs are the constant zero (DMS_mod.F90:413, :718-719)
+    const unsigned long long dms_live = (1ull << (c->dms_tab.ind.dms_ind - 1)) | (1ull << (c->dms_tab.ind.dmsp_ind - 1));
+    RC(down_k(c, h, dout.DMS_tendencies, out->DMS_tendencies, DMS_TRACER_CNT, ((1ull << DMS_TRACER_CNT) - 1ull) & ~dms_live));
     if (diag && c->diag_accumulate) {
 #define AC_D(name) if (dd.name) RC(acc_add(c, h, "dms." #name, dd.name, h.nL, 1, din.number_of_active_levels, cols));
       DMS_DIAG_LIST(AC_D)
@@ -1428,7 +1475,10 @@ extern "C" int macros_source_sink(bgc_ctx *c, const MacrosInput *in, MacrosOutpu
     }
     RC(flush_up(c, h));
     RC(macros_device(c, &din, &dout, diag ? &dd : nullptr, h.nL, h.cc, cols));
-    RC(down_k(c, h, dout.MACROS_tendencies, out->MACROS_tendencies, MACROS_TRACER_CNT));
+    // only PROT, POLY and LIP have tendencies (MACROS_mod.F90:267, :389-391)
+    const unsigned long long mac_live = (1ull << (c->macros_tab.ind.prot_ind - 1)) | (1ull << (c->macros_tab.ind.poly_ind - 1)) |
+                                        (1ull << (c->macros_tab.ind.lip_ind - 1));
+    RC(down_k(c, h, dout.MACROS_tendencies, out->MACROS_tendencies, MACROS_TRACER_CNT, ((1ull << MACROS_TRACER_CNT) - 1ull) & ~mac_live));
     if (diag && c->diag_accumulate) {
 #define AC_D(name) if (dd.name) RC(acc_add(c, h, "mac." #name, dd.name, h.nL, 1, din.number_of_active_levels, cols));
       MACROS_DIAG_LIST(AC_D)

@@ -460,10 +460,11 @@ macros_cells_kernel(const __grid_constant__ MacrosArgs A) {
 // dst(c, r) = src(r, c) for each of nSlabs 2-D slabs; src has `R` fastest.
 // 32x32 FP64 tile through padded shared memory: both sides coalesced.
 __global__ void __launch_bounds__(256)
-transpose_kernel(const double *__restrict__ src, double *__restrict__ dst, int R, int C) {
+transpose_kernel(const double *__restrict__ src, double *__restrict__ dst, int R, int C, int long_axis_is_c) {
   __shared__ double tile[32][33];
   const size_t slab = (size_t)blockIdx.z * (size_t)R * (size_t)C;
-  const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  // the longer axis (millions of columns) rides on gridDim.x, which has no 65535 limit
+  const int r0 = (long_axis_is_c ? blockIdx.y : blockIdx.x) * 32, c0 = (long_axis_is_c ? blockIdx.x : blockIdx.y) * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
 #pragma unroll
   for (int j = 0; j < 32; j += 8) {
@@ -796,10 +797,11 @@ cudaError_t launch_macros_cells(const MacrosArgs &a, cudaStream_t s) {
 
 cudaError_t launch_transpose(const double *src, double *dst, int R, int C, int nSlabs, cudaStream_t s) {
   if (R <= 0 || C <= 0 || nSlabs <= 0) return cudaSuccess;
-  // gridDim.y/z are limited to 65535: columns go on x when they are the long axis
-  dim3 grid(cdiv((size_t)R, 32), cdiv((size_t)C, 32), (unsigned)nSlabs);
+  // gridDim.y/z are limited to 65535: whichever axis is longer goes on x
+  const int c_long = C > R ? 1 : 0;
+  dim3 grid(cdiv((size_t)(c_long ? C : R), 32), cdiv((size_t)(c_long ? R : C), 32), (unsigned)nSlabs);
   if (grid.y > 65535u || grid.z > 65535u) return cudaErrorInvalidConfiguration;
-  transpose_kernel<<<grid, 256, 0, s>>>(src, dst, R, C);
+  transpose_kernel<<<grid, 256, 0, s>>>(src, dst, R, C, c_long);
   return cudaGetLastError();
 }
 
