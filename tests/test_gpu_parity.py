@@ -1016,3 +1016,27 @@ def test_mpas_thickness_weighted_tendency():
     for n in range(nT):
         assert torch.allclose(got2[:, :, n], 0.5 * h * soa[slot[n] - 1].T, rtol=1e-15, atol=0)
     ctx.close()
+
+
+def test_flavours_stay_separate_when_one_is_loaded_globally(o):
+    """Both flavours export the same names.  With the production library in the process's GLOBAL symbol
+    scope (what tests/test_fortran_shim.py does, and what a Fortran host's link line amounts to) the strict
+    library's internal calls must still reach its OWN kernels (-Bsymbolic): its answer differs from the
+    production build's in the last bits and is the one that sits within 1e-12 of the oracle."""
+    import ctypes
+    import os
+    ctypes.CDLL(os.path.join(host.CSRC, host.LIB_NAME["prod"]), mode=ctypes.RTLD_GLOBAL)
+    nL, nC = 40, 192
+    po = o.Parms()
+    res = {}
+    for flavour in ("prod", "strict"):
+        ctx, parms = _ctx(nL, nC, flavour=flavour)
+        cols, _, _ = parity.make_bgc(nL, nC, parms, ragged=True)
+        if flavour == "prod":
+            ref = cols.copy()
+            o.BGC_SourceSink(po, ref, True, nthreads=o.max_threads())
+        res[flavour] = parity.run_gpu_bgc(ctx, cols, device_mode=True)
+        ctx.close()
+    assert not np.array_equal(res["prod"].BGC_tendencies, res["strict"].BGC_tendencies)
+    worst = max(parity.nerr(res["strict"].BGC_tendencies[:, :, n], ref.BGC_tendencies[:, :, n]) for n in range(30))
+    assert worst <= 1e-12, worst
