@@ -306,7 +306,11 @@ int bgc_ctx_synchronize(bgc_ctx *ctx);
  * carbonate solve overlaps the HBM-bound DMS / MACROS / surface-flux kernels that follow. */
 int bgc_ctx_set_deferred_join(bgc_ctx *ctx, int enable);
 /* enable = 0 launches the carbonate kernel on the ctx stream after the sweep (no side stream):
- * for per-kernel timing and debugging.  Default: 1 (or the environment BGC_CONCURRENT_CO3). */
+ * for per-kernel timing and debugging.  Default: 1 (or the environment BGC_CONCURRENT_CO3) = side
+ * stream, placement chosen by the size of the sweep: beside the sweep when it has a partial last wave
+ * to fill; when the sweep is less than one wave (a GPU's slab in an 8-way split) the carbonate work is
+ * confined to the SMs the sweep cannot use, the remainder following behind the sweep.  2 and 3 pin
+ * "behind the sweep" and "confined" for experiments.  Results do not depend on the placement. */
 int bgc_ctx_set_concurrency(bgc_ctx *ctx, int enable);
 /* Zero-biomass shortcut of the column sweep (default on).  The reference zeroes a functional
  * group whose Chl, C or Fe is exactly zero in a cell (BGC_mod.F90:826-844) and then spends

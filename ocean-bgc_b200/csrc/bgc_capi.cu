@@ -109,7 +109,11 @@ struct bgc_ctx {
   // sweep: one side stream per pipeline slot, forked from / joined to the slot's stream
   cudaStream_t side_stream[2] = {nullptr, nullptr};
   cudaEvent_t fork_event[2] = {nullptr, nullptr}, join_event[2] = {nullptr, nullptr};
-  int concurrent_co3 = 1;                   // bgc_ctx_set_concurrency / BGC_CONCURRENT_CO3 (0, 1, 2: see source_sink_device)
+  int concurrent_co3 = 1;                   // bgc_ctx_set_concurrency / BGC_CONCURRENT_CO3 (0, 1, 2, 3: see source_sink_device)
+  int co3_confined = 0;                     // BGC_CO3_CONFINED=1: confine the carbonate kernel to a sub-wave sweep's idle SMs (measured: does not pay)
+  int co3_share_pct = 0;                    // BGC_CO3_SHARE: percent of the modelled share (0 = default)
+  unsigned long long *d_block_trace = nullptr;   // BGC_BLOCK_TRACE_FILE (debugging aid, bgc_kernels.cuh)
+  int co3_pblocks = 0, co3_after = 0;       // experiments: BGC_CO3_PBLOCKS (confined blocks), BGC_CO3_AFTER (launched after the sweep)
   int sm_count = 148;
   int zero_shortcut = 1;                    // bgc_ctx_set_zero_shortcut / BGC_ZERO_SHORTCUT
   bool diag_accumulate = false;             // bgc_diag_accumulate_enable
@@ -248,6 +252,15 @@ static int ctx_init(bgc_ctx *c, int device, int nLevelsMax, int nColumnsMax) {
   CU(cudaStreamCreateWithFlags(&c->pipe_stream, cudaStreamNonBlocking));
   CU(cudaEventCreateWithFlags(&c->pipe_event, cudaEventDisableTiming));
   if (const char *v = getenv("BGC_CONCURRENT_CO3")) c->concurrent_co3 = atoi(v);
+  if (const char *v = getenv("BGC_CO3_CONFINED")) c->co3_confined = atoi(v);
+  if (const char *v = getenv("BGC_CO3_SHARE")) c->co3_share_pct = atoi(v);
+  if (const char *v = getenv("BGC_CO3_PBLOCKS")) c->co3_pblocks = atoi(v);
+  if (getenv("BGC_BLOCK_TRACE_FILE")) {
+    const size_t bytes = (4 + 4 * (size_t)bgc::kBlockTraceCap) * sizeof(unsigned long long);
+    CU(cudaMalloc(&c->d_block_trace, bytes));
+    CU(cudaMemset(c->d_block_trace, 0, bytes));
+  }
+  if (const char *v = getenv("BGC_CO3_AFTER")) c->co3_after = atoi(v);
   CU(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
   if (const char *v = getenv("BGC_ZERO_SHORTCUT")) c->zero_shortcut = atoi(v);
   {
@@ -278,6 +291,20 @@ extern "C" int bgc_ctx_destroy(bgc_ctx *c) {
   if (c->pipe_stream) cudaStreamSynchronize(c->pipe_stream);
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   c->comm = nullptr;
+  if (c->d_block_trace) {   // debugging aid: one line per traced thread block
+    std::vector<unsigned long long> h(4 + 4 * (size_t)bgc::kBlockTraceCap);
+    const char *path = getenv("BGC_BLOCK_TRACE_FILE");
+    if (path && cudaMemcpy(h.data(), c->d_block_trace, h.size() * sizeof(h[0]), cudaMemcpyDeviceToHost) == cudaSuccess) {
+      if (FILE *f = fopen(path, "a")) {
+        const size_t n = h[0] < bgc::kBlockTraceCap ? (size_t)h[0] : (size_t)bgc::kBlockTraceCap;
+        for (size_t r = 0; r < n; ++r)
+          fprintf(f, "%u %u %llu %llu %llu\n", (unsigned)(h[4 + 4 * r] >> 32), (unsigned)(h[4 + 4 * r] & 0xffffffffu),
+                  h[5 + 4 * r], h[6 + 4 * r], h[7 + 4 * r]);
+        fclose(f);
+      }
+    }
+    cudaFree(c->d_block_trace);
+  }
   for (auto &kv : c->arena) if (kv.second.p) cudaFree(kv.second.p);
   for (auto &kv : c->host_stage) if (kv.second.p) cudaFreeHost(kv.second.p);
   cudaFree(c->d_status); cudaFree(c->d_inventory);
@@ -319,7 +346,9 @@ extern "C" int bgc_ctx_set_deferred_join(bgc_ctx *c, int enable) {
 extern "C" int bgc_ctx_set_concurrency(bgc_ctx *c, int enable) {
   RC(use_device(c));
   RC(join_pending(c));
-  c->concurrent_co3 = enable;   // 0 = same stream, 1 = side stream beside the sweep, 2 = side stream after the sweep
+  // 0 = same stream, 1 = side stream, placement chosen by the sweep's size (the default),
+  // 2 = side stream after the sweep, 3 = confined to the sweep's idle SMs where it has any, else 2
+  c->concurrent_co3 = enable;
   return BGC_OK;
 }
 
@@ -847,11 +876,32 @@ static int source_sink_device(bgc_ctx *c, const BgcInput *in, const BgcForcing *
   // previous kernel, and once carbonate blocks sit there the SM never empties: when the sweep is less
   // than one wave (fewer blocks than SMs: a GPU's slab in an 8-way split) its blocks starve behind
   // them and the sweep takes 1.06 instead of 0.58 ms.  There the fork moves behind the sweep
-  // (mode 2: the carbonate kernel runs beside the DMS / MACROS / surface kernels).
+  // (mode 2: the carbonate kernel runs beside the DMS / MACROS / surface kernels) - or, better, the
+  // carbonate work is CONFINED to the SMs the sub-wave sweep cannot use (mode 3): as many 512-thread
+  // carbonate blocks as there are idle SMs are launched before the sweep; each fills an SM's register
+  // file, so they land on that many different SMs and the sweep's blocks find exactly the others free,
+  // whichever kernel the block scheduler serves first.  They walk a share of the cells sized to last as
+  // long as the sweep (its duration is one column's latency however few columns there are); the rest
+  // of the cells follow behind the sweep as in mode 2.
   int co3_mode = c->concurrent_co3;
-  if (co3_mode == 1 && (nC + 255) / 256 < c->sm_count) co3_mode = 2;
+  const int sweep_blocks = bgc::eco_sweep_blocks(nC, c->eco_variant);
+  const int idle_sms = c->sm_count - sweep_blocks;
+  // (host-layout chunks are PCIe-bound and run two at a time on the pipeline slots: not confined)
+  if (co3_mode == 1 && idle_sms > 0) co3_mode = (idle_sms >= 8 && c->co3_confined && !host_call) ? 3 : 2;
+  else if (co3_mode == 3 && idle_sms <= 0) co3_mode = 1;
+  size_t co3_split = 0;   // mode 3: cells [0, co3_split) run beside the sweep, the rest behind it
+  if (co3_mode == 3) {
+    // measured on B200 (profiles/concurrency_sweep_r02.txt): the sweep takes ~9.7 us per level, a
+    // carbonate-filled SM retires ~80 cells per us; the share is cut to 85 % of that so that the
+    // confined blocks finish with the sweep rather than after it (BGC_CO3_SHARE: percent, experiments)
+    const double share = c->co3_share_pct > 0 ? c->co3_share_pct * 0.01 : 0.85;
+    const double cells = share * (double)idle_sms * 80.0 * (9.7 * (double)nL);
+    co3_split = (size_t)cells & ~(size_t)31;
+    if (co3_split >= n2) co3_split = n2;
+    if (co3_split == 0) co3_mode = 2;
+  }
   cudaStream_t co3_stream = co3_mode ? c->side_stream[slot] : main_stream;
-  if (co3_mode == 1) {   // fork BEFORE the sweep: the carbonate kernel runs beside it
+  if (co3_mode == 1 || co3_mode == 3) {   // fork BEFORE the sweep: the carbonate kernel runs beside it
     CU(cudaEventRecord(c->fork_event[slot], main_stream));
     CU(cudaStreamWaitEvent(co3_stream, c->fork_event[slot], 0));
   }
@@ -876,6 +926,7 @@ static int source_sink_device(bgc_ctx *c, const BgcInput *in, const BgcForcing *
   // declared in BGC_diagnostics_type but never zeroed nor written by the reference
   ea.d.diag_POC_ACCUM = ea.d.diag_DONr_remin = ea.d.diag_DOPr_remin = nullptr;
   ea.status = c->d_status;
+  ea.block_trace = c->d_block_trace;
   if (!bgc::eco_rows_from_tables(c->bgc_tab, ea))
     return fail(BGC_ERR_PARAMS, "bgc_source_sink: the tracer index tables do not cover the %d tracer slots", BGC_TRACER_CNT);
   // diag_mode 2 = every array the sweep owns is present -> unchecked stores.  The arrays of
@@ -905,12 +956,6 @@ static int source_sink_device(bgc_ctx *c, const BgcInput *in, const BgcForcing *
     inv_parts = bgc::eco_inventory_parts(ea, diag_mode, c->eco_variant);
     RC(arena_d(c, "inv_partials_bgc", (size_t)inv_parts * bgc::kEcoInvGroups * bgc::kInvGroup, &ea.inv_partials));
   }
-  LAUNCH(BGC_K_ECO_COLUMNS, 1, bgc::launch_eco_columns(ea, diag_mode, c->eco_variant, c->stream));
-  if (co3_mode >= 2) {   // fork AFTER the sweep: the carbonate kernel runs beside whatever follows on the ctx stream
-    CU(cudaEventRecord(c->fork_event[slot], main_stream));
-    CU(cudaStreamWaitEvent(co3_stream, c->fork_event[slot], 0));
-  }
-
   // carbonate chemistry, cell-parallel, then the saturation-depth scan (side stream)
   bgc::Co3Args ca;
   ca.nL = nL; ca.nC = nC; ca.nColumns = nCols;
@@ -921,6 +966,7 @@ static int source_sink_device(bgc_ctx *c, const BgcInput *in, const BgcForcing *
   ca.co3_alt = d.diag_CO3_ALT_CO2; ca.hco3_alt = d.diag_HCO3_ALT_CO2; ca.h2co3_alt = d.diag_H2CO3_ALT_CO2;
   ca.ph_alt = d.diag_pH_3D_ALT_CO2; ca.sat_calc = d.diag_co3_sat_calc; ca.sat_arag = d.diag_co3_sat_arag;
   ca.status = c->d_status;
+  ca.block_trace = c->d_block_trace;
   const bool want_zsat = d.diag_zsatcalc || d.diag_zsatarag;
   if (want_zsat) {   // the scan consumes these three: ctx scratch where the caller has no array
     const std::string sfx = slot ? "#1" : "#0";
@@ -928,9 +974,26 @@ static int source_sink_device(bgc_ctx *c, const BgcInput *in, const BgcForcing *
     if (!ca.sat_calc) RC(arena_d(c, "scratch_satc" + sfx, n2, &ca.sat_calc));
     if (!ca.sat_arag) RC(arena_d(c, "scratch_sata" + sfx, n2, &ca.sat_arag));
   }
+  auto launch_confined = [&]() -> int {
+    c->stream = co3_stream;   // LAUNCH brackets its timing events on c->stream
+    bgc::Co3Args part = ca;
+    part.cell_begin = 0; part.cell_end = co3_split;
+    const int pblocks = c->co3_pblocks > 0 ? c->co3_pblocks : idle_sms;
+    int rc_part = [&]() -> int { LAUNCH(BGC_K_CO3_CELLS, 1, bgc::launch_co3_cells(part, pblocks, c->stream)); return BGC_OK; }();
+    c->stream = main_stream;
+    ca.cell_begin = co3_split; ca.cell_end = 0;
+    return rc_part;
+  };
+  if (co3_mode == 3 && !c->co3_after) RC(launch_confined());
+  LAUNCH(BGC_K_ECO_COLUMNS, 1, bgc::launch_eco_columns(ea, diag_mode, c->eco_variant, c->stream));
+  if (co3_mode == 3 && c->co3_after) RC(launch_confined());
+  if (co3_mode >= 2) {   // fork AFTER the sweep: the carbonate kernel runs beside whatever follows on the ctx stream
+    CU(cudaEventRecord(c->fork_event[slot], main_stream));
+    CU(cudaStreamWaitEvent(co3_stream, c->fork_event[slot], 0));
+  }
   c->stream = co3_stream;   // LAUNCH brackets its timing events on c->stream
   int rc_side = [&]() -> int {
-    LAUNCH(BGC_K_CO3_CELLS, 1, bgc::launch_co3_cells(ca, c->stream));
+    if ((size_t)ca.cell_begin < n2) LAUNCH(BGC_K_CO3_CELLS, 1, bgc::launch_co3_cells(ca, 0, c->stream));
     if (want_zsat) {
       bgc::ZsatArgs za;
       za.nL = nL; za.nC = nC; za.nColumns = nCols; za.kmax = in->number_of_active_levels;

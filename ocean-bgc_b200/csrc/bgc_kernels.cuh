@@ -31,6 +31,32 @@ constexpr int kInvMaxGroups = 6;
 constexpr int kEcoInvGroups = 5;   // inventory groups produced by the column sweep (see below)
 
 // ---- carbonate kernel, one thread per CELL (no vertical coupling)
+
+// ---- debugging aid (BGC_BLOCK_TRACE_FILE): where and when every thread block of the two kernels of
+// bgc_source_sink ran.  trace[0] counts the records; record r = trace[4 + 4 r ...] =
+// {kernel id << 32 | SM id, start ns, end ns, blockIdx.x} (globaltimer).  NULL in production.
+constexpr unsigned kBlockTraceCap = 1u << 16;
+#ifdef __CUDACC__
+__device__ __forceinline__ unsigned block_trace_begin(unsigned long long *trace, unsigned kid) {
+  if (!trace) return ~0u;
+  const unsigned slot = (unsigned)atomicAdd(trace, 1ull);
+  if (slot >= kBlockTraceCap) return ~0u;
+  unsigned smid; unsigned long long t;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  trace[4 + 4 * (size_t)slot] = ((unsigned long long)kid << 32) | smid;
+  trace[5 + 4 * (size_t)slot] = t;
+  trace[7 + 4 * (size_t)slot] = blockIdx.x;
+  return slot;
+}
+__device__ __forceinline__ void block_trace_end(unsigned long long *trace, unsigned slot) {
+  if (slot == ~0u) return;
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  trace[6 + 4 * (size_t)slot] = t;
+}
+#endif
+
 struct Co3Args {
   int nL, nC, nColumns;
   const double *tracers;                 // (k,col,30) SoA
@@ -42,8 +68,12 @@ struct Co3Args {
   // (diagnostic arrays or ctx scratch) whenever diag_zsatcalc / diag_zsatarag are wanted.
   double *co3, *hco3, *h2co3, *ph, *co3_alt, *hco3_alt, *h2co3_alt, *ph_alt, *sat_calc, *sat_arag;
   unsigned long long *status;            // BgcStatus counters
+  // the launch's share of the mesh: cells [cell_begin, cell_end) in (k,col) order; cell_end = 0 means
+  // "to the end".  cell_begin must be a multiple of 32 (a warp never straddles two launches).
+  unsigned long long cell_begin = 0, cell_end = 0;
+  unsigned long long *block_trace = nullptr;   // debugging aid, see block_trace_begin
 };
-cudaError_t launch_co3_cells(const Co3Args &a, cudaStream_t s);
+cudaError_t launch_co3_cells(const Co3Args &a, int persistent_blocks, cudaStream_t s);
 
 // ---- saturation-depth scan (BGC_mod.F90:1003-1032), one thread per COLUMN, after the carbonate kernel
 struct ZsatArgs {
@@ -69,6 +99,7 @@ struct EcoArgs {
   BgcDiagnostics d;                      // carbonate, zsat* and never-touched members nulled by the caller
   unsigned long long *status;
   double *inv_partials;                  // NULL, or the fused stage 1 of the inventory reduction
+  unsigned long long *block_trace = nullptr;   // debugging aid, see block_trace_begin
   int bulk;                              // set by launch_eco_columns: stage the inputs with TMA bulk copies (16-byte aligned slabs)
   // Canonical stage row -> 1-based tracer slot (k_eco.cu: rows 0..15 the plain tracers in BgcIndices
   // order, 16+3a+{0,1,2} = C, Chl, Fe of group a, 28 = the Si tracer, 29 = the CaCO3 tracer); filled by
@@ -83,6 +114,7 @@ bool eco_rows_from_tables(const BgcTables &t, EcoArgs &a);
 // (k_eco.cu: launch_diag); 0 = default.
 cudaError_t launch_eco_columns(const EcoArgs &a, int diag_mode, int variant, cudaStream_t s);
 int eco_inventory_parts(const EcoArgs &a, int diag_mode, int variant);   // blocks the launch will use
+int eco_sweep_blocks(int nC, int variant);   // thread blocks of the column sweep (one per SM: k_eco.cu)
 
 // ---- surface fluxes, one thread per column
 struct SurfArgs {

@@ -10,6 +10,7 @@
 //
 // Every warp runs the Newton/bisection iteration warp-synchronously (see
 // bgc_co2.cuh), so all 32 lanes enter the solver even when some have no work.
+#include <cstdlib>
 #include "bgc_kernels.cuh"
 #include "bgc_co2.cuh"
 
@@ -36,13 +37,13 @@ __device__ __forceinline__ void report(unsigned long long *status, unsigned st) 
   }
 }
 
-__global__ void __launch_bounds__(256)
-co3_cells_kernel(const __grid_constant__ Co3Args A) {
+// One cell of the carbonate kernel.  `cell_end` bounds the launch's share of the mesh: a launch
+// covers the cells [A.cell_begin, cell_end), both multiples of 32 unless they are the ends of the mesh,
+// so that a warp never straddles two launches.
+__device__ __forceinline__ void co3_cell(const Co3Args &A, size_t cell, size_t cell_end, const ExpTable &ex) {
   const size_t nC = (size_t)A.nC;
   const size_t ncell = (size_t)A.nL * nC;
-  // whole warps only: the grid is sized so that every launched warp is complete
-  const size_t cell = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool in_range = cell < ncell;
+  const bool in_range = cell < cell_end;
   const int k = in_range ? (int)(cell / nC) : 0;
   const int col = in_range ? (int)(cell - (size_t)k * nC) : 0;
   const bool active = in_range && col < A.nColumns && k < A.kmax[col];
@@ -64,9 +65,6 @@ co3_cells_kernel(const __grid_constant__ Co3Args A) {
     ph_prev_alt = A.ph_prev_alt[cell];
   }
   const bool deep = k > 0;   // the reference's (k > 1), 1-based
-  __shared__ double s_exp2[64];
-  exp_table_load(s_exp2);
-  const ExpTable ex{s_exp2};
 
   // Both comp_CO3terms calls of a cell receive the SAME DIC/ALK/PO4/SiO3/T/S
   // (BGC_mod.F90:953 vs :975 — the alternative-CO2 call passes DIC_loc, not
@@ -138,6 +136,44 @@ co3_cells_kernel(const __grid_constant__ Co3Args A) {
     if (A.sat_calc) A.sat_calc[cell] = 0.0;
     if (A.sat_arag) A.sat_arag[cell] = 0.0;
   }
+}
+
+// PERSISTENT = false: one thread per cell of [cell_begin, cell_end), 256-thread blocks, whole warps only
+// (the grid is sized so that every launched warp is complete).
+// PERSISTENT = true: a FEW 512-thread blocks walk the range with a grid stride.  512 threads x 128
+// registers are a whole SM's register file, so each block owns one SM: bgc_capi.cu launches as many
+// as the column sweep leaves idle when it is less than one wave, and the carbonate work runs on
+// exactly those SMs while the sweep occupies the others (see source_sink_device).
+template <int BLOCK, bool PERSISTENT>
+__global__ void __launch_bounds__(BLOCK, PERSISTENT ? 1 : 2)
+co3_cells_kernel(const __grid_constant__ Co3Args A) {
+  __shared__ double s_exp2[64];
+  exp_table_load(s_exp2);
+  const ExpTable ex{s_exp2};
+  const size_t ncell = (size_t)A.nL * (size_t)A.nC;
+  const size_t end = A.cell_end ? (size_t)A.cell_end : ncell;
+  const unsigned tslot = (PERSISTENT && A.block_trace && threadIdx.x == 0) ? block_trace_begin(A.block_trace, 2u) : ~0u;
+  if (PERSISTENT) {
+    // a warp takes a trip or skips it as a whole (the solver's votes are warp-wide); no block
+    // barrier follows exp_table_load, so the warps of a block need not make the same number of trips
+    for (size_t base = (size_t)A.cell_begin + (size_t)blockIdx.x * BLOCK; base < end; base += (size_t)gridDim.x * BLOCK)
+      if (base + (threadIdx.x & ~31u) < end) co3_cell(A, base + threadIdx.x, end, ex);
+  } else {
+    co3_cell(A, (size_t)A.cell_begin + (size_t)blockIdx.x * BLOCK + threadIdx.x, end, ex);
+  }
+  if (PERSISTENT && A.block_trace) { __syncthreads(); if (threadIdx.x == 0) block_trace_end(A.block_trace, tslot); }
+}
+
+// Experiment only (BGC_CO3_DUMMY=<iterations>): SM-filling blocks that run a tiny FP64 loop instead of the
+// carbonate code, to tell what a co-resident kernel costs the column sweep apart from its code size.
+__global__ void __launch_bounds__(512, 1) fp64_spin_kernel(double *sink, int iters, unsigned long long *trace) {
+  const unsigned tslot = (trace && threadIdx.x == 0) ? block_trace_begin(trace, 2u) : ~0u;
+  double a = 1.0 + threadIdx.x * 1e-9, b = 0.5, c = 0.25, d = 0.125;
+  for (int i = 0; i < iters; ++i) {
+    a = fma(a, 1.0000001, 1e-9); b = fma(b, 0.9999999, 1e-9); c = fma(c, 1.0000002, 1e-9); d = fma(d, 0.9999998, 1e-9);
+  }
+  if (a + b + c + d == 1.2345e300) *sink = a;
+  if (trace) { __syncthreads(); if (threadIdx.x == 0) block_trace_end(trace, tslot); }
 }
 
 // Saturation-depth scan (BGC_mod.F90:1003-1032): the depth at which CO3 first falls to the
@@ -396,10 +432,20 @@ surface_fluxes_kernel(const __grid_constant__ SurfArgs A) {
 
 static inline int ceil_div_sz(size_t a, size_t b) { return (int)((a + b - 1) / b); }
 
-cudaError_t launch_co3_cells(const Co3Args &a, cudaStream_t s) {
+// persistent_blocks = 0: one thread per cell of the range; > 0: that many SM-filling blocks (see the kernel)
+cudaError_t launch_co3_cells(const Co3Args &a, int persistent_blocks, cudaStream_t s) {
   const size_t ncell = (size_t)a.nL * (size_t)a.nC;
-  if (ncell == 0) return cudaSuccess;
-  co3_cells_kernel<<<ceil_div_sz(ncell, 256), 256, 0, s>>>(a);
+  const size_t end = a.cell_end ? (size_t)a.cell_end : ncell;
+  if (ncell == 0 || end <= (size_t)a.cell_begin) return cudaSuccess;
+  if (end > ncell || ((a.cell_begin & 31) != 0)) return cudaErrorInvalidValue;
+  static int dummy = -1;
+  if (dummy < 0) { const char *v = getenv("BGC_CO3_DUMMY"); dummy = v ? atoi(v) : 0; }
+  if (persistent_blocks > 0 && dummy > 0) {
+    fp64_spin_kernel<<<persistent_blocks, 512, 0, s>>>(a.ph_prev + 0 * ncell, dummy, a.block_trace);
+    return cudaGetLastError();
+  }
+  if (persistent_blocks > 0) co3_cells_kernel<512, true><<<persistent_blocks, 512, 0, s>>>(a);
+  else co3_cells_kernel<256, false><<<ceil_div_sz(end - (size_t)a.cell_begin, 256), 256, 0, s>>>(a);
   return cudaGetLastError();
 }
 

@@ -271,6 +271,8 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
   const int col = col0 + tid;
   const int nL = A.nL, nC = A.nC;
   const bool in_range = col < nC;
+  __shared__ unsigned s_tslot;   // (debugging aid; in shared memory: no register is free to hold it)
+  if (A.block_trace && tid == 0) s_tslot = block_trace_begin(A.block_trace, 1u);
   // Element indices are 32-bit: one IMAD.WIDE.U32 forms an address from (index, base pointer).
   // The largest index, 30 * nL * nC, stays below 2^32 for any block that fits one GPU's memory
   // (180 GB / 2200 B per cell = 82 M cells); bgc_capi.cu rejects larger blocks.
@@ -1302,6 +1304,7 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
     __syncthreads();
   }   // level loop
 
+  if (A.block_trace && tid == 0) block_trace_end(A.block_trace, s_tslot);   // (after the last level's barrier)
   // ---- per-column diagnostics
   if (DIAG && in_range) {
     if (kmax > 0) {
@@ -1418,6 +1421,11 @@ bool eco_rows_from_tables(const BgcTables &t, EcoArgs &a) {
   put(CA_ROW, ca > 0 ? ca : I.spCaCO3_ind);
   for (int s = 1; s <= BGC_TRACER_CNT; ++s) if (!seen[s]) return false;
   return true;
+}
+
+int eco_sweep_blocks(int nC, int variant) {
+  const int block = block_of(variant);
+  return (nC + block - 1) / block;
 }
 
 int eco_inventory_parts(const EcoArgs &a, int diag_mode, int variant) {

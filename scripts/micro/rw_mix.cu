@@ -139,6 +139,64 @@ __global__ void __launch_bounds__(256, 1) store_paths(double *out, int nL, int n
   if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
+
+// ---- the sweep's own structure without its arithmetic: inputs staged by the TMA unit ----
+// One 256-thread block per SM; lane 0 of every warp fetches its share of the NEXT level's NR input
+// rows with cp.async.bulk (2-KB runs) into a double-buffered shared-memory stage signalled on an
+// mbarrier, exactly as eco_columns_kernel does; the compute threads read shared memory only and issue
+// the NW plain 8-byte stores of the level.  What this kernel sustains is what the memory system gives
+// the sweep's traffic at the sweep's occupancy when NO load latency is exposed; the gap between it and
+// the sweep is the sweep's arithmetic (dependency latency at 8 warps per SM), not HBM.
+template <int NR, int NW, int SPREAD>
+__global__ void __launch_bounds__(256, 1) column_tma(Ptrs p, int nL, int nC, double *sink) {
+  extern __shared__ __align__(128) double stage[];           // 2 x NR x 256 doubles, then 2 mbarriers
+  unsigned long long *bars = (unsigned long long *)(stage + 2 * NR * 256);
+  const int tid = threadIdx.x;
+  const size_t slab = (size_t)nL * nC;
+  const size_t col0 = (size_t)blockIdx.x * 256;
+  if (tid == 0) {
+    for (int b = 0; b < 2; ++b)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(&bars[b])), "r"(1) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto fetch = [&](int k) {
+    if (tid & 31) return;
+    const unsigned bar = smem_addr(&bars[k & 1]);
+    if (tid == 0)
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(NR * 2048) : "memory");
+    for (int r = tid >> 5; r < NR; r += 8)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(smem_addr(stage + ((k & 1) * NR + r) * 256)), "l"(p.in + r * slab + (size_t)k * nC + col0),
+                     "r"(2048), "r"(bar) : "memory");
+  };
+  fetch(0);
+  double s = 0;
+  for (int k = 0; k < nL; ++k) {
+    const unsigned bar = smem_addr(&bars[k & 1]), parity = (unsigned)((k >> 1) & 1);
+    asm volatile("{\n\t.reg .pred P1;\n\tLW:\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t@P1 bra DN;\n\tbra LW;\n\tDN:\n\t}"
+                 ::"r"(bar), "r"(parity) : "memory");
+    if (k + 1 < nL) fetch(k + 1);
+    const double *st = stage + (k & 1) * NR * 256;
+#pragma unroll
+    for (int r = 0; r < NR; ++r) s += st[r * 256 + tid];
+    const size_t e = (size_t)k * nC + col0 + tid;
+    // SPREAD = 0: the stores of a level back to back; 1: a dependent FP64 chain between them (8 x 8
+    // cycles each), so that they leave at the sweep's pace instead of in one burst
+#pragma unroll 8
+    for (int w = 0; w < NW; ++w) {
+      if (SPREAD) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s = fma(s, 1.0000001, 1e-9);
+      }
+      p.out[w * slab + e] = s + w;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+  }
+  if (s == 1.2345e300) *sink = s;
+}
+
 template <typename F>
 static float time_ms(F launch, int reps = 5) {
   cudaEvent_t a, b; CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
@@ -195,6 +253,17 @@ static void run_stores(double *out, int nL, int nC, const char *what) {
          (double)NW * 8.0 * nL * nC / ms * 1e-6, what);
 }
 
+template <int NR, int NW, int SPREAD>
+static void run_tma(const double *in, double *out, double *sink, int nL, int nC, const char *what) {
+  auto kern = column_tma<NR, NW, SPREAD>;
+  const int smem = 2 * NR * 2048 + 16;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  Ptrs p{in, out};
+  float ms = time_ms([&] { kern<<<nC / 256, 256, smem>>>(p, nL, nC, sink); });
+  printf("TMA-fed  %3dR+%3dW,  1 block/SM ( 8 warps/SM): %7.3f ms  %7.1f GB/s   %s\n", NR, NW, ms,
+         (double)(NR + NW) * 8.0 * nL * nC / ms * 1e-6, what);
+}
+
 int main() {
   const int nL = 60, nC = 235160;              // EC60to30
   const size_t cells = (size_t)nL * nC;
@@ -215,6 +284,13 @@ int main() {
   printf("cudaMemset      : %7.3f ms  %7.1f GB/s\n", ms, 1.0 * n2 * 16 / ms * 1e-6);
 
   const int nCt = 235008;                    // whole 256-column blocks for the tiled / bulk variants
+  if (getenv("RW_MIX_TMA")) {   // the sweep's structure (TMA-staged inputs, plain stores) without arithmetic
+    run_tma<37, 146, 0>(in, out, sink, nL, nCt, "sweep mix, inputs by cp.async.bulk, stores in a burst");
+    run_tma<37, 146, 1>(in, out, sink, nL, nCt, "sweep mix, inputs by cp.async.bulk, stores paced by an FP64 chain");
+    run_tma<33, 146, 0>(in, out, sink, nL, nCt, "33 fetched rows (as the sweep), stores in a burst");
+    run_layout<37, 146, 1, 0>(in, out, sink, nL, nCt, "per-thread loads, 1 block/SM (the r01 proxy)");
+    return 0;
+  }
   if (getenv("RW_MIX_STORES") && !getenv("RW_MIX_ALL")) {
     run_stores<146, 0>(out, nL, nCt, "st.global, 8 B per thread");
     run_stores<146, 1>(out, nL, nCt, "st.global.cs");

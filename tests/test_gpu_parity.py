@@ -884,6 +884,35 @@ def test_block_width_does_not_change_the_bits(nC_a, nC_b):
             assert np.array_equal(x[:n], y[:n]), nm
 
 
+@pytest.mark.parametrize("share", [0, 1, 100])
+def test_carbonate_placement_does_not_change_the_bits(share, monkeypatch):
+    """bgc_source_sink places the carbonate kernel by the size of the sweep (bgc_capi.cu: same stream,
+    beside the sweep, behind it, or - for a sweep of less than one wave - confined to the SMs the sweep
+    leaves idle, as SM-filling persistent blocks over a share of the cells with the rest behind the
+    sweep).  Every placement gives the same bits: share = 1 % (of the modelled capacity of the idle SMs) cuts this mesh in the middle of a level,
+    100 % puts all of it into the persistent blocks."""
+    nL, nC = 60, 2300
+    parms = host.Parms()
+    cols, _, _ = parity.make_bgc(nL, nC, parms, ragged=True)
+    if share:
+        monkeypatch.setenv("BGC_CO3_SHARE", str(share))
+    outs = []
+    for mode in ((0, 3) if share else (0, 1, 2, 3)):
+        ctx = host.Context(nL, nC, device=0, parms=parms)
+        ctx.set_concurrency(mode)
+        got = parity.run_gpu_bgc(ctx, cols, device_mode=True)
+        got = parity.run_gpu_bgc(ctx, got, device_mode=True)      # warm pass as well
+        outs.append(got)
+        ctx.close()
+    a = outs[0]
+    for b in outs[1:]:
+        assert np.array_equal(a.BGC_tendencies, b.BGC_tendencies)
+        assert np.array_equal(a.PH_PREV_3D, b.PH_PREV_3D)
+        assert np.array_equal(a.PH_PREV_ALT_CO2_3D, b.PH_PREV_ALT_CO2_3D)
+        for nm in a.diag:
+            assert np.array_equal(a.diag[nm], b.diag[nm]), nm
+
+
 def test_comp_co3terms_and_sat_vals_points(o):
     """The rest of the co2calc module's public trio on the GPU (co2calc.F90:214-316, :1096-1238), batched,
     against the oracle point by point: surface and deep levels, cold and warm brackets."""
