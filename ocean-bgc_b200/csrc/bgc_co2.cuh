@@ -80,7 +80,7 @@ __device__ __forceinline__ void co3_coeffs(bool deep, double depth, double temp,
                                            Co3Consts &c, const EXP &ex) {
   const double press_bar = press_bar_of_depth(depth, ex);
 
-  const double salt_lim = fmax(salt, kSaltMin);
+  const double salt_lim = gmax(salt, kSaltMin);
   const double tk = kT0Kelvin + temp;
   const double tk100 = tk * 1e-2;
   const double tk1002 = tk100 * tk100;
@@ -257,10 +257,10 @@ __device__ __forceinline__ void talk_residual(const Co3Consts &k, const Co3Total
 
 __device__ __forceinline__ Co3Totals co3_totals(double dic_in, double ta_in, double pt_in, double sit_in) {
   Co3Totals t;   // co2calc.F90:843-846
-  t.dic = fmax(dic_in, kDicMin) * kVolToMass;
-  t.ta = fmax(ta_in, kAlkMin) * kVolToMass;
-  t.pt = fmax(pt_in, 0.0) * kVolToMass;
-  t.sit = fmax(sit_in, 0.0) * kVolToMass;
+  t.dic = gmax(dic_in, kDicMin) * kVolToMass;
+  t.ta = gmax(ta_in, kAlkMin) * kVolToMass;
+  t.pt = gmax(pt_in, 0.0) * kVolToMass;
+  t.sit = gmax(sit_in, 0.0) * kVolToMass;
   return t;
 }
 
@@ -348,7 +348,7 @@ template <class EXP>
 __device__ __forceinline__ void co3_sat_vals(bool deep, double depth, double temp, double salt,
                                              double &co3_sat_calc, double &co3_sat_arag, const EXP &ex) {
   const double press_bar = press_bar_of_depth(depth, ex);
-  const double salt_lim = fmax(salt, kSaltMin);
+  const double salt_lim = gmax(salt, kSaltMin);
   const double tk = kT0Kelvin + temp;
   const double log10tk = cdiv(blog(tk), kLn10, 1.0 / kLn10);   // :1161-1164
   const double invtk = frcp(tk);

@@ -161,6 +161,7 @@ struct DmsArgs {
   double *tend;
   DmsDiagnostics d;
   double *inv_partials;   // NULL, or [dms_inventory_parts][kInvGroup]: fused stage 1 of the inventory
+  int l2_prefetch = 0;    // set by launch_dms_columns
 };
 cudaError_t launch_dms_columns(const DmsArgs &a, int variant, cudaStream_t s);
 

@@ -57,10 +57,10 @@ __device__ __forceinline__ void co3_cell(const Co3Args &A, size_t cell, size_t c
     temp = A.T[cell];
     salt = A.S[cell];
     depth = A.zmid[cell] * 0.01;   // cm -> m (BGC_mod.F90:950)
-    dic = fmax(0.0, A.tracers[cell + (size_t)(I.dic_ind - 1) * nLnC]);
-    alk = fmax(0.0, A.tracers[cell + (size_t)(I.alk_ind - 1) * nLnC]);
-    po4 = fmax(0.0, A.tracers[cell + (size_t)(I.po4_ind - 1) * nLnC]);
-    sio3 = fmax(0.0, A.tracers[cell + (size_t)(I.sio3_ind - 1) * nLnC]);
+    dic = gmax(0.0, A.tracers[cell + (size_t)(I.dic_ind - 1) * nLnC]);
+    alk = gmax(0.0, A.tracers[cell + (size_t)(I.alk_ind - 1) * nLnC]);
+    po4 = gmax(0.0, A.tracers[cell + (size_t)(I.po4_ind - 1) * nLnC]);
+    sio3 = gmax(0.0, A.tracers[cell + (size_t)(I.sio3_ind - 1) * nLnC]);
     ph_prev = A.ph_prev[cell];
     ph_prev_alt = A.ph_prev_alt[cell];
   }
@@ -336,7 +336,7 @@ surface_fluxes_kernel(const __grid_constant__ SurfArgs A) {
   const bool active = col < A.nColumns;
   const BgcIndices &I = c_co3.ind;
   const BgcParams &P = c_co3.p;
-#define SURF(ind_) fmax(0.0, A.tracers[(size_t)col + (size_t)((ind_) - 1) * nLnC])
+#define SURF(ind_) gmax(0.0, A.tracers[(size_t)col + (size_t)((ind_) - 1) * nLnC])
 #define FLX(arr, ind_) A.f.arr[(size_t)col + (size_t)((ind_) - 1) * nC]
 #define DG(name, val) do { if (A.d.name) A.d.name[col] = (val); } while (0)
 

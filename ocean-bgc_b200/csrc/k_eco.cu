@@ -44,6 +44,7 @@
 // depend on the carbonate kernel at all, so the two run concurrently (bgc_capi.cu) and
 // the FP64-bound carbonate work fills the SMs that the last, partial wave of this kernel
 // leaves idle (235 160 columns = 6.2 waves of 148 blocks x 256 columns).
+#include <cstdlib>
 #include "bgc_kernels.cuh"
 #include "bgc_math.cuh"
 #include "bgc_reduce.cuh"
@@ -308,7 +309,7 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
   for (int r = X_ZPHOTO; r < X_ROWS; ++r) XS(r) = 0.0;
   if (kmax > 0) {
     lat = A.lat[col];
-    const double dust_in = fmax(0.0, A.dust_flux_in[col]);
+    const double dust_in = gmax(0.0, A.dust_flux_in[col]);
     double du_s = 0.0, du_h = 0.0;
     if (dust_in != 0.0) {
       du_s = (1.0 - dust_gamma) * dust_in;
@@ -317,7 +318,7 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
     XS(X_DUS) = du_s;
     XS(X_DUH) = du_h;
     XS(X_QADUST) = dust_rho * (du_s + du_h);
-    double PAR_out = fmax(0.0, A.sw_flux[col]);
+    double PAR_out = gmax(0.0, A.sw_flux[col]);
     PAR_out = PAR_out * f_qsw_par;
     XS(X_PAROUT) = PAR_out;
   }
@@ -394,10 +395,11 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
       cp_async_commit();
     }
   };
-  // Level 0 is fetched here; level k + 1 is requested from the middle of level k (fetch_next below):
-  // right after a block barrier every warp would stall on the issue latency at the same time, while
-  // half a level later the warps have drifted apart and the other warp of the scheduler has work.
-  // Half a level (~10 k cycles) is several HBM round trips, so the data is there in time.
+  // Level 0 is fetched here; level k + 1 is requested from inside level k (FETCH_NEXT below), after the
+  // first functional group: right after a block barrier every warp would stall on the issue latency
+  // at the same time, while a group later the warps have drifted apart and the other warp of the
+  // scheduler has work.  (Requested after the LAST group, half a level ahead, the data was late often
+  // enough for the mbarrier wait to collect 2.5 % of the kernel's stall samples.)
   if (kmax_blk > 0) fetch_level(0);
 
   for (int k = 0; k < nL; ++k) {
@@ -429,7 +431,7 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
       }
     } else {
 
-#define TR(row_) fmax(0.0, IN(row_))
+#define TR(row_) gmax(0.0, IN(row_))
 #define TEND(row_) A.tend[i2 + A.tend_off[row_]]
 
     // ---- this level's inputs (setup_loop clamp folded in, :747-783)
@@ -454,7 +456,7 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
     }
 
     const double ztop = (k > 0) ? XS(X_ZBOTKM1) : 0.0;
-    const double pt100 = fmax(fmin(100.0e2 - ztop, dz), 0.0);   // upper-100 m part of this layer (:1880-1885)
+    const double pt100 = gmax(gmin(100.0e2 - ztop, dz), 0.0);   // upper-100 m part of this layer (:1880-1885)
 
     // ---- functional-group tracers: clamp, zero mask (:826-844), Pprime (:1083-1094);
     //      staged in shared memory for the rolled group loop below
@@ -483,7 +485,7 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
         const double tmpTmax = north ? at.temp_thresN : at.temp_thresS;
         if (TEMP > tmpTmax) C_loss_thres = f_loss_thres * at.loss_thres2;
       }
-      Pp[a] = fmax(vC - C_loss_thres, 0.0);
+      Pp[a] = gmax(vC - C_loss_thres, 0.0);
     }
     if (DIAG) XS(X_CHL100) = XS(X_CHL100) + Chl_100;
 
@@ -491,7 +493,7 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
     const double PAR_in = XS(X_PAROUT);
     double KPARdz;
     {
-      const double w = fmax(Chl_sum, 0.02);
+      const double w = gmax(Chl_sum, 0.02);
       if (w < 0.13224) KPARdz = 0.000919 * fpow(w, 0.3536);
       else             KPARdz = 0.001131 * fpow(w, 0.4562);
     }
@@ -529,6 +531,7 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
     //      grazing, routing (:1107-1388), tendencies (:1700-1745)
 #pragma unroll
     for (int a = 0; a < NA; ++a) {
+      if (a == 1) FETCH_NEXT();   // request level k + 1 (see fetch_level) once the first group is done
       const BgcAutotroph &at = c_eco.a[a];
       const unsigned ia = i2 + (unsigned)a * nLnC;
       const double aChl = IN(G_CHL(a)), aC = IN(G_C(a)), aFe = IN(G_FE(a)), Pprime = Pp[a];
@@ -593,21 +596,21 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
       double Qsi = 0.0, gQsi = 0.0, QCaCO3 = 0.0;
       if (has_Si) {
 #ifdef BGC_STRICT
-        Qsi = fmin(IN(SI_ROW) / (aC + epsC), gQsi_max);
+        Qsi = gmin(IN(SI_ROW) / (aC + epsC), gQsi_max);
 #else
-        Qsi = fmin(IN(SI_ROW) * rCden, gQsi_max);
+        Qsi = gmin(IN(SI_ROW) * rCden, gQsi_max);
 #endif
       }
       double gQfe = at.gQfe_0;
       if (Fe_loc < D.cks_kFe[a])
-        gQfe = fmax(cdiv(gQfe * Fe_loc, D.cks_kFe[a], D.r_cks_kFe[a]), at.gQfe_min);
+        gQfe = gmax(cdiv(gQfe * Fe_loc, D.cks_kFe[a], D.r_cks_kFe[a]), at.gQfe_min);
       if (has_Si) {
         double g = gQsi_0;
         if ((Fe_loc < D.cksi_kFe[a]) && (Fe_loc > 0.0) && (SiO3_loc > D.cksi_kSiO3[a]))
-          g = fmin(fdiv(g * P.cksi * at.kFe, Fe_loc), gQsi_max);
+          g = gmin(fdiv(g * P.cksi * at.kFe, Fe_loc), gQsi_max);
         if (Fe_loc == 0.0) g = gQsi_max;
         if (SiO3_loc < D.cksi_kSiO3[a])
-          g = fmax(cdiv(g * SiO3_loc, D.cksi_kSiO3[a], D.r_cksi_kSiO3[a]), gQsi_min);
+          g = gmax(cdiv(g * SiO3_loc, D.cksi_kSiO3[a], D.r_cksi_kSiO3[a]), gQsi_min);
         gQsi = g;
       }
       if (has_Ca) {
@@ -632,7 +635,7 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
       if (at.Nfixer) VNtot = 1.0;
 
       const double VFe = fdiv(Fe_loc, Fe_loc + at.kFe);
-      double f_nut = fmin(VNtot, VFe);
+      double f_nut = gmin(VNtot, VFe);
 
       const double rPO4 = cdiv(PO4_loc, at.kPO4, D.r_kPO4[a]), rDOP = cdiv(DOP_loc, at.kDOP, D.r_kDOP[a]);
 #ifdef BGC_STRICT
@@ -643,12 +646,12 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
       const double VPO4 = rPO4 * rPd, VDOP = rDOP * rPd;
 #endif
       const double VPtot = VPO4 + VDOP;
-      f_nut = fmin(f_nut, VPtot);
+      f_nut = gmin(f_nut, VPtot);
 
       double VSiO3 = 0.0;
       if (at.kSiO3 > 0.0) {
         VSiO3 = fdiv(SiO3_loc, SiO3_loc + at.kSiO3);
-        f_nut = fmin(f_nut, VSiO3);
+        f_nut = gmin(f_nut, VSiO3);
       }
       if (DIAG) {
         STA(diag_N_lim, VNtot);
@@ -663,7 +666,7 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
       if (at.temp_function == BGC_TFNC_QUASI_MMRT) {
         const double tmpTopt = north ? at.temp_optN : at.temp_optS;
         const double tmpTmax = north ? at.temp_thresN : at.temp_thresS;
-        PCmax = PCmax * fmin(1.0, cdiv(tmpTmax - TEMP, tmpTmax - tmpTopt, north ? D.r_dTN[a] : D.r_dTS[a]));
+        PCmax = PCmax * gmin(1.0, cdiv(tmpTmax - TEMP, tmpTmax - tmpTopt, north ? D.r_dTN[a] : D.r_dTS[a]));
         if (TEMP > tmpTmax) PCmax = 0.0;
       }
       const double aPI = at.alphaPI * thetaC * PAR_avg;
@@ -731,9 +734,9 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
         double cp = P.parm_f_prod_sp_CaCO3 * photoC;
         cp = cp * f_nut;
         if (TEMP < CaCO3_temp_thres1)
-          cp = cp * fmax((TEMP - CaCO3_temp_thres2), 0.0) / (CaCO3_temp_thres1 - CaCO3_temp_thres2);
+          cp = cp * gmax((TEMP - CaCO3_temp_thres2), 0.0) / (CaCO3_temp_thres1 - CaCO3_temp_thres2);
         if (aC > CaCO3_sp_thres)
-          cp = fmin((cp * aC / CaCO3_sp_thres), (f_photosp_CaCO3 * photoC));
+          cp = gmin((cp * aC / CaCO3_sp_thres), (f_photosp_CaCO3 * photoC));
         CaCO3_PROD = cp;
         tot_CaCO3_form = tot_CaCO3_form + cp;
         if (DIAG) {
@@ -746,8 +749,8 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
 
       // losses and aggregation (:1285-1290)
       const double auto_loss = at.mort * Pprime * Tfunc;
-      double auto_agg = fmin(D.agg_max_dps[a] * Pprime, at.mort2 * Pprime * Pprime);
-      auto_agg = fmax(D.agg_min_dps[a] * Pprime, auto_agg);
+      double auto_agg = gmin(D.agg_max_dps[a] * Pprime, at.mort2 * Pprime * Pprime);
+      auto_agg = gmax(D.agg_min_dps[a] * Pprime, auto_agg);
 
       // grazing (:1297-1324)
       double grazee_C = 0.0;
@@ -758,9 +761,9 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
       double z_umax = at.z_umax_0 * Tfunc;
       if (a + 1 == I.diat_ind) {
         if (north && (TEMP > at.temp_optN)) {
-          z_umax = z_umax * fmax(cdiv(at.temp_thresN - TEMP, at.temp_thresN - at.temp_optN, D.r_dTN[a]), 0.95);
+          z_umax = z_umax * gmax(cdiv(at.temp_thresN - TEMP, at.temp_thresN - at.temp_optN, D.r_dTN[a]), 0.95);
         } else if ((lat <= 0.0) && (TEMP > at.temp_optS)) {
-          z_umax = z_umax * fmax(cdiv(at.temp_thresS - TEMP, at.temp_thresS - at.temp_optS, D.r_dTS[a]), 0.95);
+          z_umax = z_umax * gmax(cdiv(at.temp_thresS - TEMP, at.temp_thresS - at.temp_optS, D.r_dTS[a]), 0.95);
         }
       }
       double auto_graze = 0.0;
@@ -789,8 +792,8 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
       const double auto_graze_zoo = at.graze_zoo * auto_graze;
       double auto_graze_poc, auto_loss_poc;
       if (at.imp_calcifier) {
-        auto_graze_poc = auto_graze * fmax((caco3_poc_min * QCaCO3),
-                                           fmin(spc_poc_fac * fmax(1.0, Pprime), f_graze_sp_poc_lim));
+        auto_graze_poc = auto_graze * gmax((caco3_poc_min * QCaCO3),
+                                           gmin(spc_poc_fac * gmax(1.0, Pprime), f_graze_sp_poc_lim));
         auto_loss_poc = QCaCO3 * auto_loss;
       } else {
         auto_graze_poc = at.graze_poc * auto_graze;
@@ -915,7 +918,7 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
       }
     }   // functional groups
 
-    FETCH_NEXT();   // request level k + 1 (see fetch_level)
+    FETCH_NEXT();   // (a table with a single functional group gets here first)
     if (DIAG) {   // (every diagnostic is stored as soon as its value is final: short live ranges, no store bursts)
       ST2(diag_tot_Nfix, tot_Nfix);
       ST2(diag_tot_CaCO3_form, tot_CaCO3_form);
@@ -931,7 +934,7 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
 
     // ---- zooplankton routing (:1395-1415)
     const double f_zoo_detr = fdiv(zd_num, zd_den);
-    const double Zprime = fmax(zooC_loc - f_loss_thres * loss_thres_zoo, 0.0);
+    const double Zprime = gmax(zooC_loc - f_loss_thres * loss_thres_zoo, 0.0);
     const double zoo_loss = (P.parm_z_mort2_0 * fpow15(Zprime) + P.parm_z_mort_0 * Zprime) * Tfunc;
     const double zoo_loss_doc = (1.0 - P.parm_labile_ratio) * (1.0 - f_zoo_detr) * zoo_loss;
     const double zoo_loss_dic = P.parm_labile_ratio * (1.0 - f_zoo_detr) * zoo_loss;
@@ -1073,7 +1076,7 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
       } else {
         POC_h = CaCO3_rho * (Ca_s + Ca_h) + SiO2_rho * (Si_s + Si_h) + dust_rho * (du_s + du_h) -
                 new_QA_dust_def;
-        POC_h = fmax(POC_h, 0.0);
+        POC_h = gmax(POC_h, 0.0);
       }
       POC_s = POC_s_in * decay_POC_E + POC_PROD_avail * ((1.0 - decay_POC_E) * poc_diss);
 
@@ -1099,13 +1102,13 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
         double flux = POC_s + POC_h;
         if (flux > 0.0) {
           double flux_alt = flux * mpercm * spd;
-          POC_sed = flux * fmin(0.8, P.parm_POMbury *
+          POC_sed = flux * gmin(0.8, P.parm_POMbury *
                                          (0.013 + fdiv(0.53 * flux_alt * flux_alt,
                                                        ((7.0 + flux_alt) * (7.0 + flux_alt)))));
           SED_DENITRIF = dzr * flux * (0.06 + 0.19 * fpow_base(0.99, kLn099, (O2_loc - NO3_loc)));
           if (NO3_loc < 5.0) SED_DENITRIF = 0.0;
           flux_alt = flux * 1.0e-6 * spd * 365.0;
-          OTHER_REMIN = dzr * fmin(fmin(0.1 + flux_alt, 0.5) * (flux - POC_sed),
+          OTHER_REMIN = dzr * gmin(gmin(0.1 + flux_alt, 0.5) * (flux - POC_sed),
                                    (flux - POC_sed - (SED_DENITRIF * dz * denitrif_C_N)));
           if (O2_loc < 1.0) OTHER_REMIN = dzr * (flux - POC_sed - (SED_DENITRIF * dz * denitrif_C_N));
         }
@@ -1164,7 +1167,7 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
     double DENITRIF;
     {
       double w = cdiv(((P.parm_o2_min + P.parm_o2_min_delta) - O2_loc), P.parm_o2_min_delta, D.r_o2_min_delta);
-      w = fmin(fmax(w, 0.0), 1.0);
+      w = gmin(gmax(w, 0.0), 1.0);
       if (NO3_loc == 0.0) w = 0.0;
       DENITRIF = w * (cdiv((DOC_remin + POC_remin - OTHER_REMIN), denitrif_C_N, 1.0 / denitrif_C_N) - SED_DENITRIF);
     }
@@ -1193,7 +1196,7 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
     double O2_CONSUMPTION;
     {
       double w = cdiv((O2_loc - P.parm_o2_min), P.parm_o2_min_delta, D.r_o2_min_delta);
-      w = fmin(fmax(w, 0.0), 1.0);
+      w = gmin(gmax(w, 0.0), 1.0);
       O2_CONSUMPTION = w * (cdiv((POC_remin + DOC_remin - (SED_DENITRIF * denitrif_C_N) - OTHER_REMIN +
                                   zoo_loss_dic + s_auto_loss_dic + s_auto_graze_dic),
                                  parm_Remin_D_C_O2, 1.0 / parm_Remin_D_C_O2) +

@@ -49,7 +49,7 @@ __device__ __forceinline__ DmsColumnConsts dms_column_consts(double SST_loc) {
 
 // Light attenuation over one cell (DMS_mod.F90:510-527): KPARdz and bexp(-KPARdz).
 __device__ __forceinline__ void dms_attenuation(double totalChl, double dz, double &KPARdz, double &eK) {
-  const double w = fmax(totalChl, 0.02);
+  const double w = gmax(totalChl, 0.02);
   double kp;
   if (w < 0.13224) kp = 0.000919 * fpow(w, 0.3536);
   else             kp = 0.001131 * fpow(w, 0.4562);
@@ -61,6 +61,19 @@ __device__ __forceinline__ void dms_attenuation(double totalChl, double dz, doub
 // copied by the reference (:471-472) but reach no output (DOC feeds only the unused UV_avg,
 // :531-536): not read here.
 struct DmsCellIn { double zooC, spC, diatC, diazC, phaeoC, spChl, spCaCO3, dms, dmsp, dz; };   // dz: inventory only
+
+// The cell after next: its nine lines are pulled into L2 (no register, no shared memory), so that the
+// register prefetch of the next trip finds them there instead of in HBM.
+__device__ __forceinline__ void pf_l2(const double *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void dms_prefetch_cell(const DmsArgs &A, unsigned i2, unsigned nLnC) {
+  const DmsIndices &I = c_dms.ind;
+  const double *trc = A.tracers;
+#define TR(ind_) pf_l2(trc + (i2 + (unsigned)((ind_) - 1) * nLnC))
+  TR(I.zooC_ind); TR(I.spC_ind); TR(I.diatC_ind); TR(I.diazC_ind); TR(I.phaeoC_ind); TR(I.spChl_ind);
+  TR(I.spCaCO3_ind); TR(I.dms_ind); TR(I.dmsp_ind);
+#undef TR
+  if (A.inv_partials) pf_l2(A.dz + i2);
+}
 
 __device__ __forceinline__ DmsCellIn dms_load_cell(const DmsArgs &A, unsigned i2, unsigned nLnC) {
   const DmsIndices &I = c_dms.ind;
@@ -81,9 +94,9 @@ template <bool ALLDIAG>
 __device__ __forceinline__ void dms_cell(const DmsArgs &A, unsigned i2, const DmsCellIn &in, double PAR_avg,
                                          const DmsColumnConsts cc, double &t_dms, double &t_dmsp) {
   const DmsParams &P = c_dms.p;
-  const double zooC = fmax(0.0, in.zooC), spC = fmax(0.0, in.spC), diatC = fmax(0.0, in.diatC),
-               diazC = fmax(0.0, in.diazC), phaeoC = fmax(0.0, in.phaeoC), spChl = fmax(0.0, in.spChl),
-               spCaCO3 = fmax(0.0, in.spCaCO3), DMS_loc = fmax(0.0, in.dms), DMSP_loc = fmax(0.0, in.dmsp);
+  const double zooC = gmax(0.0, in.zooC), spC = gmax(0.0, in.spC), diatC = gmax(0.0, in.diatC),
+               diazC = gmax(0.0, in.diazC), phaeoC = gmax(0.0, in.phaeoC), spChl = gmax(0.0, in.spChl),
+               spCaCO3 = gmax(0.0, in.spCaCO3), DMS_loc = gmax(0.0, in.dms), DMSP_loc = gmax(0.0, in.dmsp);
   const double k_S_p = P.k_S_p_base * (P.mort + cdiv(zooC, 0.3, 1.0 / 0.3));   // literal 0.3, not zooC_avg (:529)
   const double j_dms = P.j_dms_perI * PAR_avg;
 
@@ -240,7 +253,13 @@ dms_cells_kernel(const __grid_constant__ DmsArgs A) {
     if (w < kmax) cur = load_chl(w);
     for (int k = w; k < kmax; k += kDmsTileWarps) {
       if (k + kDmsTileWarps < kmax) nxt = load_chl(k + kDmsTileWarps);
-      const double totalChl = fmax(0.0, cur.a) + fmax(0.0, cur.b) + fmax(0.0, cur.c) + fmax(0.0, cur.d);
+      if (A.l2_prefetch && k + 2 * kDmsTileWarps < kmax) {
+        const unsigned j2 = (unsigned)col + (unsigned)nC * (unsigned)(k + 2 * kDmsTileWarps);
+        pf_l2(A.tracers + (j2 + (unsigned)(I.spChl_ind - 1) * nLnC)); pf_l2(A.tracers + (j2 + (unsigned)(I.diatChl_ind - 1) * nLnC));
+        pf_l2(A.tracers + (j2 + (unsigned)(I.diazChl_ind - 1) * nLnC)); pf_l2(A.tracers + (j2 + (unsigned)(I.phaeoChl_ind - 1) * nLnC));
+        pf_l2(A.dz + j2);
+      }
+      const double totalChl = gmax(0.0, cur.a) + gmax(0.0, cur.b) + gmax(0.0, cur.c) + gmax(0.0, cur.d);
       double kp, ek;
       dms_attenuation(totalChl, cur.dz, kp, ek);
       s_kp[k * 32 + lane] = kp;
@@ -250,7 +269,7 @@ dms_cells_kernel(const __grid_constant__ DmsArgs A) {
   }
   __syncthreads();
   if (w == 0 && kmax > 0) {
-    double PAR = fmax(0.0, A.sw_flux[col]);
+    double PAR = gmax(0.0, A.sw_flux[col]);
     PAR = PAR * c_dms.p.f_qsw_par_DMS;
     for (int k = 0; k < kmax; ++k) {
       s_pin[k * 32 + lane] = PAR;
@@ -268,6 +287,7 @@ dms_cells_kernel(const __grid_constant__ DmsArgs A) {
       const unsigned i2 = (unsigned)col + (unsigned)nC * (unsigned)k;
       const int kn = k + kDmsTileWarps;
       if (kn < kmax) nxt = dms_load_cell(A, i2 + (unsigned)nC * (unsigned)kDmsTileWarps, nLnC);
+      if (A.l2_prefetch && kn + kDmsTileWarps < kmax) dms_prefetch_cell(A, i2 + (unsigned)nC * (unsigned)(2 * kDmsTileWarps), nLnC);
       const bool active = k < kmax;
       double t_dms = 0.0, t_dmsp = 0.0;
       if (active) {   // diagnostics keep their previous contents outside active cells
@@ -309,7 +329,7 @@ dms_columns_kernel(const __grid_constant__ DmsArgs A) {
   double SST_loc = 0.0, PAR_out = 0.0;
   if (kmax > 0) {
     SST_loc = A.sst[col];
-    PAR_out = fmax(0.0, A.sw_flux[col]);
+    PAR_out = gmax(0.0, A.sw_flux[col]);
     PAR_out = PAR_out * c_dms.p.f_qsw_par_DMS;
   }
   const DmsColumnConsts cc = dms_column_consts(SST_loc);
@@ -319,7 +339,7 @@ dms_columns_kernel(const __grid_constant__ DmsArgs A) {
     const bool active = k < kmax;
     double t_dms = 0.0, t_dmsp = 0.0;
     if (active) {
-#define TR(ind_) fmax(0.0, A.tracers[i2 + (unsigned)((ind_) - 1) * nLnC])
+#define TR(ind_) gmax(0.0, A.tracers[i2 + (unsigned)((ind_) - 1) * nLnC])
       const double totalChl = TR(I.spChl_ind) + TR(I.diatChl_ind) + TR(I.diazChl_ind) + TR(I.phaeoChl_ind);
 #undef TR
       const double dz = A.dz[i2];
@@ -354,7 +374,7 @@ dms_surface_kernel(const __grid_constant__ DmsSurfArgs A) {
   const DmsIndices &I = c_dms.ind;
   constexpr double a = 0.31, e2 = 2.85, e3 = 0.612;   // DMS_mod.F90:831-838
 
-  const double seaSurfaceDMS = fmax(0.0, A.tracers[(size_t)col + (size_t)(I.dms_ind - 1) * nLnC]);
+  const double seaSurfaceDMS = gmax(0.0, A.tracers[(size_t)col + (size_t)(I.dms_ind - 1) * nLnC]);
   const double sst = A.f.SST[col];
   double ice = A.f.iceFraction[col];
   if (ice < 0.0) ice = 0.0;
@@ -413,7 +433,7 @@ macros_cells_kernel(const __grid_constant__ MacrosArgs A) {
 
   double t_prot = 0.0, t_poly = 0.0, t_lip = 0.0;
   if (active) {
-#define TR(ind_) fmax(0.0, A.tracers[cell + (size_t)((ind_) - 1) * ncell])
+#define TR(ind_) gmax(0.0, A.tracers[cell + (size_t)((ind_) - 1) * ncell])
     const double zooC = TR(I.zooC_ind), spC = TR(I.spC_ind), diatC = TR(I.diatC_ind), diazC = TR(I.diazC_ind),
                  phaeoC = TR(I.phaeoC_ind), prot = TR(I.prot_ind), poly = TR(I.poly_ind), lip = TR(I.lip_ind);
 #undef TR
@@ -768,8 +788,11 @@ static cudaError_t launch_dms_tiles(const DmsArgs &a, cudaStream_t s) {
   return cudaGetLastError();
 }
 
-cudaError_t launch_dms_columns(const DmsArgs &a, int variant, cudaStream_t s) {
+cudaError_t launch_dms_columns(const DmsArgs &a0, int variant, cudaStream_t s) {
+  DmsArgs a = a0;
   if (a.nC <= 0 || a.nL <= 0) return cudaSuccess;
+  a.l2_prefetch = (variant & 4) ? 0 : 1;   // (variant bit 2 switches the L2 prefetch off: tuning)
+  variant &= 3;
   if (!dms_use_tiles(a.nL)) {
     dms_columns_kernel<<<cdiv((size_t)a.nC, 256), 256, 0, s>>>(a);
     return cudaGetLastError();
