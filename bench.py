@@ -875,20 +875,8 @@ def run_e2e(args, pkg, host, ctx, parms, rank, world, local_rank, dev):
     pkg.synth_fill(bgc, dms, mac, bgc_ind=parms.ind, dms_ind=parms.dms_ind, macros_ind=parms.macros_ind,
                    column0=getattr(args, "column0", rank * args.columns))
     cells = int(bgc.active_mask().sum())
-    n2 = nL * nC * 8
-    abi = pkg.abi
-    # bytes the library moves per step (bgc_capi.cu host_pipeline): inputs no kernel reads are not
-    # uploaded (BGC DIC_ALT_CO2; DMS NO3, DOC; MACROS cell_thickness), and the DMS / MACROS
-    # diagnostics are not uploaded when every cell of a chunk is active (as here).
-    h2d = n2 * (29 + 5 + 1 + 2) + nC * (8 + 4 + 16) \
-        + n2 * (12 + 1) + nC * (4 + 16) \
-        + n2 * 8 + nC * 4 \
-        + nC * 8 * (30 + 10 + 5 * 30) + nC * 8 * (14 + 5 + 14 + 8)
-    # downloads: structurally-zero outputs (12 of the 14 DMS tendencies, 5 of the 8 MACROS tendencies, the three
-    # restoring diagnostics while restoring is off) are zero-filled by host threads instead of crossing PCIe
-    d2h = n2 * (30 + 2 + 58 - 3 + 18 * 4) + nC * 8 * (17 + 12) \
-        + n2 * (2 + len(abi.DMS_DIAG)) + n2 * (3 + len(abi.MACROS_DIAG)) \
-        + nC * 8 * (3 + 5 * 30 + 14) + nC * 8 * (1 + 14 + 8)
+    # (bytes per step are counted by the library: inputs no kernel reads are not uploaded, outputs that are
+    #  structurally zero are zero-filled by host threads instead of being downloaded - bgc_capi.cu host_pipeline)
     ctx.inventory_enable(False)   # the Fortran-facing calls do not use the inventory (default: off)
 
     calls = [("BGC_SourceSink", lambda: host.BGC_SourceSink(ctx, bgc, True, True)),
@@ -907,6 +895,7 @@ def run_e2e(args, pkg, host, ctx, parms, rank, world, local_rank, dev):
     step()
     for k in call_s:
         call_s[k] = 0.0
+    ctx.transfer_bytes(reset=True)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -915,6 +904,8 @@ def run_e2e(args, pkg, host, ctx, parms, rank, world, local_rank, dev):
         step()
     torch.cuda.synchronize()
     dt = (time.perf_counter() - t0) / args.e2e_steps
+    moved = ctx.transfer_bytes()   # counted by the library at every copy it issues (bgc_transfer_bytes)
+    h2d, d2h = moved[0] // args.e2e_steps, moved[1] // args.e2e_steps
     t = torch.tensor([dt], dtype=torch.float64, device=dev)
     c = torch.tensor([cells], dtype=torch.float64, device=dev)
     if world > 1:
@@ -928,14 +919,16 @@ def run_e2e(args, pkg, host, ctx, parms, rank, world, local_rank, dev):
         ctx.diag_accumulate(True)
         step()
         torch.cuda.synchronize()
+        ctx.transfer_bytes(reset=True)
         t0 = time.perf_counter()
         for _ in range(args.e2e_steps):
             step()
         torch.cuda.synchronize()
         dta = (time.perf_counter() - t0) / args.e2e_steps
+        acc_d2h = ctx.transfer_bytes()[1] // args.e2e_steps
         ctx.diag_accumulate(False)
         acc = {"value": cells / dta, "unit": UNIT, "ms_per_step": dta * 1e3,
-               "d2h_bytes_per_step": int(n2 * (30 + 2 + 2 + 3) + nC * 8 * (3 + 5 * 30 + 14) + nC * 8 * (1 + 14 + 8)),
+               "d2h_bytes_per_step": acc_d2h,
                "note": "bgc_diag_accumulate_enable: tendencies and PH_PREV come back every step, the 163 diagnostic "
                        "arrays are summed on the device for a later bgc_diag_flush (not the reference contract: "
                        "reported beside the headline, not instead of it)"}
@@ -945,8 +938,10 @@ def run_e2e(args, pkg, host, ctx, parms, rank, world, local_rank, dev):
             "api": "bgc_source_sink/bgc_surface_fluxes/dms_source_sink/dms_surface_fluxes/macros_source_sink "
                    "with BGC_MEM_HOST_FORTRAN, pinned host arrays, synchronous on return; each call is a "
                    "two-stream pipeline over column chunks (upload, transpose, kernels, transpose, download); outputs "
-                   "the reference assigns the constant zero (20 of ~217 (k,col) slabs) are zero-filled by host threads "
-                   "instead of being downloaded"}
+                   "the reference assigns the constant zero whatever the inputs are (41 of ~217 (k,col) slabs: DMS / MACROS "
+                   "tendencies of untouched tracers, restoring terms while restoring is off, per-group terms of groups that "
+                   "cannot have them, the nine sediment diagnostics outside the bottom cell) are zero-filled by host threads "
+                   "instead of being downloaded; the byte counts are the library's own (bgc_transfer_bytes)"}
 
 
 if __name__ == "__main__":

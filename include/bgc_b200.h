@@ -318,6 +318,10 @@ int bgc_ctx_set_concurrency(bgc_ctx *ctx, int enable);
  * level the sweep skips the body and writes the zeros directly; results are bit-identical.
  * enable = 0 executes the full body everywhere (for measuring the data-independent cost). */
 int bgc_ctx_set_zero_shortcut(bgc_ctx *ctx, int enable);
+/* Bytes the BGC_MEM_HOST_FORTRAN calls of this ctx have copied across PCIe since it was created or the counters
+ * were last reset: bytes[0] host -> device, bytes[1] device -> host.  (Outputs the reference assigns the constant
+ * zero whatever the inputs are do not cross PCIe: the library zero-fills those host ranges itself.) */
+int bgc_transfer_bytes(bgc_ctx *ctx, unsigned long long bytes[2], int reset);
 int bgc_carbonate_join(bgc_ctx *ctx);
 int bgc_get_status(bgc_ctx *ctx, BgcStatus *out, int reset);
 

@@ -137,7 +137,12 @@ struct bgc_ctx {
   std::map<std::string, DevBuf> arena;      // persistent device buffers (host-layout mode, scratch)
   std::map<std::string, HostStage> host_stage;   // page-locked staging buffers of the host-layout calls
   struct ZeroJob { char *p; size_t bytes; };
+  unsigned long long h2d_bytes = 0, d2h_bytes = 0;   // what the host-layout calls have copied (bgc_transfer_bytes)
   std::vector<ZeroJob> zero_jobs;                // host ranges a host-layout call fills with zeros itself (see down_k)
+  // bottom-cell values of the sediment diagnostics, scattered into the zero-filled host arrays once the call's
+  // transfers are complete: host(kmax(col) - 1, col) = vec[col] for col in [c0, c0 + cc)
+  struct ScatterJob { double *host; const double *vec; const int *kmax; int nL, c0, cc, nColumns; };
+  std::vector<ScatterJob> scatter_jobs;
   ncclComm_t comm = nullptr;
   int nranks = 1;
   // launch accounting (always on) and optional per-kernel CUDA-event timing
@@ -214,6 +219,18 @@ static int arena_get(bgc_ctx *c, const std::string &key, size_t bytes, void **ou
   *out = b.p;
   return BGC_OK;
 }
+static int host_stage_get(bgc_ctx *c, const std::string &key, size_t bytes, void **out) {
+  HostStage &hs = c->host_stage[key];
+  if (hs.bytes < bytes) {
+    if (hs.p) cudaFreeHost(hs.p);
+    hs.p = nullptr; hs.bytes = 0;
+    CU(cudaHostAlloc(&hs.p, bytes, cudaHostAllocDefault));
+    hs.bytes = bytes;
+  }
+  *out = hs.p;
+  return BGC_OK;
+}
+
 static int arena_d(bgc_ctx *c, const std::string &key, size_t n, double **out) {
   void *p = nullptr;
   RC(arena_get(c, key, n * sizeof(double), &p));
@@ -349,6 +366,13 @@ extern "C" int bgc_ctx_set_concurrency(bgc_ctx *c, int enable) {
   // 0 = same stream, 1 = side stream, placement chosen by the sweep's size (the default),
   // 2 = side stream after the sweep, 3 = confined to the sweep's idle SMs where it has any, else 2
   c->concurrent_co3 = enable;
+  return BGC_OK;
+}
+
+extern "C" int bgc_transfer_bytes(bgc_ctx *c, unsigned long long bytes[2], int reset) {
+  if (!c || !bytes) return fail(BGC_ERR_ARG, "bgc_transfer_bytes: null argument");
+  bytes[0] = c->h2d_bytes; bytes[1] = c->d2h_bytes;
+  if (reset) c->h2d_bytes = c->d2h_bytes = 0;
   return BGC_OK;
 }
 
@@ -625,6 +649,7 @@ static int up_k(bgc_ctx *c, HostChunk &h, const char *key, const double *host, i
     double *st = h.stage + h.up_slabs * n2c;
     CU(cudaMemcpy2DAsync(st, n2c * sizeof(double), host + (size_t)s0 * n2 + (size_t)h.c0 * h.nL, n2 * sizeof(double),
                          n2c * sizeof(double), (size_t)ns, cudaMemcpyHostToDevice, c->stream));
+    c->h2d_bytes += n2c * sizeof(double) * (size_t)ns;
     h.ups.push_back({nullptr, dev + (size_t)s0 * n2c, ns, h.up_slabs});
     h.up_slabs += ns;
     s0 += ns;
@@ -690,6 +715,7 @@ static int flush_down(bgc_ctx *c, HostChunk &h) {
   for (const auto &x : h.downs)
     CU(cudaMemcpy2DAsync(x.host + (size_t)h.c0 * h.nL, n2 * sizeof(double), h.stage + x.stage_slab * n2c,
                          n2c * sizeof(double), n2c * sizeof(double), (size_t)x.nSlabs, cudaMemcpyDeviceToHost, c->stream));
+  for (const auto &x : h.downs) c->d2h_bytes += n2c * sizeof(double) * (size_t)x.nSlabs;
   h.downs.clear();
   return BGC_OK;
 }
@@ -723,11 +749,13 @@ static int up_c(bgc_ctx *c, const HostChunk &h, const char *key, const void *hos
   if (!host) return fail(BGC_ERR_ARG, "null host array for %s", key);
   CU(cudaMemcpy2DAsync(dev, (size_t)h.cc * elem, (const char *)host + (size_t)h.c0 * elem, (size_t)h.nC * elem,
                        (size_t)h.cc * elem, (size_t)nSlabs, cudaMemcpyHostToDevice, c->stream));
+  c->h2d_bytes += (size_t)h.cc * elem * (size_t)nSlabs;
   return BGC_OK;
 }
 static int down_c(bgc_ctx *c, const HostChunk &h, const void *dev, void *host, size_t elem, int nSlabs) {
   CU(cudaMemcpy2DAsync((char *)host + (size_t)h.c0 * elem, (size_t)h.nC * elem, dev, (size_t)h.cc * elem,
                        (size_t)h.cc * elem, (size_t)nSlabs, cudaMemcpyDeviceToHost, c->stream));
+  c->d2h_bytes += (size_t)h.cc * elem * (size_t)nSlabs;
   return BGC_OK;
 }
 
@@ -774,6 +802,15 @@ static int host_pipeline(bgc_ctx *c, int nL, int nC, Body body) {
   if (rc == BGC_OK) run_zero_jobs(c); else c->zero_jobs.clear();
   // Fortran semantics: results are in host memory on return
   cudaError_t e1 = cudaStreamSynchronize(user), e2 = two ? cudaStreamSynchronize(c->pipe_stream) : cudaSuccess;
+  if (rc == BGC_OK && e1 == cudaSuccess && e2 == cudaSuccess) {
+    for (const auto &j : c->scatter_jobs)
+      for (int col = 0; col < j.cc; ++col) {
+        int km = (j.c0 + col) < j.nColumns ? j.kmax[j.c0 + col] : 0;
+        if (km > j.nL) km = j.nL;
+        if (km > 0) j.host[(size_t)(j.c0 + col) * j.nL + (km - 1)] = j.vec[col];
+      }
+  }
+  c->scatter_jobs.clear();
   if (rc != BGC_OK) return rc;
   if (e1 != cudaSuccess) return fail(BGC_ERR_CUDA, "%s", cudaGetErrorString(e1));
   if (e2 != cudaSuccess) return fail(BGC_ERR_CUDA, "%s", cudaGetErrorString(e2));
@@ -910,6 +947,7 @@ static int source_sink_device(bgc_ctx *c, const BgcInput *in, const BgcForcing *
   bgc::EcoArgs ea;
   ea.nL = nL; ea.nC = nC; ea.nColumns = nCols; ea.alt_co2_use_eco = alt_co2_use_eco;
   ea.zero_shortcut = c->zero_shortcut;
+  ea.any_restore = (P.lrest_no3 || P.lrest_po4 || P.lrest_sio3) ? 1 : 0;
   ea.tracers = in->BGC_tracers; ea.T = in->PotentialTemperature; ea.S = in->Salinity;
   ea.zmid = in->cell_center_depth; ea.dz = in->cell_thickness; ea.zbot = in->cell_bottom_depth;
   ea.lat = in->cell_latitude; ea.kmax = in->number_of_active_levels;
@@ -1108,8 +1146,49 @@ extern "C" int bgc_source_sink(bgc_ctx *c, const BgcInput *in, const BgcForcing 
       // and the like assign RESTORE = c0 then)
       const double *const off_no3 = P.lrest_no3 ? nullptr : dd.diag_NO3_RESTORE, *const off_po4 = P.lrest_po4 ? nullptr : dd.diag_PO4_RESTORE,
                    *const off_sio3 = P.lrest_sio3 ? nullptr : dd.diag_SiO3_RESTORE;
-#define DN_K2(name) if (dd.name) RC(down_k(c, h, dd.name, diag->name, 1, (dd.name == off_no3 || dd.name == off_po4 || dd.name == off_sio3) ? 1ull : 0ull));
-#define DN_KA(name) if (dd.name) RC(down_k(c, h, dd.name, diag->name, BGC_AUTOTROPH_CNT));
+      // structurally zero for a functional group, whatever the inputs are: N fixation of a group that
+      // is no N fixer (:1331-1338), bSi formation / the SiO3 limitation term of a group without Si quota or
+      // kSiO3 (:1140-1150, :1230), CaCO3 formation of a group that is no implicit calcifier (:1255-1278)
+      unsigned long long z_nfix = 0, z_bsi = 0, z_caco3 = 0, z_sio3lim = 0;
+      for (int g = 0; g < BGC_AUTOTROPH_CNT; ++g) {
+        const BgcAutotroph &at = c->bgc_tab.a[g];
+        if (!at.Nfixer) z_nfix |= 1ull << g;
+        if (at.Si_ind <= 0) z_bsi |= 1ull << g;
+        if (!at.imp_calcifier) z_caco3 |= 1ull << g;
+        if (!(at.kSiO3 > 0.0)) z_sio3lim |= 1ull << g;
+      }
+      auto ka_zero = [&](const double *p) -> unsigned long long {
+        return p == dd.diag_Nfix ? z_nfix : p == dd.diag_bSi_form ? z_bsi : p == dd.diag_CaCO3_form ? z_caco3 :
+               p == dd.diag_SiO3_lim ? z_sio3lim : 0ull;
+      };
+      // The nine sediment diagnostics are set in a column's BOTTOM cell alone (:2522-2631; zero fill elsewhere,
+      // :625-727): the bottom values come down as one vector per array, the host range is zero-filled by the
+      // host threads and the values are put in place when the call's transfers are complete.
+      double *const sed[9] = {dd.diag_calcToSed, dd.diag_pocToSed, dd.diag_ponToSed, dd.diag_popToSed, dd.diag_bsiToSed,
+                              dd.diag_dustToSed, dd.diag_pfeToSed, dd.diag_SedDenitrif, dd.diag_OtherRemin};
+      double *const sed_host[9] = {diag->diag_calcToSed, diag->diag_pocToSed, diag->diag_ponToSed, diag->diag_popToSed,
+                                   diag->diag_bsiToSed, diag->diag_dustToSed, diag->diag_pfeToSed, diag->diag_SedDenitrif,
+                                   diag->diag_OtherRemin};
+      bgc::BottomGatherArgs ga;
+      memset(&ga, 0, sizeof ga);
+      int sed_of[9];
+      for (int j = 0; j < 9; ++j) if (sed[j]) { ga.src[ga.n] = sed[j]; sed_of[ga.n++] = j; }
+      if (ga.n) {
+        void *hv = nullptr;
+        RC(host_stage_get(c, "bgc.bottom", (size_t)9 * h.nC * sizeof(double), &hv));
+        RC(arena_d(c, slot_key(h, "bgc.bottom"), (size_t)ga.n * h.cc, &ga.out));
+        ga.kmax = din.number_of_active_levels; ga.nL = h.nL; ga.cc = h.cc; ga.nColumns = cols;
+        LAUNCH(BGC_K_TRANSPOSE, 1, bgc::launch_bottom_gather(ga, c->stream));
+        for (int q = 0; q < ga.n; ++q) {
+          double *vec = (double *)hv + (size_t)sed_of[q] * h.nC + h.c0;
+          CU(cudaMemcpyAsync(vec, ga.out + (size_t)q * h.cc, (size_t)h.cc * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+          c->d2h_bytes += (size_t)h.cc * sizeof(double);
+          c->scatter_jobs.push_back({sed_host[sed_of[q]], vec, in->number_of_active_levels, h.nL, h.c0, h.cc, nCols});
+        }
+      }
+      auto is_sed = [&](const double *p) { for (int j = 0; j < 9; ++j) if (p == sed[j]) return true; return false; };
+#define DN_K2(name) if (dd.name) RC(down_k(c, h, dd.name, diag->name, 1, (dd.name == off_no3 || dd.name == off_po4 || dd.name == off_sio3 || is_sed(dd.name)) ? 1ull : 0ull));
+#define DN_KA(name) if (dd.name) RC(down_k(c, h, dd.name, diag->name, BGC_AUTOTROPH_CNT, ka_zero(dd.name)));
 #define DN_CA(name) if (dd.name) RC(down_c(c, h, dd.name, diag->name, sizeof(double), BGC_AUTOTROPH_CNT));
 #define DN_C1(name) if (dd.name) RC(down_c(c, h, dd.name, diag->name, sizeof(double), 1));
       BGC_DIAG_K2_LIST(DN_K2) BGC_DIAG_KA_LIST(DN_KA) BGC_DIAG_CA_LIST(DN_CA) BGC_DIAG_C1_LIST(DN_C1)
@@ -1154,6 +1233,7 @@ static int gather_level1(bgc_ctx *c, const char *key, const double *host, int nL
     for (auto &th : pool) th.join();
   }
   CU(cudaMemcpyAsync(dev, st, count * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  c->h2d_bytes += count * sizeof(double);
   return BGC_OK;
 }
 

@@ -88,6 +88,7 @@ cudaError_t launch_zsat_columns(const ZsatArgs &a, cudaStream_t s);
 // ---- ecosystem + particulate column sweep, one thread per COLUMN
 struct EcoArgs {
   int nL, nC, nColumns, alt_co2_use_eco;
+  int any_restore = 0;                   // lrest_no3 | lrest_po4 | lrest_sio3 (set by the caller from the ctx tables)
   int zero_shortcut;                     // skip the body of a functional group whose biomass is zero in a whole warp
   const double *tracers;                 // (k,col,30)
   const double *T, *S, *zmid, *dz, *zbot;
@@ -208,6 +209,9 @@ cudaError_t launch_soa_to_mpas(const double *soa, double *mpas, const MpasMap &m
 cudaError_t launch_accumulate(const double *src, double *acc, int nL, int cc, int nC, int c0, int nSlabs,
                               const int *kmax, int nColumns, double w, cudaStream_t s);
 cudaError_t launch_scale(double *a, size_t n, double w, cudaStream_t s);
+// the bottom cell of every column of up to 16 (k,col) arrays -> out[j][col] (k_misc.cu)
+struct BottomGatherArgs { const double *src[16]; double *out; const int *kmax; int nL, cc, nColumns, n; };
+cudaError_t launch_bottom_gather(const BottomGatherArgs &a, cudaStream_t s);
 
 // ---- inventory: sum_col sum_k tend(n)*dz over active cells (+ sums of per-column
 // diagnostics).  Stage 1 is fused into the source-sink kernels (block partials); stage 2:

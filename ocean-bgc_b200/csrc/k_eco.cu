@@ -1158,9 +1158,11 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
 
     // ---- nitrification / denitrification (:1545-1577)
     double RESTORE_NO3 = 0.0, RESTORE_SiO3 = 0.0, RESTORE_PO4 = 0.0;
-    if (P.lrest_no3) RESTORE_NO3 = A.rtau[i2] * (A.no3_clim[i2] - NO3_loc);
-    if (P.lrest_sio3) RESTORE_SiO3 = A.rtau[i2] * (A.sio3_clim[i2] - SiO3_loc);
-    if (P.lrest_po4) RESTORE_PO4 = A.rtau[i2] * (A.po4_clim[i2] - PO4_loc);
+    if (A.any_restore) {   // (one flag test per cell while restoring is off: the reference never switches it on, Q8)
+      if (P.lrest_no3) RESTORE_NO3 = A.rtau[i2] * (A.no3_clim[i2] - NO3_loc);
+      if (P.lrest_sio3) RESTORE_SiO3 = A.rtau[i2] * (A.sio3_clim[i2] - SiO3_loc);
+      if (P.lrest_po4) RESTORE_PO4 = A.rtau[i2] * (A.po4_clim[i2] - PO4_loc);
+    }
 
     const double NITRIF = (P.parm_kappa_nitrif * NH4_loc) * nitrif_light;
 

@@ -738,6 +738,21 @@ scale_kernel(double *a, size_t n, double w) {
   if (i < n) a[i] *= w;
 }
 
+// ---------------------------------------------------------------- bottom-cell gather
+// out[j][col] = src[j](kmax(col) - 1, col): the only element of a column that the nine sediment
+// diagnostics of BGC_SourceSink can set (BGC_mod.F90:2522-2631 run in the bottom cell alone; every
+// other element is the zero fill of :625-727).  Host-layout calls download these vectors instead of
+// the (k,col) slabs (bgc_capi.cu).
+__global__ void __launch_bounds__(256)
+bottom_gather_kernel(BottomGatherArgs a) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= a.cc) return;
+  int km = col < a.nColumns ? a.kmax[col] : 0;
+  if (km > a.nL) km = a.nL;
+  for (int j = 0; j < a.n; ++j)
+    a.out[(size_t)j * a.cc + col] = km > 0 ? a.src[j][(size_t)(km - 1) * a.cc + col] : 0.0;
+}
+
 // ---------------------------------------------------------------- inventory
 // Stage 1 of the inventory reduction is fused into the source-sink kernels: every block
 // writes its partial sums, [nParts][nGroups][kInvGroup].  Stage 2 below adds the partials
@@ -947,6 +962,11 @@ cudaError_t launch_accumulate(const double *src, double *acc, int nL, int cc, in
   dim3 grid(cdiv((size_t)cc, 256), (unsigned)nL, (unsigned)nSlabs);
   if (grid.y > 65535u || grid.z > 65535u) return cudaErrorInvalidConfiguration;
   accumulate_kernel<<<grid, 256, 0, s>>>(src, acc, nL, cc, nC, c0, kmax, nColumns, w);
+  return cudaGetLastError();
+}
+cudaError_t launch_bottom_gather(const BottomGatherArgs &a, cudaStream_t s) {
+  if (a.cc <= 0 || a.n <= 0) return cudaSuccess;
+  bottom_gather_kernel<<<cdiv((size_t)a.cc, 256), 256, 0, s>>>(a);
   return cudaGetLastError();
 }
 cudaError_t launch_scale(double *a, size_t n, double w, cudaStream_t s) {

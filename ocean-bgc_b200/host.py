@@ -41,6 +41,7 @@ ABI_SYMBOLS = [
     "bgc_graph_capture_begin", "bgc_graph_capture_end", "bgc_graph_launch", "bgc_graph_destroy",
     "bgc_ctx_set_zero_shortcut", "bgc_comp_co3terms", "bgc_comp_co3_sat_vals",
     "bgc_layout_soa_to_mpas_weighted", "bgc_state_device_ptr", "bgc_state_set", "bgc_state_get",
+    "bgc_transfer_bytes",
 ]
 
 
@@ -189,6 +190,12 @@ class Context:
 
     def set_zero_shortcut(self, on=True):
         check(self.L, self.L.bgc_ctx_set_zero_shortcut(self.ptr, C.c_int(int(on))))
+
+    def transfer_bytes(self, reset=False):
+        """(host -> device, device -> host) bytes the host-layout calls of this ctx have copied"""
+        b = (C.c_ulonglong * 2)()
+        check(self.L, self.L.bgc_transfer_bytes(self.ptr, b, C.c_int(int(reset))))
+        return int(b[0]), int(b[1])
 
     def carbonate_join(self):
         check(self.L, self.L.bgc_carbonate_join(self.ptr))

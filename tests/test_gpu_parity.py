@@ -477,6 +477,18 @@ def test_deferred_carbonate_join_gives_the_same_bits():
     for k in outs[0]:
         assert torch.equal(outs[0][k], outs[1][k]), k
     assert outs[0]["zsat"].abs().max().item() > 0
+    # With the deferred join the carbonate cells travel inside the next DMS kernel (k_misc.cu, FUSE).  When no
+    # dms_source_sink follows, the next join point computes them: same bits again.
+    ctx.set_deferred_join(True)
+    d = host.DeviceBgcColumns(nL, nC).load(cols)
+    for _ in range(2):
+        host.BGC_SourceSink(ctx, d)              # (the second call is itself a join point of the first)
+        host.BGC_SurfaceFluxes(ctx, d)
+    ctx.carbonate_join()
+    ctx.synchronize()
+    for k, v in (("tend", d.BGC_tendencies), ("ph", d.PH_PREV_3D), ("ph_alt", d.PH_PREV_ALT_CO2_3D),
+                 ("co3", d.diag["diag_CO3"]), ("zsat", d.diag["diag_zsatcalc"]), ("zsata", d.diag["diag_zsatarag"])):
+        assert torch.equal(outs[0][k], v), k
     ctx.close()
 
 
