@@ -1288,14 +1288,15 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
     }   // active cell
     if (inv && k < kmax_blk) {   // block-uniform condition
       // Transpose through shared memory: lane l adds row l (= tracer slot l) over the warp's 32
-      // columns, starting at column l (skewed: conflict-free); fixed order, no atomics.
+      // columns in the order c ^ l (skewed: conflict-free, and one XOR per address since the warp's
+      // columns start on a 256-byte boundary of the row); fixed order, no atomics.
       __syncwarp();
       const int lane = tid & 31;
       if (lane < BGC_TRACER_CNT) {
         const double *src = st + lane * BLOCK + (tid & ~31);
         double d = 0.0;
 #pragma unroll
-        for (int c = 0; c < 32; ++c) d += src[(c + lane) & 31];
+        for (int c = 0; c < 32; ++c) d += src[c ^ lane];
         inv_acc += d;
       }
     }
