@@ -15,12 +15,12 @@ BGC_BENCH_WRITE_INVENTORY=${WRITE_INV:-} python bench.py > gpurun_out/bench_$TAG
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref_$TAG.json 2> gpurun_out/bench_ref_$TAG.err; echo "ref exit $?"
 CMD="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --no-secondary"
 $CMD > gpurun_out/plain.log 2>&1 || { echo "plain run failed"; tail -20 gpurun_out/plain.log; exit 1; }
-ncu --metrics gpu__time_duration.sum --clock-control none -s ${SKIP:-48} -c ${COUNT:-24} --csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -k "regex:eco_columns|co3_cells|dms_cells|dms_columns|dms_surface|macros_cells|surface_fluxes|zsat_columns|inventory_" -s ${SKIP:-40} -c ${COUNT:-24} --csv \
     --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_launches.log 2>&1
 echo "ncu launches exit $?"
 if [ "${SKIP_FULL:-0}" != "1" ]; then
   ncu --set full --clock-control none --import-source on \
-      -k "regex:${KERNELS:-eco_columns|co3_cells|dms_columns|macros_cells}" -s ${FSKIP:-16} -c ${FCOUNT:-4} -f \
+      -k "regex:${KERNELS:-eco_columns|co3_cells|dms_cells|macros_cells|zsat_columns|surface_fluxes}" -s ${FSKIP:-16} -c ${FCOUNT:-4} -f \
       -o gpurun_out/ncu_full_$TAG $CMD > gpurun_out/ncu_full.log 2>&1
   echo "ncu full exit $?"; grep -c "==PROF== Profiling" gpurun_out/ncu_full.log
 fi
