@@ -253,8 +253,8 @@ dms_cells_kernel(const __grid_constant__ DmsArgs A) {
     if (w < kmax) cur = load_chl(w);
     for (int k = w; k < kmax; k += kDmsTileWarps) {
       if (k + kDmsTileWarps < kmax) nxt = load_chl(k + kDmsTileWarps);
-      if (A.l2_prefetch && k + 2 * kDmsTileWarps < kmax) {
-        const unsigned j2 = (unsigned)col + (unsigned)nC * (unsigned)(k + 2 * kDmsTileWarps);
+      if (A.l2_prefetch && k + A.l2_prefetch * kDmsTileWarps < kmax) {
+        const unsigned j2 = (unsigned)col + (unsigned)nC * (unsigned)(k + A.l2_prefetch * kDmsTileWarps);
         pf_l2(A.tracers + (j2 + (unsigned)(I.spChl_ind - 1) * nLnC)); pf_l2(A.tracers + (j2 + (unsigned)(I.diatChl_ind - 1) * nLnC));
         pf_l2(A.tracers + (j2 + (unsigned)(I.diazChl_ind - 1) * nLnC)); pf_l2(A.tracers + (j2 + (unsigned)(I.phaeoChl_ind - 1) * nLnC));
         pf_l2(A.dz + j2);
@@ -287,7 +287,8 @@ dms_cells_kernel(const __grid_constant__ DmsArgs A) {
       const unsigned i2 = (unsigned)col + (unsigned)nC * (unsigned)k;
       const int kn = k + kDmsTileWarps;
       if (kn < kmax) nxt = dms_load_cell(A, i2 + (unsigned)nC * (unsigned)kDmsTileWarps, nLnC);
-      if (A.l2_prefetch && kn + kDmsTileWarps < kmax) dms_prefetch_cell(A, i2 + (unsigned)nC * (unsigned)(2 * kDmsTileWarps), nLnC);
+      if (A.l2_prefetch && k + A.l2_prefetch * kDmsTileWarps < kmax)
+        dms_prefetch_cell(A, i2 + (unsigned)nC * (unsigned)(A.l2_prefetch * kDmsTileWarps), nLnC);
       const bool active = k < kmax;
       double t_dms = 0.0, t_dmsp = 0.0;
       if (active) {   // diagnostics keep their previous contents outside active cells
@@ -806,7 +807,8 @@ static cudaError_t launch_dms_tiles(const DmsArgs &a, cudaStream_t s) {
 cudaError_t launch_dms_columns(const DmsArgs &a0, int variant, cudaStream_t s) {
   DmsArgs a = a0;
   if (a.nC <= 0 || a.nL <= 0) return cudaSuccess;
-  a.l2_prefetch = (variant & 4) ? 0 : 1;   // (variant bit 2 switches the L2 prefetch off: tuning)
+  // distance of the L2 prefetch in trips (2 = the cell after next); variant bits 2.. override it (tuning): 4 = off
+  a.l2_prefetch = (variant & 4) ? 0 : ((variant >> 3) ? (variant >> 3) : 2);
   variant &= 3;
   if (!dms_use_tiles(a.nL)) {
     dms_columns_kernel<<<cdiv((size_t)a.nC, 256), 256, 0, s>>>(a);
