@@ -32,11 +32,15 @@
 // BLOCK consecutive columns = one contiguous BLOCK*8-byte run each - with
 // cp.async.bulk (the TMA unit's 1-D bulk copy) into a double-buffered shared-memory
 // stage, completion signalled on an mbarrier; the compute threads only ever read
-// shared memory.  When the slabs are not 16-byte aligned (odd nColumnsMax or a
-// misaligned caller pointer) the same stage is filled by 8-byte cp.async copies
-// (LDGSTS), one column per thread, two levels ahead as well: the staging differs,
-// the arithmetic is the SAME instantiation, so results do not depend on the width
-// of the block a host happens to pick.
+// shared memory.  With an odd nColumnsMax every other level of a block starts 8 bytes
+// off a 16-byte boundary: the bulk copy then fetches the ALIGNED SUPERSET of the run
+// (one element earlier, rounded up to 16 bytes; the stage rows are two doubles wider
+// for it) and the level's stage pointer is shifted by that one element, so the odd
+// width costs nothing.  Only when a caller's base pointer itself is not 16-byte aligned
+// (or nColumnsMax and the level count are both odd: the tracer slabs then alternate
+// between the two alignments) is the stage filled by 8-byte cp.async copies (LDGSTS),
+// one column per thread, two levels ahead as well.  The staging differs, the arithmetic is the SAME instantiation,
+// so results do not depend on the width of the block a host happens to pick.
 //
 // The carbonate solve of each cell has no vertical coupling and runs in the
 // cell-parallel kernel of k_co3.cu, and the saturation-depth scan (:1003-1032) that
@@ -278,10 +282,13 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
   // The largest index, 30 * nL * nC, stays below 2^32 for any block that fits one GPU's memory
   // (180 GB / 2200 B per cell = 82 M cells); bgc_capi.cu rejects larger blocks.
   const unsigned nLnC = (unsigned)nL * (unsigned)nC;
-  double *const xs = smem + 2 * R_ROWS * BLOCK;                       // per-thread scratch rows
+  // stage rows are PITCH doubles apart: BLOCK columns + the element in front of a run that starts 8 bytes off
+  // a 16-byte boundary (odd nC) + the one that rounds the copy up to 16 bytes
+  constexpr int PITCH = BLOCK + 2;
+  double *const xs = smem + 2 * R_ROWS * PITCH;                       // per-thread scratch rows
   unsigned long long *const bars = (unsigned long long *)(xs + X_ROWS * BLOCK);
 #define XS(row) xs[(row) * BLOCK + tid]
-#define IN(row) st[(row) * BLOCK + tid]
+#define IN(row) st[(row) * PITCH + tid]
 
   // The column's depth is compared once or twice per level and would otherwise be spilled to
   // local memory (every register is taken): it lives in a shared-memory row of its own.
@@ -346,7 +353,8 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
   if (bulk && tid == 0) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
   const int kmax_blk = s_kmax_blk;
-  const unsigned slab_bytes = (unsigned)(min(BLOCK, nC - col0) * (int)sizeof(double));
+  const int cols_blk = min(BLOCK, nC - col0);                  // columns of this block
+  const bool last_blk = col0 + BLOCK >= nC;
 
   // Source of every stage row (level 0, this block's first column): the tracer rows go through the
   // row -> slot table, the rest are the caller's separate arrays.
@@ -374,23 +382,42 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
   constexpr int N_FETCH_ROWS = DIAG ? R_ROWS : R_S;
   auto row_is_fetched = [](int r) { return r != dic_row && r != dic_alt_co2_row && r != alk_row; };
   auto fetch_level = [&](int kk) {
-    double *dst = smem + (size_t)(kk & 1) * R_ROWS * BLOCK;
+    double *dst = smem + (size_t)(kk & 1) * R_ROWS * PITCH;
     const size_t off = (size_t)nC * (size_t)kk;
     if (bulk) {
+      // The run [off + col0, + cols_blk) of every row starts on a 16-byte boundary or 8 bytes behind one
+      // (the row bases are 16-byte aligned, col0 is even): fetch from the boundary, a multiple of 16 bytes.
+      // Rounding UP reads one element past the run - the next block's first column, or the next level's
+      // first element - which exists except behind the last level of the last block: there the copy is
+      // rounded DOWN and the thread of the last column fetches its own element.
+      const unsigned mis = (unsigned)((off + (size_t)col0) & 1);
+      const unsigned need = (unsigned)cols_blk + mis;
+      unsigned n = (need + 1u) & ~1u;
+      const bool tail = (n != need) && last_blk && kk == nL - 1;
+      if (tail) {
+        n = need - 1u;
+        if (tid == cols_blk - 1) {
+#pragma unroll 1
+          for (int r = 0; r < N_FETCH_ROWS; ++r)
+            if (row_is_fetched(r)) dst[r * PITCH + mis + tid] = s_rowsrc[r][off + tid];
+        }
+      }
       if (tid & 31) return;
       const unsigned bar = smem_u32(&bars[kk & 1]);
-      if (tid == 0) mbar_expect_tx(bar, slab_bytes * (unsigned)(N_FETCH_ROWS - 3));
+      const unsigned bytes = n * (unsigned)sizeof(double);
+      if (tid == 0) mbar_expect_tx(bar, bytes * (unsigned)(N_FETCH_ROWS - 3));
+      if (bytes == 0) return;
 #pragma unroll
       for (int j = 0; j < (N_FETCH_ROWS + NW - 1) / NW; ++j) {
         const int r = (tid >> 5) + j * NW;
         if (r < N_FETCH_ROWS && row_is_fetched(r))
-          bulk_g2s(smem_u32(dst + r * BLOCK), s_rowsrc[r] + off, slab_bytes, bar);
+          bulk_g2s(smem_u32(dst + r * PITCH), s_rowsrc[r] + off - mis, bytes, bar);
       }
     } else {
       if (in_range) {
 #pragma unroll 1
         for (int r = 0; r < N_FETCH_ROWS; ++r)
-          if (row_is_fetched(r)) cp_async8(smem_u32(dst + r * BLOCK + tid), s_rowsrc[r] + off + tid);
+          if (row_is_fetched(r)) cp_async8(smem_u32(dst + r * PITCH + tid), s_rowsrc[r] + off + tid);
       }
       cp_async_commit();
     }
@@ -404,7 +431,8 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
 
   for (int k = 0; k < nL; ++k) {
     const unsigned i2 = (unsigned)col + (unsigned)nC * (unsigned)k;
-    double *const st = smem + (size_t)(k & 1) * R_ROWS * BLOCK;
+    // (bulk staging: the level's run sits one element into its stage rows when it starts 8 bytes off a boundary)
+    double *const st = smem + (size_t)(k & 1) * R_ROWS * PITCH + (bulk ? (((unsigned)nC * (unsigned)k + (unsigned)col0) & 1u) : 0u);
 
     if (bulk) {
       if (k < kmax_blk) mbar_wait(smem_u32(&bars[k & 1]), (unsigned)((k >> 1) & 1));
@@ -1293,7 +1321,7 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
       __syncwarp();
       const int lane = tid & 31;
       if (lane < BGC_TRACER_CNT) {
-        const double *src = st + lane * BLOCK + (tid & ~31);
+        const double *src = st + lane * PITCH + (tid & ~31);
         double d = 0.0;
 #pragma unroll
         for (int c = 0; c < 32; ++c) d += src[c ^ lane];
@@ -1367,7 +1395,7 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
 
 template <int DIAG, int BLOCK, int MINB>
 cudaError_t launch_variant(const EcoArgs &a, cudaStream_t s) {
-  const size_t smem = (size_t)(2 * R_ROWS + X_ROWS) * BLOCK * sizeof(double) + 2 * sizeof(unsigned long long);
+  const size_t smem = ((size_t)2 * R_ROWS * (BLOCK + 2) + (size_t)X_ROWS * BLOCK) * sizeof(double) + 2 * sizeof(unsigned long long);
   auto kern = eco_columns_kernel<DIAG, BLOCK, MINB>;
   // > 48 KB of dynamic shared memory is opt-in, per device: cheap enough to set on every launch
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1377,11 +1405,14 @@ cudaError_t launch_variant(const EcoArgs &a, cudaStream_t s) {
   return cudaGetLastError();
 }
 
-// cp.async.bulk needs 16-byte aligned global addresses and sizes: every slab starts at
-// base + 8*(k*nC + BLOCK*j), so nC must be even and every base pointer 16-byte aligned.
+// cp.async.bulk needs 16-byte aligned global addresses and sizes: every run starts at
+// base + 8*(k*nC + BLOCK*j).  With every base pointer 16-byte aligned a run starts on a boundary
+// or 8 bytes behind one, and the kernel fetches the aligned superset (fetch_level).
 // Otherwise the stage is filled with 8-byte cp.async copies (same kernel, same arithmetic).
+// (With nC AND nL odd the 30 tracer slabs, nL*nC elements apart, alternate between the two alignments, so the
+// rows of one level would need different shifts: that case takes the cp.async staging as well.)
 bool slabs_are_bulk_copyable(const EcoArgs &a, bool diag) {
-  if (a.nC & 1) return false;
+  if ((a.nC & 1) && (a.nL & 1)) return false;
   const void *p[] = {a.tracers, a.T, a.zmid, a.dz, a.zbot, a.fesedflux, diag ? a.S : a.T};
   for (const void *q : p) if (((size_t)q) & 15u) return false;
   return true;

@@ -36,7 +36,8 @@ def _ctx(nL, nC, flavour=None, parms=None):
 @pytest.mark.parametrize("nL,nC,nCols,ragged", [
     (60, 256, 256, False),    # two full blocks, bulk-copy path
     (60, 258, 250, True),     # partial last block, numColumns < numColumnsMax, land columns
-    (33, 257, 257, True),     # odd numColumnsMax -> cp.async staging instead of TMA bulk copies
+    (33, 257, 257, True),     # odd numColumnsMax and level count -> cp.async staging instead of TMA bulk copies
+    (60, 257, 255, True),     # odd numColumnsMax, even level count -> bulk copies of the aligned superset of a run
     (80, 130, 130, True),     # RRS18to6 level count
     (2, 64, 64, False),       # kmax forced to 1 below: level 1 is surface AND bottom
 ])
@@ -857,13 +858,15 @@ def test_error_codes():
 
 
 # ------------------------------------------------------------------ round 2
-@pytest.mark.parametrize("nC_a,nC_b", [(257, 258), (301, 512), (1, 2)])
-def test_block_width_does_not_change_the_bits(nC_a, nC_b):
-    """The same columns computed in blocks of different numColumnsMax - odd (8-byte cp.async staging)
-    and even (TMA bulk copies), one block and several - give identical bits in every output: there
-    is ONE instantiation of the sweep's arithmetic (k_eco.cu)."""
+@pytest.mark.parametrize("nL", [37, 36])
+@pytest.mark.parametrize("nC_a,nC_b", [(257, 258), (301, 512), (1, 2), (511, 513)])
+def test_block_width_does_not_change_the_bits(nC_a, nC_b, nL):
+    """The same columns computed in blocks of different numColumnsMax - even (TMA bulk copies of the runs), odd
+    with an even level count (bulk copies of the aligned superset of every other level's run, the last block's
+    last level rounded down with its last column fetched by its own thread), odd with an odd level count (8-byte
+    cp.async staging), one block and several - give identical bits in every output: there is ONE instantiation
+    of the sweep's arithmetic (k_eco.cu)."""
     import torch
-    nL = 37
     parms = host.Parms()
     n = min(nC_a, nC_b)
     base, _, _ = parity.make_bgc(nL, n, parms, ragged=True)
