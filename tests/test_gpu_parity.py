@@ -181,6 +181,7 @@ def _retune(parms):
     sp.kSiO3 = 0.4                                         # a silicate-limited group that carries no Si tracer
     diaz.graze_zoo, diaz.graze_poc, diaz.graze_doc = 0.25, 0.08, 0.10
     phaeo.grazee_ind = sp.grazee_ind                       # two groups share a grazer
+    phaeo.Nfixer = 1                                       # a second N fixer: diag_Nfix of this group is no structural zero any more
     diat.agg_rate_max, diat.agg_rate_min, diat.mort2 = 0.7, 0.03, 0.012
     for g in (sp, diat, diaz, phaeo):
         g.PCref *= 1.1
