@@ -1274,15 +1274,20 @@ extern "C" int bgc_surface_fluxes(bgc_ctx *c, const BgcInput *in, BgcForcing *fo
   double *surf = nullptr;
   RC(arena_d(c, "surf.tracers", (size_t)nC * BGC_TRACER_CNT, &surf));
   if (!in->BGC_tracers) return fail(BGC_ERR_ARG, "bgc_surface_fluxes: BGC_tracers is NULL");
-  RC(gather_level1(c, "surf.tracers", in->BGC_tracers, nL, (size_t)nC * BGC_TRACER_CNT, surf));
   din.BGC_tracers = surf;
   void *v = nullptr;
+  // (the forcing uploads are queued first: they fly while the host threads gather level 1 of the tracers)
 #define UPC(member, n) do { if (fo->member) { RC(up_c(c, h, "surf." #member, fo->member, sizeof(double), (n), &v)); dfo.member = (double *)v; } } while (0)
   UPC(surfacePressure, 1); UPC(iceFraction, 1); UPC(windSpeedSquared10m, 1); UPC(atmCO2, 1); UPC(atmCO2_ALT_CO2, 1);
   UPC(surface_pH, 1); UPC(surface_pH_alt_co2, 1); UPC(surfaceDepth, 1); UPC(SST, 1); UPC(SSS, 1);
   UPC(depositionFlux, BGC_TRACER_CNT); UPC(riverFlux, BGC_TRACER_CNT); UPC(gasFlux, BGC_TRACER_CNT);
-  UPC(seaIceFlux, BGC_TRACER_CNT); UPC(netFlux, BGC_TRACER_CNT);
+  UPC(seaIceFlux, BGC_TRACER_CNT);
+  // netFlux is written for every column below numColumns (BGC_mod.F90:2929-2942): the caller's values are needed
+  // only where a block has columns beyond numColumns
+  if (nCols < nC) { UPC(netFlux, BGC_TRACER_CNT); }
+  else if (fo->netFlux) { double *nf = nullptr; RC(arena_d(c, "surf.netFlux#0", (size_t)nC * BGC_TRACER_CNT, &nf)); dfo.netFlux = nf; }
 #undef UPC
+  RC(gather_level1(c, "surf.tracers", in->BGC_tracers, nL, (size_t)nC * BGC_TRACER_CNT, surf));
   if (diag) {
 #define DEV_F(name) if (diag->name) RC(arena_d(c, "surf.d." #name, (size_t)nC, &dd.name));
     BGC_FLUX_DIAG_LIST(DEV_F)
@@ -1292,9 +1297,21 @@ extern "C" int bgc_surface_fluxes(bgc_ctx *c, const BgcInput *in, BgcForcing *fo
   RC(surface_fluxes_device(c, &din, &dfo, diag ? &dd : nullptr, 1, nC, nCols));
 #define DNC(member, n) do { if (fo->member) RC(down_c(c, h, dfo.member, fo->member, sizeof(double), (n))); } while (0)
   DNC(iceFraction, 1); DNC(surface_pH, 1); DNC(surface_pH_alt_co2, 1);
-  DNC(depositionFlux, BGC_TRACER_CNT); DNC(riverFlux, BGC_TRACER_CNT); DNC(gasFlux, BGC_TRACER_CNT);
-  DNC(seaIceFlux, BGC_TRACER_CNT); DNC(netFlux, BGC_TRACER_CNT);
+  DNC(netFlux, BGC_TRACER_CNT);
 #undef DNC
+  {   // of the four input fluxes the routine touches the iron slot (bioavailable fraction, :2828-2838) and the gas
+      // fluxes it computes (O2, DIC, DIC_ALT_CO2, :2860-2925): only those (col) vectors come back
+    const BgcIndices &I = c->bgc_tab.ind;
+    auto slot_down = [&](double *dev, double *hostp, int ind) -> int {
+      if (!dev || !hostp) return BGC_OK;
+      return down_c(c, h, dev + (size_t)(ind - 1) * nC, hostp + (size_t)(ind - 1) * nC, sizeof(double), 1);
+    };
+    RC(slot_down(dfo.depositionFlux, fo->depositionFlux, I.fe_ind));
+    RC(slot_down(dfo.riverFlux, fo->riverFlux, I.fe_ind));
+    RC(slot_down(dfo.seaIceFlux, fo->seaIceFlux, I.fe_ind));
+    const int gas[4] = {I.fe_ind, I.o2_ind, I.dic_ind, I.dic_alt_co2_ind};
+    for (int q = 0; q < 4; ++q) RC(slot_down(dfo.gasFlux, fo->gasFlux, gas[q]));
+  }
   if (diag) {
 #define DN_F(name) if (dd.name) RC(down_c(c, h, dd.name, diag->name, sizeof(double), 1));
     BGC_FLUX_DIAG_LIST(DN_F)
