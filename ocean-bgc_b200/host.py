@@ -57,7 +57,9 @@ def lib(flavour=None):
     (-fmad=false parity build); default from $BGC_B200_FLAVOUR, else "prod"."""
     flavour = flavour or os.environ.get("BGC_B200_FLAVOUR", "prod")
     if flavour not in _libs:
-        path = os.path.join(CSRC, LIB_NAME[flavour])
+        # $BGC_B200_LIBDIR: another build of the libraries (A/B runs against an older tree; symbols it lacks are skipped)
+        libdir = os.environ.get("BGC_B200_LIBDIR")
+        path = os.path.join(libdir or CSRC, LIB_NAME[flavour])
         if not os.path.exists(path):
             raise BgcError("%s is missing: build it with `python -c 'import __graft_entry__ as g; "
                            "g.build()'` (there is no CPU fallback)" % path)
@@ -67,6 +69,8 @@ def lib(flavour=None):
         L.bgc_kernel_name.restype = C.c_char_p
         for s in ABI_SYMBOLS:
             if s not in ("bgc_last_error", "bgc_version", "bgc_kernel_name"):
+                if libdir and not hasattr(L, s):
+                    continue
                 getattr(L, s).restype = C.c_int
         _libs[flavour] = L
     return _libs[flavour]
