@@ -372,8 +372,8 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
   }
   __syncthreads();
 
-  // Fetch level `kk` of every input array into stage `kk & 1`.  Lane 0 of every warp issues a
-  // share of the bulk copies (rows w, w + NW, ...) so that no single warp carries the whole
+  // Fetch level `kk` of every input array into stage `kk & 1`.  The first lanes of every warp issue a
+  // share of the bulk copies (rows w, w + NW, ...: one per lane) so that no single warp carries the whole
   // issue cost; thread 0 also arms the mbarrier with the byte count of the whole level.  (A
   // copy that lands before the arm only drives the transaction count negative for a moment:
   // the phase cannot complete before thread 0's arrival.)  Rows the sweep never reads are not
@@ -402,17 +402,18 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
             if (row_is_fetched(r)) dst[r * PITCH + mis + tid] = s_rowsrc[r][off + tid];
         }
       }
-      if (tid & 31) return;
+      // lane j of warp w issues the copy of row w + j * NW: the addresses of a warp's rows are formed side by
+      // side in its first lanes and the copies leave in one pass (a loop of lane 0 over its rows cost 130 warp
+      // instructions per level, 4 % of the kernel's, for five copies)
+      const int j = tid & 31;
+      if (j >= (N_FETCH_ROWS + NW - 1) / NW) return;
       const unsigned bar = smem_u32(&bars[kk & 1]);
       const unsigned bytes = n * (unsigned)sizeof(double);
       if (tid == 0) mbar_expect_tx(bar, bytes * (unsigned)(N_FETCH_ROWS - 3));
       if (bytes == 0) return;
-#pragma unroll
-      for (int j = 0; j < (N_FETCH_ROWS + NW - 1) / NW; ++j) {
-        const int r = (tid >> 5) + j * NW;
-        if (r < N_FETCH_ROWS && row_is_fetched(r))
-          bulk_g2s(smem_u32(dst + r * PITCH), s_rowsrc[r] + off - mis, bytes, bar);
-      }
+      const int r = (tid >> 5) + j * NW;
+      if (r < N_FETCH_ROWS && row_is_fetched(r))
+        bulk_g2s(smem_u32(dst + r * PITCH), s_rowsrc[r] + off - mis, bytes, bar);
     } else {
       if (in_range) {
 #pragma unroll 1
