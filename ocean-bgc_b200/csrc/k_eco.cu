@@ -608,11 +608,8 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
         TEND(G_C(a)) = 0.0; TEND(G_CHL(a)) = 0.0; TEND(G_FE(a)) = 0.0;
         if (has_Si) TEND(SI_ROW) = 0.0;
         if (has_Ca) TEND(CA_ROW) = 0.0;
-        if (inv) {
-          IN(G_CHL(a)) = 0.0; IN(G_C(a)) = 0.0; IN(G_FE(a)) = 0.0;
-          if (has_Si) IN(SI_ROW) = 0.0;
-          if (has_Ca) IN(CA_ROW) = 0.0;
-        }
+        // (inventory: the group's stage rows already hold the zeros the zero mask wrote - aC == 0 implies the mask -
+        //  and tendency * dz = 0 is what they have to carry)
         continue;
       }
 
