@@ -44,7 +44,8 @@ __device__ __forceinline__ void co3_cell(const Co3Args &A, size_t cell, size_t c
   const size_t nC = (size_t)A.nC;
   const size_t ncell = (size_t)A.nL * nC;
   const bool in_range = cell < cell_end;
-  const int k = in_range ? (int)(cell / nC) : 0;
+  // (32-bit division: nL * nC < 2^32 / 30, bgc_capi.cu check_dims; the 64-bit one costs ~30 instructions)
+  const int k = in_range ? (int)((unsigned)cell / (unsigned)nC) : 0;
   const int col = in_range ? (int)(cell - (size_t)k * nC) : 0;
   const bool active = in_range && col < A.nColumns && k < A.kmax[col];
 

@@ -426,7 +426,8 @@ macros_cells_kernel(const __grid_constant__ MacrosArgs A) {
   __shared__ double red[kMacrosBlock / 32];
   const size_t cell = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool in_range = cell < ncell;
-  const int k = in_range ? (int)(cell / nC) : 0;
+  // (32-bit division: nL * nC < 2^32 / 30, bgc_capi.cu check_dims; the 64-bit one costs ~30 instructions)
+  const int k = in_range ? (int)((unsigned)cell / (unsigned)nC) : 0;
   const int col = in_range ? (int)(cell - (size_t)k * nC) : 0;
   const bool active = in_range && col < A.nColumns && k < A.kmax[col];
   const MacrosParams &P = c_macros.p;
