@@ -1459,14 +1459,14 @@ static int dms_source_sink_device(bgc_ctx *c, const DmsInput *in, const DmsForci
   if (diag) a.d = *diag; else memset(&a.d, 0, sizeof a.d);
   const bool inv = c->inventory_on;
   a.inv_partials = nullptr;
-  if (inv) RC(arena_d(c, "inv_partials_dms", (size_t)bgc::dms_inventory_parts(nL, nC) * bgc::kInvGroup, &a.inv_partials));
+  if (inv) RC(arena_d(c, "inv_partials_dms", (size_t)bgc::dms_inventory_parts(nL, nC, c->dms_variant) * bgc::kInvGroup, &a.inv_partials));
   LAUNCH(BGC_K_DMS_COLUMNS, 1, bgc::launch_dms_columns(a, c->dms_variant, c->stream));
   if (inv) {   // only DMS and DMSP have non-zero tendencies (DMS_mod.F90:413, :741-742)
     int oi[1][bgc::kInvGroup];
     for (int j = 0; j < bgc::kInvGroup; ++j) oi[0][j] = -1;
     oi[0][0] = 30 + c->dms_tab.ind.dms_ind - 1;
     oi[0][1] = 30 + c->dms_tab.ind.dmsp_ind - 1;
-    RC(inventory_fold(c, a.inv_partials, bgc::dms_inventory_parts(nL, nC), 1, oi));
+    RC(inventory_fold(c, a.inv_partials, bgc::dms_inventory_parts(nL, nC, c->dms_variant), 1, oi));
   }
   return BGC_OK;
 }

@@ -222,7 +222,7 @@ struct InventoryFoldArgs {
   double *inventory;                         // accumulated into (+=)
 };
 cudaError_t launch_inventory_fold(const InventoryFoldArgs &a, int nParts, cudaStream_t s);
-int dms_inventory_parts(int nL, int nC);
+int dms_inventory_parts(int nL, int nC, int variant);
 int macros_inventory_parts(int nL, int nC);
 // column sweep: [eco_inventory_parts][kEcoInvGroups][kInvGroup] = 40 values per block:
 //   [0..29] the 30 tracer slots (0-based slot = value index), [30] active cells, [31] active columns,

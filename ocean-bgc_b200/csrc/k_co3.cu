@@ -37,35 +37,67 @@ __device__ __forceinline__ void report(unsigned long long *status, unsigned st) 
   }
 }
 
-// One cell of the carbonate kernel.  `cell_end` bounds the launch's share of the mesh: a launch
-// covers the cells [A.cell_begin, cell_end), both multiples of 32 unless they are the ends of the mesh,
-// so that a warp never straddles two launches.
-__device__ __forceinline__ void co3_cell(const Co3Args &A, size_t cell, size_t cell_end, const ExpTable &ex) {
-  const size_t nC = (size_t)A.nC;
-  const size_t ncell = (size_t)A.nL * nC;
-  const bool in_range = cell < cell_end;
-  // (32-bit division: nL * nC < 2^32 / 30, bgc_capi.cu check_dims; the 64-bit one costs ~30 instructions)
-  const int k = in_range ? (int)((unsigned)cell / (unsigned)nC) : 0;
-  const int col = in_range ? (int)(cell - (size_t)k * nC) : 0;
-  const bool active = in_range && col < A.nColumns && k < A.kmax[col];
+// The nine inputs of one cell, as stored (no clamp, no unit change).
+struct Co3CellIn { double temp, salt, zmid, dic, alk, po4, sio3, ph_prev, ph_prev_alt; };
 
+// Address of input f of a cell (f in the member order of Co3CellIn).  Every cell of the (k,col)
+// range is addressable whether it is active or not, so a cell can be requested before kmax is known.
+__device__ __forceinline__ const double *co3_input_ptr(const Co3Args &A, int f, size_t cell, size_t nLnC) {
+  const BgcIndices &I = c_co3.ind;
+  switch (f) {
+    case 0: return A.T + cell;
+    case 1: return A.S + cell;
+    case 2: return A.zmid + cell;
+    case 3: return A.tracers + (cell + (size_t)(I.dic_ind - 1) * nLnC);
+    case 4: return A.tracers + (cell + (size_t)(I.alk_ind - 1) * nLnC);
+    case 5: return A.tracers + (cell + (size_t)(I.po4_ind - 1) * nLnC);
+    case 6: return A.tracers + (cell + (size_t)(I.sio3_ind - 1) * nLnC);
+    case 7: return A.ph_prev + cell;
+    default: return A.ph_prev_alt + cell;
+  }
+}
+__device__ __forceinline__ Co3CellIn co3_load(const Co3Args &A, size_t cell, size_t nLnC) {
+  Co3CellIn in;
+  in.temp = *co3_input_ptr(A, 0, cell, nLnC); in.salt = *co3_input_ptr(A, 1, cell, nLnC);
+  in.zmid = *co3_input_ptr(A, 2, cell, nLnC); in.dic = *co3_input_ptr(A, 3, cell, nLnC);
+  in.alk = *co3_input_ptr(A, 4, cell, nLnC);  in.po4 = *co3_input_ptr(A, 5, cell, nLnC);
+  in.sio3 = *co3_input_ptr(A, 6, cell, nLnC); in.ph_prev = *co3_input_ptr(A, 7, cell, nLnC);
+  in.ph_prev_alt = *co3_input_ptr(A, 8, cell, nLnC);
+  return in;
+}
+
+// (level, column) of a cell and whether it is an active ocean cell (reads kmax)
+struct Co3Where { int k; bool active; };
+__device__ __forceinline__ Co3Where co3_where(const Co3Args &A, size_t cell, bool in_range) {
+  // (32-bit division: nL * nC < 2^32 / 30, bgc_capi.cu check_dims; the 64-bit one costs ~30 instructions)
+  const int k = in_range ? (int)((unsigned)cell / (unsigned)A.nC) : 0;
+  const int col = in_range ? (int)(cell - (size_t)k * (size_t)A.nC) : 0;
+  Co3Where w;
+  w.k = k;
+  w.active = in_range && col < A.nColumns && k < A.kmax[col];
+  return w;
+}
+
+// One cell of the carbonate kernel from its (raw) inputs.  MUST be called by whole warps: lanes
+// without work (`in_range` / `active` false) run the solver on benign values.
+__device__ __forceinline__ void co3_cell_compute(const Co3Args &A, size_t cell, bool in_range, const Co3Where wh,
+                                                 const Co3CellIn &in, const ExpTable &ex) {
+  const bool active = wh.active;
   // benign mid-ocean inputs for lanes without work keep the solver well-posed
   double temp = 10.0, salt = 35.0, depth = 100.0, dic = 2000.0, alk = 2300.0, po4 = 1.0, sio3 = 10.0;
   double ph_prev = 8.0, ph_prev_alt = 8.0;
   if (active) {
-    const BgcIndices &I = c_co3.ind;
-    const size_t nLnC = ncell;
-    temp = A.T[cell];
-    salt = A.S[cell];
-    depth = A.zmid[cell] * 0.01;   // cm -> m (BGC_mod.F90:950)
-    dic = gmax(0.0, A.tracers[cell + (size_t)(I.dic_ind - 1) * nLnC]);
-    alk = gmax(0.0, A.tracers[cell + (size_t)(I.alk_ind - 1) * nLnC]);
-    po4 = gmax(0.0, A.tracers[cell + (size_t)(I.po4_ind - 1) * nLnC]);
-    sio3 = gmax(0.0, A.tracers[cell + (size_t)(I.sio3_ind - 1) * nLnC]);
-    ph_prev = A.ph_prev[cell];
-    ph_prev_alt = A.ph_prev_alt[cell];
+    temp = in.temp;
+    salt = in.salt;
+    depth = in.zmid * 0.01;   // cm -> m (BGC_mod.F90:950)
+    dic = gmax(0.0, in.dic);
+    alk = gmax(0.0, in.alk);
+    po4 = gmax(0.0, in.po4);
+    sio3 = gmax(0.0, in.sio3);
+    ph_prev = in.ph_prev;
+    ph_prev_alt = in.ph_prev_alt;
   }
-  const bool deep = k > 0;   // the reference's (k > 1), 1-based
+  const bool deep = wh.k > 0;   // the reference's (k > 1), 1-based
 
   // Both comp_CO3terms calls of a cell receive the SAME DIC/ALK/PO4/SiO3/T/S
   // (BGC_mod.F90:953 vs :975 — the alternative-CO2 call passes DIC_loc, not
@@ -137,6 +169,17 @@ __device__ __forceinline__ void co3_cell(const Co3Args &A, size_t cell, size_t c
     if (A.sat_calc) A.sat_calc[cell] = 0.0;
     if (A.sat_arag) A.sat_arag[cell] = 0.0;
   }
+}
+
+// One cell, inputs requested here.  `cell_end` bounds the launch's share of the mesh: a launch
+// covers the cells [A.cell_begin, cell_end), both multiples of 32 unless they are the ends of the mesh,
+// so that a warp never straddles two launches.  The nine inputs do not wait for kmax.
+__device__ __forceinline__ void co3_cell(const Co3Args &A, size_t cell, size_t cell_end, const ExpTable &ex) {
+  const bool in_range = cell < cell_end;
+  const size_t nLnC = (size_t)A.nL * (size_t)A.nC;
+  Co3CellIn in = {};
+  if (in_range) in = co3_load(A, cell, nLnC);
+  co3_cell_compute(A, cell, in_range, co3_where(A, cell, in_range), in, ex);
 }
 
 // PERSISTENT = false: one thread per cell of [cell_begin, cell_end), 256-thread blocks, whole warps only

@@ -312,9 +312,18 @@ dms_cells_kernel(const __grid_constant__ DmsArgs A) {
   }
 }
 
-// Fallback for level counts whose tile does not fit shared memory: one thread per column,
-// PAR carried down the column in a register.
-__global__ void __launch_bounds__(256)
+// Column kernel: one thread per column, levels in order, PAR carried down the column in a register
+// like the reference's own loop.  All blocks of a wave walk the levels in step, so the chip works on a
+// few levels of each array at a time, in 2-KB runs, where the tile kernel's unsynchronised blocks touch
+// every level at once in 256-byte pieces.  The tile kernel pays for that with the size of the arrays
+// (measured, round 2, ns per cell: 0.083 at 235 160 x 60, 0.089 at 235 160 x 80, 0.102 at 461 654 x 60,
+// 0.105 at 461 654 x 80), this kernel does not (0.090 at 235 160 x 60, 0.093 at 461 654 x 80) but needs
+// several waves of columns to fill the chip: launch_dms_columns picks it for large blocks of columns and
+// for level counts whose tile does not fit shared memory.  (Register prefetch of the next level and L2
+// prefetch of the one after made it slower on the large mesh, 3.76 against 3.43 ms: whatever the tile
+// kernel exhausts there does not like more requests in flight either.)
+template <bool ALLDIAG>
+__global__ void __launch_bounds__(256, 2)
 dms_columns_kernel(const __grid_constant__ DmsArgs A) {
   __shared__ double red[256 / 32];
   const int col = blockIdx.x * blockDim.x + threadIdx.x;
@@ -349,7 +358,7 @@ dms_columns_kernel(const __grid_constant__ DmsArgs A) {
       const double PAR_in = PAR_out;
       PAR_out = PAR_in * eK;
       const double PAR_avg = fdiv(PAR_in * (1.0 - eK), KPARdz);
-      dms_cell<false>(A, i2, dms_load_cell(A, i2, nLnC), PAR_avg, cc, t_dms, t_dmsp);
+      dms_cell<ALLDIAG>(A, i2, dms_load_cell(A, i2, nLnC), PAR_avg, cc, t_dms, t_dmsp);
       inv_dms += t_dms * dz;
       inv_dmsp += t_dmsp * dz;
     }
@@ -759,24 +768,34 @@ bottom_gather_kernel(BottomGatherArgs a) {
 // Stage 1 of the inventory reduction is fused into the source-sink kernels: every block
 // writes its partial sums, [nParts][nGroups][kInvGroup].  Stage 2 below adds the partials
 // of each value in a fixed order into the inventory vector: block = group, 128 rows of
-// kInvGroup threads, row r walks partials r, r + 128, ... with four loads in flight.
+// kInvGroup threads, row r walks partials r, r + 128, ... with kFoldDepth loads in flight.
 constexpr int kFoldRows = 128;
+constexpr int kFoldDepth = 16;
 
+// NG = number of groups when known at compile time (0: gridDim.x): the kFoldDepth loads of a trip then
+// differ by immediates from one base address - with a run-time stride each needs its own 64-bit address
+// register, and at 1024 threads (64 registers) ptxas keeps two loads in flight instead of sixteen.
+template <int NG>
 __global__ void __launch_bounds__(kFoldRows * kInvGroup)
 inventory_fold_kernel(const __grid_constant__ InventoryFoldArgs A, int nParts) {
   __shared__ double rows[kFoldRows][kInvGroup];
   const int g = blockIdx.x, j = threadIdx.x % kInvGroup, r = threadIdx.x / kInvGroup;
+  // One block per group is latency-bound (a DRAM round trip per dependent load): kFoldDepth loads of a
+  // row are in flight at once, the tail is predicated instead of walked one load at a time.
   double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-  const size_t stride = (size_t)gridDim.x * kInvGroup;
+  const unsigned stride = (NG ? NG : gridDim.x) * kInvGroup;
   const double *p = A.partials + (size_t)g * kInvGroup + j;
-  int b = r;
-  for (; b + 3 * kFoldRows < nParts; b += 4 * kFoldRows) {
-    s0 += p[(size_t)b * stride];
-    s1 += p[(size_t)(b + kFoldRows) * stride];
-    s2 += p[(size_t)(b + 2 * kFoldRows) * stride];
-    s3 += p[(size_t)(b + 3 * kFoldRows) * stride];
+  for (int b = r; b < nParts; b += kFoldDepth * kFoldRows) {
+    const double *pb = p + (size_t)((unsigned)b * stride);
+    double v[kFoldDepth];
+#pragma unroll
+    for (int u = 0; u < kFoldDepth; ++u) {
+      v[u] = 0.0;
+      if (b + u * kFoldRows < nParts) v[u] = __ldg(pb + (size_t)(u * kFoldRows) * stride);
+    }
+#pragma unroll
+    for (int u = 0; u < kFoldDepth; u += 4) { s0 += v[u]; s1 += v[u + 1]; s2 += v[u + 2]; s3 += v[u + 3]; }
   }
-  for (; b < nParts; b += kFoldRows) s0 += p[(size_t)b * stride];
   rows[r][j] = (s0 + s1) + (s2 + s3);
   __syncthreads();
   if (r == 0) {
@@ -805,21 +824,32 @@ static cudaError_t launch_dms_tiles(const DmsArgs &a, cudaStream_t s) {
   return cudaGetLastError();
 }
 
+// Which kernel DMS_SourceSink runs as: the tile kernel (nL-fold parallelism) unless its tile does not
+// fit shared memory or the mesh has so many columns that the pipelined column kernel fills the chip
+// for five waves or more (its whole-column blocks then quantise by less than the tile kernel loses to
+// its scattered accesses).  148 SMs x 2 blocks x 256 columns per wave.
+// Which kernel DMS_SourceSink runs as: the tile kernel (nL-fold parallelism) unless its tile does not fit
+// shared memory or the block has so many columns that the column kernel fills the chip for five waves
+// or more (148 SMs x 2 blocks x 256 columns per wave); see dms_columns_kernel.
+static bool dms_use_columns(int nL, int nC, int variant) {
+  if ((variant & 3) >= 2) return true;    // tuning: column kernel on request
+  if ((variant & 3) == 1) return false;   //         tile kernel on request (if it fits)
+  return (size_t)nC >= (size_t)5 * 148 * 2 * 256;
+}
+
 cudaError_t launch_dms_columns(const DmsArgs &a0, int variant, cudaStream_t s) {
   DmsArgs a = a0;
   if (a.nC <= 0 || a.nL <= 0) return cudaSuccess;
   // distance of the L2 prefetch in trips (2 = the cell after next); variant bits 2.. override it (tuning): 4 = off
   a.l2_prefetch = (variant & 4) ? 0 : ((variant >> 3) ? (variant >> 3) : 2);
-  variant &= 3;
-  if (!dms_use_tiles(a.nL)) {
-    dms_columns_kernel<<<cdiv((size_t)a.nC, 256), 256, 0, s>>>(a);
-    return cudaGetLastError();
-  }
   bool all = true;
   double *const *pp = (double *const *)&a.d;
   for (size_t i = 0; i < sizeof(DmsDiagnostics) / sizeof(double *); ++i) all = all && pp[i] != nullptr;
-  // variant 1: three blocks per SM (80 registers); default: two (128 registers, deeper prefetch)
-  if (variant == 1) return all ? launch_dms_tiles<true, 3>(a, s) : launch_dms_tiles<false, 3>(a, s);
+  if (!dms_use_tiles(a.nL) || dms_use_columns(a.nL, a.nC, variant)) {
+    if (all) dms_columns_kernel<true><<<cdiv((size_t)a.nC, 256), 256, 0, s>>>(a);
+    else     dms_columns_kernel<false><<<cdiv((size_t)a.nC, 256), 256, 0, s>>>(a);
+    return cudaGetLastError();
+  }
   return all ? launch_dms_tiles<true, 2>(a, s) : launch_dms_tiles<false, 2>(a, s);
 }
 
@@ -981,10 +1011,16 @@ cudaError_t launch_scale(double *a, size_t n, double w, cudaStream_t s) {
 cudaError_t launch_inventory_fold(const InventoryFoldArgs &a, int nParts, cudaStream_t s) {
   if (nParts <= 0 || a.nGroups <= 0) return cudaSuccess;
   if (a.nGroups > kInvMaxGroups) return cudaErrorInvalidValue;
-  inventory_fold_kernel<<<a.nGroups, kFoldRows * kInvGroup, 0, s>>>(a, nParts);
+  if (a.nGroups == 1) inventory_fold_kernel<1><<<1, kFoldRows * kInvGroup, 0, s>>>(a, nParts);
+  else if (a.nGroups == kEcoInvGroups) inventory_fold_kernel<kEcoInvGroups><<<a.nGroups, kFoldRows * kInvGroup, 0, s>>>(a, nParts);
+  else inventory_fold_kernel<0><<<a.nGroups, kFoldRows * kInvGroup, 0, s>>>(a, nParts);
   return cudaGetLastError();
 }
-int dms_inventory_parts(int nL, int nC) { return dms_use_tiles(nL) ? (nC + kDmsTileCols - 1) / kDmsTileCols : (nC + 255) / 256; }
+// blocks (= inventory partials) of the kernel launch_dms_columns picks for this shape and variant
+int dms_inventory_parts(int nL, int nC, int variant) {
+  if (!dms_use_tiles(nL) || dms_use_columns(nL, nC, variant)) return (nC + 255) / 256;
+  return (nC + kDmsTileCols - 1) / kDmsTileCols;
+}
 int macros_inventory_parts(int nL, int nC) { return (int)(((size_t)nL * (size_t)nC + kMacrosBlock - 1) / kMacrosBlock); }
 
 }  // namespace bgc

@@ -1,9 +1,9 @@
 #!/bin/bash
 # A/B of kernel variants on the EC60to30 step, device resident: "NAME=VALUE[,NAME=VALUE] ..." sets of environment
-# variables, one bench line each (step time and per-kernel times).  COLS=... for another mesh size.
+# variables, one bench line each (step time and per-kernel times).  COLS=... LEVELS=... for another mesh shape.
 mkdir -p gpurun_out
 for cfg in "$@"; do
-  env $(echo "$cfg" | tr ',' ' ') python bench.py --columns ${COLS:-235160} --steps ${STEPS:-30} --warmup 3 --no-e2e --no-cpu --no-secondary \
+  env $(echo "$cfg" | tr ',' ' ') python bench.py --columns ${COLS:-235160} --levels ${LEVELS:-60} --steps ${STEPS:-30} --warmup 3 --no-e2e --no-cpu --no-secondary \
       > gpurun_out/ab.json 2> gpurun_out/ab.err || { tail -5 gpurun_out/ab.err; continue; }
   python -c "
 import json; d=json.loads(open('gpurun_out/ab.json').read().strip().splitlines()[-1])
