@@ -418,6 +418,37 @@ def test_dms_and_macros(o, device_mode):
     ctx.close()
 
 
+@pytest.mark.parametrize("flavour", [None, "strict"])
+def test_dms_kernel_choice_does_not_change_the_bits(o, flavour, monkeypatch):
+    """DMS_SourceSink runs as a tile kernel (32 columns x all levels per block) or, for blocks of very many
+    columns, as a column kernel (k_misc.cu: launch_dms_columns).  Which one a block gets depends on its
+    width, so both must give the same tendencies and diagnostics bit for bit - a host that cuts its mesh
+    differently must not see different numbers.  Both are also held against the oracle."""
+    nL, nC, nCols = 45, 515, 511
+    parms = host.Parms(flavour)
+    _, dms, _ = parity.make_bgc(nL, nC, parms, nColumns=nCols, ragged=True, with_dms=True, with_macros=True)
+    dref = dms.copy()
+    o.DMS_SourceSink(o.Parms(), dref, nthreads=o.max_threads())
+    outs = []
+    for variant in ("1", "2"):   # 1: tile kernel, 2: column kernel (BGC_DMS_VARIANT is read when the ctx is created)
+        monkeypatch.setenv("BGC_DMS_VARIANT", variant)
+        ctx = host.Context(nL, nC, device=0, flavour=flavour, parms=parms)
+        got = dms.copy()
+        dd = host.DeviceDmsColumns(nL, nC, nCols).load(got)
+        host.DMS_SourceSink(ctx, dd)
+        ctx.synchronize()
+        dd.store(got)
+        ctx.close()
+        for n in range(abi.DMS_TRACER_CNT):
+            assert parity.nerr(got.DMS_tendencies[:, :, n], dref.DMS_tendencies[:, :, n]) <= parity.TOL_TEND, (variant, n)
+        parity.compare_fields(dref.diag, got.diag, parity.TOL_TEND, "DMS diagnostics, variant " + variant, mask=_active(dms))
+        outs.append(got)
+    a, b = outs
+    assert np.array_equal(a.DMS_tendencies, b.DMS_tendencies)
+    for nm in a.diag:
+        assert np.array_equal(a.diag[nm], b.diag[nm]), nm
+
+
 @pytest.mark.parametrize("ragged", [True, False])
 def test_host_layout_pipeline_in_column_chunks(o, ragged, monkeypatch):
     """BGC_MEM_HOST_FORTRAN calls run as a two-slot pipeline over column chunks (bgc_capi.cu:
