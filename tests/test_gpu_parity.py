@@ -421,7 +421,7 @@ def test_dms_and_macros(o, device_mode):
 @pytest.mark.parametrize("flavour", [None, "strict"])
 def test_dms_kernel_choice_does_not_change_the_bits(o, flavour, monkeypatch):
     """DMS_SourceSink runs as a tile kernel (32 columns x all levels per block) or, for blocks of very many
-    columns, as a column kernel (k_misc.cu: launch_dms_columns).  Which one a block gets depends on its
+    columns, as a column kernel (k_dms.cu: launch_dms_columns).  Which one a block gets depends on its
     width, so both must give the same tendencies and diagnostics bit for bit - a host that cuts its mesh
     differently must not see different numbers.  Both are also held against the oracle."""
     nL, nC, nCols = 45, 515, 511
@@ -510,8 +510,8 @@ def test_deferred_carbonate_join_gives_the_same_bits():
     for k in outs[0]:
         assert torch.equal(outs[0][k], outs[1][k]), k
     assert outs[0]["zsat"].abs().max().item() > 0
-    # With the deferred join the carbonate cells travel inside the next DMS kernel (k_misc.cu, FUSE).  When no
-    # dms_source_sink follows, the next join point computes them: same bits again.
+    # With the deferred join and no dms_source_sink behind it, the next join point is where the carbonate
+    # kernel is waited for: same bits again.
     ctx.set_deferred_join(True)
     d = host.DeviceBgcColumns(nL, nC).load(cols)
     for _ in range(2):
