@@ -555,6 +555,11 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
     double tot_CaCO3_form = 0.0, tot_Nfix = 0.0;
     double s_tC = 0.0, s_tCaCO3 = 0.0, s_tSi = 0.0, s_QpC = 0.0, s_Nfix_J = 0.0, photoC_NO3_TOT = 0.0;
     double bSi_form_k = 0.0, CaCO3_zint_k = 0.0, NO3_zint_k = 0.0;   // this level's additions to column integrals
+    // The zero-biomass shortcut below writes the zeros a group body would compute - which it would
+    // only from FINITE factors: with a NaN or Inf among them the reference's 0 * x is NaN, and it
+    // must stay NaN here.  One sum tells (non-finite as soon as one term is).
+    const bool lvl_finite = fabs(Tfunc + PAR_avg + NO3_loc + NH4_loc + PO4_loc + DOP_loc + Fe_loc + SiO3_loc + zooC_loc + dz)
+                            <= 1.7976931348623157e308;
 
     // ---- per functional group: quotas (:850-898), uptake, photosynthesis, losses,
     //      grazing, routing (:1107-1388), tendencies (:1700-1745)
@@ -571,9 +576,10 @@ eco_columns_kernel(const __grid_constant__ EcoArgs A) {
       //      product of the group body below is exactly zero: the only things that survive are
       //      the nutrient-limitation diagnostics (they do not involve the biomass), the
       //      epsC*epsTinv terms of f_zoo_detr (:1395-1401) and the running NO3 integral (:1844-1846).
-      //      When that holds for every active lane of the warp the body is skipped; the bits
-      //      produced are the same (x*0 = 0 and s+0 = s for the finite values that occur here).
-      if (A.zero_shortcut && !__any_sync(__activemask(), aC != 0.0)) {
+      //      When that holds for every active lane of the warp - and every factor of the level is
+      //      finite in every lane (lvl_finite) - the body is skipped; the bits produced are the same
+      //      (x*0 = 0 and s+0 = s for finite values).
+      if (A.zero_shortcut && !__any_sync(__activemask(), aC != 0.0 || !lvl_finite)) {
         if (DIAG) {
           const double rNO3 = cdiv(NO3_loc, at.kNO3, D.r_kNO3[a]), rNH4 = cdiv(NH4_loc, at.kNH4, D.r_kNH4[a]);
 #ifdef BGC_STRICT

@@ -683,6 +683,37 @@ def test_zero_biomass_shortcut_changes_nothing():
     ctx.close()
 
 
+def test_zero_biomass_shortcut_lets_nonfinite_inputs_through():
+    """0 * NaN is NaN: where the reference multiplies a zeroed functional group with a non-finite factor
+    (a NaN temperature, an infinite nutrient) its tendencies are NaN, and the model sees them.  The shortcut
+    writes the zeros of a group body only where every factor of the level is finite in the whole warp
+    (k_eco.cu: lvl_finite): with such inputs in deep cells whose biomass is exactly zero, shortcut on and
+    off give the same bits, NaN for NaN."""
+    nL, nC = 60, 512
+    ctx, parms = _ctx(nL, nC)
+    cols, _, _ = parity.make_bgc(nL, nC, parms)
+    k = nL - 5
+    assert (cols.BGC_tracers[k, :, parms.ind.spC_ind - 1] == 0).all()   # deep ocean of the synthetic columns: no biomass
+    assert cols.number_of_active_levels[[40, 300]].min() > k
+    bad = cols.copy()
+    bad.PotentialTemperature[k, 40] = np.nan
+    bad.BGC_tracers[k, 300, parms.ind.no3_ind - 1] = np.inf
+    outs = []
+    for on in (True, False):
+        ctx.set_zero_shortcut(on)
+        outs.append(parity.run_gpu_bgc(ctx, bad.copy(), device_mode=True))
+        ctx.status(reset=True)
+    a, b = outs
+    assert np.array_equal(np.isnan(a.BGC_tendencies), np.isnan(b.BGC_tendencies))
+    assert np.array_equal(np.nan_to_num(a.BGC_tendencies, nan=1.5, posinf=2.5, neginf=-2.5),
+                          np.nan_to_num(b.BGC_tendencies, nan=1.5, posinf=2.5, neginf=-2.5))
+    for n in a.diag:
+        assert np.array_equal(np.isnan(a.diag[n]), np.isnan(b.diag[n])), n
+    assert np.isnan(a.BGC_tendencies[k, 40, :]).any()          # the NaN temperature reaches the zeroed groups
+    assert not np.isfinite(a.BGC_tendencies[k, 300, :]).all()   # so does the infinite nitrate
+    ctx.close()
+
+
 # ------------------------------------------------------------------ inventory
 def test_inventory_vector_matches_the_outputs():
     nL, nC, nCols = 36, 514, 500
