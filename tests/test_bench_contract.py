@@ -59,3 +59,18 @@ def test_b200_arm_has_no_cpu_fallback(built):
     r = _run("--steps", "1")
     assert r.returncode != 0
     assert "no CUDA device" in (r.stderr + r.stdout)
+
+
+def test_traffic_json_is_what_its_ncu_summary_says(tmp_path):
+    """bench.py quotes roofline.traffic / ncu_counters from profiles/traffic.json (ncu cannot run inside a
+    timed bench).  The file names the ncu summary it was made from; regenerating it from that summary
+    (scripts/make_traffic_json.py) must give the same numbers, and the summary must be committed."""
+    tj = json.load(open(os.path.join(REPO, "profiles", "traffic.json")))
+    src = tj["source"].split(" ")[0]
+    assert os.path.exists(os.path.join(REPO, src)), src
+    out = tmp_path / "traffic.json"
+    subprocess.run([sys.executable, os.path.join(REPO, "scripts", "make_traffic_json.py"), src, tj["commit"], str(out)],
+                   cwd=REPO, check=True, capture_output=True)
+    assert json.load(open(out)) == tj
+    # the sweep's measured DRAM traffic is its algorithmic bytes (1464 B per cell): no wasted re-reads
+    assert 1464 <= tj["eco_columns_kernel_bytes_per_cell"] <= 1464 * 1.01
