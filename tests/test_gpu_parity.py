@@ -433,12 +433,19 @@ def test_dms_kernel_choice_does_not_change_the_bits(o, flavour, monkeypatch):
     for variant in ("1", "2"):   # 1: tile kernel, 2: column kernel (BGC_DMS_VARIANT is read when the ctx is created)
         monkeypatch.setenv("BGC_DMS_VARIANT", variant)
         ctx = host.Context(nL, nC, device=0, flavour=flavour, parms=parms)
+        ctx.inventory_enable(True)      # each form writes its own number of block partials for the fold
+        ctx.inventory_reset()
         got = dms.copy()
         dd = host.DeviceDmsColumns(nL, nC, nCols).load(got)
         host.DMS_SourceSink(ctx, dd)
+        inv = ctx.inventory_get()
         ctx.synchronize()
         dd.store(got)
         ctx.close()
+        dz = np.where(_active(dms), dms.cell_thickness, 0.0)
+        want = np.einsum("kcn,kc->n", got.DMS_tendencies, dz)
+        scale = np.einsum("kcn,kc->n", np.abs(got.DMS_tendencies), dz)
+        assert np.all(np.abs(inv[30:30 + abi.DMS_TRACER_CNT] - want) <= 1e-12 * np.maximum(scale, 1e-300)), (variant, inv[30:44] - want)
         for n in range(abi.DMS_TRACER_CNT):
             assert parity.nerr(got.DMS_tendencies[:, :, n], dref.DMS_tendencies[:, :, n]) <= parity.TOL_TEND, (variant, n)
         parity.compare_fields(dref.diag, got.diag, parity.TOL_TEND, "DMS diagnostics, variant " + variant, mask=_active(dms))
