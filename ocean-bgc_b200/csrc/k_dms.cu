@@ -317,10 +317,10 @@ dms_cells_kernel(const __grid_constant__ DmsArgs A) {
 // few levels of each array at a time, in 2-KB runs, where the tile kernel's unsynchronised blocks touch
 // every level at once in 256-byte pieces.  The tile kernel pays for that with the size of the arrays
 // (measured, round 2, ns per cell: 0.083 at 235 160 x 60, 0.089 at 235 160 x 80, 0.102 at 461 654 x 60,
-// 0.105 at 461 654 x 80), this kernel does not (0.090 at 235 160 x 60, 0.093 at 461 654 x 80) but needs
+// 0.105 at 461 654 x 80), this kernel does not (0.090 at 235 160 x 60 and at 461 654 x 80) but needs
 // several waves of columns to fill the chip: launch_dms_columns picks it for large blocks of columns and
 // for level counts whose tile does not fit shared memory.  (Register prefetch of the next level and L2
-// prefetch of the one after made it slower on the large mesh, 3.76 against 3.43 ms: whatever the tile
+// prefetch of the one after made it slower on the large mesh, 3.76 against 3.31-3.43 ms: whatever the tile
 // kernel exhausts there does not like more requests in flight either.)
 template <bool ALLDIAG>
 __global__ void __launch_bounds__(256, 2)
@@ -444,10 +444,6 @@ static cudaError_t launch_dms_tiles(const DmsArgs &a, cudaStream_t s) {
   return cudaGetLastError();
 }
 
-// Which kernel DMS_SourceSink runs as: the tile kernel (nL-fold parallelism) unless its tile does not
-// fit shared memory or the mesh has so many columns that the pipelined column kernel fills the chip
-// for five waves or more (its whole-column blocks then quantise by less than the tile kernel loses to
-// its scattered accesses).  148 SMs x 2 blocks x 256 columns per wave.
 // Which kernel DMS_SourceSink runs as: the tile kernel (nL-fold parallelism) unless its tile does not fit
 // shared memory or the block has so many columns that the column kernel fills the chip for five waves
 // or more (148 SMs x 2 blocks x 256 columns per wave); see dms_columns_kernel.
