@@ -45,6 +45,32 @@ def test_library_is_sm100a_and_has_no_cpu_path(built):
     assert "oracle_" not in nm
 
 
+def test_sweep_sass_has_no_local_memory_and_stages_through_tma(built):
+    """Static check on the built library (what profiles/sass_summary_r02.txt records): every
+    instantiation of the column sweep is free of local-memory (spill) accesses, brings its inputs in
+    by bulk copies through the TMA unit completed on an mbarrier, and the hot kernels are all present."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("sass_summary", os.path.join(parity.REPO, "scripts", "sass_summary.py"))
+    ss = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ss)
+    so = os.path.join(parity.REPO, "ocean-bgc_b200", "csrc", "libbgc_b200.so")
+    per = ss.sass_counts(so)
+    sweep = {k: c for k, c in per.items() if "eco_columns_kernel" in k}
+    assert len(sweep) == 6          # three diagnostics modes x two block shapes
+    for k, c in sweep.items():
+        assert c["LDL"] == 0 and c["STL"] == 0, k
+        assert c["UBLKCP"] >= 1 and c["SYNCS"] >= 1, k
+        assert c["DFMA"] > 500 and c["RCP64H"] > 50, k     # FP64 body, reciprocal-seed divisions
+    for kernel in ("co3_cells_kernel", "dms_cells_kernel", "dms_columns_kernel", "macros_cells_kernel",
+                   "surface_fluxes_kernel", "zsat_columns_kernel", "inventory_fold_kernel", "co2calc_points_kernel"):
+        assert any(kernel in k for k in per), kernel
+    res = ss.ptxas_resources()
+    if res:     # the ptxas logs exist where the library was built (not on the GPU box)
+        for k, r in res.items():
+            if "eco_columns_kernel" in k:
+                assert r["spill_st"] == 0 and r["spill_ld"] == 0 and r["stack"] == 0, (k, r)
+
+
 def test_struct_layouts_match_the_c_compiler(built):
     names = ["BgcParams", "BgcAutotroph", "BgcIndices", "DmsParams", "DmsIndices", "MacrosParams",
              "MacrosIndices", "BgcInput", "BgcForcing", "BgcOutput", "BgcFluxDiagnostics", "BgcDiagnostics",
