@@ -93,6 +93,32 @@ def test_struct_layouts_match_the_c_compiler(built):
     assert int(out["off_kFe"]) == abi.BgcAutotroph.kFe.offset
 
 
+def test_every_member_offset_matches_the_c_compiler(built):
+    """abi.py parses the header with regular expressions; gcc is the authority on where each member
+    of each struct lies."""
+    names = [n for n in abi._STRUCT_FIELDS if hasattr(abi, n)]
+    assert len(names) >= 21
+    prog = '#include <stdio.h>\n#include <stddef.h>\n#include "bgc_b200.h"\nint main(void){\n'
+    want = {}
+    for n in names:
+        for fname, _ in abi._STRUCT_FIELDS[n]:
+            prog += 'printf("%s.%s %%zu %%zu\\n", offsetof(%s, %s), sizeof(((%s *)0)->%s));\n' % (n, fname, n, fname, n, fname)
+            fld = getattr(getattr(abi, n), fname)
+            want["%s.%s" % (n, fname)] = (fld.offset, fld.size)
+    prog += "return 0;}\n"
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, "o.c")
+        open(src, "w").write(prog)
+        exe = os.path.join(d, "o")
+        subprocess.check_call(["gcc", "-I", os.path.dirname(HEADER), src, "-o", exe])
+        got = {}
+        for line in subprocess.check_output([exe], text=True).splitlines():
+            k, off, size = line.split()
+            got[k] = (int(off), int(size))
+    assert got == want
+    assert len(got) >= 350
+
+
 def test_parameter_tables_match_reference_defaults(built):
     """bgc_host_parms.c (product) and parms_oracle.c (oracle) are two independent
     restatements of BGC_parms_init / DMS_parms_init / MACROS_parms_init."""
