@@ -17,6 +17,7 @@ import json
 import os
 import subprocess
 import sys
+import threading
 
 import numpy as np
 
@@ -42,6 +43,7 @@ class TLib:
         self.lib_path, self.meta_path, self.preload = lib_path, meta_path, list(preload)
         self._lib = self._meta = None
         self._structs = {}
+        self._pristine = {}
 
     def available(self):
         return os.path.exists(self.lib_path) and os.path.exists(self.meta_path)
@@ -97,6 +99,30 @@ class TLib:
         f = getattr(self.lib(), "ref_addr__" + cname)
         f.restype = C.c_void_p
         return self.field_ctype(self.meta()["vars"][cname]).from_address(f())
+
+    # module variables a host sets like a namelist: the *_parms tunables and BGC_mod's restoring switches
+    _TUNABLE_PREFIXES = ("bgc_parms__", "dms_parms__", "macros_parms__", "bgc_mod__lrest_")
+
+    def restore_tunables(self):
+        """Put the tunable module variables of the calling thread back to what they were when this
+        thread first asked.  `*_parms_init` does not assign all of them: `f_qsw_par_DMS` gets its value
+        in its declaration (DMS_parms.F90:191-192) and the `lrest_*` switches are plain module variables
+        of BGC_mod (BGC_mod.F90:131-134), so what an earlier caller stored there (RefParms.sync_from with
+        perturbed tables) would otherwise reach every later caller of the process - as it would in the
+        Fortran; a test that asks for the defaults means the defaults."""
+        key = threading.get_ident()
+        names = [cn for cn, info in self.meta()["vars"].items()
+                 if cn.startswith(self._TUNABLE_PREFIXES) and not info["alloc"]]
+        snap = self._pristine.get(key)
+        if snap is None:
+            snap = {}
+            for cn in names:
+                v = self.var(cn)
+                snap[cn] = C.string_at(C.addressof(v), C.sizeof(v))
+            self._pristine[key] = snap
+            return
+        for cn, raw in snap.items():
+            C.memmove(C.addressof(self.var(cn)), raw, len(raw))
 
     def call(self, cname, *args):
         """Call a translated procedure.  Scalars may be given as Python numbers (wrapped, passed
@@ -219,6 +245,7 @@ class RefParms:
     def __init__(self, parms=None, t0_kelvin=273.15, L=None):
         self.L = L = L or REF
         m, struct, var, call = L.meta(), L.struct, L.var, L.call
+        L.restore_tunables()      # defaults mean defaults, whatever an earlier sync_from left behind
         self.ind = struct("bgc_parms__bgc_indices_type")()
         self.autotrophs = (struct("bgc_parms__autotroph_type") * 4)()
         self._names = {}

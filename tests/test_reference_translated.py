@@ -558,3 +558,46 @@ def test_thread_local_module_state(po):
     run.close()
     for i, (s, _, _) in enumerate(slabs):
         same(s.BGC_tendencies, whole.BGC_tendencies[:, 24 * i:24 * (i + 1), :], "slab %d" % i)
+
+
+def test_default_parms_mean_the_defaults_after_a_perturbed_caller():
+    """`f_qsw_par_DMS` gets its value in its declaration (DMS_parms.F90:191-192) and the `lrest_*`
+    switches are module variables of BGC_mod (BGC_mod.F90:131-134): no `*_init` assigns them, so a
+    caller that stored perturbed tables with sync_from (the differential fuzzer does, in the calling
+    thread) used to leave them behind for every later RefParms of the process - the GPU shim test
+    then compared the CUDA path with a reference running on another caller's PAR fraction.
+    RefParms now puts the tunables back first (TLib.restore_tunables)."""
+    res = {}
+
+    def run():
+        rt.RefParms(o.Parms())                      # this thread's first caller: the snapshot
+        po2 = o.Parms()
+        _retune(po2)
+        po2.dms.f_qsw_par_DMS = 0.31
+        po2.bgc.lrest_po4 = 1
+        rt.RefParms(po2).sync_from(po2)
+        assert rt.var("dms_parms__f_qsw_par_dms").value == 0.31
+        po = o.Parms()
+        rr = rt.RefParms(po)
+        assert rt.var("dms_parms__f_qsw_par_dms").value == 0.45
+        assert rt.var("bgc_mod__lrest_po4").value == 0
+        cols, dms, mac = parity.make_bgc(20, 33, po, ragged=True, with_dms=True, with_macros=True)
+        a, b, da, db = cols.copy(), cols.copy(), dms.copy(), dms.copy()
+        o.BGC_SourceSink(po, a, True); rt.BGC_SourceSink(rr, b, True)
+        o.DMS_SourceSink(po, da); rt.DMS_SourceSink(rr, db)
+        res.update(a=a, b=b, da=da, db=db)
+
+    import threading
+    err = []
+
+    def guarded():
+        try:
+            run()
+        except BaseException as e:      # noqa: BLE001 - re-raised in the test's thread
+            err.append(e)
+    t = threading.Thread(target=guarded)
+    t.start(); t.join()
+    if err:
+        raise err[0]
+    assert np.array_equal(res["a"].BGC_tendencies, res["b"].BGC_tendencies, equal_nan=True)
+    assert np.array_equal(res["da"].DMS_tendencies, res["db"].DMS_tendencies, equal_nan=True)
